@@ -1,0 +1,115 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference in this container.
+
+Run from the repo root (build container only; /root/reference does not exist on the GPU box):
+
+    python tools/make_golden.py
+
+How: a stub ``comfy.model_management`` (device = cpu) is put on sys.path together with
+/root/reference; ``vfi_models.rife.rife_arch.IFNet("4.6")`` and ``vfi_models.rife.RIFE_VFI``
+are imported as they are; the checkpoint table gets ``"rife46.pth": "4.6"`` (absent at this
+commit) and the downloader is replaced by a function returning a temp file with
+``oracle.rife46.synthetic_state_dict(seed)`` (no weights ship with the reference, no network).
+Inputs are regenerated from seeds by the tests, so only the reference OUTPUTS are stored.
+"""
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF = os.environ.get("VFI_REFERENCE", "/root/reference")
+
+from oracle import rife46 as O  # noqa: E402
+
+
+def _install_stub():
+    comfy = types.ModuleType("comfy")
+    mm = types.ModuleType("comfy.model_management")
+    mm.get_torch_device = lambda: torch.device("cpu")
+    mm.soft_empty_cache = lambda *a, **k: None
+    mm.is_nvidia = lambda: False
+    mm.get_torch_device_name = lambda d: str(d)
+    comfy.model_management = mm
+    sys.modules["comfy"] = comfy
+    sys.modules["comfy.model_management"] = mm
+    sys.path.insert(0, REF)
+
+
+def cases():
+    """Shared with tests/test_oracle_golden.py: name -> kwargs."""
+    return {
+        # IFNet level: pad 96x160 -> 128x192, two timesteps in one batch
+        "ifnet_96x160": dict(kind="ifnet", seed=0, gain=1.0, h=96, w=160, ts=(0.5, 0.25), clip_seed=11),
+        # larger flows (lastconv x4) so border clamping and big displacements are exercised
+        "ifnet_64x64_gain4": dict(kind="ifnet", seed=3, gain=4.0, h=64, w=64, ts=(0.5,), clip_seed=12),
+        # already a multiple of 64: no padding
+        "ifnet_128x128_rand": dict(kind="ifnet", seed=5, gain=1.0, h=128, w=128, ts=(0.75,), clip_seed=-1),
+        # node level: multiplier 3 with a skip list, 4-channel input (alpha dropped)
+        "node_m3_skip": dict(kind="node", seed=1, gain=1.0, n=4, h=40, w=72, c=4, multiplier=3,
+                             states=([1], True), clip_seed=13),
+        # node level: per-pair multiplier list shorter than the pair count (padded with 2), entry 1 => no mids
+        "node_mlist": dict(kind="node", seed=2, gain=2.0, n=5, h=64, w=64, c=3, multiplier=[2, 1, 3],
+                           states=None, clip_seed=14),
+        # node level: keep-list (is_skip_list False)
+        "node_keep": dict(kind="node", seed=4, gain=1.0, n=4, h=48, w=80, c=3, multiplier=2,
+                          states=([0, 2], False), clip_seed=15),
+    }
+
+
+def make_inputs(cfg):
+    if cfg["kind"] == "ifnet":
+        if cfg["clip_seed"] < 0:
+            g = torch.Generator().manual_seed(99)
+            fr = torch.rand(2, cfg["h"], cfg["w"], 3, generator=g) * 1.2 - 0.1  # also exercises the clamp
+        else:
+            fr = O.synthetic_clip(2, cfg["h"], cfg["w"], seed=cfg["clip_seed"])
+        return fr
+    fr = O.synthetic_clip(cfg["n"], cfg["h"], cfg["w"], seed=cfg["clip_seed"])
+    if cfg["c"] == 4:
+        fr = torch.cat([fr, torch.ones_like(fr[..., :1])], -1)
+    return fr
+
+
+def main():
+    _install_stub()
+    import vfi_models.rife as R
+    from vfi_models.rife.rife_arch import IFNet
+    from vfi_utils import InterpolationStateList
+
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    R.CKPT_NAME_VER_DICT["rife46.pth"] = "4.6"
+    for name, cfg in cases().items():
+        sd = O.synthetic_state_dict(cfg["seed"], cfg["gain"])
+        fr = make_inputs(cfg)
+        if cfg["kind"] == "ifnet":
+            m = IFNet(arch_ver="4.6").eval()
+            m.load_state_dict(sd)
+            x = fr.permute(0, 3, 1, 2)
+            ts = torch.tensor(cfg["ts"], dtype=torch.float32).view(-1, 1, 1, 1)
+            b = len(cfg["ts"])
+            with torch.inference_mode():
+                out = m(x[0:1].repeat(b, 1, 1, 1), x[1:2].repeat(b, 1, 1, 1), ts, [8, 4, 2, 1], False, False)
+            np.savez_compressed(os.path.join(out_dir, name + ".npz"), out=out.numpy())
+        else:
+            with tempfile.TemporaryDirectory() as td:
+                path = os.path.join(td, "rife46.pth")
+                torch.save(sd, path)
+                R.load_file_from_github_release = lambda model_type, ckpt_name, _p=path: _p
+                R._model_cache.clear()
+                st = None
+                if cfg["states"] is not None:
+                    st = InterpolationStateList(list(cfg["states"][0]), cfg["states"][1])
+                (out,) = R.RIFE_VFI().vfi("rife46.pth", fr, multiplier=cfg["multiplier"],
+                                          optional_interpolation_states=st)
+            np.savez_compressed(os.path.join(out_dir, name + ".npz"), out=out.numpy())
+        print(name, tuple(out.shape), float(out.mean()))
+
+
+if __name__ == "__main__":
+    main()

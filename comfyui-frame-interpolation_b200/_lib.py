@@ -1,0 +1,57 @@
+"""ctypes binding of libvfi_b200.so (declared in include/vfi_b200.h).  No fallback: a missing library is an error."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libvfi_b200.so")
+
+# every symbol include/vfi_b200.h declares (tests check the .so exports exactly these)
+SYMBOLS = [
+    "vfi_last_error", "vfi_version", "vfi_create", "vfi_destroy", "vfi_launch_count", "vfi_set_batch",
+    "vfi_rife46_load", "vfi_rife46_forward", "vfi_rife46_interpolate_host", "vfi_warp_bilinear_border",
+    "vfi_rife46_debug_layer", "vfi_rife46_debug_state", "vfi_rife46_layer_plan", "vfi_sync",
+]
+
+_lib = None
+
+
+class VfiError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VfiError(
+            f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` (nvcc, sm_100a). "
+            "There is no CPU or PyTorch fallback for this path.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
+    L.vfi_last_error.restype = C.c_char_p
+    L.vfi_version.restype = C.c_char_p
+    L.vfi_create.argtypes = [i32, C.POINTER(vp)]
+    L.vfi_destroy.argtypes = [vp]
+    L.vfi_launch_count.argtypes = [vp]
+    L.vfi_launch_count.restype = i64
+    L.vfi_set_batch.argtypes = [vp, i32]
+    L.vfi_rife46_load.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i32, i32]
+    L.vfi_rife46_forward.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, f32, vp, vp]
+    L.vfi_rife46_interpolate_host.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, f32, vp]
+    L.vfi_warp_bilinear_border.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    L.vfi_rife46_debug_layer.argtypes = [vp, i32, i32, vp, vp, vp, i32, i32, i32, i32, vp]
+    L.vfi_rife46_debug_state.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)]
+    L.vfi_rife46_layer_plan.argtypes = [vp, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32),
+                                        C.POINTER(i32), C.POINTER(i64)]
+    L.vfi_sync.argtypes = [vp]
+    for name in SYMBOLS:
+        if name not in ("vfi_last_error", "vfi_version", "vfi_launch_count"):
+            getattr(L, name).restype = i32
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise VfiError(f"libvfi_b200 error {rc}: {lib().vfi_last_error().decode()}")

@@ -1,0 +1,629 @@
+// Context, weight repacking, the RIFE-4.6 forward schedule and the C ABI (include/vfi_b200.h).
+//
+// Forward schedule of one internal pass over B (pair, timestep) tasks - reference IFNet.forward,
+// rife_arch.py:465-732, arch "4.6" (blocks (7,192) (12,128) (12,96) (12,64), rife_arch.py:404-408):
+//   prep_frames (once per source frame)                       clamp / pad           :476-485
+//   for block i, scale s_i:                                                          :519-704
+//     front      -> x      [B, Hs/2, Ws/2, 4*16]  16-bit      warp+concat+1/s       :31-70,:238-249,:589-596
+//     tapconv    -> c00    [B, Hs/4, Ws/4, 4*c/2] 16-bit      conv0.0 (+lrelu)      :181-184
+//     tapconv    -> feat   [B, Hs/4, Ws/4, c]     16-bit      conv0.1 (+lrelu)
+//     8x tapconv -> feat                                       ResConv               :20-28
+//     tapconv    -> tmp    [B, Hs, Ws] float4 + float          ConvT+PixelShuffle    :215-218
+//     upflow     -> flow, mask [B, Hp, Wp] fp32                x s, *s, += :263-266,:694-696
+//   final        -> out [B, H, W, 3] fp32                      warp, sigmoid blend, crop, clamp :703-717,:732
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/vfi_b200.h"
+#include "vfi_internal.h"
+
+namespace vfi {
+
+static thread_local std::string g_err;
+void set_error(const std::string& s) { g_err = s; }
+
+namespace {
+
+const int kBlockC[4] = {192, 128, 96, 64};
+const int kBlockCinReal[4] = {7, 12, 12, 12};
+
+uint16_t to_operand(float v, int op_type) {
+  if (op_type == OP_BF16) {
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    uint16_t u;
+    std::memcpy(&u, &h, 2);
+    return u;
+  }
+  __half h = __float2half_rn(v);
+  uint16_t u;
+  std::memcpy(&u, &h, 2);
+  return u;
+}
+
+template <class F>
+std::vector<uint16_t> pack_weights(const TapConvLayer& L, int op_type, F wfun) {
+  const size_t per_split = (size_t)L.ktotal16 * 2 * L.n_cta * 8;
+  std::vector<uint16_t> v((size_t)L.nsplit * per_split, 0);
+  for (int sp = 0; sp < L.nsplit; ++sp) {
+    int j = 0;
+    for (int e = 0; e < L.ntaps; ++e) {
+      for (int i = 0; i < L.taps[e].nk16; ++i, ++j) {
+        for (int c = 0; c < 16; ++c) {
+          const int kk = j * 2 + (c >> 3);
+          for (int nl = 0; nl < L.n_cta; ++nl) {
+            const float val = wfun(e, i * 16 + c, sp * L.n_cta + nl);
+            v[sp * per_split + ((size_t)kk * L.n_cta + nl) * 8 + (c & 7)] = to_operand(val, op_type);
+          }
+        }
+      }
+    }
+  }
+  return v;
+}
+
+// choose the output-channel split: smallest split reaching `want_stages`, else the one with most stages
+void choose_split(TapConvLayer& L, const std::vector<int>& splits, int want_stages) {
+  int best_split = -1, best_stages = 0;
+  for (int sp : splits) {
+    if (L.n_total % sp) continue;
+    const int nc = L.n_total / sp;
+    if (nc % 16) continue;
+    L.nsplit = sp;
+    L.n_cta = nc;
+    TapConvParams p{};
+    const int st = tapconv_plan(L, &p);
+    if (st >= want_stages) {
+      best_split = sp;
+      best_stages = st;
+      break;
+    }
+    if (st > best_stages) {
+      best_stages = st;
+      best_split = sp;
+    }
+  }
+  L.nsplit = best_split;
+  L.n_cta = L.n_total / best_split;
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace
+}  // namespace vfi
+
+using namespace vfi;
+
+struct vfi_ctx {
+  int device = 0;
+  int num_sms = 148;
+  int batch = 8;
+  int op_type = OP_F16;
+  bool loaded = false;
+  int64_t launches = 0;
+  TapConvLayer layers[4][11];  // [block][0=conv0.0, 1=conv0.1, 2..9=ResConv, 10=lastconv]
+  std::vector<void*> weight_allocs;
+  // workspace
+  DevBuf imgs, flow, mask, x, c00, featA, featB, tmpF, tmpM, raw, outdev, dev_frames_tmp;
+  int ws_Hp = 0, ws_Wp = 0;
+  cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      set_error(std::string(#call) + ": " + cudaGetErrorString(_e));                               \
+      return VFI_E_CUDA;                                                                           \
+    }                                                                                              \
+  } while (0)
+
+int fail(int code, const std::string& msg) {
+  set_error(msg);
+  return code;
+}
+
+void free_weights(vfi_ctx* c) {
+  for (void* p : c->weight_allocs) cudaFree(p);
+  c->weight_allocs.clear();
+  c->loaded = false;
+}
+
+template <class T>
+int upload(vfi_ctx* c, const std::vector<T>& h, void** dptr) {
+  void* d = nullptr;
+  CK(cudaMalloc(&d, h.size() * sizeof(T)));
+  c->weight_allocs.push_back(d);
+  CK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *dptr = d;
+  return VFI_OK;
+}
+
+// stride-2 3x3 conv on a space-to-depth input: kernel row ky reads s2d row offset dy and sub-row a
+void s2_map(int k, int* d, int* a) {
+  if (k == 0) { *d = -1; *a = 1; } else { *d = 0; *a = k - 1; }
+}
+
+int build_conv_s2(vfi_ctx* c, TapConvLayer& L, int Cs, int creal, int cout, int out_s2d, const float* w,
+                  const float* bias) {
+  L = TapConvLayer{};
+  L.cin = 4 * Cs;
+  L.n_total = cout;
+  L.ntaps = 9;
+  L.ktotal16 = 9 * (Cs / 16);
+  L.halo_y0 = -1; L.halo_x0 = -1; L.halo_h = kTileH + 1; L.halo_w = kTileW + 1;
+  L.epi_mode = EPI_BIAS_LRELU;
+  L.out_s2d = out_s2d;
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) {
+      int dy, a, dx, b;
+      s2_map(ky, &dy, &a);
+      s2_map(kx, &dx, &b);
+      TapEntry& t = L.taps[ky * 3 + kx];
+      t.dy = (int16_t)dy; t.dx = (int16_t)dx;
+      t.chunk0 = (int16_t)(((a * 2 + b) * Cs) / 8);
+      t.nk16 = (int16_t)(Cs / 16);
+    }
+  choose_split(L, {1, 2, 3, 4, 6, 8, 12}, 2);
+  auto wf = [&](int e, int ci, int n) -> float {
+    if (ci >= creal) return 0.f;
+    const int ky = e / 3, kx = e % 3;
+    return w[(((size_t)n * creal + ci) * 3 + ky) * 3 + kx];
+  };
+  std::vector<uint16_t> pk = pack_weights(L, c->op_type, wf);
+  std::vector<float> sc(cout, 1.f), sh(bias, bias + cout);
+  int r;
+  if ((r = upload(c, pk, &L.w))) return r;
+  if ((r = upload(c, sc, (void**)&L.scale))) return r;
+  if ((r = upload(c, sh, (void**)&L.shift))) return r;
+  return VFI_OK;
+}
+
+int build_resconv(vfi_ctx* c, TapConvLayer& L, int ch, const float* beta, const float* w, const float* bias) {
+  L = TapConvLayer{};
+  L.cin = ch;
+  L.n_total = ch;
+  L.ntaps = 9;
+  L.ktotal16 = 9 * (ch / 16);
+  L.halo_y0 = -1; L.halo_x0 = -1; L.halo_h = kTileH + 2; L.halo_w = kTileW + 2;
+  L.epi_mode = EPI_RESCONV;
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) {
+      TapEntry& t = L.taps[ky * 3 + kx];
+      t.dy = (int16_t)(ky - 1); t.dx = (int16_t)(kx - 1); t.chunk0 = 0; t.nk16 = (int16_t)(ch / 16);
+    }
+  choose_split(L, {1, 2, 3, 4, 6, 8, 12}, 3);
+  auto wf = [&](int e, int ci, int n) -> float {
+    return w[(((size_t)n * ch + ci) * 3 + e / 3) * 3 + e % 3];
+  };
+  std::vector<uint16_t> pk = pack_weights(L, c->op_type, wf);
+  std::vector<float> sc(beta, beta + ch), sh(ch);
+  for (int i = 0; i < ch; ++i) sh[i] = bias[i] * beta[i];  // (conv + b)*beta + x  ==  conv*beta + b*beta + x
+  int r;
+  if ((r = upload(c, pk, &L.w))) return r;
+  if ((r = upload(c, sc, (void**)&L.scale))) return r;
+  if ((r = upload(c, sh, (void**)&L.shift))) return r;
+  return VFI_OK;
+}
+
+// ConvTranspose2d(c, 24, 4, 2, 1) + PixelShuffle(2) as ONE 3x3 conv producing, per feature cell, the 4x4 sub-pixel
+// patch of the 5 used channels: n = c5*16 + py*4 + px, (py,px) = (2a+i, 2b+j), convT channel oc = 4*c5 + 2i + j at
+// convT position (2y+a, 2x+b); tap (dy,dx) uses transposed-kernel element ky = a+1-2dy, kx = b+1-2dx.
+int build_lastconv(vfi_ctx* c, TapConvLayer& L, int ch, const float* wt, const float* bias) {
+  L = TapConvLayer{};
+  L.cin = ch;
+  L.n_total = 80;
+  L.ntaps = 9;
+  L.ktotal16 = 9 * (ch / 16);
+  L.halo_y0 = -1; L.halo_x0 = -1; L.halo_h = kTileH + 2; L.halo_w = kTileW + 2;
+  L.epi_mode = EPI_LASTCONV;
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) {
+      TapEntry& t = L.taps[ky * 3 + kx];
+      t.dy = (int16_t)(ky - 1); t.dx = (int16_t)(kx - 1); t.chunk0 = 0; t.nk16 = (int16_t)(ch / 16);
+    }
+  choose_split(L, {1, 5}, 2);
+  auto oc_of = [](int n) {
+    const int c5 = n >> 4, pos = n & 15, py = pos >> 2, px = pos & 3;
+    return 4 * c5 + 2 * (py & 1) + (px & 1);
+  };
+  auto wf = [&](int e, int ci, int n) -> float {
+    const int dy = e / 3 - 1, dx = e % 3 - 1;
+    const int pos = n & 15, py = pos >> 2, px = pos & 3;
+    const int ky = (py >> 1) + 1 - 2 * dy, kx = (px >> 1) + 1 - 2 * dx;
+    if (ky < 0 || ky > 3 || kx < 0 || kx > 3) return 0.f;
+    return wt[(((size_t)ci * 24 + oc_of(n)) * 4 + ky) * 4 + kx];
+  };
+  std::vector<uint16_t> pk = pack_weights(L, c->op_type, wf);
+  std::vector<float> sc(80, 1.f), sh(80);
+  for (int n = 0; n < 80; ++n) sh[n] = bias[oc_of(n)];
+  int r;
+  if ((r = upload(c, pk, &L.w))) return r;
+  if ((r = upload(c, sc, (void**)&L.scale))) return r;
+  if ((r = upload(c, sh, (void**)&L.shift))) return r;
+  return VFI_OK;
+}
+
+struct Geometry {
+  int Hp, Wp;
+  int s[4];
+};
+
+int make_geometry(int H, int W, float scale_factor, Geometry* g) {
+  g->Hp = ((H - 1) / 64 + 1) * 64;  // rife_arch.py:480-482
+  g->Wp = ((W - 1) / 64 + 1) * 64;
+  const float base[4] = {8.f, 4.f, 2.f, 1.f};  // rife/__init__.py:157-160
+  for (int i = 0; i < 4; ++i) {
+    const float sf = base[i] / scale_factor;
+    const int si = (int)std::lround(sf);
+    if (std::fabs(sf - (float)si) > 1e-6f || si < 1 || (si & (si - 1)))
+      return fail(VFI_E_NOTIMPL, "scale_factor > 1 (up-scaled blocks) is not implemented; use 1.0, 0.5 or 0.25");
+    g->s[i] = si;
+    if ((g->Hp / si) % 4 || (g->Wp / si) % 4 || g->Hp % si || g->Wp % si)
+      return fail(VFI_E_INVALID,
+                  "padded size / scale is not a multiple of 4: the reference fails with a shape mismatch for this "
+                  "size and scale_factor as well");
+  }
+  return VFI_OK;
+}
+
+int ensure_workspace(vfi_ctx* c, const Geometry& g, int B, int n_frames_window) {
+  size_t x = 0, c00 = 0, feat = 0, tmp = 0;
+  for (int i = 0; i < 4; ++i) {
+    const size_t Hs = g.Hp / g.s[i], Ws = g.Wp / g.s[i];
+    x = std::max(x, (size_t)B * (Hs / 2) * (Ws / 2) * 64 * 2);
+    c00 = std::max(c00, (size_t)B * (Hs / 4) * (Ws / 4) * 2 * kBlockC[i] * 2);
+    feat = std::max(feat, (size_t)B * (Hs / 4) * (Ws / 4) * kBlockC[i] * 2);
+    tmp = std::max(tmp, (size_t)B * Hs * Ws);
+  }
+  const size_t px = (size_t)g.Hp * g.Wp;
+  CK(c->imgs.ensure((size_t)n_frames_window * px * sizeof(float4)));
+  CK(c->flow.ensure((size_t)B * px * sizeof(float4)));
+  CK(c->mask.ensure((size_t)B * px * sizeof(float)));
+  CK(c->x.ensure(x));
+  CK(c->c00.ensure(c00));
+  CK(c->featA.ensure(feat));
+  CK(c->featB.ensure(feat));
+  CK(c->tmpF.ensure(tmp * sizeof(float4)));
+  CK(c->tmpM.ensure(tmp * sizeof(float)));
+  c->ws_Hp = g.Hp;
+  c->ws_Wp = g.Wp;
+  return VFI_OK;
+}
+
+#define LAUNCH(call)                                               \
+  do {                                                             \
+    cudaError_t _e = (call);                                       \
+    c->launches++;                                                 \
+    if (_e != cudaSuccess) {                                       \
+      set_error(std::string(#call) + ": " + cudaGetErrorString(_e)); \
+      return VFI_E_CUDA;                                           \
+    }                                                              \
+  } while (0)
+
+// one internal pass: tasks (indices into the prepared frame window c->imgs) -> out [n, H, W, 3]
+int forward_pass(vfi_ctx* c, const Geometry& g, const BatchTasks& tasks, int H, int W, float* out, cudaStream_t st) {
+  const int B = tasks.n;
+  const float4* imgs = (const float4*)c->imgs.p;
+  float4* flow = (float4*)c->flow.p;
+  float* mask = (float*)c->mask.p;
+  for (int i = 0; i < 4; ++i) {
+    const int s = g.s[i];
+    const int Hs = g.Hp / s, Ws = g.Wp / s;
+    const bool first = (i == 0);
+    LAUNCH(launch_front(c->op_type, imgs, flow, mask, tasks, g.Hp, g.Wp, s, first, c->x.p, st));
+    LAUNCH(launch_tapconv(c->layers[i][0], c->op_type, c->x.p, c->c00.p, nullptr, nullptr, B, Hs / 2, Ws / 2,
+                          c->num_sms, false, st));
+    LAUNCH(launch_tapconv(c->layers[i][1], c->op_type, c->c00.p, c->featA.p, nullptr, nullptr, B, Hs / 4, Ws / 4,
+                          c->num_sms, false, st));
+    void* a = c->featA.p;
+    void* b = c->featB.p;
+    for (int j = 0; j < 8; ++j) {
+      LAUNCH(launch_tapconv(c->layers[i][2 + j], c->op_type, a, b, nullptr, nullptr, B, Hs / 4, Ws / 4, c->num_sms,
+                            false, st));
+      std::swap(a, b);
+    }
+    LAUNCH(launch_tapconv(c->layers[i][10], c->op_type, a, nullptr, (float4*)c->tmpF.p, (float*)c->tmpM.p, B, Hs / 4,
+                          Ws / 4, c->num_sms, false, st));
+    LAUNCH(launch_upflow((const float4*)c->tmpF.p, (const float*)c->tmpM.p, flow, mask, B, g.Hp, g.Wp, s, first, st));
+  }
+  LAUNCH(launch_final(imgs, flow, mask, tasks, g.Hp, g.Wp, H, W, out, st));
+  return VFI_OK;
+}
+
+int check_tasks(const int32_t* f0, const int32_t* f1, int n_tasks, int lo, int hi) {
+  for (int i = 0; i < n_tasks; ++i)
+    if (f0[i] < lo || f0[i] >= hi || f1[i] < lo || f1[i] >= hi) return fail(VFI_E_INVALID, "task frame index out of range");
+  return VFI_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* vfi_last_error(void) { return g_err.c_str(); }
+const char* vfi_version(void) { return "vfi_b200 0.1 (sm_100a; RIFE 4.6)"; }
+
+int vfi_create(int device, vfi_ctx** out) {
+  if (!out) return fail(VFI_E_INVALID, "null out");
+  int n = 0;
+  CK(cudaGetDeviceCount(&n));
+  if (device < 0 || device >= n) return fail(VFI_E_INVALID, "no such CUDA device");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(VFI_E_INVALID, "libvfi_b200 needs a compute-capability 10.x (B200, sm_100a) GPU");
+  vfi_ctx* c = new vfi_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+  *out = c;
+  return VFI_OK;
+}
+
+int vfi_destroy(vfi_ctx* c) {
+  if (!c) return VFI_OK;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  free_weights(c);
+  for (DevBuf* b : {&c->imgs, &c->flow, &c->mask, &c->x, &c->c00, &c->featA, &c->featB, &c->tmpF, &c->tmpM, &c->raw,
+                    &c->outdev, &c->dev_frames_tmp})
+    b->release();
+  if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+  if (c->s_comp) cudaStreamDestroy(c->s_comp);
+  if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+  delete c;
+  return VFI_OK;
+}
+
+int64_t vfi_launch_count(const vfi_ctx* c) { return c ? c->launches : 0; }
+
+int vfi_set_batch(vfi_ctx* c, int batch) {
+  if (!c || batch < 1 || batch > kMaxBatch) return fail(VFI_E_INVALID, "batch must be in [1,16]");
+  c->batch = batch;
+  return VFI_OK;
+}
+
+int vfi_sync(vfi_ctx* c) {
+  if (!c) return fail(VFI_E_INVALID, "null ctx");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  return VFI_OK;
+}
+
+int vfi_rife46_load(vfi_ctx* c, const float* const* T, const int64_t* numel, int n_tensors, int operand_type) {
+  if (!c || !T || !numel) return fail(VFI_E_INVALID, "null argument");
+  if (n_tensors != VFI_RIFE46_NUM_TENSORS) return fail(VFI_E_INVALID, "RIFE 4.6 has 120 state_dict tensors");
+  if (operand_type != OP_F16 && operand_type != OP_BF16) return fail(VFI_E_INVALID, "operand_type");
+  CK(cudaSetDevice(c->device));
+  free_weights(c);
+  c->op_type = operand_type;
+  int k = 0;
+  auto expect = [&](int idx, int64_t want) { return numel[idx] == want; };
+  for (int b = 0; b < 4; ++b) {
+    const int ch = kBlockC[b], cin = kBlockCinReal[b];
+    if (!expect(k, (int64_t)(ch / 2) * cin * 9) || !expect(k + 1, ch / 2) || !expect(k + 2, (int64_t)ch * (ch / 2) * 9) ||
+        !expect(k + 3, ch))
+      return fail(VFI_E_INVALID, "conv0 tensor sizes do not match RIFE 4.6");
+    int r;
+    if ((r = build_conv_s2(c, c->layers[b][0], 16, cin, ch / 2, 1, T[k], T[k + 1]))) return r;
+    if ((r = build_conv_s2(c, c->layers[b][1], ch / 2, ch / 2, ch, 0, T[k + 2], T[k + 3]))) return r;
+    k += 4;
+    for (int j = 0; j < 8; ++j) {
+      if (!expect(k, ch) || !expect(k + 1, (int64_t)ch * ch * 9) || !expect(k + 2, ch))
+        return fail(VFI_E_INVALID, "convblock tensor sizes do not match RIFE 4.6");
+      if ((r = build_resconv(c, c->layers[b][2 + j], ch, T[k], T[k + 1], T[k + 2]))) return r;
+      k += 3;
+    }
+    if (!expect(k, (int64_t)ch * 24 * 16) || !expect(k + 1, 24))
+      return fail(VFI_E_INVALID, "lastconv tensor sizes do not match RIFE 4.6");
+    if ((r = build_lastconv(c, c->layers[b][10], ch, T[k], T[k + 1]))) return r;
+    k += 2;
+  }
+  for (int b = 0; b < 4; ++b)
+    for (int l = 0; l < 11; ++l)
+      if (c->layers[b][l].nsplit < 1) return fail(VFI_E_STATE, "a layer has no shared-memory plan");
+  c->loaded = true;
+  return VFI_OK;
+}
+
+int vfi_rife46_forward(vfi_ctx* c, const float* frames, int n_frames, int H, int W, int C, const int32_t* f0,
+                       const int32_t* f1, const float* t, int n_tasks, float scale_factor, float* out, void* stream) {
+  if (!c || !frames || !out || (n_tasks > 0 && (!f0 || !f1 || !t))) return fail(VFI_E_INVALID, "null argument");
+  if (!c->loaded) return fail(VFI_E_STATE, "vfi_rife46_load has not been called");
+  if (C < 3 || H < 1 || W < 1 || n_frames < 1) return fail(VFI_E_INVALID, "bad frame shape");
+  if (n_tasks == 0) return VFI_OK;
+  int r;
+  if ((r = check_tasks(f0, f1, n_tasks, 0, n_frames))) return r;
+  CK(cudaSetDevice(c->device));
+  Geometry g;
+  if ((r = make_geometry(H, W, scale_factor, &g))) return r;
+  int lo = n_frames, hi = 0;
+  for (int i = 0; i < n_tasks; ++i) {
+    lo = std::min(lo, std::min(f0[i], f1[i]));
+    hi = std::max(hi, std::max(f0[i], f1[i]) + 1);
+  }
+  const int B = std::min(c->batch, n_tasks);
+  if ((r = ensure_workspace(c, g, B, hi - lo))) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  LAUNCH(launch_prep_frames(frames + (size_t)lo * H * W * C, hi - lo, H, W, C, (float4*)c->imgs.p, g.Hp, g.Wp, st));
+  for (int pos = 0; pos < n_tasks; pos += B) {
+    BatchTasks bt{};
+    bt.n = std::min(B, n_tasks - pos);
+    for (int i = 0; i < bt.n; ++i) {
+      bt.f0[i] = f0[pos + i] - lo;
+      bt.f1[i] = f1[pos + i] - lo;
+      bt.t[i] = t[pos + i];
+    }
+    if ((r = forward_pass(c, g, bt, H, W, out + (size_t)pos * H * W * 3, st))) return r;
+  }
+  return VFI_OK;
+}
+
+int vfi_rife46_interpolate_host(vfi_ctx* c, const float* frames, int n_frames, int H, int W, int C, int frame_lo,
+                                int frame_hi, const int32_t* f0, const int32_t* f1, const float* t,
+                                const int32_t* out_slot, int n_tasks, float scale_factor, float* out) {
+  if (!c || !frames || (n_tasks > 0 && (!out || !f0 || !f1 || !t))) return fail(VFI_E_INVALID, "null argument");
+  if (!c->loaded) return fail(VFI_E_STATE, "vfi_rife46_load has not been called");
+  if (C < 3 || H < 1 || W < 1 || frame_lo < 0 || frame_hi > n_frames || frame_lo >= frame_hi)
+    return fail(VFI_E_INVALID, "bad frame shape / range");
+  if (n_tasks == 0) return VFI_OK;
+  int r;
+  if ((r = check_tasks(f0, f1, n_tasks, frame_lo, frame_hi))) return r;
+  for (int i = 1; i < n_tasks; ++i)
+    if (std::min(f0[i], f1[i]) < std::min(f0[i - 1], f1[i - 1]))
+      return fail(VFI_E_INVALID, "tasks must be ordered by frame index (as RIFE_VFI.vfi builds them)");
+  CK(cudaSetDevice(c->device));
+  Geometry g;
+  if ((r = make_geometry(H, W, scale_factor, &g))) return r;
+  const int nf = frame_hi - frame_lo;
+  const int B = std::min(c->batch, n_tasks);
+  if ((r = ensure_workspace(c, g, B, nf))) return r;
+  const size_t frame_elems = (size_t)H * W * C, out_elems = (size_t)H * W * 3;
+  const int kRaw = 2 * kMaxBatch + 4;  // raw upload ring (frames)
+  CK(c->raw.ensure((size_t)kRaw * frame_elems * sizeof(float)));
+  CK(c->outdev.ensure((size_t)2 * B * out_elems * sizeof(float)));
+  const int nb = (n_tasks + B - 1) / B;
+  std::vector<cudaEvent_t> ev_up(nb), ev_comp(nb), ev_down(nb);
+  for (int i = 0; i < nb; ++i) {
+    CK(cudaEventCreateWithFlags(&ev_up[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev_down[i], cudaEventDisableTiming));
+  }
+  int uploaded = frame_lo;  // frames [frame_lo, uploaded) are prepared in c->imgs
+  int rc = VFI_OK;
+  auto body = [&]() -> int {
+    for (int k = 0; k < nb; ++k) {
+      const int pos = k * B, n = std::min(B, n_tasks - pos);
+      int need = uploaded;
+      for (int i = 0; i < n; ++i) need = std::max(need, std::max(f0[pos + i], f1[pos + i]) + 1);
+      // H2D + prep of the frames this pass needs, in ring-sized groups, on the copy stream
+      while (uploaded < need) {
+        const int cnt = std::min(need - uploaded, kRaw / 2);
+        for (int i = 0; i < cnt; ++i) {
+          const int f = uploaded + i;
+          CK(cudaMemcpyAsync((float*)c->raw.p + (size_t)(f % kRaw) * frame_elems, frames + (size_t)f * frame_elems,
+                             frame_elems * sizeof(float), cudaMemcpyHostToDevice, c->s_h2d));
+          LAUNCH(launch_prep_frames((float*)c->raw.p + (size_t)(f % kRaw) * frame_elems, 1, H, W, C,
+                                    (float4*)c->imgs.p + (size_t)(f - frame_lo) * g.Hp * g.Wp, g.Hp, g.Wp, c->s_h2d));
+        }
+        uploaded += cnt;
+      }
+      CK(cudaEventRecord(ev_up[k], c->s_h2d));
+      CK(cudaStreamWaitEvent(c->s_comp, ev_up[k], 0));
+      if (k >= 2) CK(cudaStreamWaitEvent(c->s_comp, ev_down[k - 2], 0));  // output slot free again
+      BatchTasks bt{};
+      bt.n = n;
+      for (int i = 0; i < n; ++i) {
+        bt.f0[i] = f0[pos + i] - frame_lo;
+        bt.f1[i] = f1[pos + i] - frame_lo;
+        bt.t[i] = t[pos + i];
+      }
+      float* od = (float*)c->outdev.p + (size_t)(k & 1) * B * out_elems;
+      int r2 = forward_pass(c, g, bt, H, W, od, c->s_comp);
+      if (r2) return r2;
+      CK(cudaEventRecord(ev_comp[k], c->s_comp));
+      CK(cudaStreamWaitEvent(c->s_d2h, ev_comp[k], 0));
+      if (!out_slot) {
+        CK(cudaMemcpyAsync(out + (size_t)pos * out_elems, od, (size_t)n * out_elems * sizeof(float),
+                           cudaMemcpyDeviceToHost, c->s_d2h));
+      } else {
+        for (int i = 0; i < n; ++i)
+          CK(cudaMemcpyAsync(out + (size_t)out_slot[pos + i] * out_elems, od + (size_t)i * out_elems,
+                             out_elems * sizeof(float), cudaMemcpyDeviceToHost, c->s_d2h));
+      }
+      CK(cudaEventRecord(ev_down[k], c->s_d2h));
+    }
+    CK(cudaStreamSynchronize(c->s_d2h));
+    CK(cudaStreamSynchronize(c->s_comp));
+    CK(cudaStreamSynchronize(c->s_h2d));
+    return VFI_OK;
+  };
+  rc = body();
+  if (rc != VFI_OK) cudaDeviceSynchronize();
+  for (int i = 0; i < nb; ++i) {
+    cudaEventDestroy(ev_up[i]);
+    cudaEventDestroy(ev_comp[i]);
+    cudaEventDestroy(ev_down[i]);
+  }
+  return rc;
+}
+
+int vfi_warp_bilinear_border(vfi_ctx* c, const float* img, const float* flow, float* out, int B, int H, int W, int C,
+                             void* stream) {
+  if (!c || !img || !flow || !out || B < 1 || H < 1 || W < 1 || C < 1) return fail(VFI_E_INVALID, "bad argument");
+  CK(cudaSetDevice(c->device));
+  LAUNCH(launch_warp(img, flow, out, B, H, W, C, (cudaStream_t)stream));
+  return VFI_OK;
+}
+
+int vfi_rife46_debug_layer(vfi_ctx* c, int block, int layer, const void* in, void* out, void* out_mask, int B, int H,
+                           int W, int impl, void* stream) {
+  if (!c || block < 0 || block > 3 || layer < 0 || layer > 10 || !in || !out) return fail(VFI_E_INVALID, "bad argument");
+  if (!c->loaded) return fail(VFI_E_STATE, "vfi_rife46_load has not been called");
+  CK(cudaSetDevice(c->device));
+  const TapConvLayer& L = c->layers[block][layer];
+  if (layer == 10) {
+    if (!out_mask) return fail(VFI_E_INVALID, "lastconv needs out_mask");
+    LAUNCH(launch_tapconv(L, c->op_type, in, nullptr, (float4*)out, (float*)out_mask, B, H, W, c->num_sms, impl == 1,
+                          (cudaStream_t)stream));
+  } else {
+    LAUNCH(launch_tapconv(L, c->op_type, in, out, nullptr, nullptr, B, H, W, c->num_sms, impl == 1,
+                          (cudaStream_t)stream));
+  }
+  return VFI_OK;
+}
+
+int vfi_rife46_debug_state(vfi_ctx* c, const float** flow4, const float** mask, int* Hp, int* Wp) {
+  if (!c || !flow4 || !mask || !Hp || !Wp) return fail(VFI_E_INVALID, "null argument");
+  *flow4 = (const float*)c->flow.p;
+  *mask = (const float*)c->mask.p;
+  *Hp = c->ws_Hp;
+  *Wp = c->ws_Wp;
+  return VFI_OK;
+}
+
+int vfi_rife46_layer_plan(vfi_ctx* c, int block, int layer, int* stages, int* n_cta, int* nsplit, int* smem_bytes,
+                          int64_t* macs_per_cell) {
+  if (!c || block < 0 || block > 3 || layer < 0 || layer > 10) return fail(VFI_E_INVALID, "bad argument");
+  if (!c->loaded) return fail(VFI_E_STATE, "vfi_rife46_load has not been called");
+  const TapConvLayer& L = c->layers[block][layer];
+  TapConvParams p{};
+  const int st = tapconv_plan(L, &p);
+  if (stages) *stages = st;
+  if (n_cta) *n_cta = L.n_cta;
+  if (nsplit) *nsplit = L.nsplit;
+  if (smem_bytes) *smem_bytes = (int)(p.off_epi + (L.epi_mode == EPI_LASTCONV ? 0u : 128u * p.epi_pitch));
+  if (macs_per_cell) *macs_per_cell = (int64_t)L.ktotal16 * 16 * L.n_total;
+  return VFI_OK;
+}
+
+}  // extern "C"

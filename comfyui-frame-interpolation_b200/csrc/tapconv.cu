@@ -1,0 +1,487 @@
+// tapconv: tap-list implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 / TMEM), sm_100a only.
+//
+// Replaces, for the RIFE IFBlock (reference rife_arch.py:237-276), the cuDNN/ATen kernels behind
+//   conv0.0 / conv0.1  Conv2d(3x3, stride 2)+LeakyReLU        rife_arch.py:96-107, :181-184
+//   convblock          8 x ResConv  lrelu(conv3x3(x)*beta + x) rife_arch.py:20-28, :201-210
+//   lastconv           ConvTranspose2d(c,24,4,2,1)+PixelShuffle rife_arch.py:215-218
+//
+// One CTA tile = 16 x 8 grid cells = the M=128 rows of one tcgen05.mma.  The input window of the tile
+// (tile + halo, all input channels) is staged ONCE in shared memory as 8-channel planes
+//      A[chunk][halo_pixel][8 ch]          (16 bytes per pixel per plane)
+// which is exactly the K-major / no-swizzle UMMA operand layout (core matrix = 8 pixels x 16 B = 128 contiguous
+// bytes).  Every filter tap is then just a different descriptor START ADDRESS into the same staged window
+// (shift by (dy*halo_w + dx) pixels = 16-byte units), so the 3x3 window is read from L2 once (x1.4 halo), not 9x.
+// Weights of the CTA's output-channel slice stay resident in shared memory for the whole launch
+// (one cp.async.bulk per CTA), accumulators live in TMEM (double buffered), the epilogue reads the residual
+// from the staged window, not from global memory.
+//
+// Warp roles (256 threads, 1 CTA/SM, persistent over tiles):
+//   warp 0      : TMEM alloc/dealloc; lane 0 issues all tcgen05.mma + tcgen05.commit
+//   warps 1..3  : producers - cp.async (LDGSTS.128, zero-fill outside the image) of the input window
+//   warps 4..7  : epilogue  - tcgen05.ld -> scale/shift/residual/LeakyReLU -> 16-bit -> coalesced global stores
+#include "ptx.cuh"
+#include "vfi_internal.h"
+
+namespace vfi {
+
+namespace {
+
+// control block layout at the start of dynamic shared memory
+constexpr int kMaxStages = 4;
+struct Ctrl {
+  uint64_t w_full;
+  uint64_t a_full[kMaxStages];
+  uint64_t a_empty[kMaxStages];
+  uint64_t t_full[2];
+  uint64_t t_empty[2];
+  uint32_t tmem_base;
+};
+constexpr uint32_t kCtrlBytes = 256;
+static_assert(sizeof(Ctrl) <= kCtrlBytes, "control block");
+
+__device__ __forceinline__ size_t out_pixel_offset(const TapConvParams& p, int b, int gy, int gx) {
+  // element offset of channel 0 of grid cell (b, gy, gx) in the output tensor
+  if (p.out_s2d) {
+    // space-to-depth store: the consumer is a stride-2 conv that reads [B, H/2, W/2, 4*n_total]
+    size_t cell = ((size_t)b * (p.H >> 1) + (gy >> 1)) * (p.W >> 1) + (gx >> 1);
+    return cell * (size_t)(4 * p.n_total) + (size_t)(((gy & 1) * 2 + (gx & 1)) * p.n_total);
+  }
+  return (((size_t)b * p.H + gy) * p.W + gx) * (size_t)p.n_total;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__ TapConvParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int split = blockIdx.x % p.nsplit;
+  const int first = blockIdx.x / p.nsplit;
+  if (first >= p.ctas_per_split) return;  // whole CTA leaves together
+  const int S = p.stages;
+  const bool residual = (p.epi_mode == EPI_RESCONV);
+
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_w = smem_base + offsetof(Ctrl, w_full);
+  const uint32_t bar_afull = smem_base + offsetof(Ctrl, a_full);
+  const uint32_t bar_aempty = smem_base + offsetof(Ctrl, a_empty);
+  const uint32_t bar_tfull = smem_base + offsetof(Ctrl, t_full);
+  const uint32_t bar_tempty = smem_base + offsetof(Ctrl, t_empty);
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_w, 1);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_afull + 8 * s, kProducerThreads);
+      mbar_init(bar_aempty + 8 * s, residual ? 4 : 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(smem_base + offsetof(Ctrl, tmem_base), p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctrl->tmem_base;
+
+  const uint32_t a_smem = smem_base + p.off_a;
+  const uint32_t w_smem = smem_base + p.off_w;
+  const int tiles_per_img = p.tiles_y * p.tiles_x;
+
+  if (warp == 0) {
+    // ======================================================= MMA issuer (one thread)
+    if (lane == 0) {
+      mbar_wait(bar_w, 0, 1);
+      const uint32_t plane = (uint32_t)p.plane_bytes;
+      const uint32_t a_sbo = (uint32_t)p.halo_w * 16u;
+      const uint32_t b_lbo = (uint32_t)p.n_cta * 16u;
+      uint32_t k = 0;
+      for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k) {
+        const uint32_t stage = k % S, use = k / S, acc = k & 1, vuse = k >> 1;
+        mbar_wait(bar_tempty + 8 * acc, (vuse & 1) ^ 1, 2);
+        mbar_wait(bar_afull + 8 * stage, use & 1, 3);
+        fence_proxy_async();  // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
+        tc_fence_after();
+        const uint32_t a_base = a_smem + stage * p.stage_bytes;
+        const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
+        uint32_t j = 0;
+        for (int e = 0; e < p.ntaps; ++e) {
+          const TapEntry te = p.taps[e];
+          const uint32_t tap_addr = a_base + (uint32_t)te.chunk0 * plane +
+                                    (uint32_t)((te.dy - p.halo_y0) * p.halo_w + (te.dx - p.halo_x0)) * 16u;
+          for (int i = 0; i < te.nk16; ++i, ++j) {
+            const uint64_t adesc = umma_desc_nosw(tap_addr + 2u * i * plane, plane, a_sbo);
+            const uint64_t bdesc = umma_desc_nosw(w_smem + j * 2u * b_lbo, b_lbo, 128u);
+            umma_f16(d_tmem, adesc, bdesc, p.idesc, j > 0 ? 1u : 0u);
+          }
+        }
+        if (!residual) umma_commit(bar_aempty + 8 * stage);  // window free once the MMAs have read it
+        umma_commit(bar_tfull + 8 * acc);                    // accumulator ready for the epilogue
+      }
+    }
+    __syncwarp();
+  } else if (warp < 4) {
+    // ======================================================= producers
+    const int ptid = threadIdx.x - 32;
+    if (ptid == 0) {
+      mbar_arrive_expect_tx(bar_w, p.w_bytes);
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + (size_t)split * p.w_bytes;
+      for (uint32_t off = 0; off < p.w_bytes; off += 16384u) {
+        const uint32_t n = min(16384u, p.w_bytes - off);
+        bulk_g2s(w_smem + off, wsrc + off, n, bar_w);
+      }
+    }
+    const uint32_t total = (uint32_t)p.halo_px * p.cpp;
+    const uint8_t* in = reinterpret_cast<const uint8_t*>(p.in);
+    const size_t row_bytes = (size_t)p.W * p.cin * 2;
+    uint32_t k = 0;
+    for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k) {
+      const uint32_t stage = k % S, use = k / S;
+      mbar_wait(bar_aempty + 8 * stage, (use & 1) ^ 1, 4);
+      const int b = t / tiles_per_img;
+      const int rem = t - b * tiles_per_img;
+      const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
+      const int gy0 = tyi * kTileH + p.halo_y0, gx0 = txi * kTileW + p.halo_x0;
+      const uint32_t dst_base = a_smem + stage * p.stage_bytes;
+      const uint8_t* img = in + (size_t)b * p.H * row_bytes;
+      for (uint32_t idx = ptid; idx < total; idx += kProducerThreads) {
+        const uint32_t px = __umulhi(idx, p.cpp_magic);   // idx / cpp
+        const uint32_t ch = idx - px * p.cpp;             // idx % cpp
+        const uint32_t hy = __umulhi(px, p.halow_magic);  // px / halo_w
+        const uint32_t hx = px - hy * p.halo_w;
+        const int gy = gy0 + (int)hy, gx = gx0 + (int)hx;
+        const bool ok = (gy >= 0) && (gy < p.H) && (gx >= 0) && (gx < p.W);
+        const uint8_t* src = ok ? img + (size_t)gy * row_bytes + ((size_t)gx * p.cin + ch * 8) * 2 : img;
+        cp_async16(dst_base + ch * (uint32_t)p.plane_bytes + px * 16u, src, ok ? 16u : 0u);
+      }
+      cp_async_arrive_noinc(bar_afull + 8 * stage);
+    }
+  } else {
+    // ======================================================= epilogue (warps 4..7 <-> TMEM lane quarters 0..3)
+    const int q = warp - 4;
+    const int etid = threadIdx.x - 128;
+    float* ss = reinterpret_cast<float*>(smem + p.off_ss);  // [0,n_cta) scale, [n_cta, 2 n_cta) shift
+    for (int i = etid; i < p.n_cta; i += 128) {
+      ss[i] = p.scale[split * p.n_cta + i];
+      ss[p.n_cta + i] = p.shift[split * p.n_cta + i];
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+
+    const int r = q * 32 + lane;           // accumulator row == TMEM lane == tile cell
+    const int py = r >> 3, px = r & 7;
+    uint8_t* stg = smem + p.off_epi + (size_t)q * 32 * p.epi_pitch;  // this warp's staging rows
+    const int n0 = split * p.n_cta;
+    const uint32_t center = (uint32_t)((py - p.halo_y0) * p.halo_w + (px - p.halo_x0)) * 16u;
+
+    uint32_t k = 0;
+    for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k) {
+      const uint32_t stage = k % S, use = k / S, acc = k & 1, vuse = k >> 1;
+      const int b = t / tiles_per_img;
+      const int rem = t - b * tiles_per_img;
+      const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
+      const int gy = tyi * kTileH + py, gx = txi * kTileW + px;
+      const bool valid = (gy < p.H) && (gx < p.W);
+
+      mbar_wait(bar_tfull + 8 * acc, vuse & 1, 5);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * p.acc_stride + ((uint32_t)(q * 32) << 16);
+
+      if (p.epi_mode == EPI_LASTCONV) {
+        // n = c5*16 + (y4*4 + x4): 16-column chunk c5 = one component (4 flow + mask) of the 4x4 sub-pixel patch
+        const int Hs = p.H * 4, Ws = p.W * 4;
+        if (p.n_cta == 80) {
+          uint32_t v[5][16];
+#pragma unroll
+          for (int c = 0; c < 5; ++c) tmem_ld16(taddr + c * 16, v[c]);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+          if (valid) {
+#pragma unroll
+            for (int y4 = 0; y4 < 4; ++y4) {
+              const size_t o = ((size_t)b * Hs + (gy * 4 + y4)) * Ws + gx * 4;
+#pragma unroll
+              for (int x4 = 0; x4 < 4; ++x4) {
+                const int pos = y4 * 4 + x4;
+                float4 f;
+                f.x = __uint_as_float(v[0][pos]) + ss[80 + 0 * 16 + pos];
+                f.y = __uint_as_float(v[1][pos]) + ss[80 + 1 * 16 + pos];
+                f.z = __uint_as_float(v[2][pos]) + ss[80 + 2 * 16 + pos];
+                f.w = __uint_as_float(v[3][pos]) + ss[80 + 3 * 16 + pos];
+                p.out_flow[o + x4] = f;
+                p.out_mask[o + x4] = __uint_as_float(v[4][pos]) + ss[80 + 4 * 16 + pos];
+              }
+            }
+          }
+        } else {
+          // output channels split across CTAs (large c): this CTA owns components [split*n_cta/16, ...)
+          const int ncomp = p.n_cta >> 4;
+          for (int cc = 0; cc < ncomp; ++cc) {
+            uint32_t v[16];
+            tmem_ld16(taddr + cc * 16, v);
+            tmem_ld_wait();
+            const int c5 = split * ncomp + cc;
+            if (valid) {
+#pragma unroll
+              for (int pos = 0; pos < 16; ++pos) {
+                const size_t o = ((size_t)b * Hs + (gy * 4 + (pos >> 2))) * Ws + gx * 4 + (pos & 3);
+                const float val = __uint_as_float(v[pos]) + ss[p.n_cta + cc * 16 + pos];
+                if (c5 < 4)
+                  reinterpret_cast<float*>(p.out_flow)[o * 4 + c5] = val;
+                else
+                  p.out_mask[o] = val;
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        }
+        continue;
+      }
+
+      if (residual) mbar_wait(bar_afull + 8 * stage, use & 1, 6);  // acquire the staged window for generic reads
+      const uint32_t a_base = a_smem + stage * p.stage_bytes;
+      const int nchunks = p.n_cta >> 4;
+      for (int cc = 0; cc < nchunks; ++cc) {
+        uint32_t v[16];
+        tmem_ld16(taddr + cc * 16, v);
+        uint4 res0 = make_uint4(0, 0, 0, 0), res1 = make_uint4(0, 0, 0, 0);
+        if (residual) {
+          const uint32_t ch = (uint32_t)((n0 >> 3) + 2 * cc);
+          const uint32_t ra = a_base + ch * (uint32_t)p.plane_bytes + center;
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(res0.x), "=r"(res0.y), "=r"(res0.z), "=r"(res0.w)
+                       : "r"(ra));
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(res1.x), "=r"(res1.y), "=r"(res1.z), "=r"(res1.w)
+                       : "r"(ra + (uint32_t)p.plane_bytes));
+        }
+        tmem_ld_wait();
+        const uint32_t rr[8] = {res0.x, res0.y, res0.z, res0.w, res1.x, res1.y, res1.z, res1.w};
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int n = cc * 16 + 2 * i;
+          const float2 rf = Pack2<T>::unpack(rr[i]);
+          float a0 = fmaf(__uint_as_float(v[2 * i]), ss[n], ss[p.n_cta + n]);
+          float a1 = fmaf(__uint_as_float(v[2 * i + 1]), ss[n + 1], ss[p.n_cta + n + 1]);
+          if (residual) {
+            a0 += rf.x;
+            a1 += rf.y;
+          }
+          o[i] = Pack2<T>::pack(lrelu02(a0), lrelu02(a1));
+        }
+        uint4* dst = reinterpret_cast<uint4*>(stg + (size_t)lane * p.epi_pitch + cc * 32);
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_tempty + 8 * acc);
+        if (residual) mbar_arrive(bar_aempty + 8 * stage);
+      }
+      // transposed read-back: consecutive lanes write consecutive 16 B of a cell's channel vector
+      const int cpo = p.n_cta >> 3;       // 16-byte chunks per cell
+      const int tot = 32 * cpo;
+      T* outp = reinterpret_cast<T*>(p.out);
+      for (int idx = lane; idx < tot; idx += 32) {
+        const int i = idx / cpo, c = idx - i * cpo;
+        const int rr2 = q * 32 + i;
+        const int y2 = tyi * kTileH + (rr2 >> 3), x2 = txi * kTileW + (rr2 & 7);
+        if (y2 < p.H && x2 < p.W) {
+          const uint4 val = *reinterpret_cast<const uint4*>(stg + (size_t)i * p.epi_pitch + c * 16);
+          *reinterpret_cast<uint4*>(outp + out_pixel_offset(p, b, y2, x2) + n0 + c * 8) = val;
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CUDA-core checker with the SAME parameters, packed weights and epilogue: one thread per (cell, n).
+// Test infrastructure for the tensor-core kernel (debug entry point only; never on the product path).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float ld16bit(const T* p);
+template <>
+__device__ __forceinline__ float ld16bit<__half>(const __half* p) { return __half2float(*p); }
+template <>
+__device__ __forceinline__ float ld16bit<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T>
+__device__ __forceinline__ T cvt16bit(float v);
+template <>
+__device__ __forceinline__ __half cvt16bit<__half>(float v) { return __float2half_rn(v); }
+template <>
+__device__ __forceinline__ __nv_bfloat16 cvt16bit<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename T>
+__global__ void tapconv_ref_kernel(const __grid_constant__ TapConvParams p) {
+  const size_t total = (size_t)p.B * p.H * p.W * p.n_total;
+  for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
+    const int n = (int)(id % p.n_total);
+    size_t cell = id / p.n_total;
+    const int gx = (int)(cell % p.W);
+    cell /= p.W;
+    const int gy = (int)(cell % p.H);
+    const int b = (int)(cell / p.H);
+    const int split = n / p.n_cta, nl = n - split * p.n_cta;
+    const T* w = reinterpret_cast<const T*>(p.w) + (size_t)split * (p.w_bytes / 2);
+    const T* in = reinterpret_cast<const T*>(p.in);
+    float acc = 0.f;
+    int j = 0;  // running K=16 step
+    for (int e = 0; e < p.ntaps; ++e) {
+      const TapEntry te = p.taps[e];
+      const int y = gy + te.dy, x = gx + te.dx;
+      const bool ok = y >= 0 && y < p.H && x >= 0 && x < p.W;
+      for (int i = 0; i < te.nk16; ++i, ++j) {
+        if (!ok) continue;
+        for (int c = 0; c < 16; ++c) {
+          const int cin_idx = te.chunk0 * 8 + i * 16 + c;
+          const float a = ld16bit<T>(in + (((size_t)b * p.H + y) * p.W + x) * p.cin + cin_idx);
+          const int kk = j * 2 + (c >> 3);  // 8-channel K chunk
+          const float wv = ld16bit<T>(w + ((size_t)kk * p.n_cta + nl) * 8 + (c & 7));
+          acc = fmaf(a, wv, acc);
+        }
+      }
+    }
+    if (p.epi_mode == EPI_LASTCONV) {
+      const int c5 = n >> 4, pos = n & 15;
+      const int Hs = p.H * 4, Ws = p.W * 4;
+      const size_t o = ((size_t)b * Hs + gy * 4 + (pos >> 2)) * Ws + gx * 4 + (pos & 3);
+      const float v = acc + p.shift[n];
+      if (c5 < 4)
+        reinterpret_cast<float*>(p.out_flow)[o * 4 + c5] = v;
+      else
+        p.out_mask[o] = v;
+    } else {
+      float v = fmaf(acc, p.scale[n], p.shift[n]);
+      if (p.epi_mode == EPI_RESCONV) v += ld16bit<T>(in + (((size_t)b * p.H + gy) * p.W + gx) * p.cin + n);
+      reinterpret_cast<T*>(p.out)[out_pixel_offset(p, b, gy, gx) + n] = cvt16bit<T>(lrelu02(v));
+    }
+  }
+}
+
+uint32_t ceil_magic(uint32_t d) { return (uint32_t)((0x100000000ull + d - 1) / d); }
+uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+int tapconv_plan(const TapConvLayer& L, TapConvParams* pp) {
+  TapConvParams& p = *pp;
+  p.cin = L.cin;
+  p.n_total = L.n_total;
+  p.n_cta = L.n_cta;
+  p.nsplit = L.nsplit;
+  p.ntaps = L.ntaps;
+  p.ktotal16 = L.ktotal16;
+  p.halo_y0 = L.halo_y0;
+  p.halo_x0 = L.halo_x0;
+  p.halo_h = L.halo_h;
+  p.halo_w = L.halo_w;
+  p.halo_px = L.halo_h * L.halo_w;
+  p.epi_mode = L.epi_mode;
+  p.out_s2d = L.out_s2d;
+  for (int e = 0; e < L.ntaps; ++e) p.taps[e] = L.taps[e];
+  int plane_px = p.halo_px | 1;  // odd number of 16-byte slots: the 8 planes one pixel is scattered to hit 8 banks
+  p.plane_bytes = plane_px * 16;
+  p.cpp = (uint32_t)L.cin / 8;
+  p.cpp_magic = ceil_magic(p.cpp);
+  p.halow_magic = ceil_magic((uint32_t)L.halo_w);
+  p.w_bytes = (uint32_t)L.ktotal16 * 2u * (uint32_t)L.n_cta * 16u;
+  p.stage_bytes = align_up(p.cpp * (uint32_t)p.plane_bytes, 128);
+  p.epi_pitch = (uint32_t)L.n_cta * 2u + 16u;
+  const uint32_t epi_bytes = (L.epi_mode == EPI_LASTCONV) ? 0u : 128u * p.epi_pitch;
+  p.off_ss = kCtrlBytes;
+  p.off_w = align_up(p.off_ss + 2u * (uint32_t)L.n_cta * 4u, 128);
+  p.off_a = align_up(p.off_w + p.w_bytes, 128);
+  int stages = 0;
+  for (int s = kMaxStages; s >= 1; --s) {
+    if (p.off_a + (uint32_t)s * p.stage_bytes + epi_bytes <= (uint32_t)kSmemLimit) {
+      stages = s;
+      break;
+    }
+  }
+  p.stages = stages;
+  p.off_epi = p.off_a + (uint32_t)stages * p.stage_bytes;
+  // accumulators: two buffers of n_cta fp32 columns, allocation is a power of two >= 32
+  uint32_t stride = 16;
+  while (stride < (uint32_t)L.n_cta) stride <<= 1;
+  p.acc_stride = stride;
+  p.tmem_cols = stride * 2 < 32 ? 32 : stride * 2;
+  return stages;
+}
+
+cudaError_t launch_tapconv(const TapConvLayer& L, int op_type, const void* in, void* out, float4* out_flow,
+                           float* out_mask, int B, int H, int W, int num_sms, bool use_ref, cudaStream_t st) {
+  TapConvParams p{};
+  if (tapconv_plan(L, &p) < 1) {
+    set_error("tapconv: layer does not fit in shared memory");
+    return cudaErrorInvalidConfiguration;
+  }
+  if (L.out_s2d && ((H | W) & 1)) {
+    set_error("tapconv: space-to-depth output needs even H and W");
+    return cudaErrorInvalidValue;
+  }
+  p.in = in;
+  p.out = out;
+  p.out_flow = out_flow;
+  p.out_mask = out_mask;
+  p.w = L.w;
+  p.scale = L.scale;
+  p.shift = L.shift;
+  p.B = B;
+  p.H = H;
+  p.W = W;
+  p.tiles_y = (H + kTileH - 1) / kTileH;
+  p.tiles_x = (W + kTileW - 1) / kTileW;
+  p.ntiles = B * p.tiles_y * p.tiles_x;
+  // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=f32, A/B = f16|bf16, both K-major,
+  // N>>3 at [17,23), M>>4 at [24,29)
+  const uint32_t fmt = (op_type == OP_BF16) ? 1u : 0u;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(L.n_cta >> 3) << 17) | ((128u >> 4) << 24);
+
+  if (use_ref) {
+    const size_t total = (size_t)B * H * W * L.n_total;
+    const int blocks = (int)((total + 255) / 256 < 65535 ? (total + 255) / 256 : 65535);
+    if (op_type == OP_BF16)
+      tapconv_ref_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(p);
+    else
+      tapconv_ref_kernel<__half><<<blocks, 256, 0, st>>>(p);
+    return cudaGetLastError();
+  }
+
+  int cps = num_sms / L.nsplit;
+  if (cps < 1) cps = 1;
+  if (cps > p.ntiles) cps = p.ntiles;
+  p.ctas_per_split = cps;
+  const int grid = cps * L.nsplit;
+  const uint32_t epi_bytes = (L.epi_mode == EPI_LASTCONV) ? 0u : 128u * p.epi_pitch;
+  const size_t smem = p.off_epi + epi_bytes;
+  cudaError_t err;
+  if (op_type == OP_BF16) {
+    err = cudaFuncSetAttribute(tapconv_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (err != cudaSuccess) return err;
+    tapconv_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(p);
+  } else {
+    err = cudaFuncSetAttribute(tapconv_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (err != cudaSuccess) return err;
+    tapconv_kernel<__half><<<grid, 256, smem, st>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace vfi

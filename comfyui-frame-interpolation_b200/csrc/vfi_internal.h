@@ -1,0 +1,101 @@
+// Internal declarations shared by the .cu files of libvfi_b200.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+namespace vfi {
+
+// ---------------------------------------------------------------------------------------------
+// tap-list implicit GEMM ("tapconv"): every convolution of an IFBlock is expressed as
+//   out[b, y, x, n] = epi( sum_e sum_{c < 16*nk16_e} in[b, y+dy_e, x+dx_e, 8*chunk0_e + c] * W_e[c, n] )
+// on ONE spatial grid (input grid == output grid, zero outside).  Stride-2 convs read a
+// space-to-depth input, the transposed conv writes a 4x4 sub-pixel patch per grid cell.
+// ---------------------------------------------------------------------------------------------
+enum EpiMode : int {
+  EPI_BIAS_LRELU = 0,  // out = lrelu(acc*scale + shift)                         (conv0.0, conv0.1)
+  EPI_RESCONV = 1,     // out = lrelu(acc*scale + shift + in[b,y,x,n])           (ResConv; scale=beta, shift=bias*beta)
+  EPI_LASTCONV = 2,    // out5[b, 4y+py, 4x+px] = acc + shift, n = c5*16 + py*4+px (ConvT(4,2,1)+PixelShuffle(2))
+};
+
+struct TapEntry {
+  int16_t dy, dx;   // spatial offset of this tap on the grid
+  int16_t chunk0;   // first 8-channel chunk of the input it reads
+  int16_t nk16;     // number of K=16 MMA steps (16 input channels each)
+};
+
+constexpr int kMaxTaps = 9;
+constexpr int kTileH = 16, kTileW = 8;        // one CTA tile = 128 grid cells = UMMA M
+constexpr int kProducerThreads = 96;          // warps 1..3
+constexpr int kSmemLimit = 232448;            // 227 KB opt-in maximum per CTA on sm_100
+
+struct TapConvParams {
+  const void* in;        // [B, H, W, cin] 16-bit, NHWC
+  void* out;             // [B, H, W, n_total] 16-bit NHWC, or its space-to-depth form when out_s2d
+  float4* out_flow;      // EPI_LASTCONV: [B, 4H, 4W] float4 (4 flow components)
+  float* out_mask;       // EPI_LASTCONV: [B, 4H, 4W]
+  const void* w;         // packed weights: [nsplit][2*ktotal16][n_cta][8] 16-bit
+  const float* scale;    // [n_total]
+  const float* shift;    // [n_total]
+  int B, H, W, cin;
+  int n_total, n_cta, nsplit;
+  int ntaps, ktotal16;
+  int halo_y0, halo_x0, halo_h, halo_w, halo_px;
+  int plane_bytes;       // bytes of one 8-channel plane of an A stage: odd multiple of 16 >= 16*halo_px
+  int stages;
+  int epi_mode, out_s2d;
+  int tiles_x, tiles_y, ntiles;
+  int ctas_per_split;
+  uint32_t idesc;
+  uint32_t tmem_cols, acc_stride;
+  uint32_t w_bytes;             // packed weight bytes of one split
+  uint32_t off_ss, off_w, off_a, stage_bytes, off_epi, epi_pitch;
+  uint32_t cpp, cpp_magic, halow_magic;   // chunks per input pixel (cin/8) and exact-division magics
+  TapEntry taps[kMaxTaps];
+};
+
+// A convolution layer bound to its packed weights.
+struct TapConvLayer {
+  int cin = 0, n_total = 0, n_cta = 0, nsplit = 1;
+  int ntaps = 0, ktotal16 = 0;
+  int halo_y0 = 0, halo_x0 = 0, halo_h = 0, halo_w = 0;
+  int epi_mode = 0, out_s2d = 0;
+  TapEntry taps[kMaxTaps];
+  void* w = nullptr;      // device
+  float* scale = nullptr; // device
+  float* shift = nullptr; // device
+};
+
+struct BatchTasks {       // passed by value to the full-resolution kernels
+  int n;
+  int f0[16];
+  int f1[16];
+  float t[16];
+};
+constexpr int kMaxBatch = 16;
+
+// operand element type of the tensor-core path
+enum OperandType : int { OP_F16 = 0, OP_BF16 = 1 };
+
+// ---- launchers (defined in tapconv.cu / elementwise.cu) -------------------------------------
+// Returns cudaSuccess or the launch error; `use_ref` runs the CUDA-core checker instead of the tcgen05 kernel.
+cudaError_t launch_tapconv(const TapConvLayer& L, int op_type, const void* in, void* out, float4* out_flow,
+                           float* out_mask, int B, int H, int W, int num_sms, bool use_ref, cudaStream_t st);
+// smem/stage plan for a layer (for DESIGN.md tables and tests); returns 0 stages when it cannot fit
+int tapconv_plan(const TapConvLayer& L, TapConvParams* p_out);
+
+cudaError_t launch_prep_frames(const float* frames, int n, int H, int W, int cstride, float4* imgs, int Hp, int Wp,
+                               cudaStream_t st);
+cudaError_t launch_front(int op_type, const float4* imgs, const float4* flow, const float* mask, BatchTasks tasks,
+                         int Hp, int Wp, int s, bool first, void* x_s2d, cudaStream_t st);
+cudaError_t launch_upflow(const float4* tmp_flow, const float* tmp_mask, float4* flow, float* mask, int B, int Hp,
+                          int Wp, int s, bool first, cudaStream_t st);
+cudaError_t launch_final(const float4* imgs, const float4* flow, const float* mask, BatchTasks tasks, int Hp, int Wp,
+                         int H, int W, float* out, cudaStream_t st);
+cudaError_t launch_warp(const float* img, const float* flow, float* out, int B, int H, int W, int C, cudaStream_t st);
+
+void set_error(const std::string& s);
+
+}  // namespace vfi

@@ -1,0 +1,152 @@
+"""Host-side engine: owns a vfi_ctx, feeds it PyTorch device memory / host buffers through the C ABI.
+
+PyTorch is plumbing here (device memory, streams); all arithmetic of the path runs in libvfi_b200.so.
+"""
+import ctypes as C
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from ._lib import VfiError, check, lib
+
+OPERAND = {"float32": 0, "float16": 0, "bfloat16": 1}
+# names in IFNet("4.6").state_dict() order (reference rife_arch.py:177-218, :404-408)
+BLOCK_C = (192, 128, 96, 64)
+
+
+def state_dict_names():
+    names = []
+    for b in range(4):
+        p = f"block{b}."
+        names += [p + "conv0.0.0.weight", p + "conv0.0.0.bias", p + "conv0.1.0.weight", p + "conv0.1.0.bias"]
+        for j in range(8):
+            q = p + f"convblock.{j}."
+            names += [q + "beta", q + "conv.weight", q + "conv.bias"]
+        names += [p + "lastconv.0.weight", p + "lastconv.0.bias"]
+    return names
+
+
+def _i32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int32))
+
+
+class Rife46Engine:
+    """RIFE 4.6 on one B200.  `state_dict` maps the reference's parameter names to tensors (any float dtype)."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device: int = 0, dtype: str = "float32", batch: int = 8):
+        if not torch.cuda.is_available():
+            raise VfiError("no CUDA device: this path has no CPU fallback")
+        if dtype not in OPERAND:
+            raise ValueError(f"dtype must be one of {list(OPERAND)}")
+        self._L = lib()
+        self.device = int(device)
+        self._ctx = C.c_void_p()
+        check(self._L.vfi_create(self.device, C.byref(self._ctx)))
+        names = state_dict_names()
+        missing = [n for n in names if n not in state_dict]
+        if missing:
+            raise KeyError(f"state_dict is not a RIFE 4.6 checkpoint; missing {missing[:3]} ...")
+        hold = [state_dict[n].detach().to("cpu", torch.float32).contiguous() for n in names]
+        ptrs = (C.c_void_p * len(hold))(*[t.data_ptr() for t in hold])
+        numel = (C.c_int64 * len(hold))(*[t.numel() for t in hold])
+        check(self._L.vfi_rife46_load(self._ctx, ptrs, numel, len(hold), OPERAND[dtype]))
+        check(self._L.vfi_set_batch(self._ctx, int(batch)))
+        self.dtype = dtype
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self._L.vfi_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ device-resident path
+    def forward(self, frames: torch.Tensor, f0: Sequence[int], f1: Sequence[int], t: Sequence[float],
+                scale_factor: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """frames: CUDA float32 [N,H,W,C>=3] NHWC; returns CUDA float32 [len(t),H,W,3] on the current stream."""
+        assert frames.is_cuda and frames.dtype == torch.float32 and frames.is_contiguous() and frames.dim() == 4
+        n, h, w, c = frames.shape
+        f0a, f1a = _i32(f0), _i32(f1)
+        ta = np.ascontiguousarray(np.asarray(t, dtype=np.float32))
+        nt = len(ta)
+        if out is None:
+            out = torch.empty((nt, h, w, 3), dtype=torch.float32, device=frames.device)
+        assert out.is_cuda and out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == (nt, h, w, 3)
+        st = torch.cuda.current_stream(frames.device).cuda_stream
+        check(self._L.vfi_rife46_forward(self._ctx, frames.data_ptr(), n, h, w, c, f0a.ctypes.data, f1a.ctypes.data,
+                                         ta.ctypes.data, nt, float(scale_factor), out.data_ptr(), st))
+        return out
+
+    # ------------------------------------------------------------------ host-buffer path (node / e2e)
+    def interpolate_host(self, frames: torch.Tensor, f0, f1, t, out: torch.Tensor, out_slots=None,
+                         frame_range=None, scale_factor: float = 1.0):
+        """frames: CPU float32 [N,H,W,C]; out: CPU float32 [M,H,W,3]; task i -> out[out_slots[i]] (default i)."""
+        assert not frames.is_cuda and frames.dtype == torch.float32 and frames.is_contiguous()
+        assert not out.is_cuda and out.dtype == torch.float32 and out.is_contiguous()
+        n, h, w, c = frames.shape
+        assert tuple(out.shape[1:]) == (h, w, 3)
+        f0a, f1a = _i32(f0), _i32(f1)
+        ta = np.ascontiguousarray(np.asarray(t, dtype=np.float32))
+        lo, hi = (0, n) if frame_range is None else frame_range
+        slots = None
+        if out_slots is not None:
+            slots = _i32(out_slots)
+            assert len(slots) == len(ta) and (len(slots) == 0 or int(slots.max()) < out.shape[0])
+        else:
+            assert out.shape[0] >= len(ta)
+        check(self._L.vfi_rife46_interpolate_host(
+            self._ctx, frames.data_ptr(), n, h, w, c, int(lo), int(hi), f0a.ctypes.data, f1a.ctypes.data,
+            ta.ctypes.data, None if slots is None else slots.ctypes.data, len(ta), float(scale_factor),
+            out.data_ptr()))
+        return out
+
+    # ------------------------------------------------------------------ primitives / hooks
+    def warp(self, img: torch.Tensor, flow: torch.Tensor) -> torch.Tensor:
+        """NHWC float32 CUDA: img [B,H,W,C], flow [B,H,W,2] (pixels) -> [B,H,W,C]  (rife_arch.warp semantics)."""
+        assert img.is_cuda and flow.is_cuda and img.is_contiguous() and flow.is_contiguous()
+        b, h, w, c = img.shape
+        assert tuple(flow.shape) == (b, h, w, 2)
+        out = torch.empty_like(img)
+        st = torch.cuda.current_stream(img.device).cuda_stream
+        check(self._L.vfi_warp_bilinear_border(self._ctx, img.data_ptr(), flow.data_ptr(), out.data_ptr(), b, h, w, c, st))
+        return out
+
+    def debug_layer(self, block, layer, x, out, out_mask=None, impl=0):
+        b, h, w = x.shape[0], x.shape[1], x.shape[2]
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        check(self._L.vfi_rife46_debug_layer(self._ctx, block, layer, x.data_ptr(), out.data_ptr(),
+                                             None if out_mask is None else out_mask.data_ptr(), b, h, w, impl, st))
+        return out
+
+    def layer_plan(self, block, layer):
+        st, nc, ns, sm, mc = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+        check(self._L.vfi_rife46_layer_plan(self._ctx, block, layer, C.byref(st), C.byref(nc), C.byref(ns),
+                                            C.byref(sm), C.byref(mc)))
+        return dict(stages=st.value, n_cta=nc.value, nsplit=ns.value, smem_bytes=sm.value, macs_per_cell=mc.value)
+
+    def debug_state(self, batch):
+        """(flow [B,Hp,Wp,4], mask [B,Hp,Wp]) of the last internal pass, copied to torch CUDA tensors."""
+        fp, mp, hp, wp = C.c_void_p(), C.c_void_p(), C.c_int(), C.c_int()
+        check(self._L.vfi_rife46_debug_state(self._ctx, C.byref(fp), C.byref(mp), C.byref(hp), C.byref(wp)))
+        self.sync()
+        n = batch * hp.value * wp.value
+        flow = torch.empty((batch, hp.value, wp.value, 4), dtype=torch.float32, device=f"cuda:{self.device}")
+        mask = torch.empty((batch, hp.value, wp.value), dtype=torch.float32, device=f"cuda:{self.device}")
+        cudart = torch.cuda.cudart()
+        cudart.cudaMemcpy(flow.data_ptr(), fp.value, n * 16, 3)
+        cudart.cudaMemcpy(mask.data_ptr(), mp.value, n * 4, 3)
+        return flow, mask
+
+    def set_batch(self, b):
+        check(self._L.vfi_set_batch(self._ctx, int(b)))
+
+    def launch_count(self) -> int:
+        return int(self._L.vfi_launch_count(self._ctx))
+
+    def sync(self):
+        check(self._L.vfi_sync(self._ctx))

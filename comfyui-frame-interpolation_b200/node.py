@@ -1,0 +1,214 @@
+"""ComfyUI node surface of the B200 path: a drop-in for the reference's `RIFE VFI` node.
+
+Mirrors vfi_models/rife/__init__.py:34-239 (class attributes, kwargs, task order, skip / multiplier-list
+semantics, output assembly, dtype round trip) and vfi_utils.py:49-81, :391-407 (InterpolationStateList,
+MakeInterpolationStateList, FloatToInt).  The per-batch hot loop (:185-222) is replaced by ONE call into
+libvfi_b200.so; there is no PyTorch/CPU fallback.
+"""
+import os
+import pathlib
+import threading
+import typing
+
+import torch
+
+from .engine import Rife46Engine
+
+MODEL_TYPE = "rife"
+# The reference table (rife/__init__.py:10-20) has no 4.6 entry at this commit although IFNet supports it and
+# GMFSS uses rife46.pth; this node adds it.  Other arch versions are the next scope row.
+CKPT_NAME_VER_DICT = {
+    "rife46.pth": "4.6",
+}
+DTYPE_OPTIONS = ["float32", "float16", "bfloat16"]
+DTYPE_MAP = {"float32": torch.float32, "float16": torch.float16, "bfloat16": torch.bfloat16}
+
+_model_cache: typing.Dict[typing.Tuple, Rife46Engine] = {}
+
+
+class InterpolationStateList:
+    """vfi_utils.py:49-57"""
+
+    def __init__(self, frame_indices: typing.List[int], is_skip_list: bool):
+        self.frame_indices = frame_indices
+        self.is_skip_list = is_skip_list
+
+    def is_frame_skipped(self, frame_index):
+        is_frame_in_list = frame_index in self.frame_indices
+        return self.is_skip_list and is_frame_in_list or not self.is_skip_list and not is_frame_in_list
+
+
+class MakeInterpolationStateList:
+    """vfi_utils.py:60-81"""
+
+    @classmethod
+    def INPUT_TYPES(s):
+        return {
+            "required": {
+                "frame_indices": ("STRING", {"multiline": True, "default": "1,2,3"}),
+                "is_skip_list": ("BOOLEAN", {"default": True},),
+            },
+        }
+
+    RETURN_TYPES = ("INTERPOLATION_STATES",)
+    FUNCTION = "create_options"
+    CATEGORY = "ComfyUI-Frame-Interpolation/VFI"
+
+    def create_options(self, frame_indices: str, is_skip_list: bool):
+        frame_indices_list = [int(item) for item in frame_indices.split(',')]
+        return (InterpolationStateList(frame_indices=frame_indices_list, is_skip_list=is_skip_list),)
+
+
+class FloatToInt:
+    """vfi_utils.py:391-407"""
+
+    @classmethod
+    def INPUT_TYPES(s):
+        return {"required": {"float": ("FLOAT", {"default": 0, 'min': 0, 'step': 0.01})}}
+
+    RETURN_TYPES = ("INT",)
+    FUNCTION = "convert"
+    CATEGORY = "ComfyUI-Frame-Interpolation"
+
+    def convert(self, float):
+        if hasattr(float, "__iter__"):
+            return (list(map(int, float)),)
+        return (int(float),)
+
+
+def get_ckpt_container_path(model_type):
+    root = os.environ.get("VFI_CKPT_DIR") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "ckpts")
+    return os.path.abspath(os.path.join(root, model_type))
+
+
+def load_file_from_github_release(model_type, ckpt_name):
+    """Same role and name as vfi_utils.py:118-133, minus the download: the file must already be in
+    <ckpts>/<model_type>/ (default ./ckpts, or $VFI_CKPT_DIR), exactly where the reference caches it."""
+    path = os.path.join(get_ckpt_container_path(model_type), ckpt_name)
+    if not os.path.exists(path):
+        raise Exception(f"{ckpt_name} not found at {path}; copy the checkpoint there (this build never downloads)")
+    return path
+
+
+def build_tasks(n_pairs, multiplier, optional_interpolation_states):
+    """Flat (pair_idx, timestep) list - rife/__init__.py:149-174."""
+    if isinstance(multiplier, int):
+        multipliers = [int(multiplier)] * n_pairs
+    else:
+        multipliers = list(map(int, multiplier))
+        multipliers += [2] * (n_pairs - len(multipliers))
+    tasks: typing.List[typing.Tuple[int, float]] = []
+    for pair_idx in range(n_pairs):
+        if optional_interpolation_states is not None and optional_interpolation_states.is_frame_skipped(pair_idx):
+            continue
+        m = multipliers[pair_idx]
+        for step in range(1, m):
+            tasks.append((pair_idx, step / m))
+    return tasks, multipliers
+
+
+class RIFE_VFI:
+    @classmethod
+    def INPUT_TYPES(s):
+        return {
+            "required": {
+                "ckpt_name": (sorted(list(CKPT_NAME_VER_DICT.keys())), {"default": "rife46.pth"}),
+                "frames": ("IMAGE",),
+                "clear_cache_after_n_frames": ("INT", {"default": 10, "min": 1, "max": 1000}),
+                "multiplier": ("INT", {"default": 2, "min": 1}),
+                "fast_mode": ("BOOLEAN", {"default": True}),
+                "ensemble": ("BOOLEAN", {"default": True}),
+                "scale_factor": ([0.25, 0.5, 1.0, 2.0, 4.0], {"default": 1.0}),
+                "dtype": (DTYPE_OPTIONS, {"default": "float32"}),
+                "torch_compile": ("BOOLEAN", {"default": False}),
+                "batch_size": ("INT", {"default": 1, "min": 1, "max": 64}),
+            },
+            "optional": {
+                "optional_interpolation_states": ("INTERPOLATION_STATES",)
+            }
+        }
+
+    RETURN_TYPES = ("IMAGE",)
+    FUNCTION = "vfi"
+    CATEGORY = "ComfyUI-Frame-Interpolation/VFI"
+
+    def vfi(
+        self,
+        ckpt_name: typing.AnyStr,
+        frames: torch.Tensor,
+        clear_cache_after_n_frames: int = 10,
+        multiplier: typing.SupportsInt = 2,
+        fast_mode: bool = False,
+        ensemble: bool = False,
+        scale_factor: float = 1.0,
+        dtype: str = "float32",
+        torch_compile: bool = False,
+        batch_size: int = 1,
+        optional_interpolation_states: InterpolationStateList = None,
+        **kwargs
+    ):
+        """Same contract as the reference: frames [N,H,W,C] float32 in [0,1] -> ([(N-1)*m+1, H, W, 3] float32 CPU,).
+
+        Accepted for API compatibility, without effect on results: clear_cache_after_n_frames (the workspace is
+        pre-allocated, nothing to clear), fast_mode / ensemble (they never reach the 4.6 maths in the reference
+        either - positional mis-wiring), torch_compile, batch_size (internal passes are sized by
+        the engine).  dtype selects the tensor-core operand type: float32/float16 -> fp16 operands with fp32
+        accumulation (same 10-bit mantissa as the TF32 convs the reference's float32 mode runs on a GPU),
+        bfloat16 -> bf16 operands; flow, mask, warps and blending are fp32 in every mode.
+        """
+        arch_ver = CKPT_NAME_VER_DICT[ckpt_name]
+        assert arch_ver == "4.6"
+        model_path = load_file_from_github_release(MODEL_TYPE, ckpt_name)
+        torch_dtype = DTYPE_MAP[dtype]
+        cache_key = (ckpt_name, dtype)
+        if cache_key not in _model_cache:
+            sd = torch.load(model_path, map_location="cpu", weights_only=False)
+            _model_cache[cache_key] = Rife46Engine(sd, device=torch.cuda.current_device(), dtype=dtype)
+        engine = _model_cache[cache_key]
+
+        assert len(frames) >= 2, f"RIFE needs at least 2 frames, only found {frames.shape[0]}"
+        frames = frames.detach()
+        src = frames.to("cpu", torch.float32).contiguous()  # borrowed, never mutated
+        n, h, w, _ = src.shape
+        n_pairs = n - 1
+        tasks, _ = build_tasks(n_pairs, multiplier, optional_interpolation_states)
+
+        # output order: each original frame followed by its interpolated frames - rife/__init__.py:225-231
+        per_pair = [0] * n_pairs
+        for p, _t in tasks:
+            per_pair[p] += 1
+        first_slot, slot = [], 0
+        for p in range(n_pairs):
+            first_slot.append(slot)
+            slot += 1 + per_pair[p]
+        total = slot + 1
+        out = torch.empty((total, h, w, 3), dtype=torch.float32, pin_memory=torch.cuda.is_available())
+        seen = [0] * n_pairs
+        f0, f1, ts, slots = [], [], [], []
+        for p, t in tasks:
+            seen[p] += 1
+            f0.append(p); f1.append(p + 1); ts.append(t); slots.append(first_slot[p] + seen[p])
+
+        err: typing.List[BaseException] = []
+
+        def run():
+            try:
+                engine.interpolate_host(src, f0, f1, ts, out, out_slots=slots, scale_factor=float(scale_factor))
+            except BaseException as e:  # surfaced on the caller's thread below
+                err.append(e)
+
+        th = threading.Thread(target=run)
+        th.start()
+        # pass-through frames are copied on the host while the GPU pipeline runs (ctypes drops the GIL)
+        orig_slots = torch.tensor(first_slot + [total - 1], dtype=torch.long)
+        passthrough = src[..., :3]
+        if torch_dtype != torch.float32:  # the reference round-trips every frame through `dtype` (:227,:230,:238)
+            passthrough = passthrough.to(torch_dtype).to(torch.float32)
+        out.index_copy_(0, orig_slots, passthrough.contiguous())
+        th.join()
+        if err:
+            raise err[0]
+        if torch_dtype != torch.float32 and slots:
+            mid = torch.tensor(slots, dtype=torch.long)
+            out.index_copy_(0, mid, out.index_select(0, mid).to(torch_dtype).to(torch.float32))
+        return (out,)

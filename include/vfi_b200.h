@@ -1,0 +1,101 @@
+/* libvfi_b200.so - C ABI of the B200-native frame-interpolation hot path (RIFE 4.6 first).
+ *
+ * The reference (Fannovel16/ComfyUI-Frame-Interpolation @ 26545cc) has no native library: its "FFI" is
+ * (a) PyTorch ATen calls from vfi_models/rife/rife_arch.py and (b) cupy RawModule launches that pass
+ * `(int32 n, raw device pointers...)` on torch's current stream (vfi_models/ops/cupy_ops/softsplat.py:206-224).
+ * This header is what a maintainer binds instead (ctypes stub in INTEGRATION.md).  Conventions:
+ *   - plain pointers and sizes only, no torch types; device pointers are owned by the caller (PyTorch);
+ *   - every function returns 0 on success or a negative VFI_E_* code; vfi_last_error() gives the text
+ *     (thread-local);  the Python host raises RuntimeError, mirroring the reference's exception behaviour;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); no hidden synchronisation
+ *     unless the function name says *_host or *_sync;
+ *   - images are float32 NHWC in [0,1] exactly as ComfyUI's IMAGE type (rife/__init__.py:146,239).
+ */
+#ifndef VFI_B200_H
+#define VFI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VFI_OK 0
+#define VFI_E_INVALID (-1)   /* bad argument / unsupported configuration */
+#define VFI_E_CUDA (-2)      /* CUDA runtime or kernel error */
+#define VFI_E_STATE (-3)     /* e.g. forward before weights were loaded */
+#define VFI_E_NOTIMPL (-4)
+
+#define VFI_OPERAND_F16 0    /* conv operands fp16, fp32 accumulate (node dtype float32 / float16) */
+#define VFI_OPERAND_BF16 1   /* conv operands bf16, fp32 accumulate (node dtype bfloat16) */
+
+#define VFI_RIFE46_NUM_TENSORS 120   /* IFNet("4.6").state_dict() - rife_arch.py:404-408 */
+#define VFI_MAX_BATCH 16
+
+typedef struct vfi_ctx vfi_ctx;
+
+/* library / context ------------------------------------------------------------------------------------ */
+const char* vfi_last_error(void);
+const char* vfi_version(void);
+/* Creates a context bound to CUDA device `device` (its own compute/copy streams, workspace, weights). */
+int vfi_create(int device, vfi_ctx** out);
+int vfi_destroy(vfi_ctx* ctx);
+/* Number of kernels this library has launched through `ctx` since creation (bench.py "gpu_launches"). */
+int64_t vfi_launch_count(const vfi_ctx* ctx);
+/* Pairs interpolated per internal pass (1..VFI_MAX_BATCH, default 8); replaces the node's batch_size knob
+ * (rife/__init__.py:64-69) - it changes scheduling only, never results. */
+int vfi_set_batch(vfi_ctx* ctx, int batch);
+
+/* Replaces: IFNet(arch_ver="4.6").load_state_dict(torch.load(path)) - rife/__init__.py:129-133.
+ * `tensors[i]` are HOST float32 arrays in state_dict order (block{b}.conv0.0.0.weight, .bias, conv0.1.0.weight,
+ * .bias, 8 x convblock.{j}.{beta, conv.weight, conv.bias}, lastconv.0.weight, .bias; b = 0..3); `numel[i]` is
+ * checked against the architecture.  Weights are repacked to the tensor-core operand layout on the device. */
+int vfi_rife46_load(vfi_ctx* ctx, const float* const* tensors, const int64_t* numel, int n_tensors, int operand_type);
+
+/* Replaces: the body of the hot loop of RIFE_VFI.vfi - rife/__init__.py:185-207 - i.e.
+ *   IFNet.forward(frame[f0[i]], frame[f1[i]], t[i], scale_list=[8,4,2,1]/scale_factor).clamp(0,1)
+ * for n_tasks (pair, timestep) tasks.  DEVICE pointers:
+ *   frames : [n_frames, H, W, C] float32 NHWC, C >= 3 (only the first 3 channels are read, vfi_utils.py:139)
+ *   out    : [n_tasks, H, W, 3] float32 NHWC
+ * Asynchronous on `stream`. */
+int vfi_rife46_forward(vfi_ctx* ctx, const float* frames, int n_frames, int H, int W, int C, const int32_t* f0,
+                       const int32_t* f1, const float* t, int n_tasks, float scale_factor, float* out, void* stream);
+
+/* Replaces: the whole per-batch loop incl. `.to(device)` / `.cpu()` - rife/__init__.py:185-222 - with a
+ * pipelined H2D / compute / D2H schedule.  HOST pointers (pinned memory gives full PCIe rate; pageable works):
+ *   frames : [n_frames, H, W, C] float32;  out : frames of [H, W, 3] float32.
+ * Task i is written to out + out_slot[i]*H*W*3 (out_slot == NULL: slot i), so the caller can have the
+ * interpolated frames land directly between the pass-through frames of the node's output tensor
+ * (rife/__init__.py:225-238) without a second host copy.
+ * Only frames in [frame_lo, frame_hi) are uploaded (the shard of this rank); tasks must reference only those.
+ * Synchronous: returns when `out` is complete. */
+int vfi_rife46_interpolate_host(vfi_ctx* ctx, const float* frames, int n_frames, int H, int W, int C, int frame_lo,
+                                int frame_hi, const int32_t* f0, const int32_t* f1, const float* t,
+                                const int32_t* out_slot, int n_tasks, float scale_factor, float* out);
+
+/* Primitive: backward bilinear warp == rife_arch.warp (rife_arch.py:31-70) ==
+ * grid_sample(bilinear, padding_mode="border", align_corners=True) on a pixel-unit flow.  DEVICE pointers, NHWC:
+ * img [B,H,W,C] float32, flow [B,H,W,2] float32 (x, y displacement in pixels), out [B,H,W,C]. */
+int vfi_warp_bilinear_border(vfi_ctx* ctx, const float* img, const float* flow, float* out, int B, int H, int W, int C,
+                             void* stream);
+
+/* Test / profiling hooks (used by tests/ and bench.py only) --------------------------------------------- */
+/* Run ONE convolution layer of block `block` (0..3): layer 0 = conv0.0, 1 = conv0.1, 2..9 = ResConv 0..7,
+ * 10 = lastconv.  `in`/`out` are device tensors in the kernel-native layouts documented in DESIGN.md
+ * (16-bit NHWC; layers 0/1 read space-to-depth inputs; layer 10 writes float4 flow + float mask planes).
+ * impl 0 = tcgen05 kernel, 1 = CUDA-core checker with the same packed weights. */
+int vfi_rife46_debug_layer(vfi_ctx* ctx, int block, int layer, const void* in, void* out, void* out_mask, int B, int H,
+                           int W, int impl, void* stream);
+/* Device pointers to the full-resolution flow (float4 [B,Hp,Wp]) and mask (float [B,Hp,Wp]) of the LAST
+ * internal pass, valid until the next forward. */
+int vfi_rife46_debug_state(vfi_ctx* ctx, const float** flow4, const float** mask, int* Hp, int* Wp);
+/* Static plan of a layer for (block, layer): shared-memory stages, CTA output channels, splits, smem bytes. */
+int vfi_rife46_layer_plan(vfi_ctx* ctx, int block, int layer, int* stages, int* n_cta, int* nsplit, int* smem_bytes,
+                          int64_t* macs_per_cell);
+int vfi_sync(vfi_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VFI_B200_H */

@@ -1,0 +1,70 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/vfi_b200.h declares; the node
+surface matches the reference's; no compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    from cfi_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "vfi_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(vfi_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared == sorted(_lib.SYMBOLS)
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for s in declared:
+        assert hasattr(L, s), s
+    assert b"sm_100a" in _lib.lib().vfi_version()
+
+
+def test_no_gpu_is_a_loud_error(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from cfi_b200._lib import VfiError, lib
+    from cfi_b200.engine import Rife46Engine
+    with pytest.raises(VfiError):
+        Rife46Engine({}, 0)
+    ctx = ctypes.c_void_p()
+    assert lib().vfi_create(0, ctypes.byref(ctx)) != 0
+    assert len(lib().vfi_last_error()) > 0
+
+
+def test_node_surface_matches_reference(pkg):
+    """rife/__init__.py:36-75 and root __init__.py:23-47."""
+    import cfi_b200 as P
+    import cfi_b200.node as N
+    assert P.NODE_CLASS_MAPPINGS["RIFE VFI"] is N.RIFE_VFI
+    it = N.RIFE_VFI.INPUT_TYPES()
+    assert list(it["required"].keys()) == ["ckpt_name", "frames", "clear_cache_after_n_frames", "multiplier",
+                                           "fast_mode", "ensemble", "scale_factor", "dtype", "torch_compile",
+                                           "batch_size"]
+    assert it["required"]["frames"] == ("IMAGE",)
+    assert it["required"]["clear_cache_after_n_frames"][1] == {"default": 10, "min": 1, "max": 1000}
+    assert it["required"]["scale_factor"][0] == [0.25, 0.5, 1.0, 2.0, 4.0]
+    assert it["required"]["dtype"][0] == ["float32", "float16", "bfloat16"]
+    assert it["optional"] == {"optional_interpolation_states": ("INTERPOLATION_STATES",)}
+    assert N.RIFE_VFI.RETURN_TYPES == ("IMAGE",) and N.RIFE_VFI.FUNCTION == "vfi"
+    assert N.RIFE_VFI.CATEGORY == "ComfyUI-Frame-Interpolation/VFI"
+    assert "rife46.pth" in it["required"]["ckpt_name"][0]
+
+
+def test_task_builder_matches_oracle(pkg):
+    import cfi_b200.node as N
+    from oracle import rife46 as O
+    for mult, states in [(3, ([1], True)), ([2, 1, 3], None), (2, ([0, 2], False)), (1, None), ([0, 4], None)]:
+        st = None if states is None else N.InterpolationStateList(list(states[0]), states[1])
+        assert N.build_tasks(4, mult, st) == O.build_tasks(5, mult, states)
+    (lst,) = N.MakeInterpolationStateList().create_options("1, 2,3", True)
+    assert lst.is_frame_skipped(2) and not lst.is_frame_skipped(0)
+    assert N.FloatToInt().convert(2.7) == (2,) and N.FloatToInt().convert([1.2, 3.9]) == ([1, 3],)
+
+
+def test_missing_checkpoint_is_an_error(pkg, monkeypatch, tmp_path):
+    import cfi_b200.node as N
+    monkeypatch.setenv("VFI_CKPT_DIR", str(tmp_path))
+    with pytest.raises(Exception):
+        N.load_file_from_github_release("rife", "rife46.pth")

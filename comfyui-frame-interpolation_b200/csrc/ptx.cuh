@@ -36,11 +36,17 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
-// Bounded wait: a protocol bug becomes a trap (a loud CUDA error), never a hung GPU.
+// Bounded wait (2 s of wall clock): a protocol bug becomes a trap (a loud CUDA error), never a hung GPU.
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
-  uint32_t spins = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = globaltimer_ns();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) {
+    if (globaltimer_ns() - t0 > 2000000000ull) {
       printf("vfi: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag, (int)blockIdx.x,
              (int)threadIdx.x, parity);
       __trap();

@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py - interpolated frames/s of the RIFE-4.6 2x path at 1080p (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one synthetic 64-frame 1080p clip per GPU (63 frame pairs, 2x ->
+63 interpolated frames; SURVEY.md section 8d config 2 / BASELINE.json configs[1]).  Weak scaling: every rank
+interpolates its own 64-frame shard of a (63*N+1)-frame clip (frame pairs are independent, one-frame halo),
+and for N > 1 the interpolated frames are gathered on rank 0 over NCCL inside the timed region (the path's
+only exchange step).
+  value : whole-job interpolated frames/s with the clip already resident in HBM (CUDA events, max over ranks)
+  e2e   : same metric through the C-ABI host call (pinned host buffers, H2D + D2H inside the timed region)
+  roofline     : the dominant kernel (tcgen05 tap-conv, block-3 ResConv layer) timed alone, against the measured
+                 bf16 tensor peak in MEASURED_PEAKS.json; plus the HBM-bound warp kernel as roofline_hbm
+  cpu_baseline : the CPU oracle port (oracle/rife46.py == the reference's PyTorch-CPU path) on the
+                 host cores, on a bounded sample of the same clip (rank 0, N = 1 only)
+--impl reference times that CPU port alone (all host threads), same metric / config.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, NFRAMES = 1080, 1920, 64
+METRIC = "interpolated frames/sec @1080p RIFE-4.6 2x"
+UNIT = "frames/s"
+FLOPS_PER_FRAME = 175.245e9          # SURVEY.md section 8d (87.62 GMAC)
+CPU_SAMPLE_FRAMES = 5                # 4 pairs of the same clip for the CPU legs
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tflops=d["bf16_tflops"], tflops_sustained=d.get("bf16_tflops_sustained"),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, tflops=1590.0, tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # "under load" = samples above the idle clock
+        load = [v for v in sm if v > 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_fps(clip, sd, steps, warmup):
+    """The CPU restatement of the reference path (== reference PyTorch-CPU eager, fp32) on all host threads."""
+    import torch
+    from oracle import rife46 as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    sample = clip[:CPU_SAMPLE_FRAMES].contiguous()
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.rife_vfi(sd, sample, multiplier=2)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    n = CPU_SAMPLE_FRAMES - 1
+    return n * len(times) / sum(times), sum(times) / len(times)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="pairs per internal pass (scheduling only)")
+    ap.add_argument("--dtype", default="float32", help="node dtype: float32/float16 -> fp16 operands, bfloat16 -> bf16")
+    ap.add_argument("--frames", type=int, default=NFRAMES)
+    a = ap.parse_args()
+
+    import torch
+    from oracle import rife46 as O
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.gpus != world and world > 1:
+        a.gpus = world
+    config = {"workload": f"RIFE 4.6, 2x multiplier, {a.frames}-frame synthetic 1080p clip per GPU (BASELINE configs[1])",
+              "resolution": [H, W], "frames_per_gpu": a.frames, "pairs_per_gpu": a.frames - 1,
+              "padded": [1088, 1920], "weights": "seeded synthetic (oracle.synthetic_state_dict(0)); no checkpoint ships",
+              "parallelism": f"frame-pair shards x{a.gpus}, NCCL gather of outputs to rank 0" if a.gpus > 1 else "1 GPU",
+              "l2": "inputs larger than L2 (1.6 GB clip, 1.6 GB output per step)"}
+
+    sd = O.synthetic_state_dict(0)
+
+    # ------------------------------------------------------------------ reference arm: CPU port only
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        clip = O.synthetic_clip(CPU_SAMPLE_FRAMES, H, W, seed=1234)
+        fps, sec = cpu_port_fps(clip, sd, max(a.steps, 1), max(a.warmup, 1))
+        cores = os.cpu_count() or 1
+        line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": 0, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": f"{CPU_SAMPLE_FRAMES - 1} pairs of the 1080p clip per step (bounded sample), "
+                                           f"oracle/rife46.py = reference PyTorch-CPU path, {cores} threads"},
+                "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import __graft_entry__ as ge
+    ge.load_package()
+    from cfi_b200.engine import Rife46Engine
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    nf = a.frames
+    clip = O.synthetic_clip(nf, H, W, seed=1234 + rank)            # this rank's shard (own content, same shape)
+    eng = Rife46Engine(sd, device=local_rank, dtype=a.dtype, batch=a.batch)
+    f0 = list(range(nf - 1))
+    f1 = list(range(1, nf))
+    ts = [0.5] * (nf - 1)
+    npairs = nf - 1
+
+    # ---- device-resident throughput ("value")
+    dev_clip = clip.cuda()
+    dev_out = torch.empty((npairs, H, W, 3), dtype=torch.float32, device="cuda")
+    gather_list = None
+    if dist is not None and rank == 0:
+        gather_list = [torch.empty_like(dev_out) for _ in range(world)]
+
+    def step_device():
+        eng.forward(dev_clip, f0, f1, ts, out=dev_out)
+        if dist is not None:
+            dist.gather(dev_out, gather_list, dst=0)
+
+    for _ in range(a.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step_device()
+    e1.record()
+    barrier()
+    launches = eng.launch_count() - l0
+    ms_dev = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the host C-ABI call ("e2e")
+    host_in = clip.contiguous().pin_memory()
+    host_out = torch.empty((npairs, H, W, 3), dtype=torch.float32).pin_memory()
+    for _ in range(max(1, min(a.warmup, 2))):
+        eng.interpolate_host(host_in, f0, f1, ts, host_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        eng.interpolate_host(host_in, f0, f1, ts, host_out)
+    barrier()
+    sec_e2e = time.perf_counter() - t0
+    # parity spot check inside the bench: host path == device path on this rank's data
+    same = bool(torch.equal(host_out[:2], dev_out[:2].cpu()))
+
+    # ---- reduce timings: max over ranks
+    tt = torch.tensor([ms_dev, sec_e2e * 1e3], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = tt.tolist()
+
+    if rank == 0:
+        peaks = _peaks()
+        total = npairs * world
+        value = total * a.steps / (ms_dev / 1e3)
+        e2e = total * a.steps / (ms_e2e / 1e3)
+
+        # ---- roofline of the dominant kernel, timed alone with CUDA events (flush L2 between launches)
+        tdt = torch.bfloat16 if a.dtype == "bfloat16" else torch.float16
+        B = a.batch
+        x = (0.1 * torch.randn(B, 272, 480, 64, device="cuda")).to(tdt)
+        y = torch.empty_like(x)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        pl = eng.layer_plan(3, 2)
+        tl = []
+        for i in range(13):
+            flush.zero_()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            eng.debug_layer(3, 2, x, y)
+            a1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                tl.append(a0.elapsed_time(a1))
+        k_ms = sum(tl) / len(tl)
+        k_flops = 2.0 * pl["macs_per_cell"] * B * 272 * 480
+        achieved = k_flops / (k_ms * 1e-3) / 1e12
+        roofline = {"kernel": "tapconv_kernel (block-3 ResConv 64->64, 272x480 cells, tcgen05)", "bound": "tensor",
+                    "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+                    "traffic": None, "peak_source": peaks["source"] + ", burst figure (kernel timed alone)",
+                    "launch_ms": k_ms, "flops_per_launch": k_flops}
+        # HBM-bound primitive: stand-alone warp on the padded 1080p frame, float4 pixels (C=4)
+        img = torch.rand(B, 1088, 1920, 4, device="cuda")
+        fl = 4 * torch.randn(B, 1088, 1920, 2, device="cuda")
+        tl = []
+        for i in range(13):
+            flush.zero_()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            eng.warp(img, fl)
+            a1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                tl.append(a0.elapsed_time(a1))
+        w_ms = sum(tl) / len(tl)
+        w_bytes = B * 1088 * 1920 * (4 + 2 + 4) * 4.0
+        roofline_hbm = {"kernel": "warp_kernel<4> (backward bilinear warp, [B,1088,1920,4] fp32)", "bound": "hbm",
+                        "achieved": w_bytes / (w_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": w_bytes / (w_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                        "peak_source": peaks["source"], "launch_ms": w_ms, "bytes_per_launch": w_bytes}
+        del img, fl, x, y, flush
+
+        cpu = None
+        if world == 1:
+            fps, sec = cpu_port_fps(clip, sd, 2, 1)
+            cores = os.cpu_count() or 1
+            cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{CPU_SAMPLE_FRAMES - 1} pairs of the same 1080p clip, 2 timed repetitions "
+                             f"({sec:.1f} s each), oracle/rife46.py == reference PyTorch-CPU path, {cores} threads"}
+
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if a.dtype == "bfloat16" else "f16",
+                "dtype_note": "conv operands 16-bit, fp32 accumulate (TMEM); flow/mask/warp/blend fp32; PSNR>=50 dB "
+                              "vs fp32 oracle enforced by tests/test_gpu_forward.py",
+                "data": "synthetic", "config": dict(config, batch=a.batch),
+                "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
+                        "h2d_bytes_per_step": nf * H * W * 3 * 4, "d2h_bytes_per_step": npairs * H * W * 3 * 4,
+                        "host_equals_device_path": same},
+                "gpu_launches": launches, "clocks": clocks,
+                "model_tflops": value * FLOPS_PER_FRAME / 1e12,
+                "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    eng.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,60 @@
+"""Frame-pair sharding across the GPUs of one box (one process per GPU, torch.distributed for the plumbing).
+
+The per-pair loop of RIFE_VFI.vfi (rife/__init__.py:164-222) is embarrassingly parallel over (pair, timestep)
+tasks: task i needs only frames[pair] and frames[pair+1].  Each rank takes a contiguous, task-count-balanced
+slice (so skip lists / per-pair multiplier lists stay balanced), uploads only its frame range (one-frame halo)
+and the only exchange is the final gather of the interpolated frames on rank 0 (NCCL over NVLink on the GPU box,
+gloo in the CPU tests).  Pure host logic: no CUDA here.
+"""
+from typing import List, Sequence, Tuple
+
+import torch
+
+
+def shard_tasks(n_tasks: int, world: int) -> List[Tuple[int, int]]:
+    """[lo, hi) task slice of every rank: contiguous, sizes differ by at most one, earlier ranks get the extra."""
+    base, extra = divmod(n_tasks, world)
+    out, lo = [], 0
+    for r in range(world):
+        hi = lo + base + (1 if r < extra else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def frame_range(tasks: Sequence[Tuple[int, float]]) -> Tuple[int, int]:
+    """[lo, hi) of the source frames a task slice touches (pair p reads frames p and p+1)."""
+    if not tasks:
+        return (0, 0)
+    ps = [p for p, _ in tasks]
+    return (min(ps), max(ps) + 2)
+
+
+def gather_frames(local: torch.Tensor, counts: Sequence[int], dist, dst: int = 0):
+    """Variable-size gather of per-rank [n_r, H, W, 3] tensors onto `dst`; returns the concatenation on dst, None
+    elsewhere.  Padded to the largest shard so it is a single collective (sizes differ by at most one frame)."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    mx = max(counts)
+    shape = (mx,) + tuple(local.shape[1:])
+    buf = local
+    if local.shape[0] != mx:
+        buf = torch.zeros(shape, dtype=local.dtype, device=local.device)
+        buf[: local.shape[0]] = local
+    bufs = [torch.empty(shape, dtype=local.dtype, device=local.device) for _ in range(world)] if rank == dst else None
+    dist.gather(buf.contiguous(), bufs, dst=dst)
+    if rank != dst:
+        return None
+    return torch.cat([b[:c] for b, c in zip(bufs, counts)], 0)
+
+
+def interpolate_sharded(run_tasks, frames: torch.Tensor, tasks: Sequence[Tuple[int, float]], dist, dst: int = 0):
+    """Run `run_tasks(frames, task_slice, (frame_lo, frame_hi)) -> [n, H, W, 3]` on this rank's slice and gather.
+
+    `run_tasks` is the engine call on the GPU box (Rife46Engine.interpolate_host / forward) and a stand-in in the
+    CPU tests.  Returns all interpolated frames in task order on `dst`."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    slices = shard_tasks(len(tasks), world)
+    lo, hi = slices[rank]
+    mine = list(tasks[lo:hi])
+    local = run_tasks(frames, mine, frame_range(mine))
+    return gather_frames(local, [b - a for a, b in slices], dist, dst)

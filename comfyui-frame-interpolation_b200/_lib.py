@@ -41,7 +41,7 @@ def lib():
     L.vfi_rife46_interpolate_host.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, f32, vp]
     L.vfi_warp_bilinear_border.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
     L.vfi_rife46_debug_layer.argtypes = [vp, i32, i32, vp, vp, vp, i32, i32, i32, i32, vp]
-    L.vfi_rife46_debug_state.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)]
+    L.vfi_rife46_debug_state.argtypes = [vp, vp, vp, i32, C.POINTER(i32), C.POINTER(i32)]
     L.vfi_rife46_layer_plan.argtypes = [vp, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32),
                                         C.POINTER(i32), C.POINTER(i64)]
     L.vfi_sync.argtypes = [vp]

@@ -602,12 +602,21 @@ int vfi_rife46_debug_layer(vfi_ctx* c, int block, int layer, const void* in, voi
   return VFI_OK;
 }
 
-int vfi_rife46_debug_state(vfi_ctx* c, const float** flow4, const float** mask, int* Hp, int* Wp) {
-  if (!c || !flow4 || !mask || !Hp || !Wp) return fail(VFI_E_INVALID, "null argument");
-  *flow4 = (const float*)c->flow.p;
-  *mask = (const float*)c->mask.p;
+int vfi_rife46_debug_state(vfi_ctx* c, float* flow4_out, float* mask_out, int batch, int* Hp, int* Wp) {
+  if (!c || !Hp || !Wp) return fail(VFI_E_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
   *Hp = c->ws_Hp;
   *Wp = c->ws_Wp;
+  const size_t n = (size_t)batch * c->ws_Hp * c->ws_Wp;
+  if (flow4_out) {
+    if (n * sizeof(float4) > c->flow.cap) return fail(VFI_E_INVALID, "batch larger than the last pass");
+    CK(cudaMemcpy(flow4_out, c->flow.p, n * sizeof(float4), cudaMemcpyDeviceToDevice));
+  }
+  if (mask_out) {
+    if (n * sizeof(float) > c->mask.cap) return fail(VFI_E_INVALID, "batch larger than the last pass");
+    CK(cudaMemcpy(mask_out, c->mask.p, n * sizeof(float), cudaMemcpyDeviceToDevice));
+  }
   return VFI_OK;
 }
 

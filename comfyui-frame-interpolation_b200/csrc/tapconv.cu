@@ -37,6 +37,8 @@ struct Ctrl {
   uint32_t tmem_base;
 };
 constexpr uint32_t kCtrlBytes = 256;
+constexpr uint32_t kAtabBytes = 512;   // up to 128 K=16 steps
+constexpr uint32_t kRowoffBytes = 512; // 128 rows
 static_assert(sizeof(Ctrl) <= kCtrlBytes, "control block");
 
 __device__ __forceinline__ size_t out_pixel_offset(const TapConvParams& p, int b, int gy, int gx) {
@@ -68,6 +70,7 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
   const uint32_t bar_aempty = smem_base + offsetof(Ctrl, a_empty);
   const uint32_t bar_tfull = smem_base + offsetof(Ctrl, t_full);
   const uint32_t bar_tempty = smem_base + offsetof(Ctrl, t_empty);
+  uint32_t* rowoff = reinterpret_cast<uint32_t*>(smem + kCtrlBytes + kAtabBytes);  // [128] output element offsets
 
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
@@ -92,37 +95,46 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
   const int tiles_per_img = p.tiles_y * p.tiles_x;
 
   if (warp == 0) {
-    // ======================================================= MMA issuer (one thread)
-    if (lane == 0) {
-      mbar_wait(bar_w, 0, 1);
-      const uint32_t plane = (uint32_t)p.plane_bytes;
-      const uint32_t a_sbo = (uint32_t)p.halo_w * 16u;
-      const uint32_t b_lbo = (uint32_t)p.n_cta * 16u;
-      uint32_t k = 0;
-      for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k) {
-        const uint32_t stage = k % S, use = k / S, acc = k & 1, vuse = k >> 1;
-        mbar_wait(bar_tempty + 8 * acc, (vuse & 1) ^ 1, 2);
-        mbar_wait(bar_afull + 8 * stage, use & 1, 3);
-        fence_proxy_async();  // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
-        tc_fence_after();
-        const uint32_t a_base = a_smem + stage * p.stage_bytes;
-        const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
-        uint32_t j = 0;
-        for (int e = 0; e < p.ntaps; ++e) {
-          const TapEntry te = p.taps[e];
-          const uint32_t tap_addr = a_base + (uint32_t)te.chunk0 * plane +
-                                    (uint32_t)((te.dy - p.halo_y0) * p.halo_w + (te.dx - p.halo_x0)) * 16u;
-          for (int i = 0; i < te.nk16; ++i, ++j) {
-            const uint64_t adesc = umma_desc_nosw(tap_addr + 2u * i * plane, plane, a_sbo);
-            const uint64_t bdesc = umma_desc_nosw(w_smem + j * 2u * b_lbo, b_lbo, 128u);
-            umma_f16(d_tmem, adesc, bdesc, p.idesc, j > 0 ? 1u : 0u);
-          }
+    // ======================================================= MMA issuer
+    // The whole warp runs the (warp-uniform) control flow so that descriptors stay in uniform registers; one
+    // elected lane issues tcgen05.mma / tcgen05.commit.
+    const uint32_t leader = elect_one_sync();
+    mbar_wait(bar_w, 0, 1);
+    // descriptor words that never change: LBO | SBO | version (see umma_desc_nosw)
+    const uint32_t plane16 = (uint32_t)p.plane_bytes >> 4;
+    const uint32_t a_lo_c = plane16 << 16;
+    const uint32_t a_hi_c = (((uint32_t)p.halo_w * 16u) >> 4) | (1u << 14);
+    const uint32_t b_step = ((uint32_t)p.n_cta * 32u) >> 4;  // two 8-channel chunks per K=16 step
+    const uint32_t b_lo_c = (((uint32_t)p.n_cta * 16u) >> 4) << 16;
+    const uint32_t b_hi_c = (128u >> 4) | (1u << 14);
+    const uint32_t b_lo0 = b_lo_c | (w_smem >> 4);
+    uint32_t k = 0;
+    for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k) {
+      const uint32_t stage = k % S, use = k / S, acc = k & 1, vuse = k >> 1;
+      mbar_wait(bar_tempty + 8 * acc, (vuse & 1) ^ 1, 2);
+      mbar_wait(bar_afull + 8 * stage, use & 1, 3);
+      fence_proxy_async();  // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
+      tc_fence_after();
+      const uint32_t a_lo0 = a_lo_c | ((a_smem + stage * p.stage_bytes) >> 4);
+      const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
+      uint32_t b_lo = b_lo0, accum = 0;
+      for (int e = 0; e < p.ntaps; ++e) {
+        const TapEntry te = p.taps[e];
+        uint32_t a_lo = a_lo0 + (uint32_t)te.chunk0 * plane16 +
+                        (uint32_t)((te.dy - p.halo_y0) * p.halo_w + (te.dx - p.halo_x0));
+        for (int i = 0; i < te.nk16; ++i) {
+          if (leader) umma_f16_split(d_tmem, a_lo, a_hi_c, b_lo, b_hi_c, p.idesc, accum);
+          accum = 1;
+          a_lo += 2u * plane16;
+          b_lo += b_step;
         }
+      }
+      if (leader) {
         if (!residual) umma_commit(bar_aempty + 8 * stage);  // window free once the MMAs have read it
         umma_commit(bar_tfull + 8 * acc);                    // accumulator ready for the epilogue
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp < 4) {
     // ======================================================= producers
     const int ptid = threadIdx.x - 32;
@@ -134,28 +146,37 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
         bulk_g2s(w_smem + off, wsrc + off, n, bar_w);
       }
     }
-    const uint32_t total = (uint32_t)p.halo_px * p.cpp;
+    // thread -> fixed 8-channel chunk `ch`, pixels px0, px0+ppi, ... of the window (96 % cpp == 0 for every layer)
+    const uint32_t cpp = p.cpp, ppi = kProducerThreads / cpp;
+    const uint32_t ch = (uint32_t)ptid % cpp, px0 = (uint32_t)ptid / cpp;
+    const uint32_t hy0 = px0 / (uint32_t)p.halo_w, hx0 = px0 - hy0 * (uint32_t)p.halo_w;
+    const uint32_t dst0 = ch * (uint32_t)p.plane_bytes + px0 * 16u;
+    const uint32_t cin2 = (uint32_t)p.cin * 2u;
+    const uint32_t row_bytes = (uint32_t)p.W * cin2;
     const uint8_t* in = reinterpret_cast<const uint8_t*>(p.in);
-    const size_t row_bytes = (size_t)p.W * p.cin * 2;
+    const size_t img_bytes = (size_t)p.H * row_bytes;
     uint32_t k = 0;
     for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k) {
       const uint32_t stage = k % S, use = k / S;
-      mbar_wait(bar_aempty + 8 * stage, (use & 1) ^ 1, 4);
       const int b = t / tiles_per_img;
       const int rem = t - b * tiles_per_img;
       const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
       const int gy0 = tyi * kTileH + p.halo_y0, gx0 = txi * kTileW + p.halo_x0;
-      const uint32_t dst_base = a_smem + stage * p.stage_bytes;
-      const uint8_t* img = in + (size_t)b * p.H * row_bytes;
-      for (uint32_t idx = ptid; idx < total; idx += kProducerThreads) {
-        const uint32_t px = __umulhi(idx, p.cpp_magic);   // idx / cpp
-        const uint32_t ch = idx - px * p.cpp;             // idx % cpp
-        const uint32_t hy = __umulhi(px, p.halow_magic);  // px / halo_w
-        const uint32_t hx = px - hy * p.halo_w;
+      const uint8_t* img = in + (size_t)b * img_bytes + ch * 16u;
+      uint32_t dst = a_smem + stage * p.stage_bytes + dst0;
+      uint32_t hy = hy0, hx = hx0;
+      mbar_wait(bar_aempty + 8 * stage, (use & 1) ^ 1, 4);
+      for (uint32_t px = px0; px < (uint32_t)p.halo_px; px += ppi) {
         const int gy = gy0 + (int)hy, gx = gx0 + (int)hx;
-        const bool ok = (gy >= 0) && (gy < p.H) && (gx >= 0) && (gx < p.W);
-        const uint8_t* src = ok ? img + (size_t)gy * row_bytes + ((size_t)gx * p.cin + ch * 8) * 2 : img;
-        cp_async16(dst_base + ch * (uint32_t)p.plane_bytes + px * 16u, src, ok ? 16u : 0u);
+        const bool ok = ((unsigned)gy < (unsigned)p.H) && ((unsigned)gx < (unsigned)p.W);
+        const uint32_t off = ok ? (uint32_t)gy * row_bytes + (uint32_t)gx * cin2 : 0u;
+        cp_async16(dst, img + off, ok ? 16u : 0u);
+        dst += ppi * 16u;
+        hx += ppi;
+        while (hx >= (uint32_t)p.halo_w) {
+          hx -= (uint32_t)p.halo_w;
+          ++hy;
+        }
       }
       cp_async_arrive_noinc(bar_afull + 8 * stage);
     }
@@ -173,8 +194,13 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
     const int r = q * 32 + lane;           // accumulator row == TMEM lane == tile cell
     const int py = r >> 3, px = r & 7;
     uint8_t* stg = smem + p.off_epi + (size_t)q * 32 * p.epi_pitch;  // this warp's staging rows
+    uint32_t* myrow = rowoff + q * 32;
     const int n0 = split * p.n_cta;
     const uint32_t center = (uint32_t)((py - p.halo_y0) * p.halo_w + (px - p.halo_x0)) * 16u;
+    const uint32_t res_off = (uint32_t)(n0 >> 3) * (uint32_t)p.plane_bytes + center;
+    const int nchunks = p.n_cta >> 4;
+    const uint32_t cpo = (uint32_t)p.n_cta >> 3;  // 16-byte chunks per cell in the output
+    const uint32_t tot = 32u * cpo;
 
     uint32_t k = 0;
     for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k) {
@@ -245,40 +271,50 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
       }
 
       if (residual) mbar_wait(bar_afull + 8 * stage, use & 1, 6);  // acquire the staged window for generic reads
-      const uint32_t a_base = a_smem + stage * p.stage_bytes;
-      const int nchunks = p.n_cta >> 4;
-      for (int cc = 0; cc < nchunks; ++cc) {
-        uint32_t v[16];
-        tmem_ld16(taddr + cc * 16, v);
-        uint4 res0 = make_uint4(0, 0, 0, 0), res1 = make_uint4(0, 0, 0, 0);
+      myrow[lane] = valid ? (uint32_t)out_pixel_offset(p, b, gy, gx) + (uint32_t)n0 : 0xFFFFFFFFu;
+      const uint32_t ra0 = a_smem + stage * p.stage_bytes + res_off;
+      for (int cc = 0; cc < nchunks; cc += 2) {
+        const bool two = (cc + 1 < nchunks);
+        uint32_t v[2][16];
+        tmem_ld16(taddr + cc * 16, v[0]);
+        if (two) tmem_ld16(taddr + cc * 16 + 16, v[1]);
+        uint32_t rr[2][8];
         if (residual) {
-          const uint32_t ch = (uint32_t)((n0 >> 3) + 2 * cc);
-          const uint32_t ra = a_base + ch * (uint32_t)p.plane_bytes + center;
-          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                       : "=r"(res0.x), "=r"(res0.y), "=r"(res0.z), "=r"(res0.w)
-                       : "r"(ra));
-          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                       : "=r"(res1.x), "=r"(res1.y), "=r"(res1.z), "=r"(res1.w)
-                       : "r"(ra + (uint32_t)p.plane_bytes));
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h == 0 || two) {
+              const uint32_t ra = ra0 + (uint32_t)(2 * (cc + h)) * (uint32_t)p.plane_bytes;
+              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                           : "=r"(rr[h][0]), "=r"(rr[h][1]), "=r"(rr[h][2]), "=r"(rr[h][3])
+                           : "r"(ra));
+              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                           : "=r"(rr[h][4]), "=r"(rr[h][5]), "=r"(rr[h][6]), "=r"(rr[h][7])
+                           : "r"(ra + (uint32_t)p.plane_bytes));
+            }
+          }
         }
         tmem_ld_wait();
-        const uint32_t rr[8] = {res0.x, res0.y, res0.z, res0.w, res1.x, res1.y, res1.z, res1.w};
-        uint32_t o[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int n = cc * 16 + 2 * i;
-          const float2 rf = Pack2<T>::unpack(rr[i]);
-          float a0 = fmaf(__uint_as_float(v[2 * i]), ss[n], ss[p.n_cta + n]);
-          float a1 = fmaf(__uint_as_float(v[2 * i + 1]), ss[n + 1], ss[p.n_cta + n + 1]);
-          if (residual) {
-            a0 += rf.x;
-            a1 += rf.y;
+        for (int h = 0; h < 2; ++h) {
+          if (h == 0 || two) {
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int n = (cc + h) * 16 + 2 * i;
+              float a0 = fmaf(__uint_as_float(v[h][2 * i]), ss[n], ss[p.n_cta + n]);
+              float a1 = fmaf(__uint_as_float(v[h][2 * i + 1]), ss[n + 1], ss[p.n_cta + n + 1]);
+              if (residual) {
+                const float2 rf = Pack2<T>::unpack(rr[h][i]);
+                a0 += rf.x;
+                a1 += rf.y;
+              }
+              o[i] = Pack2<T>::pack(lrelu02(a0), lrelu02(a1));
+            }
+            uint4* dst = reinterpret_cast<uint4*>(stg + (size_t)lane * p.epi_pitch + (cc + h) * 32);
+            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
           }
-          o[i] = Pack2<T>::pack(lrelu02(a0), lrelu02(a1));
         }
-        uint4* dst = reinterpret_cast<uint4*>(stg + (size_t)lane * p.epi_pitch + cc * 32);
-        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
       }
       tc_fence_before();
       __syncwarp();
@@ -287,16 +323,13 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
         if (residual) mbar_arrive(bar_aempty + 8 * stage);
       }
       // transposed read-back: consecutive lanes write consecutive 16 B of a cell's channel vector
-      const int cpo = p.n_cta >> 3;       // 16-byte chunks per cell
-      const int tot = 32 * cpo;
       T* outp = reinterpret_cast<T*>(p.out);
-      for (int idx = lane; idx < tot; idx += 32) {
-        const int i = idx / cpo, c = idx - i * cpo;
-        const int rr2 = q * 32 + i;
-        const int y2 = tyi * kTileH + (rr2 >> 3), x2 = txi * kTileW + (rr2 & 7);
-        if (y2 < p.H && x2 < p.W) {
+      for (uint32_t idx = lane; idx < tot; idx += 32) {
+        const uint32_t i = __umulhi(idx, p.cpo_magic), c = idx - i * cpo;
+        const uint32_t ro = myrow[i];
+        if (ro != 0xFFFFFFFFu) {
           const uint4 val = *reinterpret_cast<const uint4*>(stg + (size_t)i * p.epi_pitch + c * 16);
-          *reinterpret_cast<uint4*>(outp + out_pixel_offset(p, b, y2, x2) + n0 + c * 8) = val;
+          *reinterpret_cast<uint4*>(outp + ro + c * 8) = val;
         }
       }
       __syncwarp();
@@ -405,7 +438,8 @@ int tapconv_plan(const TapConvLayer& L, TapConvParams* pp) {
   p.stage_bytes = align_up(p.cpp * (uint32_t)p.plane_bytes, 128);
   p.epi_pitch = (uint32_t)L.n_cta * 2u + 16u;
   const uint32_t epi_bytes = (L.epi_mode == EPI_LASTCONV) ? 0u : 128u * p.epi_pitch;
-  p.off_ss = kCtrlBytes;
+  p.off_ss = kCtrlBytes + kAtabBytes + kRowoffBytes;
+  p.cpo_magic = ceil_magic((uint32_t)L.n_cta / 8);
   p.off_w = align_up(p.off_ss + 2u * (uint32_t)L.n_cta * 4u, 128);
   p.off_a = align_up(p.off_w + p.w_bytes, 128);
   int stages = 0;

@@ -52,7 +52,7 @@ struct TapConvParams {
   uint32_t tmem_cols, acc_stride;
   uint32_t w_bytes;             // packed weight bytes of one split
   uint32_t off_ss, off_w, off_a, stage_bytes, off_epi, epi_pitch;
-  uint32_t cpp, cpp_magic, halow_magic;   // chunks per input pixel (cin/8) and exact-division magics
+  uint32_t cpp, cpp_magic, halow_magic, cpo_magic;   // chunks per input pixel (cin/8) and exact-division magics
   TapEntry taps[kMaxTaps];
 };
 

@@ -130,16 +130,13 @@ class Rife46Engine:
         return dict(stages=st.value, n_cta=nc.value, nsplit=ns.value, smem_bytes=sm.value, macs_per_cell=mc.value)
 
     def debug_state(self, batch):
-        """(flow [B,Hp,Wp,4], mask [B,Hp,Wp]) of the last internal pass, copied to torch CUDA tensors."""
-        fp, mp, hp, wp = C.c_void_p(), C.c_void_p(), C.c_int(), C.c_int()
-        check(self._L.vfi_rife46_debug_state(self._ctx, C.byref(fp), C.byref(mp), C.byref(hp), C.byref(wp)))
-        self.sync()
-        n = batch * hp.value * wp.value
+        """(flow [B,Hp,Wp,4], mask [B,Hp,Wp]) of the last internal pass as torch CUDA tensors."""
+        hp, wp = C.c_int(), C.c_int()
+        check(self._L.vfi_rife46_debug_state(self._ctx, None, None, batch, C.byref(hp), C.byref(wp)))
         flow = torch.empty((batch, hp.value, wp.value, 4), dtype=torch.float32, device=f"cuda:{self.device}")
         mask = torch.empty((batch, hp.value, wp.value), dtype=torch.float32, device=f"cuda:{self.device}")
-        cudart = torch.cuda.cudart()
-        cudart.cudaMemcpy(flow.data_ptr(), fp.value, n * 16, 3)
-        cudart.cudaMemcpy(mask.data_ptr(), mp.value, n * 4, 3)
+        check(self._L.vfi_rife46_debug_state(self._ctx, flow.data_ptr(), mask.data_ptr(), batch, C.byref(hp),
+                                             C.byref(wp)))
         return flow, mask
 
     def set_batch(self, b):

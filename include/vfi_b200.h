@@ -87,9 +87,9 @@ int vfi_warp_bilinear_border(vfi_ctx* ctx, const float* img, const float* flow, 
  * impl 0 = tcgen05 kernel, 1 = CUDA-core checker with the same packed weights. */
 int vfi_rife46_debug_layer(vfi_ctx* ctx, int block, int layer, const void* in, void* out, void* out_mask, int B, int H,
                            int W, int impl, void* stream);
-/* Device pointers to the full-resolution flow (float4 [B,Hp,Wp]) and mask (float [B,Hp,Wp]) of the LAST
- * internal pass, valid until the next forward. */
-int vfi_rife46_debug_state(vfi_ctx* ctx, const float** flow4, const float** mask, int* Hp, int* Wp);
+/* Copies the full-resolution flow (float4 [batch,Hp,Wp]) and mask (float [batch,Hp,Wp]) of the LAST internal
+ * pass into caller-provided DEVICE buffers (either may be NULL to only query Hp/Wp); synchronises. */
+int vfi_rife46_debug_state(vfi_ctx* ctx, float* flow4_out, float* mask_out, int batch, int* Hp, int* Wp);
 /* Static plan of a layer for (block, layer): shared-memory stages, CTA output channels, splits, smem bytes. */
 int vfi_rife46_layer_plan(vfi_ctx* ctx, int block, int layer, int* stages, int* n_cta, int* nsplit, int* smem_bytes,
                           int64_t* macs_per_cell);

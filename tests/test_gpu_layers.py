@@ -58,6 +58,8 @@ IMPLS = [pytest.param(1, id="ref"), pytest.param(0, id="tc")]  # CUDA-core check
 @pytest.mark.parametrize("block", [3, 2, 1, 0])
 @pytest.mark.parametrize("impl", IMPLS)
 def test_resconv(engines, block, dtype, impl):
+    if impl == 1 and dtype != "float16":
+        pytest.skip("CUDA-core checker: one dtype is enough")
     sd, e = engines
     eng, c, tdt = e[dtype], BLOCK_C[block], _tdt(dtype)
     g = torch.Generator().manual_seed(block)
@@ -75,6 +77,8 @@ def test_resconv(engines, block, dtype, impl):
 @pytest.mark.parametrize("impl", IMPLS)
 def test_conv0(engines, block, dtype, impl):
     """conv0.0 then conv0.1 (both stride 2) on space-to-depth inputs."""
+    if impl == 1 and dtype != "float16":
+        pytest.skip("CUDA-core checker: one dtype is enough")
     sd, e = engines
     eng, c, tdt = e[dtype], BLOCK_C[block], _tdt(dtype)
     cin = 7 if block == 0 else 12
@@ -104,6 +108,8 @@ def test_conv0(engines, block, dtype, impl):
 @pytest.mark.parametrize("impl", IMPLS)
 def test_lastconv(engines, block, dtype, impl):
     """ConvTranspose2d(c,24,4,2,1)+PixelShuffle(2) as one 3x3 tap conv producing 4x4 sub-pixel patches."""
+    if impl == 1 and dtype != "float16":
+        pytest.skip("CUDA-core checker: one dtype is enough")
     sd, e = engines
     eng, c, tdt = e[dtype], BLOCK_C[block], _tdt(dtype)
     g = torch.Generator().manual_seed(20 + block)

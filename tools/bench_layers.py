@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--dtype", default="float16")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--json", default="")
+    ap.add_argument("--only", default="", help="block:layer, e.g. 3:2")
     a = ap.parse_args()
     ge.load_package()
     from cfi_b200.engine import Rife46Engine
@@ -39,6 +40,8 @@ def main():
                  (2, (B, Hs // 4, Ws // 4, c), (B, Hs // 4, Ws // 4, c)),
                  (10, (B, Hs // 4, Ws // 4, c), None)]
         for layer, ishape, oshape in specs:
+            if a.only and a.only != f"{blk}:{layer}":
+                continue
             x = (0.1 * torch.randn(ishape, device="cuda")).to(tdt)
             if layer == 10:
                 out = torch.empty(B, Hs, Ws, 4, device="cuda")

@@ -3,7 +3,7 @@
 //   front       : [warp(img0), warp(img1), t, mask, flow] -> bilinear 1/s -> 16-channel block input, written
 //                 directly in the space-to-depth form the stride-2 conv0.0 reads
 //                                                                       rife_arch.py:31-70, :238-249, :589-596
-//   upflow      : bilinear x s of the block output, flow = up*s, flow += / mask +=   rife_arch.py:263-266, :694-696
+//   (flow)      : flow = sum_j up_sj(T_j)*s_j is evaluated on the fly from the blocks' low-res outputs   rife_arch.py:263-266, :694-696
 //   final       : warp both frames with the final flow, sigmoid blend, crop, clamp    rife_arch.py:703-704, :713-717, :732
 //   warp        : stand-alone backward bilinear warp (border, align_corners=True), NHWC fp32, any C
 #include "ptx.cuh"
@@ -54,20 +54,92 @@ __device__ __forceinline__ float4 sample_border(const float4* __restrict__ img, 
   return o;
 }
 
-// one thread = one cell of the 1/s grid; channels: w0.rgb, w1.rgb, t, mask, flow/s (4) [, 4 zero pad]
-template <typename T, bool kFirst>
-__global__ void front_kernel(const float4* __restrict__ imgs, const float4* __restrict__ flow,
-                             const float* __restrict__ mask, const BatchTasks tasks, int Hp, int Wp, int s,
-                             T* __restrict__ x_s2d) {
+// ---------------------------------------------------------------------------------------------
+// Implicit full-resolution flow.  The reference keeps flow/mask at full resolution and adds each block's
+// up-scaled output to it (rife_arch.py:263-266, :694-696).  Here the full-resolution planes are never stored:
+// each block leaves only its low-resolution output T_j (float4 flow + float mask at 1/s_j), and every consumer
+// evaluates   flow(p) = ((up(T_0)(p)*s_0 + up(T_1)(p)*s_1) + ...)   in the reference's order, so the fp32 result
+// is the same while ~0.4 GB of HBM traffic per interpolated 1080p frame disappears (T_0..T_2 stay L2 resident).
+// ---------------------------------------------------------------------------------------------
+struct FlowLevels {
+  const float4* f[4];  // [B, Hp/s, Wp/s] flow increments of blocks 0..3
+  const float* m[4];   // [B, Hp/s, Wp/s] mask increments
+  int s[4];
+  int n;               // number of valid levels
+};
+
+// F.interpolate(scale_factor=s, bilinear, align_corners=False) of level j at full-res position (Y, X)
+__device__ __forceinline__ void up_level(const FlowLevels& L, int j, int b, int Hp, int Wp, int Y, int X, float4& uf,
+                                         float& um) {
+  const int s = L.s[j];
+  const int Hs = Hp / s, Ws = Wp / s;
+  const float4* tf = L.f[j] + (size_t)b * Hs * Ws;
+  const float* tm = L.m[j] + (size_t)b * Hs * Ws;
+  if (s == 1) {
+    uf = __ldg(tf + (size_t)Y * Ws + X);
+    um = __ldg(tm + (size_t)Y * Ws + X);
+    return;
+  }
+  const float inv_s = 1.f / (float)s;
+  const float sy = fmaxf(((float)Y + 0.5f) * inv_s - 0.5f, 0.f);
+  const float sx = fmaxf(((float)X + 0.5f) * inv_s - 0.5f, 0.f);
+  const int y0 = min((int)sy, Hs - 1), x0 = min((int)sx, Ws - 1);
+  const int y1 = min(y0 + 1, Hs - 1), x1 = min(x0 + 1, Ws - 1);
+  const float ly = sy - (float)y0, lx = sx - (float)x0;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const float4 a = __ldg(tf + (size_t)y0 * Ws + x0);
+  const float4 bq = __ldg(tf + (size_t)y0 * Ws + x1);
+  const float4 c = __ldg(tf + (size_t)y1 * Ws + x0);
+  const float4 d = __ldg(tf + (size_t)y1 * Ws + x1);
+  const float ma = __ldg(tm + (size_t)y0 * Ws + x0);
+  const float mb = __ldg(tm + (size_t)y0 * Ws + x1);
+  const float mc = __ldg(tm + (size_t)y1 * Ws + x0);
+  const float md = __ldg(tm + (size_t)y1 * Ws + x1);
+  uf.x = hy * (hx * a.x + lx * bq.x) + ly * (hx * c.x + lx * d.x);
+  uf.y = hy * (hx * a.y + lx * bq.y) + ly * (hx * c.y + lx * d.y);
+  uf.z = hy * (hx * a.z + lx * bq.z) + ly * (hx * c.z + lx * d.z);
+  uf.w = hy * (hx * a.w + lx * bq.w) + ly * (hx * c.w + lx * d.w);
+  um = hy * (hx * ma + lx * mb) + ly * (hx * mc + lx * md);
+}
+
+// accumulated flow / mask at a full-resolution position, in the reference's summation order
+template <int NLEV>
+__device__ __forceinline__ void flow_at(const FlowLevels& L, int b, int Hp, int Wp, int Y, int X, float4& f,
+                                        float& m) {
+  float4 u;
+  float um;
+  up_level(L, 0, b, Hp, Wp, Y, X, u, um);
+  const float s0 = (float)L.s[0];
+  f = make_float4(u.x * s0, u.y * s0, u.z * s0, u.w * s0);
+  m = um;
+#pragma unroll
+  for (int j = 1; j < NLEV; ++j) {
+    up_level(L, j, b, Hp, Wp, Y, X, u, um);
+    const float sj = (float)L.s[j];
+    f.x += u.x * sj;
+    f.y += u.y * sj;
+    f.z += u.z * sj;
+    f.w += u.w * sj;
+    m += um;
+  }
+}
+
+// one thread = one cell of the 1/s grid; channels: w0.rgb, w1.rgb, t, mask, flow/s (4) [, 4 zero pad].
+// Thread order (b, row pair, x, row parity) so that 4 consecutive lanes fill one 128-byte space-to-depth cell.
+template <typename T, int NLEV>
+__global__ void front_kernel(const float4* __restrict__ imgs, const FlowLevels lev, const BatchTasks tasks, int Hp,
+                             int Wp, int s, T* __restrict__ x_s2d) {
   const int Hs = Hp / s, Ws = Wp / s;
   const size_t total = (size_t)tasks.n * Hs * Ws;
   const size_t plane = (size_t)Hp * Wp;
   const float inv_s = 1.f / (float)s;
   for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
-    const int xl = (int)(id % Ws);
-    const size_t r = id / Ws;
-    const int yl = (int)(r % Hs);
-    const int b = (int)(r / Hs);
+    const int par = (int)(id & 1);
+    size_t r = id >> 1;
+    const int xl = (int)(r % Ws);
+    r /= Ws;
+    const int yl = (int)(r % (Hs >> 1)) * 2 + par;
+    const int b = (int)(r / (Hs >> 1));
     const float4* img0 = imgs + (size_t)tasks.f0[b] * plane;
     const float4* img1 = imgs + (size_t)tasks.f1[b] * plane;
     const float t = tasks.t[b];
@@ -85,14 +157,15 @@ __global__ void front_kernel(const float4* __restrict__ imgs, const float4* __re
         if (ty < ntap && tx < ntap) {
           const int Y = by + ty, X = bx + tx;
           float* v = colv[tx];
-          if (kFirst) {
+          if (NLEV == 0) {
             const float4 a = __ldg(img0 + (size_t)Y * Wp + X);
             const float4 c = __ldg(img1 + (size_t)Y * Wp + X);
             v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = c.x; v[4] = c.y; v[5] = c.z;
             v[6] = t; v[7] = 0.f; v[8] = 0.f; v[9] = 0.f; v[10] = 0.f; v[11] = 0.f;
           } else {
-            const float4 f = __ldg(flow + (size_t)b * plane + (size_t)Y * Wp + X);
-            const float m = __ldg(mask + (size_t)b * plane + (size_t)Y * Wp + X);
+            float4 f;
+            float m;
+            flow_at<(NLEV > 0 ? NLEV : 1)>(lev, b, Hp, Wp, Y, X, f, m);
             const float4 a = sample_border(img0, Hp, Wp, (float)X + f.x, (float)Y + f.y);
             const float4 c = sample_border(img1, Hp, Wp, (float)X + f.z, (float)Y + f.w);
             v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = c.x; v[4] = c.y; v[5] = c.z;
@@ -125,55 +198,23 @@ __global__ void front_kernel(const float4* __restrict__ imgs, const float4* __re
   }
 }
 
-// flow/mask (full resolution, fp32) (+)= bilinear-upsampled block output
-__global__ void upflow_kernel(const float4* __restrict__ tflow, const float* __restrict__ tmask,
-                              float4* __restrict__ flow, float* __restrict__ mask, int B, int Hp, int Wp, int s,
-                              int first) {
-  const int Hs = Hp / s, Ws = Wp / s;
+// debug / tests only: materialise the accumulated full-resolution flow and mask
+__global__ void materialize_kernel(const FlowLevels lev, float4* __restrict__ flow, float* __restrict__ mask, int B,
+                                   int Hp, int Wp) {
   const size_t total = (size_t)B * Hp * Wp;
-  const float fs = (float)s, inv_s = 1.f / fs;
   for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
     const int x = (int)(id % Wp);
     const size_t r = id / Wp;
-    const int y = (int)(r % Hp);
-    const int b = (int)(r / Hp);
-    // F.interpolate(scale_factor=s, bilinear, align_corners=False): src = (dst + 0.5)/s - 0.5, clamped at 0
-    const float sy = fmaxf(((float)y + 0.5f) * inv_s - 0.5f, 0.f);
-    const float sx = fmaxf(((float)x + 0.5f) * inv_s - 0.5f, 0.f);
-    const int y0 = min((int)sy, Hs - 1), x0 = min((int)sx, Ws - 1);
-    const int y1 = min(y0 + 1, Hs - 1), x1 = min(x0 + 1, Ws - 1);
-    const float ly = sy - (float)y0, lx = sx - (float)x0;
-    const float hy = 1.f - ly, hx = 1.f - lx;
-    const size_t base = (size_t)b * Hs * Ws;
-    const float4 a = __ldg(tflow + base + (size_t)y0 * Ws + x0);
-    const float4 bq = __ldg(tflow + base + (size_t)y0 * Ws + x1);
-    const float4 c = __ldg(tflow + base + (size_t)y1 * Ws + x0);
-    const float4 d = __ldg(tflow + base + (size_t)y1 * Ws + x1);
-    const float ma = __ldg(tmask + base + (size_t)y0 * Ws + x0);
-    const float mb = __ldg(tmask + base + (size_t)y0 * Ws + x1);
-    const float mc = __ldg(tmask + base + (size_t)y1 * Ws + x0);
-    const float md = __ldg(tmask + base + (size_t)y1 * Ws + x1);
-    float4 u;
-    u.x = hy * (hx * a.x + lx * bq.x) + ly * (hx * c.x + lx * d.x);
-    u.y = hy * (hx * a.y + lx * bq.y) + ly * (hx * c.y + lx * d.y);
-    u.z = hy * (hx * a.z + lx * bq.z) + ly * (hx * c.z + lx * d.z);
-    u.w = hy * (hx * a.w + lx * bq.w) + ly * (hx * c.w + lx * d.w);
-    const float um = hy * (hx * ma + lx * mb) + ly * (hx * mc + lx * md);
-    float4 f = make_float4(u.x * fs, u.y * fs, u.z * fs, u.w * fs);
-    float m = um;
-    if (!first) {
-      const float4 f0 = flow[id];
-      f.x += f0.x; f.y += f0.y; f.z += f0.z; f.w += f0.w;
-      m += mask[id];
-    }
+    float4 f;
+    float m;
+    flow_at<4>(lev, (int)(r / Hp), Hp, Wp, (int)(r % Hp), x, f, m);
     flow[id] = f;
     mask[id] = m;
   }
 }
 
-__global__ void final_kernel(const float4* __restrict__ imgs, const float4* __restrict__ flow,
-                             const float* __restrict__ mask, const BatchTasks tasks, int Hp, int Wp, int H, int W,
-                             float* __restrict__ out) {
+__global__ void final_kernel(const float4* __restrict__ imgs, const FlowLevels lev, const BatchTasks tasks, int Hp,
+                             int Wp, int H, int W, float* __restrict__ out) {
   const size_t total = (size_t)tasks.n * H * W;
   const size_t plane = (size_t)Hp * Wp;
   for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
@@ -181,9 +222,9 @@ __global__ void final_kernel(const float4* __restrict__ imgs, const float4* __re
     const size_t r = id / W;
     const int y = (int)(r % H);
     const int b = (int)(r / H);
-    const size_t pid = (size_t)b * plane + (size_t)y * Wp + x;
-    const float4 f = __ldg(flow + pid);
-    const float m = __ldg(mask + pid);
+    float4 f;
+    float m;
+    flow_at<4>(lev, b, Hp, Wp, y, x, f, m);
     const float4 a = sample_border(imgs + (size_t)tasks.f0[b] * plane, Hp, Wp, (float)x + f.x, (float)y + f.y);
     const float4 c = sample_border(imgs + (size_t)tasks.f1[b] * plane, Hp, Wp, (float)x + f.z, (float)y + f.w);
     const float sg = 1.f / (1.f + expf(-m));
@@ -253,35 +294,51 @@ cudaError_t launch_prep_frames(const float* frames, int n, int H, int W, int cst
   return cudaGetLastError();
 }
 
-cudaError_t launch_front(int op_type, const float4* imgs, const float4* flow, const float* mask, BatchTasks tasks,
-                         int Hp, int Wp, int s, bool first, void* x_s2d, cudaStream_t st) {
+static FlowLevels make_levels(const FlowState& fs, int nlev) {
+  FlowLevels L{};
+  L.n = nlev;
+  for (int j = 0; j < 4; ++j) {
+    L.f[j] = fs.f[j];
+    L.m[j] = fs.m[j];
+    L.s[j] = fs.s[j];
+  }
+  return L;
+}
+
+template <typename T>
+static void launch_front_t(int nlev, int g, cudaStream_t st, const float4* imgs, const FlowLevels& L,
+                           const BatchTasks& tasks, int Hp, int Wp, int s, void* x) {
+  switch (nlev) {
+    case 0: front_kernel<T, 0><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, s, (T*)x); break;
+    case 1: front_kernel<T, 1><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, s, (T*)x); break;
+    case 2: front_kernel<T, 2><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, s, (T*)x); break;
+    default: front_kernel<T, 3><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, s, (T*)x); break;
+  }
+}
+
+cudaError_t launch_front(int op_type, const float4* imgs, const FlowState& fs, int nlev, BatchTasks tasks, int Hp,
+                         int Wp, int s, void* x_s2d, cudaStream_t st) {
   const size_t total = (size_t)tasks.n * (Hp / s) * (Wp / s);
   const int g = grid_for(total, 128);
-  if (op_type == OP_BF16) {
-    if (first)
-      front_kernel<__nv_bfloat16, true><<<g, 128, 0, st>>>(imgs, flow, mask, tasks, Hp, Wp, s, (__nv_bfloat16*)x_s2d);
-    else
-      front_kernel<__nv_bfloat16, false><<<g, 128, 0, st>>>(imgs, flow, mask, tasks, Hp, Wp, s, (__nv_bfloat16*)x_s2d);
-  } else {
-    if (first)
-      front_kernel<__half, true><<<g, 128, 0, st>>>(imgs, flow, mask, tasks, Hp, Wp, s, (__half*)x_s2d);
-    else
-      front_kernel<__half, false><<<g, 128, 0, st>>>(imgs, flow, mask, tasks, Hp, Wp, s, (__half*)x_s2d);
-  }
+  const FlowLevels L = make_levels(fs, nlev);
+  if (op_type == OP_BF16)
+    launch_front_t<__nv_bfloat16>(nlev, g, st, imgs, L, tasks, Hp, Wp, s, x_s2d);
+  else
+    launch_front_t<__half>(nlev, g, st, imgs, L, tasks, Hp, Wp, s, x_s2d);
   return cudaGetLastError();
 }
 
-cudaError_t launch_upflow(const float4* tmp_flow, const float* tmp_mask, float4* flow, float* mask, int B, int Hp,
-                          int Wp, int s, bool first, cudaStream_t st) {
+cudaError_t launch_materialize(const FlowState& fs, int nlev, float4* flow, float* mask, int B, int Hp, int Wp,
+                               cudaStream_t st) {
   const size_t total = (size_t)B * Hp * Wp;
-  upflow_kernel<<<grid_for(total, 256), 256, 0, st>>>(tmp_flow, tmp_mask, flow, mask, B, Hp, Wp, s, first ? 1 : 0);
+  materialize_kernel<<<grid_for(total, 256), 256, 0, st>>>(make_levels(fs, nlev), flow, mask, B, Hp, Wp);
   return cudaGetLastError();
 }
 
-cudaError_t launch_final(const float4* imgs, const float4* flow, const float* mask, BatchTasks tasks, int Hp, int Wp,
-                         int H, int W, float* out, cudaStream_t st) {
+cudaError_t launch_final(const float4* imgs, const FlowState& fs, BatchTasks tasks, int Hp, int Wp, int H, int W,
+                         float* out, cudaStream_t st) {
   const size_t total = (size_t)tasks.n * H * W;
-  final_kernel<<<grid_for(total, 256), 256, 0, st>>>(imgs, flow, mask, tasks, Hp, Wp, H, W, out);
+  final_kernel<<<grid_for(total, 256), 256, 0, st>>>(imgs, make_levels(fs, 4), tasks, Hp, Wp, H, W, out);
   return cudaGetLastError();
 }
 

@@ -9,7 +9,7 @@
 //     tapconv    -> feat   [B, Hs/4, Ws/4, c]     16-bit      conv0.1 (+lrelu)
 //     8x tapconv -> feat                                       ResConv               :20-28
 //     tapconv    -> tmp    [B, Hs, Ws] float4 + float          ConvT+PixelShuffle    :215-218
-//     upflow     -> flow, mask [B, Hp, Wp] fp32                x s, *s, += :263-266,:694-696
+//     (no full-res flow is stored: flow(p) = sum_j up(T_j)(p)*s_j is evaluated by front/final)  :263-266,:694-696
 //   final        -> out [B, H, W, 3] fp32                      warp, sigmoid blend, crop, clamp :703-717,:732
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
@@ -125,8 +125,9 @@ struct vfi_ctx {
   TapConvLayer layers[4][11];  // [block][0=conv0.0, 1=conv0.1, 2..9=ResConv, 10=lastconv]
   std::vector<void*> weight_allocs;
   // workspace
-  DevBuf imgs, flow, mask, x, c00, featA, featB, tmpF, tmpM, raw, outdev, dev_frames_tmp;
-  int ws_Hp = 0, ws_Wp = 0;
+  DevBuf imgs, flow, mask, x, c00, featA, featB, tF[4], tM[4], raw, outdev;
+  int ws_Hp = 0, ws_Wp = 0, ws_B = 0;
+  FlowState last_fs{};
   cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
 };
 
@@ -291,24 +292,21 @@ int make_geometry(int H, int W, float scale_factor, Geometry* g) {
 }
 
 int ensure_workspace(vfi_ctx* c, const Geometry& g, int B, int n_frames_window) {
-  size_t x = 0, c00 = 0, feat = 0, tmp = 0;
+  size_t x = 0, c00 = 0, feat = 0;
   for (int i = 0; i < 4; ++i) {
     const size_t Hs = g.Hp / g.s[i], Ws = g.Wp / g.s[i];
     x = std::max(x, (size_t)B * (Hs / 2) * (Ws / 2) * 64 * 2);
     c00 = std::max(c00, (size_t)B * (Hs / 4) * (Ws / 4) * 2 * kBlockC[i] * 2);
     feat = std::max(feat, (size_t)B * (Hs / 4) * (Ws / 4) * kBlockC[i] * 2);
-    tmp = std::max(tmp, (size_t)B * Hs * Ws);
+    CK(c->tF[i].ensure((size_t)B * Hs * Ws * sizeof(float4)));  // block output T_i (flow increments at 1/s_i)
+    CK(c->tM[i].ensure((size_t)B * Hs * Ws * sizeof(float)));
   }
   const size_t px = (size_t)g.Hp * g.Wp;
   CK(c->imgs.ensure((size_t)n_frames_window * px * sizeof(float4)));
-  CK(c->flow.ensure((size_t)B * px * sizeof(float4)));
-  CK(c->mask.ensure((size_t)B * px * sizeof(float)));
   CK(c->x.ensure(x));
   CK(c->c00.ensure(c00));
   CK(c->featA.ensure(feat));
   CK(c->featB.ensure(feat));
-  CK(c->tmpF.ensure(tmp * sizeof(float4)));
-  CK(c->tmpM.ensure(tmp * sizeof(float)));
   c->ws_Hp = g.Hp;
   c->ws_Wp = g.Wp;
   return VFI_OK;
@@ -328,13 +326,16 @@ int ensure_workspace(vfi_ctx* c, const Geometry& g, int B, int n_frames_window) 
 int forward_pass(vfi_ctx* c, const Geometry& g, const BatchTasks& tasks, int H, int W, float* out, cudaStream_t st) {
   const int B = tasks.n;
   const float4* imgs = (const float4*)c->imgs.p;
-  float4* flow = (float4*)c->flow.p;
-  float* mask = (float*)c->mask.p;
+  FlowState fs{};
+  for (int i = 0; i < 4; ++i) {
+    fs.f[i] = (float4*)c->tF[i].p;
+    fs.m[i] = (float*)c->tM[i].p;
+    fs.s[i] = g.s[i];
+  }
   for (int i = 0; i < 4; ++i) {
     const int s = g.s[i];
     const int Hs = g.Hp / s, Ws = g.Wp / s;
-    const bool first = (i == 0);
-    LAUNCH(launch_front(c->op_type, imgs, flow, mask, tasks, g.Hp, g.Wp, s, first, c->x.p, st));
+    LAUNCH(launch_front(c->op_type, imgs, fs, i, tasks, g.Hp, g.Wp, s, c->x.p, st));
     LAUNCH(launch_tapconv(c->layers[i][0], c->op_type, c->x.p, c->c00.p, nullptr, nullptr, B, Hs / 2, Ws / 2,
                           c->num_sms, false, st));
     LAUNCH(launch_tapconv(c->layers[i][1], c->op_type, c->c00.p, c->featA.p, nullptr, nullptr, B, Hs / 4, Ws / 4,
@@ -346,11 +347,12 @@ int forward_pass(vfi_ctx* c, const Geometry& g, const BatchTasks& tasks, int H, 
                             false, st));
       std::swap(a, b);
     }
-    LAUNCH(launch_tapconv(c->layers[i][10], c->op_type, a, nullptr, (float4*)c->tmpF.p, (float*)c->tmpM.p, B, Hs / 4,
-                          Ws / 4, c->num_sms, false, st));
-    LAUNCH(launch_upflow((const float4*)c->tmpF.p, (const float*)c->tmpM.p, flow, mask, B, g.Hp, g.Wp, s, first, st));
+    LAUNCH(launch_tapconv(c->layers[i][10], c->op_type, a, nullptr, fs.f[i], fs.m[i], B, Hs / 4, Ws / 4, c->num_sms,
+                          false, st));
   }
-  LAUNCH(launch_final(imgs, flow, mask, tasks, g.Hp, g.Wp, H, W, out, st));
+  LAUNCH(launch_final(imgs, fs, tasks, g.Hp, g.Wp, H, W, out, st));
+  c->last_fs = fs;
+  c->ws_B = B;
   return VFI_OK;
 }
 
@@ -394,9 +396,12 @@ int vfi_destroy(vfi_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   free_weights(c);
-  for (DevBuf* b : {&c->imgs, &c->flow, &c->mask, &c->x, &c->c00, &c->featA, &c->featB, &c->tmpF, &c->tmpM, &c->raw,
-                    &c->outdev, &c->dev_frames_tmp})
+  for (DevBuf* b : {&c->imgs, &c->flow, &c->mask, &c->x, &c->c00, &c->featA, &c->featB, &c->raw, &c->outdev})
     b->release();
+  for (int i = 0; i < 4; ++i) {
+    c->tF[i].release();
+    c->tM[i].release();
+  }
   if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
   if (c->s_comp) cudaStreamDestroy(c->s_comp);
   if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
@@ -608,15 +613,16 @@ int vfi_rife46_debug_state(vfi_ctx* c, float* flow4_out, float* mask_out, int ba
   CK(cudaDeviceSynchronize());
   *Hp = c->ws_Hp;
   *Wp = c->ws_Wp;
+  if (!flow4_out && !mask_out) return VFI_OK;
+  if (batch < 1 || batch > c->ws_B) return fail(VFI_E_INVALID, "batch larger than the last pass");
+  // the full-resolution flow is implicit on the product path; materialise it for the caller
   const size_t n = (size_t)batch * c->ws_Hp * c->ws_Wp;
-  if (flow4_out) {
-    if (n * sizeof(float4) > c->flow.cap) return fail(VFI_E_INVALID, "batch larger than the last pass");
-    CK(cudaMemcpy(flow4_out, c->flow.p, n * sizeof(float4), cudaMemcpyDeviceToDevice));
-  }
-  if (mask_out) {
-    if (n * sizeof(float) > c->mask.cap) return fail(VFI_E_INVALID, "batch larger than the last pass");
-    CK(cudaMemcpy(mask_out, c->mask.p, n * sizeof(float), cudaMemcpyDeviceToDevice));
-  }
+  CK(c->flow.ensure(n * sizeof(float4)));
+  CK(c->mask.ensure(n * sizeof(float)));
+  LAUNCH(launch_materialize(c->last_fs, 4, (float4*)c->flow.p, (float*)c->mask.p, batch, c->ws_Hp, c->ws_Wp, 0));
+  CK(cudaDeviceSynchronize());
+  if (flow4_out) CK(cudaMemcpy(flow4_out, c->flow.p, n * sizeof(float4), cudaMemcpyDeviceToDevice));
+  if (mask_out) CK(cudaMemcpy(mask_out, c->mask.p, n * sizeof(float), cudaMemcpyDeviceToDevice));
   return VFI_OK;
 }
 

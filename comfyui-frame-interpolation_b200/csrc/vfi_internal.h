@@ -88,12 +88,18 @@ int tapconv_plan(const TapConvLayer& L, TapConvParams* p_out);
 
 cudaError_t launch_prep_frames(const float* frames, int n, int H, int W, int cstride, float4* imgs, int Hp, int Wp,
                                cudaStream_t st);
-cudaError_t launch_front(int op_type, const float4* imgs, const float4* flow, const float* mask, BatchTasks tasks,
-                         int Hp, int Wp, int s, bool first, void* x_s2d, cudaStream_t st);
-cudaError_t launch_upflow(const float4* tmp_flow, const float* tmp_mask, float4* flow, float* mask, int B, int Hp,
-                          int Wp, int s, bool first, cudaStream_t st);
-cudaError_t launch_final(const float4* imgs, const float4* flow, const float* mask, BatchTasks tasks, int Hp, int Wp,
-                         int H, int W, float* out, cudaStream_t st);
+// low-resolution outputs of the blocks executed so far (the accumulated full-resolution flow is implicit)
+struct FlowState {
+  float4* f[4];
+  float* m[4];
+  int s[4];
+};
+cudaError_t launch_front(int op_type, const float4* imgs, const FlowState& fs, int nlev, BatchTasks tasks, int Hp,
+                         int Wp, int s, void* x_s2d, cudaStream_t st);
+cudaError_t launch_materialize(const FlowState& fs, int nlev, float4* flow, float* mask, int B, int Hp, int Wp,
+                               cudaStream_t st);
+cudaError_t launch_final(const float4* imgs, const FlowState& fs, BatchTasks tasks, int Hp, int Wp, int H, int W,
+                         float* out, cudaStream_t st);
 cudaError_t launch_warp(const float* img, const float* flow, float* out, int B, int H, int W, int C, cudaStream_t st);
 
 void set_error(const std::string& s);

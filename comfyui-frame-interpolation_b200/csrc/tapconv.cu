@@ -37,7 +37,7 @@ struct Ctrl {
   uint32_t tmem_base;
 };
 constexpr uint32_t kCtrlBytes = 256;
-constexpr uint32_t kAtabBytes = 512;   // up to 128 K=16 steps
+constexpr uint32_t kAtabBytes = 4096;  // descriptor table: stages x K=16 steps x {a_lo, b_lo} (<= 512 entries)
 constexpr uint32_t kRowoffBytes = 512; // 128 rows
 static_assert(sizeof(Ctrl) <= kCtrlBytes, "control block");
 
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
   const uint32_t bar_aempty = smem_base + offsetof(Ctrl, a_empty);
   const uint32_t bar_tfull = smem_base + offsetof(Ctrl, t_full);
   const uint32_t bar_tempty = smem_base + offsetof(Ctrl, t_empty);
-  uint32_t* rowoff = reinterpret_cast<uint32_t*>(smem + kCtrlBytes + kAtabBytes);  // [128] output element offsets
+  uint32_t* rowoff = reinterpret_cast<uint32_t*>(smem + kCtrlBytes);  // [128] output element offsets
 
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
@@ -84,6 +84,33 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
     }
     mbar_fence_init();
   }
+  // Descriptor table, built once: for every (stage, K=16 step) the low words of the A and B shared-memory
+  // descriptors.  The MMA issue loop is then "load 8 bytes, issue" (ncu r01: the issuing warp was the bottleneck
+  // when it computed descriptors on the fly - 1240 instructions per tile).
+  {
+    uint2* tab = reinterpret_cast<uint2*>(smem + kCtrlBytes + kRowoffBytes);
+    const uint32_t plane16 = (uint32_t)p.plane_bytes >> 4;
+    const uint32_t a_lo_c = plane16 << 16;
+    const uint32_t b_lo_c = (((uint32_t)p.n_cta * 16u) >> 4) << 16;
+    const uint32_t b_step = ((uint32_t)p.n_cta * 32u) >> 4;
+    const int K16 = p.ktotal16;
+    for (int id = threadIdx.x; id < S * K16; id += blockDim.x) {
+      const int st = id / K16;
+      int j = id - st * K16, e = 0;
+      const int jj = j;
+      while (j >= p.taps[e].nk16) {
+        j -= p.taps[e].nk16;
+        ++e;
+      }
+      const TapEntry te = p.taps[e];
+      const uint32_t a_off = (uint32_t)(te.chunk0 + 2 * j) * plane16 +
+                             (uint32_t)((te.dy - p.halo_y0) * p.halo_w + (te.dx - p.halo_x0));
+      uint2 d;
+      d.x = a_lo_c | (((smem_base + p.off_a + (uint32_t)st * p.stage_bytes) >> 4) + a_off);
+      d.y = b_lo_c | (((smem_base + p.off_w) >> 4) + (uint32_t)jj * b_step);
+      tab[id] = d;
+    }
+  }
   if (warp == 0) tmem_alloc(smem_base + offsetof(Ctrl, tmem_base), p.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -96,18 +123,14 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
 
   if (warp == 0) {
     // ======================================================= MMA issuer
-    // The whole warp runs the (warp-uniform) control flow so that descriptors stay in uniform registers; one
-    // elected lane issues tcgen05.mma / tcgen05.commit.
+    // The whole warp runs the (warp-uniform) control flow; one elected lane issues tcgen05.mma / tcgen05.commit.
     const uint32_t leader = elect_one_sync();
     mbar_wait(bar_w, 0, 1);
-    // descriptor words that never change: LBO | SBO | version (see umma_desc_nosw)
-    const uint32_t plane16 = (uint32_t)p.plane_bytes >> 4;
-    const uint32_t a_lo_c = plane16 << 16;
-    const uint32_t a_hi_c = (((uint32_t)p.halo_w * 16u) >> 4) | (1u << 14);
-    const uint32_t b_step = ((uint32_t)p.n_cta * 32u) >> 4;  // two 8-channel chunks per K=16 step
-    const uint32_t b_lo_c = (((uint32_t)p.n_cta * 16u) >> 4) << 16;
+    const uint32_t a_hi_c = (((uint32_t)p.halo_w * 16u) >> 4) | (1u << 14);  // SBO | version
     const uint32_t b_hi_c = (128u >> 4) | (1u << 14);
-    const uint32_t b_lo0 = b_lo_c | (w_smem >> 4);
+    const uint2* tab0 = reinterpret_cast<const uint2*>(smem + kCtrlBytes + kRowoffBytes);
+    const int K16 = p.ktotal16;
+    const uint32_t idesc = p.idesc;
     uint32_t k = 0;
     for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k) {
       const uint32_t stage = k % S, use = k / S, acc = k & 1, vuse = k >> 1;
@@ -115,19 +138,16 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
       mbar_wait(bar_afull + 8 * stage, use & 1, 3);
       fence_proxy_async();  // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
       tc_fence_after();
-      const uint32_t a_lo0 = a_lo_c | ((a_smem + stage * p.stage_bytes) >> 4);
       const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
-      uint32_t b_lo = b_lo0, accum = 0;
-      for (int e = 0; e < p.ntaps; ++e) {
-        const TapEntry te = p.taps[e];
-        uint32_t a_lo = a_lo0 + (uint32_t)te.chunk0 * plane16 +
-                        (uint32_t)((te.dy - p.halo_y0) * p.halo_w + (te.dx - p.halo_x0));
-        for (int i = 0; i < te.nk16; ++i) {
-          if (leader) umma_f16_split(d_tmem, a_lo, a_hi_c, b_lo, b_hi_c, p.idesc, accum);
-          accum = 1;
-          a_lo += 2u * plane16;
-          b_lo += b_step;
-        }
+      const uint2* tab = tab0 + stage * K16;
+      {
+        const uint2 d = tab[0];
+        if (leader) umma_f16_split(d_tmem, d.x, a_hi_c, d.y, b_hi_c, idesc, 0u);
+      }
+#pragma unroll 4
+      for (int j = 1; j < K16; ++j) {
+        const uint2 d = tab[j];
+        if (leader) umma_f16_split(d_tmem, d.x, a_hi_c, d.y, b_hi_c, idesc, 1u);
       }
       if (leader) {
         if (!residual) umma_commit(bar_aempty + 8 * stage);  // window free once the MMAs have read it
@@ -149,10 +169,14 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
     // thread -> fixed 8-channel chunk `ch`, pixels px0, px0+ppi, ... of the window (96 % cpp == 0 for every layer)
     const uint32_t cpp = p.cpp, ppi = kProducerThreads / cpp;
     const uint32_t ch = (uint32_t)ptid % cpp, px0 = (uint32_t)ptid / cpp;
-    const uint32_t hy0 = px0 / (uint32_t)p.halo_w, hx0 = px0 - hy0 * (uint32_t)p.halo_w;
+    const uint32_t halo_w = (uint32_t)p.halo_w;
+    const uint32_t hy0 = px0 / halo_w, hx0 = px0 - hy0 * halo_w;
     const uint32_t dst0 = ch * (uint32_t)p.plane_bytes + px0 * 16u;
     const uint32_t cin2 = (uint32_t)p.cin * 2u;
     const uint32_t row_bytes = (uint32_t)p.W * cin2;
+    const uint32_t step_src = ppi * cin2, step_dst = ppi * 16u;
+    const uint32_t wrap_adj = row_bytes - halo_w * cin2;  // next window row, back to its first column
+    const int n_it = ((int)p.halo_px - (int)px0 + (int)ppi - 1) / (int)ppi;
     const uint8_t* in = reinterpret_cast<const uint8_t*>(p.in);
     const size_t img_bytes = (size_t)p.H * row_bytes;
     uint32_t k = 0;
@@ -164,18 +188,39 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
       const int gy0 = tyi * kTileH + p.halo_y0, gx0 = txi * kTileW + p.halo_x0;
       const uint8_t* img = in + (size_t)b * img_bytes + ch * 16u;
       uint32_t dst = a_smem + stage * p.stage_bytes + dst0;
-      uint32_t hy = hy0, hx = hx0;
+      uint32_t hx = hx0;
+      const bool interior = gy0 >= 0 && gx0 >= 0 && gy0 + p.halo_h <= p.H && gx0 + p.halo_w <= p.W;
       mbar_wait(bar_aempty + 8 * stage, (use & 1) ^ 1, 4);
-      for (uint32_t px = px0; px < (uint32_t)p.halo_px; px += ppi) {
-        const int gy = gy0 + (int)hy, gx = gx0 + (int)hx;
-        const bool ok = ((unsigned)gy < (unsigned)p.H) && ((unsigned)gx < (unsigned)p.W);
-        const uint32_t off = ok ? (uint32_t)gy * row_bytes + (uint32_t)gx * cin2 : 0u;
-        cp_async16(dst, img + off, ok ? 16u : 0u);
-        dst += ppi * 16u;
-        hx += ppi;
-        while (hx >= (uint32_t)p.halo_w) {
-          hx -= (uint32_t)p.halo_w;
-          ++hy;
+      if (interior) {
+        // whole window inside the image: no per-pixel bounds logic, pointer walks the window row by row
+        const uint8_t* src = img + (size_t)(gy0 + (int)hy0) * row_bytes + (size_t)(gx0 + (int)hx0) * cin2;
+        for (int it = 0; it < n_it; ++it) {
+          cp_async16(dst, src, 16u);
+          dst += step_dst;
+          src += step_src;
+          hx += ppi;
+          if (hx >= halo_w) {
+            hx -= halo_w;
+            src += wrap_adj;
+            if (hx >= halo_w) {
+              hx -= halo_w;
+              src += wrap_adj;
+            }
+          }
+        }
+      } else {
+        uint32_t hy = hy0;
+        for (int it = 0; it < n_it; ++it) {
+          const int gy = gy0 + (int)hy, gx = gx0 + (int)hx;
+          const bool ok = ((unsigned)gy < (unsigned)p.H) && ((unsigned)gx < (unsigned)p.W);
+          const uint32_t off = ok ? (uint32_t)gy * row_bytes + (uint32_t)gx * cin2 : 0u;
+          cp_async16(dst, img + off, ok ? 16u : 0u);
+          dst += step_dst;
+          hx += ppi;
+          while (hx >= halo_w) {
+            hx -= halo_w;
+            ++hy;
+          }
         }
       }
       cp_async_arrive_noinc(bar_afull + 8 * stage);
@@ -184,10 +229,10 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
     // ======================================================= epilogue (warps 4..7 <-> TMEM lane quarters 0..3)
     const int q = warp - 4;
     const int etid = threadIdx.x - 128;
-    float* ss = reinterpret_cast<float*>(smem + p.off_ss);  // [0,n_cta) scale, [n_cta, 2 n_cta) shift
+    float* ss = reinterpret_cast<float*>(smem + p.off_ss);  // interleaved: ss[2n] = scale_n, ss[2n+1] = shift_n
     for (int i = etid; i < p.n_cta; i += 128) {
-      ss[i] = p.scale[split * p.n_cta + i];
-      ss[p.n_cta + i] = p.shift[split * p.n_cta + i];
+      ss[2 * i] = p.scale[split * p.n_cta + i];
+      ss[2 * i + 1] = p.shift[split * p.n_cta + i];
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
 
@@ -234,12 +279,12 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
               for (int x4 = 0; x4 < 4; ++x4) {
                 const int pos = y4 * 4 + x4;
                 float4 f;
-                f.x = __uint_as_float(v[0][pos]) + ss[80 + 0 * 16 + pos];
-                f.y = __uint_as_float(v[1][pos]) + ss[80 + 1 * 16 + pos];
-                f.z = __uint_as_float(v[2][pos]) + ss[80 + 2 * 16 + pos];
-                f.w = __uint_as_float(v[3][pos]) + ss[80 + 3 * 16 + pos];
+                f.x = __uint_as_float(v[0][pos]) + ss[2 * (0 * 16 + pos) + 1];
+                f.y = __uint_as_float(v[1][pos]) + ss[2 * (1 * 16 + pos) + 1];
+                f.z = __uint_as_float(v[2][pos]) + ss[2 * (2 * 16 + pos) + 1];
+                f.w = __uint_as_float(v[3][pos]) + ss[2 * (3 * 16 + pos) + 1];
                 p.out_flow[o + x4] = f;
-                p.out_mask[o + x4] = __uint_as_float(v[4][pos]) + ss[80 + 4 * 16 + pos];
+                p.out_mask[o + x4] = __uint_as_float(v[4][pos]) + ss[2 * (4 * 16 + pos) + 1];
               }
             }
           }
@@ -255,7 +300,7 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
 #pragma unroll
               for (int pos = 0; pos < 16; ++pos) {
                 const size_t o = ((size_t)b * Hs + (gy * 4 + (pos >> 2))) * Ws + gx * 4 + (pos & 3);
-                const float val = __uint_as_float(v[pos]) + ss[p.n_cta + cc * 16 + pos];
+                const float val = __uint_as_float(v[pos]) + ss[2 * (cc * 16 + pos) + 1];
                 if (c5 < 4)
                   reinterpret_cast<float*>(p.out_flow)[o * 4 + c5] = val;
                 else
@@ -301,14 +346,15 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int n = (cc + h) * 16 + 2 * i;
-              float a0 = fmaf(__uint_as_float(v[h][2 * i]), ss[n], ss[p.n_cta + n]);
-              float a1 = fmaf(__uint_as_float(v[h][2 * i + 1]), ss[n + 1], ss[p.n_cta + n + 1]);
+              const float4 sc = *reinterpret_cast<const float4*>(ss + 2 * n);  // scale_n, shift_n, scale_n+1, shift_n+1
+              float a0 = fmaf(__uint_as_float(v[h][2 * i]), sc.x, sc.y);
+              float a1 = fmaf(__uint_as_float(v[h][2 * i + 1]), sc.z, sc.w);
               if (residual) {
                 const float2 rf = Pack2<T>::unpack(rr[h][i]);
                 a0 += rf.x;
                 a1 += rf.y;
               }
-              o[i] = Pack2<T>::pack(lrelu02(a0), lrelu02(a1));
+              o[i] = Pack2<T>::pack(fmaxf(a0, 0.2f * a0), fmaxf(a1, 0.2f * a1));  // LeakyReLU(0.2)
             }
             uint4* dst = reinterpret_cast<uint4*>(stg + (size_t)lane * p.epi_pitch + (cc + h) * 32);
             dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -438,7 +484,7 @@ int tapconv_plan(const TapConvLayer& L, TapConvParams* pp) {
   p.stage_bytes = align_up(p.cpp * (uint32_t)p.plane_bytes, 128);
   p.epi_pitch = (uint32_t)L.n_cta * 2u + 16u;
   const uint32_t epi_bytes = (L.epi_mode == EPI_LASTCONV) ? 0u : 128u * p.epi_pitch;
-  p.off_ss = kCtrlBytes + kAtabBytes + kRowoffBytes;
+  p.off_ss = kCtrlBytes + kRowoffBytes + kAtabBytes;
   p.cpo_magic = ceil_magic((uint32_t)L.n_cta / 8);
   p.off_w = align_up(p.off_ss + 2u * (uint32_t)L.n_cta * 4u, 128);
   p.off_a = align_up(p.off_w + p.w_bytes, 128);
@@ -449,6 +495,8 @@ int tapconv_plan(const TapConvLayer& L, TapConvParams* pp) {
       break;
     }
   }
+  while (stages > 1 && stages * L.ktotal16 > (int)(kAtabBytes / 8)) --stages;  // descriptor table capacity
+  if (stages * L.ktotal16 > (int)(kAtabBytes / 8)) stages = 0;
   p.stages = stages;
   p.off_epi = p.off_a + (uint32_t)stages * p.stage_bytes;
   // accumulators: two buffers of n_cta fp32 columns, allocation is a power of two >= 32

@@ -8,4 +8,4 @@ TAILN=60 run bench_layers python tools/bench_layers.py --batch 4 --json gpurun_o
 run ncu_resconv ncu --set full --clock-control none --import-source on -k regex:tapconv_kernel -s 3 -c 2 -f -o gpurun_out/prof_resconv_b3 python tools/bench_layers.py --batch 4 --only 3:2 --iters 3
 run ncu_conv00 ncu --set full --clock-control none --import-source on -k regex:tapconv_kernel -s 3 -c 1 -f -o gpurun_out/prof_conv00_b3 python tools/bench_layers.py --batch 4 --only 3:0 --iters 2
 TAILN=3 run bench python bench.py --steps 2 --warmup 1
-run launches ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --frames 9 --steps 1 --warmup 1
+run launches ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --frames 9 --steps 1 --warmup 1 --no-cpu

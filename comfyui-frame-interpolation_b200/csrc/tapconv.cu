@@ -166,17 +166,20 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
         bulk_g2s(w_smem + off, wsrc + off, n, bar_w);
       }
     }
-    // thread -> fixed 8-channel chunk `ch`, pixels px0, px0+ppi, ... of the window (96 % cpp == 0 for every layer)
-    const uint32_t cpp = p.cpp, ppi = kProducerThreads / cpp;
-    const uint32_t ch = (uint32_t)ptid % cpp, px0 = (uint32_t)ptid / cpp;
+    // Work unit of one warp instruction = 8 consecutive window pixels x 4 consecutive 8-channel chunks:
+    //   lane = (chunk-in-unit << 3) | pixel-in-unit
+    // so every quarter-warp writes 128 contiguous bytes of ONE plane (conflict-free LDGSTS shared-memory write:
+    // ncu r01 showed 32 wavefronts per instruction - one per lane - when a quarter-warp scattered a pixel's eight
+    // chunks over eight planes), while the four quarter-warps together read whole 32-byte sectors of 8 pixels.
+    const uint32_t pwarp = (uint32_t)warp - 1u;        // 0..2
+    const uint32_t lp = (uint32_t)lane & 7u, lc = (uint32_t)lane >> 3;
+    const uint32_t cpp = p.cpp;
+    const uint32_t nchb = cpp >> 2;                    // chunk blocks of 4 (cin is a multiple of 32 ... or 16*2)
+    const uint32_t npxb = ((uint32_t)p.halo_px + 7u) >> 3;
+    const uint32_t nunits = npxb * nchb;
     const uint32_t halo_w = (uint32_t)p.halo_w;
-    const uint32_t hy0 = px0 / halo_w, hx0 = px0 - hy0 * halo_w;
-    const uint32_t dst0 = ch * (uint32_t)p.plane_bytes + px0 * 16u;
     const uint32_t cin2 = (uint32_t)p.cin * 2u;
     const uint32_t row_bytes = (uint32_t)p.W * cin2;
-    const uint32_t step_src = ppi * cin2, step_dst = ppi * 16u;
-    const uint32_t wrap_adj = row_bytes - halo_w * cin2;  // next window row, back to its first column
-    const int n_it = ((int)p.halo_px - (int)px0 + (int)ppi - 1) / (int)ppi;
     const uint8_t* in = reinterpret_cast<const uint8_t*>(p.in);
     const size_t img_bytes = (size_t)p.H * row_bytes;
     uint32_t k = 0;
@@ -186,42 +189,18 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
       const int rem = t - b * tiles_per_img;
       const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
       const int gy0 = tyi * kTileH + p.halo_y0, gx0 = txi * kTileW + p.halo_x0;
-      const uint8_t* img = in + (size_t)b * img_bytes + ch * 16u;
-      uint32_t dst = a_smem + stage * p.stage_bytes + dst0;
-      uint32_t hx = hx0;
-      const bool interior = gy0 >= 0 && gx0 >= 0 && gy0 + p.halo_h <= p.H && gx0 + p.halo_w <= p.W;
+      const uint8_t* img = in + (size_t)b * img_bytes;
+      const uint32_t dst_base = a_smem + stage * p.stage_bytes;
       mbar_wait(bar_aempty + 8 * stage, (use & 1) ^ 1, 4);
-      if (interior) {
-        // whole window inside the image: no per-pixel bounds logic, pointer walks the window row by row
-        const uint8_t* src = img + (size_t)(gy0 + (int)hy0) * row_bytes + (size_t)(gx0 + (int)hx0) * cin2;
-        for (int it = 0; it < n_it; ++it) {
-          cp_async16(dst, src, 16u);
-          dst += step_dst;
-          src += step_src;
-          hx += ppi;
-          if (hx >= halo_w) {
-            hx -= halo_w;
-            src += wrap_adj;
-            if (hx >= halo_w) {
-              hx -= halo_w;
-              src += wrap_adj;
-            }
-          }
-        }
-      } else {
-        uint32_t hy = hy0;
-        for (int it = 0; it < n_it; ++it) {
-          const int gy = gy0 + (int)hy, gx = gx0 + (int)hx;
-          const bool ok = ((unsigned)gy < (unsigned)p.H) && ((unsigned)gx < (unsigned)p.W);
-          const uint32_t off = ok ? (uint32_t)gy * row_bytes + (uint32_t)gx * cin2 : 0u;
-          cp_async16(dst, img + off, ok ? 16u : 0u);
-          dst += step_dst;
-          hx += ppi;
-          while (hx >= halo_w) {
-            hx -= halo_w;
-            ++hy;
-          }
-        }
+      for (uint32_t u = pwarp; u < nunits; u += 3u) {
+        const uint32_t pb = u / nchb, cb = u - pb * nchb;  // chunk block fastest: neighbouring units share pixels
+        const uint32_t px = pb * 8u + lp, ch = cb * 4u + lc;
+        const uint32_t hy = __umulhi(px, p.halow_magic), hx = px - hy * halo_w;
+        const int gy = gy0 + (int)hy, gx = gx0 + (int)hx;
+        const bool ok = (px < (uint32_t)p.halo_px) && ((unsigned)gy < (unsigned)p.H) && ((unsigned)gx < (unsigned)p.W);
+        const uint32_t off = ok ? (uint32_t)gy * row_bytes + (uint32_t)gx * cin2 + ch * 16u : 0u;
+        if (px < (uint32_t)p.halo_px)
+          cp_async16(dst_base + ch * (uint32_t)p.plane_bytes + px * 16u, img + off, ok ? 16u : 0u);
       }
       cp_async_arrive_noinc(bar_afull + 8 * stage);
     }

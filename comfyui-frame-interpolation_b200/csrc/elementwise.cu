@@ -55,17 +55,24 @@ __device__ __forceinline__ float4 sample_border(const float4* __restrict__ img, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Implicit full-resolution flow.  The reference keeps flow/mask at full resolution and adds each block's
-// up-scaled output to it (rife_arch.py:263-266, :694-696).  Here the full-resolution planes are never stored:
-// each block leaves only its low-resolution output T_j (float4 flow + float mask at 1/s_j), and every consumer
-// evaluates   flow(p) = ((up(T_0)(p)*s_0 + up(T_1)(p)*s_1) + ...)   in the reference's order, so the fp32 result
-// is the same while ~0.4 GB of HBM traffic per interpolated 1080p frame disappears (T_0..T_2 stay L2 resident).
+// Flow state.  The reference keeps flow/mask at full resolution and adds each block's up-scaled output to it
+// (rife_arch.py:263-266, :694-696).  Here each block leaves only its low-resolution output T_j (float4 flow +
+// float mask at 1/s_j) and the consumers evaluate
+//      flow(p) = base(p) + sum_j up(T_j)(p) * s_j          (same fp32 summation order as the reference)
+// where `base` is a full-resolution plane that is written only by a front kernel that visits every pixel anyway
+// (s <= 2), never by a separate pass: with scales 8,4,2,1  block 1 reads {T0}, block 2 reads {T0,T1} and stores
+// F1, block 3 reads F1+{T2} and stores F2, the final blend reads F2+{T3}.  (ncu r01: a fully implicit variant was
+// instruction bound - 24 extra loads per pixel in block 3 - and a separate up-sample/accumulate pass per block
+// moved 2x the bytes.)
 // ---------------------------------------------------------------------------------------------
 struct FlowLevels {
-  const float4* f[4];  // [B, Hp/s, Wp/s] flow increments of blocks 0..3
-  const float* m[4];   // [B, Hp/s, Wp/s] mask increments
+  const float4* f[4];  // levels to add, in order: [B, Hp/s, Wp/s] flow increments
+  const float* m[4];   //                          [B, Hp/s, Wp/s] mask increments
   int s[4];
-  int n;               // number of valid levels
+  const float4* base_f;  // optional full-resolution accumulated flow [B, Hp, Wp] (nullptr: start from zero)
+  const float* base_m;
+  float4* out_f;         // optional: store the accumulated flow / mask at every visited position
+  float* out_m;
 };
 
 // F.interpolate(scale_factor=s, bilinear, align_corners=False) of level j at full-res position (Y, X)
@@ -106,14 +113,21 @@ __device__ __forceinline__ void up_level(const FlowLevels& L, int j, int b, int 
 template <int NLEV>
 __device__ __forceinline__ void flow_at(const FlowLevels& L, int b, int Hp, int Wp, int Y, int X, float4& f,
                                         float& m) {
+  const size_t pid = ((size_t)b * Hp + Y) * Wp + X;
   float4 u;
   float um;
-  up_level(L, 0, b, Hp, Wp, Y, X, u, um);
-  const float s0 = (float)L.s[0];
-  f = make_float4(u.x * s0, u.y * s0, u.z * s0, u.w * s0);
-  m = um;
+  if (L.base_f != nullptr) {
+    f = L.base_f[pid];  // plain loads: the same thread may store the updated value to this address below
+    m = L.base_m[pid];
+  } else {
+    up_level(L, 0, b, Hp, Wp, Y, X, u, um);
+    const float s0 = (float)L.s[0];
+    f = make_float4(u.x * s0, u.y * s0, u.z * s0, u.w * s0);
+    m = um;
+  }
 #pragma unroll
-  for (int j = 1; j < NLEV; ++j) {
+  for (int j = 0; j < NLEV; ++j) {
+    if (j == 0 && L.base_f == nullptr) continue;
     up_level(L, j, b, Hp, Wp, Y, X, u, um);
     const float sj = (float)L.s[j];
     f.x += u.x * sj;
@@ -121,6 +135,10 @@ __device__ __forceinline__ void flow_at(const FlowLevels& L, int b, int Hp, int 
     f.z += u.z * sj;
     f.w += u.w * sj;
     m += um;
+  }
+  if (L.out_f != nullptr) {
+    L.out_f[pid] = f;
+    L.out_m[pid] = m;
   }
 }
 
@@ -199,6 +217,7 @@ __global__ void front_kernel(const float4* __restrict__ imgs, const FlowLevels l
 }
 
 // debug / tests only: materialise the accumulated full-resolution flow and mask
+template <int NLEV>
 __global__ void materialize_kernel(const FlowLevels lev, float4* __restrict__ flow, float* __restrict__ mask, int B,
                                    int Hp, int Wp) {
   const size_t total = (size_t)B * Hp * Wp;
@@ -207,12 +226,13 @@ __global__ void materialize_kernel(const FlowLevels lev, float4* __restrict__ fl
     const size_t r = id / Wp;
     float4 f;
     float m;
-    flow_at<4>(lev, (int)(r / Hp), Hp, Wp, (int)(r % Hp), x, f, m);
+    flow_at<NLEV>(lev, (int)(r / Hp), Hp, Wp, (int)(r % Hp), x, f, m);
     flow[id] = f;
     mask[id] = m;
   }
 }
 
+template <int NLEV>
 __global__ void final_kernel(const float4* __restrict__ imgs, const FlowLevels lev, const BatchTasks tasks, int Hp,
                              int Wp, int H, int W, float* __restrict__ out) {
   const size_t total = (size_t)tasks.n * H * W;
@@ -224,7 +244,7 @@ __global__ void final_kernel(const float4* __restrict__ imgs, const FlowLevels l
     const int b = (int)(r / H);
     float4 f;
     float m;
-    flow_at<4>(lev, b, Hp, Wp, y, x, f, m);
+    flow_at<NLEV>(lev, b, Hp, Wp, y, x, f, m);
     const float4 a = sample_border(imgs + (size_t)tasks.f0[b] * plane, Hp, Wp, (float)x + f.x, (float)y + f.y);
     const float4 c = sample_border(imgs + (size_t)tasks.f1[b] * plane, Hp, Wp, (float)x + f.z, (float)y + f.w);
     const float sg = 1.f / (1.f + expf(-m));
@@ -294,14 +314,19 @@ cudaError_t launch_prep_frames(const float* frames, int n, int H, int W, int cst
   return cudaGetLastError();
 }
 
-static FlowLevels make_levels(const FlowState& fs, int nlev) {
+// levels [lo, hi) of the state (+ optional base / store planes) as a kernel argument
+static FlowLevels make_levels(const FlowState& fs, int lo, int hi, const float4* base_f, const float* base_m,
+                              float4* out_f, float* out_m) {
   FlowLevels L{};
-  L.n = nlev;
-  for (int j = 0; j < 4; ++j) {
-    L.f[j] = fs.f[j];
-    L.m[j] = fs.m[j];
-    L.s[j] = fs.s[j];
+  for (int j = lo; j < hi; ++j) {
+    L.f[j - lo] = fs.f[j];
+    L.m[j - lo] = fs.m[j];
+    L.s[j - lo] = fs.s[j];
   }
+  L.base_f = base_f;
+  L.base_m = base_m;
+  L.out_f = out_f;
+  L.out_m = out_m;
   return L;
 }
 
@@ -316,29 +341,48 @@ static void launch_front_t(int nlev, int g, cudaStream_t st, const float4* imgs,
   }
 }
 
-cudaError_t launch_front(int op_type, const float4* imgs, const FlowState& fs, int nlev, BatchTasks tasks, int Hp,
-                         int Wp, int s, void* x_s2d, cudaStream_t st) {
+// block `blk` input: flow = base (if any) + levels [lo, blk); stores the accumulated flow when `store` planes given
+cudaError_t launch_front(int op_type, const float4* imgs, const FlowState& fs, int blk, int lo, const float4* base_f,
+                         const float* base_m, float4* out_f, float* out_m, BatchTasks tasks, int Hp, int Wp, int s,
+                         void* x_s2d, cudaStream_t st) {
   const size_t total = (size_t)tasks.n * (Hp / s) * (Wp / s);
   const int g = grid_for(total, 128);
-  const FlowLevels L = make_levels(fs, nlev);
+  const FlowLevels L = make_levels(fs, lo, blk, base_f, base_m, out_f, out_m);
+  const int nlev = (blk == 0) ? 0 : (blk - lo);
+  if (blk > 0 && nlev == 0 && base_f == nullptr) return cudaErrorInvalidValue;
   if (op_type == OP_BF16)
-    launch_front_t<__nv_bfloat16>(nlev, g, st, imgs, L, tasks, Hp, Wp, s, x_s2d);
+    launch_front_t<__nv_bfloat16>(blk == 0 ? 0 : (nlev == 0 ? 1 : nlev), g, st, imgs, L, tasks, Hp, Wp, s, x_s2d);
   else
-    launch_front_t<__half>(nlev, g, st, imgs, L, tasks, Hp, Wp, s, x_s2d);
+    launch_front_t<__half>(blk == 0 ? 0 : (nlev == 0 ? 1 : nlev), g, st, imgs, L, tasks, Hp, Wp, s, x_s2d);
   return cudaGetLastError();
 }
 
-cudaError_t launch_materialize(const FlowState& fs, int nlev, float4* flow, float* mask, int B, int Hp, int Wp,
-                               cudaStream_t st) {
+cudaError_t launch_materialize(const FlowState& fs, int lo, const float4* base_f, const float* base_m, float4* flow,
+                               float* mask, int B, int Hp, int Wp, cudaStream_t st) {
   const size_t total = (size_t)B * Hp * Wp;
-  materialize_kernel<<<grid_for(total, 256), 256, 0, st>>>(make_levels(fs, nlev), flow, mask, B, Hp, Wp);
+  FlowLevels L = make_levels(fs, lo, 4, base_f, base_m, nullptr, nullptr);
+  // pad unused levels with a zero-weight copy of the last one is not needed: materialize_kernel is NLEV=4-lo generic
+  const int nlev = 4 - lo;
+  switch (nlev) {
+    case 1: materialize_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(L, flow, mask, B, Hp, Wp); break;
+    case 2: materialize_kernel<2><<<grid_for(total, 256), 256, 0, st>>>(L, flow, mask, B, Hp, Wp); break;
+    case 3: materialize_kernel<3><<<grid_for(total, 256), 256, 0, st>>>(L, flow, mask, B, Hp, Wp); break;
+    default: materialize_kernel<4><<<grid_for(total, 256), 256, 0, st>>>(L, flow, mask, B, Hp, Wp); break;
+  }
   return cudaGetLastError();
 }
 
-cudaError_t launch_final(const float4* imgs, const FlowState& fs, BatchTasks tasks, int Hp, int Wp, int H, int W,
-                         float* out, cudaStream_t st) {
+cudaError_t launch_final(const float4* imgs, const FlowState& fs, int lo, const float4* base_f, const float* base_m,
+                         BatchTasks tasks, int Hp, int Wp, int H, int W, float* out, cudaStream_t st) {
   const size_t total = (size_t)tasks.n * H * W;
-  final_kernel<<<grid_for(total, 256), 256, 0, st>>>(imgs, make_levels(fs, 4), tasks, Hp, Wp, H, W, out);
+  const FlowLevels L = make_levels(fs, lo, 4, base_f, base_m, nullptr, nullptr);
+  const int g = grid_for(total, 256);
+  switch (4 - lo) {
+    case 1: final_kernel<1><<<g, 256, 0, st>>>(imgs, L, tasks, Hp, Wp, H, W, out); break;
+    case 2: final_kernel<2><<<g, 256, 0, st>>>(imgs, L, tasks, Hp, Wp, H, W, out); break;
+    case 3: final_kernel<3><<<g, 256, 0, st>>>(imgs, L, tasks, Hp, Wp, H, W, out); break;
+    default: final_kernel<4><<<g, 256, 0, st>>>(imgs, L, tasks, Hp, Wp, H, W, out); break;
+  }
   return cudaGetLastError();
 }
 

@@ -9,7 +9,7 @@
 //     tapconv    -> feat   [B, Hs/4, Ws/4, c]     16-bit      conv0.1 (+lrelu)
 //     8x tapconv -> feat                                       ResConv               :20-28
 //     tapconv    -> tmp    [B, Hs, Ws] float4 + float          ConvT+PixelShuffle    :215-218
-//     (no full-res flow is stored: flow(p) = sum_j up(T_j)(p)*s_j is evaluated by front/final)  :263-266,:694-696
+//     (flow(p) = F(p) + sum_j up(T_j)(p)*s_j: F is stored only by fronts that visit every pixel)  :263-266,:694-696
 //   final        -> out [B, H, W, 3] fp32                      warp, sigmoid blend, crop, clamp :703-717,:732
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
@@ -128,6 +128,9 @@ struct vfi_ctx {
   DevBuf imgs, flow, mask, x, c00, featA, featB, tF[4], tM[4], raw, outdev;
   int ws_Hp = 0, ws_Wp = 0, ws_B = 0;
   FlowState last_fs{};
+  int last_lo = 0;
+  bool last_have_base = false;
+  DevBuf dbgF, dbgM;
   cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
 };
 
@@ -303,6 +306,8 @@ int ensure_workspace(vfi_ctx* c, const Geometry& g, int B, int n_frames_window) 
   }
   const size_t px = (size_t)g.Hp * g.Wp;
   CK(c->imgs.ensure((size_t)n_frames_window * px * sizeof(float4)));
+  CK(c->flow.ensure((size_t)B * px * sizeof(float4)));
+  CK(c->mask.ensure((size_t)B * px * sizeof(float)));
   CK(c->x.ensure(x));
   CK(c->c00.ensure(c00));
   CK(c->featA.ensure(feat));
@@ -326,16 +331,30 @@ int ensure_workspace(vfi_ctx* c, const Geometry& g, int B, int n_frames_window) 
 int forward_pass(vfi_ctx* c, const Geometry& g, const BatchTasks& tasks, int H, int W, float* out, cudaStream_t st) {
   const int B = tasks.n;
   const float4* imgs = (const float4*)c->imgs.p;
+  float4* F = (float4*)c->flow.p;  // accumulated full-resolution flow / mask, written only by "dense" fronts
+  float* M = (float*)c->mask.p;
   FlowState fs{};
   for (int i = 0; i < 4; ++i) {
     fs.f[i] = (float4*)c->tF[i].p;
     fs.m[i] = (float*)c->tM[i].p;
     fs.s[i] = g.s[i];
   }
+  int dense = 4;  // first block whose front visits every full-resolution pixel (scale <= 2)
+  for (int i = 3; i >= 1; --i)
+    if (g.s[i] <= 2) dense = i;
+  bool have_base = false;
+  int lo = 0;  // levels [lo, i) are not yet folded into F
   for (int i = 0; i < 4; ++i) {
     const int s = g.s[i];
     const int Hs = g.Hp / s, Ws = g.Wp / s;
-    LAUNCH(launch_front(c->op_type, imgs, fs, i, tasks, g.Hp, g.Wp, s, c->x.p, st));
+    if (i == 0 || i < dense) {
+      LAUNCH(launch_front(c->op_type, imgs, fs, i, 0, nullptr, nullptr, nullptr, nullptr, tasks, g.Hp, g.Wp, s, c->x.p, st));
+    } else {
+      LAUNCH(launch_front(c->op_type, imgs, fs, i, lo, have_base ? F : nullptr, have_base ? M : nullptr, F, M, tasks,
+                          g.Hp, g.Wp, s, c->x.p, st));
+      have_base = true;
+      lo = i;
+    }
     LAUNCH(launch_tapconv(c->layers[i][0], c->op_type, c->x.p, c->c00.p, nullptr, nullptr, B, Hs / 2, Ws / 2,
                           c->num_sms, false, st));
     LAUNCH(launch_tapconv(c->layers[i][1], c->op_type, c->c00.p, c->featA.p, nullptr, nullptr, B, Hs / 4, Ws / 4,
@@ -350,8 +369,10 @@ int forward_pass(vfi_ctx* c, const Geometry& g, const BatchTasks& tasks, int H, 
     LAUNCH(launch_tapconv(c->layers[i][10], c->op_type, a, nullptr, fs.f[i], fs.m[i], B, Hs / 4, Ws / 4, c->num_sms,
                           false, st));
   }
-  LAUNCH(launch_final(imgs, fs, tasks, g.Hp, g.Wp, H, W, out, st));
+  LAUNCH(launch_final(imgs, fs, lo, have_base ? F : nullptr, have_base ? M : nullptr, tasks, g.Hp, g.Wp, H, W, out, st));
   c->last_fs = fs;
+  c->last_lo = lo;
+  c->last_have_base = have_base;
   c->ws_B = B;
   return VFI_OK;
 }
@@ -396,7 +417,8 @@ int vfi_destroy(vfi_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   free_weights(c);
-  for (DevBuf* b : {&c->imgs, &c->flow, &c->mask, &c->x, &c->c00, &c->featA, &c->featB, &c->raw, &c->outdev})
+  for (DevBuf* b : {&c->imgs, &c->flow, &c->mask, &c->x, &c->c00, &c->featA, &c->featB, &c->raw, &c->outdev, &c->dbgF,
+                    &c->dbgM})
     b->release();
   for (int i = 0; i < 4; ++i) {
     c->tF[i].release();
@@ -617,12 +639,14 @@ int vfi_rife46_debug_state(vfi_ctx* c, float* flow4_out, float* mask_out, int ba
   if (batch < 1 || batch > c->ws_B) return fail(VFI_E_INVALID, "batch larger than the last pass");
   // the full-resolution flow is implicit on the product path; materialise it for the caller
   const size_t n = (size_t)batch * c->ws_Hp * c->ws_Wp;
-  CK(c->flow.ensure(n * sizeof(float4)));
-  CK(c->mask.ensure(n * sizeof(float)));
-  LAUNCH(launch_materialize(c->last_fs, 4, (float4*)c->flow.p, (float*)c->mask.p, batch, c->ws_Hp, c->ws_Wp, 0));
+  CK(c->dbgF.ensure(n * sizeof(float4)));
+  CK(c->dbgM.ensure(n * sizeof(float)));
+  LAUNCH(launch_materialize(c->last_fs, c->last_lo, c->last_have_base ? (const float4*)c->flow.p : nullptr,
+                            c->last_have_base ? (const float*)c->mask.p : nullptr, (float4*)c->dbgF.p,
+                            (float*)c->dbgM.p, batch, c->ws_Hp, c->ws_Wp, 0));
   CK(cudaDeviceSynchronize());
-  if (flow4_out) CK(cudaMemcpy(flow4_out, c->flow.p, n * sizeof(float4), cudaMemcpyDeviceToDevice));
-  if (mask_out) CK(cudaMemcpy(mask_out, c->mask.p, n * sizeof(float), cudaMemcpyDeviceToDevice));
+  if (flow4_out) CK(cudaMemcpy(flow4_out, c->dbgF.p, n * sizeof(float4), cudaMemcpyDeviceToDevice));
+  if (mask_out) CK(cudaMemcpy(mask_out, c->dbgM.p, n * sizeof(float), cudaMemcpyDeviceToDevice));
   return VFI_OK;
 }
 
@@ -636,7 +660,7 @@ int vfi_rife46_layer_plan(vfi_ctx* c, int block, int layer, int* stages, int* n_
   if (stages) *stages = st;
   if (n_cta) *n_cta = L.n_cta;
   if (nsplit) *nsplit = L.nsplit;
-  if (smem_bytes) *smem_bytes = (int)(p.off_epi + (L.epi_mode == EPI_LASTCONV ? 0u : 128u * p.epi_pitch));
+  if (smem_bytes) *smem_bytes = (int)p.off_epi;
   if (macs_per_cell) *macs_per_cell = (int64_t)L.ktotal16 * 16 * L.n_total;
   return VFI_OK;
 }

@@ -70,7 +70,6 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
   const uint32_t bar_aempty = smem_base + offsetof(Ctrl, a_empty);
   const uint32_t bar_tfull = smem_base + offsetof(Ctrl, t_full);
   const uint32_t bar_tempty = smem_base + offsetof(Ctrl, t_empty);
-  uint32_t* rowoff = reinterpret_cast<uint32_t*>(smem + kCtrlBytes);  // [128] output element offsets
 
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
@@ -140,14 +139,25 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
       const uint2* tab = tab0 + stage * K16;
-      {
-        const uint2 d = tab[0];
-        if (leader) umma_f16_split(d_tmem, d.x, a_hi_c, d.y, b_hi_c, idesc, 0u);
-      }
-#pragma unroll 4
-      for (int j = 1; j < K16; ++j) {
-        const uint2 d = tab[j];
-        if (leader) umma_f16_split(d_tmem, d.x, a_hi_c, d.y, b_hi_c, idesc, 1u);
+      // K16 is a multiple of 9 for every layer (9 taps x c/16 or 9 x c/32): issue in groups of nine, the next
+      // group's descriptors are fetched into registers before the current group is issued, so the shared-memory
+      // latency never sits between two MMAs (ncu r01 v2: the issuing warp spent ~140 cycles per MMA).
+      uint2 cur[9], nxt[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) cur[i] = tab[i];
+      const int ngroups = K16 / 9;
+      for (int g = 0; g < ngroups; ++g) {
+        if (g + 1 < ngroups) {
+#pragma unroll
+          for (int i = 0; i < 9; ++i) nxt[i] = tab[(g + 1) * 9 + i];
+        }
+        if (leader) {
+          umma_f16_split(d_tmem, cur[0].x, a_hi_c, cur[0].y, b_hi_c, idesc, g > 0 ? 1u : 0u);
+#pragma unroll
+          for (int i = 1; i < 9; ++i) umma_f16_split(d_tmem, cur[i].x, a_hi_c, cur[i].y, b_hi_c, idesc, 1u);
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) cur[i] = nxt[i];
       }
       if (leader) {
         if (!residual) umma_commit(bar_aempty + 8 * stage);  // window free once the MMAs have read it
@@ -166,20 +176,17 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
         bulk_g2s(w_smem + off, wsrc + off, n, bar_w);
       }
     }
-    // Work unit of one warp instruction = 8 consecutive window pixels x 4 consecutive 8-channel chunks:
-    //   lane = (chunk-in-unit << 3) | pixel-in-unit
-    // so every quarter-warp writes 128 contiguous bytes of ONE plane (conflict-free LDGSTS shared-memory write:
-    // ncu r01 showed 32 wavefronts per instruction - one per lane - when a quarter-warp scattered a pixel's eight
-    // chunks over eight planes), while the four quarter-warps together read whole 32-byte sectors of 8 pixels.
-    const uint32_t pwarp = (uint32_t)warp - 1u;        // 0..2
-    const uint32_t lp = (uint32_t)lane & 7u, lc = (uint32_t)lane >> 3;
-    const uint32_t cpp = p.cpp;
-    const uint32_t nchb = cpp >> 2;                    // chunk blocks of 4 (cin is a multiple of 32 ... or 16*2)
-    const uint32_t npxb = ((uint32_t)p.halo_px + 7u) >> 3;
-    const uint32_t nunits = npxb * nchb;
+    // thread -> fixed 8-channel chunk `ch`, pixels px0, px0+ppi, ... of the window (96 % cpp == 0 for every layer)
+    const uint32_t cpp = p.cpp, ppi = kProducerThreads / cpp;
+    const uint32_t ch = (uint32_t)ptid % cpp, px0 = (uint32_t)ptid / cpp;
     const uint32_t halo_w = (uint32_t)p.halo_w;
+    const uint32_t hy0 = px0 / halo_w, hx0 = px0 - hy0 * halo_w;
+    const uint32_t dst0 = ch * (uint32_t)p.plane_bytes + px0 * 16u;
     const uint32_t cin2 = (uint32_t)p.cin * 2u;
     const uint32_t row_bytes = (uint32_t)p.W * cin2;
+    const uint32_t step_src = ppi * cin2, step_dst = ppi * 16u;
+    const uint32_t wrap_adj = row_bytes - halo_w * cin2;  // next window row, back to its first column
+    const int n_it = ((int)p.halo_px - (int)px0 + (int)ppi - 1) / (int)ppi;
     const uint8_t* in = reinterpret_cast<const uint8_t*>(p.in);
     const size_t img_bytes = (size_t)p.H * row_bytes;
     uint32_t k = 0;
@@ -189,18 +196,42 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
       const int rem = t - b * tiles_per_img;
       const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
       const int gy0 = tyi * kTileH + p.halo_y0, gx0 = txi * kTileW + p.halo_x0;
-      const uint8_t* img = in + (size_t)b * img_bytes;
-      const uint32_t dst_base = a_smem + stage * p.stage_bytes;
+      const uint8_t* img = in + (size_t)b * img_bytes + ch * 16u;
+      uint32_t dst = a_smem + stage * p.stage_bytes + dst0;
+      uint32_t hx = hx0;
+      const bool interior = gy0 >= 0 && gx0 >= 0 && gy0 + p.halo_h <= p.H && gx0 + p.halo_w <= p.W;
       mbar_wait(bar_aempty + 8 * stage, (use & 1) ^ 1, 4);
-      for (uint32_t u = pwarp; u < nunits; u += 3u) {
-        const uint32_t pb = u / nchb, cb = u - pb * nchb;  // chunk block fastest: neighbouring units share pixels
-        const uint32_t px = pb * 8u + lp, ch = cb * 4u + lc;
-        const uint32_t hy = __umulhi(px, p.halow_magic), hx = px - hy * halo_w;
-        const int gy = gy0 + (int)hy, gx = gx0 + (int)hx;
-        const bool ok = (px < (uint32_t)p.halo_px) && ((unsigned)gy < (unsigned)p.H) && ((unsigned)gx < (unsigned)p.W);
-        const uint32_t off = ok ? (uint32_t)gy * row_bytes + (uint32_t)gx * cin2 + ch * 16u : 0u;
-        if (px < (uint32_t)p.halo_px)
-          cp_async16(dst_base + ch * (uint32_t)p.plane_bytes + px * 16u, img + off, ok ? 16u : 0u);
+      if (interior) {
+        // whole window inside the image: no per-pixel bounds logic, pointer walks the window row by row
+        const uint8_t* src = img + (size_t)(gy0 + (int)hy0) * row_bytes + (size_t)(gx0 + (int)hx0) * cin2;
+        for (int it = 0; it < n_it; ++it) {
+          cp_async16(dst, src, 16u);
+          dst += step_dst;
+          src += step_src;
+          hx += ppi;
+          if (hx >= halo_w) {
+            hx -= halo_w;
+            src += wrap_adj;
+            if (hx >= halo_w) {
+              hx -= halo_w;
+              src += wrap_adj;
+            }
+          }
+        }
+      } else {
+        uint32_t hy = hy0;
+        for (int it = 0; it < n_it; ++it) {
+          const int gy = gy0 + (int)hy, gx = gx0 + (int)hx;
+          const bool ok = ((unsigned)gy < (unsigned)p.H) && ((unsigned)gx < (unsigned)p.W);
+          const uint32_t off = ok ? (uint32_t)gy * row_bytes + (uint32_t)gx * cin2 : 0u;
+          cp_async16(dst, img + off, ok ? 16u : 0u);
+          dst += step_dst;
+          hx += ppi;
+          while (hx >= halo_w) {
+            hx -= halo_w;
+            ++hy;
+          }
+        }
       }
       cp_async_arrive_noinc(bar_afull + 8 * stage);
     }
@@ -217,14 +248,10 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
 
     const int r = q * 32 + lane;           // accumulator row == TMEM lane == tile cell
     const int py = r >> 3, px = r & 7;
-    uint8_t* stg = smem + p.off_epi + (size_t)q * 32 * p.epi_pitch;  // this warp's staging rows
-    uint32_t* myrow = rowoff + q * 32;
     const int n0 = split * p.n_cta;
     const uint32_t center = (uint32_t)((py - p.halo_y0) * p.halo_w + (px - p.halo_x0)) * 16u;
     const uint32_t res_off = (uint32_t)(n0 >> 3) * (uint32_t)p.plane_bytes + center;
     const int nchunks = p.n_cta >> 4;
-    const uint32_t cpo = (uint32_t)p.n_cta >> 3;  // 16-byte chunks per cell in the output
-    const uint32_t tot = 32u * cpo;
 
     uint32_t k = 0;
     for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k) {
@@ -295,7 +322,7 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
       }
 
       if (residual) mbar_wait(bar_afull + 8 * stage, use & 1, 6);  // acquire the staged window for generic reads
-      myrow[lane] = valid ? (uint32_t)out_pixel_offset(p, b, gy, gx) + (uint32_t)n0 : 0xFFFFFFFFu;
+      T* orow = reinterpret_cast<T*>(p.out) + (valid ? out_pixel_offset(p, b, gy, gx) + (size_t)n0 : 0);
       const uint32_t ra0 = a_smem + stage * p.stage_bytes + res_off;
       for (int cc = 0; cc < nchunks; cc += 2) {
         const bool two = (cc + 1 < nchunks);
@@ -335,9 +362,14 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
               }
               o[i] = Pack2<T>::pack(fmaxf(a0, 0.2f * a0), fmaxf(a1, 0.2f * a1));  // LeakyReLU(0.2)
             }
-            uint4* dst = reinterpret_cast<uint4*>(stg + (size_t)lane * p.epi_pitch + (cc + h) * 32);
-            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            // each thread owns one grid cell: 32 contiguous bytes (16 channels) of its channel vector per step.
+            // (ncu r01: a shared-memory transpose for 512-byte-contiguous stores cost more instructions and
+            // shared-memory wavefronts than it saved; L2 merges the 16-byte halves of a sector.)
+            if (valid) {
+              uint4* dst = reinterpret_cast<uint4*>(orow + (cc + h) * 16);
+              dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+              dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            }
           }
         }
       }
@@ -346,16 +378,6 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
       if (lane == 0) {
         mbar_arrive(bar_tempty + 8 * acc);
         if (residual) mbar_arrive(bar_aempty + 8 * stage);
-      }
-      // transposed read-back: consecutive lanes write consecutive 16 B of a cell's channel vector
-      T* outp = reinterpret_cast<T*>(p.out);
-      for (uint32_t idx = lane; idx < tot; idx += 32) {
-        const uint32_t i = __umulhi(idx, p.cpo_magic), c = idx - i * cpo;
-        const uint32_t ro = myrow[i];
-        if (ro != 0xFFFFFFFFu) {
-          const uint4 val = *reinterpret_cast<const uint4*>(stg + (size_t)i * p.epi_pitch + c * 16);
-          *reinterpret_cast<uint4*>(outp + ro + c * 8) = val;
-        }
       }
       __syncwarp();
     }
@@ -462,7 +484,7 @@ int tapconv_plan(const TapConvLayer& L, TapConvParams* pp) {
   p.w_bytes = (uint32_t)L.ktotal16 * 2u * (uint32_t)L.n_cta * 16u;
   p.stage_bytes = align_up(p.cpp * (uint32_t)p.plane_bytes, 128);
   p.epi_pitch = (uint32_t)L.n_cta * 2u + 16u;
-  const uint32_t epi_bytes = (L.epi_mode == EPI_LASTCONV) ? 0u : 128u * p.epi_pitch;
+  const uint32_t epi_bytes = 0u;  // the epilogue stores straight from registers
   p.off_ss = kCtrlBytes + kRowoffBytes + kAtabBytes;
   p.cpo_magic = ceil_magic((uint32_t)L.n_cta / 8);
   p.off_w = align_up(p.off_ss + 2u * (uint32_t)L.n_cta * 4u, 128);
@@ -530,8 +552,7 @@ cudaError_t launch_tapconv(const TapConvLayer& L, int op_type, const void* in, v
   if (cps > p.ntiles) cps = p.ntiles;
   p.ctas_per_split = cps;
   const int grid = cps * L.nsplit;
-  const uint32_t epi_bytes = (L.epi_mode == EPI_LASTCONV) ? 0u : 128u * p.epi_pitch;
-  const size_t smem = p.off_epi + epi_bytes;
+  const size_t smem = p.off_epi;
   cudaError_t err;
   if (op_type == OP_BF16) {
     err = cudaFuncSetAttribute(tapconv_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);

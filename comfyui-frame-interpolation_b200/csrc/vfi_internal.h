@@ -94,12 +94,13 @@ struct FlowState {
   float* m[4];
   int s[4];
 };
-cudaError_t launch_front(int op_type, const float4* imgs, const FlowState& fs, int nlev, BatchTasks tasks, int Hp,
-                         int Wp, int s, void* x_s2d, cudaStream_t st);
-cudaError_t launch_materialize(const FlowState& fs, int nlev, float4* flow, float* mask, int B, int Hp, int Wp,
-                               cudaStream_t st);
-cudaError_t launch_final(const float4* imgs, const FlowState& fs, BatchTasks tasks, int Hp, int Wp, int H, int W,
-                         float* out, cudaStream_t st);
+cudaError_t launch_front(int op_type, const float4* imgs, const FlowState& fs, int blk, int lo, const float4* base_f,
+                         const float* base_m, float4* out_f, float* out_m, BatchTasks tasks, int Hp, int Wp, int s,
+                         void* x_s2d, cudaStream_t st);
+cudaError_t launch_materialize(const FlowState& fs, int lo, const float4* base_f, const float* base_m, float4* flow,
+                               float* mask, int B, int Hp, int Wp, cudaStream_t st);
+cudaError_t launch_final(const float4* imgs, const FlowState& fs, int lo, const float4* base_f, const float* base_m,
+                         BatchTasks tasks, int Hp, int Wp, int H, int W, float* out, cudaStream_t st);
 cudaError_t launch_warp(const float* img, const float* flow, float* out, int B, int H, int W, int C, cudaStream_t st);
 
 void set_error(const std::string& s);

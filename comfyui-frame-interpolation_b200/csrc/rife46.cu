@@ -198,10 +198,9 @@ int build_conv_s2(vfi_ctx* c, TapConvLayer& L, int Cs, int creal, int cout, int 
     return w[(((size_t)n * creal + ci) * 3 + ky) * 3 + kx];
   };
   std::vector<uint16_t> pk = pack_weights(L, c->op_type, wf);
-  std::vector<float> sc(cout, 1.f), sh(bias, bias + cout);
+  std::vector<float> sh(bias, bias + cout);
   int r;
   if ((r = upload(c, pk, &L.w))) return r;
-  if ((r = upload(c, sc, (void**)&L.scale))) return r;
   if ((r = upload(c, sh, (void**)&L.shift))) return r;
   return VFI_OK;
 }
@@ -220,15 +219,16 @@ int build_resconv(vfi_ctx* c, TapConvLayer& L, int ch, const float* beta, const 
       t.dy = (int16_t)(ky - 1); t.dx = (int16_t)(kx - 1); t.chunk0 = 0; t.nk16 = (int16_t)(ch / 16);
     }
   choose_split(L, {1, 2, 3, 4, 6, 8, 12}, 3);
+  // (conv(x) + b) * beta + x  ==  conv_{w*beta}(x) + b*beta + x : beta is folded into the packed weights (one 16-bit
+  // rounding of w*beta instead of w) so the epilogue is a pure add
   auto wf = [&](int e, int ci, int n) -> float {
-    return w[(((size_t)n * ch + ci) * 3 + e / 3) * 3 + e % 3];
+    return w[(((size_t)n * ch + ci) * 3 + e / 3) * 3 + e % 3] * beta[n];
   };
   std::vector<uint16_t> pk = pack_weights(L, c->op_type, wf);
-  std::vector<float> sc(beta, beta + ch), sh(ch);
-  for (int i = 0; i < ch; ++i) sh[i] = bias[i] * beta[i];  // (conv + b)*beta + x  ==  conv*beta + b*beta + x
+  std::vector<float> sh(ch);
+  for (int i = 0; i < ch; ++i) sh[i] = bias[i] * beta[i];
   int r;
   if ((r = upload(c, pk, &L.w))) return r;
-  if ((r = upload(c, sc, (void**)&L.scale))) return r;
   if ((r = upload(c, sh, (void**)&L.shift))) return r;
   return VFI_OK;
 }
@@ -262,11 +262,10 @@ int build_lastconv(vfi_ctx* c, TapConvLayer& L, int ch, const float* wt, const f
     return wt[(((size_t)ci * 24 + oc_of(n)) * 4 + ky) * 4 + kx];
   };
   std::vector<uint16_t> pk = pack_weights(L, c->op_type, wf);
-  std::vector<float> sc(80, 1.f), sh(80);
+  std::vector<float> sh(80);
   for (int n = 0; n < 80; ++n) sh[n] = bias[oc_of(n)];
   int r;
   if ((r = upload(c, pk, &L.w))) return r;
-  if ((r = upload(c, sc, (void**)&L.scale))) return r;
   if ((r = upload(c, sh, (void**)&L.shift))) return r;
   return VFI_OK;
 }

@@ -239,11 +239,8 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
     // ======================================================= epilogue (warps 4..7 <-> TMEM lane quarters 0..3)
     const int q = warp - 4;
     const int etid = threadIdx.x - 128;
-    float* ss = reinterpret_cast<float*>(smem + p.off_ss);  // interleaved: ss[2n] = scale_n, ss[2n+1] = shift_n
-    for (int i = etid; i < p.n_cta; i += 128) {
-      ss[2 * i] = p.scale[split * p.n_cta + i];
-      ss[2 * i + 1] = p.shift[split * p.n_cta + i];
-    }
+    float* ss = reinterpret_cast<float*>(smem + p.off_ss);  // per-channel shift of this CTA's output slice
+    for (int i = etid; i < p.n_cta; i += 128) ss[i] = p.shift[split * p.n_cta + i];
     asm volatile("bar.sync 1, 128;" ::: "memory");
 
     const int r = q * 32 + lane;           // accumulator row == TMEM lane == tile cell
@@ -285,12 +282,12 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
               for (int x4 = 0; x4 < 4; ++x4) {
                 const int pos = y4 * 4 + x4;
                 float4 f;
-                f.x = __uint_as_float(v[0][pos]) + ss[2 * (0 * 16 + pos) + 1];
-                f.y = __uint_as_float(v[1][pos]) + ss[2 * (1 * 16 + pos) + 1];
-                f.z = __uint_as_float(v[2][pos]) + ss[2 * (2 * 16 + pos) + 1];
-                f.w = __uint_as_float(v[3][pos]) + ss[2 * (3 * 16 + pos) + 1];
+                f.x = __uint_as_float(v[0][pos]) + ss[0 * 16 + pos];
+                f.y = __uint_as_float(v[1][pos]) + ss[1 * 16 + pos];
+                f.z = __uint_as_float(v[2][pos]) + ss[2 * 16 + pos];
+                f.w = __uint_as_float(v[3][pos]) + ss[3 * 16 + pos];
                 p.out_flow[o + x4] = f;
-                p.out_mask[o + x4] = __uint_as_float(v[4][pos]) + ss[2 * (4 * 16 + pos) + 1];
+                p.out_mask[o + x4] = __uint_as_float(v[4][pos]) + ss[4 * 16 + pos];
               }
             }
           }
@@ -306,7 +303,7 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
 #pragma unroll
               for (int pos = 0; pos < 16; ++pos) {
                 const size_t o = ((size_t)b * Hs + (gy * 4 + (pos >> 2))) * Ws + gx * 4 + (pos & 3);
-                const float val = __uint_as_float(v[pos]) + ss[2 * (cc * 16 + pos) + 1];
+                const float val = __uint_as_float(v[pos]) + ss[cc * 16 + pos];
                 if (c5 < 4)
                   reinterpret_cast<float*>(p.out_flow)[o * 4 + c5] = val;
                 else
@@ -329,17 +326,22 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
         uint32_t v[2][16];
         tmem_ld16(taddr + cc * 16, v[0]);
         if (two) tmem_ld16(taddr + cc * 16 + 16, v[1]);
-        uint32_t rr[2][8];
-        if (residual) {
+        // shared-memory operands of this step are fetched while the TMEM load is in flight
+        float4 sh[2][4];
+        uint4 rr[2][2];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (h == 0 || two) {
+        for (int h = 0; h < 2; ++h) {
+          if (h == 0 || two) {
+            const float4* sp = reinterpret_cast<const float4*>(ss + (cc + h) * 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sh[h][i] = sp[i];
+            if (residual) {
               const uint32_t ra = ra0 + (uint32_t)(2 * (cc + h)) * (uint32_t)p.plane_bytes;
               asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                           : "=r"(rr[h][0]), "=r"(rr[h][1]), "=r"(rr[h][2]), "=r"(rr[h][3])
+                           : "=r"(rr[h][0].x), "=r"(rr[h][0].y), "=r"(rr[h][0].z), "=r"(rr[h][0].w)
                            : "r"(ra));
               asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                           : "=r"(rr[h][4]), "=r"(rr[h][5]), "=r"(rr[h][6]), "=r"(rr[h][7])
+                           : "=r"(rr[h][1].x), "=r"(rr[h][1].y), "=r"(rr[h][1].z), "=r"(rr[h][1].w)
                            : "r"(ra + (uint32_t)p.plane_bytes));
             }
           }
@@ -348,15 +350,18 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           if (h == 0 || two) {
+            const float shf[16] = {sh[h][0].x, sh[h][0].y, sh[h][0].z, sh[h][0].w, sh[h][1].x, sh[h][1].y,
+                                   sh[h][1].z, sh[h][1].w, sh[h][2].x, sh[h][2].y, sh[h][2].z, sh[h][2].w,
+                                   sh[h][3].x, sh[h][3].y, sh[h][3].z, sh[h][3].w};
+            const uint32_t rw[8] = {rr[h][0].x, rr[h][0].y, rr[h][0].z, rr[h][0].w,
+                                    rr[h][1].x, rr[h][1].y, rr[h][1].z, rr[h][1].w};
             uint32_t o[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const int n = (cc + h) * 16 + 2 * i;
-              const float4 sc = *reinterpret_cast<const float4*>(ss + 2 * n);  // scale_n, shift_n, scale_n+1, shift_n+1
-              float a0 = fmaf(__uint_as_float(v[h][2 * i]), sc.x, sc.y);
-              float a1 = fmaf(__uint_as_float(v[h][2 * i + 1]), sc.z, sc.w);
+              float a0 = __uint_as_float(v[h][2 * i]) + shf[2 * i];
+              float a1 = __uint_as_float(v[h][2 * i + 1]) + shf[2 * i + 1];
               if (residual) {
-                const float2 rf = Pack2<T>::unpack(rr[h][i]);
+                const float2 rf = Pack2<T>::unpack(rw[i]);
                 a0 += rf.x;
                 a1 += rf.y;
               }
@@ -448,7 +453,7 @@ __global__ void tapconv_ref_kernel(const __grid_constant__ TapConvParams p) {
       else
         p.out_mask[o] = v;
     } else {
-      float v = fmaf(acc, p.scale[n], p.shift[n]);
+      float v = acc + p.shift[n];
       if (p.epi_mode == EPI_RESCONV) v += ld16bit<T>(in + (((size_t)b * p.H + gy) * p.W + gx) * p.cin + n);
       reinterpret_cast<T*>(p.out)[out_pixel_offset(p, b, gy, gx) + n] = cvt16bit<T>(lrelu02(v));
     }
@@ -487,7 +492,7 @@ int tapconv_plan(const TapConvLayer& L, TapConvParams* pp) {
   const uint32_t epi_bytes = 0u;  // the epilogue stores straight from registers
   p.off_ss = kCtrlBytes + kRowoffBytes + kAtabBytes;
   p.cpo_magic = ceil_magic((uint32_t)L.n_cta / 8);
-  p.off_w = align_up(p.off_ss + 2u * (uint32_t)L.n_cta * 4u, 128);
+  p.off_w = align_up(p.off_ss + (uint32_t)L.n_cta * 4u, 128);
   p.off_a = align_up(p.off_w + p.w_bytes, 128);
   int stages = 0;
   for (int s = kMaxStages; s >= 1; --s) {
@@ -524,7 +529,6 @@ cudaError_t launch_tapconv(const TapConvLayer& L, int op_type, const void* in, v
   p.out_flow = out_flow;
   p.out_mask = out_mask;
   p.w = L.w;
-  p.scale = L.scale;
   p.shift = L.shift;
   p.B = B;
   p.H = H;

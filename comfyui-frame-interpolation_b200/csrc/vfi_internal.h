@@ -15,8 +15,8 @@ namespace vfi {
 // space-to-depth input, the transposed conv writes a 4x4 sub-pixel patch per grid cell.
 // ---------------------------------------------------------------------------------------------
 enum EpiMode : int {
-  EPI_BIAS_LRELU = 0,  // out = lrelu(acc*scale + shift)                         (conv0.0, conv0.1)
-  EPI_RESCONV = 1,     // out = lrelu(acc*scale + shift + in[b,y,x,n])           (ResConv; scale=beta, shift=bias*beta)
+  EPI_BIAS_LRELU = 0,  // out = lrelu(acc + shift)                               (conv0.0, conv0.1)
+  EPI_RESCONV = 1,     // out = lrelu(acc + shift + in[b,y,x,n])                 (ResConv; beta folded into W, shift=bias*beta)
   EPI_LASTCONV = 2,    // out5[b, 4y+py, 4x+px] = acc + shift, n = c5*16 + py*4+px (ConvT(4,2,1)+PixelShuffle(2))
 };
 
@@ -37,7 +37,6 @@ struct TapConvParams {
   float4* out_flow;      // EPI_LASTCONV: [B, 4H, 4W] float4 (4 flow components)
   float* out_mask;       // EPI_LASTCONV: [B, 4H, 4W]
   const void* w;         // packed weights: [nsplit][2*ktotal16][n_cta][8] 16-bit
-  const float* scale;    // [n_total]
   const float* shift;    // [n_total]
   int B, H, W, cin;
   int n_total, n_cta, nsplit;
@@ -64,7 +63,6 @@ struct TapConvLayer {
   int epi_mode = 0, out_s2d = 0;
   TapEntry taps[kMaxTaps];
   void* w = nullptr;      // device
-  float* scale = nullptr; // device
   float* shift = nullptr; // device
 };
 

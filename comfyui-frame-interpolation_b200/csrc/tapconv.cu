@@ -15,10 +15,11 @@
 // (one cp.async.bulk per CTA), accumulators live in TMEM (double buffered), the epilogue reads the residual
 // from the staged window, not from global memory.
 //
-// Warp roles (256 threads, 1 CTA/SM, persistent over tiles):
+// Warp roles (384 threads, 1 CTA/SM, persistent over tiles):
 //   warp 0      : TMEM alloc/dealloc; lane 0 issues all tcgen05.mma + tcgen05.commit
 //   warps 1..3  : producers - cp.async (LDGSTS.128, zero-fill outside the image) of the input window
-//   warps 4..7  : epilogue  - tcgen05.ld -> scale/shift/residual/LeakyReLU -> 16-bit -> coalesced global stores
+//   warps 4..11 : epilogue  - two sets of four (one per accumulator buffer): tcgen05.ld -> +shift (+residual)
+//                 -> LeakyReLU -> 16-bit -> global stores (or the fp32 4x4 flow/mask patch for lastconv)
 #include "ptx.cuh"
 #include "vfi_internal.h"
 
@@ -37,7 +38,7 @@ struct Ctrl {
   uint32_t tmem_base;
 };
 constexpr uint32_t kCtrlBytes = 256;
-constexpr uint32_t kAtabBytes = 4096;  // descriptor table: stages x K=16 steps x {a_lo, b_lo} (<= 512 entries)
+constexpr uint32_t kAtabBytes = 8192;  // descriptor table: stages x K=16 steps x {a_lo, a_hi, b_lo, b_hi} (<= 512 entries)
 constexpr uint32_t kRowoffBytes = 512; // 128 rows
 static_assert(sizeof(Ctrl) <= kCtrlBytes, "control block");
 
@@ -52,8 +53,8 @@ __device__ __forceinline__ size_t out_pixel_offset(const TapConvParams& p, int b
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__ TapConvParams p) {
-  extern __shared__ __align__(128) uint8_t smem[];
+__global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__ TapConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
     for (int s = 0; s < S; ++s) {
-      mbar_init(bar_afull + 8 * s, kProducerThreads);
+      mbar_init(bar_afull + 8 * s, p.layout == LAYOUT_SWZ ? 1 : kProducerThreads);
       mbar_init(bar_aempty + 8 * s, residual ? 4 : 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -83,15 +84,11 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
     }
     mbar_fence_init();
   }
-  // Descriptor table, built once: for every (stage, K=16 step) the low words of the A and B shared-memory
-  // descriptors.  The MMA issue loop is then "load 8 bytes, issue" (ncu r01: the issuing warp was the bottleneck
-  // when it computed descriptors on the fly - 1240 instructions per tile).
+  // Descriptor table, built once: for every (stage, K=16 step) the A and B shared-memory descriptors.  The MMA
+  // issue loop is then "load 16 bytes, issue" (ncu r01: the issuing warp was the bottleneck when it computed
+  // descriptors on the fly - 1240 instructions per tile).
   {
-    uint2* tab = reinterpret_cast<uint2*>(smem + kCtrlBytes + kRowoffBytes);
-    const uint32_t plane16 = (uint32_t)p.plane_bytes >> 4;
-    const uint32_t a_lo_c = plane16 << 16;
-    const uint32_t b_lo_c = (((uint32_t)p.n_cta * 16u) >> 4) << 16;
-    const uint32_t b_step = ((uint32_t)p.n_cta * 32u) >> 4;
+    uint4* tab = reinterpret_cast<uint4*>(smem + kCtrlBytes + kRowoffBytes);
     const int K16 = p.ktotal16;
     for (int id = threadIdx.x; id < S * K16; id += blockDim.x) {
       const int st = id / K16;
@@ -102,11 +99,35 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
         ++e;
       }
       const TapEntry te = p.taps[e];
-      const uint32_t a_off = (uint32_t)(te.chunk0 + 2 * j) * plane16 +
-                             (uint32_t)((te.dy - p.halo_y0) * p.halo_w + (te.dx - p.halo_x0));
-      uint2 d;
-      d.x = a_lo_c | (((smem_base + p.off_a + (uint32_t)st * p.stage_bytes) >> 4) + a_off);
-      d.y = b_lo_c | (((smem_base + p.off_w) >> 4) + (uint32_t)jj * b_step);
+      const uint32_t stage_addr = smem_base + p.off_a + (uint32_t)st * p.stage_bytes;
+      uint4 d;
+      if (p.layout == LAYOUT_SWZ) {
+        // rows = window pixels, 128 B (64 ch, SWIZZLE_128B) or 64 B (32-channel tail, SWIZZLE_64B) each; a tap is a
+        // start-address shift of whole rows, a K=16 step a 32-byte shift inside the row (the hardware applies the
+        // XOR swizzle on the absolute shared-memory address, exactly as TMA wrote it).
+        const int ch0 = te.chunk0 * 8 + 16 * j;               // first input channel of this step
+        const int kb = ch0 >> 6;
+        const bool tail = (kb == p.nkb - 1) && (p.cin & 63);  // 32-channel tail block
+        const uint32_t rowb = tail ? 64u : 128u;
+        const uint32_t a_addr = stage_addr + p.kb_off[kb] +
+                                (uint32_t)((te.dy - p.halo_y0) * p.halo_pitch + (te.dx - p.halo_x0)) * rowb +
+                                (uint32_t)(ch0 - kb * 64) * 2u;
+        const uint32_t a_sbo = (uint32_t)p.halo_pitch * rowb;
+        d.x = ((a_addr >> 4) & 0x3FFFu) | (1u << 16);
+        d.y = (a_sbo >> 4) | (1u << 14) | ((tail ? 4u : 2u) << 29);
+        if (p.desc_mode & 1) d.y |= ((a_addr >> 7) & 7u) << 17;  // base_offset field, bits [49,52)
+        const uint32_t b_addr = smem_base + p.off_w + (uint32_t)(jj >> 2) * ((uint32_t)p.n_cta * 128u) + (uint32_t)(jj & 3) * 32u;
+        d.z = ((b_addr >> 4) & 0x3FFFu) | (1u << 16);
+        d.w = (1024u >> 4) | (1u << 14) | (2u << 29);
+      } else {
+        const uint32_t plane16 = (uint32_t)p.plane_bytes >> 4;
+        const uint32_t a_off = (uint32_t)(te.chunk0 + 2 * j) * plane16 +
+                               (uint32_t)((te.dy - p.halo_y0) * p.halo_w + (te.dx - p.halo_x0));
+        d.x = (plane16 << 16) | ((stage_addr >> 4) + a_off);
+        d.y = (((uint32_t)p.halo_w * 16u) >> 4) | (1u << 14);   // SBO | version
+        d.z = ((((uint32_t)p.n_cta * 16u) >> 4) << 16) | (((smem_base + p.off_w) >> 4) + (uint32_t)jj * (((uint32_t)p.n_cta * 32u) >> 4));
+        d.w = (128u >> 4) | (1u << 14);
+      }
       tab[id] = d;
     }
   }
@@ -125,9 +146,7 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
     // The whole warp runs the (warp-uniform) control flow; one elected lane issues tcgen05.mma / tcgen05.commit.
     const uint32_t leader = elect_one_sync();
     mbar_wait(bar_w, 0, 1);
-    const uint32_t a_hi_c = (((uint32_t)p.halo_w * 16u) >> 4) | (1u << 14);  // SBO | version
-    const uint32_t b_hi_c = (128u >> 4) | (1u << 14);
-    const uint2* tab0 = reinterpret_cast<const uint2*>(smem + kCtrlBytes + kRowoffBytes);
+    const uint4* tab0 = reinterpret_cast<const uint4*>(smem + kCtrlBytes + kRowoffBytes);
     const int K16 = p.ktotal16;
     const uint32_t idesc = p.idesc;
     uint32_t k = 0;
@@ -138,11 +157,11 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
       fence_proxy_async();  // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
-      const uint2* tab = tab0 + stage * K16;
+      const uint4* tab = tab0 + stage * K16;
       // K16 is a multiple of 9 for every layer (9 taps x c/16 or 9 x c/32): issue in groups of nine, the next
       // group's descriptors are fetched into registers before the current group is issued, so the shared-memory
       // latency never sits between two MMAs (ncu r01 v2: the issuing warp spent ~140 cycles per MMA).
-      uint2 cur[9], nxt[9];
+      uint4 cur[9], nxt[9];
 #pragma unroll
       for (int i = 0; i < 9; ++i) cur[i] = tab[i];
       const int ngroups = K16 / 9;
@@ -152,9 +171,9 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
           for (int i = 0; i < 9; ++i) nxt[i] = tab[(g + 1) * 9 + i];
         }
         if (leader) {
-          umma_f16_split(d_tmem, cur[0].x, a_hi_c, cur[0].y, b_hi_c, idesc, g > 0 ? 1u : 0u);
+          umma_f16_split(d_tmem, cur[0].x, cur[0].y, cur[0].z, cur[0].w, idesc, g > 0 ? 1u : 0u);
 #pragma unroll
-          for (int i = 1; i < 9; ++i) umma_f16_split(d_tmem, cur[i].x, a_hi_c, cur[i].y, b_hi_c, idesc, 1u);
+          for (int i = 1; i < 9; ++i) umma_f16_split(d_tmem, cur[i].x, cur[i].y, cur[i].z, cur[i].w, idesc, 1u);
         }
 #pragma unroll
         for (int i = 0; i < 9; ++i) cur[i] = nxt[i];
@@ -176,6 +195,27 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
         bulk_g2s(w_smem + off, wsrc + off, n, bar_w);
       }
     }
+    if (p.layout == LAYOUT_SWZ) {
+      // one thread feeds the whole pipeline: a 4-D tensor copy per k-block drops the window (zero-filled outside
+      // the image = conv padding) into shared memory already in the swizzled K-major operand layout
+      if (ptid == 0) {
+        uint32_t k = 0;
+        for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k) {
+          const uint32_t stage = k % S, use = k / S;
+          const int b = t / tiles_per_img;
+          const int rem = t - b * tiles_per_img;
+          const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
+          const int gy0 = tyi * kTileH + p.halo_y0, gx0 = txi * kTileW + p.halo_x0;
+          mbar_wait(bar_aempty + 8 * stage, (use & 1) ^ 1, 4);
+          mbar_arrive_expect_tx(bar_afull + 8 * stage, p.tx_bytes);
+          const uint32_t dst = a_smem + stage * p.stage_bytes;
+          for (int kb = 0; kb < p.nkb; ++kb) {
+            const bool tail = (kb == p.nkb - 1) && (p.cin & 63);
+            tma_load_4d(dst + p.kb_off[kb], tail ? &p.tm32 : &p.tm64, bar_afull + 8 * stage, kb * 64, gx0, gy0, b);
+          }
+        }
+      }
+    } else {
     // thread -> fixed 8-channel chunk `ch`, pixels px0, px0+ppi, ... of the window (96 % cpp == 0 for every layer)
     const uint32_t cpp = p.cpp, ppi = kProducerThreads / cpp;
     const uint32_t ch = (uint32_t)ptid % cpp, px0 = (uint32_t)ptid / cpp;
@@ -235,24 +275,30 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
       }
       cp_async_arrive_noinc(bar_afull + 8 * stage);
     }
+    }
   } else {
     // ======================================================= epilogue (warps 4..7 <-> TMEM lane quarters 0..3)
-    const int q = warp - 4;
+    // two epilogue warp sets (warps 4..7 and 8..11): set s drains accumulator buffer s, i.e. every other tile, so
+    // one tile's epilogue overlaps the next tile's (ncu r01 v5: a single set was busy 100 % of the time)
+    const int q = (warp - 4) & 3;
+    const uint32_t eset = (uint32_t)(warp - 4) >> 2;
     const int etid = threadIdx.x - 128;
     float* ss = reinterpret_cast<float*>(smem + p.off_ss);  // per-channel shift of this CTA's output slice
-    for (int i = etid; i < p.n_cta; i += 128) ss[i] = p.shift[split * p.n_cta + i];
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int i = etid; i < p.n_cta; i += 256) ss[i] = p.shift[split * p.n_cta + i];
+    asm volatile("bar.sync 1, 256;" ::: "memory");
 
     const int r = q * 32 + lane;           // accumulator row == TMEM lane == tile cell
     const int py = r >> 3, px = r & 7;
     const int n0 = split * p.n_cta;
     const uint32_t center = (uint32_t)((py - p.halo_y0) * p.halo_w + (px - p.halo_x0)) * 16u;
     const uint32_t res_off = (uint32_t)(n0 >> 3) * (uint32_t)p.plane_bytes + center;
+    const uint32_t center_px = (uint32_t)((py - p.halo_y0) * p.halo_pitch + (px - p.halo_x0));  // LAYOUT_SWZ
     const int nchunks = p.n_cta >> 4;
 
     uint32_t k = 0;
     for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k) {
       const uint32_t stage = k % S, use = k / S, acc = k & 1, vuse = k >> 1;
+      if (acc != eset) continue;
       const int b = t / tiles_per_img;
       const int rem = t - b * tiles_per_img;
       const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
@@ -336,13 +382,26 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
 #pragma unroll
             for (int i = 0; i < 4; ++i) sh[h][i] = sp[i];
             if (residual) {
-              const uint32_t ra = ra0 + (uint32_t)(2 * (cc + h)) * (uint32_t)p.plane_bytes;
+              uint32_t ra, rb;  // shared-memory addresses of the two 16-byte chunks (16 residual channels)
+              if (p.layout == LAYOUT_SWZ) {
+                const int ch0 = n0 + (cc + h) * 16;
+                const int kb = ch0 >> 6;
+                const bool tail = (kb == p.nkb - 1) && (p.cin & 63);
+                const uint32_t rowb = tail ? 64u : 128u, msk = tail ? 3u : 7u;
+                const uint32_t row = a_smem + stage * p.stage_bytes + p.kb_off[kb] + center_px * rowb;
+                const uint32_t c0 = (uint32_t)(ch0 - kb * 64) >> 3, sw = (row >> 7) & msk;
+                ra = row + ((c0 ^ sw) << 4);
+                rb = row + (((c0 + 1u) ^ sw) << 4);
+              } else {
+                ra = ra0 + (uint32_t)(2 * (cc + h)) * (uint32_t)p.plane_bytes;
+                rb = ra + (uint32_t)p.plane_bytes;
+              }
               asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
                            : "=r"(rr[h][0].x), "=r"(rr[h][0].y), "=r"(rr[h][0].z), "=r"(rr[h][0].w)
                            : "r"(ra));
               asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
                            : "=r"(rr[h][1].x), "=r"(rr[h][1].y), "=r"(rr[h][1].z), "=r"(rr[h][1].w)
-                           : "r"(ra + (uint32_t)p.plane_bytes));
+                           : "r"(rb));
             }
           }
         }
@@ -379,6 +438,7 @@ __global__ void __launch_bounds__(256, 1) tapconv_kernel(const __grid_constant__
         }
       }
       tc_fence_before();
+      if (residual && p.layout == LAYOUT_SWZ) fence_proxy_async();  // generic reads before the next TMA write
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(bar_tempty + 8 * acc);
@@ -437,8 +497,15 @@ __global__ void tapconv_ref_kernel(const __grid_constant__ TapConvParams p) {
         for (int c = 0; c < 16; ++c) {
           const int cin_idx = te.chunk0 * 8 + i * 16 + c;
           const float a = ld16bit<T>(in + (((size_t)b * p.H + y) * p.W + x) * p.cin + cin_idx);
-          const int kk = j * 2 + (c >> 3);  // 8-channel K chunk
-          const float wv = ld16bit<T>(w + ((size_t)kk * p.n_cta + nl) * 8 + (c & 7));
+          size_t widx;
+          if (p.layout == LAYOUT_SWZ) {  // [j/4][n][128 B row, 16-byte chunks XOR (n & 7)]
+            const int chunk = (j & 3) * 2 + (c >> 3);
+            widx = ((size_t)(j >> 2) * p.n_cta + nl) * 64 + (size_t)((chunk ^ (nl & 7)) * 8 + (c & 7));
+          } else {
+            const int kk = j * 2 + (c >> 3);  // 8-channel K chunk
+            widx = ((size_t)kk * p.n_cta + nl) * 8 + (c & 7);
+          }
+          const float wv = ld16bit<T>(w + widx);
           acc = fmaf(a, wv, acc);
         }
       }
@@ -458,6 +525,35 @@ __global__ void tapconv_ref_kernel(const __grid_constant__ TapConvParams p) {
       reinterpret_cast<T*>(p.out)[out_pixel_offset(p, b, gy, gx) + n] = cvt16bit<T>(lrelu02(v));
     }
   }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+bool make_tmap(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, int C, int W, int H, int B, int box_c,
+               int box_w, int box_h, CUtensorMapSwizzle swz) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || !f) {
+      set_error("cuTensorMapEncodeTiled is not available from this driver");
+      return false;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(f);
+  }
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  const CUresult r = fn(tm, dt, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return false;
+  }
+  return true;
 }
 
 uint32_t ceil_magic(uint32_t d) { return (uint32_t)((0x100000000ull + d - 1) / d); }
@@ -486,14 +582,35 @@ int tapconv_plan(const TapConvLayer& L, TapConvParams* pp) {
   p.cpp = (uint32_t)L.cin / 8;
   p.cpp_magic = ceil_magic(p.cpp);
   p.halow_magic = ceil_magic((uint32_t)L.halo_w);
-  p.w_bytes = (uint32_t)L.ktotal16 * 2u * (uint32_t)L.n_cta * 16u;
-  p.stage_bytes = align_up(p.cpp * (uint32_t)p.plane_bytes, 128);
+  p.layout = L.layout;
+  p.desc_mode = L.desc_mode;
+  p.halo_pitch = L.halo_pitch > 0 ? L.halo_pitch : L.halo_w;
+  uint32_t walign = 128;
+  if (L.layout == LAYOUT_SWZ) {
+    // weights: [ceil(K16/4)][n_cta] rows of 128 B (four K=16 steps), 128B-swizzled; window: one region per k-block
+    p.w_bytes = (uint32_t)((L.ktotal16 + 3) / 4) * (uint32_t)L.n_cta * 128u;
+    p.nkb = (L.cin + 63) / 64;
+    uint32_t off = 0;
+    p.tx_bytes = 0;
+    for (int kb = 0; kb < p.nkb; ++kb) {
+      const bool tail = (kb == p.nkb - 1) && (L.cin & 63);
+      const uint32_t bytes = (uint32_t)p.halo_pitch * (uint32_t)L.halo_h * (tail ? 64u : 128u);
+      p.kb_off[kb] = off;
+      off += align_up(bytes, 1024);
+      p.tx_bytes += bytes;
+    }
+    p.stage_bytes = off;
+    walign = 1024;
+  } else {
+    p.w_bytes = (uint32_t)L.ktotal16 * 2u * (uint32_t)L.n_cta * 16u;
+    p.stage_bytes = align_up(p.cpp * (uint32_t)p.plane_bytes, 128);
+  }
   p.epi_pitch = (uint32_t)L.n_cta * 2u + 16u;
   const uint32_t epi_bytes = 0u;  // the epilogue stores straight from registers
   p.off_ss = kCtrlBytes + kRowoffBytes + kAtabBytes;
   p.cpo_magic = ceil_magic((uint32_t)L.n_cta / 8);
-  p.off_w = align_up(p.off_ss + (uint32_t)L.n_cta * 4u, 128);
-  p.off_a = align_up(p.off_w + p.w_bytes, 128);
+  p.off_w = align_up(p.off_ss + (uint32_t)L.n_cta * 4u, walign);
+  p.off_a = align_up(p.off_w + p.w_bytes, walign);
   int stages = 0;
   for (int s = kMaxStages; s >= 1; --s) {
     if (p.off_a + (uint32_t)s * p.stage_bytes + epi_bytes <= (uint32_t)kSmemLimit) {
@@ -501,8 +618,8 @@ int tapconv_plan(const TapConvLayer& L, TapConvParams* pp) {
       break;
     }
   }
-  while (stages > 1 && stages * L.ktotal16 > (int)(kAtabBytes / 8)) --stages;  // descriptor table capacity
-  if (stages * L.ktotal16 > (int)(kAtabBytes / 8)) stages = 0;
+  while (stages > 1 && stages * L.ktotal16 > (int)(kAtabBytes / 16)) --stages;  // descriptor table capacity
+  if (stages * L.ktotal16 > (int)(kAtabBytes / 16)) stages = 0;
   p.stages = stages;
   p.off_epi = p.off_a + (uint32_t)stages * p.stage_bytes;
   // accumulators: two buffers of n_cta fp32 columns, allocation is a power of two >= 32
@@ -551,6 +668,17 @@ cudaError_t launch_tapconv(const TapConvLayer& L, int op_type, const void* in, v
     return cudaGetLastError();
   }
 
+  if (L.layout == LAYOUT_SWZ) {
+    const CUtensorMapDataType dt = (op_type == OP_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    if (!make_tmap(&p.tm64, dt, in, L.cin, W, H, B, 64, p.halo_pitch, L.halo_h, CU_TENSOR_MAP_SWIZZLE_128B))
+      return cudaErrorInvalidValue;
+    if (L.cin & 63) {
+      if (!make_tmap(&p.tm32, dt, in, L.cin, W, H, B, 32, p.halo_pitch, L.halo_h, CU_TENSOR_MAP_SWIZZLE_64B))
+        return cudaErrorInvalidValue;
+    } else {
+      p.tm32 = p.tm64;
+    }
+  }
   int cps = num_sms / L.nsplit;
   if (cps < 1) cps = 1;
   if (cps > p.ntiles) cps = p.ntiles;
@@ -561,11 +689,11 @@ cudaError_t launch_tapconv(const TapConvLayer& L, int op_type, const void* in, v
   if (op_type == OP_BF16) {
     err = cudaFuncSetAttribute(tapconv_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (err != cudaSuccess) return err;
-    tapconv_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(p);
+    tapconv_kernel<__nv_bfloat16><<<grid, 384, smem, st>>>(p);
   } else {
     err = cudaFuncSetAttribute(tapconv_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (err != cudaSuccess) return err;
-    tapconv_kernel<__half><<<grid, 256, smem, st>>>(p);
+    tapconv_kernel<__half><<<grid, 384, smem, st>>>(p);
   }
   return cudaGetLastError();
 }

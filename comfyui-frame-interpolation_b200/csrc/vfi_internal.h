@@ -1,5 +1,6 @@
 // Internal declarations shared by the .cu files of libvfi_b200.so (not part of the C ABI).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -31,7 +32,16 @@ constexpr int kTileH = 16, kTileW = 8;        // one CTA tile = 128 grid cells =
 constexpr int kProducerThreads = 96;          // warps 1..3
 constexpr int kSmemLimit = 232448;            // 227 KB opt-in maximum per CTA on sm_100
 
-struct TapConvParams {
+// shared-memory layout of the staged input window / weights
+enum TapLayout : int {
+  LAYOUT_PLANES = 0,  // A[chunk][pixel][8ch] no-swizzle K-major planes, filled by LDGSTS (cp.async)
+  LAYOUT_SWZ = 1,     // A[k-block][pixel][64|32 ch] 128B/64B-swizzled K-major rows, filled by TMA tensor copies
+};
+constexpr int kMaxKBlocks = 6;
+
+struct alignas(64) TapConvParams {
+  CUtensorMap tm64;      // LAYOUT_SWZ: input as [B,H,W,C] with a {64ch, pitch, halo_h, 1} box, SWIZZLE_128B
+  CUtensorMap tm32;      // LAYOUT_SWZ: same with a {32ch, ...} box, SWIZZLE_64B (only when cin % 64 == 32)
   const void* in;        // [B, H, W, cin] 16-bit, NHWC
   void* out;             // [B, H, W, n_total] 16-bit NHWC, or its space-to-depth form when out_s2d
   float4* out_flow;      // EPI_LASTCONV: [B, 4H, 4W] float4 (4 flow components)
@@ -52,6 +62,12 @@ struct TapConvParams {
   uint32_t w_bytes;             // packed weight bytes of one split
   uint32_t off_ss, off_w, off_a, stage_bytes, off_epi, epi_pitch;
   uint32_t cpp, cpp_magic, halow_magic, cpo_magic;   // chunks per input pixel (cin/8) and exact-division magics
+  int layout;            // TapLayout
+  int halo_pitch;        // LAYOUT_SWZ: pixels per window row in shared memory (halo_w, or 16)
+  int desc_mode;         // LAYOUT_SWZ: bit0 = put (start>>7)&7 into the descriptor's base_offset field
+  int nkb;               // LAYOUT_SWZ: k-blocks (64 channels each, a 32-channel tail when cin%64==32)
+  uint32_t kb_off[kMaxKBlocks];   // byte offset of each k-block inside a stage (1024-aligned)
+  uint32_t tx_bytes;     // bytes one stage fill delivers
   TapEntry taps[kMaxTaps];
 };
 
@@ -61,6 +77,7 @@ struct TapConvLayer {
   int ntaps = 0, ktotal16 = 0;
   int halo_y0 = 0, halo_x0 = 0, halo_h = 0, halo_w = 0;
   int epi_mode = 0, out_s2d = 0;
+  int layout = 0, halo_pitch = 0, desc_mode = 0;
   TapEntry taps[kMaxTaps];
   void* w = nullptr;      // device
   float* shift = nullptr; // device

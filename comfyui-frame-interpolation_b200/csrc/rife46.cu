@@ -46,43 +46,24 @@ uint16_t to_operand(float v, int op_type) {
   return u;
 }
 
+// Packed weights = the SWIZZLE_128B K-major UMMA B operand, bit for bit: [split][K16/4 (padded)][n][128-byte row of
+// four K=16 steps], 16-byte chunks XOR-swizzled with (n & 7); bulk-copied to shared memory verbatim.
 template <class F>
 std::vector<uint16_t> pack_weights(const TapConvLayer& L, int op_type, F wfun) {
-  if (L.layout == LAYOUT_SWZ) {
-    // [split][K16/4 (padded)][n][128-byte row = four K=16 steps], 16-byte chunks XOR-swizzled with (n & 7): the
-    // SWIZZLE_128B K-major UMMA operand, copied to shared memory verbatim
-    const size_t per_split = (size_t)((L.ktotal16 + 3) / 4) * L.n_cta * 64;
-    std::vector<uint16_t> v((size_t)L.nsplit * per_split, 0);
-    for (int sp = 0; sp < L.nsplit; ++sp) {
-      int j = 0;
-      for (int e = 0; e < L.ntaps; ++e)
-        for (int i = 0; i < L.taps[e].nk16; ++i, ++j)
-          for (int c = 0; c < 16; ++c) {
-            const int chunk = (j & 3) * 2 + (c >> 3);
-            for (int nl = 0; nl < L.n_cta; ++nl) {
-              const float val = wfun(e, i * 16 + c, sp * L.n_cta + nl);
-              v[sp * per_split + ((size_t)(j >> 2) * L.n_cta + nl) * 64 + (size_t)((chunk ^ (nl & 7)) * 8 + (c & 7))] =
-                  to_operand(val, op_type);
-            }
-          }
-    }
-    return v;
-  }
-  const size_t per_split = (size_t)L.ktotal16 * 2 * L.n_cta * 8;
+  const size_t per_split = (size_t)((L.ktotal16 + 3) / 4) * L.n_cta * 64;
   std::vector<uint16_t> v((size_t)L.nsplit * per_split, 0);
   for (int sp = 0; sp < L.nsplit; ++sp) {
     int j = 0;
-    for (int e = 0; e < L.ntaps; ++e) {
-      for (int i = 0; i < L.taps[e].nk16; ++i, ++j) {
+    for (int e = 0; e < L.ntaps; ++e)
+      for (int i = 0; i < L.taps[e].nk16; ++i, ++j)
         for (int c = 0; c < 16; ++c) {
-          const int kk = j * 2 + (c >> 3);
+          const int chunk = (j & 3) * 2 + (c >> 3);
           for (int nl = 0; nl < L.n_cta; ++nl) {
             const float val = wfun(e, i * 16 + c, sp * L.n_cta + nl);
-            v[sp * per_split + ((size_t)kk * L.n_cta + nl) * 8 + (c & 7)] = to_operand(val, op_type);
+            v[sp * per_split + ((size_t)(j >> 2) * L.n_cta + nl) * 64 + (size_t)((chunk ^ (nl & 7)) * 8 + (c & 7))] =
+                to_operand(val, op_type);
           }
         }
-      }
-    }
   }
   return v;
 }
@@ -141,8 +122,6 @@ struct vfi_ctx {
   int num_sms = 148;
   int batch = 8;
   int op_type = OP_F16;
-  int layout = 0;     // TapLayout of the conv kernels (VFI_TAPCONV_LAYOUT)
-  int desc_mode = 0;  // VFI_TMA_MODE: bit0 base_offset in descriptors, bit1 16-pixel window pitch
   bool loaded = false;
   int64_t launches = 0;
   TapConvLayer layers[4][11];  // [block][0=conv0.0, 1=conv0.1, 2..9=ResConv, 10=lastconv]
@@ -214,7 +193,6 @@ int build_conv_s2(vfi_ctx* c, TapConvLayer& L, int Cs, int creal, int cout, int 
       t.chunk0 = (int16_t)(((a * 2 + b) * Cs) / 8);
       t.nk16 = (int16_t)(Cs / 16);
     }
-  L.layout = c->layout; L.desc_mode = c->desc_mode; L.halo_pitch = (c->desc_mode & 2) ? 16 : 0;
   choose_split(L, {1, 2, 3, 4, 6, 8, 12}, 2);
   auto wf = [&](int e, int ci, int n) -> float {
     if (ci >= creal) return 0.f;
@@ -242,7 +220,6 @@ int build_resconv(vfi_ctx* c, TapConvLayer& L, int ch, const float* beta, const 
       TapEntry& t = L.taps[ky * 3 + kx];
       t.dy = (int16_t)(ky - 1); t.dx = (int16_t)(kx - 1); t.chunk0 = 0; t.nk16 = (int16_t)(ch / 16);
     }
-  L.layout = c->layout; L.desc_mode = c->desc_mode; L.halo_pitch = (c->desc_mode & 2) ? 16 : 0;
   choose_split(L, {1, 2, 3, 4, 6, 8, 12}, 3);
   // (conv(x) + b) * beta + x  ==  conv_{w*beta}(x) + b*beta + x : beta is folded into the packed weights (one 16-bit
   // rounding of w*beta instead of w) so the epilogue is a pure add
@@ -274,7 +251,6 @@ int build_lastconv(vfi_ctx* c, TapConvLayer& L, int ch, const float* wt, const f
       TapEntry& t = L.taps[ky * 3 + kx];
       t.dy = (int16_t)(ky - 1); t.dx = (int16_t)(kx - 1); t.chunk0 = 0; t.nk16 = (int16_t)(ch / 16);
     }
-  L.layout = c->layout; L.desc_mode = c->desc_mode; L.halo_pitch = (c->desc_mode & 2) ? 16 : 0;
   choose_split(L, {1, 5}, 2);
   auto oc_of = [](int n) {
     const int c5 = n >> 4, pos = n & 15, py = pos >> 2, px = pos & 3;
@@ -478,8 +454,6 @@ int vfi_rife46_load(vfi_ctx* c, const float* const* T, const int64_t* numel, int
   CK(cudaSetDevice(c->device));
   free_weights(c);
   c->op_type = operand_type;
-  if (const char* e = getenv("VFI_TAPCONV_LAYOUT")) c->layout = atoi(e) ? LAYOUT_SWZ : LAYOUT_PLANES;
-  if (const char* e = getenv("VFI_TMA_MODE")) c->desc_mode = atoi(e);
   int k = 0;
   auto expect = [&](int idx, int64_t want) { return numel[idx] == want; };
   for (int b = 0; b < 4; ++b) {
@@ -687,7 +661,7 @@ int vfi_rife46_layer_plan(vfi_ctx* c, int block, int layer, int* stages, int* n_
   if (stages) *stages = st;
   if (n_cta) *n_cta = L.n_cta;
   if (nsplit) *nsplit = L.nsplit;
-  if (smem_bytes) *smem_bytes = (int)p.off_epi;
+  if (smem_bytes) *smem_bytes = (int)p.smem_bytes;
   if (macs_per_cell) *macs_per_cell = (int64_t)L.ktotal16 * 16 * L.n_total;
   return VFI_OK;
 }

@@ -29,45 +29,34 @@ struct TapEntry {
 
 constexpr int kMaxTaps = 9;
 constexpr int kTileH = 16, kTileW = 8;        // one CTA tile = 128 grid cells = UMMA M
-constexpr int kProducerThreads = 96;          // warps 1..3
 constexpr int kSmemLimit = 232448;            // 227 KB opt-in maximum per CTA on sm_100
 
-// shared-memory layout of the staged input window / weights
-enum TapLayout : int {
-  LAYOUT_PLANES = 0,  // A[chunk][pixel][8ch] no-swizzle K-major planes, filled by LDGSTS (cp.async)
-  LAYOUT_SWZ = 1,     // A[k-block][pixel][64|32 ch] 128B/64B-swizzled K-major rows, filled by TMA tensor copies
-};
 constexpr int kMaxKBlocks = 6;
 
 struct alignas(64) TapConvParams {
-  CUtensorMap tm64;      // LAYOUT_SWZ: input as [B,H,W,C] with a {64ch, pitch, halo_h, 1} box, SWIZZLE_128B
-  CUtensorMap tm32;      // LAYOUT_SWZ: same with a {32ch, ...} box, SWIZZLE_64B (only when cin % 64 == 32)
+  CUtensorMap tm64;      // input as a {C, W, H, B} tensor with a {64 ch, halo_w, halo_h, 1} box, SWIZZLE_128B
+  CUtensorMap tm32;      // same with a {32 ch, ...} box, SWIZZLE_64B (only used when cin % 64 == 32)
   const void* in;        // [B, H, W, cin] 16-bit, NHWC
   void* out;             // [B, H, W, n_total] 16-bit NHWC, or its space-to-depth form when out_s2d
   float4* out_flow;      // EPI_LASTCONV: [B, 4H, 4W] float4 (4 flow components)
   float* out_mask;       // EPI_LASTCONV: [B, 4H, 4W]
-  const void* w;         // packed weights: [nsplit][2*ktotal16][n_cta][8] 16-bit
+  const void* w;         // packed weights: [nsplit][ceil(K16/4)][n_cta][128 B swizzled row] 16-bit
   const float* shift;    // [n_total]
   int B, H, W, cin;
   int n_total, n_cta, nsplit;
   int ntaps, ktotal16;
-  int halo_y0, halo_x0, halo_h, halo_w, halo_px;
-  int plane_bytes;       // bytes of one 8-channel plane of an A stage: odd multiple of 16 >= 16*halo_px
+  int halo_y0, halo_x0, halo_h, halo_w;
   int stages;
   int epi_mode, out_s2d;
   int tiles_x, tiles_y, ntiles;
   int ctas_per_split;
   uint32_t idesc;
   uint32_t tmem_cols, acc_stride;
-  uint32_t w_bytes;             // packed weight bytes of one split
-  uint32_t off_ss, off_w, off_a, stage_bytes, off_epi, epi_pitch;
-  uint32_t cpp, cpp_magic, halow_magic, cpo_magic;   // chunks per input pixel (cin/8) and exact-division magics
-  int layout;            // TapLayout
-  int halo_pitch;        // LAYOUT_SWZ: pixels per window row in shared memory (halo_w, or 16)
-  int desc_mode;         // LAYOUT_SWZ: bit0 = put (start>>7)&7 into the descriptor's base_offset field
-  int nkb;               // LAYOUT_SWZ: k-blocks (64 channels each, a 32-channel tail when cin%64==32)
+  uint32_t w_bytes;               // packed weight bytes of one split
+  uint32_t off_ss, off_w, off_a, stage_bytes, smem_bytes;
+  int nkb;                        // k-blocks of the staged window: 64 channels each, 32-channel tail if cin%64==32
   uint32_t kb_off[kMaxKBlocks];   // byte offset of each k-block inside a stage (1024-aligned)
-  uint32_t tx_bytes;     // bytes one stage fill delivers
+  uint32_t tx_bytes;              // bytes one stage fill delivers (mbarrier transaction count)
   TapEntry taps[kMaxTaps];
 };
 
@@ -77,7 +66,6 @@ struct TapConvLayer {
   int ntaps = 0, ktotal16 = 0;
   int halo_y0 = 0, halo_x0 = 0, halo_h = 0, halo_w = 0;
   int epi_mode = 0, out_s2d = 0;
-  int layout = 0, halo_pitch = 0, desc_mode = 0;
   TapEntry taps[kMaxTaps];
   void* w = nullptr;      // device
   float* shift = nullptr; // device

@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvfi_b200.so")
-SOURCES = ["tapconv.cu", "elementwise.cu", "rife46.cu"]
+SOURCES = ["tapconv.cu", "elementwise.cu", "ops.cu", "rife46.cu"]
 HEADERS = ["ptx.cuh", "vfi_internal.h", os.path.join("..", "..", "include", "vfi_b200.h")]
 
 
@@ -26,7 +26,7 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+           "--threads", "4", "-Xcompiler", "-fPIC", "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

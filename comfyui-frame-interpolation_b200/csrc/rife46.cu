@@ -613,6 +613,39 @@ int vfi_warp_bilinear_border(vfi_ctx* c, const float* img, const float* flow, fl
   return VFI_OK;
 }
 
+int vfi_softsplat_sum(vfi_ctx* c, const float* in, const float* flow, float* out, int N, int C, int H, int W,
+                      void* stream) {
+  if (!c || !in || !flow || !out || N < 1 || C < 1 || H < 1 || W < 1) return fail(VFI_E_INVALID, "bad argument");
+  CK(cudaSetDevice(c->device));
+  LAUNCH(launch_softsplat_sum(in, flow, out, N, C, H, W, (cudaStream_t)stream));
+  return VFI_OK;
+}
+
+int vfi_costvol_l1(vfi_ctx* c, const float* one, const float* two, float* out, int N, int C, int H, int W,
+                   void* stream) {
+  if (!c || !one || !two || !out || N < 1 || C < 1 || H < 1 || W < 1) return fail(VFI_E_INVALID, "bad argument");
+  CK(cudaSetDevice(c->device));
+  LAUNCH(launch_volume81(false, one, two, out, N, C, H, W, (cudaStream_t)stream));
+  return VFI_OK;
+}
+
+int vfi_corr_dot(vfi_ctx* c, const float* first, const float* second, float* out, int N, int C, int H, int W,
+                 void* stream) {
+  if (!c || !first || !second || !out || N < 1 || C < 1 || H < 1 || W < 1) return fail(VFI_E_INVALID, "bad argument");
+  CK(cudaSetDevice(c->device));
+  LAUNCH(launch_volume81(true, first, second, out, N, C, H, W, (cudaStream_t)stream));
+  return VFI_OK;
+}
+
+int vfi_sepconv(vfi_ctx* c, const float* in, const float* ver, const float* hor, float* out, int N, int C, int H,
+                int W, int Kv, int Kh, void* stream) {
+  if (!c || !in || !ver || !hor || !out || N < 1 || C < 1 || H < 1 || W < 1 || Kv < 1 || Kh < 1)
+    return fail(VFI_E_INVALID, "bad argument");
+  CK(cudaSetDevice(c->device));
+  LAUNCH(launch_sepconv(in, ver, hor, out, N, C, H, W, Kv, Kh, (cudaStream_t)stream));
+  return VFI_OK;
+}
+
 int vfi_rife46_debug_layer(vfi_ctx* c, int block, int layer, const void* in, void* out, void* out_mask, int B, int H,
                            int W, int impl, void* stream) {
   if (!c || block < 0 || block > 3 || layer < 0 || layer > 10 || !in || !out) return fail(VFI_E_INVALID, "bad argument");

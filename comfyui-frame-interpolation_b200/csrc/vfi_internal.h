@@ -106,6 +106,13 @@ cudaError_t launch_final(const float4* imgs, const FlowState& fs, int lo, const 
                          BatchTasks tasks, int Hp, int Wp, int H, int W, float* out, cudaStream_t st);
 cudaError_t launch_warp(const float* img, const float* flow, float* out, int B, int H, int W, int C, cudaStream_t st);
 
+cudaError_t launch_softsplat_sum(const float* in, const float* flow, float* out, int N, int C, int H, int W,
+                                 cudaStream_t st);
+cudaError_t launch_volume81(bool dot, const float* one, const float* two, float* out, int N, int C, int H, int W,
+                            cudaStream_t st);
+cudaError_t launch_sepconv(const float* in, const float* ver, const float* hor, float* out, int N, int C, int H, int W,
+                           int Kv, int Kh, cudaStream_t st);
+
 void set_error(const std::string& s);
 
 }  // namespace vfi

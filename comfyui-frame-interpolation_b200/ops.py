@@ -1,0 +1,159 @@
+"""Op-level surface of the reference's `vfi_models.ops` package (vfi_models/ops/__init__.py:19-21), backed by the
+ahead-of-time sm_100a kernels in libvfi_b200.so instead of cupy/NVRTC or taichi.  Same names, argument meaning and
+tensor contract (CUDA float32 NCHW); inference only - the reference's backward kernels (training) are out of scope.
+There is no CPU path: CPU tensors raise.
+"""
+import ctypes as C
+
+import torch
+
+from ._lib import VfiError, check, lib
+
+_ctx = {}
+
+
+def _context(device: torch.device):
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _ctx:
+        h = C.c_void_p()
+        check(lib().vfi_create(idx, C.byref(h)))
+        _ctx[idx] = h
+    return _ctx[idx]
+
+
+def _prep(*ts):
+    out = []
+    for t in ts:
+        if not t.is_cuda:
+            raise VfiError("vfi ops need CUDA tensors (no CPU fallback)")
+        out.append(t.to(torch.float32).contiguous())  # reference: @custom_fwd(cast_inputs=torch.float32)
+    return out
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def init():
+    """Reference: cupy_ops.init() warms the NVRTC cache; nothing to compile here."""
+    return None
+
+
+class softsplat_func:
+    """cupy_ops/softsplat.py:195-224 (forward only)."""
+
+    @staticmethod
+    def apply(tenIn, tenFlow):
+        tenIn, tenFlow = _prep(tenIn, tenFlow)
+        n, c, h, w = tenIn.shape
+        assert tuple(tenFlow.shape) == (n, 2, h, w)
+        out = torch.empty_like(tenIn)
+        check(lib().vfi_softsplat_sum(_context(tenIn.device), tenIn.data_ptr(), tenFlow.data_ptr(), out.data_ptr(),
+                                      n, c, h, w, _stream(tenIn)))
+        return out
+
+
+def softsplat(tenIn, tenFlow, tenMetric, strMode: str):
+    """cupy_ops/softsplat.py:382-435."""
+    assert strMode.split("-")[0] in ["sum", "avg", "linear", "soft"]
+    if strMode == "sum":
+        assert tenMetric is None
+    if strMode == "avg":
+        assert tenMetric is None
+    if strMode.split("-")[0] == "linear":
+        assert tenMetric is not None
+    if strMode.split("-")[0] == "soft":
+        assert tenMetric is not None
+    if strMode == "avg":
+        tenIn = torch.cat([tenIn, tenIn.new_ones([tenIn.shape[0], 1, tenIn.shape[2], tenIn.shape[3]])], 1)
+    elif strMode.split("-")[0] == "linear":
+        tenIn = torch.cat([tenIn * tenMetric, tenMetric], 1)
+    elif strMode.split("-")[0] == "soft":
+        tenIn = torch.cat([tenIn * tenMetric.exp(), tenMetric.exp()], 1)
+    tenOut = softsplat_func.apply(tenIn, tenFlow)
+    if strMode.split("-")[0] in ["avg", "linear", "soft"]:
+        tenNormalize = tenOut[:, -1:, :, :]
+        if len(strMode.split("-")) == 1:
+            tenNormalize = tenNormalize + 0.0000001
+        elif strMode.split("-")[1] == "addeps":
+            tenNormalize = tenNormalize + 0.0000001
+        elif strMode.split("-")[1] == "zeroeps":
+            tenNormalize[tenNormalize == 0.0] = 1.0
+        elif strMode.split("-")[1] == "clipeps":
+            tenNormalize = tenNormalize.clip(0.0000001, None)
+        tenOut = tenOut[:, :-1, :, :] / tenNormalize
+    return tenOut
+
+
+def FunctionSoftsplat(tenInput, tenFlow, tenMetric, strType):
+    """cupy_ops/softsplat.py:325-358 (older spelling used by EISAI): summation / average / linear / softmax."""
+    mode = {"summation": "sum", "average": "avg", "linear": "linear", "softmax": "soft"}[strType]
+    return softsplat(tenInput, tenFlow, tenMetric, mode)
+
+
+class ModuleSoftsplat(torch.nn.Module):
+    def __init__(self, strType):
+        super().__init__()
+        self.strType = strType
+
+    def forward(self, tenInput, tenFlow, tenMetric):
+        return FunctionSoftsplat(tenInput, tenFlow, tenMetric, self.strType)
+
+
+class costvol_func:
+    """cupy_ops/costvol.py:135-179 (forward only): [N,C,H,W] x2 -> [N,81,H,W]."""
+
+    @staticmethod
+    def apply(tenOne, tenTwo):
+        tenOne, tenTwo = _prep(tenOne, tenTwo)
+        n, c, h, w = tenOne.shape
+        out = tenOne.new_empty([n, 81, h, w])
+        check(lib().vfi_costvol_l1(_context(tenOne.device), tenOne.data_ptr(), tenTwo.data_ptr(), out.data_ptr(),
+                                   n, c, h, w, _stream(tenOne)))
+        return out
+
+
+class sepconv_func:
+    """cupy_ops/sepconv.py:155-190 (forward only): in [N,C,H+Kv-1,W+Kh-1], ver [N,Kv,H,W], hor [N,Kh,H,W]."""
+
+    @staticmethod
+    def apply(tenIn, tenVer, tenHor):
+        tenIn, tenVer, tenHor = _prep(tenIn, tenVer, tenHor)
+        n, c = tenIn.shape[:2]
+        kv, kh = tenVer.shape[1], tenHor.shape[1]
+        h, w = tenVer.shape[2], tenVer.shape[3]
+        assert tenIn.shape[2] == h + kv - 1 and tenIn.shape[3] == w + kh - 1 and tuple(tenHor.shape[2:]) == (h, w)
+        out = tenIn.new_empty([n, c, h, w])
+        check(lib().vfi_sepconv(_context(tenIn.device), tenIn.data_ptr(), tenVer.data_ptr(), tenHor.data_ptr(),
+                                out.data_ptr(), n, c, h, w, kv, kh, _stream(tenIn)))
+        return out
+
+
+class _FunctionCorrelation:
+    """cupy_ops/correlation.py:231-296 (forward only)."""
+
+    @staticmethod
+    def apply(first, second):
+        first, second = _prep(first, second)
+        n, c, h, w = first.shape
+        out = first.new_empty([n, 81, h, w])
+        check(lib().vfi_corr_dot(_context(first.device), first.data_ptr(), second.data_ptr(), out.data_ptr(),
+                                 n, c, h, w, _stream(first)))
+        return out
+
+
+def FunctionCorrelation(tenFirst, tenSecond):
+    return _FunctionCorrelation.apply(tenFirst, tenSecond)
+
+
+class ModuleCorrelation(torch.nn.Module):
+    def forward(self, tenFirst, tenSecond):
+        return _FunctionCorrelation.apply(tenFirst, tenSecond)
+
+
+def batch_edt(*a, **k):
+    raise NotImplementedError("batch_edt: only used by the unregistered EISAI node (SURVEY.md 2.1); not built")
+
+
+def FunctionAdaCoF(*a, **k):
+    raise NotImplementedError("FunctionAdaCoF: ST-MFNet only (4-frame model, out of scope, SURVEY.md 2.1)")

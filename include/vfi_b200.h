@@ -80,6 +80,22 @@ int vfi_rife46_interpolate_host(vfi_ctx* ctx, const float* frames, int n_frames,
 int vfi_warp_bilinear_border(vfi_ctx* ctx, const float* img, const float* flow, float* out, int B, int H, int W, int C,
                              void* stream);
 
+/* Op-level surface of vfi_models/ops (the names the reference's models import, vfi_models/ops/__init__.py:19-21).
+ * DEVICE pointers, contiguous NCHW float32 exactly like the reference's cupy launches (cupy_ops/softsplat.py:206-224).
+ *   vfi_softsplat_sum : softsplat_out (cupy_ops/softsplat.py:140-192): out[N,C,H,W] (zeroed here) += forward splat of in
+ *                       along flow [N,2,H,W]; the avg/linear/soft modes are host-side arithmetic around it (:382-435)
+ *   vfi_costvol_l1    : costvol_out (cupy_ops/costvol.py:4-43): out[N,81,H,W] = mean_c |one - two(+-4 shifted)|
+ *   vfi_corr_dot      : kernel_Correlation_updateOutput (cupy_ops/correlation.py:31-99): out[N,81,H,W], zero padded
+ *   vfi_sepconv       : sepconv_out (cupy_ops/sepconv.py:86-117): in [N,C,H+Kv-1,W+Kh-1], ver [N,Kv,H,W], hor [N,Kh,H,W] */
+int vfi_softsplat_sum(vfi_ctx* ctx, const float* in, const float* flow, float* out, int N, int C, int H, int W,
+                      void* stream);
+int vfi_costvol_l1(vfi_ctx* ctx, const float* one, const float* two, float* out, int N, int C, int H, int W,
+                   void* stream);
+int vfi_corr_dot(vfi_ctx* ctx, const float* first, const float* second, float* out, int N, int C, int H, int W,
+                 void* stream);
+int vfi_sepconv(vfi_ctx* ctx, const float* in, const float* ver, const float* hor, float* out, int N, int C, int H,
+                int W, int Kv, int Kh, void* stream);
+
 /* Test / profiling hooks (used by tests/ and bench.py only) --------------------------------------------- */
 /* Run ONE convolution layer of block `block` (0..3): layer 0 = conv0.0, 1 = conv0.1, 2..9 = ResConv 0..7,
  * 10 = lastconv.  `in`/`out` are device tensors in the kernel-native layouts documented in DESIGN.md

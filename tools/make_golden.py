@@ -61,6 +61,29 @@ def cases():
     }
 
 
+def loop_cases():
+    """generic_frame_loop cases (vfi_utils.py:339-389) with a stand-in model function; shared with the tests."""
+    return {
+        "loop_ts_m3_skip": dict(n=5, multiplier=3, states=([1, 3], True), use_timestep=True),
+        "loop_bisect_m4": dict(n=3, multiplier=4, states=None, use_timestep=False),
+        "loop_bisect_m7_keep": dict(n=4, multiplier=7, states=([0, 2], False), use_timestep=False),
+        "loop_list": dict(n=5, multiplier=[3, 0, 2], states=([0], False), use_timestep=True),
+        "loop_list_bisect": dict(n=4, multiplier=[2, 5], states=None, use_timestep=False),
+    }
+
+
+def loop_model(f0, f1, t, gain):
+    """Stand-in for a model's middle-frame function: order sensitive, timestep sensitive."""
+    if t is None:
+        return 0.5 * (f0 + f1) + gain * (f1 - f0).abs()
+    return (1 - t) * f0 + t * f1 + gain * t * t
+
+
+def loop_frames(n):
+    g = torch.Generator().manual_seed(100 + n)
+    return torch.rand(n, 3, 6, 8, generator=g)
+
+
 def make_inputs(cfg):
     if cfg["kind"] == "ifnet":
         if cfg["clip_seed"] < 0:
@@ -108,6 +131,13 @@ def main():
                 (out,) = R.RIFE_VFI().vfi("rife46.pth", fr, multiplier=cfg["multiplier"],
                                           optional_interpolation_states=st)
             np.savez_compressed(os.path.join(out_dir, name + ".npz"), out=out.numpy())
+        print(name, tuple(out.shape), float(out.mean()))
+    import vfi_utils as VU
+    for name, cfg in loop_cases().items():
+        st = None if cfg["states"] is None else InterpolationStateList(list(cfg["states"][0]), cfg["states"][1])
+        out = VU.generic_frame_loop("Stand_In_VFI", loop_frames(cfg["n"]), 10, cfg["multiplier"], loop_model, 0.03,
+                                    interpolation_states=st, use_timestep=cfg["use_timestep"], dtype=torch.float32)
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"), out=out.numpy())
         print(name, tuple(out.shape), float(out.mean()))
 
 

@@ -42,7 +42,6 @@ struct Ctrl {
   uint32_t tmem_base;
 };
 constexpr uint32_t kCtrlBytes = 256;
-constexpr uint32_t kTabBytes = 8192;  // descriptor table: stages x K=16 steps x {a_lo, a_hi, b_lo, b_hi}
 static_assert(sizeof(Ctrl) <= kCtrlBytes, "control block");
 
 __device__ __forceinline__ size_t out_pixel_offset(const TapConvParams& p, int b, int gy, int gx) {
@@ -53,6 +52,20 @@ __device__ __forceinline__ size_t out_pixel_offset(const TapConvParams& p, int b
     return cell * (size_t)(4 * p.n_total) + (size_t)(((gy & 1) * 2 + (gx & 1)) * p.n_total);
   }
   return (((size_t)b * p.H + gy) * p.W + gx) * (size_t)p.n_total;
+}
+
+// One tile's MMAs.  K16 is a compile-time constant so that every p.mma[j] is a fixed constant-bank address: the
+// descriptor words reach the tensor core through uniform loads / uniform adds only (ncu r01: with a table in shared
+// memory, or a run-time index into the parameters, every operand went LDS/LDC -> vector register -> R2UR and the
+// issuing warp needed ~15 instructions, ~90 cycles, per MMA).
+template <int K16>
+__device__ __forceinline__ void issue_mmas(const TapConvParams& p, uint32_t d_tmem, uint32_t a_lo0, uint32_t b_lo0,
+                                           uint32_t b_hi, uint32_t idesc) {
+#pragma unroll
+  for (int j = 0; j < K16; ++j) {
+    const uint4 d = p.mma[j];
+    umma_f16_split(d_tmem, a_lo0 + d.x, d.y, b_lo0 + d.z, b_hi, idesc, j > 0 ? 1u : 0u);
+  }
 }
 
 template <typename T>
@@ -90,36 +103,6 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
     }
     mbar_fence_init();
   }
-  // Descriptor table, built once: for every (stage, K=16 step) the A and B shared-memory descriptors, so the MMA
-  // issue loop is "load 16 bytes, issue" (ncu r01: the issuing warp was the bottleneck when it computed them).
-  {
-    uint4* tab = reinterpret_cast<uint4*>(smem + kCtrlBytes);
-    const int K16 = p.ktotal16;
-    for (int id = threadIdx.x; id < S * K16; id += blockDim.x) {
-      const int st = id / K16;
-      int j = id - st * K16, e = 0;
-      const int jj = j;
-      while (j >= p.taps[e].nk16) {
-        j -= p.taps[e].nk16;
-        ++e;
-      }
-      const TapEntry te = p.taps[e];
-      const int ch0 = te.chunk0 * 8 + 16 * j;  // first input channel of this step
-      const int kb = ch0 >> 6;
-      const bool tail = has_tail && (kb == p.nkb - 1);
-      const uint32_t rowb = tail ? 64u : 128u;
-      const uint32_t a_addr = a_smem + (uint32_t)st * p.stage_bytes + p.kb_off[kb] +
-                              (uint32_t)((te.dy - p.halo_y0) * p.halo_w + (te.dx - p.halo_x0)) * rowb +
-                              (uint32_t)(ch0 - kb * 64) * 2u;
-      const uint32_t b_addr = w_smem + (uint32_t)(jj >> 2) * ((uint32_t)p.n_cta * 128u) + (uint32_t)(jj & 3) * 32u;
-      uint4 d;  // cute/arch/mma_sm100_desc.hpp: lo = start>>4 | LBO(=1)<<16 ; hi = SBO>>4 | version<<14 | layout<<29
-      d.x = ((a_addr >> 4) & 0x3FFFu) | (1u << 16);
-      d.y = (((uint32_t)p.halo_w * rowb) >> 4) | (1u << 14) | ((tail ? 4u : 2u) << 29);  // SWIZZLE_64B : SWIZZLE_128B
-      d.z = ((b_addr >> 4) & 0x3FFFu) | (1u << 16);
-      d.w = (1024u >> 4) | (1u << 14) | (2u << 29);
-      tab[id] = d;
-    }
-  }
   if (warp == 0) tmem_alloc(smem_base + offsetof(Ctrl, tmem_base), p.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -132,9 +115,10 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
     // The whole warp runs the (warp-uniform) control flow; one elected lane issues tcgen05.mma / tcgen05.commit.
     const uint32_t leader = elect_one_sync();
     mbar_wait(bar_w, 0, 1);
-    const uint4* tab0 = reinterpret_cast<const uint4*>(smem + kCtrlBytes);
     const int K16 = p.ktotal16;
     const uint32_t idesc = p.idesc;
+    const uint32_t b_lo0 = (1u << 16) | (w_smem >> 4);  // LBO(=1) | start address, 16-byte units
+    const uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO | version | SWIZZLE_128B
     uint32_t k = 0;
     for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k) {
       const uint32_t stage = k % S, use = k / S, acc = k & 1, vuse = k >> 1;
@@ -142,26 +126,17 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
       mbar_wait(bar_afull + 8 * stage, use & 1, 3);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
-      const uint4* tab = tab0 + stage * K16;
-      // K16 is a multiple of 9 for every layer: issue in groups of nine, the next group's descriptors are fetched
-      // into registers before the current group is issued, so shared-memory latency never sits between two MMAs
-      // (ncu r01 v2: the issuing warp spent ~140 cycles per MMA; now 4-5 SASS instructions).
-      uint4 cur[9], nxt[9];
-#pragma unroll
-      for (int i = 0; i < 9; ++i) cur[i] = tab[i];
-      const int ngroups = K16 / 9;
-      for (int g = 0; g < ngroups; ++g) {
-        if (g + 1 < ngroups) {
-#pragma unroll
-          for (int i = 0; i < 9; ++i) nxt[i] = tab[(g + 1) * 9 + i];
+      const uint32_t a_lo0 = (1u << 16) | ((a_smem + stage * p.stage_bytes) >> 4);
+      if (leader) {
+        switch (K16) {  // fully unrolled issue sequences: descriptor offsets become constant-bank operands
+          case 9: issue_mmas<9>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
+          case 18: issue_mmas<18>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
+          case 27: issue_mmas<27>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
+          case 36: issue_mmas<36>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
+          case 54: issue_mmas<54>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
+          case 72: issue_mmas<72>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
+          default: issue_mmas<108>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
         }
-        if (leader) {
-          umma_f16_split(d_tmem, cur[0].x, cur[0].y, cur[0].z, cur[0].w, idesc, g > 0 ? 1u : 0u);
-#pragma unroll
-          for (int i = 1; i < 9; ++i) umma_f16_split(d_tmem, cur[i].x, cur[i].y, cur[i].z, cur[i].w, idesc, 1u);
-        }
-#pragma unroll
-        for (int i = 0; i < 9; ++i) cur[i] = nxt[i];
       }
       if (leader) {
         if (!residual) umma_commit(bar_aempty + 8 * stage);  // window free once the MMAs have read it
@@ -462,7 +437,11 @@ int tapconv_plan(const TapConvLayer& L, TapConvParams* pp) {
   p.w_bytes = (uint32_t)((L.ktotal16 + 3) / 4) * (uint32_t)L.n_cta * 128u;
   // input window: one 1024-aligned region per k-block (64 channels = 128-byte rows; 32-channel tail = 64-byte rows)
   p.nkb = (L.cin + 63) / 64;
-  if (p.nkb > kMaxKBlocks || L.n_cta > 96 || (L.n_cta & 15) || (L.ktotal16 % 9)) return 0;
+  {
+    const int k = L.ktotal16;  // the unrolled issue sequences the kernel has
+    if (!(k == 9 || k == 18 || k == 27 || k == 36 || k == 54 || k == 72 || k == 108)) return 0;
+  }
+  if (p.nkb > kMaxKBlocks || L.n_cta > 96 || (L.n_cta & 15)) return 0;
   uint32_t off = 0;
   p.tx_bytes = 0;
   for (int kb = 0; kb < p.nkb; ++kb) {
@@ -473,7 +452,25 @@ int tapconv_plan(const TapConvLayer& L, TapConvParams* pp) {
     p.tx_bytes += bytes;
   }
   p.stage_bytes = off;
-  p.off_ss = kCtrlBytes + kTabBytes;
+  {
+    // descriptor words per K=16 step (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14) | LBO [16,30) ; SBO>>4 [32,46) |
+    // version=1 [46,48) | layout [61,64) (2 = SWIZZLE_128B, 4 = SWIZZLE_64B); base_offset stays 0
+    int j = 0;
+    for (int e = 0; e < L.ntaps; ++e)
+      for (int i = 0; i < L.taps[e].nk16; ++i, ++j) {
+        const TapEntry te = L.taps[e];
+        const int ch0 = te.chunk0 * 8 + 16 * i;
+        const int kb = ch0 >> 6;
+        const bool tail = (kb == p.nkb - 1) && (L.cin & 63);
+        const uint32_t rowb = tail ? 64u : 128u;
+        const uint32_t a_off = p.kb_off[kb] + (uint32_t)((te.dy - L.halo_y0) * L.halo_w + (te.dx - L.halo_x0)) * rowb +
+                               (uint32_t)(ch0 - kb * 64) * 2u;
+        const uint32_t b_off = (uint32_t)(j >> 2) * ((uint32_t)L.n_cta * 128u) + (uint32_t)(j & 3) * 32u;
+        p.mma[j] = make_uint4(a_off >> 4, (((uint32_t)L.halo_w * rowb) >> 4) | (1u << 14) | ((tail ? 4u : 2u) << 29),
+                              b_off >> 4, 0u);
+      }
+  }
+  p.off_ss = kCtrlBytes;
   p.off_w = align_up(p.off_ss + (uint32_t)L.n_cta * 4u, 1024);
   p.off_a = align_up(p.off_w + p.w_bytes, 1024);
   int stages = 0;
@@ -483,8 +480,6 @@ int tapconv_plan(const TapConvLayer& L, TapConvParams* pp) {
       break;
     }
   }
-  while (stages > 1 && stages * L.ktotal16 > (int)(kTabBytes / 16)) --stages;  // descriptor table capacity
-  if (stages * L.ktotal16 > (int)(kTabBytes / 16)) stages = 0;
   p.stages = stages;
   p.smem_bytes = p.off_a + (uint32_t)stages * p.stage_bytes;
   // accumulators: two buffers of n_cta fp32 columns, allocation is a power of two >= 32

@@ -32,6 +32,7 @@ constexpr int kTileH = 16, kTileW = 8;        // one CTA tile = 128 grid cells =
 constexpr int kSmemLimit = 232448;            // 227 KB opt-in maximum per CTA on sm_100
 
 constexpr int kMaxKBlocks = 6;
+constexpr int kMaxK16 = 108;   // 9 taps x 192/16
 
 struct alignas(64) TapConvParams {
   CUtensorMap tm64;      // input as a {C, W, H, B} tensor with a {64 ch, halo_w, halo_h, 1} box, SWIZZLE_128B
@@ -58,6 +59,10 @@ struct alignas(64) TapConvParams {
   uint32_t kb_off[kMaxKBlocks];   // byte offset of each k-block inside a stage (1024-aligned)
   uint32_t tx_bytes;              // bytes one stage fill delivers (mbarrier transaction count)
   TapEntry taps[kMaxTaps];
+  // per K=16 step: {A start offset inside a stage, A descriptor high word, B start offset inside the weights, 0},
+  // offsets in 16-byte units.  Lives in the kernel parameters (constant bank) so that the MMA-issuing warp gets it
+  // through uniform loads straight into uniform registers.
+  uint4 mma[kMaxK16];
 };
 
 // A convolution layer bound to its packed weights.

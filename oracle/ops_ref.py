@@ -79,7 +79,8 @@ def costvol_l1(one: torch.Tensor, two: torch.Tensor) -> torch.Tensor:
             shifted = torch.zeros_like(two)
             ys0, ys1 = max(0, -dy), min(h, h - dy)
             xs0, xs1 = max(0, -dx), min(w, w - dx)
-            shifted[:, :, ys0:ys1, xs0:xs1] = two[:, :, ys0 + dy:ys1 + dy, xs0 + dx:xs1 + dx]
+            if ys1 > ys0 and xs1 > xs0:
+                shifted[:, :, ys0:ys1, xs0:xs1] = two[:, :, ys0 + dy:ys1 + dy, xs0 + dx:xs1 + dx]
             # outside: shifted == 0 so |one - 0| = |one|, exactly the reference's else-branch
             out[:, k] = (one - shifted).abs().sum(1) / c
             k += 1

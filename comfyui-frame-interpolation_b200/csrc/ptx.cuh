@@ -45,8 +45,9 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
   if (mbar_try_wait(bar, parity)) return;
   const uint64_t t0 = globaltimer_ns();
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (globaltimer_ns() - t0 > 2000000000ull) {
+    if ((++polls & 1023u) == 0 && globaltimer_ns() - t0 > 2000000000ull) {
       printf("vfi: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag, (int)blockIdx.x,
              (int)threadIdx.x, parity);
       __trap();

@@ -25,6 +25,8 @@
 //   warps 4..11 : epilogue - two sets of four warps (TMEM lane quarters 0..3), each set takes half of the
 //                 accumulator columns of EVERY tile: tcgen05.ld -> release TMEM -> +shift (+residual) -> LeakyReLU
 //                 -> 16-bit -> global stores (lastconv: the fp32 4x4 flow/mask sub-pixel patch)
+#include <cstdlib>
+
 #include "ptx.cuh"
 #include "vfi_internal.h"
 
@@ -332,6 +334,12 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
           }
           o[i][0] = make_uint4(w[0], w[1], w[2], w[3]);
           o[i][1] = make_uint4(w[4], w[5], w[6], w[7]);
+          if (p.epi_order == 0 && valid) {  // store each chunk as soon as it is ready
+            T* orow0 = reinterpret_cast<T*>(p.out) + out_pixel_offset(p, b, gy, gx) + (size_t)n0;
+            uint4* dst = reinterpret_cast<uint4*>(orow0 + (c_lo + i) * 16);
+            dst[0] = o[i][0];
+            dst[1] = o[i][1];
+          }
         }
       }
       if (residual) {
@@ -341,7 +349,7 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_aempty + 8 * stage);
       }
-      if (valid) {
+      if (valid && p.epi_order != 0) {
         // 32 contiguous bytes (16 channels) of this cell's channel vector per chunk; L2 merges the sector halves
         T* orow = reinterpret_cast<T*>(p.out) + out_pixel_offset(p, b, gy, gx) + (size_t)n0;
 #pragma unroll
@@ -532,6 +540,9 @@ int tapconv_plan(const TapConvLayer& L, TapConvParams* pp) {
   while (stride < (uint32_t)L.n_cta) stride <<= 1;
   p.acc_stride = stride;
   p.nacc = (stride * 4 <= 512) ? 4 : 2;
+  if (const char* e = getenv("VFI_NACC")) p.nacc = (atoi(e) == 4 && stride * 4 <= 512) ? 4 : 2;
+  p.epi_order = 1;
+  if (const char* e = getenv("VFI_EPI_ORDER")) p.epi_order = atoi(e);
   p.tmem_cols = stride * p.nacc < 32 ? 32 : stride * p.nacc;
   return stages;
 }

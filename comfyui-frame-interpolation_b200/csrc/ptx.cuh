@@ -30,11 +30,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
-      // suspend-time hint (ns): the thread sleeps in hardware until the phase completes instead of spinning and
-      // stealing issue slots from the working warps of its scheduler (r01: a tighter software spin cost ~15 %)
-      "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+      "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
       : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(0x989680)
+      : "r"(bar), "r"(parity)
       : "memory");
   return ok;
 }
@@ -47,9 +45,8 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
   if (mbar_try_wait(bar, parity)) return;
   const uint64_t t0 = globaltimer_ns();
-  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++polls & 1023u) == 0 && globaltimer_ns() - t0 > 2000000000ull) {
+    if (globaltimer_ns() - t0 > 2000000000ull) {
       printf("vfi: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag, (int)blockIdx.x,
              (int)threadIdx.x, parity);
       __trap();

@@ -16,7 +16,7 @@
 // unaligned start addresses and SBO = 1280 B work with base_offset = 0).  So the 3x3 window is read from L2 once
 // (x1.41 halo), not 9x as with im2col.  Weights of the CTA's output-channel slice are resident in shared memory for
 // the whole launch (one bulk copy, already in the swizzled operand layout), accumulators live in TMEM (double
-// buffered x4), the epilogue reads the ResConv residual back from the staged window instead of from global memory.
+// buffered), the epilogue reads the ResConv residual back from the staged window instead of from global memory.
 //
 // Warp roles (384 threads, 1 CTA/SM, persistent over tiles):
 //   warp 0      : TMEM alloc/dealloc; one elected lane issues tcgen05.mma + tcgen05.commit
@@ -25,8 +25,6 @@
 //   warps 4..11 : epilogue - two sets of four warps (TMEM lane quarters 0..3), each set takes half of the
 //                 accumulator columns of EVERY tile: tcgen05.ld -> release TMEM -> +shift (+residual) -> LeakyReLU
 //                 -> 16-bit -> global stores (lastconv: the fp32 4x4 flow/mask sub-pixel patch)
-#include <cstdlib>
-
 #include "ptx.cuh"
 #include "vfi_internal.h"
 
@@ -39,8 +37,8 @@ struct Ctrl {
   uint64_t w_full;
   uint64_t a_full[kMaxStages];
   uint64_t a_empty[kMaxStages];
-  uint64_t t_full[4];
-  uint64_t t_empty[4];
+  uint64_t t_full[2];
+  uint64_t t_empty[2];
   uint32_t tmem_base;
 };
 constexpr uint32_t kCtrlBytes = 256;
@@ -55,40 +53,6 @@ __device__ __forceinline__ size_t out_pixel_offset(const TapConvParams& p, int b
   }
   return (((size_t)b * p.H + gy) * p.W + gx) * (size_t)p.n_total;
 }
-
-// Walks the tiles of one CTA (t = first, first + cps, ...) keeping (image, tile row, tile column) incrementally:
-// the per-tile divisions cost the epilogue warps ~60 instructions per tile (ncu r01 v8).
-struct TileIter {
-  int b, ty, tx;      // current tile
-  int db, dy, dx;     // decomposition of the stride cps
-  int tiles_x, tiles_y;
-  __device__ __forceinline__ TileIter(const TapConvParams& p, int first) {
-    tiles_x = p.tiles_x;
-    tiles_y = p.tiles_y;
-    const int per_img = tiles_x * tiles_y;
-    b = first / per_img;
-    int rem = first - b * per_img;
-    ty = rem / tiles_x;
-    tx = rem - ty * tiles_x;
-    db = p.ctas_per_split / per_img;
-    rem = p.ctas_per_split - db * per_img;
-    dy = rem / tiles_x;
-    dx = rem - dy * tiles_x;
-  }
-  __device__ __forceinline__ void next() {
-    tx += dx;
-    ty += dy;
-    b += db;
-    if (tx >= tiles_x) {
-      tx -= tiles_x;
-      ++ty;
-    }
-    if (ty >= tiles_y) {
-      ty -= tiles_y;
-      ++b;
-    }
-  }
-};
 
 // One tile's MMAs.  K16 is a compile-time constant so that every p.mma[j] is a fixed constant-bank address: the
 // descriptor words reach the tensor core through uniform loads / uniform adds only (ncu r01: with a table in shared
@@ -115,7 +79,6 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
   const int first = blockIdx.x / p.nsplit;
   if (first >= p.ctas_per_split) return;  // whole CTA leaves together
   const int S = p.stages;
-  const uint32_t NA = p.nacc;  // TMEM accumulator buffers (2 or 4): MMAs of tile k+NA-1 overlap the epilogue of tile k
   const bool residual = (p.epi_mode == EPI_RESCONV);
 
   const uint32_t smem_base = smem_u32(smem);
@@ -134,7 +97,7 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
       mbar_init(bar_afull + 8 * s, 1);                  // producer's arrive.expect_tx (+ TMA transaction bytes)
       mbar_init(bar_aempty + 8 * s, residual ? 8 : 1);  // 8 epilogue warps, or the MMA commit
     }
-    for (int a = 0; a < 4; ++a) {
+    for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
       mbar_init(bar_tempty + 8 * a, 8);
     }
@@ -145,6 +108,7 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctrl->tmem_base;
+  const int tiles_per_img = p.tiles_y * p.tiles_x;
 
   if (warp == 0) {
     // ======================================================= MMA issuer
@@ -157,7 +121,7 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
     const uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO | version | SWIZZLE_128B
     uint32_t k = 0;
     for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k) {
-      const uint32_t stage = k % S, use = k / S, acc = k % NA, vuse = k / NA;
+      const uint32_t stage = k % S, use = k / S, acc = k & 1, vuse = k >> 1;
       mbar_wait(bar_tempty + 8 * acc, (vuse & 1) ^ 1, 2);
       mbar_wait(bar_afull + 8 * stage, use & 1, 3);
       tc_fence_after();
@@ -188,11 +152,12 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
       for (uint32_t off = 0; off < p.w_bytes; off += 32768u)
         bulk_g2s(w_smem + off, wsrc + off, min(32768u, p.w_bytes - off), bar_w);
       uint32_t k = 0;
-      TileIter it(p, first);
-      for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k, it.next()) {
+      for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k) {
         const uint32_t stage = k % S, use = k / S;
-        const int b = it.b;
-        const int gy0 = it.ty * kTileH + p.halo_y0, gx0 = it.tx * kTileW + p.halo_x0;
+        const int b = t / tiles_per_img;
+        const int rem = t - b * tiles_per_img;
+        const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
+        const int gy0 = tyi * kTileH + p.halo_y0, gx0 = txi * kTileW + p.halo_x0;
         mbar_wait(bar_aempty + 8 * stage, (use & 1) ^ 1, 4);
         mbar_arrive_expect_tx(bar_afull + 8 * stage, p.tx_bytes);
         const uint32_t dst = a_smem + stage * p.stage_bytes;
@@ -222,11 +187,12 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
     const int nmine = eset ? nchunks - h0 : h0;
 
     uint32_t k = 0;
-    TileIter it(p, first);
-    for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k, it.next()) {
-      const uint32_t stage = k % S, use = k / S, acc = k % NA, vuse = k / NA;
-      const int b = it.b;
-      const int gy = it.ty * kTileH + py, gx = it.tx * kTileW + px;
+    for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k) {
+      const uint32_t stage = k % S, use = k / S, acc = k & 1, vuse = k >> 1;
+      const int b = t / tiles_per_img;
+      const int rem = t - b * tiles_per_img;
+      const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
+      const int gy = tyi * kTileH + py, gx = txi * kTileW + px;
       const bool valid = (gy < p.H) && (gx < p.W);
 
       mbar_wait(bar_tfull + 8 * acc, vuse & 1, 5);
@@ -307,59 +273,40 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);  // TMEM buffer free: the next tile's MMAs may start
-      uint4 o[3][2];  // packed 16-bit outputs, 16 channels per chunk
+      T* orow = reinterpret_cast<T*>(p.out) + (valid ? out_pixel_offset(p, b, gy, gx) + (size_t)n0 : 0);
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         if (i < nmine) {
           const float4* sp = reinterpret_cast<const float4*>(ss + (c_lo + i) * 16);
-          uint32_t w[8];
+          const float4 s0 = sp[0], s1 = sp[1], s2 = sp[2], s3 = sp[3];
+          const float shf[16] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w,
+                                 s2.x, s2.y, s2.z, s2.w, s3.x, s3.y, s3.z, s3.w};
+          const uint32_t rw[8] = {rr[i][0].x, rr[i][0].y, rr[i][0].z, rr[i][0].w,
+                                  rr[i][1].x, rr[i][1].y, rr[i][1].z, rr[i][1].w};
+          uint32_t o[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {  // four channels per step: shift sp[j], accumulators v[i][4j..4j+3]
-            const float4 sf = sp[j];
-            float a0 = __uint_as_float(v[i][4 * j + 0]) + sf.x;
-            float a1 = __uint_as_float(v[i][4 * j + 1]) + sf.y;
-            float a2 = __uint_as_float(v[i][4 * j + 2]) + sf.z;
-            float a3 = __uint_as_float(v[i][4 * j + 3]) + sf.w;
+          for (int j = 0; j < 8; ++j) {
+            float a0 = __uint_as_float(v[i][2 * j]) + shf[2 * j];
+            float a1 = __uint_as_float(v[i][2 * j + 1]) + shf[2 * j + 1];
             if (residual) {
-              const uint4 rq = rr[i][j >> 1];
-              const float2 r0 = Pack2<T>::unpack((j & 1) ? rq.z : rq.x);
-              const float2 r1 = Pack2<T>::unpack((j & 1) ? rq.w : rq.y);
-              a0 += r0.x;
-              a1 += r0.y;
-              a2 += r1.x;
-              a3 += r1.y;
+              const float2 rf = Pack2<T>::unpack(rw[j]);
+              a0 += rf.x;
+              a1 += rf.y;
             }
-            w[2 * j] = Pack2<T>::pack(fmaxf(a0, 0.2f * a0), fmaxf(a1, 0.2f * a1));  // LeakyReLU(0.2)
-            w[2 * j + 1] = Pack2<T>::pack(fmaxf(a2, 0.2f * a2), fmaxf(a3, 0.2f * a3));
+            o[j] = Pack2<T>::pack(fmaxf(a0, 0.2f * a0), fmaxf(a1, 0.2f * a1));  // LeakyReLU(0.2)
           }
-          o[i][0] = make_uint4(w[0], w[1], w[2], w[3]);
-          o[i][1] = make_uint4(w[4], w[5], w[6], w[7]);
-          if (p.epi_order == 0 && valid) {  // store each chunk as soon as it is ready
-            T* orow0 = reinterpret_cast<T*>(p.out) + out_pixel_offset(p, b, gy, gx) + (size_t)n0;
-            uint4* dst = reinterpret_cast<uint4*>(orow0 + (c_lo + i) * 16);
-            dst[0] = o[i][0];
-            dst[1] = o[i][1];
+          // 32 contiguous bytes (16 channels) of this cell's channel vector; L2 merges the halves of a sector
+          if (valid) {
+            uint4* dst = reinterpret_cast<uint4*>(orow + (c_lo + i) * 16);
+            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
           }
         }
       }
       if (residual) {
-        // the window has been consumed (the residual values are in registers): release it BEFORE the global stores,
-        // the proxy fence orders our generic-proxy reads before the next TMA (async proxy) write to this stage
-        fence_proxy_async();
+        fence_proxy_async();  // generic-proxy reads of the window before the next TMA (async proxy) overwrites it
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_aempty + 8 * stage);
-      }
-      if (valid && p.epi_order != 0) {
-        // 32 contiguous bytes (16 channels) of this cell's channel vector per chunk; L2 merges the sector halves
-        T* orow = reinterpret_cast<T*>(p.out) + out_pixel_offset(p, b, gy, gx) + (size_t)n0;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          if (i < nmine) {
-            uint4* dst = reinterpret_cast<uint4*>(orow + (c_lo + i) * 16);
-            dst[0] = o[i][0];
-            dst[1] = o[i][1];
-          }
-        }
       }
     }
   }
@@ -535,15 +482,11 @@ int tapconv_plan(const TapConvLayer& L, TapConvParams* pp) {
   }
   p.stages = stages;
   p.smem_bytes = p.off_a + (uint32_t)stages * p.stage_bytes;
-  // accumulators: up to four buffers of n_cta fp32 columns (TMEM has 512), allocation is a power of two >= 32
+  // accumulators: two buffers of n_cta fp32 columns, allocation is a power of two >= 32
   uint32_t stride = 16;
   while (stride < (uint32_t)L.n_cta) stride <<= 1;
   p.acc_stride = stride;
-  p.nacc = (stride * 4 <= 512) ? 4 : 2;
-  if (const char* e = getenv("VFI_NACC")) p.nacc = (atoi(e) == 4 && stride * 4 <= 512) ? 4 : 2;
-  p.epi_order = 1;
-  if (const char* e = getenv("VFI_EPI_ORDER")) p.epi_order = atoi(e);
-  p.tmem_cols = stride * p.nacc < 32 ? 32 : stride * p.nacc;
+  p.tmem_cols = stride * 2 < 32 ? 32 : stride * 2;
   return stages;
 }
 

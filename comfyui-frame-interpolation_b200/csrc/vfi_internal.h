@@ -52,8 +52,7 @@ struct alignas(64) TapConvParams {
   int tiles_x, tiles_y, ntiles;
   int ctas_per_split;
   uint32_t idesc;
-  uint32_t tmem_cols, acc_stride, nacc;
-  int epi_order;
+  uint32_t tmem_cols, acc_stride;
   uint32_t w_bytes;               // packed weight bytes of one split
   uint32_t off_ss, off_w, off_a, stage_bytes, smem_bytes;
   int nkb;                        // k-blocks of the staged window: 64 channels each, 32-channel tail if cin%64==32

@@ -264,8 +264,9 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
             const uint32_t rowb = tail ? 64u : 128u, msk = tail ? 3u : 7u;
             const uint32_t row = a_smem + stage * p.stage_bytes + p.kb_off[kb] + center_px * rowb;
             const uint32_t c0 = (uint32_t)(ch0 - kb * 64) >> 3, sw = (row >> 7) & msk;
-            rr[i][0] = lds128(row + ((c0 ^ sw) << 4));
-            rr[i][1] = lds128(row + (((c0 + 1u) ^ sw) << 4));
+            const uint8_t* rowp = smem + (row - smem_base);  // generic pointer: ordinary loads, freely scheduled
+            rr[i][0] = *reinterpret_cast<const uint4*>(rowp + ((c0 ^ sw) << 4));
+            rr[i][1] = *reinterpret_cast<const uint4*>(rowp + (((c0 + 1u) ^ sw) << 4));
           }
         }
       }
@@ -304,7 +305,8 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
         }
       }
       if (residual) {
-        fence_proxy_async();  // generic-proxy reads of the window before the next TMA (async proxy) overwrites it
+        // our generic-proxy READS of the window are complete (values consumed above); the mbarrier arrive/wait pair
+        // orders them before the producer's next TMA write - no generic write is involved, so no proxy fence
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_aempty + 8 * stage);
       }

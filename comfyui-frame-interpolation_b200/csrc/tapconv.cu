@@ -54,6 +54,38 @@ __device__ __forceinline__ size_t out_pixel_offset(const TapConvParams& p, int b
   return (((size_t)b * p.H + gy) * p.W + gx) * (size_t)p.n_total;
 }
 
+// Walks the tiles of one CTA (t = first, first + cps, ...) keeping (image, tile row, tile column) incrementally
+// instead of two integer divisions per tile and role.
+struct TileIter {
+  int b, ty, tx, db, dy, dx, tiles_x, tiles_y;
+  __device__ __forceinline__ TileIter(const TapConvParams& p, int first) {
+    tiles_x = p.tiles_x;
+    tiles_y = p.tiles_y;
+    const int per_img = tiles_x * tiles_y;
+    b = first / per_img;
+    int rem = first - b * per_img;
+    ty = rem / tiles_x;
+    tx = rem - ty * tiles_x;
+    db = p.ctas_per_split / per_img;
+    rem = p.ctas_per_split - db * per_img;
+    dy = rem / tiles_x;
+    dx = rem - dy * tiles_x;
+  }
+  __device__ __forceinline__ void next() {
+    tx += dx;
+    ty += dy;
+    b += db;
+    if (tx >= tiles_x) {
+      tx -= tiles_x;
+      ++ty;
+    }
+    if (ty >= tiles_y) {
+      ty -= tiles_y;
+      ++b;
+    }
+  }
+};
+
 // One tile's MMAs.  K16 is a compile-time constant so that every p.mma[j] is a fixed constant-bank address: the
 // descriptor words reach the tensor core through uniform loads / uniform adds only (ncu r01: with a table in shared
 // memory, or a run-time index into the parameters, every operand went LDS/LDC -> vector register -> R2UR and the
@@ -108,7 +140,6 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctrl->tmem_base;
-  const int tiles_per_img = p.tiles_y * p.tiles_x;
 
   if (warp == 0) {
     // ======================================================= MMA issuer
@@ -152,12 +183,11 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
       for (uint32_t off = 0; off < p.w_bytes; off += 32768u)
         bulk_g2s(w_smem + off, wsrc + off, min(32768u, p.w_bytes - off), bar_w);
       uint32_t k = 0;
-      for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k) {
+      TileIter it(p, first);
+      for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k, it.next()) {
         const uint32_t stage = k % S, use = k / S;
-        const int b = t / tiles_per_img;
-        const int rem = t - b * tiles_per_img;
-        const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
-        const int gy0 = tyi * kTileH + p.halo_y0, gx0 = txi * kTileW + p.halo_x0;
+        const int b = it.b;
+        const int gy0 = it.ty * kTileH + p.halo_y0, gx0 = it.tx * kTileW + p.halo_x0;
         mbar_wait(bar_aempty + 8 * stage, (use & 1) ^ 1, 4);
         mbar_arrive_expect_tx(bar_afull + 8 * stage, p.tx_bytes);
         const uint32_t dst = a_smem + stage * p.stage_bytes;
@@ -186,13 +216,30 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
     const int c_lo = eset ? h0 : 0;    // this set's chunks: [c_lo, c_lo + nmine), nmine <= 3
     const int nmine = eset ? nchunks - h0 : h0;
 
+    // residual chunk offsets inside a stage are tile independent (stage size and base are multiples of 1024, so the
+    // swizzle phase of a row does not depend on the stage): computed once
+    uint32_t roff[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    if (residual) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        if (i < nmine) {
+          const int ch0 = n0 + (c_lo + i) * 16;
+          const int kb = ch0 >> 6;
+          const bool tail = has_tail && (kb == p.nkb - 1);
+          const uint32_t rowb = tail ? 64u : 128u, msk = tail ? 3u : 7u;
+          const uint32_t row = p.off_a + p.kb_off[kb] + center_px * rowb;  // offset from the smem base
+          const uint32_t c0 = (uint32_t)(ch0 - kb * 64) >> 3, sw = ((smem_base + row) >> 7) & msk;
+          roff[i][0] = row + ((c0 ^ sw) << 4);
+          roff[i][1] = row + (((c0 + 1u) ^ sw) << 4);
+        }
+      }
+    }
     uint32_t k = 0;
-    for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k) {
+    TileIter it(p, first);
+    for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k, it.next()) {
       const uint32_t stage = k % S, use = k / S, acc = k & 1, vuse = k >> 1;
-      const int b = t / tiles_per_img;
-      const int rem = t - b * tiles_per_img;
-      const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
-      const int gy = tyi * kTileH + py, gx = txi * kTileW + px;
+      const int b = it.b;
+      const int gy = it.ty * kTileH + py, gx = it.tx * kTileW + px;
       const bool valid = (gy < p.H) && (gx < p.W);
 
       mbar_wait(bar_tfull + 8 * acc, vuse & 1, 5);
@@ -258,15 +305,9 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
         if (i < nmine) {
           if (residual) {
             // residual = input channels n0 + 16*(c_lo+i) .. +15 of the centre pixel: two 16-byte chunks of its row
-            const int ch0 = n0 + (c_lo + i) * 16;
-            const int kb = ch0 >> 6;
-            const bool tail = has_tail && (kb == p.nkb - 1);
-            const uint32_t rowb = tail ? 64u : 128u, msk = tail ? 3u : 7u;
-            const uint32_t row = a_smem + stage * p.stage_bytes + p.kb_off[kb] + center_px * rowb;
-            const uint32_t c0 = (uint32_t)(ch0 - kb * 64) >> 3, sw = (row >> 7) & msk;
-            const uint8_t* rowp = smem + (row - smem_base);  // generic pointer: ordinary loads, freely scheduled
-            rr[i][0] = *reinterpret_cast<const uint4*>(rowp + ((c0 ^ sw) << 4));
-            rr[i][1] = *reinterpret_cast<const uint4*>(rowp + (((c0 + 1u) ^ sw) << 4));
+            const uint8_t* st = smem + stage * p.stage_bytes;  // generic pointer: ordinary, freely scheduled loads
+            rr[i][0] = *reinterpret_cast<const uint4*>(st + roff[i][0]);
+            rr[i][1] = *reinterpret_cast<const uint4*>(st + roff[i][1]);
           }
         }
       }

@@ -62,6 +62,22 @@ def test_flow_and_mask_match_oracle(pkg):
     assert ef < 0.05 and em < 0.05
 
 
+@pytest.mark.parametrize("scale_factor,h,w", [(0.5, 128, 192), (0.25, 128, 256)])
+def test_scale_factor(pkg, scale_factor, h, w):
+    """The node's scale_factor widget rescales the block scales (rife/__init__.py:157-160): 16,8,4,2 / 32,16,8,4."""
+    sd = O.synthetic_state_dict(6)
+    fr = O.synthetic_clip(2, h, w, seed=21)
+    eng = _engine(pkg, sd)
+    out = eng.forward(fr.cuda(), [0], [1], [0.5], scale_factor=scale_factor).cpu()
+    eng.close()
+    sl = [8 / scale_factor, 4 / scale_factor, 2 / scale_factor, 1 / scale_factor]
+    ref = O.ifnet46_forward(sd, fr[0:1].permute(0, 3, 1, 2), fr[1:2].permute(0, 3, 1, 2),
+                            torch.tensor([0.5]).view(1, 1, 1, 1), scale_list=sl).clamp(0, 1).permute(0, 2, 3, 1)
+    p = O.psnr(out, ref)
+    print(f"scale_factor {scale_factor}: PSNR {p:.2f} dB")
+    assert p >= PSNR_MIN
+
+
 def test_batches_and_batch_size_do_not_change_results(pkg):
     sd = O.synthetic_state_dict(1)
     fr = O.synthetic_clip(4, 72, 104, seed=5).cuda()

@@ -8,7 +8,7 @@ LIB_PATH = os.path.join(HERE, "libvfi_b200.so")
 # every symbol include/vfi_b200.h declares (tests check the .so exports exactly these)
 SYMBOLS = [
     "vfi_last_error", "vfi_version", "vfi_create", "vfi_destroy", "vfi_launch_count", "vfi_set_batch",
-    "vfi_rife46_load", "vfi_rife46_forward", "vfi_rife46_interpolate_host", "vfi_warp_bilinear_border",
+    "vfi_rife46_load", "vfi_rife_load", "vfi_rife46_forward", "vfi_rife46_interpolate_host", "vfi_warp_bilinear_border",
     "vfi_softsplat_sum", "vfi_costvol_l1", "vfi_corr_dot", "vfi_sepconv",
     "vfi_rife46_debug_layer", "vfi_rife46_debug_state", "vfi_rife46_layer_plan", "vfi_sync",
 ]
@@ -38,6 +38,7 @@ def lib():
     L.vfi_launch_count.restype = i64
     L.vfi_set_batch.argtypes = [vp, i32]
     L.vfi_rife46_load.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i32, i32]
+    L.vfi_rife_load.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64), i32, i32]
     L.vfi_rife46_forward.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, f32, vp, vp]
     L.vfi_rife46_interpolate_host.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, f32, vp]
     L.vfi_warp_bilinear_border.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]

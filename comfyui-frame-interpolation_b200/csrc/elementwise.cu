@@ -54,6 +54,27 @@ __device__ __forceinline__ float4 sample_border(const float4* __restrict__ img, 
   return o;
 }
 
+// same sampling for a 4-channel feature plane (arch 4.7 encode features)
+__device__ __forceinline__ float4 sample_border4(const float4* __restrict__ img, int Hp, int Wp, float sx, float sy) {
+  sx = fminf(fmaxf(sx, 0.f), (float)(Wp - 1));
+  sy = fminf(fmaxf(sy, 0.f), (float)(Hp - 1));
+  const float fx0 = floorf(sx), fy0 = floorf(sy);
+  const int x0 = (int)fx0, y0 = (int)fy0;
+  const int x1 = min(x0 + 1, Wp - 1), y1 = min(y0 + 1, Hp - 1);
+  const float ax = sx - fx0, ay = sy - fy0;
+  const float w00 = (1.f - ax) * (1.f - ay), w01 = ax * (1.f - ay), w10 = (1.f - ax) * ay, w11 = ax * ay;
+  const float4 a = __ldg(img + (size_t)y0 * Wp + x0);
+  const float4 b = __ldg(img + (size_t)y0 * Wp + x1);
+  const float4 c = __ldg(img + (size_t)y1 * Wp + x0);
+  const float4 d = __ldg(img + (size_t)y1 * Wp + x1);
+  float4 o;
+  o.x = a.x * w00 + b.x * w01 + c.x * w10 + d.x * w11;
+  o.y = a.y * w00 + b.y * w01 + c.y * w10 + d.y * w11;
+  o.z = a.z * w00 + b.z * w01 + c.z * w10 + d.z * w11;
+  o.w = a.w * w00 + b.w * w01 + c.w * w10 + d.w * w11;
+  return o;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Flow state.  The reference keeps flow/mask at full resolution and adds each block's up-scaled output to it
 // (rife_arch.py:263-266, :694-696).  Here each block leaves only its low-resolution output T_j (float4 flow +
@@ -73,6 +94,7 @@ struct FlowLevels {
   const float* base_m;
   float4* out_f;         // optional: store the accumulated flow / mask at every visited position
   float* out_m;
+  int mask_replace;      // arch 4.7+: mask = the newest level's mask (rife_arch.py:698-699), not the running sum
 };
 
 // F.interpolate(scale_factor=s, bilinear, align_corners=False) of level j at full-res position (Y, X)
@@ -134,7 +156,7 @@ __device__ __forceinline__ void flow_at(const FlowLevels& L, int b, int Hp, int 
     f.y += u.y * sj;
     f.z += u.z * sj;
     f.w += u.w * sj;
-    m += um;
+    m = L.mask_replace ? um : m + um;
   }
   if (L.out_f != nullptr) {
     L.out_f[pid] = f;
@@ -213,6 +235,173 @@ __global__ void front_kernel(const float4* __restrict__ imgs, const FlowLevels l
     hi.w = 0u;
     reinterpret_cast<uint4*>(dst)[0] = lo;
     reinterpret_cast<uint4*>(dst)[1] = hi;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// arch 4.7 (rife47.pth / rife49.pth): encode head  f = ConvTranspose2d(16,4,4,2,1)(Conv2d(3,16,3,2,1)(img))
+// (rife_arch.py:414-416, :501-503), once per source frame, fp32 on the CUDA cores (0.76 GMAC per 1080p frame).
+// ---------------------------------------------------------------------------------------------
+__global__ void encode_conv_kernel(const float4* __restrict__ imgs, const float* __restrict__ w,
+                                   const float* __restrict__ bias, float* __restrict__ e16, int n, int Hp, int Wp) {
+  __shared__ float ws[16 * 27 + 16];
+  for (int i = threadIdx.x; i < 16 * 27; i += blockDim.x) ws[i] = w[i];
+  for (int i = threadIdx.x; i < 16; i += blockDim.x) ws[16 * 27 + i] = bias[i];
+  __syncthreads();
+  const int Hh = Hp >> 1, Wh = Wp >> 1;
+  const size_t total = (size_t)n * Hh * Wh;
+  for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(id % Wh);
+    const size_t r = id / Wh;
+    const int y = (int)(r % Hh);
+    const int f = (int)(r / Hh);
+    const float4* img = imgs + (size_t)f * Hp * Wp;
+    float acc[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) acc[o] = ws[16 * 27 + o];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int Y = 2 * y + ky - 1;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int X = 2 * x + kx - 1;
+        if (Y >= 0 && Y < Hp && X >= 0 && X < Wp) {
+          const float4 p = __ldg(img + (size_t)Y * Wp + X);
+#pragma unroll
+          for (int o = 0; o < 16; ++o) {  // weight [o][c][ky][kx]
+            acc[o] = fmaf(p.x, ws[(o * 3 + 0) * 9 + ky * 3 + kx], acc[o]);
+            acc[o] = fmaf(p.y, ws[(o * 3 + 1) * 9 + ky * 3 + kx], acc[o]);
+            acc[o] = fmaf(p.z, ws[(o * 3 + 2) * 9 + ky * 3 + kx], acc[o]);
+          }
+        }
+      }
+    }
+    float4* dst = reinterpret_cast<float4*>(e16 + id * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+  }
+}
+
+__global__ void encode_deconv_kernel(const float* __restrict__ e16, const float* __restrict__ w,
+                                     const float* __restrict__ bias, float4* __restrict__ feats, int n, int Hp,
+                                     int Wp) {
+  __shared__ float ws[16 * 4 * 16 + 4];  // ConvTranspose2d weight [16 in][4 out][4][4]
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) ws[i] = w[i];
+  if (threadIdx.x < 4) ws[1024 + threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int Hh = Hp >> 1, Wh = Wp >> 1;
+  const size_t total = (size_t)n * Hp * Wp;
+  for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
+    const int X = (int)(id % Wp);
+    const size_t r = id / Wp;
+    const int Y = (int)(r % Hp);
+    const int f = (int)(r / Hp);
+    float o[4] = {ws[1024], ws[1025], ws[1026], ws[1027]};
+    // out[2i-1+ky] += in[i]*w[ky]  ->  contributing input rows i = (Y+1)>>1 (ky = Y+1-2i in {0,1}) and i-1 (ky+2)
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const int i = ((Y + 1) >> 1) - dy, ky = Y + 1 - 2 * i;
+      if (i < 0 || i >= Hh) continue;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int j = ((X + 1) >> 1) - dx, kx = X + 1 - 2 * j;
+        if (j < 0 || j >= Wh) continue;
+        const float4* src = reinterpret_cast<const float4*>(e16 + (((size_t)f * Hh + i) * Wh + j) * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 v = __ldg(src + q);
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int ci = 4 * q + c;
+#pragma unroll
+            for (int oc = 0; oc < 4; ++oc) o[oc] = fmaf(vv[c], ws[((ci * 4 + oc) * 4 + ky) * 4 + kx], o[oc]);
+          }
+        }
+      }
+    }
+    feats[id] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// arch 4.7 block input: [w0.rgb, w1.rgb, warp(f0) (4), warp(f1) (4), t, mask, flow/s (4)] = 20 of 32 channels
+// (block 0: [img0, img1, f0, f1, t] = 15), space-to-depth cell = 4 x 32 channels
+template <typename T, int NLEV>
+__global__ void front47_kernel(const float4* __restrict__ imgs, const float4* __restrict__ feats,
+                               const FlowLevels lev, const BatchTasks tasks, int Hp, int Wp, int s,
+                               T* __restrict__ x_s2d) {
+  const int Hs = Hp / s, Ws = Wp / s;
+  const size_t total = (size_t)tasks.n * Hs * Ws;
+  const size_t plane = (size_t)Hp * Wp;
+  const float inv_s = 1.f / (float)s;
+  for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
+    const int par = (int)(id & 1);
+    size_t r = id >> 1;
+    const int xl = (int)(r % Ws);
+    r /= Ws;
+    const int yl = (int)(r % (Hs >> 1)) * 2 + par;
+    const int b = (int)(r / (Hs >> 1));
+    const float4* img0 = imgs + (size_t)tasks.f0[b] * plane;
+    const float4* img1 = imgs + (size_t)tasks.f1[b] * plane;
+    const float4* ft0 = feats + (size_t)tasks.f0[b] * plane;
+    const float4* ft1 = feats + (size_t)tasks.f1[b] * plane;
+    const float t = tasks.t[b];
+    const int ntap = (s == 1) ? 1 : 2;
+    const int by = (s == 1) ? yl : s * yl + s / 2 - 1;
+    const int bx = (s == 1) ? xl : s * xl + s / 2 - 1;
+    float ch[20];
+#pragma unroll
+    for (int i = 0; i < 20; ++i) ch[i] = 0.f;
+    float rowacc[2][20];
+#pragma unroll
+    for (int ty = 0; ty < 2; ++ty) {
+      float colv[2][20];
+#pragma unroll
+      for (int tx = 0; tx < 2; ++tx) {
+        if (ty < ntap && tx < ntap) {
+          const int Y = by + ty, X = bx + tx;
+          float* v = colv[tx];
+          float4 a, c, fa, fc;
+          if (NLEV == 0) {
+            a = __ldg(img0 + (size_t)Y * Wp + X);
+            c = __ldg(img1 + (size_t)Y * Wp + X);
+            fa = __ldg(ft0 + (size_t)Y * Wp + X);
+            fc = __ldg(ft1 + (size_t)Y * Wp + X);
+            v[14] = t; v[15] = 0.f; v[16] = 0.f; v[17] = 0.f; v[18] = 0.f; v[19] = 0.f;
+          } else {
+            float4 f;
+            float m;
+            flow_at<(NLEV > 0 ? NLEV : 1)>(lev, b, Hp, Wp, Y, X, f, m);
+            a = sample_border(img0, Hp, Wp, (float)X + f.x, (float)Y + f.y);
+            c = sample_border(img1, Hp, Wp, (float)X + f.z, (float)Y + f.w);
+            fa = sample_border4(ft0, Hp, Wp, (float)X + f.x, (float)Y + f.y);
+            fc = sample_border4(ft1, Hp, Wp, (float)X + f.z, (float)Y + f.w);
+            v[14] = t; v[15] = m; v[16] = f.x; v[17] = f.y; v[18] = f.z; v[19] = f.w;
+          }
+          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = c.x; v[4] = c.y; v[5] = c.z;
+          v[6] = fa.x; v[7] = fa.y; v[8] = fa.z; v[9] = fa.w; v[10] = fc.x; v[11] = fc.y; v[12] = fc.z; v[13] = fc.w;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 20; ++i) rowacc[ty][i] = (ntap == 1) ? colv[0][i] : (colv[0][i] + colv[1][i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 20; ++i) ch[i] = (ntap == 1) ? rowacc[0][i] : 0.25f * (rowacc[0][i] + rowacc[1][i]);
+#pragma unroll
+    for (int i = 16; i < 20; ++i) ch[i] *= inv_s;
+    const size_t cell = ((size_t)b * (Hs >> 1) + (yl >> 1)) * (Ws >> 1) + (xl >> 1);
+    T* dst = x_s2d + cell * 128 + ((yl & 1) * 2 + (xl & 1)) * 32;
+    uint4 q0, q1, q2;
+    q0.x = Pack2<T>::pack(ch[0], ch[1]);   q0.y = Pack2<T>::pack(ch[2], ch[3]);
+    q0.z = Pack2<T>::pack(ch[4], ch[5]);   q0.w = Pack2<T>::pack(ch[6], ch[7]);
+    q1.x = Pack2<T>::pack(ch[8], ch[9]);   q1.y = Pack2<T>::pack(ch[10], ch[11]);
+    q1.z = Pack2<T>::pack(ch[12], ch[13]); q1.w = Pack2<T>::pack(ch[14], ch[15]);
+    q2.x = Pack2<T>::pack(ch[16], ch[17]); q2.y = Pack2<T>::pack(ch[18], ch[19]);
+    q2.z = 0u; q2.w = 0u;
+    reinterpret_cast<uint4*>(dst)[0] = q0;
+    reinterpret_cast<uint4*>(dst)[1] = q1;
+    reinterpret_cast<uint4*>(dst)[2] = q2;
+    reinterpret_cast<uint4*>(dst)[3] = make_uint4(0u, 0u, 0u, 0u);
   }
 }
 
@@ -318,6 +507,7 @@ cudaError_t launch_prep_frames(const float* frames, int n, int H, int W, int cst
 static FlowLevels make_levels(const FlowState& fs, int lo, int hi, const float4* base_f, const float* base_m,
                               float4* out_f, float* out_m) {
   FlowLevels L{};
+  L.mask_replace = fs.mask_replace;
   for (int j = lo; j < hi; ++j) {
     L.f[j - lo] = fs.f[j];
     L.m[j - lo] = fs.m[j];
@@ -328,6 +518,17 @@ static FlowLevels make_levels(const FlowState& fs, int lo, int hi, const float4*
   L.out_f = out_f;
   L.out_m = out_m;
   return L;
+}
+
+template <typename T>
+static void launch_front47_t(int nlev, int g, cudaStream_t st, const float4* imgs, const float4* feats,
+                             const FlowLevels& L, const BatchTasks& tasks, int Hp, int Wp, int s, void* x) {
+  switch (nlev) {
+    case 0: front47_kernel<T, 0><<<g, 128, 0, st>>>(imgs, feats, L, tasks, Hp, Wp, s, (T*)x); break;
+    case 1: front47_kernel<T, 1><<<g, 128, 0, st>>>(imgs, feats, L, tasks, Hp, Wp, s, (T*)x); break;
+    case 2: front47_kernel<T, 2><<<g, 128, 0, st>>>(imgs, feats, L, tasks, Hp, Wp, s, (T*)x); break;
+    default: front47_kernel<T, 3><<<g, 128, 0, st>>>(imgs, feats, L, tasks, Hp, Wp, s, (T*)x); break;
+  }
 }
 
 template <typename T>
@@ -342,14 +543,31 @@ static void launch_front_t(int nlev, int g, cudaStream_t st, const float4* imgs,
 }
 
 // block `blk` input: flow = base (if any) + levels [lo, blk); stores the accumulated flow when `store` planes given
-cudaError_t launch_front(int op_type, const float4* imgs, const FlowState& fs, int blk, int lo, const float4* base_f,
-                         const float* base_m, float4* out_f, float* out_m, BatchTasks tasks, int Hp, int Wp, int s,
-                         void* x_s2d, cudaStream_t st) {
+cudaError_t launch_encode(const float4* imgs, const float* w0, const float* b0, const float* w1, const float* b1,
+                          float* e16, float4* feats, int n, int Hp, int Wp, cudaStream_t st) {
+  const size_t t0 = (size_t)n * (Hp / 2) * (Wp / 2), t1 = (size_t)n * Hp * Wp;
+  encode_conv_kernel<<<grid_for(t0, 128), 128, 0, st>>>(imgs, w0, b0, e16, n, Hp, Wp);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  encode_deconv_kernel<<<grid_for(t1, 256), 256, 0, st>>>(e16, w1, b1, feats, n, Hp, Wp);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_front(int op_type, const float4* imgs, const float4* feats, const FlowState& fs, int blk, int lo,
+                         const float4* base_f, const float* base_m, float4* out_f, float* out_m, BatchTasks tasks,
+                         int Hp, int Wp, int s, void* x_s2d, cudaStream_t st) {
   const size_t total = (size_t)tasks.n * (Hp / s) * (Wp / s);
   const int g = grid_for(total, 128);
   const FlowLevels L = make_levels(fs, lo, blk, base_f, base_m, out_f, out_m);
   const int nlev = (blk == 0) ? 0 : (blk - lo);
   if (blk > 0 && nlev == 0 && base_f == nullptr) return cudaErrorInvalidValue;
+  if (feats != nullptr) {  // arch 4.7
+    if (op_type == OP_BF16)
+      launch_front47_t<__nv_bfloat16>(blk == 0 ? 0 : nlev, g, st, imgs, feats, L, tasks, Hp, Wp, s, x_s2d);
+    else
+      launch_front47_t<__half>(blk == 0 ? 0 : nlev, g, st, imgs, feats, L, tasks, Hp, Wp, s, x_s2d);
+    return cudaGetLastError();
+  }
   if (op_type == OP_BF16)
     launch_front_t<__nv_bfloat16>(blk == 0 ? 0 : (nlev == 0 ? 1 : nlev), g, st, imgs, L, tasks, Hp, Wp, s, x_s2d);
   else

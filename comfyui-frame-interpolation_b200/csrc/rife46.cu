@@ -31,7 +31,8 @@ void set_error(const std::string& s) { g_err = s; }
 namespace {
 
 const int kBlockC[4] = {192, 128, 96, 64};
-const int kBlockCinReal[4] = {7, 12, 12, 12};
+const int kBlockCinReal[4] = {7, 12, 12, 12};        // arch 4.6: img0,img1,t | w0,w1,t,mask + flow
+const int kBlockCinReal47[4] = {15, 20, 20, 20};     // arch 4.7: + encoded features f0,f1 (4 ch each)
 
 uint16_t to_operand(float v, int op_type) {
   if (op_type == OP_BF16) {
@@ -128,6 +129,9 @@ struct vfi_ctx {
   std::vector<void*> weight_allocs;
   // workspace
   DevBuf imgs, flow, mask, x, c00, featA, featB, tF[4], tM[4], raw, outdev;
+  int arch = 46;                 // 46 | 47 (rife47.pth / rife49.pth)
+  DevBuf feats, e16;             // arch 4.7: encoded features per source frame (float4), half-res temp
+  float* enc[4] = {nullptr, nullptr, nullptr, nullptr};  // encode.0.weight/.bias, encode.1.weight/.bias (fp32)
   int ws_Hp = 0, ws_Wp = 0, ws_B = 0;
   FlowState last_fs{};
   int last_lo = 0;
@@ -299,7 +303,7 @@ int ensure_workspace(vfi_ctx* c, const Geometry& g, int B, int n_frames_window) 
   size_t x = 0, c00 = 0, feat = 0;
   for (int i = 0; i < 4; ++i) {
     const size_t Hs = g.Hp / g.s[i], Ws = g.Wp / g.s[i];
-    x = std::max(x, (size_t)B * (Hs / 2) * (Ws / 2) * 64 * 2);
+    x = std::max(x, (size_t)B * (Hs / 2) * (Ws / 2) * (c->arch == 47 ? 128 : 64) * 2);
     c00 = std::max(c00, (size_t)B * (Hs / 4) * (Ws / 4) * 2 * kBlockC[i] * 2);
     feat = std::max(feat, (size_t)B * (Hs / 4) * (Ws / 4) * kBlockC[i] * 2);
     CK(c->tF[i].ensure((size_t)B * Hs * Ws * sizeof(float4)));  // block output T_i (flow increments at 1/s_i)
@@ -307,6 +311,10 @@ int ensure_workspace(vfi_ctx* c, const Geometry& g, int B, int n_frames_window) 
   }
   const size_t px = (size_t)g.Hp * g.Wp;
   CK(c->imgs.ensure((size_t)n_frames_window * px * sizeof(float4)));
+  if (c->arch == 47) {
+    CK(c->feats.ensure((size_t)n_frames_window * px * sizeof(float4)));
+    CK(c->e16.ensure((size_t)(kMaxBatch + 2) * (px / 4) * 16 * sizeof(float)));
+  }
   CK(c->flow.ensure((size_t)B * px * sizeof(float4)));
   CK(c->mask.ensure((size_t)B * px * sizeof(float)));
   CK(c->x.ensure(x));
@@ -332,6 +340,7 @@ int ensure_workspace(vfi_ctx* c, const Geometry& g, int B, int n_frames_window) 
 int forward_pass(vfi_ctx* c, const Geometry& g, const BatchTasks& tasks, int H, int W, float* out, cudaStream_t st) {
   const int B = tasks.n;
   const float4* imgs = (const float4*)c->imgs.p;
+  const float4* feats = c->arch == 47 ? (const float4*)c->feats.p : nullptr;
   float4* F = (float4*)c->flow.p;  // accumulated full-resolution flow / mask, written only by "dense" fronts
   float* M = (float*)c->mask.p;
   FlowState fs{};
@@ -340,6 +349,7 @@ int forward_pass(vfi_ctx* c, const Geometry& g, const BatchTasks& tasks, int H, 
     fs.m[i] = (float*)c->tM[i].p;
     fs.s[i] = g.s[i];
   }
+  fs.mask_replace = (c->arch == 47) ? 1 : 0;
   int dense = 4;  // first block whose front visits every full-resolution pixel (scale <= 2)
   for (int i = 3; i >= 1; --i)
     if (g.s[i] <= 2) dense = i;
@@ -349,9 +359,10 @@ int forward_pass(vfi_ctx* c, const Geometry& g, const BatchTasks& tasks, int H, 
     const int s = g.s[i];
     const int Hs = g.Hp / s, Ws = g.Wp / s;
     if (i == 0 || i < dense) {
-      LAUNCH(launch_front(c->op_type, imgs, fs, i, 0, nullptr, nullptr, nullptr, nullptr, tasks, g.Hp, g.Wp, s, c->x.p, st));
+      LAUNCH(launch_front(c->op_type, imgs, feats, fs, i, 0, nullptr, nullptr, nullptr, nullptr, tasks, g.Hp, g.Wp, s,
+                          c->x.p, st));
     } else {
-      LAUNCH(launch_front(c->op_type, imgs, fs, i, lo, have_base ? F : nullptr, have_base ? M : nullptr, F, M, tasks,
+      LAUNCH(launch_front(c->op_type, imgs, feats, fs, i, lo, have_base ? F : nullptr, have_base ? M : nullptr, F, M, tasks,
                           g.Hp, g.Wp, s, c->x.p, st));
       have_base = true;
       lo = i;
@@ -418,7 +429,7 @@ int vfi_destroy(vfi_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   free_weights(c);
-  for (DevBuf* b : {&c->imgs, &c->flow, &c->mask, &c->x, &c->c00, &c->featA, &c->featB, &c->raw, &c->outdev, &c->dbgF,
+  for (DevBuf* b : {&c->imgs, &c->flow, &c->mask, &c->x, &c->c00, &c->featA, &c->featB, &c->raw, &c->outdev, &c->feats, &c->e16, &c->dbgF,
                     &c->dbgM})
     b->release();
   for (int i = 0; i < 4; ++i) {
@@ -448,21 +459,28 @@ int vfi_sync(vfi_ctx* c) {
 }
 
 int vfi_rife46_load(vfi_ctx* c, const float* const* T, const int64_t* numel, int n_tensors, int operand_type) {
+  return vfi_rife_load(c, 46, T, numel, n_tensors, operand_type);
+}
+
+int vfi_rife_load(vfi_ctx* c, int arch, const float* const* T, const int64_t* numel, int n_tensors, int operand_type) {
   if (!c || !T || !numel) return fail(VFI_E_INVALID, "null argument");
-  if (n_tensors != VFI_RIFE46_NUM_TENSORS) return fail(VFI_E_INVALID, "RIFE 4.6 has 120 state_dict tensors");
+  if (arch != 46 && arch != 47) return fail(VFI_E_NOTIMPL, "RIFE arch must be 46 (rife46.pth) or 47 (rife47/rife49.pth)");
+  if (n_tensors != (arch == 46 ? VFI_RIFE46_NUM_TENSORS : VFI_RIFE47_NUM_TENSORS))
+    return fail(VFI_E_INVALID, "wrong number of state_dict tensors for this RIFE arch (4.6: 120, 4.7: 124)");
   if (operand_type != OP_F16 && operand_type != OP_BF16) return fail(VFI_E_INVALID, "operand_type");
   CK(cudaSetDevice(c->device));
   free_weights(c);
   c->op_type = operand_type;
+  c->arch = arch;
   int k = 0;
   auto expect = [&](int idx, int64_t want) { return numel[idx] == want; };
   for (int b = 0; b < 4; ++b) {
-    const int ch = kBlockC[b], cin = kBlockCinReal[b];
+    const int ch = kBlockC[b], cin = (arch == 47 ? kBlockCinReal47 : kBlockCinReal)[b];
     if (!expect(k, (int64_t)(ch / 2) * cin * 9) || !expect(k + 1, ch / 2) || !expect(k + 2, (int64_t)ch * (ch / 2) * 9) ||
         !expect(k + 3, ch))
       return fail(VFI_E_INVALID, "conv0 tensor sizes do not match RIFE 4.6");
     int r;
-    if ((r = build_conv_s2(c, c->layers[b][0], 16, cin, ch / 2, 1, T[k], T[k + 1]))) return r;
+    if ((r = build_conv_s2(c, c->layers[b][0], arch == 47 ? 32 : 16, cin, ch / 2, 1, T[k], T[k + 1]))) return r;
     if ((r = build_conv_s2(c, c->layers[b][1], ch / 2, ch / 2, ch, 0, T[k + 2], T[k + 3]))) return r;
     k += 4;
     for (int j = 0; j < 8; ++j) {
@@ -475,6 +493,16 @@ int vfi_rife46_load(vfi_ctx* c, const float* const* T, const int64_t* numel, int
       return fail(VFI_E_INVALID, "lastconv tensor sizes do not match RIFE 4.6");
     if ((r = build_lastconv(c, c->layers[b][10], ch, T[k], T[k + 1]))) return r;
     k += 2;
+  }
+  if (arch == 47) {  // encode = Conv2d(3,16,3,2,1) + ConvTranspose2d(16,4,4,2,1), fp32 on the CUDA cores
+    const int64_t want[4] = {16 * 3 * 9, 16, 16 * 4 * 16, 4};
+    for (int i = 0; i < 4; ++i) {
+      if (numel[k + i] != want[i]) return fail(VFI_E_INVALID, "encode tensor sizes do not match RIFE 4.7");
+      std::vector<float> h(T[k + i], T[k + i] + want[i]);
+      int r;
+      if ((r = upload(c, h, (void**)&c->enc[i]))) return r;
+    }
+    k += 4;
   }
   for (int b = 0; b < 4; ++b)
     for (int l = 0; l < 11; ++l)
@@ -503,6 +531,14 @@ int vfi_rife46_forward(vfi_ctx* c, const float* frames, int n_frames, int H, int
   if ((r = ensure_workspace(c, g, B, hi - lo))) return r;
   cudaStream_t st = (cudaStream_t)stream;
   LAUNCH(launch_prep_frames(frames + (size_t)lo * H * W * C, hi - lo, H, W, C, (float4*)c->imgs.p, g.Hp, g.Wp, st));
+  if (c->arch == 47) {  // encode head, once per source frame, in groups that fit the half-resolution scratch
+    const size_t px = (size_t)g.Hp * g.Wp;
+    for (int f = 0; f < hi - lo; f += kMaxBatch) {
+      const int cnt = std::min(kMaxBatch, hi - lo - f);
+      LAUNCH(launch_encode((const float4*)c->imgs.p + (size_t)f * px, c->enc[0], c->enc[1], c->enc[2], c->enc[3],
+                           (float*)c->e16.p, (float4*)c->feats.p + (size_t)f * px, cnt, g.Hp, g.Wp, st));
+    }
+  }
   for (int pos = 0; pos < n_tasks; pos += B) {
     BatchTasks bt{};
     bt.n = std::min(B, n_tasks - pos);
@@ -562,6 +598,10 @@ int vfi_rife46_interpolate_host(vfi_ctx* c, const float* frames, int n_frames, i
                              frame_elems * sizeof(float), cudaMemcpyHostToDevice, c->s_h2d));
           LAUNCH(launch_prep_frames((float*)c->raw.p + (size_t)(f % kRaw) * frame_elems, 1, H, W, C,
                                     (float4*)c->imgs.p + (size_t)(f - frame_lo) * g.Hp * g.Wp, g.Hp, g.Wp, c->s_h2d));
+          if (c->arch == 47)
+            LAUNCH(launch_encode((const float4*)c->imgs.p + (size_t)(f - frame_lo) * g.Hp * g.Wp, c->enc[0], c->enc[1],
+                                 c->enc[2], c->enc[3], (float*)c->e16.p,
+                                 (float4*)c->feats.p + (size_t)(f - frame_lo) * g.Hp * g.Wp, 1, g.Hp, g.Wp, c->s_h2d));
         }
         uploaded += cnt;
       }

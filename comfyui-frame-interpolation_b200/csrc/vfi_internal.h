@@ -101,10 +101,13 @@ struct FlowState {
   float4* f[4];
   float* m[4];
   int s[4];
+  int mask_replace;  // arch 4.7: mask = newest level only
 };
-cudaError_t launch_front(int op_type, const float4* imgs, const FlowState& fs, int blk, int lo, const float4* base_f,
-                         const float* base_m, float4* out_f, float* out_m, BatchTasks tasks, int Hp, int Wp, int s,
-                         void* x_s2d, cudaStream_t st);
+cudaError_t launch_encode(const float4* imgs, const float* w0, const float* b0, const float* w1, const float* b1,
+                          float* e16, float4* feats, int n, int Hp, int Wp, cudaStream_t st);
+cudaError_t launch_front(int op_type, const float4* imgs, const float4* feats, const FlowState& fs, int blk, int lo,
+                         const float4* base_f, const float* base_m, float4* out_f, float* out_m, BatchTasks tasks,
+                         int Hp, int Wp, int s, void* x_s2d, cudaStream_t st);
 cudaError_t launch_materialize(const FlowState& fs, int lo, const float4* base_f, const float* base_m, float4* flow,
                                float* mask, int B, int Hp, int Wp, cudaStream_t st);
 cudaError_t launch_final(const float4* imgs, const FlowState& fs, int lo, const float4* base_f, const float* base_m,

@@ -15,7 +15,7 @@ OPERAND = {"float32": 0, "float16": 0, "bfloat16": 1}
 BLOCK_C = (192, 128, 96, 64)
 
 
-def state_dict_names():
+def state_dict_names(arch: str = "4.6"):
     names = []
     for b in range(4):
         p = f"block{b}."
@@ -24,6 +24,8 @@ def state_dict_names():
             q = p + f"convblock.{j}."
             names += [q + "beta", q + "conv.weight", q + "conv.bias"]
         names += [p + "lastconv.0.weight", p + "lastconv.0.bias"]
+    if arch == "4.7":
+        names += ["encode.0.weight", "encode.0.bias", "encode.1.weight", "encode.1.bias"]
     return names
 
 
@@ -32,9 +34,10 @@ def _i32(a):
 
 
 class Rife46Engine:
-    """RIFE 4.6 on one B200.  `state_dict` maps the reference's parameter names to tensors (any float dtype)."""
+    """RIFE 4.6 / 4.7 (rife46.pth; rife47.pth, rife49.pth) on one B200.  `state_dict` maps the reference's parameter names to tensors (any float dtype)."""
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device: int = 0, dtype: str = "float32", batch: int = 8):
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device: int = 0, dtype: str = "float32", batch: int = 8,
+                 arch: str = None):
         if not torch.cuda.is_available():
             raise VfiError("no CUDA device: this path has no CPU fallback")
         if dtype not in OPERAND:
@@ -43,14 +46,19 @@ class Rife46Engine:
         self.device = int(device)
         self._ctx = C.c_void_p()
         check(self._L.vfi_create(self.device, C.byref(self._ctx)))
-        names = state_dict_names()
+        if arch is None:  # the 4.7 family (rife47.pth / rife49.pth) has the encode head
+            arch = "4.7" if "encode.0.weight" in state_dict else "4.6"
+        if arch not in ("4.6", "4.7"):
+            raise VfiError(f"RIFE arch {arch} is not built (4.6 and 4.7 are)")
+        self.arch = arch
+        names = state_dict_names(arch)
         missing = [n for n in names if n not in state_dict]
         if missing:
-            raise KeyError(f"state_dict is not a RIFE 4.6 checkpoint; missing {missing[:3]} ...")
+            raise KeyError(f"state_dict is not a RIFE {arch} checkpoint; missing {missing[:3]} ...")
         hold = [state_dict[n].detach().to("cpu", torch.float32).contiguous() for n in names]
         ptrs = (C.c_void_p * len(hold))(*[t.data_ptr() for t in hold])
         numel = (C.c_int64 * len(hold))(*[t.numel() for t in hold])
-        check(self._L.vfi_rife46_load(self._ctx, ptrs, numel, len(hold), OPERAND[dtype]))
+        check(self._L.vfi_rife_load(self._ctx, 46 if arch == "4.6" else 47, ptrs, numel, len(hold), OPERAND[dtype]))
         check(self._L.vfi_set_batch(self._ctx, int(batch)))
         self.dtype = dtype
 

@@ -16,9 +16,12 @@ from .engine import Rife46Engine
 
 MODEL_TYPE = "rife"
 # The reference table (rife/__init__.py:10-20) has no 4.6 entry at this commit although IFNet supports it and
-# GMFSS uses rife46.pth; this node adds it.  Other arch versions are the next scope row.
+# GMFSS uses rife46.pth; this node adds it.  Built archs: 4.6 and 4.7 (rife47/rife49, the reference's
+# default); 4.17 / 4.26 / 4.0 are the next scope rows.
 CKPT_NAME_VER_DICT = {
     "rife46.pth": "4.6",
+    "rife47.pth": "4.7",
+    "rife49.pth": "4.7",
 }
 DTYPE_OPTIONS = ["float32", "float16", "bfloat16"]
 DTYPE_MAP = {"float32": torch.float32, "float16": torch.float16, "bfloat16": torch.bfloat16}
@@ -112,7 +115,7 @@ class RIFE_VFI:
     def INPUT_TYPES(s):
         return {
             "required": {
-                "ckpt_name": (sorted(list(CKPT_NAME_VER_DICT.keys())), {"default": "rife46.pth"}),
+                "ckpt_name": (sorted(list(CKPT_NAME_VER_DICT.keys())), {"default": "rife49.pth"}),
                 "frames": ("IMAGE",),
                 "clear_cache_after_n_frames": ("INT", {"default": 10, "min": 1, "max": 1000}),
                 "multiplier": ("INT", {"default": 2, "min": 1}),
@@ -157,13 +160,12 @@ class RIFE_VFI:
         bfloat16 -> bf16 operands; flow, mask, warps and blending are fp32 in every mode.
         """
         arch_ver = CKPT_NAME_VER_DICT[ckpt_name]
-        assert arch_ver == "4.6"
         model_path = load_file_from_github_release(MODEL_TYPE, ckpt_name)
         torch_dtype = DTYPE_MAP[dtype]
         cache_key = (ckpt_name, dtype)
         if cache_key not in _model_cache:
             sd = torch.load(model_path, map_location="cpu", weights_only=False)
-            _model_cache[cache_key] = Rife46Engine(sd, device=torch.cuda.current_device(), dtype=dtype)
+            _model_cache[cache_key] = Rife46Engine(sd, device=torch.cuda.current_device(), dtype=dtype, arch=arch_ver)
         engine = _model_cache[cache_key]
 
         assert len(frames) >= 2, f"RIFE needs at least 2 frames, only found {frames.shape[0]}"

@@ -30,15 +30,20 @@ BLOCK_SPECS: Tuple[Tuple[int, int], ...] = ((7, 192), (12, 128), (12, 96), (12, 
 LRELU_SLOPE = 0.2  # rife_arch.py:106 / :26
 
 
-def state_dict_spec() -> List[Tuple[str, Tuple[int, ...]]]:
-    """Names and shapes of IFNet("4.6").state_dict(), in the reference's order.
+# arch 4.7 (checkpoints rife47.pth / rife49.pth, rife/__init__.py:10-12): same IFBlocks with 8 (block 0) / 8 more input
+# channels for the encoded features of both frames, plus the `encode` head -- rife_arch.py:409-417
+BLOCK_SPECS_47: Tuple[Tuple[int, int], ...] = ((7 + 8, 192), (8 + 4 + 8, 128), (8 + 4 + 8, 96), (8 + 4 + 8, 64))
+
+
+def state_dict_spec(arch: str = "4.6") -> List[Tuple[str, Tuple[int, ...]]]:
+    """Names and shapes of IFNet(arch).state_dict(), in the reference's order (arch "4.6" or "4.7").
 
     Follows the module construction in rife_arch.py:177-218 (IFBlock.__init__),
     :20-28 (ResConv) and :404-408 (IFNet.__init__ for arch 4.6): 4 blocks x
     (conv0.0, conv0.1, 8 x ResConv{beta, conv}, lastconv) = 120 tensors, 5,306,256 values.
     """
     spec: List[Tuple[str, Tuple[int, ...]]] = []
-    for b, (cin, c) in enumerate(BLOCK_SPECS):
+    for b, (cin, c) in enumerate(BLOCK_SPECS if arch == "4.6" else BLOCK_SPECS_47):
         p = f"block{b}."
         spec += [(p + "conv0.0.0.weight", (c // 2, cin, 3, 3)), (p + "conv0.0.0.bias", (c // 2,))]
         spec += [(p + "conv0.1.0.weight", (c, c // 2, 3, 3)), (p + "conv0.1.0.bias", (c,))]
@@ -46,10 +51,14 @@ def state_dict_spec() -> List[Tuple[str, Tuple[int, ...]]]:
             q = p + f"convblock.{j}."
             spec += [(q + "beta", (1, c, 1, 1)), (q + "conv.weight", (c, c, 3, 3)), (q + "conv.bias", (c,))]
         spec += [(p + "lastconv.0.weight", (c, 24, 4, 4)), (p + "lastconv.0.bias", (24,))]
+    if arch == "4.7":  # encode = Sequential(Conv2d(3,16,3,2,1), ConvTranspose2d(16,4,4,2,1)) -- rife_arch.py:414-416
+        spec += [("encode.0.weight", (16, 3, 3, 3)), ("encode.0.bias", (16,)),
+                 ("encode.1.weight", (16, 4, 4, 4)), ("encode.1.bias", (4,))]
     return spec
 
 
-def synthetic_state_dict(seed: int = 0, flow_gain: float = 1.0, beta_jitter: float = 0.25) -> Dict[str, torch.Tensor]:
+def synthetic_state_dict(seed: int = 0, flow_gain: float = 1.0, beta_jitter: float = 0.25,
+                         arch: str = "4.6") -> Dict[str, torch.Tensor]:
     """Seeded synthetic weights (no checkpoint ships with the reference and there is no network).
 
     Same family as PyTorch's default init the reference would get from ``IFNet("4.6")``
@@ -61,7 +70,7 @@ def synthetic_state_dict(seed: int = 0, flow_gain: float = 1.0, beta_jitter: flo
     """
     g = torch.Generator().manual_seed(seed)
     sd: Dict[str, torch.Tensor] = {}
-    for name, shape in state_dict_spec():
+    for name, shape in state_dict_spec(arch):
         if name.endswith("beta"):
             sd[name] = 1.0 + beta_jitter * (2 * torch.rand(shape, generator=g) - 1)
             continue
@@ -185,6 +194,53 @@ def ifnet46_forward(sd: Dict[str, torch.Tensor], img0: torch.Tensor, img1: torch
     return merged[:, :, :h, :w]
 
 
+def ifnet47_forward(sd: Dict[str, torch.Tensor], img0: torch.Tensor, img1: torch.Tensor, timestep: torch.Tensor,
+                    scale_list: Sequence[float] = (8, 4, 2, 1), taps: Optional[dict] = None) -> torch.Tensor:
+    """IFNet.forward restricted to arch 4.7 (rife47.pth / rife49.pth), ensemble=False -- rife_arch.py:465-732.
+
+    Differences to 4.6: f0/f1 = encode(img) (Conv2d 3->16 s2, ConvTranspose2d 16->4, no activation; :501-503) are
+    concatenated to block 0's input (:543-548) and, warped with the current flow, to the later blocks' inputs
+    (:629-645); `flow = flow + fd` but `mask = m0` is REPLACED, not accumulated (:646, :698-699); the final blend
+    uses sigmoid of that last mask (:721-723)."""
+    img0 = torch.clamp(img0, 0, 1)
+    img1 = torch.clamp(img1, 0, 1)
+    n, c, h, w = img0.shape
+    ph = ((h - 1) // 64 + 1) * 64
+    pw = ((w - 1) // 64 + 1) * 64
+    img0 = F.pad(img0, (0, pw - w, 0, ph - h))
+    img1 = F.pad(img1, (0, pw - w, 0, ph - h))
+    t = timestep.reshape(n, 1, 1, 1).to(img0.dtype).repeat(1, 1, ph, pw)
+
+    def encode(x):
+        y = F.conv2d(x, sd["encode.0.weight"], sd["encode.0.bias"], stride=2, padding=1)
+        return F.conv_transpose2d(y, sd["encode.1.weight"], sd["encode.1.bias"], stride=2, padding=1)
+
+    f0, f1 = encode(img0), encode(img1)
+    if taps is not None:
+        taps["f0"], taps["f1"] = f0, f1
+    w0, w1, flow, mask = img0, img1, None, None
+    for i in range(4):
+        if flow is None:
+            flow, mask = ifblock(sd, i, torch.cat((img0, img1, f0, f1, t), 1), None, scale_list[i], taps)
+        else:
+            fd, m0 = ifblock(sd, i, torch.cat((w0, w1, warp(f0, flow[:, :2]), warp(f1, flow[:, 2:4]), t, mask), 1),
+                             flow, scale_list[i], taps)
+            flow = flow + fd
+            mask = m0
+        if taps is not None:
+            taps[f"flow{i}"] = flow
+            taps[f"mask{i}"] = mask
+        w0 = warp(img0, flow[:, :2])
+        w1 = warp(img1, flow[:, 2:4])
+    m = torch.sigmoid(mask)
+    merged = w0 * m + w1 * (1 - m)
+    return merged[:, :, :h, :w]
+
+
+def ifnet_forward(arch: str, sd, img0, img1, timestep, scale_list=(8, 4, 2, 1), taps=None):
+    return (ifnet46_forward if arch == "4.6" else ifnet47_forward)(sd, img0, img1, timestep, scale_list, taps)
+
+
 # --------------------------------------------------------------------------------------
 # node-level loop
 # --------------------------------------------------------------------------------------
@@ -213,7 +269,8 @@ def build_tasks(n_frames: int, multiplier, states: Optional[Tuple[Sequence[int],
 
 
 def rife_vfi(sd: Dict[str, torch.Tensor], frames: torch.Tensor, multiplier=2, scale_factor: float = 1.0,
-             states: Optional[Tuple[Sequence[int], bool]] = None, batch_size: int = 1) -> torch.Tensor:
+             states: Optional[Tuple[Sequence[int], bool]] = None, batch_size: int = 1,
+             arch: str = "4.6") -> torch.Tensor:
     """RIFE_VFI.vfi for ckpt arch 4.6, dtype float32 -- rife/__init__.py:146-239.
 
     frames: [N,H,W,C>=3] fp32 NHWC in [0,1]; returns [(sum over pairs of mids)+N, H, W, 3] fp32
@@ -231,7 +288,7 @@ def rife_vfi(sd: Dict[str, torch.Tensor], frames: torch.Tensor, multiplier=2, sc
             f0 = torch.cat([fr[p:p + 1] for p, _ in bt]).float()
             f1 = torch.cat([fr[p + 1:p + 2] for p, _ in bt]).float()
             ts = torch.tensor([t for _, t in bt], dtype=torch.float32).view(-1, 1, 1, 1)
-            mid = ifnet46_forward(sd, f0, f1, ts, scale_list).clamp(0, 1)
+            mid = ifnet_forward(arch, sd, f0, f1, ts, scale_list).clamp(0, 1)
             for k, (p, _) in enumerate(bt):
                 results[p].append(mid[k:k + 1])
             pos += len(bt)

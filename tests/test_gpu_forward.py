@@ -32,7 +32,7 @@ def test_ifnet_golden(pkg, name, dtype):
     """C-ABI forward vs the UNMODIFIED reference's output (tests/golden, made by tools/make_golden.py)."""
     cfg = cases()[name]
     ref = torch.from_numpy(np.load(os.path.join(GOLD, name + ".npz"))["out"]).clamp(0, 1)  # node clamps, :207
-    sd = O.synthetic_state_dict(cfg["seed"], cfg["gain"])
+    sd = O.synthetic_state_dict(cfg["seed"], cfg["gain"], arch=cfg.get("arch", "4.6"))
     fr = make_inputs(cfg)
     eng = _engine(pkg, sd, dtype)
     b = len(cfg["ts"])
@@ -43,16 +43,17 @@ def test_ifnet_golden(pkg, name, dtype):
     assert p >= PSNR_MIN
 
 
-def test_flow_and_mask_match_oracle(pkg):
+@pytest.mark.parametrize("arch", ["4.6", "4.7"])
+def test_flow_and_mask_match_oracle(pkg, arch):
     """Intermediate state: final full-resolution flow / mask vs the oracle's (fp32)."""
-    sd = O.synthetic_state_dict(0)
+    sd = O.synthetic_state_dict(0, arch=arch)
     fr = O.synthetic_clip(2, 96, 160, seed=11)
     eng = _engine(pkg, sd)
     eng.forward(fr.cuda(), [0], [1], [0.5])
     flow, mask = eng.debug_state(1)
     taps = {}
-    O.ifnet46_forward(sd, fr[0:1].permute(0, 3, 1, 2), fr[1:2].permute(0, 3, 1, 2),
-                      torch.tensor([0.5]).view(1, 1, 1, 1), taps=taps)
+    O.ifnet_forward(arch, sd, fr[0:1].permute(0, 3, 1, 2), fr[1:2].permute(0, 3, 1, 2),
+                    torch.tensor([0.5]).view(1, 1, 1, 1), taps=taps)
     eng.close()
     f_ref = taps["flow3"].permute(0, 2, 3, 1)
     m_ref = taps["mask3"][:, 0]
@@ -112,8 +113,9 @@ def test_node_golden(pkg, name, tmp_path, monkeypatch):
     import cfi_b200.node as N
     cfg = cases()[name]
     ref = torch.from_numpy(np.load(os.path.join(GOLD, name + ".npz"))["out"])
-    sd = O.synthetic_state_dict(cfg["seed"], cfg["gain"])
-    path = tmp_path / "rife46.pth"
+    sd = O.synthetic_state_dict(cfg["seed"], cfg["gain"], arch=cfg.get("arch", "4.6"))
+    ckpt = cfg.get("ckpt", "rife46.pth")
+    path = tmp_path / ckpt
     torch.save(sd, path)
     monkeypatch.setattr(N, "load_file_from_github_release", lambda model_type, ckpt_name: str(path))
     N._model_cache.clear()
@@ -121,7 +123,7 @@ def test_node_golden(pkg, name, tmp_path, monkeypatch):
     st = None
     if cfg["states"] is not None:
         st = N.InterpolationStateList(list(cfg["states"][0]), cfg["states"][1])
-    (out,) = N.RIFE_VFI().vfi("rife46.pth", fr, multiplier=cfg["multiplier"], optional_interpolation_states=st)
+    (out,) = N.RIFE_VFI().vfi(ckpt, fr, multiplier=cfg["multiplier"], optional_interpolation_states=st)
     N._model_cache.clear()
     assert out.shape == ref.shape and out.dtype == torch.float32 and not out.is_cuda
     tasks, mults = O.build_tasks(cfg["n"], cfg["multiplier"], cfg["states"])

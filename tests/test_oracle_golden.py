@@ -19,15 +19,16 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 def test_oracle_matches_reference_output(name):
     cfg = cases()[name]
     ref = torch.from_numpy(np.load(os.path.join(GOLD, name + ".npz"))["out"])
-    sd = O.synthetic_state_dict(cfg["seed"], cfg["gain"])
+    arch = cfg.get("arch", "4.6")
+    sd = O.synthetic_state_dict(cfg["seed"], cfg["gain"], arch=arch)
     fr = make_inputs(cfg)
     if cfg["kind"] == "ifnet":
         x = fr.permute(0, 3, 1, 2)
         b = len(cfg["ts"])
         ts = torch.tensor(cfg["ts"], dtype=torch.float32).view(-1, 1, 1, 1)
-        out = O.ifnet46_forward(sd, x[0:1].repeat(b, 1, 1, 1), x[1:2].repeat(b, 1, 1, 1), ts)
+        out = O.ifnet_forward(arch, sd, x[0:1].repeat(b, 1, 1, 1), x[1:2].repeat(b, 1, 1, 1), ts)
     else:
-        out = O.rife_vfi(sd, fr, multiplier=cfg["multiplier"], states=cfg["states"])
+        out = O.rife_vfi(sd, fr, multiplier=cfg["multiplier"], states=cfg["states"], arch=arch)
     assert out.shape == ref.shape
     # same ATen CPU kernels in the same order: agreement is at rounding level
     assert (out - ref).abs().max().item() <= 1e-6

@@ -55,6 +55,11 @@ def cases():
         # node level: per-pair multiplier list shorter than the pair count (padded with 2), entry 1 => no mids
         "node_mlist": dict(kind="node", seed=2, gain=2.0, n=5, h=64, w=64, c=3, multiplier=[2, 1, 3],
                            states=None, clip_seed=14),
+        # arch 4.7 (rife47.pth / rife49.pth): encode head, feature warps, replaced mask
+        "ifnet47_96x160": dict(kind="ifnet", arch="4.7", seed=8, gain=1.0, h=96, w=160, ts=(0.5, 0.3), clip_seed=16),
+        "ifnet47_64x128_gain3": dict(kind="ifnet", arch="4.7", seed=9, gain=3.0, h=64, w=128, ts=(0.5,), clip_seed=17),
+        "node47_m2": dict(kind="node", arch="4.7", ckpt="rife49.pth", seed=10, gain=1.0, n=3, h=56, w=88, c=3,
+                          multiplier=2, states=None, clip_seed=18),
         # node level: keep-list (is_skip_list False)
         "node_keep": dict(kind="node", seed=4, gain=1.0, n=4, h=48, w=80, c=3, multiplier=2,
                           states=([0, 2], False), clip_seed=15),
@@ -108,10 +113,11 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     R.CKPT_NAME_VER_DICT["rife46.pth"] = "4.6"
     for name, cfg in cases().items():
-        sd = O.synthetic_state_dict(cfg["seed"], cfg["gain"])
+        arch = cfg.get("arch", "4.6")
+        sd = O.synthetic_state_dict(cfg["seed"], cfg["gain"], arch=arch)
         fr = make_inputs(cfg)
         if cfg["kind"] == "ifnet":
-            m = IFNet(arch_ver="4.6").eval()
+            m = IFNet(arch_ver=arch).eval()
             m.load_state_dict(sd)
             x = fr.permute(0, 3, 1, 2)
             ts = torch.tensor(cfg["ts"], dtype=torch.float32).view(-1, 1, 1, 1)
@@ -121,14 +127,15 @@ def main():
             np.savez_compressed(os.path.join(out_dir, name + ".npz"), out=out.numpy())
         else:
             with tempfile.TemporaryDirectory() as td:
-                path = os.path.join(td, "rife46.pth")
+                ckpt = cfg.get("ckpt", "rife46.pth")
+                path = os.path.join(td, ckpt)
                 torch.save(sd, path)
                 R.load_file_from_github_release = lambda model_type, ckpt_name, _p=path: _p
                 R._model_cache.clear()
                 st = None
                 if cfg["states"] is not None:
                     st = InterpolationStateList(list(cfg["states"][0]), cfg["states"][1])
-                (out,) = R.RIFE_VFI().vfi("rife46.pth", fr, multiplier=cfg["multiplier"],
+                (out,) = R.RIFE_VFI().vfi(ckpt, fr, multiplier=cfg["multiplier"],
                                           optional_interpolation_states=st)
             np.savez_compressed(os.path.join(out_dir, name + ".npz"), out=out.numpy())
         print(name, tuple(out.shape), float(out.mean()))

@@ -591,19 +591,19 @@ int vfi_rife46_interpolate_host(vfi_ctx* c, const float* frames, int n_frames, i
       for (int i = 0; i < n; ++i) need = std::max(need, std::max(f0[pos + i], f1[pos + i]) + 1);
       // H2D + prep of the frames this pass needs, in ring-sized groups, on the copy stream
       while (uploaded < need) {
-        const int cnt = std::min(need - uploaded, kRaw / 2);
-        for (int i = 0; i < cnt; ++i) {
-          const int f = uploaded + i;
-          CK(cudaMemcpyAsync((float*)c->raw.p + (size_t)(f % kRaw) * frame_elems, frames + (size_t)f * frame_elems,
-                             frame_elems * sizeof(float), cudaMemcpyHostToDevice, c->s_h2d));
-          LAUNCH(launch_prep_frames((float*)c->raw.p + (size_t)(f % kRaw) * frame_elems, 1, H, W, C,
-                                    (float4*)c->imgs.p + (size_t)(f - frame_lo) * g.Hp * g.Wp, g.Hp, g.Wp, c->s_h2d));
-          if (c->arch == 47)
-            LAUNCH(launch_encode((const float4*)c->imgs.p + (size_t)(f - frame_lo) * g.Hp * g.Wp, c->enc[0], c->enc[1],
-                                 c->enc[2], c->enc[3], (float*)c->e16.p,
-                                 (float4*)c->feats.p + (size_t)(f - frame_lo) * g.Hp * g.Wp, 1, g.Hp, g.Wp, c->s_h2d));
-        }
-        uploaded += cnt;
+        // one copy + one prep launch per contiguous run of ring slots (source frames are contiguous on the host)
+        const int slot = uploaded % kRaw;
+        const int run = std::min(std::min(need - uploaded, kRaw / 2), kRaw - slot);
+        float* rawp = (float*)c->raw.p + (size_t)slot * frame_elems;
+        float4* imgp = (float4*)c->imgs.p + (size_t)(uploaded - frame_lo) * g.Hp * g.Wp;
+        CK(cudaMemcpyAsync(rawp, frames + (size_t)uploaded * frame_elems, (size_t)run * frame_elems * sizeof(float),
+                           cudaMemcpyHostToDevice, c->s_h2d));
+        LAUNCH(launch_prep_frames(rawp, run, H, W, C, imgp, g.Hp, g.Wp, c->s_h2d));
+        if (c->arch == 47)
+          LAUNCH(launch_encode(imgp, c->enc[0], c->enc[1], c->enc[2], c->enc[3], (float*)c->e16.p,
+                               (float4*)c->feats.p + (size_t)(uploaded - frame_lo) * g.Hp * g.Wp, run, g.Hp, g.Wp,
+                               c->s_h2d));
+        uploaded += run;
       }
       CK(cudaEventRecord(ev_up[k], c->s_h2d));
       CK(cudaStreamWaitEvent(c->s_comp, ev_up[k], 0));

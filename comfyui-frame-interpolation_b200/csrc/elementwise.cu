@@ -166,9 +166,10 @@ __device__ __forceinline__ void flow_at(const FlowLevels& L, int b, int Hp, int 
 
 // one thread = one cell of the 1/s grid; channels: w0.rgb, w1.rgb, t, mask, flow/s (4) [, 4 zero pad].
 // Thread order (b, row pair, x, row parity) so that 4 consecutive lanes fill one 128-byte space-to-depth cell.
-template <typename T, int NLEV>
+template <typename T, int NLEV, int S>
 __global__ void front_kernel(const float4* __restrict__ imgs, const FlowLevels lev, const BatchTasks tasks, int Hp,
-                             int Wp, int s, T* __restrict__ x_s2d) {
+                             int Wp, int s_rt, T* __restrict__ x_s2d) {
+  const int s = S ? S : s_rt;
   const int Hs = Hp / s, Ws = Wp / s;
   const size_t total = (size_t)tasks.n * Hs * Ws;
   const size_t plane = (size_t)Hp * Wp;
@@ -222,6 +223,143 @@ __global__ void front_kernel(const float4* __restrict__ imgs, const FlowLevels l
     for (int i = 8; i < 12; ++i) ch[i] *= inv_s;  // flow is also divided by the scale (rife_arch.py:242-248)
 
     // space-to-depth store: cell (yl, xl) -> [b, yl/2, xl/2, ((yl&1)*2 + (xl&1))*16 + c]
+    const size_t cell = ((size_t)b * (Hs >> 1) + (yl >> 1)) * (Ws >> 1) + (xl >> 1);
+    T* dst = x_s2d + cell * 64 + ((yl & 1) * 2 + (xl & 1)) * 16;
+    uint4 lo, hi;
+    lo.x = Pack2<T>::pack(ch[0], ch[1]);
+    lo.y = Pack2<T>::pack(ch[2], ch[3]);
+    lo.z = Pack2<T>::pack(ch[4], ch[5]);
+    lo.w = Pack2<T>::pack(ch[6], ch[7]);
+    hi.x = Pack2<T>::pack(ch[8], ch[9]);
+    hi.y = Pack2<T>::pack(ch[10], ch[11]);
+    hi.z = 0u;
+    hi.w = 0u;
+    reinterpret_cast<uint4*>(dst)[0] = lo;
+    reinterpret_cast<uint4*>(dst)[1] = hi;
+  }
+}
+
+
+// ---- scale-2 front with shared level taps ---------------------------------------------------------------------
+// The four full-resolution pixels (2yl+ty, 2xl+tx) of one half-resolution cell fall between the same 2x2 samples of
+// every coarser level (scale s_l = 4, 8, ...: an integer sample boundary u = n would need s_l(n + 1/2) = 2xl + 1,
+// even = odd), so the level taps are loaded once per cell and only the bilinear weights differ per pixel.  Same
+// arithmetic per pixel as up_level()/flow_at().
+struct LevelTap {
+  float4 a, b, c, d;
+  float ma, mb, mc, md;
+  float fy0, fx0, inv_s, sc;
+};
+
+__device__ __forceinline__ void load_level_tap(const FlowLevels& L, int j, int b, int Hp, int Wp, int Y0, int X0,
+                                               LevelTap& t) {
+  const int s = L.s[j];
+  const int Hs = Hp / s, Ws = Wp / s;
+  const float4* tf = L.f[j] + (size_t)b * Hs * Ws;
+  const float* tm = L.m[j] + (size_t)b * Hs * Ws;
+  t.inv_s = 1.f / (float)s;
+  t.sc = (float)s;
+  const float sy = fmaxf(((float)Y0 + 0.5f) * t.inv_s - 0.5f, 0.f);
+  const float sx = fmaxf(((float)X0 + 0.5f) * t.inv_s - 0.5f, 0.f);
+  const int y0 = min((int)sy, Hs - 1), x0 = min((int)sx, Ws - 1);
+  const int y1 = min(y0 + 1, Hs - 1), x1 = min(x0 + 1, Ws - 1);
+  t.fy0 = (float)y0;
+  t.fx0 = (float)x0;
+  t.a = __ldg(tf + (size_t)y0 * Ws + x0);
+  t.b = __ldg(tf + (size_t)y0 * Ws + x1);
+  t.c = __ldg(tf + (size_t)y1 * Ws + x0);
+  t.d = __ldg(tf + (size_t)y1 * Ws + x1);
+  t.ma = __ldg(tm + (size_t)y0 * Ws + x0);
+  t.mb = __ldg(tm + (size_t)y0 * Ws + x1);
+  t.mc = __ldg(tm + (size_t)y1 * Ws + x0);
+  t.md = __ldg(tm + (size_t)y1 * Ws + x1);
+}
+
+__device__ __forceinline__ void eval_level_tap(const LevelTap& t, int Y, int X, float4& uf, float& um) {
+  const float sy = fmaxf(((float)Y + 0.5f) * t.inv_s - 0.5f, 0.f);
+  const float sx = fmaxf(((float)X + 0.5f) * t.inv_s - 0.5f, 0.f);
+  const float ly = sy - t.fy0, lx = sx - t.fx0;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  uf.x = hy * (hx * t.a.x + lx * t.b.x) + ly * (hx * t.c.x + lx * t.d.x);
+  uf.y = hy * (hx * t.a.y + lx * t.b.y) + ly * (hx * t.c.y + lx * t.d.y);
+  uf.z = hy * (hx * t.a.z + lx * t.b.z) + ly * (hx * t.c.z + lx * t.d.z);
+  uf.w = hy * (hx * t.a.w + lx * t.b.w) + ly * (hx * t.c.w + lx * t.d.w);
+  um = hy * (hx * t.ma + lx * t.mb) + ly * (hx * t.mc + lx * t.md);
+}
+
+// one thread = one half-resolution cell, no base plane (the first dense front), levels 0..NLEV-1 all of scale >= 4
+template <typename T, int NLEV>
+__global__ void front2_kernel(const float4* __restrict__ imgs, const FlowLevels lev, const BatchTasks tasks, int Hp,
+                              int Wp, T* __restrict__ x_s2d) {
+  const int Hs = Hp >> 1, Ws = Wp >> 1;
+  const size_t total = (size_t)tasks.n * Hs * Ws;
+  const size_t plane = (size_t)Hp * Wp;
+  for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
+    const int par = (int)(id & 1);
+    size_t r = id >> 1;
+    const int xl = (int)(r % Ws);
+    r /= Ws;
+    const int yl = (int)(r % (Hs >> 1)) * 2 + par;
+    const int b = (int)(r / (Hs >> 1));
+    const float4* img0 = imgs + (size_t)tasks.f0[b] * plane;
+    const float4* img1 = imgs + (size_t)tasks.f1[b] * plane;
+    const int Y0 = 2 * yl, X0 = 2 * xl;
+    float4 f[4];
+    float m[4];
+#pragma unroll
+    for (int j = 0; j < NLEV; ++j) {
+      LevelTap tp;
+      load_level_tap(lev, j, b, Hp, Wp, Y0, X0, tp);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 u;
+        float um;
+        eval_level_tap(tp, Y0 + (q >> 1), X0 + (q & 1), u, um);
+        if (j == 0) {
+          f[q] = make_float4(u.x * tp.sc, u.y * tp.sc, u.z * tp.sc, u.w * tp.sc);
+          m[q] = um;
+        } else {
+          f[q].x += u.x * tp.sc;
+          f[q].y += u.y * tp.sc;
+          f[q].z += u.z * tp.sc;
+          f[q].w += u.w * tp.sc;
+          m[q] = lev.mask_replace ? um : m[q] + um;
+        }
+      }
+    }
+    float ch[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) ch[i] = 0.f;
+    // same summation order as the generic kernel: (tap00 + tap01) + (tap10 + tap11), then * 0.25
+    float row[2][12];
+#pragma unroll
+    for (int ty = 0; ty < 2; ++ty) {
+      float v[2][12];
+#pragma unroll
+      for (int tx = 0; tx < 2; ++tx) {
+        const int q = ty * 2 + tx;
+        const int Y = Y0 + ty, X = X0 + tx;
+        const float4 a = sample_border(img0, Hp, Wp, (float)X + f[q].x, (float)Y + f[q].y);
+        const float4 c = sample_border(img1, Hp, Wp, (float)X + f[q].z, (float)Y + f[q].w);
+        v[tx][0] = a.x; v[tx][1] = a.y; v[tx][2] = a.z; v[tx][3] = c.x; v[tx][4] = c.y; v[tx][5] = c.z;
+        v[tx][6] = tasks.t[b]; v[tx][7] = m[q];
+        v[tx][8] = f[q].x; v[tx][9] = f[q].y; v[tx][10] = f[q].z; v[tx][11] = f[q].w;
+      }
+#pragma unroll
+      for (int i = 0; i < 12; ++i) row[ty][i] = v[0][i] + v[1][i];
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) ch[i] = 0.25f * (row[0][i] + row[1][i]);
+#pragma unroll
+    for (int i = 8; i < 12; ++i) ch[i] *= 0.5f;
+    if (lev.out_f != nullptr) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const size_t pid = ((size_t)b * Hp + Y0 + (q >> 1)) * Wp + X0 + (q & 1);
+        lev.out_f[pid] = f[q];
+        lev.out_m[pid] = m[q];
+      }
+    }
     const size_t cell = ((size_t)b * (Hs >> 1) + (yl >> 1)) * (Ws >> 1) + (xl >> 1);
     T* dst = x_s2d + cell * 64 + ((yl & 1) * 2 + (xl & 1)) * 16;
     uint4 lo, hi;
@@ -532,13 +670,39 @@ static void launch_front47_t(int nlev, int g, cudaStream_t st, const float4* img
 }
 
 template <typename T>
-static void launch_front_t(int nlev, int g, cudaStream_t st, const float4* imgs, const FlowLevels& L,
-                           const BatchTasks& tasks, int Hp, int Wp, int s, void* x) {
+static void launch_front2_t(int nlev, int g, cudaStream_t st, const float4* imgs, const FlowLevels& L,
+                            const BatchTasks& tasks, int Hp, int Wp, void* x) {
   switch (nlev) {
-    case 0: front_kernel<T, 0><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, s, (T*)x); break;
-    case 1: front_kernel<T, 1><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, s, (T*)x); break;
-    case 2: front_kernel<T, 2><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, s, (T*)x); break;
-    default: front_kernel<T, 3><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, s, (T*)x); break;
+    case 1: front2_kernel<T, 1><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, (T*)x); break;
+    case 2: front2_kernel<T, 2><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, (T*)x); break;
+    default: front2_kernel<T, 3><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, (T*)x); break;
+  }
+}
+
+template <typename T, int S>
+static void launch_front_ts(int nlev, int g, cudaStream_t st, const float4* imgs, const FlowLevels& L,
+                            const BatchTasks& tasks, int Hp, int Wp, int s, void* x) {
+  switch (nlev) {
+    case 0: front_kernel<T, 0, S><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, s, (T*)x); break;
+    case 1: front_kernel<T, 1, S><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, s, (T*)x); break;
+    case 2: front_kernel<T, 2, S><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, s, (T*)x); break;
+    default: front_kernel<T, 3, S><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, s, (T*)x); break;
+  }
+}
+
+template <typename T>
+static void launch_front_t(int nlev, bool shared_taps, int g, cudaStream_t st, const float4* imgs, const FlowLevels& L,
+                           const BatchTasks& tasks, int Hp, int Wp, int s, void* x) {
+  if (shared_taps) {
+    switch (nlev) {
+      case 1: front2_kernel<T, 1><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, (T*)x); break;
+      case 2: front2_kernel<T, 2><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, (T*)x); break;
+      default: front2_kernel<T, 3><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, (T*)x); break;
+    }
+  } else if (s == 1) {
+    launch_front_ts<T, 1>(nlev, g, st, imgs, L, tasks, Hp, Wp, s, x);  // compile-time scale: 56 instead of 93 registers
+  } else {
+    launch_front_ts<T, 0>(nlev, g, st, imgs, L, tasks, Hp, Wp, s, x);
   }
 }
 
@@ -568,10 +732,14 @@ cudaError_t launch_front(int op_type, const float4* imgs, const float4* feats, c
       launch_front47_t<__half>(blk == 0 ? 0 : nlev, g, st, imgs, feats, L, tasks, Hp, Wp, s, x_s2d);
     return cudaGetLastError();
   }
+  // scale-2 front without a base plane whose levels are all at scale 4, 8, ...: the level taps are shared per cell
+  bool shared_taps = (s == 2 && blk > 0 && base_f == nullptr && nlev >= 1);
+  for (int j = 0; j < nlev; ++j) shared_taps = shared_taps && L.s[j] >= 4 && (L.s[j] & (L.s[j] - 1)) == 0;
+  const int nl = blk == 0 ? 0 : (nlev == 0 ? 1 : nlev);
   if (op_type == OP_BF16)
-    launch_front_t<__nv_bfloat16>(blk == 0 ? 0 : (nlev == 0 ? 1 : nlev), g, st, imgs, L, tasks, Hp, Wp, s, x_s2d);
+    launch_front_t<__nv_bfloat16>(nl, shared_taps, g, st, imgs, L, tasks, Hp, Wp, s, x_s2d);
   else
-    launch_front_t<__half>(blk == 0 ? 0 : (nlev == 0 ? 1 : nlev), g, st, imgs, L, tasks, Hp, Wp, s, x_s2d);
+    launch_front_t<__half>(nl, shared_taps, g, st, imgs, L, tasks, Hp, Wp, s, x_s2d);
   return cudaGetLastError();
 }
 

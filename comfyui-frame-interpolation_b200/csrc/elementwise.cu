@@ -15,7 +15,7 @@ namespace {
 __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
 
 __global__ void prep_frames_kernel(const float* __restrict__ frames, int n, int H, int W, int cstride,
-                                   float4* __restrict__ imgs, int Hp, int Wp) {
+                                   float4* __restrict__ imgs, uint2* __restrict__ imgs_h, int Hp, int Wp) {
   const size_t total = (size_t)n * Hp * Wp;
   for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
     const int x = (int)(id % Wp);
@@ -30,7 +30,14 @@ __global__ void prep_frames_kernel(const float* __restrict__ frames, int n, int 
       v.z = clamp01(__ldg(s + 2));
     }
     imgs[id] = v;
+    imgs_h[id] = make_uint2(Pack2<__half>::pack(v.x, v.y), Pack2<__half>::pack(v.z, 0.f));
   }
+}
+
+// half4 pixel -> float4
+__device__ __forceinline__ float4 unpack_h4(uint2 q) {
+  const float2 a = Pack2<__half>::unpack(q.x), b = Pack2<__half>::unpack(q.y);
+  return make_float4(a.x, a.y, b.x, b.y);
 }
 
 // grid_sample(bilinear, border, align_corners=True) at (x + fx, y + fy) of a float4 image [Hp][Wp]
@@ -46,6 +53,27 @@ __device__ __forceinline__ float4 sample_border(const float4* __restrict__ img, 
   const float4 b = __ldg(img + (size_t)y0 * Wp + x1);
   const float4 c = __ldg(img + (size_t)y1 * Wp + x0);
   const float4 d = __ldg(img + (size_t)y1 * Wp + x1);
+  float4 o;
+  o.x = a.x * w00 + b.x * w01 + c.x * w10 + d.x * w11;
+  o.y = a.y * w00 + b.y * w01 + c.y * w10 + d.y * w11;
+  o.z = a.z * w00 + b.z * w01 + c.z * w10 + d.z * w11;
+  o.w = 0.f;
+  return o;
+}
+
+// the same sampling of a half4 image plane (block inputs; interpolation in fp32)
+__device__ __forceinline__ float4 sample_border(const uint2* __restrict__ img, int Hp, int Wp, float sx, float sy) {
+  sx = fminf(fmaxf(sx, 0.f), (float)(Wp - 1));
+  sy = fminf(fmaxf(sy, 0.f), (float)(Hp - 1));
+  const float fx0 = floorf(sx), fy0 = floorf(sy);
+  const int x0 = (int)fx0, y0 = (int)fy0;
+  const int x1 = min(x0 + 1, Wp - 1), y1 = min(y0 + 1, Hp - 1);
+  const float ax = sx - fx0, ay = sy - fy0;
+  const float w00 = (1.f - ax) * (1.f - ay), w01 = ax * (1.f - ay), w10 = (1.f - ax) * ay, w11 = ax * ay;
+  const float4 a = unpack_h4(__ldg(img + (size_t)y0 * Wp + x0));
+  const float4 b = unpack_h4(__ldg(img + (size_t)y0 * Wp + x1));
+  const float4 c = unpack_h4(__ldg(img + (size_t)y1 * Wp + x0));
+  const float4 d = unpack_h4(__ldg(img + (size_t)y1 * Wp + x1));
   float4 o;
   o.x = a.x * w00 + b.x * w01 + c.x * w10 + d.x * w11;
   o.y = a.y * w00 + b.y * w01 + c.y * w10 + d.y * w11;
@@ -167,7 +195,7 @@ __device__ __forceinline__ void flow_at(const FlowLevels& L, int b, int Hp, int 
 // one thread = one cell of the 1/s grid; channels: w0.rgb, w1.rgb, t, mask, flow/s (4) [, 4 zero pad].
 // Thread order (b, row pair, x, row parity) so that 4 consecutive lanes fill one 128-byte space-to-depth cell.
 template <typename T, int NLEV, int S>
-__global__ void front_kernel(const float4* __restrict__ imgs, const FlowLevels lev, const BatchTasks tasks, int Hp,
+__global__ void front_kernel(const uint2* __restrict__ imgs, const FlowLevels lev, const BatchTasks tasks, int Hp,
                              int Wp, int s_rt, T* __restrict__ x_s2d) {
   const int s = S ? S : s_rt;
   const int Hs = Hp / s, Ws = Wp / s;
@@ -181,8 +209,8 @@ __global__ void front_kernel(const float4* __restrict__ imgs, const FlowLevels l
     r /= Ws;
     const int yl = (int)(r % (Hs >> 1)) * 2 + par;
     const int b = (int)(r / (Hs >> 1));
-    const float4* img0 = imgs + (size_t)tasks.f0[b] * plane;
-    const float4* img1 = imgs + (size_t)tasks.f1[b] * plane;
+    const uint2* img0 = imgs + (size_t)tasks.f0[b] * plane;
+    const uint2* img1 = imgs + (size_t)tasks.f1[b] * plane;
     const float t = tasks.t[b];
     // bilinear 1/s, align_corners=False: the two source taps per axis are s*i + s/2 - 1 and s*i + s/2, weight 1/2
     const int ntap = (s == 1) ? 1 : 2;
@@ -199,8 +227,8 @@ __global__ void front_kernel(const float4* __restrict__ imgs, const FlowLevels l
           const int Y = by + ty, X = bx + tx;
           float* v = colv[tx];
           if (NLEV == 0) {
-            const float4 a = __ldg(img0 + (size_t)Y * Wp + X);
-            const float4 c = __ldg(img1 + (size_t)Y * Wp + X);
+            const float4 a = unpack_h4(__ldg(img0 + (size_t)Y * Wp + X));
+            const float4 c = unpack_h4(__ldg(img1 + (size_t)Y * Wp + X));
             v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = c.x; v[4] = c.y; v[5] = c.z;
             v[6] = t; v[7] = 0.f; v[8] = 0.f; v[9] = 0.f; v[10] = 0.f; v[11] = 0.f;
           } else {
@@ -289,7 +317,7 @@ __device__ __forceinline__ void eval_level_tap(const LevelTap& t, int Y, int X, 
 
 // one thread = one half-resolution cell, no base plane (the first dense front), levels 0..NLEV-1 all of scale >= 4
 template <typename T, int NLEV>
-__global__ void front2_kernel(const float4* __restrict__ imgs, const FlowLevels lev, const BatchTasks tasks, int Hp,
+__global__ void front2_kernel(const uint2* __restrict__ imgs, const FlowLevels lev, const BatchTasks tasks, int Hp,
                               int Wp, T* __restrict__ x_s2d) {
   const int Hs = Hp >> 1, Ws = Wp >> 1;
   const size_t total = (size_t)tasks.n * Hs * Ws;
@@ -301,8 +329,8 @@ __global__ void front2_kernel(const float4* __restrict__ imgs, const FlowLevels 
     r /= Ws;
     const int yl = (int)(r % (Hs >> 1)) * 2 + par;
     const int b = (int)(r / (Hs >> 1));
-    const float4* img0 = imgs + (size_t)tasks.f0[b] * plane;
-    const float4* img1 = imgs + (size_t)tasks.f1[b] * plane;
+    const uint2* img0 = imgs + (size_t)tasks.f0[b] * plane;
+    const uint2* img1 = imgs + (size_t)tasks.f1[b] * plane;
     const int Y0 = 2 * yl, X0 = 2 * xl;
     float4 f[4];
     float m[4];
@@ -634,10 +662,10 @@ inline int grid_for(size_t total, int block) {
 
 }  // namespace
 
-cudaError_t launch_prep_frames(const float* frames, int n, int H, int W, int cstride, float4* imgs, int Hp, int Wp,
-                               cudaStream_t st) {
+cudaError_t launch_prep_frames(const float* frames, int n, int H, int W, int cstride, float4* imgs, uint2* imgs_h,
+                               int Hp, int Wp, cudaStream_t st) {
   const size_t total = (size_t)n * Hp * Wp;
-  prep_frames_kernel<<<grid_for(total, 256), 256, 0, st>>>(frames, n, H, W, cstride, imgs, Hp, Wp);
+  prep_frames_kernel<<<grid_for(total, 256), 256, 0, st>>>(frames, n, H, W, cstride, imgs, imgs_h, Hp, Wp);
   return cudaGetLastError();
 }
 
@@ -680,7 +708,7 @@ static void launch_front2_t(int nlev, int g, cudaStream_t st, const float4* imgs
 }
 
 template <typename T, int S>
-static void launch_front_ts(int nlev, int g, cudaStream_t st, const float4* imgs, const FlowLevels& L,
+static void launch_front_ts(int nlev, int g, cudaStream_t st, const uint2* imgs, const FlowLevels& L,
                             const BatchTasks& tasks, int Hp, int Wp, int s, void* x) {
   switch (nlev) {
     case 0: front_kernel<T, 0, S><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, s, (T*)x); break;
@@ -691,7 +719,7 @@ static void launch_front_ts(int nlev, int g, cudaStream_t st, const float4* imgs
 }
 
 template <typename T>
-static void launch_front_t(int nlev, bool shared_taps, int g, cudaStream_t st, const float4* imgs, const FlowLevels& L,
+static void launch_front_t(int nlev, bool shared_taps, int g, cudaStream_t st, const uint2* imgs, const FlowLevels& L,
                            const BatchTasks& tasks, int Hp, int Wp, int s, void* x) {
   if (shared_taps) {
     switch (nlev) {
@@ -717,8 +745,8 @@ cudaError_t launch_encode(const float4* imgs, const float* w0, const float* b0, 
   return cudaGetLastError();
 }
 
-cudaError_t launch_front(int op_type, const float4* imgs, const float4* feats, const FlowState& fs, int blk, int lo,
-                         const float4* base_f, const float* base_m, float4* out_f, float* out_m, BatchTasks tasks,
+cudaError_t launch_front(int op_type, const float4* imgs, const uint2* imgs_h, const float4* feats, const FlowState& fs,
+                         int blk, int lo, const float4* base_f, const float* base_m, float4* out_f, float* out_m, BatchTasks tasks,
                          int Hp, int Wp, int s, void* x_s2d, cudaStream_t st) {
   const size_t total = (size_t)tasks.n * (Hp / s) * (Wp / s);
   const int g = grid_for(total, 128);
@@ -737,9 +765,9 @@ cudaError_t launch_front(int op_type, const float4* imgs, const float4* feats, c
   for (int j = 0; j < nlev; ++j) shared_taps = shared_taps && L.s[j] >= 4 && (L.s[j] & (L.s[j] - 1)) == 0;
   const int nl = blk == 0 ? 0 : (nlev == 0 ? 1 : nlev);
   if (op_type == OP_BF16)
-    launch_front_t<__nv_bfloat16>(nl, shared_taps, g, st, imgs, L, tasks, Hp, Wp, s, x_s2d);
+    launch_front_t<__nv_bfloat16>(nl, shared_taps, g, st, imgs_h, L, tasks, Hp, Wp, s, x_s2d);
   else
-    launch_front_t<__half>(nl, shared_taps, g, st, imgs, L, tasks, Hp, Wp, s, x_s2d);
+    launch_front_t<__half>(nl, shared_taps, g, st, imgs_h, L, tasks, Hp, Wp, s, x_s2d);
   return cudaGetLastError();
 }
 

@@ -128,7 +128,7 @@ struct vfi_ctx {
   TapConvLayer layers[4][11];  // [block][0=conv0.0, 1=conv0.1, 2..9=ResConv, 10=lastconv]
   std::vector<void*> weight_allocs;
   // workspace
-  DevBuf imgs, flow, mask, x, c00, featA, featB, tF[4], tM[4], raw, outdev;
+  DevBuf imgs, imgs_h, flow, mask, x, c00, featA, featB, tF[4], tM[4], raw, outdev;
   int arch = 46;                 // 46 | 47 (rife47.pth / rife49.pth)
   DevBuf feats, e16;             // arch 4.7: encoded features per source frame (float4), half-res temp
   float* enc[4] = {nullptr, nullptr, nullptr, nullptr};  // encode.0.weight/.bias, encode.1.weight/.bias (fp32)
@@ -211,6 +211,34 @@ int build_conv_s2(vfi_ctx* c, TapConvLayer& L, int Cs, int creal, int cout, int 
   return VFI_OK;
 }
 
+// 3x3 taps over all `ch` input channels.  ring: k-block-major (kb, tap) entries of 64 channels each, the order the
+// ring pipeline consumes the window in (tapconv.cu); the packed weights follow the same order.
+void set_taps_3x3(TapConvLayer& L, int ch, bool ring) {
+  L.ring = ring ? 1 : 0;
+  const int nkb = ring ? ch / 64 : 1;
+  L.ntaps = 9 * nkb;
+  for (int kb = 0; kb < nkb; ++kb)
+    for (int e = 0; e < 9; ++e) {
+      TapEntry& t = L.taps[kb * 9 + e];
+      t.dy = (int16_t)(e / 3 - 1);
+      t.dx = (int16_t)(e % 3 - 1);
+      t.chunk0 = (int16_t)(kb * 8);
+      t.nk16 = (int16_t)(ring ? 4 : ch / 16);
+    }
+}
+
+// Wide, deep layers (c = 128, 192): with the whole window staged per tile the resident weight slice leaves room for
+// only n_cta = 16..32 output channels, and one tcgen05.mma costs ~80 cycles whatever its N (profiles/README.md), so
+// the layer time is ~ 1/n_cta.  The ring pipeline stages one 64-channel k-block at a time, which frees shared
+// memory for n_cta = 48 (c = 192) / 64 (c = 128).  VFI_RING=0 disables it (A/B runs).
+bool want_ring(int ch) {
+  static const bool on = [] {
+    const char* e = std::getenv("VFI_RING");
+    return !(e && e[0] == '0');
+  }();
+  return on && ch >= 128 && ch % 64 == 0;
+}
+
 int build_resconv(vfi_ctx* c, TapConvLayer& L, int ch, const float* beta, const float* w, const float* bias) {
   L = TapConvLayer{};
   L.cin = ch;
@@ -219,16 +247,14 @@ int build_resconv(vfi_ctx* c, TapConvLayer& L, int ch, const float* beta, const 
   L.ktotal16 = 9 * (ch / 16);
   L.halo_y0 = -1; L.halo_x0 = -1; L.halo_h = kTileH + 2; L.halo_w = kTileW + 2;
   L.epi_mode = EPI_RESCONV;
-  for (int ky = 0; ky < 3; ++ky)
-    for (int kx = 0; kx < 3; ++kx) {
-      TapEntry& t = L.taps[ky * 3 + kx];
-      t.dy = (int16_t)(ky - 1); t.dx = (int16_t)(kx - 1); t.chunk0 = 0; t.nk16 = (int16_t)(ch / 16);
-    }
-  choose_split(L, {1, 2, 3, 4, 6, 8, 12}, 3);
+  const bool ring = want_ring(ch);
+  set_taps_3x3(L, ch, ring);
+  choose_split(L, {1, 2, 3, 4, 6, 8, 12}, ring ? 2 : 3);
   // (conv(x) + b) * beta + x  ==  conv_{w*beta}(x) + b*beta + x : beta is folded into the packed weights (one 16-bit
   // rounding of w*beta instead of w) so the epilogue is a pure add
-  auto wf = [&](int e, int ci, int n) -> float {
-    return w[(((size_t)n * ch + ci) * 3 + e / 3) * 3 + e % 3] * beta[n];
+  auto wf = [&](int e, int ci, int n) -> float {  // e = kb * 9 + tap (kb = 0 unless ring), ci relative to the k-block
+    const int tap = e % 9, cin = (e / 9) * 64 + ci;
+    return w[(((size_t)n * ch + cin) * 3 + tap / 3) * 3 + tap % 3] * beta[n];
   };
   std::vector<uint16_t> pk = pack_weights(L, c->op_type, wf);
   std::vector<float> sh(ch);
@@ -250,18 +276,20 @@ int build_lastconv(vfi_ctx* c, TapConvLayer& L, int ch, const float* wt, const f
   L.ktotal16 = 9 * (ch / 16);
   L.halo_y0 = -1; L.halo_x0 = -1; L.halo_h = kTileH + 2; L.halo_w = kTileW + 2;
   L.epi_mode = EPI_LASTCONV;
-  for (int ky = 0; ky < 3; ++ky)
-    for (int kx = 0; kx < 3; ++kx) {
-      TapEntry& t = L.taps[ky * 3 + kx];
-      t.dy = (int16_t)(ky - 1); t.dx = (int16_t)(kx - 1); t.chunk0 = 0; t.nk16 = (int16_t)(ch / 16);
-    }
+  const bool ring = want_ring(ch);
+  set_taps_3x3(L, ch, ring);
   choose_split(L, {1, 5}, 2);
+  if (ring && L.nsplit != 1) {  // the ring only pays when it keeps all 80 columns in one CTA (c = 128)
+    set_taps_3x3(L, ch, false);
+    choose_split(L, {1, 5}, 2);
+  }
   auto oc_of = [](int n) {
     const int c5 = n >> 4, pos = n & 15, py = pos >> 2, px = pos & 3;
     return 4 * c5 + 2 * (py & 1) + (px & 1);
   };
-  auto wf = [&](int e, int ci, int n) -> float {
-    const int dy = e / 3 - 1, dx = e % 3 - 1;
+  auto wf = [&](int e, int cr, int n) -> float {  // e = kb * 9 + tap, cr relative to the k-block
+    const int tap = e % 9, ci = (e / 9) * 64 + cr;
+    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
     const int pos = n & 15, py = pos >> 2, px = pos & 3;
     const int ky = (py >> 1) + 1 - 2 * dy, kx = (px >> 1) + 1 - 2 * dx;
     if (ky < 0 || ky > 3 || kx < 0 || kx > 3) return 0.f;
@@ -311,6 +339,7 @@ int ensure_workspace(vfi_ctx* c, const Geometry& g, int B, int n_frames_window) 
   }
   const size_t px = (size_t)g.Hp * g.Wp;
   CK(c->imgs.ensure((size_t)n_frames_window * px * sizeof(float4)));
+  CK(c->imgs_h.ensure((size_t)n_frames_window * px * sizeof(uint2)));
   if (c->arch == 47) {
     CK(c->feats.ensure((size_t)n_frames_window * px * sizeof(float4)));
     CK(c->e16.ensure((size_t)(kMaxBatch + 2) * (px / 4) * 16 * sizeof(float)));
@@ -340,6 +369,7 @@ int ensure_workspace(vfi_ctx* c, const Geometry& g, int B, int n_frames_window) 
 int forward_pass(vfi_ctx* c, const Geometry& g, const BatchTasks& tasks, int H, int W, float* out, cudaStream_t st) {
   const int B = tasks.n;
   const float4* imgs = (const float4*)c->imgs.p;
+  const uint2* imgs_h = (const uint2*)c->imgs_h.p;
   const float4* feats = c->arch == 47 ? (const float4*)c->feats.p : nullptr;
   float4* F = (float4*)c->flow.p;  // accumulated full-resolution flow / mask, written only by "dense" fronts
   float* M = (float*)c->mask.p;
@@ -359,10 +389,10 @@ int forward_pass(vfi_ctx* c, const Geometry& g, const BatchTasks& tasks, int H, 
     const int s = g.s[i];
     const int Hs = g.Hp / s, Ws = g.Wp / s;
     if (i == 0 || i < dense) {
-      LAUNCH(launch_front(c->op_type, imgs, feats, fs, i, 0, nullptr, nullptr, nullptr, nullptr, tasks, g.Hp, g.Wp, s,
+      LAUNCH(launch_front(c->op_type, imgs, imgs_h, feats, fs, i, 0, nullptr, nullptr, nullptr, nullptr, tasks, g.Hp, g.Wp, s,
                           c->x.p, st));
     } else {
-      LAUNCH(launch_front(c->op_type, imgs, feats, fs, i, lo, have_base ? F : nullptr, have_base ? M : nullptr, F, M, tasks,
+      LAUNCH(launch_front(c->op_type, imgs, imgs_h, feats, fs, i, lo, have_base ? F : nullptr, have_base ? M : nullptr, F, M, tasks,
                           g.Hp, g.Wp, s, c->x.p, st));
       have_base = true;
       lo = i;
@@ -429,7 +459,7 @@ int vfi_destroy(vfi_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   free_weights(c);
-  for (DevBuf* b : {&c->imgs, &c->flow, &c->mask, &c->x, &c->c00, &c->featA, &c->featB, &c->raw, &c->outdev, &c->feats, &c->e16, &c->dbgF,
+  for (DevBuf* b : {&c->imgs, &c->imgs_h, &c->flow, &c->mask, &c->x, &c->c00, &c->featA, &c->featB, &c->raw, &c->outdev, &c->feats, &c->e16, &c->dbgF,
                     &c->dbgM})
     b->release();
   for (int i = 0; i < 4; ++i) {
@@ -530,7 +560,8 @@ int vfi_rife46_forward(vfi_ctx* c, const float* frames, int n_frames, int H, int
   const int B = std::min(c->batch, n_tasks);
   if ((r = ensure_workspace(c, g, B, hi - lo))) return r;
   cudaStream_t st = (cudaStream_t)stream;
-  LAUNCH(launch_prep_frames(frames + (size_t)lo * H * W * C, hi - lo, H, W, C, (float4*)c->imgs.p, g.Hp, g.Wp, st));
+  LAUNCH(launch_prep_frames(frames + (size_t)lo * H * W * C, hi - lo, H, W, C, (float4*)c->imgs.p, (uint2*)c->imgs_h.p,
+                            g.Hp, g.Wp, st));
   if (c->arch == 47) {  // encode head, once per source frame, in groups that fit the half-resolution scratch
     const size_t px = (size_t)g.Hp * g.Wp;
     for (int f = 0; f < hi - lo; f += kMaxBatch) {
@@ -621,7 +652,8 @@ int vfi_rife46_interpolate_host(vfi_ctx* c, const float* frames, int n_frames, i
         float4* imgp = (float4*)c->imgs.p + (size_t)(uploaded - frame_lo) * g.Hp * g.Wp;
         CK(cudaMemcpyAsync(rawp, frames + (size_t)uploaded * frame_elems, (size_t)run * frame_elems * sizeof(float),
                            cudaMemcpyHostToDevice, c->s_h2d));
-        LAUNCH(launch_prep_frames(rawp, run, H, W, C, imgp, g.Hp, g.Wp, c->s_h2d));
+        LAUNCH(launch_prep_frames(rawp, run, H, W, C, imgp,
+                                  (uint2*)c->imgs_h.p + (size_t)(uploaded - frame_lo) * g.Hp * g.Wp, g.Hp, g.Wp, c->s_h2d));
         if (c->arch == 47)
           LAUNCH(launch_encode(imgp, c->enc[0], c->enc[1], c->enc[2], c->enc[3], (float*)c->e16.p,
                                (float4*)c->feats.p + (size_t)(uploaded - frame_lo) * g.Hp * g.Wp, run, g.Hp, g.Wp,

@@ -32,7 +32,7 @@ namespace vfi {
 
 namespace {
 
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = 6;   // window stages (<= 4 used) or ring slots
 struct Ctrl {
   uint64_t w_full;
   uint64_t a_full[kMaxStages];
@@ -92,15 +92,15 @@ struct TileIter {
 // issuing warp needed ~15 instructions, ~90 cycles, per MMA).
 template <int K16>
 __device__ __forceinline__ void issue_mmas(const TapConvParams& p, uint32_t d_tmem, uint32_t a_lo0, uint32_t b_lo0,
-                                           uint32_t b_hi, uint32_t idesc) {
+                                           uint32_t b_hi, uint32_t idesc, uint32_t accumulate_first = 0u) {
 #pragma unroll
   for (int j = 0; j < K16; ++j) {
     const uint4 d = p.mma[j];
-    umma_f16_split(d_tmem, a_lo0 + d.x, d.y, b_lo0 + d.z, b_hi, idesc, j > 0 ? 1u : 0u);
+    umma_f16_split(d_tmem, a_lo0 + d.x, d.y, b_lo0 + d.z, b_hi, idesc, j > 0 ? 1u : accumulate_first);
   }
 }
 
-template <typename T>
+template <typename T, bool RING>
 __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__ TapConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem);
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
     mbar_init(bar_w, 1);
     for (int s = 0; s < S; ++s) {
       mbar_init(bar_afull + 8 * s, 1);                  // producer's arrive.expect_tx (+ TMA transaction bytes)
-      mbar_init(bar_aempty + 8 * s, residual ? 8 : 1);  // 8 epilogue warps, or the MMA commit
+      mbar_init(bar_aempty + 8 * s, (residual && !RING) ? 8 : 1);  // 8 epilogue warps, or the MMA commit
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
@@ -151,6 +151,32 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
     const uint32_t b_lo0 = (1u << 16) | (w_smem >> 4);  // LBO(=1) | start address, 16-byte units
     const uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO | version | SWIZZLE_128B
     uint32_t k = 0;
+    if (RING) {
+      // ring of single k-block slots: 36 MMAs (9 taps x 64 channels) per slot, slot released by its own commit
+      const uint32_t b_kb = (9u * (uint32_t)p.n_cta * 128u) >> 4;  // weight bytes of one k-block, 16-byte units
+      uint32_t slot = 0, ph = 0;
+      for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k) {
+        const uint32_t acc = k & 1, vuse = k >> 1;
+        mbar_wait(bar_tempty + 8 * acc, (vuse & 1) ^ 1, 2);
+        const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait(bar_afull + 8 * slot, ph, 3);
+          tc_fence_after();
+          const uint32_t a_lo0 = (1u << 16) | ((a_smem + slot * p.stage_bytes) >> 4);
+          if (leader) {
+            issue_mmas<36>(p, d_tmem, a_lo0, b_lo0 + (uint32_t)kb * b_kb, b_hi, idesc, kb > 0 ? 1u : 0u);
+            umma_commit(bar_aempty + 8 * slot);
+          }
+          __syncwarp();
+          if (++slot == (uint32_t)S) {
+            slot = 0;
+            ph ^= 1u;
+          }
+        }
+        if (leader) umma_commit(bar_tfull + 8 * acc);
+        __syncwarp();
+      }
+    } else
     for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k) {
       const uint32_t stage = k % S, use = k / S, acc = k & 1, vuse = k >> 1;
       mbar_wait(bar_tempty + 8 * acc, (vuse & 1) ^ 1, 2);
@@ -184,6 +210,21 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
         bulk_g2s(w_smem + off, wsrc + off, min(32768u, p.w_bytes - off), bar_w);
       uint32_t k = 0;
       TileIter it(p, first);
+      if (RING) {
+        uint32_t slot = 0, ph = 0;
+        for (int t = first; t < p.ntiles; t += p.ctas_per_split, it.next()) {
+          const int gy0 = it.ty * kTileH + p.halo_y0, gx0 = it.tx * kTileW + p.halo_x0;
+          for (int kb = 0; kb < p.nkb; ++kb) {
+            mbar_wait(bar_aempty + 8 * slot, ph ^ 1u, 4);
+            mbar_arrive_expect_tx(bar_afull + 8 * slot, p.tx_bytes);
+            tma_load_4d(a_smem + slot * p.stage_bytes, &p.tm64, bar_afull + 8 * slot, kb * 64, gx0, gy0, it.b);
+            if (++slot == (uint32_t)S) {
+              slot = 0;
+              ph ^= 1u;
+            }
+          }
+        }
+      } else
       for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k, it.next()) {
         const uint32_t stage = k % S, use = k / S;
         const int b = it.b;
@@ -219,7 +260,8 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
     // residual chunk offsets inside a stage are tile independent (stage size and base are multiples of 1024, so the
     // swizzle phase of a row does not depend on the stage): computed once
     uint32_t roff[3][2] = {{0, 0}, {0, 0}, {0, 0}};
-    if (residual) {
+    const bool res_smem = residual && !RING;  // ring layers read the residual from global memory (L2 hit)
+    if (res_smem) {
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         if (i < nmine) {
@@ -242,6 +284,20 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
       const int gy = it.ty * kTileH + py, gx = it.tx * kTileW + px;
       const bool valid = (gy < p.H) && (gx < p.W);
 
+      uint4 rr[3][2];
+      if (RING && residual) {
+        // ring layer: the centre pixel's channels come from the input tensor itself, requested before the wait for the
+        // accumulator so that the latency hides behind the tile's MMAs
+        const uint4* src = reinterpret_cast<const uint4*>(
+            reinterpret_cast<const T*>(p.in) + ((((size_t)b * p.H + gy) * p.W + gx) * (size_t)p.cin + (size_t)n0));
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          if (i < nmine) {
+            rr[i][0] = valid ? __ldg(src + (c_lo + i) * 2) : make_uint4(0u, 0u, 0u, 0u);
+            rr[i][1] = valid ? __ldg(src + (c_lo + i) * 2 + 1) : make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+      }
       mbar_wait(bar_tfull + 8 * acc, vuse & 1, 5);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * p.acc_stride + ((uint32_t)(q * 32) << 16);
@@ -298,12 +354,11 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
       for (int i = 0; i < 3; ++i)
         if (i < nmine) tmem_ld16(taddr + (c_lo + i) * 16, v[i]);
       // shared-memory operands are fetched while the TMEM loads are in flight
-      uint4 rr[3][2];
-      if (residual) mbar_wait(bar_afull + 8 * stage, use & 1, 6);  // acquire the TMA-written window
+      if (res_smem) mbar_wait(bar_afull + 8 * stage, use & 1, 6);  // acquire the TMA-written window
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         if (i < nmine) {
-          if (residual) {
+          if (res_smem) {
             // residual = input channels n0 + 16*(c_lo+i) .. +15 of the centre pixel: two 16-byte chunks of its row
             const uint8_t* st = smem + stage * p.stage_bytes;  // generic pointer: ordinary, freely scheduled loads
             rr[i][0] = *reinterpret_cast<const uint4*>(st + roff[i][0]);
@@ -345,7 +400,7 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
           }
         }
       }
-      if (residual) {
+      if (res_smem) {
         // our generic-proxy READS of the window are complete (values consumed above); the mbarrier arrive/wait pair
         // orders them before the producer's next TMA write - no generic write is involved, so no proxy fence
         __syncwarp();
@@ -480,24 +535,36 @@ int tapconv_plan(const TapConvLayer& L, TapConvParams* pp) {
   p.w_bytes = (uint32_t)((L.ktotal16 + 3) / 4) * (uint32_t)L.n_cta * 128u;
   // input window: one 1024-aligned region per k-block (64 channels = 128-byte rows; 32-channel tail = 64-byte rows)
   p.nkb = (L.cin + 63) / 64;
+  p.ring = L.ring;
   {
     const int k = L.ktotal16;  // the unrolled issue sequences the kernel has
     if (!(k == 9 || k == 18 || k == 27 || k == 36 || k == 54 || k == 72 || k == 108)) return 0;
   }
   if (p.nkb > kMaxKBlocks || L.n_cta > 96 || (L.n_cta & 15)) return 0;
+  if (L.ring && ((L.cin & 63) || L.ntaps != 9 * p.nkb || L.ktotal16 != 36 * p.nkb)) return 0;
   uint32_t off = 0;
   p.tx_bytes = 0;
-  for (int kb = 0; kb < p.nkb; ++kb) {
-    const bool tail = (kb == p.nkb - 1) && (L.cin & 63);
-    const uint32_t bytes = (uint32_t)L.halo_w * (uint32_t)L.halo_h * (tail ? 64u : 128u);
-    p.kb_off[kb] = off;
-    off += align_up(bytes, 1024);
-    p.tx_bytes += bytes;
+  if (L.ring) {
+    // ring: every slot holds ONE k-block of a tile's window; p.stage_bytes / p.tx_bytes are per slot
+    const uint32_t bytes = (uint32_t)L.halo_w * (uint32_t)L.halo_h * 128u;
+    for (int kb = 0; kb < p.nkb; ++kb) p.kb_off[kb] = 0;
+    off = align_up(bytes, 1024);
+    p.tx_bytes = bytes;
+  } else {
+    for (int kb = 0; kb < p.nkb; ++kb) {
+      const bool tail = (kb == p.nkb - 1) && (L.cin & 63);
+      const uint32_t bytes = (uint32_t)L.halo_w * (uint32_t)L.halo_h * (tail ? 64u : 128u);
+      p.kb_off[kb] = off;
+      off += align_up(bytes, 1024);
+      p.tx_bytes += bytes;
+    }
   }
   p.stage_bytes = off;
   {
     // descriptor words per K=16 step (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14) | LBO [16,30) ; SBO>>4 [32,46) |
-    // version=1 [46,48) | layout [61,64) (2 = SWIZZLE_128B, 4 = SWIZZLE_64B); base_offset stays 0
+    // version=1 [46,48) | layout [61,64) (2 = SWIZZLE_128B, 4 = SWIZZLE_64B); base_offset stays 0.
+    // Ring layers list their taps k-block-major, so entries [0,36) (k-block 0) serve every k-block: the kernel adds
+    // the slot address to A and kb * (9 * n_cta * 128 B) to B.
     int j = 0;
     for (int e = 0; e < L.ntaps; ++e)
       for (int i = 0; i < L.taps[e].nk16; ++i, ++j) {
@@ -517,7 +584,7 @@ int tapconv_plan(const TapConvLayer& L, TapConvParams* pp) {
   p.off_w = align_up(p.off_ss + (uint32_t)L.n_cta * 4u, 1024);
   p.off_a = align_up(p.off_w + p.w_bytes, 1024);
   int stages = 0;
-  for (int s = kMaxStages; s >= 1; --s) {
+  for (int s = (L.ring ? kMaxStages : 4); s >= 1; --s) {
     if (p.off_a + (uint32_t)s * p.stage_bytes <= (uint32_t)kSmemLimit) {
       stages = s;
       break;
@@ -586,15 +653,17 @@ cudaError_t launch_tapconv(const TapConvLayer& L, int op_type, const void* in, v
   p.ctas_per_split = cps;
   const int grid = cps * L.nsplit;
   cudaError_t err;  // (per device: set on every launch, it is a cheap driver call)
-  if (op_type == OP_BF16) {
-    err = cudaFuncSetAttribute(tapconv_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-    if (err != cudaSuccess) return err;
-    tapconv_kernel<__nv_bfloat16><<<grid, 384, p.smem_bytes, st>>>(p);
-  } else {
-    err = cudaFuncSetAttribute(tapconv_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-    if (err != cudaSuccess) return err;
-    tapconv_kernel<__half><<<grid, 384, p.smem_bytes, st>>>(p);
-  }
+  auto go = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, 384, p.smem_bytes, st>>>(p);
+    return cudaSuccess;
+  };
+  if (op_type == OP_BF16)
+    err = L.ring ? go(tapconv_kernel<__nv_bfloat16, true>) : go(tapconv_kernel<__nv_bfloat16, false>);
+  else
+    err = L.ring ? go(tapconv_kernel<__half, true>) : go(tapconv_kernel<__half, false>);
+  if (err != cudaSuccess) return err;
   return cudaGetLastError();
 }
 

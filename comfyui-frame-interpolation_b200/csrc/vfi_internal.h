@@ -27,7 +27,7 @@ struct TapEntry {
   int16_t nk16;     // number of K=16 MMA steps (16 input channels each)
 };
 
-constexpr int kMaxTaps = 9;
+constexpr int kMaxTaps = 27;  // 9 taps, or 9 taps x 3 k-blocks in k-block-major (ring) order
 constexpr int kTileH = 16, kTileW = 8;        // one CTA tile = 128 grid cells = UMMA M
 constexpr int kSmemLimit = 232448;            // 227 KB opt-in maximum per CTA on sm_100
 
@@ -49,6 +49,7 @@ struct alignas(64) TapConvParams {
   int halo_y0, halo_x0, halo_h, halo_w;
   int stages;
   int epi_mode, out_s2d;
+  int ring;              // 1: the window streams through a ring of single k-block slots (see tapconv.cu)
   int tiles_x, tiles_y, ntiles;
   int ctas_per_split;
   uint32_t idesc;
@@ -71,6 +72,7 @@ struct TapConvLayer {
   int ntaps = 0, ktotal16 = 0;
   int halo_y0 = 0, halo_x0 = 0, halo_h = 0, halo_w = 0;
   int epi_mode = 0, out_s2d = 0;
+  int ring = 0;           // taps are listed k-block-major (kb, tap) with nk16 = 4; needs cin % 64 == 0
   TapEntry taps[kMaxTaps];
   void* w = nullptr;      // device
   float* shift = nullptr; // device
@@ -94,8 +96,10 @@ cudaError_t launch_tapconv(const TapConvLayer& L, int op_type, const void* in, v
 // smem/stage plan for a layer (for DESIGN.md tables and tests); returns 0 stages when it cannot fit
 int tapconv_plan(const TapConvLayer& L, TapConvParams* p_out);
 
-cudaError_t launch_prep_frames(const float* frames, int n, int H, int W, int cstride, float4* imgs, int Hp, int Wp,
-                               cudaStream_t st);
+// imgs: fp32 float4 planes (final blend); imgs_h: the same pixels as half4 (8 bytes) for the block-input warps, whose
+// results are rounded to 16 bits anyway - half the gather bytes through L1
+cudaError_t launch_prep_frames(const float* frames, int n, int H, int W, int cstride, float4* imgs, uint2* imgs_h,
+                               int Hp, int Wp, cudaStream_t st);
 // low-resolution outputs of the blocks executed so far (the accumulated full-resolution flow is implicit)
 struct FlowState {
   float4* f[4];
@@ -105,7 +109,8 @@ struct FlowState {
 };
 cudaError_t launch_encode(const float4* imgs, const float* w0, const float* b0, const float* w1, const float* b1,
                           float* e16, float4* feats, int n, int Hp, int Wp, cudaStream_t st);
-cudaError_t launch_front(int op_type, const float4* imgs, const float4* feats, const FlowState& fs, int blk, int lo,
+cudaError_t launch_front(int op_type, const float4* imgs, const uint2* imgs_h, const float4* feats, const FlowState& fs,
+                         int blk, int lo,
                          const float4* base_f, const float* base_m, float4* out_f, float* out_m, BatchTasks tasks,
                          int Hp, int Wp, int s, void* x_s2d, cudaStream_t st);
 cudaError_t launch_materialize(const FlowState& fs, int lo, const float4* base_f, const float* base_m, float4* flow,

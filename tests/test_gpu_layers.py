@@ -72,6 +72,21 @@ def test_resconv(engines, block, dtype, impl):
         assert rel_err(out.cpu().float(), ref) < _tol(dtype)
 
 
+@pytest.mark.parametrize("block", [3, 1, 0])
+def test_resconv_many_tiles(engines, block):
+    """More tiles than persistent CTAs: every CTA walks several tiles, so the window stages / ring slots, both TMEM
+    accumulators and all mbarrier phases wrap several times (blocks 0 and 1 run the k-block ring pipeline)."""
+    sd, e = engines
+    eng, c = e["float16"], BLOCK_C[block]
+    g = torch.Generator().manual_seed(40 + block)
+    x = (0.5 * torch.randn(3, 203, 181, c, generator=g)).half()
+    q = f"block{block}.convblock.3."
+    out = torch.empty_like(x, device="cuda")
+    eng.debug_layer(block, 2 + 3, x.cuda(), out, impl=0)
+    ref = nhwc(O.resconv(nchw(x.float()), _rw(sd, q + "conv.weight", "float16"), sd[q + "conv.bias"], sd[q + "beta"]))
+    assert rel_err(out.cpu().float(), ref) < _tol("float16")
+
+
 @pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
 @pytest.mark.parametrize("block", [3, 1, 0])
 @pytest.mark.parametrize("impl", IMPLS)

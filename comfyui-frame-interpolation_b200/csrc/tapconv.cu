@@ -18,13 +18,16 @@
 // the whole launch (one bulk copy, already in the swizzled operand layout), accumulators live in TMEM (double
 // buffered), the epilogue reads the ResConv residual back from the staged window instead of from global memory.
 //
-// Warp roles (384 threads, 1 CTA/SM, persistent over tiles):
-//   warp 0      : TMEM alloc/dealloc; one elected lane issues tcgen05.mma + tcgen05.commit
-//   warp 1      : one elected lane: weight bulk copy, then one 4-D TMA tensor copy per k-block and tile
-//   warps 2,3   : idle
-//   warps 4..11 : epilogue - two sets of four warps (TMEM lane quarters 0..3), each set takes half of the
-//                 accumulator columns of EVERY tile: tcgen05.ld -> release TMEM -> +shift (+residual) -> LeakyReLU
-//                 -> 16-bit -> global stores (lastconv: the fp32 4x4 flow/mask sub-pixel patch)
+// Warp roles (576 threads, 1 CTA/SM, persistent over tiles):
+//   warps 0..15 : epilogue - four sets of four warps (TMEM lane quarters 0..3).  Sets {0,1} take the even tiles of
+//                 the CTA (TMEM accumulator 0), sets {2,3} the odd ones (accumulator 1); inside a pair each set takes
+//                 half of the accumulator columns: tcgen05.ld -> release TMEM -> +shift (+residual) -> LeakyReLU
+//                 -> 16-bit -> global stores (lastconv: the fp32 4x4 flow/mask sub-pixel patch).
+//                 (ncu r01_v11: with 8 epilogue warps each warp needed ~480 dependent instructions per tile at ~9
+//                 cycles each = the whole tile time, while the tensor pipe was 14 % busy; tools/mma_rate.cu: the
+//                 hardware floor for an N=64 MMA of this form is 48 cycles.)
+//   warp 16     : TMEM alloc/dealloc; one elected lane issues tcgen05.mma + tcgen05.commit
+//   warp 17     : one elected lane: weight bulk copy, then one 4-D TMA tensor copy per k-block and tile
 #include "ptx.cuh"
 #include "vfi_internal.h"
 
@@ -42,6 +45,7 @@ struct Ctrl {
   uint32_t tmem_base;
 };
 constexpr uint32_t kCtrlBytes = 256;
+constexpr int kEpiWarps = 16, kMmaWarp = 16, kTmaWarp = 17, kThreads = 32 * 18;
 static_assert(sizeof(Ctrl) <= kCtrlBytes, "control block");
 
 __device__ __forceinline__ size_t out_pixel_offset(const TapConvParams& p, int b, int gy, int gx) {
@@ -58,7 +62,7 @@ __device__ __forceinline__ size_t out_pixel_offset(const TapConvParams& p, int b
 // instead of two integer divisions per tile and role.
 struct TileIter {
   int b, ty, tx, db, dy, dx, tiles_x, tiles_y;
-  __device__ __forceinline__ TileIter(const TapConvParams& p, int first) {
+  __device__ __forceinline__ TileIter(const TapConvParams& p, int first, int step) {
     tiles_x = p.tiles_x;
     tiles_y = p.tiles_y;
     const int per_img = tiles_x * tiles_y;
@@ -66,8 +70,8 @@ struct TileIter {
     int rem = first - b * per_img;
     ty = rem / tiles_x;
     tx = rem - ty * tiles_x;
-    db = p.ctas_per_split / per_img;
-    rem = p.ctas_per_split - db * per_img;
+    db = step / per_img;
+    rem = step - db * per_img;
     dy = rem / tiles_x;
     dx = rem - dy * tiles_x;
   }
@@ -79,7 +83,7 @@ struct TileIter {
       tx -= tiles_x;
       ++ty;
     }
-    if (ty >= tiles_y) {
+    if (ty >= tiles_y) {  // dy < tiles_y and the carry add at most tiles_y
       ty -= tiles_y;
       ++b;
     }
@@ -100,8 +104,8 @@ __device__ __forceinline__ void issue_mmas(const TapConvParams& p, uint32_t d_tm
   }
 }
 
-template <typename T, bool RING>
-__global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__ TapConvParams p) {
+template <typename T, bool RING, bool LAST>
+__global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_constant__ TapConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem);
   const int warp = threadIdx.x >> 5;
@@ -111,7 +115,7 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
   const int first = blockIdx.x / p.nsplit;
   if (first >= p.ctas_per_split) return;  // whole CTA leaves together
   const int S = p.stages;
-  const bool residual = (p.epi_mode == EPI_RESCONV);
+  const bool residual = !LAST && (p.epi_mode == EPI_RESCONV);
 
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_w = smem_base + offsetof(Ctrl, w_full);
@@ -135,13 +139,13 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
     }
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc(smem_base + offsetof(Ctrl, tmem_base), p.tmem_cols);
+  if (warp == kMmaWarp) tmem_alloc(smem_base + offsetof(Ctrl, tmem_base), p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctrl->tmem_base;
 
-  if (warp == 0) {
+  if (warp == kMmaWarp) {
     // ======================================================= MMA issuer
     // The whole warp runs the (warp-uniform) control flow; one elected lane issues tcgen05.mma / tcgen05.commit.
     const uint32_t leader = elect_one_sync();
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
       }
       __syncwarp();
     }
-  } else if (warp == 1) {
+  } else if (warp == kTmaWarp) {
     // ======================================================= TMA producer (one thread feeds the whole pipeline)
     if (elect_one_sync()) {
       mbar_arrive_expect_tx(bar_w, p.w_bytes);
@@ -209,7 +213,7 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
       for (uint32_t off = 0; off < p.w_bytes; off += 32768u)
         bulk_g2s(w_smem + off, wsrc + off, min(32768u, p.w_bytes - off), bar_w);
       uint32_t k = 0;
-      TileIter it(p, first);
+      TileIter it(p, first, p.ctas_per_split);
       if (RING) {
         uint32_t slot = 0, ph = 0;
         for (int t = first; t < p.ntiles; t += p.ctas_per_split, it.next()) {
@@ -239,14 +243,14 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
-    // ======================================================= epilogue
-    const int q = (warp - 4) & 3;                     // TMEM lane quarter this warp may read
-    const uint32_t eset = (uint32_t)(warp - 4) >> 2;  // 0 / 1: which half of the accumulator columns
-    const int etid = threadIdx.x - 128;
+  } else {
+    // ======================================================= epilogue (warps 0..15)
+    const int q = warp & 3;                            // TMEM lane quarter this warp may read
+    const uint32_t eset = ((uint32_t)warp >> 2) & 1u;  // which half of the accumulator columns
+    const uint32_t acc = (uint32_t)warp >> 3;          // tile parity this warp serves == its TMEM accumulator
     float* ss = reinterpret_cast<float*>(smem + p.off_ss);  // per-channel shift of this CTA's output slice
-    for (int i = etid; i < p.n_cta; i += 256) ss[i] = p.shift[split * p.n_cta + i];
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    for (int i = threadIdx.x; i < p.n_cta; i += 32 * kEpiWarps) ss[i] = p.shift[split * p.n_cta + i];
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
 
     const int r = q * 32 + lane;  // accumulator row == TMEM lane == tile cell
     const int py = r >> 3, px = r & 7;
@@ -276,33 +280,20 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
         }
       }
     }
-    uint32_t k = 0;
-    TileIter it(p, first);
-    for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k, it.next()) {
-      const uint32_t stage = k % S, use = k / S, acc = k & 1, vuse = k >> 1;
+    // this warp's tiles: k = acc, acc + 2, ... (k counts the CTA's tiles)
+    uint32_t k = acc;
+    TileIter it(p, first + (int)acc * p.ctas_per_split, 2 * p.ctas_per_split);
+    for (int t = first + (int)acc * p.ctas_per_split; t < p.ntiles; t += 2 * p.ctas_per_split, k += 2, it.next()) {
+      const uint32_t stage = k % S, use = k / S, vuse = k >> 1;
       const int b = it.b;
       const int gy = it.ty * kTileH + py, gx = it.tx * kTileW + px;
       const bool valid = (gy < p.H) && (gx < p.W);
 
-      uint4 rr[3][2];
-      if (RING && residual) {
-        // ring layer: the centre pixel's channels come from the input tensor itself, requested before the wait for the
-        // accumulator so that the latency hides behind the tile's MMAs
-        const uint4* src = reinterpret_cast<const uint4*>(
-            reinterpret_cast<const T*>(p.in) + ((((size_t)b * p.H + gy) * p.W + gx) * (size_t)p.cin + (size_t)n0));
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          if (i < nmine) {
-            rr[i][0] = valid ? __ldg(src + (c_lo + i) * 2) : make_uint4(0u, 0u, 0u, 0u);
-            rr[i][1] = valid ? __ldg(src + (c_lo + i) * 2 + 1) : make_uint4(0u, 0u, 0u, 0u);
-          }
-        }
-      }
       mbar_wait(bar_tfull + 8 * acc, vuse & 1, 5);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * p.acc_stride + ((uint32_t)(q * 32) << 16);
 
-      if (p.epi_mode == EPI_LASTCONV) {
+      if (LAST) {
         // accumulator column n = c5*16 + pos: component c5 (4 flow + mask) of sub-pixel pos = y4*4 + x4 of the 4x4
         // patch of this feature cell; this set owns pos [8*eset, 8*eset + 8) = patch rows 2*eset, 2*eset+1
         const int ncomp = nchunks;  // 5 (all components in this CTA) or 1 (component = split)
@@ -349,56 +340,67 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
       }
 
       // ---- conv0.x / ResConv: this thread owns one grid cell and the 16-channel chunks [c_lo, c_lo + nmine)
-      uint32_t v[3][16];
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-        if (i < nmine) tmem_ld16(taddr + (c_lo + i) * 16, v[i]);
-      // shared-memory operands are fetched while the TMEM loads are in flight
-      if (res_smem) mbar_wait(bar_afull + 8 * stage, use & 1, 6);  // acquire the TMA-written window
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        if (i < nmine) {
-          if (res_smem) {
-            // residual = input channels n0 + 16*(c_lo+i) .. +15 of the centre pixel: two 16-byte chunks of its row
-            const uint8_t* st = smem + stage * p.stage_bytes;  // generic pointer: ordinary, freely scheduled loads
-            rr[i][0] = *reinterpret_cast<const uint4*>(st + roff[i][0]);
-            rr[i][1] = *reinterpret_cast<const uint4*>(st + roff[i][1]);
-          }
-        }
-      }
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);  // TMEM buffer free: the next tile's MMAs may start
+      // Chunks 0 and 1 are read from TMEM together, a third one (n_cta = 80, 96) in a second round, so that at most
+      // 32 accumulator values are live per thread (576 threads: 96 registers each).
       T* orow = reinterpret_cast<T*>(p.out) + (valid ? out_pixel_offset(p, b, gy, gx) + (size_t)n0 : 0);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        if (i < nmine) {
-          const float4* sp = reinterpret_cast<const float4*>(ss + (c_lo + i) * 16);
-          const float4 s0 = sp[0], s1 = sp[1], s2 = sp[2], s3 = sp[3];
-          const float shf[16] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w,
-                                 s2.x, s2.y, s2.z, s2.w, s3.x, s3.y, s3.z, s3.w};
-          const uint32_t rw[8] = {rr[i][0].x, rr[i][0].y, rr[i][0].z, rr[i][0].w,
-                                  rr[i][1].x, rr[i][1].y, rr[i][1].z, rr[i][1].w};
-          uint32_t o[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float a0 = __uint_as_float(v[i][2 * j]) + shf[2 * j];
-            float a1 = __uint_as_float(v[i][2 * j + 1]) + shf[2 * j + 1];
-            if (residual) {
-              const float2 rf = Pack2<T>::unpack(rw[j]);
-              a0 += rf.x;
-              a1 += rf.y;
-            }
-            o[j] = Pack2<T>::pack(fmaxf(a0, 0.2f * a0), fmaxf(a1, 0.2f * a1));  // LeakyReLU(0.2)
-          }
-          // 32 contiguous bytes (16 channels) of this cell's channel vector; L2 merges the halves of a sector
-          if (valid) {
-            uint4* dst = reinterpret_cast<uint4*>(orow + (c_lo + i) * 16);
-            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-          }
+      const uint4* gres = nullptr;  // ring layers: the centre pixel's channels in the input tensor (L2 hit)
+      if (RING && residual)
+        gres = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.in) +
+                                              ((((size_t)b * p.H + gy) * p.W + gx) * (size_t)p.cin + (size_t)n0));
+      const uint8_t* st = smem + stage * p.stage_bytes;  // generic pointer: ordinary, freely scheduled loads
+      auto finish_chunk = [&](int i, const uint32_t(&vv)[16]) {
+        uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+        if (res_smem) {
+          // residual = input channels n0 + 16*(c_lo+i) .. +15 of the centre pixel: two 16-byte chunks of its row
+          r0 = *reinterpret_cast<const uint4*>(st + roff[i][0]);
+          r1 = *reinterpret_cast<const uint4*>(st + roff[i][1]);
+        } else if (RING && residual && valid) {
+          r0 = __ldg(gres + (c_lo + i) * 2);
+          r1 = __ldg(gres + (c_lo + i) * 2 + 1);
         }
+        const float4* sp = reinterpret_cast<const float4*>(ss + (c_lo + i) * 16);
+        const float4 s0 = sp[0], s1 = sp[1], s2 = sp[2], s3 = sp[3];
+        const float shf[16] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w,
+                               s2.x, s2.y, s2.z, s2.w, s3.x, s3.y, s3.z, s3.w};
+        const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        uint32_t o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float a0 = __uint_as_float(vv[2 * j]) + shf[2 * j];
+          float a1 = __uint_as_float(vv[2 * j + 1]) + shf[2 * j + 1];
+          if (residual) {
+            const float2 rf = Pack2<T>::unpack(rw[j]);
+            a0 += rf.x;
+            a1 += rf.y;
+          }
+          o[j] = Pack2<T>::pack(fmaxf(a0, 0.2f * a0), fmaxf(a1, 0.2f * a1));  // LeakyReLU(0.2)
+        }
+        // 32 contiguous bytes (16 channels) of this cell's channel vector; L2 merges the halves of a sector
+        if (valid) {
+          uint4* dst = reinterpret_cast<uint4*>(orow + (c_lo + i) * 16);
+          dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+          dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+      };
+      uint32_t v0[16], v1[16];
+      tmem_ld16(taddr + c_lo * 16, v0);
+      if (nmine > 1) tmem_ld16(taddr + (c_lo + 1) * 16, v1);
+      if (res_smem) mbar_wait(bar_afull + 8 * stage, use & 1, 6);  // acquire the TMA-written window
+      tmem_ld_wait();
+      if (nmine <= 2) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);  // TMEM buffer free: the next tile's MMAs may start
+      }
+      finish_chunk(0, v0);
+      if (nmine > 1) finish_chunk(1, v1);
+      if (nmine > 2) {
+        tmem_ld16(taddr + (c_lo + 2) * 16, v0);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        finish_chunk(2, v0);
       }
       if (res_smem) {
         // our generic-proxy READS of the window are complete (values consumed above); the mbarrier arrive/wait pair
@@ -411,7 +413,7 @@ __global__ void __launch_bounds__(384, 1) tapconv_kernel(const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
@@ -656,13 +658,21 @@ cudaError_t launch_tapconv(const TapConvLayer& L, int op_type, const void* in, v
   auto go = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) return e;
-    kern<<<grid, 384, p.smem_bytes, st>>>(p);
+    kern<<<grid, kThreads, p.smem_bytes, st>>>(p);
     return cudaSuccess;
   };
-  if (op_type == OP_BF16)
-    err = L.ring ? go(tapconv_kernel<__nv_bfloat16, true>) : go(tapconv_kernel<__nv_bfloat16, false>);
-  else
-    err = L.ring ? go(tapconv_kernel<__half, true>) : go(tapconv_kernel<__half, false>);
+  const bool last = (L.epi_mode == EPI_LASTCONV);
+  if (op_type == OP_BF16) {
+    if (last)
+      err = L.ring ? go(tapconv_kernel<__nv_bfloat16, true, true>) : go(tapconv_kernel<__nv_bfloat16, false, true>);
+    else
+      err = L.ring ? go(tapconv_kernel<__nv_bfloat16, true, false>) : go(tapconv_kernel<__nv_bfloat16, false, false>);
+  } else {
+    if (last)
+      err = L.ring ? go(tapconv_kernel<__half, true, true>) : go(tapconv_kernel<__half, false, true>);
+    else
+      err = L.ring ? go(tapconv_kernel<__half, true, false>) : go(tapconv_kernel<__half, false, false>);
+  }
   if (err != cudaSuccess) return err;
   return cudaGetLastError();
 }

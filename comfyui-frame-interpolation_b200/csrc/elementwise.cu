@@ -46,13 +46,14 @@ __device__ __forceinline__ float4 sample_border(const float4* __restrict__ img, 
   sy = fminf(fmaxf(sy, 0.f), (float)(Hp - 1));
   const float fx0 = floorf(sx), fy0 = floorf(sy);
   const int x0 = (int)fx0, y0 = (int)fy0;
-  const int x1 = min(x0 + 1, Wp - 1), y1 = min(y0 + 1, Hp - 1);
+  const int dx = (x0 + 1 < Wp) ? 1 : 0, dyw = (y0 + 1 < Hp) ? Wp : 0;  // x1 = min(x0+1, Wp-1), y1 likewise
   const float ax = sx - fx0, ay = sy - fy0;
   const float w00 = (1.f - ax) * (1.f - ay), w01 = ax * (1.f - ay), w10 = (1.f - ax) * ay, w11 = ax * ay;
-  const float4 a = __ldg(img + (size_t)y0 * Wp + x0);
-  const float4 b = __ldg(img + (size_t)y0 * Wp + x1);
-  const float4 c = __ldg(img + (size_t)y1 * Wp + x0);
-  const float4 d = __ldg(img + (size_t)y1 * Wp + x1);
+  const float4* p = img + (y0 * Wp + x0);  // one plane is < 2^31 pixels: 32-bit offsets
+  const float4 a = __ldg(p);
+  const float4 b = __ldg(p + dx);
+  const float4 c = __ldg(p + dyw);
+  const float4 d = __ldg(p + dyw + dx);
   float4 o;
   o.x = a.x * w00 + b.x * w01 + c.x * w10 + d.x * w11;
   o.y = a.y * w00 + b.y * w01 + c.y * w10 + d.y * w11;
@@ -67,13 +68,14 @@ __device__ __forceinline__ float4 sample_border(const uint2* __restrict__ img, i
   sy = fminf(fmaxf(sy, 0.f), (float)(Hp - 1));
   const float fx0 = floorf(sx), fy0 = floorf(sy);
   const int x0 = (int)fx0, y0 = (int)fy0;
-  const int x1 = min(x0 + 1, Wp - 1), y1 = min(y0 + 1, Hp - 1);
+  const int dx = (x0 + 1 < Wp) ? 1 : 0, dyw = (y0 + 1 < Hp) ? Wp : 0;
   const float ax = sx - fx0, ay = sy - fy0;
   const float w00 = (1.f - ax) * (1.f - ay), w01 = ax * (1.f - ay), w10 = (1.f - ax) * ay, w11 = ax * ay;
-  const float4 a = unpack_h4(__ldg(img + (size_t)y0 * Wp + x0));
-  const float4 b = unpack_h4(__ldg(img + (size_t)y0 * Wp + x1));
-  const float4 c = unpack_h4(__ldg(img + (size_t)y1 * Wp + x0));
-  const float4 d = unpack_h4(__ldg(img + (size_t)y1 * Wp + x1));
+  const uint2* p = img + (y0 * Wp + x0);
+  const float4 a = unpack_h4(__ldg(p));
+  const float4 b = unpack_h4(__ldg(p + dx));
+  const float4 c = unpack_h4(__ldg(p + dyw));
+  const float4 d = unpack_h4(__ldg(p + dyw + dx));
   float4 o;
   o.x = a.x * w00 + b.x * w01 + c.x * w10 + d.x * w11;
   o.y = a.y * w00 + b.y * w01 + c.y * w10 + d.y * w11;
@@ -88,13 +90,14 @@ __device__ __forceinline__ float4 sample_border4(const float4* __restrict__ img,
   sy = fminf(fmaxf(sy, 0.f), (float)(Hp - 1));
   const float fx0 = floorf(sx), fy0 = floorf(sy);
   const int x0 = (int)fx0, y0 = (int)fy0;
-  const int x1 = min(x0 + 1, Wp - 1), y1 = min(y0 + 1, Hp - 1);
+  const int dx = (x0 + 1 < Wp) ? 1 : 0, dyw = (y0 + 1 < Hp) ? Wp : 0;
   const float ax = sx - fx0, ay = sy - fy0;
   const float w00 = (1.f - ax) * (1.f - ay), w01 = ax * (1.f - ay), w10 = (1.f - ax) * ay, w11 = ax * ay;
-  const float4 a = __ldg(img + (size_t)y0 * Wp + x0);
-  const float4 b = __ldg(img + (size_t)y0 * Wp + x1);
-  const float4 c = __ldg(img + (size_t)y1 * Wp + x0);
-  const float4 d = __ldg(img + (size_t)y1 * Wp + x1);
+  const float4* p = img + (y0 * Wp + x0);
+  const float4 a = __ldg(p);
+  const float4 b = __ldg(p + dx);
+  const float4 c = __ldg(p + dyw);
+  const float4 d = __ldg(p + dyw + dx);
   float4 o;
   o.x = a.x * w00 + b.x * w01 + c.x * w10 + d.x * w11;
   o.y = a.y * w00 + b.y * w01 + c.y * w10 + d.y * w11;
@@ -118,6 +121,8 @@ struct FlowLevels {
   const float4* f[4];  // levels to add, in order: [B, Hp/s, Wp/s] flow increments
   const float* m[4];   //                          [B, Hp/s, Wp/s] mask increments
   int s[4];
+  int hs[4], ws[4];      // level size Hp/s, Wp/s (set by the host: no integer division in the kernels)
+  float inv_s[4];        // 1/s
   const float4* base_f;  // optional full-resolution accumulated flow [B, Hp, Wp] (nullptr: start from zero)
   const float* base_m;
   float4* out_f;         // optional: store the accumulated flow / mask at every visited position
@@ -129,29 +134,30 @@ struct FlowLevels {
 __device__ __forceinline__ void up_level(const FlowLevels& L, int j, int b, int Hp, int Wp, int Y, int X, float4& uf,
                                          float& um) {
   const int s = L.s[j];
-  const int Hs = Hp / s, Ws = Wp / s;
+  const int Hs = L.hs[j], Ws = L.ws[j];
   const float4* tf = L.f[j] + (size_t)b * Hs * Ws;
   const float* tm = L.m[j] + (size_t)b * Hs * Ws;
   if (s == 1) {
-    uf = __ldg(tf + (size_t)Y * Ws + X);
-    um = __ldg(tm + (size_t)Y * Ws + X);
+    uf = __ldg(tf + (Y * Ws + X));
+    um = __ldg(tm + (Y * Ws + X));
     return;
   }
-  const float inv_s = 1.f / (float)s;
+  const float inv_s = L.inv_s[j];
   const float sy = fmaxf(((float)Y + 0.5f) * inv_s - 0.5f, 0.f);
   const float sx = fmaxf(((float)X + 0.5f) * inv_s - 0.5f, 0.f);
   const int y0 = min((int)sy, Hs - 1), x0 = min((int)sx, Ws - 1);
-  const int y1 = min(y0 + 1, Hs - 1), x1 = min(x0 + 1, Ws - 1);
+  const int dx = (x0 + 1 < Ws) ? 1 : 0, dyw = (y0 + 1 < Hs) ? Ws : 0;  // x1 = min(x0+1, Ws-1), y1 likewise
   const float ly = sy - (float)y0, lx = sx - (float)x0;
   const float hy = 1.f - ly, hx = 1.f - lx;
-  const float4 a = __ldg(tf + (size_t)y0 * Ws + x0);
-  const float4 bq = __ldg(tf + (size_t)y0 * Ws + x1);
-  const float4 c = __ldg(tf + (size_t)y1 * Ws + x0);
-  const float4 d = __ldg(tf + (size_t)y1 * Ws + x1);
-  const float ma = __ldg(tm + (size_t)y0 * Ws + x0);
-  const float mb = __ldg(tm + (size_t)y0 * Ws + x1);
-  const float mc = __ldg(tm + (size_t)y1 * Ws + x0);
-  const float md = __ldg(tm + (size_t)y1 * Ws + x1);
+  const int o00 = y0 * Ws + x0;  // one level plane is < 2^31 elements
+  const float4 a = __ldg(tf + o00);
+  const float4 bq = __ldg(tf + o00 + dx);
+  const float4 c = __ldg(tf + o00 + dyw);
+  const float4 d = __ldg(tf + o00 + dyw + dx);
+  const float ma = __ldg(tm + o00);
+  const float mb = __ldg(tm + o00 + dx);
+  const float mc = __ldg(tm + o00 + dyw);
+  const float md = __ldg(tm + o00 + dyw + dx);
   uf.x = hy * (hx * a.x + lx * bq.x) + ly * (hx * c.x + lx * d.x);
   uf.y = hy * (hx * a.y + lx * bq.y) + ly * (hx * c.y + lx * d.y);
   uf.z = hy * (hx * a.z + lx * bq.z) + ly * (hx * c.z + lx * d.z);
@@ -199,16 +205,16 @@ __global__ void front_kernel(const uint2* __restrict__ imgs, const FlowLevels le
                              int Wp, int s_rt, T* __restrict__ x_s2d) {
   const int s = S ? S : s_rt;
   const int Hs = Hp / s, Ws = Wp / s;
-  const size_t total = (size_t)tasks.n * Hs * Ws;
   const size_t plane = (size_t)Hp * Wp;
   const float inv_s = 1.f / (float)s;
-  for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
-    const int par = (int)(id & 1);
-    size_t r = id >> 1;
-    const int xl = (int)(r % Ws);
-    r /= Ws;
-    const int yl = (int)(r % (Hs >> 1)) * 2 + par;
-    const int b = (int)(r / (Hs >> 1));
+  // grid = (x cells / 64, row pairs, images): no integer division per thread (ncu r01_v11: the 64-bit div/mod of a
+  // flat index was a large part of the ~450 instructions per pixel)
+  {
+    const int par = (int)(threadIdx.x & 1);
+    const int xl = (int)(blockIdx.x * (blockDim.x >> 1) + (threadIdx.x >> 1));
+    if (xl >= Ws) return;
+    const int yl = (int)blockIdx.y * 2 + par;
+    const int b = (int)blockIdx.z;
     const uint2* img0 = imgs + (size_t)tasks.f0[b] * plane;
     const uint2* img1 = imgs + (size_t)tasks.f1[b] * plane;
     const float t = tasks.t[b];
@@ -281,26 +287,26 @@ struct LevelTap {
 
 __device__ __forceinline__ void load_level_tap(const FlowLevels& L, int j, int b, int Hp, int Wp, int Y0, int X0,
                                                LevelTap& t) {
-  const int s = L.s[j];
-  const int Hs = Hp / s, Ws = Wp / s;
+  const int Hs = L.hs[j], Ws = L.ws[j];
   const float4* tf = L.f[j] + (size_t)b * Hs * Ws;
   const float* tm = L.m[j] + (size_t)b * Hs * Ws;
-  t.inv_s = 1.f / (float)s;
-  t.sc = (float)s;
+  t.inv_s = L.inv_s[j];
+  t.sc = (float)L.s[j];
   const float sy = fmaxf(((float)Y0 + 0.5f) * t.inv_s - 0.5f, 0.f);
   const float sx = fmaxf(((float)X0 + 0.5f) * t.inv_s - 0.5f, 0.f);
   const int y0 = min((int)sy, Hs - 1), x0 = min((int)sx, Ws - 1);
-  const int y1 = min(y0 + 1, Hs - 1), x1 = min(x0 + 1, Ws - 1);
+  const int dx = (x0 + 1 < Ws) ? 1 : 0, dyw = (y0 + 1 < Hs) ? Ws : 0;
   t.fy0 = (float)y0;
   t.fx0 = (float)x0;
-  t.a = __ldg(tf + (size_t)y0 * Ws + x0);
-  t.b = __ldg(tf + (size_t)y0 * Ws + x1);
-  t.c = __ldg(tf + (size_t)y1 * Ws + x0);
-  t.d = __ldg(tf + (size_t)y1 * Ws + x1);
-  t.ma = __ldg(tm + (size_t)y0 * Ws + x0);
-  t.mb = __ldg(tm + (size_t)y0 * Ws + x1);
-  t.mc = __ldg(tm + (size_t)y1 * Ws + x0);
-  t.md = __ldg(tm + (size_t)y1 * Ws + x1);
+  const int o00 = y0 * Ws + x0;
+  t.a = __ldg(tf + o00);
+  t.b = __ldg(tf + o00 + dx);
+  t.c = __ldg(tf + o00 + dyw);
+  t.d = __ldg(tf + o00 + dyw + dx);
+  t.ma = __ldg(tm + o00);
+  t.mb = __ldg(tm + o00 + dx);
+  t.mc = __ldg(tm + o00 + dyw);
+  t.md = __ldg(tm + o00 + dyw + dx);
 }
 
 __device__ __forceinline__ void eval_level_tap(const LevelTap& t, int Y, int X, float4& uf, float& um) {
@@ -320,15 +326,13 @@ template <typename T, int NLEV>
 __global__ void front2_kernel(const uint2* __restrict__ imgs, const FlowLevels lev, const BatchTasks tasks, int Hp,
                               int Wp, T* __restrict__ x_s2d) {
   const int Hs = Hp >> 1, Ws = Wp >> 1;
-  const size_t total = (size_t)tasks.n * Hs * Ws;
   const size_t plane = (size_t)Hp * Wp;
-  for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
-    const int par = (int)(id & 1);
-    size_t r = id >> 1;
-    const int xl = (int)(r % Ws);
-    r /= Ws;
-    const int yl = (int)(r % (Hs >> 1)) * 2 + par;
-    const int b = (int)(r / (Hs >> 1));
+  {
+    const int par = (int)(threadIdx.x & 1);
+    const int xl = (int)(blockIdx.x * (blockDim.x >> 1) + (threadIdx.x >> 1));
+    if (xl >= Ws) return;
+    const int yl = (int)blockIdx.y * 2 + par;
+    const int b = (int)blockIdx.z;
     const uint2* img0 = imgs + (size_t)tasks.f0[b] * plane;
     const uint2* img1 = imgs + (size_t)tasks.f1[b] * plane;
     const int Y0 = 2 * yl, X0 = 2 * xl;
@@ -497,16 +501,14 @@ __global__ void front47_kernel(const float4* __restrict__ imgs, const float4* __
                                const FlowLevels lev, const BatchTasks tasks, int Hp, int Wp, int s,
                                T* __restrict__ x_s2d) {
   const int Hs = Hp / s, Ws = Wp / s;
-  const size_t total = (size_t)tasks.n * Hs * Ws;
   const size_t plane = (size_t)Hp * Wp;
   const float inv_s = 1.f / (float)s;
-  for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
-    const int par = (int)(id & 1);
-    size_t r = id >> 1;
-    const int xl = (int)(r % Ws);
-    r /= Ws;
-    const int yl = (int)(r % (Hs >> 1)) * 2 + par;
-    const int b = (int)(r / (Hs >> 1));
+  {
+    const int par = (int)(threadIdx.x & 1);
+    const int xl = (int)(blockIdx.x * (blockDim.x >> 1) + (threadIdx.x >> 1));
+    if (xl >= Ws) return;
+    const int yl = (int)blockIdx.y * 2 + par;
+    const int b = (int)blockIdx.z;
     const float4* img0 = imgs + (size_t)tasks.f0[b] * plane;
     const float4* img1 = imgs + (size_t)tasks.f1[b] * plane;
     const float4* ft0 = feats + (size_t)tasks.f0[b] * plane;
@@ -590,13 +592,13 @@ __global__ void materialize_kernel(const FlowLevels lev, float4* __restrict__ fl
 template <int NLEV>
 __global__ void final_kernel(const float4* __restrict__ imgs, const FlowLevels lev, const BatchTasks tasks, int Hp,
                              int Wp, int H, int W, float* __restrict__ out) {
-  const size_t total = (size_t)tasks.n * H * W;
   const size_t plane = (size_t)Hp * Wp;
-  for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
-    const int x = (int)(id % W);
-    const size_t r = id / W;
-    const int y = (int)(r % H);
-    const int b = (int)(r / H);
+  {
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (x >= W) return;
+    const int y = (int)blockIdx.y;
+    const int b = (int)blockIdx.z;
+    const size_t id = ((size_t)b * H + y) * W + x;
     float4 f;
     float m;
     flow_at<NLEV>(lev, b, Hp, Wp, y, x, f, m);
@@ -671,13 +673,16 @@ cudaError_t launch_prep_frames(const float* frames, int n, int H, int W, int cst
 
 // levels [lo, hi) of the state (+ optional base / store planes) as a kernel argument
 static FlowLevels make_levels(const FlowState& fs, int lo, int hi, const float4* base_f, const float* base_m,
-                              float4* out_f, float* out_m) {
+                              float4* out_f, float* out_m, int Hp, int Wp) {
   FlowLevels L{};
   L.mask_replace = fs.mask_replace;
   for (int j = lo; j < hi; ++j) {
     L.f[j - lo] = fs.f[j];
     L.m[j - lo] = fs.m[j];
     L.s[j - lo] = fs.s[j];
+    L.hs[j - lo] = Hp / fs.s[j];
+    L.ws[j - lo] = Wp / fs.s[j];
+    L.inv_s[j - lo] = 1.f / (float)fs.s[j];
   }
   L.base_f = base_f;
   L.base_m = base_m;
@@ -687,7 +692,7 @@ static FlowLevels make_levels(const FlowState& fs, int lo, int hi, const float4*
 }
 
 template <typename T>
-static void launch_front47_t(int nlev, int g, cudaStream_t st, const float4* imgs, const float4* feats,
+static void launch_front47_t(int nlev, dim3 g, cudaStream_t st, const float4* imgs, const float4* feats,
                              const FlowLevels& L, const BatchTasks& tasks, int Hp, int Wp, int s, void* x) {
   switch (nlev) {
     case 0: front47_kernel<T, 0><<<g, 128, 0, st>>>(imgs, feats, L, tasks, Hp, Wp, s, (T*)x); break;
@@ -708,7 +713,7 @@ static void launch_front2_t(int nlev, int g, cudaStream_t st, const float4* imgs
 }
 
 template <typename T, int S>
-static void launch_front_ts(int nlev, int g, cudaStream_t st, const uint2* imgs, const FlowLevels& L,
+static void launch_front_ts(int nlev, dim3 g, cudaStream_t st, const uint2* imgs, const FlowLevels& L,
                             const BatchTasks& tasks, int Hp, int Wp, int s, void* x) {
   switch (nlev) {
     case 0: front_kernel<T, 0, S><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, s, (T*)x); break;
@@ -719,7 +724,7 @@ static void launch_front_ts(int nlev, int g, cudaStream_t st, const uint2* imgs,
 }
 
 template <typename T>
-static void launch_front_t(int nlev, bool shared_taps, int g, cudaStream_t st, const uint2* imgs, const FlowLevels& L,
+static void launch_front_t(int nlev, bool shared_taps, dim3 g, cudaStream_t st, const uint2* imgs, const FlowLevels& L,
                            const BatchTasks& tasks, int Hp, int Wp, int s, void* x) {
   if (shared_taps) {
     switch (nlev) {
@@ -748,9 +753,8 @@ cudaError_t launch_encode(const float4* imgs, const float* w0, const float* b0, 
 cudaError_t launch_front(int op_type, const float4* imgs, const uint2* imgs_h, const float4* feats, const FlowState& fs,
                          int blk, int lo, const float4* base_f, const float* base_m, float4* out_f, float* out_m, BatchTasks tasks,
                          int Hp, int Wp, int s, void* x_s2d, cudaStream_t st) {
-  const size_t total = (size_t)tasks.n * (Hp / s) * (Wp / s);
-  const int g = grid_for(total, 128);
-  const FlowLevels L = make_levels(fs, lo, blk, base_f, base_m, out_f, out_m);
+  const dim3 g((unsigned)((Wp / s + 63) / 64), (unsigned)(Hp / s / 2), (unsigned)tasks.n);  // 64 cells x 2 rows per block
+  const FlowLevels L = make_levels(fs, lo, blk, base_f, base_m, out_f, out_m, Hp, Wp);
   const int nlev = (blk == 0) ? 0 : (blk - lo);
   if (blk > 0 && nlev == 0 && base_f == nullptr) return cudaErrorInvalidValue;
   if (feats != nullptr) {  // arch 4.7
@@ -774,7 +778,7 @@ cudaError_t launch_front(int op_type, const float4* imgs, const uint2* imgs_h, c
 cudaError_t launch_materialize(const FlowState& fs, int lo, const float4* base_f, const float* base_m, float4* flow,
                                float* mask, int B, int Hp, int Wp, cudaStream_t st) {
   const size_t total = (size_t)B * Hp * Wp;
-  FlowLevels L = make_levels(fs, lo, 4, base_f, base_m, nullptr, nullptr);
+  FlowLevels L = make_levels(fs, lo, 4, base_f, base_m, nullptr, nullptr, Hp, Wp);
   // pad unused levels with a zero-weight copy of the last one is not needed: materialize_kernel is NLEV=4-lo generic
   const int nlev = 4 - lo;
   switch (nlev) {
@@ -788,9 +792,8 @@ cudaError_t launch_materialize(const FlowState& fs, int lo, const float4* base_f
 
 cudaError_t launch_final(const float4* imgs, const FlowState& fs, int lo, const float4* base_f, const float* base_m,
                          BatchTasks tasks, int Hp, int Wp, int H, int W, float* out, cudaStream_t st) {
-  const size_t total = (size_t)tasks.n * H * W;
-  const FlowLevels L = make_levels(fs, lo, 4, base_f, base_m, nullptr, nullptr);
-  const int g = grid_for(total, 256);
+  const FlowLevels L = make_levels(fs, lo, 4, base_f, base_m, nullptr, nullptr, Hp, Wp);
+  const dim3 g((unsigned)((W + 255) / 256), (unsigned)H, (unsigned)tasks.n);
   switch (4 - lo) {
     case 1: final_kernel<1><<<g, 256, 0, st>>>(imgs, L, tasks, Hp, Wp, H, W, out); break;
     case 2: final_kernel<2><<<g, 256, 0, st>>>(imgs, L, tasks, Hp, Wp, H, W, out); break;

@@ -90,17 +90,20 @@ struct TileIter {
   }
 };
 
-// One tile's MMAs.  K16 is a compile-time constant so that every p.mma[j] is a fixed constant-bank address: the
-// descriptor words reach the tensor core through uniform loads / uniform adds only (ncu r01: with a table in shared
-// memory, or a run-time index into the parameters, every operand went LDS/LDC -> vector register -> R2UR and the
-// issuing warp needed ~15 instructions, ~90 cycles, per MMA).
-template <int K16>
-__device__ __forceinline__ void issue_mmas(const TapConvParams& p, uint32_t d_tmem, uint32_t a_lo0, uint32_t b_lo0,
+// One tile's MMAs as NR "runs" of L consecutive K=16 steps (same tap, same k-block: both descriptors advance by
+// 32 bytes per step).  NR and L are compile-time constants, so every p.mma[r] is a fixed constant-bank address and the
+// steps inside a run are immediate adds: ~4.7 SASS instructions per MMA for L = 4 (r01_v11: a table entry per step
+// cost 8-15 - LDC/IMAD/R2UR chains - and the issuing warp, not the tensor pipe, set the tile time).
+template <int NR, int L>
+__device__ __forceinline__ void issue_runs(const TapConvParams& p, uint32_t d_tmem, uint32_t a_lo0, uint32_t b_lo0,
                                            uint32_t b_hi, uint32_t idesc, uint32_t accumulate_first = 0u) {
 #pragma unroll
-  for (int j = 0; j < K16; ++j) {
-    const uint4 d = p.mma[j];
-    umma_f16_split(d_tmem, a_lo0 + d.x, d.y, b_lo0 + d.z, b_hi, idesc, j > 0 ? 1u : accumulate_first);
+  for (int r = 0; r < NR; ++r) {
+    const uint4 d = p.mma[r];
+    const uint32_t a = a_lo0 + d.x, b = b_lo0 + d.z;
+#pragma unroll
+    for (int i = 0; i < L; ++i)
+      umma_f16_split(d_tmem, a + 2u * i, d.y, b + 2u * i, b_hi, idesc, (r | i) ? 1u : accumulate_first);
   }
 }
 
@@ -150,7 +153,6 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
     // The whole warp runs the (warp-uniform) control flow; one elected lane issues tcgen05.mma / tcgen05.commit.
     const uint32_t leader = elect_one_sync();
     mbar_wait(bar_w, 0, 1);
-    const int K16 = p.ktotal16;
     const uint32_t idesc = p.idesc;
     const uint32_t b_lo0 = (1u << 16) | (w_smem >> 4);  // LBO(=1) | start address, 16-byte units
     const uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO | version | SWIZZLE_128B
@@ -168,7 +170,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
           tc_fence_after();
           const uint32_t a_lo0 = (1u << 16) | ((a_smem + slot * p.stage_bytes) >> 4);
           if (leader) {
-            issue_mmas<36>(p, d_tmem, a_lo0, b_lo0 + (uint32_t)kb * b_kb, b_hi, idesc, kb > 0 ? 1u : 0u);
+            issue_runs<9, 4>(p, d_tmem, a_lo0, b_lo0 + (uint32_t)kb * b_kb, b_hi, idesc, kb > 0 ? 1u : 0u);
             umma_commit(bar_aempty + 8 * slot);
           }
           __syncwarp();
@@ -189,14 +191,14 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
       const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
       const uint32_t a_lo0 = (1u << 16) | ((a_smem + stage * p.stage_bytes) >> 4);
       if (leader) {
-        switch (K16) {  // fully unrolled issue sequences: descriptor offsets become constant-bank operands
-          case 9: issue_mmas<9>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
-          case 18: issue_mmas<18>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
-          case 27: issue_mmas<27>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
-          case 36: issue_mmas<36>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
-          case 54: issue_mmas<54>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
-          case 72: issue_mmas<72>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
-          default: issue_mmas<108>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
+        switch (p.nruns * 8 + p.run_len) {  // fully unrolled issue sequences (tapconv_plan admits only these)
+          case 9 * 8 + 1: issue_runs<9, 1>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
+          case 27 * 8 + 1: issue_runs<27, 1>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
+          case 9 * 8 + 2: issue_runs<9, 2>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
+          case 27 * 8 + 2: issue_runs<27, 2>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
+          case 9 * 8 + 4: issue_runs<9, 4>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
+          case 18 * 8 + 4: issue_runs<18, 4>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
+          default: issue_runs<27, 4>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
         }
       }
       if (leader) {
@@ -538,10 +540,7 @@ int tapconv_plan(const TapConvLayer& L, TapConvParams* pp) {
   // input window: one 1024-aligned region per k-block (64 channels = 128-byte rows; 32-channel tail = 64-byte rows)
   p.nkb = (L.cin + 63) / 64;
   p.ring = L.ring;
-  {
-    const int k = L.ktotal16;  // the unrolled issue sequences the kernel has
-    if (!(k == 9 || k == 18 || k == 27 || k == 36 || k == 54 || k == 72 || k == 108)) return 0;
-  }
+  if (L.ktotal16 > kMaxK16) return 0;
   if (p.nkb > kMaxKBlocks || L.n_cta > 96 || (L.n_cta & 15)) return 0;
   if (L.ring && ((L.cin & 63) || L.ntaps != 9 * p.nkb || L.ktotal16 != 36 * p.nkb)) return 0;
   uint32_t off = 0;
@@ -567,6 +566,7 @@ int tapconv_plan(const TapConvLayer& L, TapConvParams* pp) {
     // version=1 [46,48) | layout [61,64) (2 = SWIZZLE_128B, 4 = SWIZZLE_64B); base_offset stays 0.
     // Ring layers list their taps k-block-major, so entries [0,36) (k-block 0) serve every k-block: the kernel adds
     // the slot address to A and kb * (9 * n_cta * 128 B) to B.
+    uint4 step[kMaxK16];
     int j = 0;
     for (int e = 0; e < L.ntaps; ++e)
       for (int i = 0; i < L.taps[e].nk16; ++i, ++j) {
@@ -578,9 +578,32 @@ int tapconv_plan(const TapConvLayer& L, TapConvParams* pp) {
         const uint32_t a_off = p.kb_off[kb] + (uint32_t)((te.dy - L.halo_y0) * L.halo_w + (te.dx - L.halo_x0)) * rowb +
                                (uint32_t)(ch0 - kb * 64) * 2u;
         const uint32_t b_off = (uint32_t)(j >> 2) * ((uint32_t)L.n_cta * 128u) + (uint32_t)(j & 3) * 32u;
-        p.mma[j] = make_uint4(a_off >> 4, (((uint32_t)L.halo_w * rowb) >> 4) | (1u << 14) | ((tail ? 4u : 2u) << 29),
-                              b_off >> 4, 0u);
+        step[j] = make_uint4(a_off >> 4, (((uint32_t)L.halo_w * rowb) >> 4) | (1u << 14) | ((tail ? 4u : 2u) << 29),
+                             b_off >> 4, 0u);
       }
+    // group the steps into runs of run_len = 4, 2 or 1 whose descriptors advance by 32 B (2 units) per step
+    const int nsteps = L.ring ? 36 : L.ktotal16;  // ring: the first k-block's entries serve every slot
+    int run_len = 1;
+    for (int len : {4, 2}) {
+      bool ok = (nsteps % len) == 0;
+      for (int r = 0; ok && r < nsteps; r += len)
+        for (int i = 1; i < len; ++i)
+          ok = ok && step[r + i].x == step[r].x + 2u * i && step[r + i].y == step[r].y &&
+               step[r + i].z == step[r].z + 2u * i;
+      if (ok) {
+        run_len = len;
+        break;
+      }
+    }
+    p.run_len = run_len;
+    p.nruns = nsteps / run_len;
+    {
+      const int key = p.nruns * 8 + run_len;  // the issue sequences the kernel has
+      const bool have = key == 9 * 8 + 1 || key == 27 * 8 + 1 || key == 9 * 8 + 2 || key == 27 * 8 + 2 ||
+                        key == 9 * 8 + 4 || key == 18 * 8 + 4 || key == 27 * 8 + 4;
+      if (!have || (L.ring && key != 9 * 8 + 4)) return 0;
+    }
+    for (int r = 0; r < p.nruns; ++r) p.mma[r] = step[r * run_len];
   }
   p.off_ss = kCtrlBytes;
   p.off_w = align_up(p.off_ss + (uint32_t)L.n_cta * 4u, 1024);

@@ -49,6 +49,7 @@ struct alignas(64) TapConvParams {
   int halo_y0, halo_x0, halo_h, halo_w;
   int stages;
   int epi_mode, out_s2d;
+  int nruns, run_len;    // MMA issue: nruns runs of run_len consecutive K=16 steps (mma[r] = first step of run r)
   int ring;              // 1: the window streams through a ring of single k-block slots (see tapconv.cu)
   int tiles_x, tiles_y, ntiles;
   int ctas_per_split;
@@ -60,7 +61,7 @@ struct alignas(64) TapConvParams {
   uint32_t kb_off[kMaxKBlocks];   // byte offset of each k-block inside a stage (1024-aligned)
   uint32_t tx_bytes;              // bytes one stage fill delivers (mbarrier transaction count)
   TapEntry taps[kMaxTaps];
-  // per K=16 step: {A start offset inside a stage, A descriptor high word, B start offset inside the weights, 0},
+  // per run: {A start offset inside a stage, A descriptor high word, B start offset inside the weights, 0},
   // offsets in 16-byte units.  Lives in the kernel parameters (constant bank) so that the MMA-issuing warp gets it
   // through uniform loads straight into uniform registers.
   uint4 mma[kMaxK16];

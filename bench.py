@@ -178,6 +178,7 @@ def main():
     import __graft_entry__ as ge
     ge.load_package()
     from cfi_b200.engine import Rife46Engine
+    from cfi_b200 import _lib as cfi_lib
 
     torch.cuda.set_device(local_rank)
     dist = None
@@ -317,7 +318,7 @@ def main():
                 "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
                         "h2d_bytes_per_step": nf * H * W * 3 * 4, "d2h_bytes_per_step": npairs * H * W * 3 * 4,
                         "host_equals_device_path": same},
-                "gpu_launches": launches, "clocks": clocks,
+                "gpu_launches": launches, "lib": cfi_lib.lib().vfi_version().decode(), "clocks": clocks,
                 "model_tflops": value * FLOPS_PER_FRAME / 1e12,
                 "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu}
         print(json.dumps(line))

@@ -16,7 +16,7 @@
 // unaligned start addresses and SBO = 1280 B work with base_offset = 0).  So the 3x3 window is read from L2 once
 // (x1.41 halo), not 9x as with im2col.  Weights of the CTA's output-channel slice are resident in shared memory for
 // the whole launch (one bulk copy, already in the swizzled operand layout), accumulators live in TMEM (double
-// buffered), the epilogue reads the ResConv residual from the input tensor (L2 hit).
+// buffered), the epilogue reads the ResConv residual back from the staged window instead of from global memory.
 //
 // Warp roles (576 threads, 1 CTA/SM, persistent over tiles):
 //   warps 0..15 : epilogue - four sets of four warps (TMEM lane quarters 0..3).  Sets {0,1} take the even tiles of
@@ -109,6 +109,15 @@ __device__ __forceinline__ void issue_runs(const TapConvParams& p, uint32_t d_tm
   }
 }
 
+// Diagnostic build only (-DVFI_ABLATE, tools/ablate.py): p.ablate switches parts of the pipeline off so that the tile time
+// of what remains can be measured.  1: no epilogue global stores / residual loads, 2: epilogue = tcgen05.ld + barrier
+// hand-shake only, 4: no tcgen05.ld either, 8: producer signals "full" without issuing TMA, 16: no tcgen05.mma.
+#ifdef VFI_ABLATE
+#define ABLATE(bit) ((p.ablate & (bit)) != 0)
+#else
+#define ABLATE(bit) false
+#endif
+
 template <typename T, bool RING, bool LAST>
 __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_constant__ TapConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -136,7 +145,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
     mbar_init(bar_w, 1);
     for (int s = 0; s < S; ++s) {
       mbar_init(bar_afull + 8 * s, 1);                  // producer's arrive.expect_tx (+ TMA transaction bytes)
-      mbar_init(bar_aempty + 8 * s, 1);                 // the MMA commit
+      mbar_init(bar_aempty + 8 * s, (residual && !RING) ? 8 : 1);  // 8 epilogue warps, or the MMA commit
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
@@ -192,7 +201,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
       const uint32_t a_lo0 = (1u << 16) | ((a_smem + stage * p.stage_bytes) >> 4);
-      if (leader) {
+      if (leader && !ABLATE(16)) {
         switch (p.nruns * 8 + p.run_len) {  // fully unrolled issue sequences (tapconv_plan admits only these)
           case 9 * 8 + 1: issue_runs<9, 1>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
           case 27 * 8 + 1: issue_runs<27, 1>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
@@ -204,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
         }
       }
       if (leader) {
-        umma_commit(bar_aempty + 8 * stage);  // window free once the MMAs have read it
+        if (!residual) umma_commit(bar_aempty + 8 * stage);  // window free once the MMAs have read it
         umma_commit(bar_tfull + 8 * acc);                    // accumulator ready for the epilogue
       }
       __syncwarp();
@@ -238,6 +247,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
         const int b = it.b;
         const int gy0 = it.ty * kTileH + p.halo_y0, gx0 = it.tx * kTileW + p.halo_x0;
         mbar_wait(bar_aempty + 8 * stage, (use & 1) ^ 1, 4);
+        if (ABLATE(8)) {
+          mbar_arrive(bar_afull + 8 * stage);
+          continue;
+        }
         mbar_arrive_expect_tx(bar_afull + 8 * stage, p.tx_bytes);
         const uint32_t dst = a_smem + stage * p.stage_bytes;
         for (int kb = 0; kb < p.nkb; ++kb) {
@@ -259,37 +272,40 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
     const int r = q * 32 + lane;  // accumulator row == TMEM lane == tile cell
     const int py = r >> 3, px = r & 7;
     const int n0 = split * p.n_cta;
+    const uint32_t center_px = (uint32_t)((py - p.halo_y0) * p.halo_w + (px - p.halo_x0));
     const int nchunks = p.n_cta >> 4;  // 16-column chunks of this CTA's accumulator
     const int h0 = (nchunks + 1) >> 1;
     const int c_lo = eset ? h0 : 0;    // this set's chunks: [c_lo, c_lo + nmine), nmine <= 3
     const int nmine = eset ? nchunks - h0 : h0;
 
+    // residual chunk offsets inside a stage are tile independent (stage size and base are multiples of 1024, so the
+    // swizzle phase of a row does not depend on the stage): computed once
+    uint32_t roff[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    const bool res_smem = residual && !RING;  // ring layers read the residual from global memory (L2 hit)
+    if (res_smem) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        if (i < nmine) {
+          const int ch0 = n0 + (c_lo + i) * 16;
+          const int kb = ch0 >> 6;
+          const bool tail = has_tail && (kb == p.nkb - 1);
+          const uint32_t rowb = tail ? 64u : 128u, msk = tail ? 3u : 7u;
+          const uint32_t row = p.off_a + p.kb_off[kb] + center_px * rowb;  // offset from the smem base
+          const uint32_t c0 = (uint32_t)(ch0 - kb * 64) >> 3, sw = ((smem_base + row) >> 7) & msk;
+          roff[i][0] = row + ((c0 ^ sw) << 4);
+          roff[i][1] = row + (((c0 + 1u) ^ sw) << 4);
+        }
+      }
+    }
     // this warp's tiles: k = acc, acc + 2, ... (k counts the CTA's tiles)
     uint32_t k = acc;
     TileIter it(p, first + (int)acc * p.ctas_per_split, 2 * p.ctas_per_split);
     for (int t = first + (int)acc * p.ctas_per_split; t < p.ntiles; t += 2 * p.ctas_per_split, k += 2, it.next()) {
-      const uint32_t vuse = k >> 1;
+      const uint32_t stage = k % S, use = k / S, vuse = k >> 1;
       const int b = it.b;
       const int gy = it.ty * kTileH + py, gx = it.tx * kTileW + px;
       const bool valid = (gy < p.H) && (gx < p.W);
 
-      // ResConv residual = the centre pixel's channels, read from the input tensor itself (an L2 hit: TMA fetched the
-      // same lines for the window moments ago; reading them back from the swizzled window cost 4-way bank conflicts on
-      // the shared-memory port the MMA operand fetch saturates, r01_v11); the first two chunks are requested before the wait for the
-      // accumulator so that the L2 latency hides behind the tile's MMAs
-      const uint4* gres = nullptr;
-      uint4 pre[2][2] = {{make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)},
-                         {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)}};
-      if (!LAST && residual && valid) {
-        gres = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.in) +
-                                              ((((size_t)b * p.H + gy) * p.W + gx) * (size_t)p.cin + (size_t)n0));
-        pre[0][0] = __ldg(gres + c_lo * 2);
-        pre[0][1] = __ldg(gres + c_lo * 2 + 1);
-        if (nmine > 1) {
-          pre[1][0] = __ldg(gres + (c_lo + 1) * 2);
-          pre[1][1] = __ldg(gres + (c_lo + 1) * 2 + 1);
-        }
-      }
       mbar_wait(bar_tfull + 8 * acc, vuse & 1, 5);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * p.acc_stride + ((uint32_t)(q * 32) << 16);
@@ -344,10 +360,20 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
       // Chunks 0 and 1 are read from TMEM together, a third one (n_cta = 80, 96) in a second round, so that at most
       // 32 accumulator values are live per thread (576 threads: 96 registers each).
       T* orow = reinterpret_cast<T*>(p.out) + (valid ? out_pixel_offset(p, b, gy, gx) + (size_t)n0 : 0);
-      auto finish_chunk = [&](int i, const uint32_t(&vv)[16], uint4 r0, uint4 r1) {
-        if (i == 2 && gres != nullptr) {
-          r0 = __ldg(gres + (c_lo + 2) * 2);
-          r1 = __ldg(gres + (c_lo + 2) * 2 + 1);
+      const uint4* gres = nullptr;  // ring layers: the centre pixel's channels in the input tensor (L2 hit)
+      if (RING && residual)
+        gres = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.in) +
+                                              ((((size_t)b * p.H + gy) * p.W + gx) * (size_t)p.cin + (size_t)n0));
+      const uint8_t* st = smem + stage * p.stage_bytes;  // generic pointer: ordinary, freely scheduled loads
+      auto finish_chunk = [&](int i, const uint32_t(&vv)[16]) {
+        uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+        if (res_smem && !ABLATE(1)) {
+          // residual = input channels n0 + 16*(c_lo+i) .. +15 of the centre pixel: two 16-byte chunks of its row
+          r0 = *reinterpret_cast<const uint4*>(st + roff[i][0]);
+          r1 = *reinterpret_cast<const uint4*>(st + roff[i][1]);
+        } else if (RING && residual && valid) {
+          r0 = __ldg(gres + (c_lo + i) * 2);
+          r1 = __ldg(gres + (c_lo + i) * 2 + 1);
         }
         const float4* sp = reinterpret_cast<const float4*>(ss + (c_lo + i) * 16);
         const float4 s0 = sp[0], s1 = sp[1], s2 = sp[2], s3 = sp[3];
@@ -367,30 +393,51 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
           o[j] = Pack2<T>::pack(fmaxf(a0, 0.2f * a0), fmaxf(a1, 0.2f * a1));  // LeakyReLU(0.2)
         }
         // 32 contiguous bytes (16 channels) of this cell's channel vector; L2 merges the halves of a sector
-        if (valid) {
+        if (valid && (!ABLATE(1) || o[0] == 0x12345678u)) {
           uint4* dst = reinterpret_cast<uint4*>(orow + (c_lo + i) * 16);
           dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
           dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
         }
       };
       uint32_t v0[16], v1[16];
+      if (ABLATE(4)) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        if (res_smem && lane == 0) mbar_arrive(bar_aempty + 8 * stage);
+        continue;
+      }
       tmem_ld16(taddr + c_lo * 16, v0);
       if (nmine > 1) tmem_ld16(taddr + (c_lo + 1) * 16, v1);
+      if (res_smem) mbar_wait(bar_afull + 8 * stage, use & 1, 6);  // acquire the TMA-written window
       tmem_ld_wait();
+      if (ABLATE(2)) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        if (res_smem && lane == 0) mbar_arrive(bar_aempty + 8 * stage);
+        if (v0[0] == 0x12345678u && v1[1] == 0x9abcdef0u) reinterpret_cast<T*>(p.out)[0] = T(1.f);  // keep the loads
+        continue;
+      }
       if (nmine <= 2) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);  // TMEM buffer free: the next tile's MMAs may start
       }
-      finish_chunk(0, v0, pre[0][0], pre[0][1]);
-      if (nmine > 1) finish_chunk(1, v1, pre[1][0], pre[1][1]);
+      finish_chunk(0, v0);
+      if (nmine > 1) finish_chunk(1, v1);
       if (nmine > 2) {
         tmem_ld16(taddr + (c_lo + 2) * 16, v0);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-        finish_chunk(2, v0, make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u));
+        finish_chunk(2, v0);
+      }
+      if (res_smem) {
+        // our generic-proxy READS of the window are complete (values consumed above); the mbarrier arrive/wait pair
+        // orders them before the producer's next TMA write - no generic write is involved, so no proxy fence
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_aempty + 8 * stage);
       }
     }
   }
@@ -618,6 +665,12 @@ cudaError_t launch_tapconv(const TapConvLayer& L, int op_type, const void* in, v
     set_error("tapconv: space-to-depth output needs even H and W");
     return cudaErrorInvalidValue;
   }
+#ifdef VFI_ABLATE
+  {
+    const char* e = std::getenv("VFI_ABLATE");
+    p.ablate = e ? std::atoi(e) : 0;
+  }
+#endif
   p.in = in;
   p.out = out;
   p.out_flow = out_flow;

@@ -23,8 +23,12 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--json", default="")
     ap.add_argument("--only", default="", help="block:layer, e.g. 3:2")
+    ap.add_argument("--lib", default="", help="alternate libvfi_b200 build (diagnostic builds, tools/ablate.sh)")
     a = ap.parse_args()
     ge.load_package()
+    if a.lib:
+        from cfi_b200 import _lib
+        _lib.LIB_PATH = os.path.abspath(a.lib)
     from cfi_b200.engine import Rife46Engine
     eng = Rife46Engine(O.synthetic_state_dict(0), 0, a.dtype)
     tdt = torch.float16 if a.dtype != "bfloat16" else torch.bfloat16

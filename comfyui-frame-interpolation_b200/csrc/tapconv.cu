@@ -102,21 +102,84 @@ __device__ __forceinline__ void issue_runs(const TapConvParams& p, uint32_t d_tm
 #pragma unroll
   for (int r = 0; r < NR; ++r) {
     const uint4 d = p.mma[r];
-    const uint32_t a = a_lo0 + d.x, b = b_lo0 + d.z;
+    // whole 64-bit descriptors advanced in place (+32 B per K=16 step): each stays in one uniform register pair, no
+    // per-MMA re-packing of {lo, hi} (r01: that cost UMOVs and uniform-register spills, ~83 cycles of issue per MMA)
+    uint64_t a64 = ((uint64_t)d.y << 32) | (uint64_t)(a_lo0 + d.x);
+    uint64_t b64 = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo0 + d.z);
 #pragma unroll
-    for (int i = 0; i < L; ++i)
-      umma_f16_split(d_tmem, a + 2u * i, d.y, b + 2u * i, b_hi, idesc, (r | i) ? 1u : accumulate_first);
+    for (int i = 0; i < L; ++i) {
+      umma_f16(d_tmem, a64, b64, idesc, (r | i) ? 1u : accumulate_first);
+      a64 += 2;
+      b64 += 2;
+    }
   }
 }
 
+struct MmaLoopArgs {
+  uint32_t bar_tfull, bar_tempty, bar_afull, bar_aempty;  // shared-memory addresses of the barrier arrays
+  uint32_t tmem_base, a_base, b_lo0, b_hi;
+  int ntiles;        // tiles of this CTA
+  uint32_t S;        // window stages / ring slots
+  bool commit_stage; // the MMA commit releases the window stage (false: the epilogue does, after reading the residual)
+};
+
 // Diagnostic build only (-DVFI_ABLATE, tools/ablate.py): p.ablate switches parts of the pipeline off so that the tile time
 // of what remains can be measured.  1: no epilogue global stores / residual loads, 2: epilogue = tcgen05.ld + barrier
-// hand-shake only, 4: no tcgen05.ld either, 8: producer signals "full" without issuing TMA, 16: no tcgen05.mma.
+// hand-shake only, 4: no tcgen05.ld either, 8: producer signals "full" without issuing TMA, 16: no tcgen05.mma,
+// 32 / 64: the MMA warp does not wait for the accumulator / the window, 256: no tcgen05.fence in its loop, 512: no
+// tcgen05.commit, 1024: only the MMA warp runs (results are garbage, timing only).
 #ifdef VFI_ABLATE
 #define ABLATE(bit) ((p.ablate & (bit)) != 0)
 #else
 #define ABLATE(bit) false
 #endif
+
+// The issuing thread's whole life: for every tile of the CTA wait for a free accumulator and a full window (or, for
+// ring layers, k-block slot by slot), issue the MMAs, commit.
+template <int NR, int L, bool RING>
+__device__ __forceinline__ void mma_tile_loop(const TapConvParams& p, const MmaLoopArgs& g) {
+  const uint32_t idesc = p.idesc;
+  const uint32_t stage_units = p.stage_bytes >> 4;
+  uint32_t stage = 0, aph = 0;        // window stage / ring slot and its "full" parity
+  uint32_t a_lo = g.a_base;           // descriptor low word of the current stage
+  uint32_t acc = 0, tph = 1;          // accumulator buffer and the parity of its "empty" barrier
+  const uint32_t b_kb = (9u * (uint32_t)p.n_cta * 128u) >> 4;  // ring: weight bytes of one k-block, 16-byte units
+  for (int k = 0; k < g.ntiles; ++k) {
+    if (!ABLATE(32)) mbar_wait(g.bar_tempty + 8 * acc, tph, 2);
+    const uint32_t d_tmem = g.tmem_base + acc * p.acc_stride;
+    if (RING) {
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        mbar_wait(g.bar_afull + 8 * stage, aph, 3);
+        tc_fence_after();
+        issue_runs<NR, L>(p, d_tmem, a_lo, g.b_lo0 + (uint32_t)kb * b_kb, g.b_hi, idesc, kb > 0 ? 1u : 0u);
+        umma_commit(g.bar_aempty + 8 * stage);
+        a_lo += stage_units;
+        if (++stage == g.S) {
+          stage = 0;
+          aph ^= 1u;
+          a_lo = g.a_base;
+        }
+      }
+      umma_commit(g.bar_tfull + 8 * acc);
+    } else {
+      if (!ABLATE(64)) mbar_wait(g.bar_afull + 8 * stage, aph, 3);
+      if (!ABLATE(256)) tc_fence_after();
+      if (!ABLATE(16)) issue_runs<NR, L>(p, d_tmem, a_lo, g.b_lo0, g.b_hi, idesc);
+      if (!ABLATE(512)) {
+        if (g.commit_stage) umma_commit(g.bar_aempty + 8 * stage);  // window free once the MMAs have read it
+        umma_commit(g.bar_tfull + 8 * acc);                          // accumulator ready for the epilogue
+      }
+      a_lo += stage_units;
+      if (++stage == g.S) {
+        stage = 0;
+        aph ^= 1u;
+        a_lo = g.a_base;
+      }
+    }
+    acc ^= 1u;
+    if (acc == 0) tph ^= 1u;
+  }
+}
 
 template <typename T, bool RING, bool LAST>
 __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_constant__ TapConvParams p) {
@@ -130,6 +193,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
   if (first >= p.ctas_per_split) return;  // whole CTA leaves together
   const int S = p.stages;
   const bool residual = !LAST && (p.epi_mode == EPI_RESCONV);
+  const bool res_smem = residual && !RING;  // ring layers read the residual from global memory (L2 hit)
 
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_w = smem_base + offsetof(Ctrl, w_full);
@@ -161,71 +225,49 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
 
   if (warp == kMmaWarp) {
     // ======================================================= MMA issuer
-    // The whole warp runs the (warp-uniform) control flow; one elected lane issues tcgen05.mma / tcgen05.commit.
-    const uint32_t leader = elect_one_sync();
-    mbar_wait(bar_w, 0, 1);
-    const uint32_t idesc = p.idesc;
-    const uint32_t b_lo0 = (1u << 16) | (w_smem >> 4);  // LBO(=1) | start address, 16-byte units
-    const uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO | version | SWIZZLE_128B
-    uint32_t k = 0;
-    if (RING) {
-      // ring of single k-block slots: 36 MMAs (9 taps x 64 channels) per slot, slot released by its own commit
-      const uint32_t b_kb = (9u * (uint32_t)p.n_cta * 128u) >> 4;  // weight bytes of one k-block, 16-byte units
-      uint32_t slot = 0, ph = 0;
-      for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k) {
-        const uint32_t acc = k & 1, vuse = k >> 1;
-        mbar_wait(bar_tempty + 8 * acc, (vuse & 1) ^ 1, 2);
-        const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
-        for (int kb = 0; kb < p.nkb; ++kb) {
-          mbar_wait(bar_afull + 8 * slot, ph, 3);
-          tc_fence_after();
-          const uint32_t a_lo0 = (1u << 16) | ((a_smem + slot * p.stage_bytes) >> 4);
-          if (leader) {
-            issue_runs<9, 4>(p, d_tmem, a_lo0, b_lo0 + (uint32_t)kb * b_kb, b_hi, idesc, kb > 0 ? 1u : 0u);
-            umma_commit(bar_aempty + 8 * slot);
-          }
-          __syncwarp();
-          if (++slot == (uint32_t)S) {
-            slot = 0;
-            ph ^= 1u;
-          }
-        }
-        if (leader) umma_commit(bar_tfull + 8 * acc);
-        __syncwarp();
-      }
-    } else
-    for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k) {
-      const uint32_t stage = k % S, use = k / S, acc = k & 1, vuse = k >> 1;
-      mbar_wait(bar_tempty + 8 * acc, (vuse & 1) ^ 1, 2);
-      mbar_wait(bar_afull + 8 * stage, use & 1, 3);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
-      const uint32_t a_lo0 = (1u << 16) | ((a_smem + stage * p.stage_bytes) >> 4);
-      if (leader && !ABLATE(16)) {
+    // ONE elected lane runs the whole tile loop (the other lanes go straight to the final barrier).  Per tile it does
+    // two mbarrier waits, the fence, the unrolled MMAs and the commits - nothing else: stage / phase / accumulator
+    // state is carried incrementally and the issue shape is dispatched once, outside the loop (r01 ablation: with a
+    // division, a switch and warp re-convergence per tile the loop cost 660 cycles per tile on top of the MMAs, none
+    // of it overlapped with the tensor pipe, whose queue is only a few MMAs deep).
+    if (elect_one_sync()) {
+      if (!ABLATE(1024)) mbar_wait(bar_w, 0, 1);
+      const uint32_t b_lo0 = (1u << 16) | (w_smem >> 4);              // LBO(=1) | start address, 16-byte units
+      const uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO | version | SWIZZLE_128B
+      const int my_tiles = (p.ntiles - first + p.ctas_per_split - 1) / p.ctas_per_split;
+      MmaLoopArgs g;
+      g.bar_tfull = bar_tfull;
+      g.bar_tempty = bar_tempty;
+      g.bar_afull = bar_afull;
+      g.bar_aempty = bar_aempty;
+      g.tmem_base = tmem_base;
+      g.a_base = (1u << 16) | (a_smem >> 4);
+      g.b_lo0 = b_lo0;
+      g.b_hi = b_hi;
+      g.ntiles = my_tiles;
+      g.S = (uint32_t)S;
+      g.commit_stage = !res_smem;
+      if (RING) {
+        mma_tile_loop<9, 4, true>(p, g);
+      } else {
         switch (p.nruns * 8 + p.run_len) {  // fully unrolled issue sequences (tapconv_plan admits only these)
-          case 9 * 8 + 1: issue_runs<9, 1>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
-          case 27 * 8 + 1: issue_runs<27, 1>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
-          case 9 * 8 + 2: issue_runs<9, 2>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
-          case 27 * 8 + 2: issue_runs<27, 2>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
-          case 9 * 8 + 4: issue_runs<9, 4>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
-          case 18 * 8 + 4: issue_runs<18, 4>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
-          default: issue_runs<27, 4>(p, d_tmem, a_lo0, b_lo0, b_hi, idesc); break;
+          case 9 * 8 + 1: mma_tile_loop<9, 1, false>(p, g); break;
+          case 27 * 8 + 1: mma_tile_loop<27, 1, false>(p, g); break;
+          case 9 * 8 + 2: mma_tile_loop<9, 2, false>(p, g); break;
+          case 27 * 8 + 2: mma_tile_loop<27, 2, false>(p, g); break;
+          case 9 * 8 + 4: mma_tile_loop<9, 4, false>(p, g); break;
+          case 18 * 8 + 4: mma_tile_loop<18, 4, false>(p, g); break;
+          default: mma_tile_loop<27, 4, false>(p, g); break;
         }
       }
-      if (leader) {
-        if (!residual) umma_commit(bar_aempty + 8 * stage);  // window free once the MMAs have read it
-        umma_commit(bar_tfull + 8 * acc);                    // accumulator ready for the epilogue
-      }
-      __syncwarp();
     }
   } else if (warp == kTmaWarp) {
     // ======================================================= TMA producer (one thread feeds the whole pipeline)
-    if (elect_one_sync()) {
+    if (elect_one_sync() && !ABLATE(1024)) {
       mbar_arrive_expect_tx(bar_w, p.w_bytes);
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + (size_t)split * p.w_bytes;
       for (uint32_t off = 0; off < p.w_bytes; off += 32768u)
         bulk_g2s(w_smem + off, wsrc + off, min(32768u, p.w_bytes - off), bar_w);
-      uint32_t k = 0;
       TileIter it(p, first, p.ctas_per_split);
       if (RING) {
         uint32_t slot = 0, ph = 0;
@@ -241,22 +283,27 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
             }
           }
         }
-      } else
-      for (int t = first; t < p.ntiles; t += p.ctas_per_split, ++k, it.next()) {
-        const uint32_t stage = k % S, use = k / S;
+      } else {
+      uint32_t stage = 0, eph = 1;  // window stage and the parity of its "empty" barrier
+      for (int t = first; t < p.ntiles; t += p.ctas_per_split, it.next()) {
         const int b = it.b;
         const int gy0 = it.ty * kTileH + p.halo_y0, gx0 = it.tx * kTileW + p.halo_x0;
-        mbar_wait(bar_aempty + 8 * stage, (use & 1) ^ 1, 4);
+        mbar_wait(bar_aempty + 8 * stage, eph, 4);
         if (ABLATE(8)) {
           mbar_arrive(bar_afull + 8 * stage);
-          continue;
+        } else {
+          mbar_arrive_expect_tx(bar_afull + 8 * stage, p.tx_bytes);
+          const uint32_t dst = a_smem + stage * p.stage_bytes;
+          for (int kb = 0; kb < p.nkb; ++kb) {
+            const bool tail = has_tail && (kb == p.nkb - 1);
+            tma_load_4d(dst + p.kb_off[kb], tail ? &p.tm32 : &p.tm64, bar_afull + 8 * stage, kb * 64, gx0, gy0, b);
+          }
         }
-        mbar_arrive_expect_tx(bar_afull + 8 * stage, p.tx_bytes);
-        const uint32_t dst = a_smem + stage * p.stage_bytes;
-        for (int kb = 0; kb < p.nkb; ++kb) {
-          const bool tail = has_tail && (kb == p.nkb - 1);
-          tma_load_4d(dst + p.kb_off[kb], tail ? &p.tm32 : &p.tm64, bar_afull + 8 * stage, kb * 64, gx0, gy0, b);
+        if (++stage == (uint32_t)S) {
+          stage = 0;
+          eph ^= 1u;
         }
+      }
       }
     }
     __syncwarp();
@@ -281,7 +328,6 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
     // residual chunk offsets inside a stage are tile independent (stage size and base are multiples of 1024, so the
     // swizzle phase of a row does not depend on the stage): computed once
     uint32_t roff[3][2] = {{0, 0}, {0, 0}, {0, 0}};
-    const bool res_smem = residual && !RING;  // ring layers read the residual from global memory (L2 hit)
     if (res_smem) {
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
@@ -299,9 +345,22 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
     }
     // this warp's tiles: k = acc, acc + 2, ... (k counts the CTA's tiles)
     uint32_t k = acc;
+    uint32_t stage = acc % (uint32_t)S, use = acc / (uint32_t)S;  // window stage of tile k (= k % S) and its use count
+    if (ABLATE(1024)) k = 0x7fffffffu;
     TileIter it(p, first + (int)acc * p.ctas_per_split, 2 * p.ctas_per_split);
-    for (int t = first + (int)acc * p.ctas_per_split; t < p.ntiles; t += 2 * p.ctas_per_split, k += 2, it.next()) {
-      const uint32_t stage = k % S, use = k / S, vuse = k >> 1;
+    for (int t = first + (int)acc * p.ctas_per_split; t < p.ntiles && k != 0x7fffffffu; t += 2 * p.ctas_per_split, k += 2, it.next()) {
+      if (k != acc) {  // advance (stage, use) by two tiles
+        stage += 2;
+        if (stage >= (uint32_t)S) {
+          stage -= (uint32_t)S;
+          ++use;
+          if (stage >= (uint32_t)S) {  // S == 1
+            stage -= (uint32_t)S;
+            ++use;
+          }
+        }
+      }
+      const uint32_t vuse = k >> 1;
       const int b = it.b;
       const int gy = it.ty * kTileH + py, gx = it.tx * kTileW + px;
       const bool valid = (gy < p.H) && (gx < p.W);

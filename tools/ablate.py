@@ -22,7 +22,7 @@ eng = Rife46Engine(O.synthetic_state_dict(0), 0, "float16")
 print(_lib.lib().vfi_version().decode())
 B, Hp, Wp = 8, 1088, 1920
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for blk, layer in ((3, 2), (2, 2), (1, 2), (3, 1), (3, 0)):
+for blk, layer in ((3, 2), (3, 1), (2, 2)):
     s = (8, 4, 2, 1)[blk]
     c = BLOCK_C[blk]
     Hs, Ws = Hp // s, Wp // s
@@ -33,7 +33,7 @@ for blk, layer in ((3, 2), (2, 2), (1, 2), (3, 1), (3, 0)):
     om = torch.zeros(16, device="cuda")
     tiles = B * ((ishape[1] + 15) // 16) * ((ishape[2] + 7) // 8)
     pl = eng.layer_plan(blk, layer)
-    for m in (0, 1, 2, 4, 8, 16, 12, 24, 20, 28):
+    for m in (0, 12, 12 + 96, 28, 1024 + 96, 1024 + 96 + 16):
         os.environ["VFI_ABLATE"] = str(m)
         ts = []
         for it in range(6):

@@ -12,13 +12,18 @@ using namespace vfi;
 
 struct Res { long long cycles; };
 
-__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int shifted, int iters, Res* out) {
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int shifted, int iters, int pattern, int commit_every, Res* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
   const uint32_t base = smem_u32(smem);
   // zero the operands (values do not matter for timing; zeros keep the accumulator finite)
-  for (int i = threadIdx.x; i < (64 * 1024) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < (64 * 1024) / 2; i += blockDim.x) {
+    uint32_t h = (uint32_t)i * 2654435761u + 12345u * (blockIdx.x + 1);
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    const float f = pattern ? ((float)(h & 0xffff) / 32768.f - 1.f) * 0.5f : 0.f;
+    reinterpret_cast<__half*>(smem)[i] = __float2half(f);
+  }
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&bar), 1);
     mbar_fence_init();
@@ -38,13 +43,14 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int shifted, in
   if (threadIdx.x == 0) {
     t0 = clock64();
     for (int it = 0; it < iters; ++it) {
+      const uint32_t tm = tmem + ((commit_every && (it & 1)) ? 128u : 0u);  // alternate two accumulators
 #pragma unroll
       for (int j = 0; j < 36; ++j) {
         const int tap = j >> 2, k = j & 3;
         const uint32_t a_off = shifted ? (uint32_t)((tap / 3) * 10 + (tap % 3)) * 128u + k * 32u : k * 32u;
         const uint32_t a_lo = (1u << 16) | ((a_base + a_off) >> 4);
         const uint32_t b_lo = (1u << 16) | ((b_base + k * 32u) >> 4);
-        umma_f16_split(tmem, a_lo, a_hi, b_lo, b_hi, idesc, (it | j) ? 1u : 0u);
+        umma_f16_split(tm, a_lo, a_hi, b_lo, b_hi, idesc, (commit_every ? j : (it | j)) ? 1u : 0u);
       }
     }
     umma_commit(smem_u32(&bar));
@@ -68,11 +74,22 @@ int main() {
   cudaMalloc(&d, sizeof(Res) * sms);
   cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   const int iters = 200;
+  printf("-- N = 64, tap-shifted: zeros vs random fp16 operands, one accumulator vs two alternating (fresh each 36)\n");
+  for (int pattern = 0; pattern < 2; ++pattern)
+    for (int ce = 0; ce < 2; ++ce) {
+      for (int rep = 0; rep < 2; ++rep) mma_rate_kernel<<<sms, 128, 64 * 1024>>>(64, 1, iters, pattern, ce, d);
+      cudaDeviceSynchronize();
+      Res h[256];
+      cudaMemcpy(h, d, sizeof(Res) * sms, cudaMemcpyDeviceToHost);
+      double mean = 0;
+      for (int i = 0; i < sms; ++i) mean += (double)h[i].cycles;
+      printf("pattern %d two_acc %d: %.1f cycles/MMA\n", pattern, ce, mean / sms / (iters * 36.0));
+    }
   printf("tcgen05.mma M128 x N x K16 (SS, SW128 K-major), %d SMs, %d MMAs per CTA\n", sms, iters * 36);
   printf("%5s %8s %14s %14s %12s\n", "N", "shifted", "cycles/MMA", "math cyc@4096", "TF/s all SMs");
   for (int shifted = 0; shifted < 2; ++shifted)
     for (int N : {16, 32, 48, 64, 80, 96, 128, 192, 256}) {
-      for (int rep = 0; rep < 2; ++rep) mma_rate_kernel<<<sms, 128, 64 * 1024>>>(N, shifted, iters, d);
+      for (int rep = 0; rep < 2; ++rep) mma_rate_kernel<<<sms, 128, 64 * 1024>>>(N, shifted, iters, 0, 0, d);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
       Res h[256];

@@ -47,7 +47,7 @@ struct Ctrl {
   uint32_t tmem_base;
 };
 constexpr uint32_t kCtrlBytes = 256;
-constexpr int kEpiWarps = 16, kMmaWarp = 16, kTmaWarp = 17, kThreads = 32 * 18;
+constexpr int kEpiWarps = 16, kMmaWarp = 16, kMmaWarp2 = 17, kTmaWarp = 18, kThreads = 32 * 19;
 static_assert(sizeof(Ctrl) <= kCtrlBytes, "control block");
 
 __device__ __forceinline__ size_t out_pixel_offset(const TapConvParams& p, int b, int gy, int gx) {
@@ -127,57 +127,62 @@ struct MmaLoopArgs {
 // of what remains can be measured.  1: no epilogue global stores / residual loads, 2: epilogue = tcgen05.ld + barrier
 // hand-shake only, 4: no tcgen05.ld either, 8: producer signals "full" without issuing TMA, 16: no tcgen05.mma,
 // 32 / 64: the MMA warp does not wait for the accumulator / the window, 256: no tcgen05.fence in its loop, 512: no
-// tcgen05.commit, 1024: only the MMA warp runs (results are garbage, timing only).
+// tcgen05.commit, 1024: only the MMA warps run (results are garbage, timing only), 2048: one issuing thread.
 #ifdef VFI_ABLATE
 #define ABLATE(bit) ((p.ablate & (bit)) != 0)
 #else
 #define ABLATE(bit) false
 #endif
 
-// The issuing thread's whole life: for every tile of the CTA wait for a free accumulator and a full window (or, for
-// ring layers, k-block slot by slot), issue the MMAs, commit.
+// An issuing thread's whole life.  With an even number of window stages TWO threads (one lane of warp 16, one of
+// warp 17) share the work: thread `which` takes the CTA's tiles which, which + 2, ... and with them TMEM accumulator
+// `which` and the window stages of its parity - every barrier keeps exactly one waiter that sees each of its phases
+// in turn (an mbarrier parity wait cannot tell phase n from n + 2).  Ring layers and odd stage counts use one thread.  While one of them sits in its
+// commit / fence / barrier waits (~600 cycles per tile, r01 ablation, with a tensor-pipe queue only a few MMAs deep)
+// the other one keeps the pipe fed.  Per tile: wait for the free accumulator and the full window (ring layers: k-block
+// slot by slot), issue the MMAs, commit.
+__device__ __forceinline__ void advance_stage(uint32_t& stage, uint32_t& ph, uint32_t n, uint32_t S) {
+  stage += n;
+  while (stage >= S) {
+    stage -= S;
+    ph ^= 1u;
+  }
+}
+
 template <int NR, int L, bool RING>
-__device__ __forceinline__ void mma_tile_loop(const TapConvParams& p, const MmaLoopArgs& g) {
+__device__ __forceinline__ void mma_tile_loop(const TapConvParams& p, const MmaLoopArgs& g, uint32_t which,
+                                              uint32_t nissuers) {
   const uint32_t idesc = p.idesc;
   const uint32_t stage_units = p.stage_bytes >> 4;
-  uint32_t stage = 0, aph = 0;        // window stage / ring slot and its "full" parity
-  uint32_t a_lo = g.a_base;           // descriptor low word of the current stage
-  uint32_t acc = 0, tph = 1;          // accumulator buffer and the parity of its "empty" barrier
+  uint32_t stage = 0, aph = 0;                            // window stage / ring slot and its "full" parity
+  const uint32_t per_tile = RING ? (uint32_t)p.nkb : 1u;  // stages / slots one tile consumes
+  advance_stage(stage, aph, which * per_tile, g.S);
   const uint32_t b_kb = (9u * (uint32_t)p.n_cta * 128u) >> 4;  // ring: weight bytes of one k-block, 16-byte units
-  for (int k = 0; k < g.ntiles; ++k) {
-    if (!ABLATE(32)) mbar_wait(g.bar_tempty + 8 * acc, tph, 2);
+  for (uint32_t k = which; k < (uint32_t)g.ntiles; k += nissuers) {
+    const uint32_t acc = k & 1u;  // accumulator buffer; its "empty" barrier is waited with parity ((k >> 1) & 1) ^ 1
     const uint32_t d_tmem = g.tmem_base + acc * p.acc_stride;
+    if (!ABLATE(32)) mbar_wait(g.bar_tempty + 8 * acc, ((k >> 1) & 1u) ^ 1u, 2);
     if (RING) {
       for (int kb = 0; kb < p.nkb; ++kb) {
         mbar_wait(g.bar_afull + 8 * stage, aph, 3);
         tc_fence_after();
-        issue_runs<NR, L>(p, d_tmem, a_lo, g.b_lo0 + (uint32_t)kb * b_kb, g.b_hi, idesc, kb > 0 ? 1u : 0u);
+        issue_runs<NR, L>(p, d_tmem, g.a_base + stage * stage_units, g.b_lo0 + (uint32_t)kb * b_kb, g.b_hi, idesc,
+                          kb > 0 ? 1u : 0u);
         umma_commit(g.bar_aempty + 8 * stage);
-        a_lo += stage_units;
-        if (++stage == g.S) {
-          stage = 0;
-          aph ^= 1u;
-          a_lo = g.a_base;
-        }
+        advance_stage(stage, aph, 1u, g.S);
       }
       umma_commit(g.bar_tfull + 8 * acc);
+      if (nissuers > 1) advance_stage(stage, aph, per_tile, g.S);  // the other thread's tile
     } else {
       if (!ABLATE(64)) mbar_wait(g.bar_afull + 8 * stage, aph, 3);
       if (!ABLATE(256)) tc_fence_after();
-      if (!ABLATE(16)) issue_runs<NR, L>(p, d_tmem, a_lo, g.b_lo0, g.b_hi, idesc);
+      if (!ABLATE(16)) issue_runs<NR, L>(p, d_tmem, g.a_base + stage * stage_units, g.b_lo0, g.b_hi, idesc);
       if (!ABLATE(512)) {
         if (g.commit_stage) umma_commit(g.bar_aempty + 8 * stage);  // window free once the MMAs have read it
         umma_commit(g.bar_tfull + 8 * acc);                          // accumulator ready for the epilogue
       }
-      a_lo += stage_units;
-      if (++stage == g.S) {
-        stage = 0;
-        aph ^= 1u;
-        a_lo = g.a_base;
-      }
+      advance_stage(stage, aph, nissuers, g.S);
     }
-    acc ^= 1u;
-    if (acc == 0) tph ^= 1u;
   }
 }
 
@@ -223,9 +228,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = ctrl->tmem_base;
 
-  if (warp == kMmaWarp) {
-    // ======================================================= MMA issuer
-    // ONE elected lane runs the whole tile loop (the other lanes go straight to the final barrier).  Per tile it does
+  if (warp == kMmaWarp || warp == kMmaWarp2) {
+    // ======================================================= MMA issuers
+    // ONE elected lane per issuing warp runs its tile loop (the other lanes go straight to the final barrier).  Per tile it does
     // two mbarrier waits, the fence, the unrolled MMAs and the commits - nothing else: stage / phase / accumulator
     // state is carried incrementally and the issue shape is dispatched once, outside the loop (r01 ablation: with a
     // division, a switch and warp re-convergence per tile the loop cost 660 cycles per tile on top of the MMAs, none
@@ -247,17 +252,20 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
       g.ntiles = my_tiles;
       g.S = (uint32_t)S;
       g.commit_stage = !res_smem;
+      const uint32_t which = (warp == kMmaWarp) ? 0u : 1u;
+      const uint32_t nissuers = (!RING && (S & 1) == 0 && !ABLATE(2048)) ? 2u : 1u;
+      if (which >= nissuers) g.ntiles = 0;
       if (RING) {
-        mma_tile_loop<9, 4, true>(p, g);
+        mma_tile_loop<9, 4, true>(p, g, which, nissuers);
       } else {
         switch (p.nruns * 8 + p.run_len) {  // fully unrolled issue sequences (tapconv_plan admits only these)
-          case 9 * 8 + 1: mma_tile_loop<9, 1, false>(p, g); break;
-          case 27 * 8 + 1: mma_tile_loop<27, 1, false>(p, g); break;
-          case 9 * 8 + 2: mma_tile_loop<9, 2, false>(p, g); break;
-          case 27 * 8 + 2: mma_tile_loop<27, 2, false>(p, g); break;
-          case 9 * 8 + 4: mma_tile_loop<9, 4, false>(p, g); break;
-          case 18 * 8 + 4: mma_tile_loop<18, 4, false>(p, g); break;
-          default: mma_tile_loop<27, 4, false>(p, g); break;
+          case 9 * 8 + 1: mma_tile_loop<9, 1, false>(p, g, which, nissuers); break;
+          case 27 * 8 + 1: mma_tile_loop<27, 1, false>(p, g, which, nissuers); break;
+          case 9 * 8 + 2: mma_tile_loop<9, 2, false>(p, g, which, nissuers); break;
+          case 27 * 8 + 2: mma_tile_loop<27, 2, false>(p, g, which, nissuers); break;
+          case 9 * 8 + 4: mma_tile_loop<9, 4, false>(p, g, which, nissuers); break;
+          case 18 * 8 + 4: mma_tile_loop<18, 4, false>(p, g, which, nissuers); break;
+          default: mma_tile_loop<27, 4, false>(p, g, which, nissuers); break;
         }
       }
     }

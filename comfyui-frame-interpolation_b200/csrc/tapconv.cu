@@ -127,7 +127,7 @@ struct MmaLoopArgs {
 // of what remains can be measured.  1: no epilogue global stores / residual loads, 2: epilogue = tcgen05.ld + barrier
 // hand-shake only, 4: no tcgen05.ld either, 8: producer signals "full" without issuing TMA, 16: no tcgen05.mma,
 // 32 / 64: the MMA warp does not wait for the accumulator / the window, 256: no tcgen05.fence in its loop, 512: no
-// tcgen05.commit, 1024: only the MMA warps run (results are garbage, timing only), 2048: one issuing thread.
+// tcgen05.commit, 1024: only the MMA warps run (results are garbage, timing only).
 #ifdef VFI_ABLATE
 #define ABLATE(bit) ((p.ablate & (bit)) != 0)
 #else
@@ -253,7 +253,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
       g.S = (uint32_t)S;
       g.commit_stage = !res_smem;
       const uint32_t which = (warp == kMmaWarp) ? 0u : 1u;
-      const uint32_t nissuers = (!RING && (S & 1) == 0 && !ABLATE(2048)) ? 2u : 1u;
+      // Two issuers lift the MMA-only floor (ablation, block-3 ResConv: 2445 -> 2154 cycles per tile) but not the whole
+      // kernel (3397 vs 3686: more contention with the epilogue warps on the same schedulers), so one is the default;
+      // p.issuers = 2 (VFI_ISSUERS=2) keeps the other path measurable.
+      const uint32_t nissuers = (p.issuers == 2 && !RING && (S & 1) == 0) ? 2u : 1u;
       if (which >= nissuers) g.ntiles = 0;
       if (RING) {
         mma_tile_loop<9, 4, true>(p, g, which, nissuers);
@@ -731,6 +734,13 @@ cudaError_t launch_tapconv(const TapConvLayer& L, int op_type, const void* in, v
   if (L.out_s2d && ((H | W) & 1)) {
     set_error("tapconv: space-to-depth output needs even H and W");
     return cudaErrorInvalidValue;
+  }
+  {
+    static const int issuers = [] {
+      const char* e = std::getenv("VFI_ISSUERS");
+      return (e && e[0] == '2') ? 2 : 1;
+    }();
+    p.issuers = issuers;
   }
 #ifdef VFI_ABLATE
   {

@@ -50,6 +50,7 @@ struct alignas(64) TapConvParams {
   int stages;
   int epi_mode, out_s2d;
   int nruns, run_len;    // MMA issue: nruns runs of run_len consecutive K=16 steps (mma[r] = first step of run r)
+  int issuers;           // MMA-issuing threads: 1 (default) or 2 (even stage counts only; VFI_ISSUERS=2)
   int ablate;            // diagnostic builds only (-DVFI_ABLATE): pipeline parts switched off, see tapconv.cu
   int ring;              // 1: the window streams through a ring of single k-block slots (see tapconv.cu)
   int tiles_x, tiles_y, ntiles;

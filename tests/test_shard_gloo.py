@@ -39,8 +39,19 @@ def _worker(rank, world, port, q):
     frames = O.synthetic_clip(6, 16, 24, seed=3)
     tasks, _ = O.build_tasks(6, [3, 2, 1, 4], ([4], True))  # ragged: 2+1+0+3+skip = 6 tasks over 5 pairs
     out = shard.interpolate_sharded(_fake_run, frames, tasks, dist)
+    # chunked compute-then-gather pipeline (the N>1 device path of bench.py): same result as the single gather
+    slices = shard.shard_tasks(len(tasks), world)
+    counts = [b - a for a, b in slices]
+    lo, hi = slices[rank]
+    mine = list(tasks[lo:hi])
+    local = torch.full((max(counts), 16, 24, 3), float("nan"))
+
+    def run_slice(a, b):
+        local[a:b] = _fake_run(frames, mine[a:b], shard.frame_range(mine))
+
+    bufs = shard.forward_and_gather(run_slice, local, counts, dist, nchunks=2)
     if rank == 0:
-        q.put(out)
+        q.put((out, torch.cat([b_[:c] for b_, c in zip(bufs, counts)], 0)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -53,7 +64,7 @@ def test_sharded_equals_single_process(pkg):
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got = q.get(timeout=120)
+    got, got_pipelined = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -61,6 +72,7 @@ def test_sharded_equals_single_process(pkg):
     tasks, _ = O.build_tasks(6, [3, 2, 1, 4], ([4], True))
     want = _fake_run(frames, tasks, shard.frame_range(tasks))
     assert torch.equal(got, want)
+    assert torch.equal(got_pipelined, want)
 
 
 def test_shard_tasks_balance(pkg):
@@ -69,3 +81,5 @@ def test_shard_tasks_balance(pkg):
     assert shard.shard_tasks(3, 4) == [(0, 1), (1, 2), (2, 3), (3, 3)]
     assert shard.shard_tasks(0, 2) == [(0, 0), (0, 0)]
     assert shard.frame_range([(2, 0.5), (2, 0.75), (5, 0.5)]) == (2, 7)
+    assert shard.chunk_bounds(63, 4) == [(0, 16), (16, 32), (32, 48), (48, 63)]
+    assert shard.chunk_bounds(2, 4) == [(0, 1), (1, 2)]

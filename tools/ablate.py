@@ -33,7 +33,7 @@ for blk, layer in ((3, 2), (3, 1), (2, 2)):
     om = torch.zeros(16, device="cuda")
     tiles = B * ((ishape[1] + 15) // 16) * ((ishape[2] + 7) // 8)
     pl = eng.layer_plan(blk, layer)
-    for m in (0, 2048, 12, 12 + 2048, 28, 1024 + 96, 1024 + 96 + 2048):
+    for m in (0, 12, 24, 28, 1024 + 96):
         os.environ["VFI_ABLATE"] = str(m)
         ts = []
         for it in range(6):

@@ -573,6 +573,171 @@ __global__ void front47_kernel(const float4* __restrict__ imgs, const float4* __
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// arch 4.17 (rife417.pth): encode = Head_417 (rife_arch.py:356-375).  cnn0 (Conv2d 3->32, stride 2) + LeakyReLU runs
+// here on the CUDA cores (0.45 GMAC per 1080p frame) and leaves a 16-bit NHWC [Hh][Wh][32] tensor for the tensor-core
+// layers cnn1, cnn2 (32->32) and cnn3 (ConvTranspose 32->8, stored as the space-to-depth tensor [Hh][Wh][(a,b,oc)]).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void head0_kernel(const float4* __restrict__ imgs, const float* __restrict__ w,
+                             const float* __restrict__ bias, T* __restrict__ out, int n, int Hp, int Wp) {
+  __shared__ float ws[32 * 27 + 32];
+  for (int i = threadIdx.x; i < 32 * 27; i += blockDim.x) ws[i] = w[i];
+  for (int i = threadIdx.x; i < 32; i += blockDim.x) ws[32 * 27 + i] = bias[i];
+  __syncthreads();
+  const int Hh = Hp >> 1, Wh = Wp >> 1;
+  const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (x >= Wh) return;
+  const int y = (int)blockIdx.y, f = (int)blockIdx.z;
+  const float4* img = imgs + (size_t)f * Hp * Wp;
+  float acc[32];
+#pragma unroll
+  for (int o = 0; o < 32; ++o) acc[o] = ws[32 * 27 + o];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int Y = 2 * y + ky - 1;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int X = 2 * x + kx - 1;
+      if (Y >= 0 && Y < Hp && X >= 0 && X < Wp) {
+        const float4 px = __ldg(img + (Y * Wp + X));
+#pragma unroll
+        for (int o = 0; o < 32; ++o) {  // weight [o][c][ky][kx]
+          acc[o] = fmaf(px.x, ws[(o * 3 + 0) * 9 + ky * 3 + kx], acc[o]);
+          acc[o] = fmaf(px.y, ws[(o * 3 + 1) * 9 + ky * 3 + kx], acc[o]);
+          acc[o] = fmaf(px.z, ws[(o * 3 + 2) * 9 + ky * 3 + kx], acc[o]);
+        }
+      }
+    }
+  }
+  uint4* dst = reinterpret_cast<uint4*>(out + (((size_t)f * Hh + y) * Wh + x) * 32);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a0 = acc[8 * q + 2 * j], a1 = acc[8 * q + 2 * j + 1];
+      o[j] = Pack2<T>::pack(fmaxf(a0, 0.2f * a0), fmaxf(a1, 0.2f * a1));
+    }
+    dst[q] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// 8-channel 16-bit features stored space-to-depth: pixel (Y, X) of frame plane `ft` ([Hh][Wh][4 x 8]) is one uint4
+template <typename T>
+__device__ __forceinline__ void load_feat8(const uint4* __restrict__ ft, int Wh, int Y, int X, float (&v)[8]) {
+  const uint4 q = __ldg(ft + ((size_t)((Y >> 1) * Wh + (X >> 1)) * 4 + ((Y & 1) * 2 + (X & 1))));
+  const float2 a = Pack2<T>::unpack(q.x), b = Pack2<T>::unpack(q.y), c = Pack2<T>::unpack(q.z), d = Pack2<T>::unpack(q.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+
+// grid_sample(bilinear, border, align_corners=True) of the 8-channel feature plane at (sx, sy)
+template <typename T>
+__device__ __forceinline__ void sample_border8(const uint4* __restrict__ ft, int Hp, int Wp, float sx, float sy,
+                                               float (&o)[8]) {
+  sx = fminf(fmaxf(sx, 0.f), (float)(Wp - 1));
+  sy = fminf(fmaxf(sy, 0.f), (float)(Hp - 1));
+  const float fx0 = floorf(sx), fy0 = floorf(sy);
+  const int x0 = (int)fx0, y0 = (int)fy0;
+  const int x1 = min(x0 + 1, Wp - 1), y1 = min(y0 + 1, Hp - 1);
+  const float ax = sx - fx0, ay = sy - fy0;
+  const float w00 = (1.f - ax) * (1.f - ay), w01 = ax * (1.f - ay), w10 = (1.f - ax) * ay, w11 = ax * ay;
+  float a[8], b[8], c[8], d[8];
+  load_feat8<T>(ft, Wp >> 1, y0, x0, a);
+  load_feat8<T>(ft, Wp >> 1, y0, x1, b);
+  load_feat8<T>(ft, Wp >> 1, y1, x0, c);
+  load_feat8<T>(ft, Wp >> 1, y1, x1, d);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = a[i] * w00 + b[i] * w01 + c[i] * w10 + d[i] * w11;
+}
+
+// arch 4.17 block input: [w0.rgb, w1.rgb, warp(f0) (8), warp(f1) (8), t, mask, flow/s (4)] = 28 of 32 channels
+// (block 0: [img0, img1, f0, f1, t] = 23), space-to-depth cell = 4 x 32 channels.  Same structure as front47_kernel;
+// the 2x2 centre taps are summed row by row in the reference's order ((a + b) + (c + d)) * 0.25.
+template <typename T, int NLEV>
+__global__ void front417_kernel(const float4* __restrict__ imgs, const uint4* __restrict__ feats,
+                                const FlowLevels lev, const BatchTasks tasks, int Hp, int Wp, int s,
+                                T* __restrict__ x_s2d) {
+  const int Hs = Hp / s, Ws = Wp / s;
+  const size_t plane = (size_t)Hp * Wp;
+  const size_t fplane = plane / 4 * 4;  // uint4 per pixel: (Hp/2)*(Wp/2) cells x 4
+  const float inv_s = 1.f / (float)s;
+  const int par = (int)(threadIdx.x & 1);
+  const int xl = (int)(blockIdx.x * (blockDim.x >> 1) + (threadIdx.x >> 1));
+  if (xl >= Ws) return;
+  const int yl = (int)blockIdx.y * 2 + par;
+  const int b = (int)blockIdx.z;
+  const float4* img0 = imgs + (size_t)tasks.f0[b] * plane;
+  const float4* img1 = imgs + (size_t)tasks.f1[b] * plane;
+  const uint4* ft0 = feats + (size_t)tasks.f0[b] * fplane;
+  const uint4* ft1 = feats + (size_t)tasks.f1[b] * fplane;
+  const float t = tasks.t[b];
+  const int ntap = (s == 1) ? 1 : 2;
+  const int by = (s == 1) ? yl : s * yl + s / 2 - 1;
+  const int bx = (s == 1) ? xl : s * xl + s / 2 - 1;
+  float ch[28];
+#pragma unroll
+  for (int ty = 0; ty < 2; ++ty) {
+    float row[28];
+#pragma unroll
+    for (int tx = 0; tx < 2; ++tx) {
+      if (ty < ntap && tx < ntap) {
+        const int Y = by + ty, X = bx + tx;
+        float v[28];
+        float4 a, c;
+        float fa[8], fc[8];
+        if (NLEV == 0) {
+          a = __ldg(img0 + (size_t)Y * Wp + X);
+          c = __ldg(img1 + (size_t)Y * Wp + X);
+          load_feat8<T>(ft0, Wp >> 1, Y, X, fa);
+          load_feat8<T>(ft1, Wp >> 1, Y, X, fc);
+          v[22] = t; v[23] = 0.f; v[24] = 0.f; v[25] = 0.f; v[26] = 0.f; v[27] = 0.f;
+        } else {
+          float4 f;
+          float m;
+          flow_at<(NLEV > 0 ? NLEV : 1)>(lev, b, Hp, Wp, Y, X, f, m);
+          a = sample_border(img0, Hp, Wp, (float)X + f.x, (float)Y + f.y);
+          c = sample_border(img1, Hp, Wp, (float)X + f.z, (float)Y + f.w);
+          sample_border8<T>(ft0, Hp, Wp, (float)X + f.x, (float)Y + f.y, fa);
+          sample_border8<T>(ft1, Hp, Wp, (float)X + f.z, (float)Y + f.w, fc);
+          v[22] = t; v[23] = m; v[24] = f.x; v[25] = f.y; v[26] = f.z; v[27] = f.w;
+        }
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = c.x; v[4] = c.y; v[5] = c.z;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          v[6 + i] = fa[i];
+          v[14 + i] = fc[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 28; ++i) row[i] = (tx == 0) ? v[i] : row[i] + v[i];
+      }
+    }
+    if (ty < ntap) {
+#pragma unroll
+      for (int i = 0; i < 28; ++i) ch[i] = (ty == 0) ? row[i] : ch[i] + row[i];
+    }
+  }
+  if (ntap == 2) {
+#pragma unroll
+    for (int i = 0; i < 28; ++i) ch[i] *= 0.25f;
+  }
+#pragma unroll
+  for (int i = 24; i < 28; ++i) ch[i] *= inv_s;  // flow is also divided by the scale (rife_arch.py:242-248)
+  const size_t cell = ((size_t)b * (Hs >> 1) + (yl >> 1)) * (Ws >> 1) + (xl >> 1);
+  T* dst = x_s2d + cell * 128 + ((yl & 1) * 2 + (xl & 1)) * 32;
+  uint4 q[4];
+  q[0] = make_uint4(Pack2<T>::pack(ch[0], ch[1]), Pack2<T>::pack(ch[2], ch[3]), Pack2<T>::pack(ch[4], ch[5]),
+                    Pack2<T>::pack(ch[6], ch[7]));
+  q[1] = make_uint4(Pack2<T>::pack(ch[8], ch[9]), Pack2<T>::pack(ch[10], ch[11]), Pack2<T>::pack(ch[12], ch[13]),
+                    Pack2<T>::pack(ch[14], ch[15]));
+  q[2] = make_uint4(Pack2<T>::pack(ch[16], ch[17]), Pack2<T>::pack(ch[18], ch[19]), Pack2<T>::pack(ch[20], ch[21]),
+                    Pack2<T>::pack(ch[22], ch[23]));
+  q[3] = make_uint4(Pack2<T>::pack(ch[24], ch[25]), Pack2<T>::pack(ch[26], ch[27]), 0u, 0u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(dst)[i] = q[i];
+}
+
 // debug / tests only: materialise the accumulated full-resolution flow and mask
 template <int NLEV>
 __global__ void materialize_kernel(const FlowLevels lev, float4* __restrict__ flow, float* __restrict__ mask, int B,
@@ -739,6 +904,27 @@ static void launch_front_t(int nlev, bool shared_taps, dim3 g, cudaStream_t st, 
   }
 }
 
+template <typename T>
+static void launch_front417_t(int nlev, dim3 g, cudaStream_t st, const float4* imgs, const uint4* feats,
+                              const FlowLevels& L, const BatchTasks& tasks, int Hp, int Wp, int s, void* x) {
+  switch (nlev) {
+    case 0: front417_kernel<T, 0><<<g, 128, 0, st>>>(imgs, feats, L, tasks, Hp, Wp, s, (T*)x); break;
+    case 1: front417_kernel<T, 1><<<g, 128, 0, st>>>(imgs, feats, L, tasks, Hp, Wp, s, (T*)x); break;
+    case 2: front417_kernel<T, 2><<<g, 128, 0, st>>>(imgs, feats, L, tasks, Hp, Wp, s, (T*)x); break;
+    default: front417_kernel<T, 3><<<g, 128, 0, st>>>(imgs, feats, L, tasks, Hp, Wp, s, (T*)x); break;
+  }
+}
+
+cudaError_t launch_head0(int op_type, const float4* imgs, const float* w, const float* bias, void* out, int n, int Hp,
+                         int Wp, cudaStream_t st) {
+  const dim3 g((unsigned)((Wp / 2 + 127) / 128), (unsigned)(Hp / 2), (unsigned)n);
+  if (op_type == OP_BF16)
+    head0_kernel<__nv_bfloat16><<<g, 128, 0, st>>>(imgs, w, bias, (__nv_bfloat16*)out, n, Hp, Wp);
+  else
+    head0_kernel<__half><<<g, 128, 0, st>>>(imgs, w, bias, (__half*)out, n, Hp, Wp);
+  return cudaGetLastError();
+}
+
 // block `blk` input: flow = base (if any) + levels [lo, blk); stores the accumulated flow when `store` planes given
 cudaError_t launch_encode(const float4* imgs, const float* w0, const float* b0, const float* w1, const float* b1,
                           float* e16, float4* feats, int n, int Hp, int Wp, cudaStream_t st) {
@@ -750,18 +936,25 @@ cudaError_t launch_encode(const float4* imgs, const float* w0, const float* b0, 
   return cudaGetLastError();
 }
 
-cudaError_t launch_front(int op_type, const float4* imgs, const uint2* imgs_h, const float4* feats, const FlowState& fs,
-                         int blk, int lo, const float4* base_f, const float* base_m, float4* out_f, float* out_m, BatchTasks tasks,
+cudaError_t launch_front(int op_type, const float4* imgs, const uint2* imgs_h, const void* feats, int feat_ch,
+                         const FlowState& fs, int blk, int lo, const float4* base_f, const float* base_m, float4* out_f, float* out_m, BatchTasks tasks,
                          int Hp, int Wp, int s, void* x_s2d, cudaStream_t st) {
   const dim3 g((unsigned)((Wp / s + 63) / 64), (unsigned)(Hp / s / 2), (unsigned)tasks.n);  // 64 cells x 2 rows per block
   const FlowLevels L = make_levels(fs, lo, blk, base_f, base_m, out_f, out_m, Hp, Wp);
   const int nlev = (blk == 0) ? 0 : (blk - lo);
   if (blk > 0 && nlev == 0 && base_f == nullptr) return cudaErrorInvalidValue;
-  if (feats != nullptr) {  // arch 4.7
+  if (feats != nullptr && feat_ch == 4) {  // arch 4.7
     if (op_type == OP_BF16)
-      launch_front47_t<__nv_bfloat16>(blk == 0 ? 0 : nlev, g, st, imgs, feats, L, tasks, Hp, Wp, s, x_s2d);
+      launch_front47_t<__nv_bfloat16>(blk == 0 ? 0 : nlev, g, st, imgs, (const float4*)feats, L, tasks, Hp, Wp, s, x_s2d);
     else
-      launch_front47_t<__half>(blk == 0 ? 0 : nlev, g, st, imgs, feats, L, tasks, Hp, Wp, s, x_s2d);
+      launch_front47_t<__half>(blk == 0 ? 0 : nlev, g, st, imgs, (const float4*)feats, L, tasks, Hp, Wp, s, x_s2d);
+    return cudaGetLastError();
+  }
+  if (feats != nullptr) {  // arch 4.17: 8 feature channels, 16-bit, space-to-depth
+    if (op_type == OP_BF16)
+      launch_front417_t<__nv_bfloat16>(blk == 0 ? 0 : nlev, g, st, imgs, (const uint4*)feats, L, tasks, Hp, Wp, s, x_s2d);
+    else
+      launch_front417_t<__half>(blk == 0 ? 0 : nlev, g, st, imgs, (const uint4*)feats, L, tasks, Hp, Wp, s, x_s2d);
     return cudaGetLastError();
   }
   // scale-2 front without a base plane whose levels are all at scale 4, 8, ...: the level taps are shared per cell

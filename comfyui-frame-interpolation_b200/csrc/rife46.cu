@@ -33,6 +33,7 @@ namespace {
 const int kBlockC[4] = {192, 128, 96, 64};
 const int kBlockCinReal[4] = {7, 12, 12, 12};        // arch 4.6: img0,img1,t | w0,w1,t,mask + flow
 const int kBlockCinReal47[4] = {15, 20, 20, 20};     // arch 4.7: + encoded features f0,f1 (4 ch each)
+const int kBlockCinReal417[4] = {23, 28, 28, 28};    // arch 4.17: + Head_417 features f0,f1 (8 ch each)
 
 uint16_t to_operand(float v, int op_type) {
   if (op_type == OP_BF16) {
@@ -132,6 +133,8 @@ struct vfi_ctx {
   int arch = 46;                 // 46 | 47 (rife47.pth / rife49.pth)
   DevBuf feats, e16;             // arch 4.7: encoded features per source frame (float4), half-res temp
   float* enc[4] = {nullptr, nullptr, nullptr, nullptr};  // encode.0.weight/.bias, encode.1.weight/.bias (fp32)
+  TapConvLayer head[3];          // arch 4.17: Head_417 cnn1, cnn2 (32->32 + LeakyReLU), cnn3 (ConvTranspose 32->8)
+  DevBuf hA, hB;                 // arch 4.17: half-resolution 32-channel scratch of the head (ping-pong)
   int ws_Hp = 0, ws_Wp = 0, ws_B = 0;
   FlowState last_fs{};
   int last_lo = 0;
@@ -304,6 +307,53 @@ int build_lastconv(vfi_ctx* c, TapConvLayer& L, int ch, const float* wt, const f
   return VFI_OK;
 }
 
+// Head_417.cnn1 / cnn2: plain 3x3 conv + LeakyReLU on a 32-channel half-resolution tensor (one 32-channel k-block)
+int build_conv3x3_lrelu(vfi_ctx* c, TapConvLayer& L, int ch, const float* w, const float* bias) {
+  L = TapConvLayer{};
+  L.cin = ch;
+  L.n_total = ch;
+  L.ktotal16 = 9 * (ch / 16);
+  L.halo_y0 = -1; L.halo_x0 = -1; L.halo_h = kTileH + 2; L.halo_w = kTileW + 2;
+  L.epi_mode = EPI_BIAS_LRELU;
+  set_taps_3x3(L, ch, false);
+  choose_split(L, {1}, 2);
+  auto wf = [&](int e, int ci, int n) -> float { return w[(((size_t)n * ch + ci) * 3 + e / 3) * 3 + e % 3]; };
+  std::vector<uint16_t> pk = pack_weights(L, c->op_type, wf);
+  std::vector<float> sh(bias, bias + ch);
+  int r;
+  if ((r = upload(c, pk, &L.w))) return r;
+  if ((r = upload(c, sh, (void**)&L.shift))) return r;
+  return VFI_OK;
+}
+
+// Head_417.cnn3 = ConvTranspose2d(ch, cout, 4, 2, 1), no activation, as ONE 3x3 conv producing the 2x2 sub-pixels of
+// every input cell: n = (a*2 + b)*cout + oc at output position (2y+a, 2x+b); tap (dy,dx) uses transposed-kernel element
+// ky = a+1-2dy, kx = b+1-2dx.  The NHWC output [Hh][Wh][4*cout] IS the space-to-depth form of the feature map.
+int build_deconv_s2d(vfi_ctx* c, TapConvLayer& L, int ch, int cout, const float* wt, const float* bias) {
+  L = TapConvLayer{};
+  L.cin = ch;
+  L.n_total = 4 * cout;
+  L.ktotal16 = 9 * (ch / 16);
+  L.halo_y0 = -1; L.halo_x0 = -1; L.halo_h = kTileH + 2; L.halo_w = kTileW + 2;
+  L.epi_mode = EPI_BIAS;
+  set_taps_3x3(L, ch, false);
+  choose_split(L, {1}, 2);
+  auto wf = [&](int e, int ci, int n) -> float {
+    const int dy = e / 3 - 1, dx = e % 3 - 1;
+    const int sub = n / cout, oc = n % cout, a = sub >> 1, b = sub & 1;
+    const int ky = a + 1 - 2 * dy, kx = b + 1 - 2 * dx;
+    if (ky < 0 || ky > 3 || kx < 0 || kx > 3) return 0.f;
+    return wt[(((size_t)ci * cout + oc) * 4 + ky) * 4 + kx];
+  };
+  std::vector<uint16_t> pk = pack_weights(L, c->op_type, wf);
+  std::vector<float> sh(4 * cout);
+  for (int n = 0; n < 4 * cout; ++n) sh[n] = bias[n % cout];
+  int r;
+  if ((r = upload(c, pk, &L.w))) return r;
+  if ((r = upload(c, sh, (void**)&L.shift))) return r;
+  return VFI_OK;
+}
+
 struct Geometry {
   int Hp, Wp;
   int s[4];
@@ -331,7 +381,7 @@ int ensure_workspace(vfi_ctx* c, const Geometry& g, int B, int n_frames_window) 
   size_t x = 0, c00 = 0, feat = 0;
   for (int i = 0; i < 4; ++i) {
     const size_t Hs = g.Hp / g.s[i], Ws = g.Wp / g.s[i];
-    x = std::max(x, (size_t)B * (Hs / 2) * (Ws / 2) * (c->arch == 47 ? 128 : 64) * 2);
+    x = std::max(x, (size_t)B * (Hs / 2) * (Ws / 2) * (c->arch != 46 ? 128 : 64) * 2);
     c00 = std::max(c00, (size_t)B * (Hs / 4) * (Ws / 4) * 2 * kBlockC[i] * 2);
     feat = std::max(feat, (size_t)B * (Hs / 4) * (Ws / 4) * kBlockC[i] * 2);
     CK(c->tF[i].ensure((size_t)B * Hs * Ws * sizeof(float4)));  // block output T_i (flow increments at 1/s_i)
@@ -343,6 +393,11 @@ int ensure_workspace(vfi_ctx* c, const Geometry& g, int B, int n_frames_window) 
   if (c->arch == 47) {
     CK(c->feats.ensure((size_t)n_frames_window * px * sizeof(float4)));
     CK(c->e16.ensure((size_t)(kMaxBatch + 2) * (px / 4) * 16 * sizeof(float)));
+  }
+  if (c->arch == 417) {  // features: 8 x 16-bit per pixel (space-to-depth cells of 32); head scratch: 32 ch at 1/2 res
+    CK(c->feats.ensure((size_t)n_frames_window * px * 16));
+    CK(c->hA.ensure((size_t)(kMaxBatch + 2) * (px / 4) * 32 * 2));
+    CK(c->hB.ensure((size_t)(kMaxBatch + 2) * (px / 4) * 32 * 2));
   }
   CK(c->flow.ensure((size_t)B * px * sizeof(float4)));
   CK(c->mask.ensure((size_t)B * px * sizeof(float)));
@@ -365,12 +420,31 @@ int ensure_workspace(vfi_ctx* c, const Geometry& g, int B, int n_frames_window) 
     }                                                              \
   } while (0)
 
+// encode head of arch 4.7 / 4.17 for frames [f, f + n) of the prepared window (n <= kMaxBatch + 2), once per source frame
+int run_encode(vfi_ctx* c, const Geometry& g, int f, int n, cudaStream_t st) {
+  const size_t px = (size_t)g.Hp * g.Wp;
+  const float4* imgs = (const float4*)c->imgs.p + (size_t)f * px;
+  if (c->arch == 47) {
+    LAUNCH(launch_encode(imgs, c->enc[0], c->enc[1], c->enc[2], c->enc[3], (float*)c->e16.p,
+                         (float4*)c->feats.p + (size_t)f * px, n, g.Hp, g.Wp, st));
+  } else if (c->arch == 417) {
+    const int Hh = g.Hp / 2, Wh = g.Wp / 2;
+    LAUNCH(launch_head0(c->op_type, imgs, c->enc[0], c->enc[1], c->hA.p, n, g.Hp, g.Wp, st));
+    LAUNCH(launch_tapconv(c->head[0], c->op_type, c->hA.p, c->hB.p, nullptr, nullptr, n, Hh, Wh, c->num_sms, false, st));
+    LAUNCH(launch_tapconv(c->head[1], c->op_type, c->hB.p, c->hA.p, nullptr, nullptr, n, Hh, Wh, c->num_sms, false, st));
+    LAUNCH(launch_tapconv(c->head[2], c->op_type, c->hA.p, (uint8_t*)c->feats.p + (size_t)f * px * 16, nullptr, nullptr,
+                          n, Hh, Wh, c->num_sms, false, st));
+  }
+  return VFI_OK;
+}
+
 // one internal pass: tasks (indices into the prepared frame window c->imgs) -> out [n, H, W, 3]
 int forward_pass(vfi_ctx* c, const Geometry& g, const BatchTasks& tasks, int H, int W, float* out, cudaStream_t st) {
   const int B = tasks.n;
   const float4* imgs = (const float4*)c->imgs.p;
   const uint2* imgs_h = (const uint2*)c->imgs_h.p;
-  const float4* feats = c->arch == 47 ? (const float4*)c->feats.p : nullptr;
+  const void* feats = c->arch != 46 ? c->feats.p : nullptr;
+  const int feat_ch = c->arch == 417 ? 8 : 4;
   float4* F = (float4*)c->flow.p;  // accumulated full-resolution flow / mask, written only by "dense" fronts
   float* M = (float*)c->mask.p;
   FlowState fs{};
@@ -379,7 +453,7 @@ int forward_pass(vfi_ctx* c, const Geometry& g, const BatchTasks& tasks, int H, 
     fs.m[i] = (float*)c->tM[i].p;
     fs.s[i] = g.s[i];
   }
-  fs.mask_replace = (c->arch == 47) ? 1 : 0;
+  fs.mask_replace = (c->arch != 46) ? 1 : 0;
   int dense = 4;  // first block whose front visits every full-resolution pixel (scale <= 2)
   for (int i = 3; i >= 1; --i)
     if (g.s[i] <= 2) dense = i;
@@ -389,10 +463,10 @@ int forward_pass(vfi_ctx* c, const Geometry& g, const BatchTasks& tasks, int H, 
     const int s = g.s[i];
     const int Hs = g.Hp / s, Ws = g.Wp / s;
     if (i == 0 || i < dense) {
-      LAUNCH(launch_front(c->op_type, imgs, imgs_h, feats, fs, i, 0, nullptr, nullptr, nullptr, nullptr, tasks, g.Hp, g.Wp, s,
+      LAUNCH(launch_front(c->op_type, imgs, imgs_h, feats, feat_ch, fs, i, 0, nullptr, nullptr, nullptr, nullptr, tasks, g.Hp, g.Wp, s,
                           c->x.p, st));
     } else {
-      LAUNCH(launch_front(c->op_type, imgs, imgs_h, feats, fs, i, lo, have_base ? F : nullptr, have_base ? M : nullptr, F, M, tasks,
+      LAUNCH(launch_front(c->op_type, imgs, imgs_h, feats, feat_ch, fs, i, lo, have_base ? F : nullptr, have_base ? M : nullptr, F, M, tasks,
                           g.Hp, g.Wp, s, c->x.p, st));
       have_base = true;
       lo = i;
@@ -433,7 +507,7 @@ int check_tasks(const int32_t* f0, const int32_t* f1, int n_tasks, int lo, int h
 extern "C" {
 
 const char* vfi_last_error(void) { return g_err.c_str(); }
-const char* vfi_version(void) { return "vfi_b200 0.1 (sm_100a; RIFE 4.6/4.7; built " __DATE__ " " __TIME__ ")"; }
+const char* vfi_version(void) { return "vfi_b200 0.1 (sm_100a; RIFE 4.6/4.7/4.17; built " __DATE__ " " __TIME__ ")"; }
 
 int vfi_create(int device, vfi_ctx** out) {
   if (!out) return fail(VFI_E_INVALID, "null out");
@@ -459,7 +533,7 @@ int vfi_destroy(vfi_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   free_weights(c);
-  for (DevBuf* b : {&c->imgs, &c->imgs_h, &c->flow, &c->mask, &c->x, &c->c00, &c->featA, &c->featB, &c->raw, &c->outdev, &c->feats, &c->e16, &c->dbgF,
+  for (DevBuf* b : {&c->imgs, &c->imgs_h, &c->flow, &c->mask, &c->x, &c->c00, &c->featA, &c->featB, &c->raw, &c->outdev, &c->feats, &c->e16, &c->hA, &c->hB, &c->dbgF,
                     &c->dbgM})
     b->release();
   for (int i = 0; i < 4; ++i) {
@@ -494,9 +568,10 @@ int vfi_rife46_load(vfi_ctx* c, const float* const* T, const int64_t* numel, int
 
 int vfi_rife_load(vfi_ctx* c, int arch, const float* const* T, const int64_t* numel, int n_tensors, int operand_type) {
   if (!c || !T || !numel) return fail(VFI_E_INVALID, "null argument");
-  if (arch != 46 && arch != 47) return fail(VFI_E_NOTIMPL, "RIFE arch must be 46 (rife46.pth) or 47 (rife47/rife49.pth)");
-  if (n_tensors != (arch == 46 ? VFI_RIFE46_NUM_TENSORS : VFI_RIFE47_NUM_TENSORS))
-    return fail(VFI_E_INVALID, "wrong number of state_dict tensors for this RIFE arch (4.6: 120, 4.7: 124)");
+  if (arch != 46 && arch != 47 && arch != 417)
+    return fail(VFI_E_NOTIMPL, "RIFE arch must be 46 (rife46.pth), 47 (rife47/rife49.pth) or 417 (rife417.pth)");
+  if (n_tensors != (arch == 46 ? VFI_RIFE46_NUM_TENSORS : arch == 47 ? VFI_RIFE47_NUM_TENSORS : VFI_RIFE417_NUM_TENSORS))
+    return fail(VFI_E_INVALID, "wrong number of state_dict tensors for this RIFE arch (4.6: 120, 4.7: 124, 4.17: 128)");
   if (operand_type != OP_F16 && operand_type != OP_BF16) return fail(VFI_E_INVALID, "operand_type");
   CK(cudaSetDevice(c->device));
   free_weights(c);
@@ -505,12 +580,12 @@ int vfi_rife_load(vfi_ctx* c, int arch, const float* const* T, const int64_t* nu
   int k = 0;
   auto expect = [&](int idx, int64_t want) { return numel[idx] == want; };
   for (int b = 0; b < 4; ++b) {
-    const int ch = kBlockC[b], cin = (arch == 47 ? kBlockCinReal47 : kBlockCinReal)[b];
+    const int ch = kBlockC[b], cin = (arch == 417 ? kBlockCinReal417 : arch == 47 ? kBlockCinReal47 : kBlockCinReal)[b];
     if (!expect(k, (int64_t)(ch / 2) * cin * 9) || !expect(k + 1, ch / 2) || !expect(k + 2, (int64_t)ch * (ch / 2) * 9) ||
         !expect(k + 3, ch))
       return fail(VFI_E_INVALID, "conv0 tensor sizes do not match RIFE 4.6");
     int r;
-    if ((r = build_conv_s2(c, c->layers[b][0], arch == 47 ? 32 : 16, cin, ch / 2, 1, T[k], T[k + 1]))) return r;
+    if ((r = build_conv_s2(c, c->layers[b][0], arch != 46 ? 32 : 16, cin, ch / 2, 1, T[k], T[k + 1]))) return r;
     if ((r = build_conv_s2(c, c->layers[b][1], ch / 2, ch / 2, ch, 0, T[k + 2], T[k + 3]))) return r;
     k += 4;
     for (int j = 0; j < 8; ++j) {
@@ -533,6 +608,22 @@ int vfi_rife_load(vfi_ctx* c, int arch, const float* const* T, const int64_t* nu
       if ((r = upload(c, h, (void**)&c->enc[i]))) return r;
     }
     k += 4;
+  }
+  if (arch == 417) {  // encode = Head_417: cnn0 on the CUDA cores (fp32 weights), cnn1..cnn3 as tapconv layers
+    const int64_t want[8] = {32 * 3 * 9, 32, 32 * 32 * 9, 32, 32 * 32 * 9, 32, 32 * 8 * 16, 8};
+    for (int i = 0; i < 8; ++i)
+      if (numel[k + i] != want[i]) return fail(VFI_E_INVALID, "encode tensor sizes do not match RIFE 4.17");
+    int r;
+    for (int i = 0; i < 2; ++i) {
+      std::vector<float> h(T[k + i], T[k + i] + want[i]);
+      if ((r = upload(c, h, (void**)&c->enc[i]))) return r;
+    }
+    if ((r = build_conv3x3_lrelu(c, c->head[0], 32, T[k + 2], T[k + 3]))) return r;
+    if ((r = build_conv3x3_lrelu(c, c->head[1], 32, T[k + 4], T[k + 5]))) return r;
+    if ((r = build_deconv_s2d(c, c->head[2], 32, 8, T[k + 6], T[k + 7]))) return r;
+    for (int i = 0; i < 3; ++i)
+      if (c->head[i].nsplit < 1) return fail(VFI_E_STATE, "a head layer has no shared-memory plan");
+    k += 8;
   }
   for (int b = 0; b < 4; ++b)
     for (int l = 0; l < 11; ++l)
@@ -562,12 +653,10 @@ int vfi_rife46_forward(vfi_ctx* c, const float* frames, int n_frames, int H, int
   cudaStream_t st = (cudaStream_t)stream;
   LAUNCH(launch_prep_frames(frames + (size_t)lo * H * W * C, hi - lo, H, W, C, (float4*)c->imgs.p, (uint2*)c->imgs_h.p,
                             g.Hp, g.Wp, st));
-  if (c->arch == 47) {  // encode head, once per source frame, in groups that fit the half-resolution scratch
-    const size_t px = (size_t)g.Hp * g.Wp;
+  if (c->arch != 46) {  // encode head, once per source frame, in groups that fit the half-resolution scratch
     for (int f = 0; f < hi - lo; f += kMaxBatch) {
       const int cnt = std::min(kMaxBatch, hi - lo - f);
-      LAUNCH(launch_encode((const float4*)c->imgs.p + (size_t)f * px, c->enc[0], c->enc[1], c->enc[2], c->enc[3],
-                           (float*)c->e16.p, (float4*)c->feats.p + (size_t)f * px, cnt, g.Hp, g.Wp, st));
+      if ((r = run_encode(c, g, f, cnt, st))) return r;
     }
   }
   for (int pos = 0; pos < n_tasks; pos += B) {
@@ -654,10 +743,10 @@ int vfi_rife46_interpolate_host(vfi_ctx* c, const float* frames, int n_frames, i
                            cudaMemcpyHostToDevice, c->s_h2d));
         LAUNCH(launch_prep_frames(rawp, run, H, W, C, imgp,
                                   (uint2*)c->imgs_h.p + (size_t)(uploaded - frame_lo) * g.Hp * g.Wp, g.Hp, g.Wp, c->s_h2d));
-        if (c->arch == 47)
-          LAUNCH(launch_encode(imgp, c->enc[0], c->enc[1], c->enc[2], c->enc[3], (float*)c->e16.p,
-                               (float4*)c->feats.p + (size_t)(uploaded - frame_lo) * g.Hp * g.Wp, run, g.Hp, g.Wp,
-                               c->s_h2d));
+        if (c->arch != 46) {
+          const int r3 = run_encode(c, g, uploaded - frame_lo, run, c->s_h2d);
+          if (r3) return r3;
+        }
         uploaded += run;
       }
       CK(cudaEventRecord(ev_up[k], c->s_h2d));

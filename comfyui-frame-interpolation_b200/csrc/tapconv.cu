@@ -335,6 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
     const int n0 = split * p.n_cta;
     const uint32_t center_px = (uint32_t)((py - p.halo_y0) * p.halo_w + (px - p.halo_x0));
     const int nchunks = p.n_cta >> 4;  // 16-column chunks of this CTA's accumulator (<= 6)
+    const float slope = (p.epi_mode == EPI_BIAS) ? 1.f : 0.2f;  // max(a, slope * a): LeakyReLU(0.2), or no activation
 
     // this group's tiles: k = acc, acc + 4, ... (k counts the CTA's tiles); window stage of tile k = k % S, carried
     // incrementally together with its use count (parity of the "full" barrier)
@@ -451,7 +452,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
             a0 += rf.x;
             a1 += rf.y;
           }
-          o[j] = Pack2<T>::pack(fmaxf(a0, 0.2f * a0), fmaxf(a1, 0.2f * a1));  // LeakyReLU(0.2)
+          o[j] = Pack2<T>::pack(fmaxf(a0, slope * a0), fmaxf(a1, slope * a1));  // LeakyReLU(0.2) / identity
         }
         // 32 contiguous bytes (16 channels) of this cell's channel vector; L2 merges the halves of a sector
         if (valid && (!ABLATE(1) || o[0] == 0x12345678u)) {
@@ -562,7 +563,8 @@ __global__ void tapconv_ref_kernel(const __grid_constant__ TapConvParams p) {
     } else {
       float v = acc + p.shift[n];
       if (p.epi_mode == EPI_RESCONV) v += ld16bit<T>(in + (((size_t)b * p.H + gy) * p.W + gx) * p.cin + n);
-      reinterpret_cast<T*>(p.out)[out_pixel_offset(p, b, gy, gx) + n] = cvt16bit<T>(lrelu02(v));
+      reinterpret_cast<T*>(p.out)[out_pixel_offset(p, b, gy, gx) + n] =
+          cvt16bit<T>(p.epi_mode == EPI_BIAS ? v : lrelu02(v));
     }
   }
 }
@@ -758,11 +760,12 @@ cudaError_t launch_tapconv(const TapConvLayer& L, int op_type, const void* in, v
   }
 
   const CUtensorMapDataType dt = (op_type == OP_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  if (!make_tmap(&p.tm64, dt, in, L.cin, W, H, B, 64, L.halo_w, L.halo_h, CU_TENSOR_MAP_SWIZZLE_128B))
+  if (L.cin >= 64 && !make_tmap(&p.tm64, dt, in, L.cin, W, H, B, 64, L.halo_w, L.halo_h, CU_TENSOR_MAP_SWIZZLE_128B))
     return cudaErrorInvalidValue;
   if (L.cin & 63) {
     if (!make_tmap(&p.tm32, dt, in, L.cin, W, H, B, 32, L.halo_w, L.halo_h, CU_TENSOR_MAP_SWIZZLE_64B))
       return cudaErrorInvalidValue;
+    if (L.cin < 64) p.tm64 = p.tm32;  // a single 32-channel k-block: the 64-channel map is never used
   } else {
     p.tm32 = p.tm64;
   }

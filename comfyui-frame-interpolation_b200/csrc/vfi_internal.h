@@ -19,6 +19,7 @@ enum EpiMode : int {
   EPI_BIAS_LRELU = 0,  // out = lrelu(acc + shift)                               (conv0.0, conv0.1)
   EPI_RESCONV = 1,     // out = lrelu(acc + shift + in[b,y,x,n])                 (ResConv; beta folded into W, shift=bias*beta)
   EPI_LASTCONV = 2,    // out5[b, 4y+py, 4x+px] = acc + shift, n = c5*16 + py*4+px (ConvT(4,2,1)+PixelShuffle(2))
+  EPI_BIAS = 3,        // out = acc + shift, no activation                        (Head_417.cnn3)
 };
 
 struct TapEntry {
@@ -112,8 +113,11 @@ struct FlowState {
 };
 cudaError_t launch_encode(const float4* imgs, const float* w0, const float* b0, const float* w1, const float* b1,
                           float* e16, float4* feats, int n, int Hp, int Wp, cudaStream_t st);
-cudaError_t launch_front(int op_type, const float4* imgs, const uint2* imgs_h, const float4* feats, const FlowState& fs,
-                         int blk, int lo,
+cudaError_t launch_head0(int op_type, const float4* imgs, const float* w, const float* bias, void* out, int n, int Hp,
+                         int Wp, cudaStream_t st);
+// feats: arch 4.7 float4 planes (feat_ch 4), arch 4.17 16-bit space-to-depth planes (feat_ch 8), or nullptr (4.6)
+cudaError_t launch_front(int op_type, const float4* imgs, const uint2* imgs_h, const void* feats, int feat_ch,
+                         const FlowState& fs, int blk, int lo,
                          const float4* base_f, const float* base_m, float4* out_f, float* out_m, BatchTasks tasks,
                          int Hp, int Wp, int s, void* x_s2d, cudaStream_t st);
 cudaError_t launch_materialize(const FlowState& fs, int lo, const float4* base_f, const float* base_m, float4* flow,

@@ -26,7 +26,12 @@ def state_dict_names(arch: str = "4.6"):
         names += [p + "lastconv.0.weight", p + "lastconv.0.bias"]
     if arch == "4.7":
         names += ["encode.0.weight", "encode.0.bias", "encode.1.weight", "encode.1.bias"]
+    if arch == "4.17":  # Head_417 - rife_arch.py:356-363
+        names += [f"encode.cnn{i}.{k}" for i in range(4) for k in ("weight", "bias")]
     return names
+
+
+ARCH_CODE = {"4.6": 46, "4.7": 47, "4.17": 417}
 
 
 def _i32(a):
@@ -34,7 +39,7 @@ def _i32(a):
 
 
 class Rife46Engine:
-    """RIFE 4.6 / 4.7 (rife46.pth; rife47.pth, rife49.pth) on one B200.  `state_dict` maps the reference's parameter names to tensors (any float dtype)."""
+    """RIFE 4.6 / 4.7 / 4.17 (rife46.pth; rife47.pth, rife49.pth; rife417.pth) on one B200.  `state_dict` maps the reference's parameter names to tensors (any float dtype)."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], device: int = 0, dtype: str = "float32", batch: int = 8,
                  arch: str = None):
@@ -46,10 +51,11 @@ class Rife46Engine:
         self.device = int(device)
         self._ctx = C.c_void_p()
         check(self._L.vfi_create(self.device, C.byref(self._ctx)))
-        if arch is None:  # the 4.7 family (rife47.pth / rife49.pth) has the encode head
-            arch = "4.7" if "encode.0.weight" in state_dict else "4.6"
-        if arch not in ("4.6", "4.7"):
-            raise VfiError(f"RIFE arch {arch} is not built (4.6 and 4.7 are)")
+        if arch is None:  # the 4.7 family (rife47.pth / rife49.pth) has the encode head, rife417.pth the Head_417 one
+            arch = ("4.17" if "encode.cnn0.weight" in state_dict else
+                    "4.7" if "encode.0.weight" in state_dict else "4.6")
+        if arch not in ARCH_CODE:
+            raise VfiError(f"RIFE arch {arch} is not built (4.6, 4.7 and 4.17 are)")
         self.arch = arch
         names = state_dict_names(arch)
         missing = [n for n in names if n not in state_dict]
@@ -58,7 +64,7 @@ class Rife46Engine:
         hold = [state_dict[n].detach().to("cpu", torch.float32).contiguous() for n in names]
         ptrs = (C.c_void_p * len(hold))(*[t.data_ptr() for t in hold])
         numel = (C.c_int64 * len(hold))(*[t.numel() for t in hold])
-        check(self._L.vfi_rife_load(self._ctx, 46 if arch == "4.6" else 47, ptrs, numel, len(hold), OPERAND[dtype]))
+        check(self._L.vfi_rife_load(self._ctx, ARCH_CODE[arch], ptrs, numel, len(hold), OPERAND[dtype]))
         check(self._L.vfi_set_batch(self._ctx, int(batch)))
         self.dtype = dtype
 

@@ -22,6 +22,7 @@ CKPT_NAME_VER_DICT = {
     "rife46.pth": "4.6",
     "rife47.pth": "4.7",
     "rife49.pth": "4.7",
+    "rife417.pth": "4.17",
 }
 DTYPE_OPTIONS = ["float32", "float16", "bfloat16"]
 DTYPE_MAP = {"float32": torch.float32, "float16": torch.float16, "bfloat16": torch.bfloat16}

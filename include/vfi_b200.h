@@ -32,6 +32,7 @@ extern "C" {
 
 #define VFI_RIFE46_NUM_TENSORS 120   /* IFNet("4.6").state_dict() - rife_arch.py:404-408 */
 #define VFI_RIFE47_NUM_TENSORS 124   /* IFNet("4.7"): + encode.{0,1}.{weight,bias} - rife_arch.py:409-417 */
+#define VFI_RIFE417_NUM_TENSORS 128  /* + encode.cnn0..cnn3 weight, bias (Head_417, rife_arch.py:356-363) */
 #define VFI_MAX_BATCH 16
 
 typedef struct vfi_ctx vfi_ctx;
@@ -53,7 +54,8 @@ int vfi_set_batch(vfi_ctx* ctx, int batch);
  * .bias, 8 x convblock.{j}.{beta, conv.weight, conv.bias}, lastconv.0.weight, .bias; b = 0..3); `numel[i]` is
  * checked against the architecture.  Weights are repacked to the tensor-core operand layout on the device. */
 int vfi_rife46_load(vfi_ctx* ctx, const float* const* tensors, const int64_t* numel, int n_tensors, int operand_type);
-/* Same for any built arch: 46 (rife46.pth) or 47 (rife47.pth / rife49.pth, CKPT_NAME_VER_DICT rife/__init__.py:10-12;
+/* Same for any built arch: 46 (rife46.pth), 47 (rife47.pth / rife49.pth) or 417 (rife417.pth; CKPT_NAME_VER_DICT
+ * rife/__init__.py:10-13;
  * state_dict order = blocks 0..3 then encode.0.weight, encode.0.bias, encode.1.weight, encode.1.bias).  The
  * vfi_rife46_forward / _interpolate_host entry points below run whichever arch was loaded. */
 int vfi_rife_load(vfi_ctx* ctx, int arch, const float* const* tensors, const int64_t* numel, int n_tensors,

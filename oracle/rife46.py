@@ -33,17 +33,20 @@ LRELU_SLOPE = 0.2  # rife_arch.py:106 / :26
 # arch 4.7 (checkpoints rife47.pth / rife49.pth, rife/__init__.py:10-12): same IFBlocks with 8 (block 0) / 8 more input
 # channels for the encoded features of both frames, plus the `encode` head -- rife_arch.py:409-417
 BLOCK_SPECS_47: Tuple[Tuple[int, int], ...] = ((7 + 8, 192), (8 + 4 + 8, 128), (8 + 4 + 8, 96), (8 + 4 + 8, 64))
+# arch 4.17 (rife417.pth): + Head_417 features, 8 channels per frame -- rife_arch.py:417-421, :356-375
+BLOCK_SPECS_417: Tuple[Tuple[int, int], ...] = ((7 + 16, 192), (8 + 4 + 16, 128), (8 + 4 + 16, 96), (8 + 4 + 16, 64))
+_BLOCKS = {"4.6": BLOCK_SPECS, "4.7": BLOCK_SPECS_47, "4.17": BLOCK_SPECS_417}
 
 
 def state_dict_spec(arch: str = "4.6") -> List[Tuple[str, Tuple[int, ...]]]:
-    """Names and shapes of IFNet(arch).state_dict(), in the reference's order (arch "4.6" or "4.7").
+    """Names and shapes of IFNet(arch).state_dict(), in the reference's order (arch "4.6", "4.7" or "4.17").
 
     Follows the module construction in rife_arch.py:177-218 (IFBlock.__init__),
     :20-28 (ResConv) and :404-408 (IFNet.__init__ for arch 4.6): 4 blocks x
     (conv0.0, conv0.1, 8 x ResConv{beta, conv}, lastconv) = 120 tensors, 5,306,256 values.
     """
     spec: List[Tuple[str, Tuple[int, ...]]] = []
-    for b, (cin, c) in enumerate(BLOCK_SPECS if arch == "4.6" else BLOCK_SPECS_47):
+    for b, (cin, c) in enumerate(_BLOCKS[arch]):
         p = f"block{b}."
         spec += [(p + "conv0.0.0.weight", (c // 2, cin, 3, 3)), (p + "conv0.0.0.bias", (c // 2,))]
         spec += [(p + "conv0.1.0.weight", (c, c // 2, 3, 3)), (p + "conv0.1.0.bias", (c,))]
@@ -54,6 +57,11 @@ def state_dict_spec(arch: str = "4.6") -> List[Tuple[str, Tuple[int, ...]]]:
     if arch == "4.7":  # encode = Sequential(Conv2d(3,16,3,2,1), ConvTranspose2d(16,4,4,2,1)) -- rife_arch.py:414-416
         spec += [("encode.0.weight", (16, 3, 3, 3)), ("encode.0.bias", (16,)),
                  ("encode.1.weight", (16, 4, 4, 4)), ("encode.1.bias", (4,))]
+    if arch == "4.17":  # encode = Head_417: cnn0 3->32 s2, cnn1/cnn2 32->32, cnn3 ConvT 32->8 -- rife_arch.py:356-363
+        spec += [("encode.cnn0.weight", (32, 3, 3, 3)), ("encode.cnn0.bias", (32,)),
+                 ("encode.cnn1.weight", (32, 32, 3, 3)), ("encode.cnn1.bias", (32,)),
+                 ("encode.cnn2.weight", (32, 32, 3, 3)), ("encode.cnn2.bias", (32,)),
+                 ("encode.cnn3.weight", (32, 8, 4, 4)), ("encode.cnn3.bias", (8,))]
     return spec
 
 
@@ -196,7 +204,8 @@ def ifnet46_forward(sd: Dict[str, torch.Tensor], img0: torch.Tensor, img1: torch
 
 def ifnet47_forward(sd: Dict[str, torch.Tensor], img0: torch.Tensor, img1: torch.Tensor, timestep: torch.Tensor,
                     scale_list: Sequence[float] = (8, 4, 2, 1), taps: Optional[dict] = None) -> torch.Tensor:
-    """IFNet.forward restricted to arch 4.7 (rife47.pth / rife49.pth), ensemble=False -- rife_arch.py:465-732.
+    """IFNet.forward restricted to arch 4.7 (rife47.pth / rife49.pth) and 4.17 (rife417.pth, same forward with the
+    Head_417 encoder and 8 feature channels per frame), ensemble=False -- rife_arch.py:465-732.
 
     Differences to 4.6: f0/f1 = encode(img) (Conv2d 3->16 s2, ConvTranspose2d 16->4, no activation; :501-503) are
     concatenated to block 0's input (:543-548) and, warped with the current flow, to the later blocks' inputs
@@ -212,6 +221,11 @@ def ifnet47_forward(sd: Dict[str, torch.Tensor], img0: torch.Tensor, img1: torch
     t = timestep.reshape(n, 1, 1, 1).to(img0.dtype).repeat(1, 1, ph, pw)
 
     def encode(x):
+        if "encode.cnn0.weight" in sd:  # arch 4.17, Head_417.forward -- rife_arch.py:365-375 (feat=False)
+            y = F.leaky_relu(F.conv2d(x, sd["encode.cnn0.weight"], sd["encode.cnn0.bias"], stride=2, padding=1), 0.2)
+            y = F.leaky_relu(F.conv2d(y, sd["encode.cnn1.weight"], sd["encode.cnn1.bias"], padding=1), 0.2)
+            y = F.leaky_relu(F.conv2d(y, sd["encode.cnn2.weight"], sd["encode.cnn2.bias"], padding=1), 0.2)
+            return F.conv_transpose2d(y, sd["encode.cnn3.weight"], sd["encode.cnn3.bias"], stride=2, padding=1)
         y = F.conv2d(x, sd["encode.0.weight"], sd["encode.0.bias"], stride=2, padding=1)
         return F.conv_transpose2d(y, sd["encode.1.weight"], sd["encode.1.bias"], stride=2, padding=1)
 

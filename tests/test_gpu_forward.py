@@ -43,7 +43,7 @@ def test_ifnet_golden(pkg, name, dtype):
     assert p >= PSNR_MIN
 
 
-@pytest.mark.parametrize("arch", ["4.6", "4.7"])
+@pytest.mark.parametrize("arch", ["4.6", "4.7", "4.17"])
 def test_flow_and_mask_match_oracle(pkg, arch):
     """Intermediate state: final full-resolution flow / mask vs the oracle's (fp32)."""
     sd = O.synthetic_state_dict(0, arch=arch)

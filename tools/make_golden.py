@@ -60,6 +60,12 @@ def cases():
         "ifnet47_64x128_gain3": dict(kind="ifnet", arch="4.7", seed=9, gain=3.0, h=64, w=128, ts=(0.5,), clip_seed=17),
         "node47_m2": dict(kind="node", arch="4.7", ckpt="rife49.pth", seed=10, gain=1.0, n=3, h=56, w=88, c=3,
                           multiplier=2, states=None, clip_seed=18),
+        # arch 4.17 (rife417.pth): Head_417 encoder (three 32-channel convs + ConvT), 8 feature channels per frame
+        "ifnet417_96x160": dict(kind="ifnet", arch="4.17", seed=20, gain=1.0, h=96, w=160, ts=(0.5, 0.7), clip_seed=21),
+        "ifnet417_64x128_gain3": dict(kind="ifnet", arch="4.17", seed=22, gain=3.0, h=64, w=128, ts=(0.25,),
+                                      clip_seed=23),
+        "node417_m3": dict(kind="node", arch="4.17", ckpt="rife417.pth", seed=24, gain=1.0, n=3, h=56, w=88, c=3,
+                           multiplier=3, states=None, clip_seed=25),
         # node level: keep-list (is_skip_list False)
         "node_keep": dict(kind="node", seed=4, gain=1.0, n=4, h=48, w=80, c=3, multiplier=2,
                           states=([0, 2], False), clip_seed=15),

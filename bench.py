@@ -34,6 +34,7 @@ METRIC = "interpolated frames/sec @1080p RIFE-4.6 2x"
 UNIT = "frames/s"
 FLOPS_PER_FRAME = 175.245e9          # SURVEY.md section 8d (87.62 GMAC)
 CPU_SAMPLE_FRAMES = 3                # 2 pairs of the same clip for the CPU legs (bounded sample)
+CPU_ARCH = "4.6"
 
 
 def _peaks():
@@ -102,9 +103,9 @@ def _pick_threads(sd):
     best, best_t = cands[0], float("inf")
     for c in cands:
         torch.set_num_threads(c)
-        O.rife_vfi(sd, small, multiplier=2)
+        O.rife_vfi(sd, small, multiplier=2, arch=CPU_ARCH)
         t0 = time.perf_counter()
-        O.rife_vfi(sd, small, multiplier=2)
+        O.rife_vfi(sd, small, multiplier=2, arch=CPU_ARCH)
         dt = time.perf_counter() - t0
         if dt < best_t:
             best, best_t = c, dt
@@ -121,7 +122,7 @@ def cpu_port_fps(clip, sd, steps, warmup):
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        O.rife_vfi(sd, sample, multiplier=2)
+        O.rife_vfi(sd, sample, multiplier=2, arch=CPU_ARCH)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
@@ -139,6 +140,8 @@ def main():
     ap.add_argument("--dtype", default="float32", help="node dtype: float32/float16 -> fp16 operands, bfloat16 -> bf16")
     ap.add_argument("--frames", type=int, default=NFRAMES)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--arch", default="4.6", choices=["4.6", "4.7", "4.17", "4.26"],
+                    help="RIFE arch (default 4.6 = the BASELINE.json metric; the others are side measurements)")
     a = ap.parse_args()
 
     import torch
@@ -149,13 +152,15 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if a.gpus != world and world > 1:
         a.gpus = world
-    config = {"workload": f"RIFE 4.6, 2x multiplier, {a.frames}-frame synthetic 1080p clip per GPU (BASELINE configs[1])",
+    config = {"workload": f"RIFE {a.arch}, 2x multiplier, {a.frames}-frame synthetic 1080p clip per GPU (BASELINE configs[1])",
               "resolution": [H, W], "frames_per_gpu": a.frames, "pairs_per_gpu": a.frames - 1,
               "padded": [1088, 1920], "weights": "seeded synthetic (oracle.synthetic_state_dict(0)); no checkpoint ships",
               "parallelism": f"frame-pair shards x{a.gpus}; each rank's outputs gathered to rank 0 by NCCL in 4 chunks, overlapped with the next chunk's compute" if a.gpus > 1 else "1 GPU",
               "l2": "inputs larger than L2 (1.6 GB clip, 1.6 GB output per step)"}
 
-    sd = O.synthetic_state_dict(0)
+    sd = O.synthetic_state_dict(0, arch=a.arch)
+    global CPU_ARCH
+    CPU_ARCH = a.arch
 
     # ------------------------------------------------------------------ reference arm: CPU port only
     if a.impl == "reference":
@@ -193,7 +198,7 @@ def main():
 
     nf = a.frames
     clip = O.synthetic_clip(nf, H, W, seed=1234 + rank)            # this rank's shard (own content, same shape)
-    eng = Rife46Engine(sd, device=local_rank, dtype=a.dtype, batch=a.batch)
+    eng = Rife46Engine(sd, device=local_rank, dtype=a.dtype, batch=a.batch, arch=a.arch)
     f0 = list(range(nf - 1))
     f1 = list(range(1, nf))
     ts = [0.5] * (nf - 1)
@@ -330,7 +335,7 @@ def main():
                         "h2d_bytes_per_step": nf * H * W * 3 * 4, "d2h_bytes_per_step": npairs * H * W * 3 * 4,
                         "host_equals_device_path": same},
                 "gpu_launches": launches, "lib": cfi_lib.lib().vfi_version().decode(), "clocks": clocks,
-                "model_tflops": value * FLOPS_PER_FRAME / 1e12,
+                "model_tflops": value * FLOPS_PER_FRAME / 1e12 if a.arch == "4.6" else None,
                 "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu}
         print(json.dumps(line))
     eng.close()

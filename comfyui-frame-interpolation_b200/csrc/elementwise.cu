@@ -118,11 +118,11 @@ __device__ __forceinline__ float4 sample_border4(const float4* __restrict__ img,
 // moved 2x the bytes.)
 // ---------------------------------------------------------------------------------------------
 struct FlowLevels {
-  const float4* f[4];  // levels to add, in order: [B, Hp/s, Wp/s] flow increments
-  const float* m[4];   //                          [B, Hp/s, Wp/s] mask increments
-  int s[4];
-  int hs[4], ws[4];      // level size Hp/s, Wp/s (set by the host: no integer division in the kernels)
-  float inv_s[4];        // 1/s
+  const float4* f[kMaxBlocks];  // levels to add, in order: [B, Hp/s, Wp/s] flow increments
+  const float* m[kMaxBlocks];   //                          [B, Hp/s, Wp/s] mask increments
+  int s[kMaxBlocks];
+  int hs[kMaxBlocks], ws[kMaxBlocks];  // level size Hp/s, Wp/s (set by the host: no integer division in the kernels)
+  float inv_s[kMaxBlocks];             // 1/s
   const float4* base_f;  // optional full-resolution accumulated flow [B, Hp, Wp] (nullptr: start from zero)
   const float* base_m;
   float4* out_f;         // optional: store the accumulated flow / mask at every visited position
@@ -738,6 +738,163 @@ __global__ void front417_kernel(const float4* __restrict__ imgs, const uint4* __
   for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(dst)[i] = q[i];
 }
 
+// ---------------------------------------------------------------------------------------------
+// arch 4.26 (rife426.pth): encode = Head (rife_arch.py:378-395; cnn0 on the CUDA cores via head0_kernel with the 16
+// output channels zero-padded to 32, cnn1..cnn3 as tapconv layers) -> 4-channel 16-bit features stored space-to-depth
+// ([Hh][Wh][4 x 4]: one uint2 per pixel).  Block input (rife_arch.py:521-526, :563-587):
+//   block 0 : [img0, img1, f0 (4), f1 (4), t]                                                        = 15 of 32 channels
+//   block i : [w0.rgb, w1.rgb, warp(f0), warp(f1), t, mask, feat (8), flow/s (4)]                     = 28 of 32 channels
+// where `feat` = the previous block's 8 extra lastconv channels, bilinearly up-scaled to full resolution by its scale
+// (rife_arch.py:267-274) and, like every other channel, down-scaled by 1/s here (2x2 centre taps).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void load_feat4(const uint2* __restrict__ ft, int Wh, int Y, int X, float (&v)[4]) {
+  const uint2 q = __ldg(ft + ((size_t)((Y >> 1) * Wh + (X >> 1)) * 4 + ((Y & 1) * 2 + (X & 1))));
+  const float2 a = Pack2<T>::unpack(q.x), b = Pack2<T>::unpack(q.y);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+template <typename T>
+__device__ __forceinline__ void sample_border4h(const uint2* __restrict__ ft, int Hp, int Wp, float sx, float sy,
+                                                float (&o)[4]) {
+  sx = fminf(fmaxf(sx, 0.f), (float)(Wp - 1));
+  sy = fminf(fmaxf(sy, 0.f), (float)(Hp - 1));
+  const float fx0 = floorf(sx), fy0 = floorf(sy);
+  const int x0 = (int)fx0, y0 = (int)fy0;
+  const int x1 = min(x0 + 1, Wp - 1), y1 = min(y0 + 1, Hp - 1);
+  const float ax = sx - fx0, ay = sy - fy0;
+  const float w00 = (1.f - ax) * (1.f - ay), w01 = ax * (1.f - ay), w10 = (1.f - ax) * ay, w11 = ax * ay;
+  float a[4], b[4], c[4], d[4];
+  load_feat4<T>(ft, Wp >> 1, y0, x0, a);
+  load_feat4<T>(ft, Wp >> 1, y0, x1, b);
+  load_feat4<T>(ft, Wp >> 1, y1, x0, c);
+  load_feat4<T>(ft, Wp >> 1, y1, x1, d);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o[i] = a[i] * w00 + b[i] * w01 + c[i] * w10 + d[i] * w11;
+}
+
+template <typename T>
+__device__ __forceinline__ void unpack8(const uint4 q, float (&v)[8]) {
+  const float2 a = Pack2<T>::unpack(q.x), b = Pack2<T>::unpack(q.y), c = Pack2<T>::unpack(q.z), d = Pack2<T>::unpack(q.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+
+// F.interpolate(scale_factor=s, bilinear, align_corners=False) of the 8-channel plane pf [Hs][Ws] at full-res (Y, X)
+template <typename T>
+__device__ __forceinline__ void up_feat8(const uint4* __restrict__ pf, int Hs, int Ws, int s, float inv_s, int Y, int X,
+                                         float (&o)[8]) {
+  if (s == 1) {
+    unpack8<T>(__ldg(pf + (Y * Ws + X)), o);
+    return;
+  }
+  const float sy = fmaxf(((float)Y + 0.5f) * inv_s - 0.5f, 0.f);
+  const float sx = fmaxf(((float)X + 0.5f) * inv_s - 0.5f, 0.f);
+  const int y0 = min((int)sy, Hs - 1), x0 = min((int)sx, Ws - 1);
+  const int dx = (x0 + 1 < Ws) ? 1 : 0, dyw = (y0 + 1 < Hs) ? Ws : 0;
+  const float ly = sy - (float)y0, lx = sx - (float)x0;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const int o00 = y0 * Ws + x0;
+  float a[8], b[8], c[8], d[8];
+  unpack8<T>(__ldg(pf + o00), a);
+  unpack8<T>(__ldg(pf + o00 + dx), b);
+  unpack8<T>(__ldg(pf + o00 + dyw), c);
+  unpack8<T>(__ldg(pf + o00 + dyw + dx), d);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = hy * (hx * a[i] + lx * b[i]) + ly * (hx * c[i] + lx * d[i]);
+}
+
+template <typename T, int NLEV>
+__global__ void front426_kernel(const uint2* __restrict__ imgs, const uint2* __restrict__ feats,
+                                const uint4* __restrict__ prev_feat, int prev_s, const FlowLevels lev,
+                                const BatchTasks tasks, int Hp, int Wp, int s, T* __restrict__ x_s2d) {
+  const int Hs = Hp / s, Ws = Wp / s;
+  const size_t plane = (size_t)Hp * Wp;
+  const float inv_s = 1.f / (float)s;
+  const int par = (int)(threadIdx.x & 1);
+  const int xl = (int)(blockIdx.x * (blockDim.x >> 1) + (threadIdx.x >> 1));
+  if (xl >= Ws) return;
+  const int yl = (int)blockIdx.y * 2 + par;
+  const int b = (int)blockIdx.z;
+  const uint2* img0 = imgs + (size_t)tasks.f0[b] * plane;
+  const uint2* img1 = imgs + (size_t)tasks.f1[b] * plane;
+  const uint2* ft0 = feats + (size_t)tasks.f0[b] * plane;  // one uint2 per pixel
+  const uint2* ft1 = feats + (size_t)tasks.f1[b] * plane;
+  const int pHs = NLEV ? Hp / prev_s : 1, pWs = NLEV ? Wp / prev_s : 1;
+  const uint4* pf = NLEV ? prev_feat + (size_t)b * pHs * pWs : nullptr;
+  const float pinv = NLEV ? 1.f / (float)prev_s : 1.f;
+  const float t = tasks.t[b];
+  const int ntap = (s == 1) ? 1 : 2;
+  const int by = (s == 1) ? yl : s * yl + s / 2 - 1;
+  const int bx = (s == 1) ? xl : s * xl + s / 2 - 1;
+  float ch[28];
+#pragma unroll
+  for (int ty = 0; ty < 2; ++ty) {
+    float row[28];
+#pragma unroll
+    for (int tx = 0; tx < 2; ++tx) {
+      if (ty < ntap && tx < ntap) {
+        const int Y = by + ty, X = bx + tx;
+        float v[28];
+        float4 a, c;
+        float fa[4], fc[4];
+        if (NLEV == 0) {
+          a = unpack_h4(__ldg(img0 + (size_t)Y * Wp + X));
+          c = unpack_h4(__ldg(img1 + (size_t)Y * Wp + X));
+          load_feat4<T>(ft0, Wp >> 1, Y, X, fa);
+          load_feat4<T>(ft1, Wp >> 1, Y, X, fc);
+          v[14] = t;
+#pragma unroll
+          for (int i = 15; i < 28; ++i) v[i] = 0.f;
+        } else {
+          float4 f;
+          float m;
+          flow_at<(NLEV > 0 ? NLEV : 1)>(lev, b, Hp, Wp, Y, X, f, m);
+          a = sample_border(img0, Hp, Wp, (float)X + f.x, (float)Y + f.y);
+          c = sample_border(img1, Hp, Wp, (float)X + f.z, (float)Y + f.w);
+          sample_border4h<T>(ft0, Hp, Wp, (float)X + f.x, (float)Y + f.y, fa);
+          sample_border4h<T>(ft1, Hp, Wp, (float)X + f.z, (float)Y + f.w, fc);
+          float pe[8];
+          up_feat8<T>(pf, pHs, pWs, prev_s, pinv, Y, X, pe);
+          v[14] = t; v[15] = m;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[16 + i] = pe[i];
+          v[24] = f.x; v[25] = f.y; v[26] = f.z; v[27] = f.w;
+        }
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = c.x; v[4] = c.y; v[5] = c.z;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          v[6 + i] = fa[i];
+          v[10 + i] = fc[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 28; ++i) row[i] = (tx == 0) ? v[i] : row[i] + v[i];
+      }
+    }
+    if (ty < ntap) {
+#pragma unroll
+      for (int i = 0; i < 28; ++i) ch[i] = (ty == 0) ? row[i] : ch[i] + row[i];
+    }
+  }
+  if (ntap == 2) {
+#pragma unroll
+    for (int i = 0; i < 28; ++i) ch[i] *= 0.25f;
+  }
+#pragma unroll
+  for (int i = 24; i < 28; ++i) ch[i] *= inv_s;  // flow is also divided by the scale (rife_arch.py:242-248)
+  const size_t cell = ((size_t)b * (Hs >> 1) + (yl >> 1)) * (Ws >> 1) + (xl >> 1);
+  T* dst = x_s2d + cell * 128 + ((yl & 1) * 2 + (xl & 1)) * 32;
+  uint4 q[4];
+  q[0] = make_uint4(Pack2<T>::pack(ch[0], ch[1]), Pack2<T>::pack(ch[2], ch[3]), Pack2<T>::pack(ch[4], ch[5]),
+                    Pack2<T>::pack(ch[6], ch[7]));
+  q[1] = make_uint4(Pack2<T>::pack(ch[8], ch[9]), Pack2<T>::pack(ch[10], ch[11]), Pack2<T>::pack(ch[12], ch[13]),
+                    Pack2<T>::pack(ch[14], ch[15]));
+  q[2] = make_uint4(Pack2<T>::pack(ch[16], ch[17]), Pack2<T>::pack(ch[18], ch[19]), Pack2<T>::pack(ch[20], ch[21]),
+                    Pack2<T>::pack(ch[22], ch[23]));
+  q[3] = make_uint4(Pack2<T>::pack(ch[24], ch[25]), Pack2<T>::pack(ch[26], ch[27]), 0u, 0u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(dst)[i] = q[i];
+}
+
 // debug / tests only: materialise the accumulated full-resolution flow and mask
 template <int NLEV>
 __global__ void materialize_kernel(const FlowLevels lev, float4* __restrict__ flow, float* __restrict__ mask, int B,
@@ -915,6 +1072,19 @@ static void launch_front417_t(int nlev, dim3 g, cudaStream_t st, const float4* i
   }
 }
 
+template <typename T>
+static void launch_front426_t(int nlev, dim3 g, cudaStream_t st, const uint2* imgs, const uint2* feats,
+                              const uint4* prev_feat, int prev_s, const FlowLevels& L, const BatchTasks& tasks, int Hp,
+                              int Wp, int s, void* x) {
+  switch (nlev) {
+    case 0: front426_kernel<T, 0><<<g, 128, 0, st>>>(imgs, feats, prev_feat, prev_s, L, tasks, Hp, Wp, s, (T*)x); break;
+    case 1: front426_kernel<T, 1><<<g, 128, 0, st>>>(imgs, feats, prev_feat, prev_s, L, tasks, Hp, Wp, s, (T*)x); break;
+    case 2: front426_kernel<T, 2><<<g, 128, 0, st>>>(imgs, feats, prev_feat, prev_s, L, tasks, Hp, Wp, s, (T*)x); break;
+    case 3: front426_kernel<T, 3><<<g, 128, 0, st>>>(imgs, feats, prev_feat, prev_s, L, tasks, Hp, Wp, s, (T*)x); break;
+    default: front426_kernel<T, 4><<<g, 128, 0, st>>>(imgs, feats, prev_feat, prev_s, L, tasks, Hp, Wp, s, (T*)x); break;
+  }
+}
+
 cudaError_t launch_head0(int op_type, const float4* imgs, const float* w, const float* bias, void* out, int n, int Hp,
                          int Wp, cudaStream_t st) {
   const dim3 g((unsigned)((Wp / 2 + 127) / 128), (unsigned)(Hp / 2), (unsigned)n);
@@ -936,13 +1106,24 @@ cudaError_t launch_encode(const float4* imgs, const float* w0, const float* b0, 
   return cudaGetLastError();
 }
 
-cudaError_t launch_front(int op_type, const float4* imgs, const uint2* imgs_h, const void* feats, int feat_ch,
-                         const FlowState& fs, int blk, int lo, const float4* base_f, const float* base_m, float4* out_f, float* out_m, BatchTasks tasks,
+cudaError_t launch_front(int op_type, int arch, const float4* imgs, const uint2* imgs_h, const void* feats, int feat_ch,
+                         const void* prev_feat, int prev_s, const FlowState& fs, int blk, int lo, const float4* base_f, const float* base_m, float4* out_f, float* out_m, BatchTasks tasks,
                          int Hp, int Wp, int s, void* x_s2d, cudaStream_t st) {
   const dim3 g((unsigned)((Wp / s + 63) / 64), (unsigned)(Hp / s / 2), (unsigned)tasks.n);  // 64 cells x 2 rows per block
   const FlowLevels L = make_levels(fs, lo, blk, base_f, base_m, out_f, out_m, Hp, Wp);
   const int nlev = (blk == 0) ? 0 : (blk - lo);
   if (blk > 0 && nlev == 0 && base_f == nullptr) return cudaErrorInvalidValue;
+  if (nlev > 4 || (arch != 426 && nlev > 3)) return cudaErrorInvalidValue;  // front kernels are built for <= 3 (4.26: 4) levels
+  if (arch == 426) {  // 4-channel 16-bit space-to-depth features + the previous block's 8 feature channels
+    if (feats == nullptr || (blk > 0 && prev_feat == nullptr)) return cudaErrorInvalidValue;
+    if (op_type == OP_BF16)
+      launch_front426_t<__nv_bfloat16>(blk == 0 ? 0 : (nlev == 0 ? 1 : nlev), g, st, imgs_h, (const uint2*)feats,
+                                       (const uint4*)prev_feat, prev_s, L, tasks, Hp, Wp, s, x_s2d);
+    else
+      launch_front426_t<__half>(blk == 0 ? 0 : (nlev == 0 ? 1 : nlev), g, st, imgs_h, (const uint2*)feats,
+                                (const uint4*)prev_feat, prev_s, L, tasks, Hp, Wp, s, x_s2d);
+    return cudaGetLastError();
+  }
   if (feats != nullptr && feat_ch == 4) {  // arch 4.7
     if (op_type == OP_BF16)
       launch_front47_t<__nv_bfloat16>(blk == 0 ? 0 : nlev, g, st, imgs, (const float4*)feats, L, tasks, Hp, Wp, s, x_s2d);
@@ -971,27 +1152,28 @@ cudaError_t launch_front(int op_type, const float4* imgs, const uint2* imgs_h, c
 cudaError_t launch_materialize(const FlowState& fs, int lo, const float4* base_f, const float* base_m, float4* flow,
                                float* mask, int B, int Hp, int Wp, cudaStream_t st) {
   const size_t total = (size_t)B * Hp * Wp;
-  FlowLevels L = make_levels(fs, lo, 4, base_f, base_m, nullptr, nullptr, Hp, Wp);
-  // pad unused levels with a zero-weight copy of the last one is not needed: materialize_kernel is NLEV=4-lo generic
-  const int nlev = 4 - lo;
+  FlowLevels L = make_levels(fs, lo, fs.n, base_f, base_m, nullptr, nullptr, Hp, Wp);
+  const int nlev = fs.n - lo;
   switch (nlev) {
     case 1: materialize_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(L, flow, mask, B, Hp, Wp); break;
     case 2: materialize_kernel<2><<<grid_for(total, 256), 256, 0, st>>>(L, flow, mask, B, Hp, Wp); break;
     case 3: materialize_kernel<3><<<grid_for(total, 256), 256, 0, st>>>(L, flow, mask, B, Hp, Wp); break;
-    default: materialize_kernel<4><<<grid_for(total, 256), 256, 0, st>>>(L, flow, mask, B, Hp, Wp); break;
+    case 4: materialize_kernel<4><<<grid_for(total, 256), 256, 0, st>>>(L, flow, mask, B, Hp, Wp); break;
+    default: materialize_kernel<5><<<grid_for(total, 256), 256, 0, st>>>(L, flow, mask, B, Hp, Wp); break;
   }
   return cudaGetLastError();
 }
 
 cudaError_t launch_final(const float4* imgs, const FlowState& fs, int lo, const float4* base_f, const float* base_m,
                          BatchTasks tasks, int Hp, int Wp, int H, int W, float* out, cudaStream_t st) {
-  const FlowLevels L = make_levels(fs, lo, 4, base_f, base_m, nullptr, nullptr, Hp, Wp);
+  const FlowLevels L = make_levels(fs, lo, fs.n, base_f, base_m, nullptr, nullptr, Hp, Wp);
   const dim3 g((unsigned)((W + 255) / 256), (unsigned)H, (unsigned)tasks.n);
-  switch (4 - lo) {
+  switch (fs.n - lo) {
     case 1: final_kernel<1><<<g, 256, 0, st>>>(imgs, L, tasks, Hp, Wp, H, W, out); break;
     case 2: final_kernel<2><<<g, 256, 0, st>>>(imgs, L, tasks, Hp, Wp, H, W, out); break;
     case 3: final_kernel<3><<<g, 256, 0, st>>>(imgs, L, tasks, Hp, Wp, H, W, out); break;
-    default: final_kernel<4><<<g, 256, 0, st>>>(imgs, L, tasks, Hp, Wp, H, W, out); break;
+    case 4: final_kernel<4><<<g, 256, 0, st>>>(imgs, L, tasks, Hp, Wp, H, W, out); break;
+    default: final_kernel<5><<<g, 256, 0, st>>>(imgs, L, tasks, Hp, Wp, H, W, out); break;
   }
   return cudaGetLastError();
 }

@@ -30,10 +30,12 @@ void set_error(const std::string& s) { g_err = s; }
 
 namespace {
 
-const int kBlockC[4] = {192, 128, 96, 64};
+const int kBlockC[kMaxBlocks] = {192, 128, 96, 64, 32};  // (the fifth block exists in arch 4.26 only)
 const int kBlockCinReal[4] = {7, 12, 12, 12};        // arch 4.6: img0,img1,t | w0,w1,t,mask + flow
 const int kBlockCinReal47[4] = {15, 20, 20, 20};     // arch 4.7: + encoded features f0,f1 (4 ch each)
 const int kBlockCinReal417[4] = {23, 28, 28, 28};    // arch 4.17: + Head_417 features f0,f1 (8 ch each)
+const int kBlockCinReal426[kMaxBlocks] = {15, 28, 28, 28, 28};  // arch 4.26: f0,f1 (4 each) [+ mask, 8 fed-back features, flow]
+inline int num_blocks(int arch) { return arch == 426 ? 5 : 4; }
 
 uint16_t to_operand(float v, int op_type) {
   if (op_type == OP_BF16) {
@@ -126,14 +128,16 @@ struct vfi_ctx {
   int op_type = OP_F16;
   bool loaded = false;
   int64_t launches = 0;
-  TapConvLayer layers[4][11];  // [block][0=conv0.0, 1=conv0.1, 2..9=ResConv, 10=lastconv]
+  TapConvLayer layers[kMaxBlocks][12];  // [block][0=conv0.0, 1=conv0.1, 2..9=ResConv, 10=lastconv (flow + mask),
+                                        //          11 = arch 4.26: the 8 feature channels of lastconv]
   std::vector<void*> weight_allocs;
   // workspace
-  DevBuf imgs, imgs_h, flow, mask, x, c00, featA, featB, tF[4], tM[4], raw, outdev;
+  DevBuf imgs, imgs_h, flow, mask, x, c00, featA, featB, tF[kMaxBlocks], tM[kMaxBlocks], raw, outdev;
+  DevBuf tE[kMaxBlocks];         // arch 4.26: block outputs' 8 feature channels [B, Hp/s, Wp/s, 8] 16-bit
   int arch = 46;                 // 46 | 47 (rife47.pth / rife49.pth)
   DevBuf feats, e16;             // arch 4.7: encoded features per source frame (float4), half-res temp
   float* enc[4] = {nullptr, nullptr, nullptr, nullptr};  // encode.0.weight/.bias, encode.1.weight/.bias (fp32)
-  TapConvLayer head[3];          // arch 4.17: Head_417 cnn1, cnn2 (32->32 + LeakyReLU), cnn3 (ConvTranspose 32->8)
+  TapConvLayer head[3];          // arch 4.17 / 4.26: Head cnn1, cnn2 (+ LeakyReLU), cnn3 (ConvTranspose), 32 (padded) channels
   DevBuf hA, hB;                 // arch 4.17: half-resolution 32-channel scratch of the head (ping-pong)
   int ws_Hp = 0, ws_Wp = 0, ws_B = 0;
   FlowState last_fs{};
@@ -271,7 +275,7 @@ int build_resconv(vfi_ctx* c, TapConvLayer& L, int ch, const float* beta, const 
 // ConvTranspose2d(c, 24, 4, 2, 1) + PixelShuffle(2) as ONE 3x3 conv producing, per feature cell, the 4x4 sub-pixel
 // patch of the 5 used channels: n = c5*16 + py*4 + px, (py,px) = (2a+i, 2b+j), convT channel oc = 4*c5 + 2i + j at
 // convT position (2y+a, 2x+b); tap (dy,dx) uses transposed-kernel element ky = a+1-2dy, kx = b+1-2dx.
-int build_lastconv(vfi_ctx* c, TapConvLayer& L, int ch, const float* wt, const float* bias) {
+int build_lastconv(vfi_ctx* c, TapConvLayer& L, int ch, int cout, const float* wt, const float* bias) {
   L = TapConvLayer{};
   L.cin = ch;
   L.n_total = 80;
@@ -296,7 +300,7 @@ int build_lastconv(vfi_ctx* c, TapConvLayer& L, int ch, const float* wt, const f
     const int pos = n & 15, py = pos >> 2, px = pos & 3;
     const int ky = (py >> 1) + 1 - 2 * dy, kx = (px >> 1) + 1 - 2 * dx;
     if (ky < 0 || ky > 3 || kx < 0 || kx > 3) return 0.f;
-    return wt[(((size_t)ci * 24 + oc_of(n)) * 4 + ky) * 4 + kx];
+    return wt[(((size_t)ci * cout + oc_of(n)) * 4 + ky) * 4 + kx];
   };
   std::vector<uint16_t> pk = pack_weights(L, c->op_type, wf);
   std::vector<float> sh(80);
@@ -307,8 +311,46 @@ int build_lastconv(vfi_ctx* c, TapConvLayer& L, int ch, const float* wt, const f
   return VFI_OK;
 }
 
-// Head_417.cnn1 / cnn2: plain 3x3 conv + LeakyReLU on a 32-channel half-resolution tensor (one 32-channel k-block)
-int build_conv3x3_lrelu(vfi_ctx* c, TapConvLayer& L, int ch, const float* w, const float* bias) {
+// arch 4.26: channels 5..12 of ConvTranspose2d(c, 52, 4, 2, 1) + PixelShuffle(2) (rife_arch.py:230-233, :272) - the 8
+// feature channels handed to the next block - as a second 3x3 tap conv over the same input: column
+// n = (py*4 + px)*8 + f holds feature f at sub-pixel (py, px) of the cell's 4x4 patch, so 16 consecutive columns are
+// two x-adjacent sub-pixels x 8 channels = 32 contiguous bytes of the [B, 4H, 4W, 8] output (out_s2d = 2).
+int build_lastfeat(vfi_ctx* c, TapConvLayer& L, int ch, int cout, const float* wt, const float* bias) {
+  L = TapConvLayer{};
+  L.cin = ch;
+  L.n_total = 128;
+  L.ntaps = 9;
+  L.ktotal16 = 9 * (ch / 16);
+  L.halo_y0 = -1; L.halo_x0 = -1; L.halo_h = kTileH + 2; L.halo_w = kTileW + 2;
+  L.epi_mode = EPI_BIAS;
+  L.out_s2d = 2;
+  const bool ring = want_ring(ch);
+  set_taps_3x3(L, ch, ring);
+  choose_split(L, {2, 4, 8}, 2);
+  auto oc_of = [](int n) {
+    const int f = n & 7, pos = n >> 3, py = pos >> 2, px = pos & 3;
+    return 4 * (5 + f) + 2 * (py & 1) + (px & 1);
+  };
+  auto wf = [&](int e, int cr, int n) -> float {  // e = kb * 9 + tap, cr relative to the k-block
+    const int tap = e % 9, ci = (e / 9) * 64 + cr;
+    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+    const int pos = n >> 3, py = pos >> 2, px = pos & 3;
+    const int ky = (py >> 1) + 1 - 2 * dy, kx = (px >> 1) + 1 - 2 * dx;
+    if (ky < 0 || ky > 3 || kx < 0 || kx > 3) return 0.f;
+    return wt[(((size_t)ci * cout + oc_of(n)) * 4 + ky) * 4 + kx];
+  };
+  std::vector<uint16_t> pk = pack_weights(L, c->op_type, wf);
+  std::vector<float> sh(128);
+  for (int n = 0; n < 128; ++n) sh[n] = bias[oc_of(n)];
+  int r;
+  if ((r = upload(c, pk, &L.w))) return r;
+  if ((r = upload(c, sh, (void**)&L.shift))) return r;
+  return VFI_OK;
+}
+
+// Head_417.cnn1 / cnn2: plain 3x3 conv + LeakyReLU on a 32-channel half-resolution tensor (one 32-channel k-block).
+// `creal` < ch: arch 4.26's 16-channel Head layers run zero-padded to 32 channels (the kernel's smallest k-block).
+int build_conv3x3_lrelu(vfi_ctx* c, TapConvLayer& L, int ch, int creal, const float* w, const float* bias) {
   L = TapConvLayer{};
   L.cin = ch;
   L.n_total = ch;
@@ -317,9 +359,13 @@ int build_conv3x3_lrelu(vfi_ctx* c, TapConvLayer& L, int ch, const float* w, con
   L.epi_mode = EPI_BIAS_LRELU;
   set_taps_3x3(L, ch, false);
   choose_split(L, {1}, 2);
-  auto wf = [&](int e, int ci, int n) -> float { return w[(((size_t)n * ch + ci) * 3 + e / 3) * 3 + e % 3]; };
+  auto wf = [&](int e, int ci, int n) -> float {
+    if (ci >= creal || n >= creal) return 0.f;
+    return w[(((size_t)n * creal + ci) * 3 + e / 3) * 3 + e % 3];
+  };
   std::vector<uint16_t> pk = pack_weights(L, c->op_type, wf);
-  std::vector<float> sh(bias, bias + ch);
+  std::vector<float> sh(ch, 0.f);
+  for (int i = 0; i < creal; ++i) sh[i] = bias[i];
   int r;
   if ((r = upload(c, pk, &L.w))) return r;
   if ((r = upload(c, sh, (void**)&L.shift))) return r;
@@ -329,7 +375,7 @@ int build_conv3x3_lrelu(vfi_ctx* c, TapConvLayer& L, int ch, const float* w, con
 // Head_417.cnn3 = ConvTranspose2d(ch, cout, 4, 2, 1), no activation, as ONE 3x3 conv producing the 2x2 sub-pixels of
 // every input cell: n = (a*2 + b)*cout + oc at output position (2y+a, 2x+b); tap (dy,dx) uses transposed-kernel element
 // ky = a+1-2dy, kx = b+1-2dx.  The NHWC output [Hh][Wh][4*cout] IS the space-to-depth form of the feature map.
-int build_deconv_s2d(vfi_ctx* c, TapConvLayer& L, int ch, int cout, const float* wt, const float* bias) {
+int build_deconv_s2d(vfi_ctx* c, TapConvLayer& L, int ch, int creal, int cout, const float* wt, const float* bias) {
   L = TapConvLayer{};
   L.cin = ch;
   L.n_total = 4 * cout;
@@ -342,7 +388,7 @@ int build_deconv_s2d(vfi_ctx* c, TapConvLayer& L, int ch, int cout, const float*
     const int dy = e / 3 - 1, dx = e % 3 - 1;
     const int sub = n / cout, oc = n % cout, a = sub >> 1, b = sub & 1;
     const int ky = a + 1 - 2 * dy, kx = b + 1 - 2 * dx;
-    if (ky < 0 || ky > 3 || kx < 0 || kx > 3) return 0.f;
+    if (ky < 0 || ky > 3 || kx < 0 || kx > 3 || ci >= creal) return 0.f;
     return wt[(((size_t)ci * cout + oc) * 4 + ky) * 4 + kx];
   };
   std::vector<uint16_t> pk = pack_weights(L, c->op_type, wf);
@@ -356,15 +402,16 @@ int build_deconv_s2d(vfi_ctx* c, TapConvLayer& L, int ch, int cout, const float*
 
 struct Geometry {
   int Hp, Wp;
-  int s[4];
+  int nb;  // blocks: 4, arch 4.26: 5
+  int s[kMaxBlocks];
 };
 
-int make_geometry(int H, int W, float scale_factor, Geometry* g) {
+int make_geometry(int arch, int H, int W, float scale_factor, Geometry* g) {
   g->Hp = ((H - 1) / 64 + 1) * 64;  // rife_arch.py:480-482
   g->Wp = ((W - 1) / 64 + 1) * 64;
-  const float base[4] = {8.f, 4.f, 2.f, 1.f};  // rife/__init__.py:157-160
-  for (int i = 0; i < 4; ++i) {
-    const float sf = base[i] / scale_factor;
+  g->nb = num_blocks(arch);
+  for (int i = 0; i < g->nb; ++i) {
+    const float sf = (float)(1 << (g->nb - 1 - i)) / scale_factor;  // [8,4,2,1] or [16,8,4,2,1] / scale_factor, rife/__init__.py:156-160
     const int si = (int)std::lround(sf);
     if (std::fabs(sf - (float)si) > 1e-6f || si < 1 || (si & (si - 1)))
       return fail(VFI_E_NOTIMPL, "scale_factor > 1 (up-scaled blocks) is not implemented; use 1.0, 0.5 or 0.25");
@@ -379,13 +426,14 @@ int make_geometry(int H, int W, float scale_factor, Geometry* g) {
 
 int ensure_workspace(vfi_ctx* c, const Geometry& g, int B, int n_frames_window) {
   size_t x = 0, c00 = 0, feat = 0;
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < g.nb; ++i) {
     const size_t Hs = g.Hp / g.s[i], Ws = g.Wp / g.s[i];
     x = std::max(x, (size_t)B * (Hs / 2) * (Ws / 2) * (c->arch != 46 ? 128 : 64) * 2);
     c00 = std::max(c00, (size_t)B * (Hs / 4) * (Ws / 4) * 2 * kBlockC[i] * 2);
     feat = std::max(feat, (size_t)B * (Hs / 4) * (Ws / 4) * kBlockC[i] * 2);
     CK(c->tF[i].ensure((size_t)B * Hs * Ws * sizeof(float4)));  // block output T_i (flow increments at 1/s_i)
     CK(c->tM[i].ensure((size_t)B * Hs * Ws * sizeof(float)));
+    if (c->arch == 426 && i + 1 < g.nb) CK(c->tE[i].ensure((size_t)B * Hs * Ws * 16));
   }
   const size_t px = (size_t)g.Hp * g.Wp;
   CK(c->imgs.ensure((size_t)n_frames_window * px * sizeof(float4)));
@@ -394,8 +442,9 @@ int ensure_workspace(vfi_ctx* c, const Geometry& g, int B, int n_frames_window) 
     CK(c->feats.ensure((size_t)n_frames_window * px * sizeof(float4)));
     CK(c->e16.ensure((size_t)(kMaxBatch + 2) * (px / 4) * 16 * sizeof(float)));
   }
-  if (c->arch == 417) {  // features: 8 x 16-bit per pixel (space-to-depth cells of 32); head scratch: 32 ch at 1/2 res
-    CK(c->feats.ensure((size_t)n_frames_window * px * 16));
+  if (c->arch == 417 || c->arch == 426) {
+    // features: 8 (4.26: 4) x 16-bit per pixel, space-to-depth cells of 32 (16) values; head scratch: 32 ch at 1/2 res
+    CK(c->feats.ensure((size_t)n_frames_window * px * (c->arch == 417 ? 16 : 8)));
     CK(c->hA.ensure((size_t)(kMaxBatch + 2) * (px / 4) * 32 * 2));
     CK(c->hB.ensure((size_t)(kMaxBatch + 2) * (px / 4) * 32 * 2));
   }
@@ -427,12 +476,13 @@ int run_encode(vfi_ctx* c, const Geometry& g, int f, int n, cudaStream_t st) {
   if (c->arch == 47) {
     LAUNCH(launch_encode(imgs, c->enc[0], c->enc[1], c->enc[2], c->enc[3], (float*)c->e16.p,
                          (float4*)c->feats.p + (size_t)f * px, n, g.Hp, g.Wp, st));
-  } else if (c->arch == 417) {
+  } else if (c->arch == 417 || c->arch == 426) {
     const int Hh = g.Hp / 2, Wh = g.Wp / 2;
+    const size_t fbytes = c->arch == 417 ? 16 : 8;  // feature bytes per full-resolution pixel
     LAUNCH(launch_head0(c->op_type, imgs, c->enc[0], c->enc[1], c->hA.p, n, g.Hp, g.Wp, st));
     LAUNCH(launch_tapconv(c->head[0], c->op_type, c->hA.p, c->hB.p, nullptr, nullptr, n, Hh, Wh, c->num_sms, false, st));
     LAUNCH(launch_tapconv(c->head[1], c->op_type, c->hB.p, c->hA.p, nullptr, nullptr, n, Hh, Wh, c->num_sms, false, st));
-    LAUNCH(launch_tapconv(c->head[2], c->op_type, c->hA.p, (uint8_t*)c->feats.p + (size_t)f * px * 16, nullptr, nullptr,
+    LAUNCH(launch_tapconv(c->head[2], c->op_type, c->hA.p, (uint8_t*)c->feats.p + (size_t)f * px * fbytes, nullptr, nullptr,
                           n, Hh, Wh, c->num_sms, false, st));
   }
   return VFI_OK;
@@ -445,29 +495,33 @@ int forward_pass(vfi_ctx* c, const Geometry& g, const BatchTasks& tasks, int H, 
   const uint2* imgs_h = (const uint2*)c->imgs_h.p;
   const void* feats = c->arch != 46 ? c->feats.p : nullptr;
   const int feat_ch = c->arch == 417 ? 8 : 4;
+  const int nb = g.nb;
   float4* F = (float4*)c->flow.p;  // accumulated full-resolution flow / mask, written only by "dense" fronts
   float* M = (float*)c->mask.p;
   FlowState fs{};
-  for (int i = 0; i < 4; ++i) {
+  fs.n = nb;
+  for (int i = 0; i < nb; ++i) {
     fs.f[i] = (float4*)c->tF[i].p;
     fs.m[i] = (float*)c->tM[i].p;
     fs.s[i] = g.s[i];
   }
   fs.mask_replace = (c->arch != 46) ? 1 : 0;
-  int dense = 4;  // first block whose front visits every full-resolution pixel (scale <= 2)
-  for (int i = 3; i >= 1; --i)
+  int dense = nb;  // first block whose front visits every full-resolution pixel (scale <= 2)
+  for (int i = nb - 1; i >= 1; --i)
     if (g.s[i] <= 2) dense = i;
   bool have_base = false;
   int lo = 0;  // levels [lo, i) are not yet folded into F
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < nb; ++i) {
     const int s = g.s[i];
     const int Hs = g.Hp / s, Ws = g.Wp / s;
+    const void* pfeat = (c->arch == 426 && i > 0) ? c->tE[i - 1].p : nullptr;  // previous block's 8 feature channels
+    const int ps = i > 0 ? g.s[i - 1] : 1;
     if (i == 0 || i < dense) {
-      LAUNCH(launch_front(c->op_type, imgs, imgs_h, feats, feat_ch, fs, i, 0, nullptr, nullptr, nullptr, nullptr, tasks, g.Hp, g.Wp, s,
-                          c->x.p, st));
+      LAUNCH(launch_front(c->op_type, c->arch, imgs, imgs_h, feats, feat_ch, pfeat, ps, fs, i, 0, nullptr, nullptr, nullptr,
+                          nullptr, tasks, g.Hp, g.Wp, s, c->x.p, st));
     } else {
-      LAUNCH(launch_front(c->op_type, imgs, imgs_h, feats, feat_ch, fs, i, lo, have_base ? F : nullptr, have_base ? M : nullptr, F, M, tasks,
-                          g.Hp, g.Wp, s, c->x.p, st));
+      LAUNCH(launch_front(c->op_type, c->arch, imgs, imgs_h, feats, feat_ch, pfeat, ps, fs, i, lo, have_base ? F : nullptr,
+                          have_base ? M : nullptr, F, M, tasks, g.Hp, g.Wp, s, c->x.p, st));
       have_base = true;
       lo = i;
     }
@@ -484,6 +538,9 @@ int forward_pass(vfi_ctx* c, const Geometry& g, const BatchTasks& tasks, int H, 
     }
     LAUNCH(launch_tapconv(c->layers[i][10], c->op_type, a, nullptr, fs.f[i], fs.m[i], B, Hs / 4, Ws / 4, c->num_sms,
                           false, st));
+    if (c->arch == 426 && i + 1 < nb)  // the 8 feature channels of lastconv, for the next block's input
+      LAUNCH(launch_tapconv(c->layers[i][11], c->op_type, a, c->tE[i].p, nullptr, nullptr, B, Hs / 4, Ws / 4, c->num_sms,
+                            false, st));
   }
   LAUNCH(launch_final(imgs, fs, lo, have_base ? F : nullptr, have_base ? M : nullptr, tasks, g.Hp, g.Wp, H, W, out, st));
   c->last_fs = fs;
@@ -507,7 +564,7 @@ int check_tasks(const int32_t* f0, const int32_t* f1, int n_tasks, int lo, int h
 extern "C" {
 
 const char* vfi_last_error(void) { return g_err.c_str(); }
-const char* vfi_version(void) { return "vfi_b200 0.1 (sm_100a; RIFE 4.6/4.7/4.17; built " __DATE__ " " __TIME__ ")"; }
+const char* vfi_version(void) { return "vfi_b200 0.1 (sm_100a; RIFE 4.6/4.7/4.17/4.26; built " __DATE__ " " __TIME__ ")"; }
 
 int vfi_create(int device, vfi_ctx** out) {
   if (!out) return fail(VFI_E_INVALID, "null out");
@@ -536,9 +593,10 @@ int vfi_destroy(vfi_ctx* c) {
   for (DevBuf* b : {&c->imgs, &c->imgs_h, &c->flow, &c->mask, &c->x, &c->c00, &c->featA, &c->featB, &c->raw, &c->outdev, &c->feats, &c->e16, &c->hA, &c->hB, &c->dbgF,
                     &c->dbgM})
     b->release();
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < kMaxBlocks; ++i) {
     c->tF[i].release();
     c->tM[i].release();
+    c->tE[i].release();
   }
   if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
   if (c->s_comp) cudaStreamDestroy(c->s_comp);
@@ -568,10 +626,13 @@ int vfi_rife46_load(vfi_ctx* c, const float* const* T, const int64_t* numel, int
 
 int vfi_rife_load(vfi_ctx* c, int arch, const float* const* T, const int64_t* numel, int n_tensors, int operand_type) {
   if (!c || !T || !numel) return fail(VFI_E_INVALID, "null argument");
-  if (arch != 46 && arch != 47 && arch != 417)
-    return fail(VFI_E_NOTIMPL, "RIFE arch must be 46 (rife46.pth), 47 (rife47/rife49.pth) or 417 (rife417.pth)");
-  if (n_tensors != (arch == 46 ? VFI_RIFE46_NUM_TENSORS : arch == 47 ? VFI_RIFE47_NUM_TENSORS : VFI_RIFE417_NUM_TENSORS))
-    return fail(VFI_E_INVALID, "wrong number of state_dict tensors for this RIFE arch (4.6: 120, 4.7: 124, 4.17: 128)");
+  if (arch != 46 && arch != 47 && arch != 417 && arch != 426)
+    return fail(VFI_E_NOTIMPL,
+                "RIFE arch must be 46 (rife46.pth), 47 (rife47/rife49.pth), 417 (rife417.pth) or 426 (rife426.pth)");
+  if (n_tensors != (arch == 46 ? VFI_RIFE46_NUM_TENSORS : arch == 47 ? VFI_RIFE47_NUM_TENSORS
+                    : arch == 417 ? VFI_RIFE417_NUM_TENSORS : VFI_RIFE426_NUM_TENSORS))
+    return fail(VFI_E_INVALID,
+                "wrong number of state_dict tensors for this RIFE arch (4.6: 120, 4.7: 124, 4.17: 128, 4.26: 158)");
   if (operand_type != OP_F16 && operand_type != OP_BF16) return fail(VFI_E_INVALID, "operand_type");
   CK(cudaSetDevice(c->device));
   free_weights(c);
@@ -579,8 +640,12 @@ int vfi_rife_load(vfi_ctx* c, int arch, const float* const* T, const int64_t* nu
   c->arch = arch;
   int k = 0;
   auto expect = [&](int idx, int64_t want) { return numel[idx] == want; };
-  for (int b = 0; b < 4; ++b) {
-    const int ch = kBlockC[b], cin = (arch == 417 ? kBlockCinReal417 : arch == 47 ? kBlockCinReal47 : kBlockCinReal)[b];
+  const int nb = num_blocks(arch);
+  const int nlast = arch == 426 ? 52 : 24;  // lastconv = ConvTranspose2d(c, 4*6 | 4*13, 4, 2, 1) - rife_arch.py:215-218, :230-233
+  for (int b = 0; b < nb; ++b) {
+    const int ch = kBlockC[b];
+    const int cin = (arch == 426 ? kBlockCinReal426 : arch == 417 ? kBlockCinReal417 : arch == 47 ? kBlockCinReal47
+                                                                                                  : kBlockCinReal)[b];
     if (!expect(k, (int64_t)(ch / 2) * cin * 9) || !expect(k + 1, ch / 2) || !expect(k + 2, (int64_t)ch * (ch / 2) * 9) ||
         !expect(k + 3, ch))
       return fail(VFI_E_INVALID, "conv0 tensor sizes do not match RIFE 4.6");
@@ -594,9 +659,10 @@ int vfi_rife_load(vfi_ctx* c, int arch, const float* const* T, const int64_t* nu
       if ((r = build_resconv(c, c->layers[b][2 + j], ch, T[k], T[k + 1], T[k + 2]))) return r;
       k += 3;
     }
-    if (!expect(k, (int64_t)ch * 24 * 16) || !expect(k + 1, 24))
-      return fail(VFI_E_INVALID, "lastconv tensor sizes do not match RIFE 4.6");
-    if ((r = build_lastconv(c, c->layers[b][10], ch, T[k], T[k + 1]))) return r;
+    if (!expect(k, (int64_t)ch * nlast * 16) || !expect(k + 1, nlast))
+      return fail(VFI_E_INVALID, "lastconv tensor sizes do not match this RIFE arch");
+    if ((r = build_lastconv(c, c->layers[b][10], ch, nlast, T[k], T[k + 1]))) return r;
+    if (arch == 426 && b + 1 < nb && (r = build_lastfeat(c, c->layers[b][11], ch, nlast, T[k], T[k + 1]))) return r;
     k += 2;
   }
   if (arch == 47) {  // encode = Conv2d(3,16,3,2,1) + ConvTranspose2d(16,4,4,2,1), fp32 on the CUDA cores
@@ -618,15 +684,35 @@ int vfi_rife_load(vfi_ctx* c, int arch, const float* const* T, const int64_t* nu
       std::vector<float> h(T[k + i], T[k + i] + want[i]);
       if ((r = upload(c, h, (void**)&c->enc[i]))) return r;
     }
-    if ((r = build_conv3x3_lrelu(c, c->head[0], 32, T[k + 2], T[k + 3]))) return r;
-    if ((r = build_conv3x3_lrelu(c, c->head[1], 32, T[k + 4], T[k + 5]))) return r;
-    if ((r = build_deconv_s2d(c, c->head[2], 32, 8, T[k + 6], T[k + 7]))) return r;
+    if ((r = build_conv3x3_lrelu(c, c->head[0], 32, 32, T[k + 2], T[k + 3]))) return r;
+    if ((r = build_conv3x3_lrelu(c, c->head[1], 32, 32, T[k + 4], T[k + 5]))) return r;
+    if ((r = build_deconv_s2d(c, c->head[2], 32, 32, 8, T[k + 6], T[k + 7]))) return r;
     for (int i = 0; i < 3; ++i)
       if (c->head[i].nsplit < 1) return fail(VFI_E_STATE, "a head layer has no shared-memory plan");
     k += 8;
   }
-  for (int b = 0; b < 4; ++b)
-    for (int l = 0; l < 11; ++l)
+  if (arch == 426) {
+    // encode = Head (rife_arch.py:378-395): the 16-channel layers run zero-padded to 32 channels - cnn0 on the CUDA
+    // cores (fp32 weights, outputs 16..31 have zero weights and bias), cnn1..cnn3 as tapconv layers; cnn3's 4 output
+    // channels x 2x2 sub-pixels = 16 columns = the space-to-depth form of the 4-channel feature map
+    const int64_t want[8] = {16 * 3 * 9, 16, 16 * 16 * 9, 16, 16 * 16 * 9, 16, 16 * 4 * 16, 4};
+    for (int i = 0; i < 8; ++i)
+      if (numel[k + i] != want[i]) return fail(VFI_E_INVALID, "encode tensor sizes do not match RIFE 4.26");
+    int r;
+    std::vector<float> w0(32 * 27, 0.f), b0(32, 0.f);
+    std::copy(T[k], T[k] + 16 * 27, w0.begin());
+    std::copy(T[k + 1], T[k + 1] + 16, b0.begin());
+    if ((r = upload(c, w0, (void**)&c->enc[0]))) return r;
+    if ((r = upload(c, b0, (void**)&c->enc[1]))) return r;
+    if ((r = build_conv3x3_lrelu(c, c->head[0], 32, 16, T[k + 2], T[k + 3]))) return r;
+    if ((r = build_conv3x3_lrelu(c, c->head[1], 32, 16, T[k + 4], T[k + 5]))) return r;
+    if ((r = build_deconv_s2d(c, c->head[2], 32, 16, 4, T[k + 6], T[k + 7]))) return r;
+    for (int i = 0; i < 3; ++i)
+      if (c->head[i].nsplit < 1) return fail(VFI_E_STATE, "a head layer has no shared-memory plan");
+    k += 8;
+  }
+  for (int b = 0; b < nb; ++b)
+    for (int l = 0; l < (arch == 426 && b + 1 < nb ? 12 : 11); ++l)
       if (c->layers[b][l].nsplit < 1) return fail(VFI_E_STATE, "a layer has no shared-memory plan");
   c->loaded = true;
   return VFI_OK;
@@ -642,7 +728,7 @@ int vfi_rife46_forward(vfi_ctx* c, const float* frames, int n_frames, int H, int
   if ((r = check_tasks(f0, f1, n_tasks, 0, n_frames))) return r;
   CK(cudaSetDevice(c->device));
   Geometry g;
-  if ((r = make_geometry(H, W, scale_factor, &g))) return r;
+  if ((r = make_geometry(c->arch, H, W, scale_factor, &g))) return r;
   int lo = n_frames, hi = 0;
   for (int i = 0; i < n_tasks; ++i) {
     lo = std::min(lo, std::min(f0[i], f1[i]));
@@ -687,7 +773,7 @@ int vfi_rife46_interpolate_host(vfi_ctx* c, const float* frames, int n_frames, i
       return fail(VFI_E_INVALID, "tasks must be ordered by frame index (as RIFE_VFI.vfi builds them)");
   CK(cudaSetDevice(c->device));
   Geometry g;
-  if ((r = make_geometry(H, W, scale_factor, &g))) return r;
+  if ((r = make_geometry(c->arch, H, W, scale_factor, &g))) return r;
   const int nf = frame_hi - frame_lo;
   const int B = std::min(c->batch, n_tasks);
   if ((r = ensure_workspace(c, g, B, nf))) return r;
@@ -832,8 +918,10 @@ int vfi_sepconv(vfi_ctx* c, const float* in, const float* ver, const float* hor,
 
 int vfi_rife46_debug_layer(vfi_ctx* c, int block, int layer, const void* in, void* out, void* out_mask, int B, int H,
                            int W, int impl, void* stream) {
-  if (!c || block < 0 || block > 3 || layer < 0 || layer > 10 || !in || !out) return fail(VFI_E_INVALID, "bad argument");
+  if (!c || block < 0 || layer < 0 || !in || !out) return fail(VFI_E_INVALID, "bad argument");
   if (!c->loaded) return fail(VFI_E_STATE, "vfi_rife46_load has not been called");
+  if (block >= num_blocks(c->arch) || layer > 11 || (layer == 11 && (c->arch != 426 || block + 1 >= num_blocks(c->arch))))
+    return fail(VFI_E_INVALID, "no such block / layer in the loaded arch");
   CK(cudaSetDevice(c->device));
   const TapConvLayer& L = c->layers[block][layer];
   if (layer == 10) {
@@ -870,8 +958,10 @@ int vfi_rife46_debug_state(vfi_ctx* c, float* flow4_out, float* mask_out, int ba
 
 int vfi_rife46_layer_plan(vfi_ctx* c, int block, int layer, int* stages, int* n_cta, int* nsplit, int* smem_bytes,
                           int64_t* macs_per_cell) {
-  if (!c || block < 0 || block > 3 || layer < 0 || layer > 10) return fail(VFI_E_INVALID, "bad argument");
+  if (!c || block < 0 || layer < 0) return fail(VFI_E_INVALID, "bad argument");
   if (!c->loaded) return fail(VFI_E_STATE, "vfi_rife46_load has not been called");
+  if (block >= num_blocks(c->arch) || layer > 11 || (layer == 11 && (c->arch != 426 || block + 1 >= num_blocks(c->arch))))
+    return fail(VFI_E_INVALID, "no such block / layer in the loaded arch");
   const TapConvLayer& L = c->layers[block][layer];
   TapConvParams p{};
   const int st = tapconv_plan(L, &p);

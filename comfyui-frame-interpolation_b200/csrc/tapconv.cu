@@ -53,11 +53,13 @@ static_assert(sizeof(Ctrl) <= kCtrlBytes, "control block");
 
 __device__ __forceinline__ size_t out_pixel_offset(const TapConvParams& p, int b, int gy, int gx) {
   // element offset of channel 0 of grid cell (b, gy, gx) in the output tensor
-  if (p.out_s2d) {
+  if (p.out_s2d == 1) {
     // space-to-depth store: the consumer is a stride-2 conv that reads [B, H/2, W/2, 4*n_total]
     size_t cell = ((size_t)b * (p.H >> 1) + (gy >> 1)) * (p.W >> 1) + (gx >> 1);
     return cell * (size_t)(4 * p.n_total) + (size_t)(((gy & 1) * 2 + (gx & 1)) * p.n_total);
   }
+  if (p.out_s2d == 2)  // patch form [B, 4H, 4W, 8]: element offset of sub-pixel (0, 0) of this cell's 4x4 patch
+    return (((size_t)b * (4 * p.H) + 4 * gy) * (size_t)(4 * p.W) + 4 * gx) * 8;
   return (((size_t)b * p.H + gy) * p.W + gx) * (size_t)p.n_total;
 }
 
@@ -414,7 +416,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
 
       // ---- conv0.x / ResConv: this thread owns one grid cell and all n_cta channels of it, two 16-channel chunks per
       // round (at most 32 accumulator values live per thread: 608 threads, 96 registers each)
-      T* orow = reinterpret_cast<T*>(p.out) + (valid ? out_pixel_offset(p, b, gy, gx) + (size_t)n0 : 0);
+      // (patch form, out_s2d == 2: columns are (sub-pixel, channel) pairs, placed per chunk in finish_chunk)
+      const bool patch = (p.out_s2d == 2);
+      T* orow = reinterpret_cast<T*>(p.out) + (valid ? out_pixel_offset(p, b, gy, gx) + (patch ? 0 : (size_t)n0) : 0);
       const uint4* gres = nullptr;  // ring layers: the centre pixel's channels in the input tensor (L2 hit)
       if (RING && residual)
         gres = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.in) +
@@ -457,6 +461,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
         // 32 contiguous bytes (16 channels) of this cell's channel vector; L2 merges the halves of a sector
         if (valid && (!ABLATE(1) || o[0] == 0x12345678u)) {
           uint4* dst = reinterpret_cast<uint4*>(orow + c * 16);
+          if (patch) {  // 16 columns = sub-pixels pos0, pos0 + 1 (same patch row, adjacent x) x 8 channels: 32 contiguous bytes
+            const int pos0 = (n0 + c * 16) >> 3;
+            dst = reinterpret_cast<uint4*>(orow + ((size_t)(pos0 >> 2) * (size_t)(4 * p.W) + (size_t)(pos0 & 3)) * 8);
+          }
           dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
           dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
         }
@@ -563,8 +571,12 @@ __global__ void tapconv_ref_kernel(const __grid_constant__ TapConvParams p) {
     } else {
       float v = acc + p.shift[n];
       if (p.epi_mode == EPI_RESCONV) v += ld16bit<T>(in + (((size_t)b * p.H + gy) * p.W + gx) * p.cin + n);
-      reinterpret_cast<T*>(p.out)[out_pixel_offset(p, b, gy, gx) + n] =
-          cvt16bit<T>(p.epi_mode == EPI_BIAS ? v : lrelu02(v));
+      size_t o = out_pixel_offset(p, b, gy, gx) + n;
+      if (p.out_s2d == 2) {
+        const int pos = n >> 3;
+        o = out_pixel_offset(p, b, gy, gx) + ((size_t)(pos >> 2) * (size_t)(4 * p.W) + (size_t)(pos & 3)) * 8 + (n & 7);
+      }
+      reinterpret_cast<T*>(p.out)[o] = cvt16bit<T>(p.epi_mode == EPI_BIAS ? v : lrelu02(v));
     }
   }
 }
@@ -715,7 +727,7 @@ cudaError_t launch_tapconv(const TapConvLayer& L, int op_type, const void* in, v
     set_error("tapconv: layer does not fit in shared memory");
     return cudaErrorInvalidConfiguration;
   }
-  if (L.out_s2d && ((H | W) & 1)) {
+  if (L.out_s2d == 1 && ((H | W) & 1)) {
     set_error("tapconv: space-to-depth output needs even H and W");
     return cudaErrorInvalidValue;
   }

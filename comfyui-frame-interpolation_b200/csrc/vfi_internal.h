@@ -39,7 +39,8 @@ struct alignas(64) TapConvParams {
   CUtensorMap tm64;      // input as a {C, W, H, B} tensor with a {64 ch, halo_w, halo_h, 1} box, SWIZZLE_128B
   CUtensorMap tm32;      // same with a {32 ch, ...} box, SWIZZLE_64B (only used when cin % 64 == 32)
   const void* in;        // [B, H, W, cin] 16-bit, NHWC
-  void* out;             // [B, H, W, n_total] 16-bit NHWC, or its space-to-depth form when out_s2d
+  void* out;             // [B, H, W, n_total] 16-bit NHWC; out_s2d = 1: its space-to-depth form; out_s2d = 2: the 4x4
+                         // sub-pixel patch form [B, 4H, 4W, 8] with column n = (py*4 + px)*8 + ch (arch 4.26 lastconv features)
   float4* out_flow;      // EPI_LASTCONV: [B, 4H, 4W] float4 (4 flow components)
   float* out_mask;       // EPI_LASTCONV: [B, 4H, 4W]
   const void* w;         // packed weights: [nsplit][ceil(K16/4)][n_cta][128 B swizzled row] 16-bit
@@ -105,21 +106,26 @@ int tapconv_plan(const TapConvLayer& L, TapConvParams* p_out);
 cudaError_t launch_prep_frames(const float* frames, int n, int H, int W, int cstride, float4* imgs, uint2* imgs_h,
                                int Hp, int Wp, cudaStream_t st);
 // low-resolution outputs of the blocks executed so far (the accumulated full-resolution flow is implicit)
+constexpr int kMaxBlocks = 5;  // arch 4.26 has five IFBlocks, the others four
 struct FlowState {
-  float4* f[4];
-  float* m[4];
-  int s[4];
-  int mask_replace;  // arch 4.7: mask = newest level only
+  float4* f[kMaxBlocks];
+  float* m[kMaxBlocks];
+  int s[kMaxBlocks];
+  int n;             // number of blocks
+  int mask_replace;  // arch 4.7+: mask = newest level only
 };
 cudaError_t launch_encode(const float4* imgs, const float* w0, const float* b0, const float* w1, const float* b1,
                           float* e16, float4* feats, int n, int Hp, int Wp, cudaStream_t st);
 cudaError_t launch_head0(int op_type, const float4* imgs, const float* w, const float* bias, void* out, int n, int Hp,
                          int Wp, cudaStream_t st);
-// feats: arch 4.7 float4 planes (feat_ch 4), arch 4.17 16-bit space-to-depth planes (feat_ch 8), or nullptr (4.6)
-cudaError_t launch_front(int op_type, const float4* imgs, const uint2* imgs_h, const void* feats, int feat_ch,
-                         const FlowState& fs, int blk, int lo,
+// feats: arch 4.7 float4 planes (feat_ch 4), arch 4.17 16-bit space-to-depth planes (feat_ch 8), arch 4.26 16-bit
+// space-to-depth planes of 4 channels (feat_ch 4, arch 426), or nullptr (4.6).  prev_feat: arch 4.26, blocks > 0: the
+// previous block's 8 lastconv feature channels [B, Hp/prev_s, Wp/prev_s, 8] 16-bit.
+cudaError_t launch_front(int op_type, int arch, const float4* imgs, const uint2* imgs_h, const void* feats, int feat_ch,
+                         const void* prev_feat, int prev_s, const FlowState& fs, int blk, int lo,
                          const float4* base_f, const float* base_m, float4* out_f, float* out_m, BatchTasks tasks,
                          int Hp, int Wp, int s, void* x_s2d, cudaStream_t st);
+// (launch_materialize / launch_final add levels [lo, fs.n) to the base)
 cudaError_t launch_materialize(const FlowState& fs, int lo, const float4* base_f, const float* base_m, float4* flow,
                                float* mask, int B, int Hp, int Wp, cudaStream_t st);
 cudaError_t launch_final(const float4* imgs, const FlowState& fs, int lo, const float4* base_f, const float* base_m,

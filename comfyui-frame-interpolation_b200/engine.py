@@ -17,7 +17,7 @@ BLOCK_C = (192, 128, 96, 64)
 
 def state_dict_names(arch: str = "4.6"):
     names = []
-    for b in range(4):
+    for b in range(5 if arch == "4.26" else 4):  # rife_arch.py:453-459: arch 4.26 has block0..block4
         p = f"block{b}."
         names += [p + "conv0.0.0.weight", p + "conv0.0.0.bias", p + "conv0.1.0.weight", p + "conv0.1.0.bias"]
         for j in range(8):
@@ -26,12 +26,12 @@ def state_dict_names(arch: str = "4.6"):
         names += [p + "lastconv.0.weight", p + "lastconv.0.bias"]
     if arch == "4.7":
         names += ["encode.0.weight", "encode.0.bias", "encode.1.weight", "encode.1.bias"]
-    if arch == "4.17":  # Head_417 - rife_arch.py:356-363
+    if arch in ("4.17", "4.26"):  # Head_417 - rife_arch.py:356-363; Head - rife_arch.py:378-385
         names += [f"encode.cnn{i}.{k}" for i in range(4) for k in ("weight", "bias")]
     return names
 
 
-ARCH_CODE = {"4.6": 46, "4.7": 47, "4.17": 417}
+ARCH_CODE = {"4.6": 46, "4.7": 47, "4.17": 417, "4.26": 426}
 
 
 def _i32(a):
@@ -39,7 +39,7 @@ def _i32(a):
 
 
 class Rife46Engine:
-    """RIFE 4.6 / 4.7 / 4.17 (rife46.pth; rife47.pth, rife49.pth; rife417.pth) on one B200.  `state_dict` maps the reference's parameter names to tensors (any float dtype)."""
+    """RIFE 4.6 / 4.7 / 4.17 / 4.26 (rife46.pth; rife47.pth, rife49.pth; rife417.pth; rife426.pth) on one B200.  `state_dict` maps the reference's parameter names to tensors (any float dtype)."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], device: int = 0, dtype: str = "float32", batch: int = 8,
                  arch: str = None):
@@ -52,10 +52,11 @@ class Rife46Engine:
         self._ctx = C.c_void_p()
         check(self._L.vfi_create(self.device, C.byref(self._ctx)))
         if arch is None:  # the 4.7 family (rife47.pth / rife49.pth) has the encode head, rife417.pth the Head_417 one
-            arch = ("4.17" if "encode.cnn0.weight" in state_dict else
+            arch = ("4.26" if "block4.conv0.0.0.weight" in state_dict else
+                    "4.17" if "encode.cnn0.weight" in state_dict else
                     "4.7" if "encode.0.weight" in state_dict else "4.6")
         if arch not in ARCH_CODE:
-            raise VfiError(f"RIFE arch {arch} is not built (4.6, 4.7 and 4.17 are)")
+            raise VfiError(f"RIFE arch {arch} is not built (4.6, 4.7, 4.17 and 4.26 are)")
         self.arch = arch
         names = state_dict_names(arch)
         missing = [n for n in names if n not in state_dict]

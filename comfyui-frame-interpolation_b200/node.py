@@ -16,13 +16,14 @@ from .engine import Rife46Engine
 
 MODEL_TYPE = "rife"
 # The reference table (rife/__init__.py:10-20) has no 4.6 entry at this commit although IFNet supports it and
-# GMFSS uses rife46.pth; this node adds it.  Built archs: 4.6 and 4.7 (rife47/rife49, the reference's
-# default); 4.17 / 4.26 / 4.0 are the next scope rows.
+# GMFSS uses rife46.pth; this node adds it.  Built archs: 4.6, 4.7 (rife47/rife49, the reference's
+# default), 4.17 and 4.26; arch 4.0 (sudo_rife4, with contextnet/unet) is not built and raises KeyError here.
 CKPT_NAME_VER_DICT = {
     "rife46.pth": "4.6",
     "rife47.pth": "4.7",
     "rife49.pth": "4.7",
     "rife417.pth": "4.17",
+    "rife426.pth": "4.26",
 }
 DTYPE_OPTIONS = ["float32", "float16", "bfloat16"]
 DTYPE_MAP = {"float32": torch.float32, "float16": torch.float16, "bfloat16": torch.bfloat16}

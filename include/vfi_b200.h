@@ -33,6 +33,7 @@ extern "C" {
 #define VFI_RIFE46_NUM_TENSORS 120   /* IFNet("4.6").state_dict() - rife_arch.py:404-408 */
 #define VFI_RIFE47_NUM_TENSORS 124   /* IFNet("4.7"): + encode.{0,1}.{weight,bias} - rife_arch.py:409-417 */
 #define VFI_RIFE417_NUM_TENSORS 128  /* + encode.cnn0..cnn3 weight, bias (Head_417, rife_arch.py:356-363) */
+#define VFI_RIFE426_NUM_TENSORS 158  /* IFNet("4.26"): 5 blocks x 30 + Head cnn0..cnn3 weight, bias (rife_arch.py:453-459) */
 #define VFI_MAX_BATCH 16
 
 typedef struct vfi_ctx vfi_ctx;
@@ -54,8 +55,8 @@ int vfi_set_batch(vfi_ctx* ctx, int batch);
  * .bias, 8 x convblock.{j}.{beta, conv.weight, conv.bias}, lastconv.0.weight, .bias; b = 0..3); `numel[i]` is
  * checked against the architecture.  Weights are repacked to the tensor-core operand layout on the device. */
 int vfi_rife46_load(vfi_ctx* ctx, const float* const* tensors, const int64_t* numel, int n_tensors, int operand_type);
-/* Same for any built arch: 46 (rife46.pth), 47 (rife47.pth / rife49.pth) or 417 (rife417.pth; CKPT_NAME_VER_DICT
- * rife/__init__.py:10-13;
+/* Same for any built arch: 46 (rife46.pth), 47 (rife47.pth / rife49.pth), 417 (rife417.pth) or 426 (rife426.pth: five
+ * blocks, scale list [16,8,4,2,1]/scale_factor, rife/__init__.py:156-158; CKPT_NAME_VER_DICT rife/__init__.py:10-14;
  * state_dict order = blocks 0..3 then encode.0.weight, encode.0.bias, encode.1.weight, encode.1.bias).  The
  * vfi_rife46_forward / _interpolate_host entry points below run whichever arch was loaded. */
 int vfi_rife_load(vfi_ctx* ctx, int arch, const float* const* tensors, const int64_t* numel, int n_tensors,
@@ -105,8 +106,9 @@ int vfi_sepconv(vfi_ctx* ctx, const float* in, const float* ver, const float* ho
                 int W, int Kv, int Kh, void* stream);
 
 /* Test / profiling hooks (used by tests/ and bench.py only) --------------------------------------------- */
-/* Run ONE convolution layer of block `block` (0..3): layer 0 = conv0.0, 1 = conv0.1, 2..9 = ResConv 0..7,
- * 10 = lastconv.  `in`/`out` are device tensors in the kernel-native layouts documented in DESIGN.md
+/* Run ONE convolution layer of block `block` (0..3; arch 4.26: 0..4): layer 0 = conv0.0, 1 = conv0.1, 2..9 = ResConv
+ * 0..7, 10 = lastconv (flow + mask), 11 = arch 4.26 blocks 0..3: the 8 feature channels of lastconv, written as
+ * [B, 4H, 4W, 8] 16-bit.  `in`/`out` are device tensors in the kernel-native layouts documented in DESIGN.md
  * (16-bit NHWC; layers 0/1 read space-to-depth inputs; layer 10 writes float4 flow + float mask planes).
  * impl 0 = tcgen05 kernel, 1 = CUDA-core checker with the same packed weights. */
 int vfi_rife46_debug_layer(vfi_ctx* ctx, int block, int layer, const void* in, void* out, void* out_mask, int B, int H,

@@ -35,7 +35,13 @@ LRELU_SLOPE = 0.2  # rife_arch.py:106 / :26
 BLOCK_SPECS_47: Tuple[Tuple[int, int], ...] = ((7 + 8, 192), (8 + 4 + 8, 128), (8 + 4 + 8, 96), (8 + 4 + 8, 64))
 # arch 4.17 (rife417.pth): + Head_417 features, 8 channels per frame -- rife_arch.py:417-421, :356-375
 BLOCK_SPECS_417: Tuple[Tuple[int, int], ...] = ((7 + 16, 192), (8 + 4 + 16, 128), (8 + 4 + 16, 96), (8 + 4 + 16, 64))
-_BLOCKS = {"4.6": BLOCK_SPECS, "4.7": BLOCK_SPECS_47, "4.17": BLOCK_SPECS_417}
+# arch 4.26 (rife426.pth): five blocks; inputs carry the 4-channel Head features of both frames (block 0) plus, from
+# block 1 on, the previous block's 8 feature channels; lastconv has 13 = 4 flow + mask + 8 feature channels
+# -- rife_arch.py:453-459, :226-233
+BLOCK_SPECS_426: Tuple[Tuple[int, int], ...] = ((7 + 8, 192), (8 + 4 + 8 + 8, 128), (8 + 4 + 8 + 8, 96),
+                                                (8 + 4 + 8 + 8, 64), (8 + 4 + 8 + 8, 32))
+_BLOCKS = {"4.6": BLOCK_SPECS, "4.7": BLOCK_SPECS_47, "4.17": BLOCK_SPECS_417, "4.26": BLOCK_SPECS_426}
+SCALE_LIST = {"4.6": (8, 4, 2, 1), "4.7": (8, 4, 2, 1), "4.17": (8, 4, 2, 1), "4.26": (16, 8, 4, 2, 1)}
 
 
 def state_dict_spec(arch: str = "4.6") -> List[Tuple[str, Tuple[int, ...]]]:
@@ -53,7 +59,8 @@ def state_dict_spec(arch: str = "4.6") -> List[Tuple[str, Tuple[int, ...]]]:
         for j in range(8):
             q = p + f"convblock.{j}."
             spec += [(q + "beta", (1, c, 1, 1)), (q + "conv.weight", (c, c, 3, 3)), (q + "conv.bias", (c,))]
-        spec += [(p + "lastconv.0.weight", (c, 24, 4, 4)), (p + "lastconv.0.bias", (24,))]
+        nlast = 4 * 13 if arch == "4.26" else 4 * 6  # rife_arch.py:215-218 / :230-233
+        spec += [(p + "lastconv.0.weight", (c, nlast, 4, 4)), (p + "lastconv.0.bias", (nlast,))]
     if arch == "4.7":  # encode = Sequential(Conv2d(3,16,3,2,1), ConvTranspose2d(16,4,4,2,1)) -- rife_arch.py:414-416
         spec += [("encode.0.weight", (16, 3, 3, 3)), ("encode.0.bias", (16,)),
                  ("encode.1.weight", (16, 4, 4, 4)), ("encode.1.bias", (4,))]
@@ -62,6 +69,11 @@ def state_dict_spec(arch: str = "4.6") -> List[Tuple[str, Tuple[int, ...]]]:
                  ("encode.cnn1.weight", (32, 32, 3, 3)), ("encode.cnn1.bias", (32,)),
                  ("encode.cnn2.weight", (32, 32, 3, 3)), ("encode.cnn2.bias", (32,)),
                  ("encode.cnn3.weight", (32, 8, 4, 4)), ("encode.cnn3.bias", (8,))]
+    if arch == "4.26":  # encode = Head: cnn0 3->16 s2, cnn1/cnn2 16->16, cnn3 ConvT 16->4 -- rife_arch.py:378-385
+        spec += [("encode.cnn0.weight", (16, 3, 3, 3)), ("encode.cnn0.bias", (16,)),
+                 ("encode.cnn1.weight", (16, 16, 3, 3)), ("encode.cnn1.bias", (16,)),
+                 ("encode.cnn2.weight", (16, 16, 3, 3)), ("encode.cnn2.bias", (16,)),
+                 ("encode.cnn3.weight", (16, 4, 4, 4)), ("encode.cnn3.bias", (4,))]
     return spec
 
 
@@ -161,6 +173,8 @@ def ifblock(sd: Dict[str, torch.Tensor], b: int, x: torch.Tensor, flow: Optional
     if taps is not None:
         taps[f"b{b}.tmp"] = tmp
     tmp = F.interpolate(tmp, scale_factor=scale, mode="bilinear", align_corners=False)
+    if tmp.shape[1] == 13:  # arch 4.26: flow, mask, 8 feature channels for the next block -- rife_arch.py:267-274
+        return tmp[:, :4] * scale, tmp[:, 4:5], tmp[:, 5:]
     return tmp[:, :4] * scale, tmp[:, 4:5]
 
 
@@ -251,8 +265,58 @@ def ifnet47_forward(sd: Dict[str, torch.Tensor], img0: torch.Tensor, img1: torch
     return merged[:, :, :h, :w]
 
 
-def ifnet_forward(arch: str, sd, img0, img1, timestep, scale_list=(8, 4, 2, 1), taps=None):
-    return (ifnet46_forward if arch == "4.6" else ifnet47_forward)(sd, img0, img1, timestep, scale_list, taps)
+def ifnet426_forward(sd: Dict[str, torch.Tensor], img0: torch.Tensor, img1: torch.Tensor, timestep: torch.Tensor,
+                     scale_list: Sequence[float] = (16, 8, 4, 2, 1), taps: Optional[dict] = None) -> torch.Tensor:
+    """IFNet.forward restricted to arch 4.26 (rife426.pth; the node forces ensemble=False, rife/__init__.py:123-125)
+    -- rife_arch.py:465-732.
+
+    Five blocks at scales 16..1 (:508-511; still padded to x64 only, :480-482).  f0/f1 = Head(img) (cnn0 3->16 stride 2,
+    cnn1, cnn2 16->16, each + LeakyReLU(0.2), cnn3 ConvTranspose 16->4; :378-395).  Block 0 sees cat(img0, img1, f0, f1, t)
+    (:521-526); block i > 0 sees cat(warped0, warped1, warp(f0), warp(f1), t, mask, feat) + flow, where `feat` is the
+    previous block's 8 extra lastconv channels up-scaled to full resolution (:563-587); `flow += fd`, `mask = m0`
+    REPLACED (:586-587); blend with sigmoid of the last mask (:707-711)."""
+    img0 = torch.clamp(img0, 0, 1)
+    img1 = torch.clamp(img1, 0, 1)
+    n, c, h, w = img0.shape
+    ph = ((h - 1) // 64 + 1) * 64
+    pw = ((w - 1) // 64 + 1) * 64
+    img0 = F.pad(img0, (0, pw - w, 0, ph - h))
+    img1 = F.pad(img1, (0, pw - w, 0, ph - h))
+    t = timestep.reshape(n, 1, 1, 1).to(img0.dtype).repeat(1, 1, ph, pw)
+
+    def encode(x):  # Head.forward, feat=False -- rife_arch.py:387-395
+        y = F.leaky_relu(F.conv2d(x, sd["encode.cnn0.weight"], sd["encode.cnn0.bias"], stride=2, padding=1), 0.2)
+        y = F.leaky_relu(F.conv2d(y, sd["encode.cnn1.weight"], sd["encode.cnn1.bias"], padding=1), 0.2)
+        y = F.leaky_relu(F.conv2d(y, sd["encode.cnn2.weight"], sd["encode.cnn2.bias"], padding=1), 0.2)
+        return F.conv_transpose2d(y, sd["encode.cnn3.weight"], sd["encode.cnn3.bias"], stride=2, padding=1)
+
+    f0, f1 = encode(img0), encode(img1)
+    if taps is not None:
+        taps["f0"], taps["f1"] = f0, f1
+    w0, w1, flow, mask, feat = img0, img1, None, None, None
+    for i in range(5):
+        if flow is None:
+            flow, mask, feat = ifblock(sd, i, torch.cat((img0, img1, f0, f1, t), 1), None, scale_list[i], taps)
+        else:
+            x = torch.cat((w0, w1, warp(f0, flow[:, :2]), warp(f1, flow[:, 2:4]), t, mask, feat), 1)
+            fd, m0, feat = ifblock(sd, i, x, flow, scale_list[i], taps)
+            flow = flow + fd
+            mask = m0
+        if taps is not None:
+            taps[f"flow{i}"] = flow
+            taps[f"mask{i}"] = mask
+        w0 = warp(img0, flow[:, :2])
+        w1 = warp(img1, flow[:, 2:4])
+    m = torch.sigmoid(mask)
+    merged = w0 * m + w1 * (1 - m)
+    return merged[:, :, :h, :w]
+
+
+def ifnet_forward(arch: str, sd, img0, img1, timestep, scale_list=None, taps=None):
+    if scale_list is None:
+        scale_list = SCALE_LIST[arch]
+    fn = ifnet46_forward if arch == "4.6" else ifnet426_forward if arch == "4.26" else ifnet47_forward
+    return fn(sd, img0, img1, timestep, scale_list, taps)
 
 
 # --------------------------------------------------------------------------------------
@@ -293,7 +357,7 @@ def rife_vfi(sd: Dict[str, torch.Tensor], frames: torch.Tensor, multiplier=2, sc
     """
     fr = frames[..., :3].permute(0, 3, 1, 2)
     tasks, _ = build_tasks(len(fr), multiplier, states)
-    scale_list = [8 / scale_factor, 4 / scale_factor, 2 / scale_factor, 1 / scale_factor]
+    scale_list = [s / scale_factor for s in SCALE_LIST[arch]]  # rife/__init__.py:156-160
     results: Dict[int, List[torch.Tensor]] = {i: [] for i in range(len(fr) - 1)}
     with torch.inference_mode():
         pos = 0

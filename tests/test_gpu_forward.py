@@ -43,7 +43,7 @@ def test_ifnet_golden(pkg, name, dtype):
     assert p >= PSNR_MIN
 
 
-@pytest.mark.parametrize("arch", ["4.6", "4.7", "4.17"])
+@pytest.mark.parametrize("arch", ["4.6", "4.7", "4.17", "4.26"])
 def test_flow_and_mask_match_oracle(pkg, arch):
     """Intermediate state: final full-resolution flow / mask vs the oracle's (fp32)."""
     sd = O.synthetic_state_dict(0, arch=arch)
@@ -55,8 +55,9 @@ def test_flow_and_mask_match_oracle(pkg, arch):
     O.ifnet_forward(arch, sd, fr[0:1].permute(0, 3, 1, 2), fr[1:2].permute(0, 3, 1, 2),
                     torch.tensor([0.5]).view(1, 1, 1, 1), taps=taps)
     eng.close()
-    f_ref = taps["flow3"].permute(0, 2, 3, 1)
-    m_ref = taps["mask3"][:, 0]
+    last = len(O.SCALE_LIST[arch]) - 1
+    f_ref = taps[f"flow{last}"].permute(0, 2, 3, 1)
+    m_ref = taps[f"mask{last}"][:, 0]
     ef = (flow.cpu() - f_ref).abs().max().item()
     em = (mask.cpu() - m_ref).abs().max().item()
     print(f"max |flow err| {ef:.4f} px (max |flow| {f_ref.abs().max():.2f}), max |mask err| {em:.4f}")
@@ -76,6 +77,20 @@ def test_scale_factor(pkg, scale_factor, h, w):
                             torch.tensor([0.5]).view(1, 1, 1, 1), scale_list=sl).clamp(0, 1).permute(0, 2, 3, 1)
     p = O.psnr(out, ref)
     print(f"scale_factor {scale_factor}: PSNR {p:.2f} dB")
+    assert p >= PSNR_MIN
+
+
+def test_scale_factor_426(pkg):
+    """arch 4.26 at scale_factor 0.5: block scales 32,16,8,4,2 - the last front adds four coarser levels."""
+    sd = O.synthetic_state_dict(26, arch="4.26")
+    fr = O.synthetic_clip(2, 128, 256, seed=27)
+    eng = _engine(pkg, sd)
+    out = eng.forward(fr.cuda(), [0], [1], [0.4], scale_factor=0.5).cpu()
+    eng.close()
+    ref = O.ifnet426_forward(sd, fr[0:1].permute(0, 3, 1, 2), fr[1:2].permute(0, 3, 1, 2),
+                             torch.tensor([0.4]).view(1, 1, 1, 1), scale_list=[32, 16, 8, 4, 2])
+    p = O.psnr(out, ref.clamp(0, 1).permute(0, 2, 3, 1))
+    print(f"arch 4.26 scale_factor 0.5: PSNR {p:.2f} dB")
     assert p >= PSNR_MIN
 
 

@@ -146,3 +146,89 @@ def test_layer_plans(engines):
         for l in range(11):
             pl = eng.layer_plan(b, l)
             assert pl["stages"] >= 1 and pl["smem_bytes"] <= 232448, (b, l, pl)
+
+
+# ---- arch 4.26 (rife426.pth): the fifth block (c = 32: a single 32-channel k-block), the 52-channel lastconv split in
+# ---- its flow + mask part (layer 10) and its 8 feature channels (layer 11, [B, 4H, 4W, 8] 16-bit), every block width
+BLOCK_C426 = (192, 128, 96, 64, 32)
+
+
+@pytest.fixture(scope="module")
+def engines426(pkg):
+    from cfi_b200.engine import Rife46Engine
+    sd = O.synthetic_state_dict(17, arch="4.26")
+    e = {"float16": Rife46Engine(sd, 0, "float16"), "bfloat16": Rife46Engine(sd, 0, "bfloat16")}
+    yield sd, e
+    for v in e.values():
+        v.close()
+
+
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+@pytest.mark.parametrize("impl", IMPLS)
+def test_block4_resconv_and_conv0(engines426, dtype, impl):
+    if impl == 1 and dtype != "float16":
+        pytest.skip("CUDA-core checker: one dtype is enough")
+    sd, e = engines426
+    eng, c, tdt = e[dtype], 32, _tdt(dtype)
+    g = torch.Generator().manual_seed(77)
+    x = (0.5 * torch.randn(2, 37, 29, c, generator=g)).to(tdt)
+    q = "block4.convblock.2."
+    out = torch.empty_like(x, device="cuda")
+    eng.debug_layer(4, 2 + 2, x.cuda(), out, impl=impl)
+    ref = nhwc(O.resconv(nchw(x.float()), _rw(sd, q + "conv.weight", dtype), sd[q + "conv.bias"], sd[q + "beta"]))
+    assert rel_err(out.cpu().float(), ref) < _tol(dtype)
+    # conv0.0 (28 real of 32 channels -> 16) and conv0.1 (16 -> 32), both stride 2 on space-to-depth inputs
+    hs, ws = 40, 56
+    xi = torch.zeros(2, hs, ws, 32)
+    xi[..., :28] = torch.randn(2, hs, ws, 28, generator=g)
+    xi = xi.to(tdt)
+    y0 = torch.empty(2, hs // 4, ws // 4, 4 * 16, dtype=tdt, device="cuda")
+    eng.debug_layer(4, 0, s2d(xi).cuda(), y0, impl=impl)
+    ref0 = nhwc(O.conv_lrelu(nchw(xi[..., :28].float()), _rw(sd, "block4.conv0.0.0.weight", dtype),
+                             sd["block4.conv0.0.0.bias"], 2))
+    assert rel_err(un_s2d(y0.cpu(), 16).float(), ref0) < _tol(dtype)
+    x1 = ref0.to(tdt)
+    y1 = torch.empty(2, hs // 4, ws // 4, 32, dtype=tdt, device="cuda")
+    eng.debug_layer(4, 1, s2d(x1).cuda(), y1, impl=impl)
+    ref1 = nhwc(O.conv_lrelu(nchw(x1.float()), _rw(sd, "block4.conv0.1.0.weight", dtype), sd["block4.conv0.1.0.bias"], 2))
+    assert rel_err(y1.cpu().float(), ref1) < _tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+@pytest.mark.parametrize("block", [4, 3, 2, 1, 0])
+@pytest.mark.parametrize("impl", IMPLS)
+def test_lastconv426(engines426, block, dtype, impl):
+    """ConvTranspose2d(c,52,4,2,1)+PixelShuffle(2): channels 0-4 (flow, mask) as fp32 planes, 5-12 (features) as a
+    16-bit [B,4H,4W,8] tensor from a second tap conv over the same input."""
+    if impl == 1 and dtype != "float16":
+        pytest.skip("CUDA-core checker: one dtype is enough")
+    sd, e = engines426
+    eng, c, tdt = e[dtype], BLOCK_C426[block], _tdt(dtype)
+    g = torch.Generator().manual_seed(120 + block)
+    x = (0.5 * torch.randn(2, 19, 13, c, generator=g)).to(tdt)
+    p = f"block{block}."
+    tmp = F.pixel_shuffle(F.conv_transpose2d(nchw(x.float()), _rw(sd, p + "lastconv.0.weight", dtype),
+                                             sd[p + "lastconv.0.bias"], stride=2, padding=1), 2)
+    assert tmp.shape[1] == 13
+    flow = torch.full((2, 76, 52, 4), float("nan"), device="cuda")
+    mask = torch.full((2, 76, 52), float("nan"), device="cuda")
+    eng.debug_layer(block, 10, x.cuda(), flow, out_mask=mask, impl=impl)
+    assert rel_err(flow.cpu(), nhwc(tmp[:, :4])) < 1e-4
+    assert rel_err(mask.cpu(), tmp[:, 4]) < 1e-4
+    if block < 4:  # the last block's features are never used (rife_arch.py:563-587): no such layer
+        feat = torch.full((2, 76, 52, 8), float("nan"), dtype=tdt, device="cuda")
+        eng.debug_layer(block, 11, x.cuda(), feat, impl=impl)
+        assert rel_err(feat.cpu().float(), nhwc(tmp[:, 5:])) < _tol(dtype)
+    else:
+        from cfi_b200._lib import VfiError
+        with pytest.raises(VfiError):
+            eng.debug_layer(block, 11, x.cuda(), torch.empty(2, 76, 52, 8, dtype=tdt, device="cuda"), impl=impl)
+
+
+def test_layer_plans426(engines426):
+    sd, e = engines426
+    eng = e["float16"]
+    for b in range(5):
+        for l in range(12 if b < 4 else 11):
+            pl = eng.layer_plan(b, l)
+            assert pl["stages"] >= 1 and pl["smem_bytes"] <= 232448, (b, l, pl)

@@ -66,6 +66,12 @@ def cases():
                                       clip_seed=23),
         "node417_m3": dict(kind="node", arch="4.17", ckpt="rife417.pth", seed=24, gain=1.0, n=3, h=56, w=88, c=3,
                            multiplier=3, states=None, clip_seed=25),
+        # arch 4.26 (rife426.pth): five blocks (scales 16..1), Head encoder, 13-channel lastconv with feature feedback
+        "ifnet426_96x160": dict(kind="ifnet", arch="4.26", seed=30, gain=1.0, h=96, w=160, ts=(0.5, 0.35), clip_seed=31),
+        "ifnet426_128x128_gain3": dict(kind="ifnet", arch="4.26", seed=32, gain=3.0, h=128, w=128, ts=(0.75,),
+                                       clip_seed=33),
+        "node426_m2": dict(kind="node", arch="4.26", ckpt="rife426.pth", seed=34, gain=1.0, n=3, h=56, w=88, c=3,
+                           multiplier=2, states=None, clip_seed=35),
         # node level: keep-list (is_skip_list False)
         "node_keep": dict(kind="node", seed=4, gain=1.0, n=4, h=48, w=80, c=3, multiplier=2,
                           states=([0, 2], False), clip_seed=15),
@@ -118,7 +124,10 @@ def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
     R.CKPT_NAME_VER_DICT["rife46.pth"] = "4.6"
+    only = set(sys.argv[1:])  # optional: regenerate only the named cases
     for name, cfg in cases().items():
+        if only and name not in only:
+            continue
         arch = cfg.get("arch", "4.6")
         sd = O.synthetic_state_dict(cfg["seed"], cfg["gain"], arch=arch)
         fr = make_inputs(cfg)
@@ -129,7 +138,7 @@ def main():
             ts = torch.tensor(cfg["ts"], dtype=torch.float32).view(-1, 1, 1, 1)
             b = len(cfg["ts"])
             with torch.inference_mode():
-                out = m(x[0:1].repeat(b, 1, 1, 1), x[1:2].repeat(b, 1, 1, 1), ts, [8, 4, 2, 1], False, False)
+                out = m(x[0:1].repeat(b, 1, 1, 1), x[1:2].repeat(b, 1, 1, 1), ts, list(O.SCALE_LIST[arch]), False, False)
             np.savez_compressed(os.path.join(out_dir, name + ".npz"), out=out.numpy())
         else:
             with tempfile.TemporaryDirectory() as td:
@@ -147,6 +156,8 @@ def main():
         print(name, tuple(out.shape), float(out.mean()))
     import vfi_utils as VU
     for name, cfg in loop_cases().items():
+        if only and name not in only:
+            continue
         st = None if cfg["states"] is None else InterpolationStateList(list(cfg["states"][0]), cfg["states"][1])
         out = VU.generic_frame_loop("Stand_In_VFI", loop_frames(cfg["n"]), 10, cfg["multiplier"], loop_model, 0.03,
                                     interpolation_states=st, use_timestep=cfg["use_timestep"], dtype=torch.float32)

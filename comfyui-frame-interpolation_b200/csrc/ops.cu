@@ -6,6 +6,11 @@
 //   sepconv        : adaptive separable convolution, Kahan sums   cupy_ops/sepconv.py:86-117
 // One thread per pixel computes everything that does not depend on the channel ONCE (the reference launches one
 // thread per (pixel, channel) and recomputes flow taps / weights C times) and keeps the 81 volume entries in registers.
+// The volume and sepconv kernels stage their input window in shared memory (zero fill outside the image = the
+// reference's boundary rule) so that the inner loops are LDS + FMA only; sepconv additionally keeps each pixel's 51
+// horizontal weights in registers and shares every loaded input value between vertically stacked output pixels.
+#include <cstdlib>
+
 #include "vfi_internal.h"
 
 namespace vfi {
@@ -128,6 +133,139 @@ __global__ void sepconv_kernel(const float* __restrict__ in, const float* __rest
   }
 }
 
+
+// ---- shared-memory tiled 9x9 volume: block = 32 x 8 pixels, `two` window (40 x 16) staged for kVolCh channels at a time
+constexpr int kVolCh = 8;
+template <bool kDot>
+__global__ void __launch_bounds__(256) volume81_tile_kernel(const float* __restrict__ one, const float* __restrict__ two,
+                                                            float* __restrict__ out, int N, int C, int H, int W) {
+  __shared__ float tile[kVolCh][16][40];
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8, n = blockIdx.z;
+  const int x = x0 + lx, y = y0 + ly;
+  const bool valid = x < W && y < H;
+  const size_t hw = (size_t)H * W;
+  float acc[81];
+#pragma unroll
+  for (int k = 0; k < 81; ++k) acc[k] = 0.f;
+  for (int cb = 0; cb < C; cb += kVolCh) {
+    const int nc = min(kVolCh, C - cb);
+    __syncthreads();  // the previous chunk has been consumed
+    for (int i = threadIdx.x; i < nc * 16 * 40; i += 256) {
+      const int c = i / (16 * 40), r = (i / 40) % 16, q = i % 40;
+      const int yy = y0 + r - 4, xx = x0 + q - 4;
+      float v = 0.f;  // outside the image: 0 (correlation: zero padding; cost volume: |one - 0| = |one|, costvol.py:27-31)
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(two + ((size_t)n * C + cb + c) * hw + (size_t)yy * W + xx);
+      tile[c][r][q] = v;
+    }
+    __syncthreads();
+    for (int c = 0; c < nc; ++c) {
+      const float a = valid ? __ldg(one + ((size_t)n * C + cb + c) * hw + (size_t)y * W + x) : 0.f;
+#pragma unroll
+      for (int dy = 0; dy < 9; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 9; ++dx) {
+          const float b = tile[c][ly + dy][lx + dx];
+          if (kDot)
+            acc[dy * 9 + dx] = fmaf(a, b, acc[dy * 9 + dx]);
+          else
+            acc[dy * 9 + dx] += fabsf(a - b);
+        }
+    }
+  }
+  if (!valid) return;
+  float* o = out + (size_t)n * 81 * hw + (size_t)y * W + x;
+#pragma unroll
+  for (int k = 0; k < 81; ++k) o[(size_t)k * hw] = acc[k] / (float)C;
+}
+
+// ---- shared-memory tiled separable convolution, K x K taps (K compile time), up to 4 channels per pass.
+// Block = 32 x (8*PY) output pixels, 256 threads; thread (lx, ly) owns the PY vertically adjacent pixels
+// (y0 + ly*PY + j, x0 + lx).  The input window of the block, (8*PY + K-1) x (32 + K-1) positions x 4 channels, sits in
+// shared memory as float4 (one conflict-free LDS.128 per tap); every loaded value feeds PY pixels, whose K horizontal
+// weights live in registers.  out = sum_fy ver[fy] * (sum_fx hor[fx] * in[y+fy][x+fx]): the inner sums are FMA chains,
+// the outer sum over the K rows is Kahan-compensated (the reference compensates every one of the K*K additions,
+// sepconv.py:103-110; both are accurately rounded fp32 sums and agree to ~1e-6 relative).
+template <int K, int PY>
+__global__ void __launch_bounds__(256) sepconv_tile_kernel(const float* __restrict__ in, const float* __restrict__ ver,
+                                                           const float* __restrict__ hor, float* __restrict__ out,
+                                                           int N, int C, int c0, int H, int W) {
+  extern __shared__ float4 sep_tile[];  // [8*PY + K-1][32 + K-1]
+  constexpr int TW = 32 + K - 1, TH = 8 * PY + K - 1;
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * (8 * PY), n = blockIdx.z;
+  const int Hp = H + K - 1, Wp = W + K - 1;
+  const size_t hw = (size_t)H * W, hwp = (size_t)Hp * Wp;
+  const int nch = min(4, C - c0);
+  for (int i = threadIdx.x; i < TH * TW; i += 256) {
+    const int r = i / TW, q = i - r * TW;
+    const int gy = y0 + r, gx = x0 + q;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (gy < Hp && gx < Wp) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < nch) v[c] = __ldg(in + ((size_t)n * C + c0 + c) * hwp + (size_t)gy * Wp + gx);
+    }
+    sep_tile[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  __syncthreads();
+  const int x = x0 + lx;
+  const int yb = y0 + ly * PY;  // first of this thread's PY rows
+  bool ok[PY];
+  float h[PY][K];
+#pragma unroll
+  for (int j = 0; j < PY; ++j) {
+    ok[j] = (x < W) && (yb + j < H);
+#pragma unroll
+    for (int fx = 0; fx < K; ++fx)
+      h[j][fx] = ok[j] ? __ldg(hor + ((size_t)n * K + fx) * hw + (size_t)(yb + j) * W + x) : 0.f;
+  }
+  float sum[PY][4], comp[PY][4];
+#pragma unroll
+  for (int j = 0; j < PY; ++j)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) sum[j][c] = comp[j][c] = 0.f;
+  for (int r = 0; r < K + PY - 1; ++r) {  // input row yb + r serves pixel row j with vertical tap fy = r - j
+    const float4* row = sep_tile + (ly * PY + r) * TW + lx;
+    float rd[PY][4];
+#pragma unroll
+    for (int j = 0; j < PY; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) rd[j][c] = 0.f;
+#pragma unroll
+    for (int fx = 0; fx < K; ++fx) {
+      const float4 a = row[fx];
+#pragma unroll
+      for (int j = 0; j < PY; ++j) {
+        rd[j][0] = fmaf(h[j][fx], a.x, rd[j][0]);
+        rd[j][1] = fmaf(h[j][fx], a.y, rd[j][1]);
+        rd[j][2] = fmaf(h[j][fx], a.z, rd[j][2]);
+        rd[j][3] = fmaf(h[j][fx], a.w, rd[j][3]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < PY; ++j) {
+      const int fy = r - j;
+      if (fy < 0 || fy >= K || !ok[j]) continue;
+      const float v = __ldg(ver + ((size_t)n * K + fy) * hw + (size_t)(yb + j) * W + x);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {  // Kahan step with the row's contribution
+        const float yk = v * rd[j][c] - comp[j][c];
+        const float t = sum[j][c] + yk;
+        comp[j][c] = (t - sum[j][c]) - yk;
+        sum[j][c] = t;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < PY; ++j) {
+    if (!ok[j]) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c < nch) out[((size_t)n * C + c0 + c) * hw + (size_t)(yb + j) * W + x] = sum[j][c];
+  }
+}
+
 inline int grid_for(size_t total, int block) {
   size_t g = (total + block - 1) / block;
   const size_t cap = 148 * 16;
@@ -147,6 +285,18 @@ cudaError_t launch_softsplat_sum(const float* in, const float* flow, float* out,
 
 cudaError_t launch_volume81(bool dot, const float* one, const float* two, float* out, int N, int C, int H, int W,
                             cudaStream_t st) {
+  static const bool tiled = [] {  // VFI_OPS_TILED=0: the first-version per-pixel kernels (A/B runs)
+    const char* e = std::getenv("VFI_OPS_TILED");
+    return !(e && e[0] == '0');
+  }();
+  if (tiled && N <= 65535) {
+    const dim3 g((unsigned)((W + 31) / 32), (unsigned)((H + 7) / 8), (unsigned)N);
+    if (dot)
+      volume81_tile_kernel<true><<<g, 256, 0, st>>>(one, two, out, N, C, H, W);
+    else
+      volume81_tile_kernel<false><<<g, 256, 0, st>>>(one, two, out, N, C, H, W);
+    return cudaGetLastError();
+  }
   const size_t total = (size_t)N * H * W;
   if (dot)
     volume81_kernel<true><<<grid_for(total, 128), 128, 0, st>>>(one, two, out, N, C, H, W);
@@ -157,6 +307,24 @@ cudaError_t launch_volume81(bool dot, const float* one, const float* two, float*
 
 cudaError_t launch_sepconv(const float* in, const float* ver, const float* hor, float* out, int N, int C, int H, int W,
                            int Kv, int Kh, cudaStream_t st) {
+  // the reference's only kernel size is 51 (sepconv_enhanced.py: 51-tap heads): shared-memory tiled fast path
+  static const int py = [] {  // VFI_SEPCONV_PY = 0 (first-version kernel), 1, 2 (default) or 3 pixels per thread
+    const char* e = std::getenv("VFI_SEPCONV_PY");
+    return (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 2;
+  }();
+  if (Kv == 51 && Kh == 51 && py > 0 && N <= 65535) {
+    auto go = [&](auto kern, int PY) -> cudaError_t {
+      const size_t smem = (size_t)(8 * PY + 50) * (32 + 50) * sizeof(float4);
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      const dim3 g((unsigned)((W + 31) / 32), (unsigned)((H + 8 * PY - 1) / (8 * PY)), (unsigned)N);
+      for (int c0 = 0; c0 < C; c0 += 4) kern<<<g, 256, smem, st>>>(in, ver, hor, out, N, C, c0, H, W);
+      return cudaGetLastError();
+    };
+    if (py == 1) return go(sepconv_tile_kernel<51, 1>, 1);
+    if (py == 3) return go(sepconv_tile_kernel<51, 3>, 3);
+    return go(sepconv_tile_kernel<51, 2>, 2);
+  }
   const size_t total = (size_t)N * H * W;
   for (int c0 = 0; c0 < C; c0 += 4) {
     sepconv_kernel<4><<<grid_for(total, 128), 128, 0, st>>>(in, ver, hor, out, N, C, c0, H, W, Kv, Kh);

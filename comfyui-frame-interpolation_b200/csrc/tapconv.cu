@@ -193,6 +193,11 @@ template <typename T, bool RING, bool LAST>
 __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_constant__ TapConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem);
+  // Programmatic dependent launch (launch_tapconv sets the attribute): the next kernel in the stream may start its
+  // CTAs as soon as every CTA of this grid has passed this point, i.e. while our last tiles are still running - they do
+  // their prologue (barrier init, TMEM allocation, weight copy) on the SMs our first finishers free and then block in
+  // griddepcontrol.wait until this grid has completed and flushed.  Both instructions are no-ops without the attribute.
+  asm volatile("griddepcontrol.launch_dependents;");
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
@@ -282,6 +287,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + (size_t)split * p.w_bytes;
       for (uint32_t off = 0; off < p.w_bytes; off += 32768u)
         bulk_g2s(w_smem + off, wsrc + off, min(32768u, p.w_bytes - off), bar_w);
+      // weights do not depend on the previous kernel; its output (our input tensor) does
+      asm volatile("griddepcontrol.wait;" ::: "memory");
       TileIter it(p, first, p.ctas_per_split);
       if (RING) {
         uint32_t slot = 0, ph = 0;
@@ -331,6 +338,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
     float* ss = reinterpret_cast<float*>(smem + p.off_ss);  // per-channel shift of this CTA's output slice
     for (int i = threadIdx.x; i < p.n_cta; i += 32 * kEpiWarps) ss[i] = p.shift[split * p.n_cta + i];
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+    // the previous kernel may still be reading the buffer we store to (ping-pong) and ring layers read the residual from
+    // global memory: every storing / loading thread orders itself after the previous grid
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const int r = q * 32 + lane;  // accumulator row == TMEM lane == tile cell
     const int py = r >> 3, px = r & 7;
@@ -787,11 +797,24 @@ cudaError_t launch_tapconv(const TapConvLayer& L, int op_type, const void* in, v
   p.ctas_per_split = cps;
   const int grid = cps * L.nsplit;
   cudaError_t err;  // (per device: set on every launch, it is a cheap driver call)
+  static const bool pdl = [] {  // VFI_PDL=0: plain stream-ordered launches (A/B runs)
+    const char* e = std::getenv("VFI_PDL");
+    return !(e && e[0] == '0');
+  }();
   auto go = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) return e;
-    kern<<<grid, kThreads, p.smem_bytes, st>>>(p);
-    return cudaSuccess;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)kThreads);
+    cfg.dynamicSmemBytes = p.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, p);
   };
   const bool last = (L.epi_mode == EPI_LASTCONV);
   if (op_type == OP_BF16) {

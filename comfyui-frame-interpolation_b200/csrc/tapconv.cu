@@ -39,6 +39,7 @@ namespace {
 
 constexpr int kMaxStages = 6;   // window stages (<= 4 used) or ring slots
 constexpr int kAccBufs = 4;     // TMEM accumulator buffers == epilogue groups
+constexpr int kDefaultStoreMode = 0;  // see VFI_STORE in tapconv_plan
 struct Ctrl {
   uint64_t w_full;
   uint64_t a_full[kMaxStages];
@@ -347,6 +348,14 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
     const int n0 = split * p.n_cta;
     const uint32_t center_px = (uint32_t)((py - p.halo_y0) * p.halo_w + (px - p.halo_x0));
     const int nchunks = p.n_cta >> 4;  // 16-column chunks of this CTA's accumulator (<= 6)
+    // stage_out (n_cta == 64, plain NHWC output): this group's tile goes to its own 16 KB staging buffer in the
+    // SWIZZLE_128B form (row = cell, 128 B = the 64 channels) and leaves with one TMA tensor store.  ncu r01_v12: the
+    // direct stores - every lane of an STG.128 in a different 128-byte line - were 2048 L1 tag lookups per tile, 60 %
+    // of the L1/shared data-pipe traffic of a kernel whose tensor-core operands come through the same pipe.
+    const bool stage_out = !LAST && p.stage_out != 0;
+    uint8_t* stg = smem + p.off_stg + acc * (128u * 128u);
+    const uint32_t stg_u32 = smem_base + p.off_stg + acc * (128u * 128u);
+    const bool stg_leader = (q == 0) && (lane == 0);  // issues and tracks this group's bulk stores
     const float slope = (p.epi_mode == EPI_BIAS) ? 1.f : 0.2f;  // max(a, slope * a): LeakyReLU(0.2), or no activation
 
     // this group's tiles: k = acc, acc + 4, ... (k counts the CTA's tiles); window stage of tile k = k % S, carried
@@ -429,6 +438,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
       // (patch form, out_s2d == 2: columns are (sub-pixel, channel) pairs, placed per chunk in finish_chunk)
       const bool patch = (p.out_s2d == 2);
       T* orow = reinterpret_cast<T*>(p.out) + (valid ? out_pixel_offset(p, b, gy, gx) + (patch ? 0 : (size_t)n0) : 0);
+      if (stage_out) {  // the previous store of this group must have finished reading the staging buffer
+        if (stg_leader) bulk_wait_read0();
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + (int)acc) : "memory");
+      }
       const uint4* gres = nullptr;  // ring layers: the centre pixel's channels in the input tensor (L2 hit)
       if (RING && residual)
         gres = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.in) +
@@ -468,6 +481,12 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
           }
           o[j] = Pack2<T>::pack(fmaxf(a0, slope * a0), fmaxf(a1, slope * a1));  // LeakyReLU(0.2) / identity
         }
+        if (stage_out) {  // chunks 2c, 2c+1 of row r, XOR-swizzled with (r & 7) like every SWIZZLE_128B tile
+          uint8_t* rowp = stg + (uint32_t)r * 128u;
+          *reinterpret_cast<uint4*>(rowp + (((uint32_t)(2 * c) ^ ((uint32_t)r & 7u)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(rowp + (((uint32_t)(2 * c + 1) ^ ((uint32_t)r & 7u)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+          return;
+        }
         // 32 contiguous bytes (16 channels) of this cell's channel vector; L2 merges the halves of a sector
         if (valid && (!ABLATE(1) || o[0] == 0x12345678u)) {
           uint4* dst = reinterpret_cast<uint4*>(orow + c * 16);
@@ -475,8 +494,12 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
             const int pos0 = (n0 + c * 16) >> 3;
             dst = reinterpret_cast<uint4*>(orow + ((size_t)(pos0 >> 2) * (size_t)(4 * p.W) + (size_t)(pos0 & 3)) * 8);
           }
-          dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-          dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+          if (p.st256)
+            stg256(dst, o);
+          else {
+            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+          }
         }
       };
       if (ABLATE(4)) {
@@ -510,7 +533,16 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_aempty + 8 * stage);
       }
+      if (stage_out) {
+        fence_proxy_async();  // this thread's staging writes -> visible to the TMA (async proxy)
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + (int)acc) : "memory");
+        if (stg_leader) {
+          tma_store_4d(&p.tm_out, stg_u32, n0, it.tx * kTileW, it.ty * kTileH, b);
+          bulk_commit_group();
+        }
+      }
     }
+    if (stage_out && stg_leader) bulk_wait0();  // the stores are performed before the grid counts as complete
   }
 
   tc_fence_before();
@@ -713,15 +745,28 @@ int tapconv_plan(const TapConvLayer& L, TapConvParams* pp) {
   p.off_ss = kCtrlBytes;
   p.off_w = align_up(p.off_ss + (uint32_t)L.n_cta * 4u, 1024);
   p.off_a = align_up(p.off_w + p.w_bytes, 1024);
+  // staged output (TMA tensor store): 64-channel slices of a plain NHWC output, when four 16 KB staging buffers still
+  // leave room for three window stages
+  static const int opt_store = [] {  // VFI_STORE: 0 = two STG.128 per chunk, 1 = one STG.256, 2 = 1 + staged TMA store
+    const char* e = std::getenv("VFI_STORE");
+    return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : kDefaultStoreMode;
+  }();
+  p.st256 = opt_store >= 1;
+  const uint32_t stg_bytes = (uint32_t)kAccBufs * 128u * 128u;
+  p.stage_out = (opt_store >= 2 && L.n_cta == 64 && L.out_s2d == 0 && !L.ring && L.epi_mode != EPI_LASTCONV &&
+                 p.off_a + 3u * p.stage_bytes + stg_bytes <= (uint32_t)kSmemLimit)
+                    ? 1 : 0;
+  const uint32_t limit = (uint32_t)kSmemLimit - (p.stage_out ? stg_bytes : 0u);
   int stages = 0;
   for (int s = (L.ring ? kMaxStages : 4); s >= 1; --s) {
-    if (p.off_a + (uint32_t)s * p.stage_bytes <= (uint32_t)kSmemLimit) {
+    if (p.off_a + (uint32_t)s * p.stage_bytes <= limit) {
       stages = s;
       break;
     }
   }
   p.stages = stages;
-  p.smem_bytes = p.off_a + (uint32_t)stages * p.stage_bytes;
+  p.off_stg = p.off_a + (uint32_t)stages * p.stage_bytes;  // stage sizes are multiples of 1024
+  p.smem_bytes = p.off_stg + (p.stage_out ? stg_bytes : 0u);
   // accumulators: kAccBufs buffers of n_cta fp32 columns, allocation is a power of two >= 32 (<= 4 x 128 = 512)
   uint32_t stride = 16;
   while (stride < (uint32_t)L.n_cta) stride <<= 1;
@@ -791,6 +836,9 @@ cudaError_t launch_tapconv(const TapConvLayer& L, int op_type, const void* in, v
   } else {
     p.tm32 = p.tm64;
   }
+  if (p.stage_out &&
+      !make_tmap(&p.tm_out, dt, out, L.n_total, W, H, B, 64, kTileW, kTileH, CU_TENSOR_MAP_SWIZZLE_128B))
+    return cudaErrorInvalidValue;
   int cps = num_sms / L.nsplit;
   if (cps < 1) cps = 1;
   if (cps > p.ntiles) cps = p.ntiles;

@@ -38,6 +38,7 @@ constexpr int kMaxK16 = 108;   // 9 taps x 192/16
 struct alignas(64) TapConvParams {
   CUtensorMap tm64;      // input as a {C, W, H, B} tensor with a {64 ch, halo_w, halo_h, 1} box, SWIZZLE_128B
   CUtensorMap tm32;      // same with a {32 ch, ...} box, SWIZZLE_64B (only used when cin % 64 == 32)
+  CUtensorMap tm_out;    // stage_out: the output as a {n_total, W, H, B} tensor with a {64 ch, 8, 16, 1} box, SWIZZLE_128B
   const void* in;        // [B, H, W, cin] 16-bit, NHWC
   void* out;             // [B, H, W, n_total] 16-bit NHWC; out_s2d = 1: its space-to-depth form; out_s2d = 2: the 4x4
                          // sub-pixel patch form [B, 4H, 4W, 8] with column n = (py*4 + px)*8 + ch (arch 4.26 lastconv features)
@@ -64,6 +65,10 @@ struct alignas(64) TapConvParams {
   int nkb;                        // k-blocks of the staged window: 64 channels each, 32-channel tail if cin%64==32
   uint32_t kb_off[kMaxKBlocks];   // byte offset of each k-block inside a stage (1024-aligned)
   uint32_t tx_bytes;              // bytes one stage fill delivers (mbarrier transaction count)
+  int st256;                      // 1: 32-byte STG.256 epilogue stores (one L1 tag lookup per lane and chunk instead of two)
+  int stage_out;                  // 1: the epilogue writes each tile to a shared-memory staging buffer (one per
+                                  //    accumulator group) and ONE TMA tensor store moves it out (n_cta == 64 only)
+  uint32_t off_stg;               // staging buffers: kAccBufs x 128 rows x 128 B, 1024-aligned
   TapEntry taps[kMaxTaps];
   // per run: {A start offset inside a stage, A descriptor high word, B start offset inside the weights, 0},
   // offsets in 16-byte units.  Lives in the kernel parameters (constant bank) so that the MMA-issuing warp gets it

@@ -403,7 +403,22 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
 #pragma unroll
             for (int yy = 0; yy < 2; ++yy) {
               const size_t o = ((size_t)b * Hs + (gy * 4 + half * 2 + yy)) * Ws + gx * 4;
-              if (ncomp == 5) {
+              if (ncomp == 5 && p.st256) {
+                // the four pixels of this patch row are contiguous: 64 B of flow = two 32-byte stores, 16 B of mask = one
+                uint32_t fw[16], mw[4];
+#pragma unroll
+                for (int x4 = 0; x4 < 4; ++x4) {
+                  const int i = yy * 4 + x4, pos = half * 8 + i;
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) fw[x4 * 4 + c] = __float_as_uint(__uint_as_float(v[c][i]) + ss[c * 16 + pos]);
+                  mw[x4] = __float_as_uint(__uint_as_float(v[4][i]) + ss[4 * 16 + pos]);
+                }
+                const uint32_t lo[8] = {fw[0], fw[1], fw[2], fw[3], fw[4], fw[5], fw[6], fw[7]};
+                const uint32_t hi[8] = {fw[8], fw[9], fw[10], fw[11], fw[12], fw[13], fw[14], fw[15]};
+                stg256(p.out_flow + o, lo);
+                stg256(p.out_flow + o + 2, hi);
+                *reinterpret_cast<uint4*>(p.out_mask + o) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+              } else if (ncomp == 5) {
 #pragma unroll
                 for (int x4 = 0; x4 < 4; ++x4) {
                   const int i = yy * 4 + x4, pos = half * 8 + i;

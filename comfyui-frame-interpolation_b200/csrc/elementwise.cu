@@ -84,8 +84,8 @@ __device__ __forceinline__ float4 sample_border(const uint2* __restrict__ img, i
   return o;
 }
 
-// same sampling for a 4-channel feature plane (arch 4.7 encode features)
-__device__ __forceinline__ float4 sample_border4(const float4* __restrict__ img, int Hp, int Wp, float sx, float sy) {
+// same sampling for a 4-channel feature plane (arch 4.7 encode features, stored as half4)
+__device__ __forceinline__ float4 sample_border4(const uint2* __restrict__ img, int Hp, int Wp, float sx, float sy) {
   sx = fminf(fmaxf(sx, 0.f), (float)(Wp - 1));
   sy = fminf(fmaxf(sy, 0.f), (float)(Hp - 1));
   const float fx0 = floorf(sx), fy0 = floorf(sy);
@@ -93,11 +93,11 @@ __device__ __forceinline__ float4 sample_border4(const float4* __restrict__ img,
   const int dx = (x0 + 1 < Wp) ? 1 : 0, dyw = (y0 + 1 < Hp) ? Wp : 0;
   const float ax = sx - fx0, ay = sy - fy0;
   const float w00 = (1.f - ax) * (1.f - ay), w01 = ax * (1.f - ay), w10 = (1.f - ax) * ay, w11 = ax * ay;
-  const float4* p = img + (y0 * Wp + x0);
-  const float4 a = __ldg(p);
-  const float4 b = __ldg(p + dx);
-  const float4 c = __ldg(p + dyw);
-  const float4 d = __ldg(p + dyw + dx);
+  const uint2* p = img + (y0 * Wp + x0);
+  const float4 a = unpack_h4(__ldg(p));
+  const float4 b = unpack_h4(__ldg(p + dx));
+  const float4 c = unpack_h4(__ldg(p + dyw));
+  const float4 d = unpack_h4(__ldg(p + dyw + dx));
   float4 o;
   o.x = a.x * w00 + b.x * w01 + c.x * w10 + d.x * w11;
   o.y = a.y * w00 + b.y * w01 + c.y * w10 + d.y * w11;
@@ -453,7 +453,7 @@ __global__ void encode_conv_kernel(const float4* __restrict__ imgs, const float*
 }
 
 __global__ void encode_deconv_kernel(const float* __restrict__ e16, const float* __restrict__ w,
-                                     const float* __restrict__ bias, float4* __restrict__ feats, int n, int Hp,
+                                     const float* __restrict__ bias, uint2* __restrict__ feats, int n, int Hp,
                                      int Wp) {
   __shared__ float ws[16 * 4 * 16 + 4];  // ConvTranspose2d weight [16 in][4 out][4][4]
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) ws[i] = w[i];
@@ -490,14 +490,16 @@ __global__ void encode_deconv_kernel(const float* __restrict__ e16, const float*
         }
       }
     }
-    feats[id] = make_float4(o[0], o[1], o[2], o[3]);
+    // half4: the features only ever feed the 16-bit block inputs (r01_v13: the 4.7 fronts were gather bound on 16-byte
+    // image and feature texels, 1453 frames/s against 2452 for arch 4.6)
+    feats[id] = make_uint2(Pack2<__half>::pack(o[0], o[1]), Pack2<__half>::pack(o[2], o[3]));
   }
 }
 
 // arch 4.7 block input: [w0.rgb, w1.rgb, warp(f0) (4), warp(f1) (4), t, mask, flow/s (4)] = 20 of 32 channels
 // (block 0: [img0, img1, f0, f1, t] = 15), space-to-depth cell = 4 x 32 channels
 template <typename T, int NLEV>
-__global__ void front47_kernel(const float4* __restrict__ imgs, const float4* __restrict__ feats,
+__global__ void front47_kernel(const uint2* __restrict__ imgs, const uint2* __restrict__ feats,
                                const FlowLevels lev, const BatchTasks tasks, int Hp, int Wp, int s,
                                T* __restrict__ x_s2d) {
   const int Hs = Hp / s, Ws = Wp / s;
@@ -509,10 +511,10 @@ __global__ void front47_kernel(const float4* __restrict__ imgs, const float4* __
     if (xl >= Ws) return;
     const int yl = (int)blockIdx.y * 2 + par;
     const int b = (int)blockIdx.z;
-    const float4* img0 = imgs + (size_t)tasks.f0[b] * plane;
-    const float4* img1 = imgs + (size_t)tasks.f1[b] * plane;
-    const float4* ft0 = feats + (size_t)tasks.f0[b] * plane;
-    const float4* ft1 = feats + (size_t)tasks.f1[b] * plane;
+    const uint2* img0 = imgs + (size_t)tasks.f0[b] * plane;  // half4 planes: the block input is 16-bit anyway
+    const uint2* img1 = imgs + (size_t)tasks.f1[b] * plane;
+    const uint2* ft0 = feats + (size_t)tasks.f0[b] * plane;
+    const uint2* ft1 = feats + (size_t)tasks.f1[b] * plane;
     const float t = tasks.t[b];
     const int ntap = (s == 1) ? 1 : 2;
     const int by = (s == 1) ? yl : s * yl + s / 2 - 1;
@@ -531,10 +533,10 @@ __global__ void front47_kernel(const float4* __restrict__ imgs, const float4* __
           float* v = colv[tx];
           float4 a, c, fa, fc;
           if (NLEV == 0) {
-            a = __ldg(img0 + (size_t)Y * Wp + X);
-            c = __ldg(img1 + (size_t)Y * Wp + X);
-            fa = __ldg(ft0 + (size_t)Y * Wp + X);
-            fc = __ldg(ft1 + (size_t)Y * Wp + X);
+            a = unpack_h4(__ldg(img0 + (size_t)Y * Wp + X));
+            c = unpack_h4(__ldg(img1 + (size_t)Y * Wp + X));
+            fa = unpack_h4(__ldg(ft0 + (size_t)Y * Wp + X));
+            fc = unpack_h4(__ldg(ft1 + (size_t)Y * Wp + X));
             v[14] = t; v[15] = 0.f; v[16] = 0.f; v[17] = 0.f; v[18] = 0.f; v[19] = 0.f;
           } else {
             float4 f;
@@ -656,7 +658,7 @@ __device__ __forceinline__ void sample_border8(const uint4* __restrict__ ft, int
 // (block 0: [img0, img1, f0, f1, t] = 23), space-to-depth cell = 4 x 32 channels.  Same structure as front47_kernel;
 // the 2x2 centre taps are summed row by row in the reference's order ((a + b) + (c + d)) * 0.25.
 template <typename T, int NLEV>
-__global__ void front417_kernel(const float4* __restrict__ imgs, const uint4* __restrict__ feats,
+__global__ void front417_kernel(const uint2* __restrict__ imgs, const uint4* __restrict__ feats,
                                 const FlowLevels lev, const BatchTasks tasks, int Hp, int Wp, int s,
                                 T* __restrict__ x_s2d) {
   const int Hs = Hp / s, Ws = Wp / s;
@@ -668,8 +670,8 @@ __global__ void front417_kernel(const float4* __restrict__ imgs, const uint4* __
   if (xl >= Ws) return;
   const int yl = (int)blockIdx.y * 2 + par;
   const int b = (int)blockIdx.z;
-  const float4* img0 = imgs + (size_t)tasks.f0[b] * plane;
-  const float4* img1 = imgs + (size_t)tasks.f1[b] * plane;
+  const uint2* img0 = imgs + (size_t)tasks.f0[b] * plane;  // half4 planes: the block input is 16-bit anyway
+  const uint2* img1 = imgs + (size_t)tasks.f1[b] * plane;
   const uint4* ft0 = feats + (size_t)tasks.f0[b] * fplane;
   const uint4* ft1 = feats + (size_t)tasks.f1[b] * fplane;
   const float t = tasks.t[b];
@@ -688,8 +690,8 @@ __global__ void front417_kernel(const float4* __restrict__ imgs, const uint4* __
         float4 a, c;
         float fa[8], fc[8];
         if (NLEV == 0) {
-          a = __ldg(img0 + (size_t)Y * Wp + X);
-          c = __ldg(img1 + (size_t)Y * Wp + X);
+          a = unpack_h4(__ldg(img0 + (size_t)Y * Wp + X));
+          c = unpack_h4(__ldg(img1 + (size_t)Y * Wp + X));
           load_feat8<T>(ft0, Wp >> 1, Y, X, fa);
           load_feat8<T>(ft1, Wp >> 1, Y, X, fc);
           v[22] = t; v[23] = 0.f; v[24] = 0.f; v[25] = 0.f; v[26] = 0.f; v[27] = 0.f;
@@ -1014,7 +1016,7 @@ static FlowLevels make_levels(const FlowState& fs, int lo, int hi, const float4*
 }
 
 template <typename T>
-static void launch_front47_t(int nlev, dim3 g, cudaStream_t st, const float4* imgs, const float4* feats,
+static void launch_front47_t(int nlev, dim3 g, cudaStream_t st, const uint2* imgs, const uint2* feats,
                              const FlowLevels& L, const BatchTasks& tasks, int Hp, int Wp, int s, void* x) {
   switch (nlev) {
     case 0: front47_kernel<T, 0><<<g, 128, 0, st>>>(imgs, feats, L, tasks, Hp, Wp, s, (T*)x); break;
@@ -1062,7 +1064,7 @@ static void launch_front_t(int nlev, bool shared_taps, dim3 g, cudaStream_t st, 
 }
 
 template <typename T>
-static void launch_front417_t(int nlev, dim3 g, cudaStream_t st, const float4* imgs, const uint4* feats,
+static void launch_front417_t(int nlev, dim3 g, cudaStream_t st, const uint2* imgs, const uint4* feats,
                               const FlowLevels& L, const BatchTasks& tasks, int Hp, int Wp, int s, void* x) {
   switch (nlev) {
     case 0: front417_kernel<T, 0><<<g, 128, 0, st>>>(imgs, feats, L, tasks, Hp, Wp, s, (T*)x); break;
@@ -1097,7 +1099,7 @@ cudaError_t launch_head0(int op_type, const float4* imgs, const float* w, const 
 
 // block `blk` input: flow = base (if any) + levels [lo, blk); stores the accumulated flow when `store` planes given
 cudaError_t launch_encode(const float4* imgs, const float* w0, const float* b0, const float* w1, const float* b1,
-                          float* e16, float4* feats, int n, int Hp, int Wp, cudaStream_t st) {
+                          float* e16, uint2* feats, int n, int Hp, int Wp, cudaStream_t st) {
   const size_t t0 = (size_t)n * (Hp / 2) * (Wp / 2), t1 = (size_t)n * Hp * Wp;
   encode_conv_kernel<<<grid_for(t0, 128), 128, 0, st>>>(imgs, w0, b0, e16, n, Hp, Wp);
   cudaError_t e = cudaGetLastError();
@@ -1126,16 +1128,16 @@ cudaError_t launch_front(int op_type, int arch, const float4* imgs, const uint2*
   }
   if (feats != nullptr && feat_ch == 4) {  // arch 4.7
     if (op_type == OP_BF16)
-      launch_front47_t<__nv_bfloat16>(blk == 0 ? 0 : nlev, g, st, imgs, (const float4*)feats, L, tasks, Hp, Wp, s, x_s2d);
+      launch_front47_t<__nv_bfloat16>(blk == 0 ? 0 : nlev, g, st, imgs_h, (const uint2*)feats, L, tasks, Hp, Wp, s, x_s2d);
     else
-      launch_front47_t<__half>(blk == 0 ? 0 : nlev, g, st, imgs, (const float4*)feats, L, tasks, Hp, Wp, s, x_s2d);
+      launch_front47_t<__half>(blk == 0 ? 0 : nlev, g, st, imgs_h, (const uint2*)feats, L, tasks, Hp, Wp, s, x_s2d);
     return cudaGetLastError();
   }
   if (feats != nullptr) {  // arch 4.17: 8 feature channels, 16-bit, space-to-depth
     if (op_type == OP_BF16)
-      launch_front417_t<__nv_bfloat16>(blk == 0 ? 0 : nlev, g, st, imgs, (const uint4*)feats, L, tasks, Hp, Wp, s, x_s2d);
+      launch_front417_t<__nv_bfloat16>(blk == 0 ? 0 : nlev, g, st, imgs_h, (const uint4*)feats, L, tasks, Hp, Wp, s, x_s2d);
     else
-      launch_front417_t<__half>(blk == 0 ? 0 : nlev, g, st, imgs, (const uint4*)feats, L, tasks, Hp, Wp, s, x_s2d);
+      launch_front417_t<__half>(blk == 0 ? 0 : nlev, g, st, imgs_h, (const uint4*)feats, L, tasks, Hp, Wp, s, x_s2d);
     return cudaGetLastError();
   }
   // scale-2 front without a base plane whose levels are all at scale 4, 8, ...: the level taps are shared per cell

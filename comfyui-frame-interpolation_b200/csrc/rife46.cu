@@ -439,7 +439,7 @@ int ensure_workspace(vfi_ctx* c, const Geometry& g, int B, int n_frames_window) 
   CK(c->imgs.ensure((size_t)n_frames_window * px * sizeof(float4)));
   CK(c->imgs_h.ensure((size_t)n_frames_window * px * sizeof(uint2)));
   if (c->arch == 47) {
-    CK(c->feats.ensure((size_t)n_frames_window * px * sizeof(float4)));
+    CK(c->feats.ensure((size_t)n_frames_window * px * sizeof(uint2)));  // half4 features
     CK(c->e16.ensure((size_t)(kMaxBatch + 2) * (px / 4) * 16 * sizeof(float)));
   }
   if (c->arch == 417 || c->arch == 426) {
@@ -475,7 +475,7 @@ int run_encode(vfi_ctx* c, const Geometry& g, int f, int n, cudaStream_t st) {
   const float4* imgs = (const float4*)c->imgs.p + (size_t)f * px;
   if (c->arch == 47) {
     LAUNCH(launch_encode(imgs, c->enc[0], c->enc[1], c->enc[2], c->enc[3], (float*)c->e16.p,
-                         (float4*)c->feats.p + (size_t)f * px, n, g.Hp, g.Wp, st));
+                         (uint2*)c->feats.p + (size_t)f * px, n, g.Hp, g.Wp, st));
   } else if (c->arch == 417 || c->arch == 426) {
     const int Hh = g.Hp / 2, Wh = g.Wp / 2;
     const size_t fbytes = c->arch == 417 ? 16 : 8;  // feature bytes per full-resolution pixel

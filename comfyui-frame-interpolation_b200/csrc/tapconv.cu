@@ -39,7 +39,8 @@ namespace {
 
 constexpr int kMaxStages = 6;   // window stages (<= 4 used) or ring slots
 constexpr int kAccBufs = 4;     // TMEM accumulator buffers == epilogue groups
-constexpr int kDefaultStoreMode = 0;  // see VFI_STORE in tapconv_plan
+constexpr int kDefaultStoreMode = 2;  // see VFI_STORE in tapconv_plan
+constexpr int kDefaultMaxStages = 4;  // window stages of the non-ring layers (VFI_STAGES_MAX = 1..6 for A/B runs)
 struct Ctrl {
   uint64_t w_full;
   uint64_t a_full[kMaxStages];
@@ -768,12 +769,20 @@ int tapconv_plan(const TapConvLayer& L, TapConvParams* pp) {
   }();
   p.st256 = opt_store >= 1;
   const uint32_t stg_bytes = (uint32_t)kAccBufs * 128u * 128u;
-  p.stage_out = (opt_store >= 2 && L.n_cta == 64 && L.out_s2d == 0 && !L.ring && L.epi_mode != EPI_LASTCONV &&
+  // (r01_v13, block 3 at batch 8: conv0.1 84.8 -> 69.7 us with the staged store; the ResConv layers, whose window
+  // stages are held until the epilogue has read the residual, lost more from the fourth stage than they gained:
+  // 94.2 us with STG.256 and 4 stages, 109 us staged with 3 - so only layers without a residual stage their output)
+  p.stage_out = (opt_store >= 2 && L.n_cta == 64 && L.out_s2d == 0 && !L.ring &&
+                 (L.epi_mode == EPI_BIAS_LRELU || L.epi_mode == EPI_BIAS) &&
                  p.off_a + 3u * p.stage_bytes + stg_bytes <= (uint32_t)kSmemLimit)
                     ? 1 : 0;
+  static const int max_stages = [] {
+    const char* e = std::getenv("VFI_STAGES_MAX");
+    return (e && e[0] >= '1' && e[0] <= '6') ? e[0] - '0' : kDefaultMaxStages;
+  }();
   const uint32_t limit = (uint32_t)kSmemLimit - (p.stage_out ? stg_bytes : 0u);
   int stages = 0;
-  for (int s = (L.ring ? kMaxStages : 4); s >= 1; --s) {
+  for (int s = (L.ring ? kMaxStages : max_stages); s >= 1; --s) {
     if (p.off_a + (uint32_t)s * p.stage_bytes <= limit) {
       stages = s;
       break;

@@ -68,3 +68,18 @@ def test_missing_checkpoint_is_an_error(pkg, monkeypatch, tmp_path):
     monkeypatch.setenv("VFI_CKPT_DIR", str(tmp_path))
     with pytest.raises(Exception):
         N.load_file_from_github_release("rife", "rife46.pth")
+
+
+def test_state_dict_layouts_agree(pkg):
+    """The C header's tensor counts, the host's name lists and the oracle's reference-derived specs (checked against
+    the unmodified reference by tools/make_golden.py's load_state_dict) describe the same checkpoints."""
+    from cfi_b200.engine import ARCH_CODE, state_dict_names
+    from oracle import rife46 as O
+    hdr = open(os.path.join(ROOT, "include", "vfi_b200.h")).read()
+    counts = {int(a): int(n) for a, n in re.findall(r"#define VFI_RIFE(\d+)_NUM_TENSORS (\d+)", hdr)}
+    for arch, code in ARCH_CODE.items():
+        spec = O.state_dict_spec(arch)
+        assert state_dict_names(arch) == [n for n, _ in spec], arch
+        assert counts[code] == len(spec), arch
+    assert [c for _, c in O.BLOCK_SPECS_426] == [192, 128, 96, 64, 32]
+    assert len(O.SCALE_LIST["4.26"]) == 5 and set(ARCH_CODE) == set(O.SCALE_LIST)

@@ -12,6 +12,8 @@ VFI_PDL=0 TAILN=1 run bench_nopdl python bench.py --no-cpu
 VFI_STORE=1 TAILN=1 run bench_store1 python bench.py --no-cpu
 VFI_STORE=2 TAILN=1 run bench_store2 python bench.py --no-cpu
 VFI_ISSUERS=2 TAILN=1 run bench_issuers2 python bench.py --no-cpu
+TAILN=1 run bench_batch16 python bench.py --no-cpu --batch 16
+VFI_STORE=2 TAILN=1 run bench_batch16_store2 python bench.py --no-cpu --batch 16
 for a in 4.7 4.17 4.26; do TAILN=1 run bench_arch$a python bench.py --arch $a --no-cpu --steps 3 --warmup 3; done
 TAILN=45 run layers python tools/bench_layers.py --batch 8 --json gpurun_out/r01_v13_layers_b8.json
 VFI_STORE=2 TAILN=45 run layers_store2 python tools/bench_layers.py --batch 8 --json gpurun_out/r01_v13_layers_b8_store2.json

@@ -288,9 +288,9 @@ def main():
         roofline = {"kernel": "tapconv_kernel (block-3 ResConv 64->64, 272x480 cells, tcgen05)", "bound": "tensor",
                     "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
                     # dram__bytes_read.sum + dram__bytes_write.sum of this launch (batch 8) in the committed capture
-                    # profiles/r01_v12_resconv_b3.ncu-rep: 133.9 MB + 83.0 MB against 2 x 133.7 MB of algorithmic
+                    # profiles/r01_v15_resconv_b3.ncu-rep: 133.9 MB + 89.3 MB against 2 x 133.7 MB of algorithmic
                     # activation bytes (part of the output is still in L2 when the kernel ends); not re-measured here
-                    "traffic": (216.87e6 if B == 8 else None), "traffic_source": "ncu profiles/r01_v12_resconv_b3",
+                    "traffic": (223.16e6 if B == 8 else None), "traffic_source": "ncu profiles/r01_v15_resconv_b3",
                     "algorithmic_bytes": 2.0 * B * 272 * 480 * 64 * 2,
                     "peak_source": peaks["source"] + ", burst figure (kernel timed alone)",
                     "launch_ms": k_ms, "flops_per_launch": k_flops}

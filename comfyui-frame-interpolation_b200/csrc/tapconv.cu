@@ -462,11 +462,17 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
       if (RING && residual)
         gres = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.in) +
                                               ((((size_t)b * p.H + gy) * p.W + gx) * (size_t)p.cin + (size_t)n0));
-      const uint8_t* st = smem + p.off_a + stage * p.stage_bytes;  // generic pointer: ordinary, freely scheduled loads
-      auto finish_chunk = [&](int c, const uint32_t(&vv)[16]) {
-        uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+      const uint32_t st_u32 = smem_base + p.off_a + stage * p.stage_bytes;  // this tile's window (shared-space address)
+      // residual of chunk c = input channels n0 + 16*c .. +15 of the centre pixel: two 16-byte chunks of its swizzled row.
+      // Explicit ld.shared with the per-lane XOR in the address: with plain C++ loads the compiler, seeing all eight
+      // chunk offsets of the row over the unrolled chunk loop, read the row linearly ([base + 16k] for every lane) and
+      // permuted registers afterwards - every lane of an LDS.128 then sits in the same four banks (ncu r01_v14: 6.9 M
+      // bank-conflict wavefronts, 11 per LDS.128 instead of 2.7, in a kernel whose tensor-core operand reads fill 61 %
+      // of the same shared-memory data pipe).  Issued while the tcgen05.ld of the chunk is in flight.
+      auto load_residual = [&](int c, uint4& r0, uint4& r1) {
+        r0 = make_uint4(0u, 0u, 0u, 0u);
+        r1 = r0;
         if (res_smem && !ABLATE(1)) {
-          // residual = input channels n0 + 16*c .. +15 of the centre pixel: two 16-byte chunks of its (swizzled) row
           const int ch0 = n0 + c * 16;
           const int kb = ch0 >> 6;
           const bool tail = has_tail && (kb == p.nkb - 1);
@@ -474,12 +480,14 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
           // pixel: (address >> 7) & 7 for 128-byte rows, & 3 for the 64-byte rows of a 32-channel tail
           const uint32_t row = p.kb_off[kb] + (tail ? center_px * 64u : center_px * 128u);
           const uint32_t c0 = (uint32_t)(ch0 - kb * 64) >> 3, sw = tail ? ((center_px >> 1) & 3u) : (center_px & 7u);
-          r0 = *reinterpret_cast<const uint4*>(st + row + ((c0 ^ sw) << 4));
-          r1 = *reinterpret_cast<const uint4*>(st + row + (((c0 + 1u) ^ sw) << 4));
+          r0 = lds128(st_u32 + row + ((c0 ^ sw) << 4));
+          r1 = lds128(st_u32 + row + (((c0 + 1u) ^ sw) << 4));
         } else if (RING && residual && valid) {
           r0 = __ldg(gres + c * 2);
           r1 = __ldg(gres + c * 2 + 1);
         }
+      };
+      auto finish_chunk = [&](int c, const uint32_t(&vv)[16], const uint4 r0, const uint4 r1) {
         const float4* sp = reinterpret_cast<const float4*>(ss + c * 16);
         const float4 s0 = sp[0], s1 = sp[1], s2 = sp[2], s3 = sp[3];
         const float shf[16] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w,
@@ -530,6 +538,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
         const bool two = (c + 1 < nchunks);
         tmem_ld16(taddr + c * 16, v0);
         if (two) tmem_ld16(taddr + (c + 1) * 16, v1);
+        uint4 ra0, ra1, rb0, rb1;
+        load_residual(c, ra0, ra1);
+        if (two) load_residual(c + 1, rb0, rb1);
         tmem_ld_wait();
         if (c + 2 >= nchunks) {  // last round: the accumulator has been read completely
           tc_fence_before();
@@ -540,8 +551,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
           if (v0[0] == 0x12345678u && v1[1] == 0x9abcdef0u) reinterpret_cast<T*>(p.out)[0] = T(1.f);  // keep the loads
           continue;
         }
-        finish_chunk(c, v0);
-        if (two) finish_chunk(c + 1, v1);
+        finish_chunk(c, v0, ra0, ra1);
+        if (two) finish_chunk(c + 1, v1, rb0, rb1);
       }
       if (res_smem) {
         // our generic-proxy READS of the window are complete (values consumed above); the mbarrier arrive/wait pair
@@ -782,7 +793,10 @@ int tapconv_plan(const TapConvLayer& L, TapConvParams* pp) {
   }();
   const uint32_t limit = (uint32_t)kSmemLimit - (p.stage_out ? stg_bytes : 0u);
   int stages = 0;
-  for (int s = (L.ring ? kMaxStages : max_stages); s >= 1; --s) {
+  // ResConv layers hold a window stage until the epilogue - up to three tiles behind the MMAs - has read the residual
+  // from it, so they take up to six stages (r01_v14, block 3 at batch 8: 93.2 -> 87.8 -> 82.9 us with 4 / 5 / 6)
+  const int cap = L.ring ? kMaxStages : (L.epi_mode == EPI_RESCONV ? kMaxStages : max_stages);
+  for (int s = cap; s >= 1; --s) {
     if (p.off_a + (uint32_t)s * p.stage_bytes <= limit) {
       stages = s;
       break;

@@ -48,7 +48,7 @@ def _peaks():
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -60,7 +60,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -69,15 +69,32 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            cells = [c.strip() for c in line.split(",")]
+            try:  # nvidia-smi's own time stamp (local time), not the arrival time of a possibly buffered pipe
+                import datetime
+                ts = datetime.datetime.strptime(cells[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except Exception:
+                ts = time.time()
+            self.rows.append((ts, cells))
 
-    def stop(self):
+    def wait_first(self, timeout=3.0):
+        """nvidia-smi needs ~1 s before its first row: block until the sampler is actually sampling."""
+        t0 = time.time()
+        while self.proc and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
+    def stop(self, t_begin=None, t_end=None):
+        """Median SM clock and throttle reasons of the samples taken inside [t_begin, t_end] (the timed region)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = [r for ts, r in self.rows if t_begin is None or t_begin <= ts <= t_end + 0.03]
+        scope = "timed region"
+        if not rows:  # region shorter than the sampling period: fall back to every sample of the run
+            rows, scope = [r for _, r in self.rows], "whole run (no sample fell inside the timed region)"
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except Exception:
@@ -88,7 +105,7 @@ class ClockSampler:
         # "under load" = samples above the idle clock
         load = [v for v in sm if v > 0.5 * max(sm)] if sm else []
         return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "scope": scope}
 
 
 def _pick_threads(sd):
@@ -112,22 +129,25 @@ def _pick_threads(sd):
     return best, ncpu
 
 
-def cpu_port_fps(clip, sd, steps, warmup):
-    """The CPU restatement of the reference path (== reference PyTorch-CPU eager, fp32) on the host cores."""
+def cpu_port_fps(clip, sd, steps, warmup, min_seconds=0.0):
+    """The CPU restatement of the reference path (== reference PyTorch-CPU eager, fp32) on the host cores.
+    Runs `steps` timed repetitions, and more until `min_seconds` of timed CPU work (at most 16 repetitions)."""
     import torch
     from oracle import rife46 as O
     threads, ncpu = _pick_threads(sd)
     torch.set_num_threads(threads)
     sample = clip[:CPU_SAMPLE_FRAMES].contiguous()
     times = []
-    for i in range(warmup + steps):
+    i = 0
+    while i < warmup + steps or (sum(times) < min_seconds and len(times) < 16):
         t0 = time.perf_counter()
         O.rife_vfi(sd, sample, multiplier=2, arch=CPU_ARCH)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
+        i += 1
     n = CPU_SAMPLE_FRAMES - 1
-    return n * len(times) / sum(times), sum(times) / len(times), threads, ncpu
+    return n * len(times) / sum(times), sum(times) / len(times), threads, ncpu, len(times)
 
 
 def main():
@@ -167,7 +187,7 @@ def main():
         if rank != 0:
             return
         clip = O.synthetic_clip(CPU_SAMPLE_FRAMES, H, W, seed=1234)
-        fps, sec, cores, ncpu = cpu_port_fps(clip, sd, max(a.steps, 1), max(a.warmup, 1))
+        fps, sec, cores, ncpu, _reps = cpu_port_fps(clip, sd, max(a.steps, 1), max(a.warmup, 1))
         line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": 0, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
@@ -228,16 +248,22 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.wait_first()
+    barrier()
+    step_device()  # one more untimed step on every rank: the GPUs are under load again when the sampled region starts
+    barrier()
     l0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.time()
     e0.record()
     for _ in range(a.steps):
         step_device()
     e1.record()
     barrier()
+    t_end = time.time()
     launches = eng.launch_count() - l0
     ms_dev = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
 
     # ---- end to end through the host C-ABI call ("e2e")
     host_in = clip.contiguous().pin_memory()
@@ -319,11 +345,11 @@ def main():
 
         cpu = None
         if world == 1 and not a.no_cpu:
-            fps, sec, cores, ncpu = cpu_port_fps(clip, sd, 1, 1)
+            fps, sec, cores, ncpu, reps = cpu_port_fps(clip, sd, 0, 1, min_seconds=10.0)
             cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{CPU_SAMPLE_FRAMES - 1} pairs of the same 1080p clip, 1 warm-up + 1 timed repetition "
-                             f"({sec:.1f} s), oracle/rife46.py == reference PyTorch-CPU path, {cores} threads "
-                             f"(fastest of 8..{ncpu} on this host)"}
+                   "sample": f"{CPU_SAMPLE_FRAMES - 1} pairs of the same 1080p clip, 1 warm-up + {reps} timed repetitions "
+                             f"({sec * reps:.1f} s of CPU work), oracle/rife46.py == reference PyTorch-CPU path, {cores} "
+                             f"threads (fastest of 8..{ncpu} on this host)"}
 
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -11,6 +11,8 @@ SYMBOLS = [
     "vfi_rife46_load", "vfi_rife_load", "vfi_rife46_forward", "vfi_rife46_interpolate_host", "vfi_warp_bilinear_border",
     "vfi_softsplat_sum", "vfi_costvol_l1", "vfi_corr_dot", "vfi_sepconv",
     "vfi_rife46_debug_layer", "vfi_rife46_debug_state", "vfi_rife46_layer_plan", "vfi_sync",
+    "vfi_film_load", "vfi_film_forward", "vfi_film_debug_set_ref", "vfi_film_debug_conv", "vfi_film_layer_plan",
+    "vfi_film_last_macs",
 ]
 
 _lib = None
@@ -51,8 +53,15 @@ def lib():
     L.vfi_rife46_layer_plan.argtypes = [vp, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32),
                                         C.POINTER(i32), C.POINTER(i64)]
     L.vfi_sync.argtypes = [vp]
+    L.vfi_film_load.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i32, i32]
+    L.vfi_film_forward.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp]
+    L.vfi_film_debug_set_ref.argtypes = [vp, i32]
+    L.vfi_film_debug_conv.argtypes = [vp, i32, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp]
+    L.vfi_film_layer_plan.argtypes = [vp, i32, i32] + [C.POINTER(i32)] * 10
+    L.vfi_film_last_macs.argtypes = [vp]
+    L.vfi_film_last_macs.restype = i64
     for name in SYMBOLS:
-        if name not in ("vfi_last_error", "vfi_version", "vfi_launch_count"):
+        if name not in ("vfi_last_error", "vfi_version", "vfi_launch_count", "vfi_film_last_macs"):
             getattr(L, name).restype = i32
     _lib = L
     return L

@@ -7,6 +7,8 @@
 #include <string>
 #include <vector>
 
+struct vfi_ctx;
+
 namespace vfi {
 
 // ---------------------------------------------------------------------------------------------
@@ -144,6 +146,83 @@ cudaError_t launch_volume81(bool dot, const float* one, const float* two, float*
 cudaError_t launch_sepconv(const float* in, const float* ver, const float* hor, float* out, int N, int C, int H, int W,
                            int Kv, int Kh, cudaStream_t st);
 
+
+// ---------------------------------------------------------------------------------------------
+// streamconv (streamconv.cu): k x k 'same' convolution with streamed weights - the FILM conv kernel.
+//   out[b, y, x, n] = act( bias[n] + sum_{tap, c} in[b, y+dy, x+dx, c] * W[tap, c, n] ),  in = cat(src0[:c0], src1[:c1])
+// ---------------------------------------------------------------------------------------------
+struct StreamConvLayer {
+  int ksize = 3;          // 1, 2 or 3; padding='same' (film_arch.py:784-790)
+  int c0 = 0, c1 = 0;     // input channels taken from source 0 / source 1 (multiples of 64; c1 may be 0)
+  int n_total = 0;        // output channels (multiple of 16; padded with zero weights where the layer has fewer)
+  int act = 1;            // 1: LeakyReLU(0.2), 0: none
+  void* w = nullptr;      // device, packed [split][k-block][tap][n_cta][64 ch, 16-byte chunks XOR (n & 7)] 16-bit
+  float* shift = nullptr; // device, [n_total] bias
+};
+
+struct alignas(64) StreamConvParams {
+  CUtensorMap tm[2];      // sources as {C, W, H, B} tensors, box {64, halo_w, halo_h, 1}, SWIZZLE_128B
+  const void* src[2];     // (checker kernel) source pointers and pixel pitches in elements
+  int src_pitch[2];
+  void* out;              // 16-bit NHWC, channel 0 of this layer's slice
+  int out_pitch;          // elements per pixel of the output tensor
+  const void* w;
+  const float* shift;
+  size_t w_split_bytes;   // packed weight bytes of one output-channel split
+  int B, H, W;
+  int ksize, ntaps, nkb0, nkb;
+  int n_total, n_cta, nsplit, act;
+  int halo_y0, halo_x0, halo_h, halo_w;
+  int mt, nsets;          // tiles per CTA pass (accumulators sharing a weight slot), accumulator sets (epilogue overlap)
+  int a_slots, b_slots;
+  int tiles_x, tiles_y, ntiles, npasses, ctas_per_split;
+  uint32_t idesc, tmem_cols, acc_stride;
+  uint32_t a_tx_bytes, a_win_bytes, a_slot_bytes, b_slot_bytes;
+  uint32_t off_ss, off_b, off_a, smem_bytes;
+  uint32_t a_hi;          // high word of the A descriptors
+  uint32_t tap_off[9];    // start-address offset of each tap inside a window, 16-byte units
+};
+
+bool streamconv_plan(const StreamConvLayer& L, StreamConvParams* p_out);
+cudaError_t launch_streamconv(const StreamConvLayer& L, int op_type, const void* src0, int pitch0, const void* src1,
+                              int pitch1, void* out, int out_pitch, int B, int H, int W, int num_sms, bool use_ref,
+                              cudaStream_t st);
+
+// ---- FILM element-wise kernels (film_elem.cu); 16-bit tensors are NHWC slices {pointer, pixel pitch in elements} ----
+struct FilmFrameIdx {  // source frame of every image of a pass (first frames of all pairs, then second frames)
+  int i[2 * 16];
+};
+cudaError_t launch_film_gather_rgb(const float* frames, int cstride, const FilmFrameIdx& idx, int n, int H, int W,
+                                   float* out, cudaStream_t st);
+cudaError_t launch_film_pool_rgb(const float* in, float* out, int n, int H, int W, cudaStream_t st);
+cudaError_t launch_film_conv_rgb(int op_type, const float* img, const float* w, const float* bias, void* out,
+                                 int out_pitch, int n, int H, int W, cudaStream_t st);
+cudaError_t launch_film_pool16(int op_type, const void* in, int in_pitch, void* out, int out_pitch, int C, int n, int H,
+                               int W, cudaStream_t st);
+cudaError_t launch_film_flow_up(const float* v, int h, int w, float* out, int B, int H, int W, cudaStream_t st);
+cudaError_t launch_film_warp16(int op_type, const void* src, int src_pitch, int C, const float* flow, float fscale,
+                               void* dst, int dst_pitch, int B, int H, int W, cudaStream_t st);
+cudaError_t launch_film_misc64(int op_type, const float* img0, const float* img1, const float* bflow,
+                               const float* fflow, void* dst, int dst_pitch, int B, int H, int W, cudaStream_t st);
+cudaError_t launch_film_nearest16(const void* in, int h, int w, void* out, int C, int B, int H, int W, cudaStream_t st);
+cudaError_t launch_film_flow_head(int op_type, const void* x, int pitch, int C, const float* w, const float* bias,
+                                  const float* v_up, float* v_out, int B, int H, int W, cudaStream_t st);
+cudaError_t launch_film_out_rgb(int op_type, const void* x, int pitch, const float* w, const float* bias, int clamp01,
+                                float* out, int B, int H, int W, cudaStream_t st);
+
 void set_error(const std::string& s);
+
+// ---- context access for film.cu (vfi_ctx is defined in rife46.cu) ----
+struct FilmState;
+struct CtxInfo {
+  int device, num_sms;
+  cudaStream_t s_h2d, s_comp, s_d2h;
+};
+void film_destroy(FilmState* f);  // film.cu
+
+
+CtxInfo ctx_info(::vfi_ctx* c);
+FilmState*& ctx_film(::vfi_ctx* c);
+void ctx_add_launches(::vfi_ctx* c, int n);
 
 }  // namespace vfi

@@ -162,3 +162,108 @@ class Rife46Engine:
 
     def sync(self):
         check(self._L.vfi_sync(self._ctx))
+
+
+# ------------------------------------------------------------------------------------------------- FILM
+def film_state_dict_names():
+    """film_arch.Interpolator().state_dict() order (film_arch.py:91-100, :515-528, :550-565, :222-256, :391-393)."""
+    names = []
+    for i in range(4):
+        for j in range(2):
+            names += [f"extract.extract_sublevels.convs.{i}.{j}.0.weight", f"extract.extract_sublevels.convs.{i}.{j}.0.bias"]
+    for prefix in ["predict_flow._predictor"] + [f"predict_flow._predictors.{k}" for k in range(3)]:
+        for j in range(4):
+            names += [f"{prefix}._convs.{j}.0.weight", f"{prefix}._convs.{j}.0.bias"]
+        names += [f"{prefix}._convs.4.weight", f"{prefix}._convs.4.bias"]
+    names += ["fuse.output_conv.weight", "fuse.output_conv.bias"]
+    for k in range(4):
+        names += [f"fuse.convs.{k}.0.weight", f"fuse.convs.{k}.0.bias"]
+        for j in (1, 2):
+            names += [f"fuse.convs.{k}.{j}.0.weight", f"fuse.convs.{k}.{j}.0.bias"]
+    return names
+
+
+class FilmEngine:
+    """FILM (film_net_fp32.pt) on one B200: `state_dict` = the TorchScript module's / Interpolator's state_dict."""
+
+    MAX_PAIRS = 16
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device: int = 0, dtype: str = "float32"):
+        if not torch.cuda.is_available():
+            raise VfiError("no CUDA device: this path has no CPU fallback")
+        if dtype not in OPERAND:
+            raise ValueError(f"dtype must be one of {list(OPERAND)}")
+        self._L = lib()
+        self.device = int(device)
+        self._ctx = C.c_void_p()
+        check(self._L.vfi_create(self.device, C.byref(self._ctx)))
+        names = film_state_dict_names()
+        missing = [n for n in names if n not in state_dict]
+        if missing:
+            raise KeyError(f"state_dict is not a FILM checkpoint; missing {missing[:3]} ...")
+        hold = [state_dict[n].detach().to("cpu", torch.float32).contiguous() for n in names]
+        ptrs = (C.c_void_p * len(hold))(*[t.data_ptr() for t in hold])
+        numel = (C.c_int64 * len(hold))(*[t.numel() for t in hold])
+        check(self._L.vfi_film_load(self._ctx, ptrs, numel, len(hold), OPERAND[dtype]))
+        self.dtype = dtype
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self._L.vfi_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def forward(self, frames: torch.Tensor, f0: Sequence[int], f1: Sequence[int], clamp: bool = False,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """frames: CUDA float32 [N,H,W,C>=3] NHWC -> CUDA float32 [len(f0),H,W,3]: the midpoint frame of every pair
+        (Interpolator.forward, film_arch.py:458-459), optionally clamped to [0,1] as the node does (film/__init__.py:38)."""
+        assert frames.is_cuda and frames.dtype == torch.float32 and frames.is_contiguous() and frames.dim() == 4
+        n, h, w, c = frames.shape
+        f0a, f1a = _i32(f0), _i32(f1)
+        npairs = len(f0a)
+        assert npairs == len(f1a) and 1 <= npairs <= self.MAX_PAIRS
+        if out is None:
+            out = torch.empty((npairs, h, w, 3), dtype=torch.float32, device=frames.device)
+        assert out.is_cuda and out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == (npairs, h, w, 3)
+        st = torch.cuda.current_stream(frames.device).cuda_stream
+        check(self._L.vfi_film_forward(self._ctx, frames.data_ptr(), n, h, w, c, f0a.ctypes.data, f1a.ctypes.data, npairs,
+                                       1 if clamp else 0, out.data_ptr(), st))
+        return out
+
+    def midpoint(self, x0: torch.Tensor, x1: torch.Tensor) -> torch.Tensor:
+        """[H,W,3] x 2 (CUDA float32) -> clamped midpoint [H,W,3]: one `model(x0, x1, dt).clamp(0, 1)` of the node."""
+        pair = torch.stack([x0, x1]).contiguous()
+        return self.forward(pair, [0], [1], clamp=True)[0]
+
+    # ------------------------------------------------------------------ hooks
+    def set_ref(self, use_ref: bool):
+        check(self._L.vfi_film_debug_set_ref(self._ctx, 1 if use_ref else 0))
+
+    def debug_conv(self, group, layer, src0, src1, out, B, H, W, impl=0, pitch0=None, pitch1=None, out_pitch=None):
+        st = torch.cuda.current_stream(src0.device).cuda_stream
+        check(self._L.vfi_film_debug_conv(
+            self._ctx, group, layer, src0.data_ptr(), int(pitch0 if pitch0 is not None else src0.shape[-1]),
+            None if src1 is None else src1.data_ptr(),
+            0 if src1 is None else int(pitch1 if pitch1 is not None else src1.shape[-1]),
+            out.data_ptr(), int(out_pitch if out_pitch is not None else out.shape[-1]), B, H, W, impl, st))
+        return out
+
+    def layer_plan(self, group, layer):
+        v = [C.c_int() for _ in range(10)]
+        check(self._L.vfi_film_layer_plan(self._ctx, group, layer, *[C.byref(x) for x in v]))
+        keys = ("c0", "c1", "n_total", "ksize", "n_cta", "nsplit", "mt", "a_slots", "b_slots", "smem_bytes")
+        return dict(zip(keys, [x.value for x in v]))
+
+    def last_macs(self) -> int:
+        return int(self._L.vfi_film_last_macs(self._ctx))
+
+    def launch_count(self) -> int:
+        return int(self._L.vfi_launch_count(self._ctx))
+
+    def sync(self):
+        check(self._L.vfi_sync(self._ctx))

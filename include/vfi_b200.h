@@ -105,6 +105,31 @@ int vfi_corr_dot(vfi_ctx* ctx, const float* first, const float* second, float* o
 int vfi_sepconv(vfi_ctx* ctx, const float* in, const float* ver, const float* hor, float* out, int N, int C, int H,
                 int W, int Kv, int Kh, void* stream);
 
+/* FILM (film_net) - SURVEY.md section 8 row a10 --------------------------------------------------------- */
+#define VFI_FILM_NUM_TENSORS 82      /* film_arch.Interpolator().state_dict() (film_arch.py:377-393) */
+/* Replaces: torch.jit.load(film_net_fp32.pt) - film/__init__.py:74.  `tensors[i]` are HOST float32 arrays in the
+ * order of Interpolator.state_dict() (extract.extract_sublevels.convs.{0..3}.{0,1}.0.{weight,bias}, predict_flow.
+ * _predictor._convs.{0..3}.0 / .4, predict_flow._predictors.{0,1,2}._convs..., fuse.output_conv, fuse.convs.{0..3}.
+ * {0, 1.0, 2.0}); sizes are checked.  Weights are repacked to the streamed tensor-core operand layout. */
+int vfi_film_load(vfi_ctx* ctx, const float* const* tensors, const int64_t* numel, int n_tensors, int operand_type);
+/* Replaces: `model(x0, x1, dt)` in film/__init__.py:35-38 (Interpolator.forward, film_arch.py:458-459; the network
+ * always predicts the midpoint, `dt` is not an input) for n_pairs independent pairs, optionally followed by the
+ * node's clamp(0, 1) (:38).  DEVICE pointers: frames [n_frames, H, W, C] float32 NHWC (C >= 3, first three channels
+ * read, vfi_utils.py:139), out [n_pairs, H, W, 3] float32 NHWC; f0 / f1: HOST index arrays.  H, W >= 64 (seven
+ * pyramid levels), any other size as in the reference.  Asynchronous on `stream`. */
+int vfi_film_forward(vfi_ctx* ctx, const float* frames, int n_frames, int H, int W, int C, const int32_t* f0,
+                     const int32_t* f1, int n_pairs, int clamp01, float* out, void* stream);
+/* Test / profiling hooks: route every FILM conv through the CUDA-core checker (1) or the tcgen05 kernel (0); run one
+ * conv layer (group 0 = extract: layer 2*j + {0,1}; 1 = flow estimators: 4*predictor + conv; 2 = fusion: 3*k + conv)
+ * on caller tensors (16-bit NHWC channel slices: pointer + pixel pitch in elements); static plan of a layer; tensor-core
+ * MACs (unpadded channels) of the last forward. */
+int vfi_film_debug_set_ref(vfi_ctx* ctx, int use_ref);
+int vfi_film_debug_conv(vfi_ctx* ctx, int group, int layer, const void* src0, int pitch0, const void* src1, int pitch1,
+                        void* out, int out_pitch, int B, int H, int W, int impl, void* stream);
+int vfi_film_layer_plan(vfi_ctx* ctx, int group, int layer, int* c0, int* c1, int* n_total, int* ksize, int* n_cta,
+                        int* nsplit, int* mt, int* a_slots, int* b_slots, int* smem_bytes);
+int64_t vfi_film_last_macs(const vfi_ctx* ctx);
+
 /* Test / profiling hooks (used by tests/ and bench.py only) --------------------------------------------- */
 /* Run ONE convolution layer of block `block` (0..3; arch 4.26: 0..4): layer 0 = conv0.0, 1 = conv0.1, 2..9 = ResConv
  * 0..7, 10 = lastconv (flow + mask), 11 = arch 4.26 blocks 0..3: the 8 feature channels of lastconv, written as

@@ -12,7 +12,7 @@ SYMBOLS = [
     "vfi_softsplat_sum", "vfi_costvol_l1", "vfi_corr_dot", "vfi_sepconv",
     "vfi_rife46_debug_layer", "vfi_rife46_debug_state", "vfi_rife46_layer_plan", "vfi_sync",
     "vfi_film_load", "vfi_film_forward", "vfi_film_debug_set_ref", "vfi_film_debug_conv", "vfi_film_layer_plan",
-    "vfi_film_last_macs",
+    "vfi_film_last_macs", "vfi_film_debug_pack_host",
 ]
 
 _lib = None
@@ -59,6 +59,7 @@ def lib():
     L.vfi_film_debug_conv.argtypes = [vp, i32, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp]
     L.vfi_film_layer_plan.argtypes = [vp, i32, i32] + [C.POINTER(i32)] * 10
     L.vfi_film_last_macs.argtypes = [vp]
+    L.vfi_film_debug_pack_host.argtypes = [i32, i32, i32, i32, i32, i32, vp, i32, i32, vp, i64] + [C.POINTER(i32)] * 4
     L.vfi_film_last_macs.restype = i64
     for name in SYMBOLS:
         if name not in ("vfi_last_error", "vfi_version", "vfi_launch_count", "vfi_film_last_macs"):

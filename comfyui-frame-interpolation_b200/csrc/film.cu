@@ -127,22 +127,24 @@ int fupload(FilmState* f, const T* h, size_t n, void** dptr) {
   return VFI_OK;
 }
 
-// Builds one streamconv layer from a PyTorch Conv2d weight [cout][cin][k][k] + bias [cout].
-// kmap[j] = reference input channel of padded input channel j (or -1: zero weight); size c0 + c1.
-int build_conv(FilmState* f, StreamConvLayer& L, int ksize, int c0, int c1, int n_total, int act, const float* w,
-               const float* bias, int cout, int cin, const std::vector<int>& kmap) {
-  L = StreamConvLayer{};
+// Packs a PyTorch Conv2d weight [cout][cin][k][k] into streamconv's operand layout (host only, no CUDA calls):
+// [split][k-block][tap][n_cta rows][64 channels, 16-byte chunks XOR (row & 7)], zero where the padded input channel
+// has no reference channel (kmap[j] = -1) or the padded output column no filter (n >= cout).
+int pack_conv(int op_type, int ksize, int c0, int c1, int n_total, const float* w, int cout, int cin,
+              const std::vector<int>& kmap, std::vector<uint16_t>* out, StreamConvParams* plan) {
+  StreamConvLayer L;
   L.ksize = ksize;
   L.c0 = c0;
   L.c1 = c1;
   L.n_total = n_total;
-  L.act = act;
-  StreamConvParams p{};
+  StreamConvParams& p = *plan;
+  p = StreamConvParams{};
   if (!streamconv_plan(L, &p)) return ffail(VFI_E_INVALID, "film: layer shape not supported by streamconv");
   if ((int)kmap.size() != c0 + c1) return ffail(VFI_E_INVALID, "film: channel map size");
   const int ntaps = ksize * ksize;
   const size_t per_split = (size_t)p.nkb * ntaps * p.n_cta * 64;
-  std::vector<uint16_t> pk((size_t)p.nsplit * per_split, 0);
+  std::vector<uint16_t>& pk = *out;
+  pk.assign((size_t)p.nsplit * per_split, 0);
   for (int sp = 0; sp < p.nsplit; ++sp)
     for (int kb = 0; kb < p.nkb; ++kb)
       for (int tap = 0; tap < ntaps; ++tap)
@@ -156,12 +158,29 @@ int build_conv(FilmState* f, StreamConvLayer& L, int ksize, int c0, int c1, int 
             if (ci >= cin) return ffail(VFI_E_INVALID, "film: channel map out of range");
             // tap = ky * k + kx, PyTorch weight [n][ci][ky][kx]
             const float val = w[((size_t)n * cin + ci) * ntaps + tap];
-            row[(((c >> 3) ^ (nl & 7)) * 8) + (c & 7)] = to_op(val, f->op_type);
+            row[(((c >> 3) ^ (nl & 7)) * 8) + (c & 7)] = to_op(val, op_type);
           }
         }
+  return VFI_OK;
+}
+
+// Builds one streamconv layer (packed weights + bias on the device) from a PyTorch Conv2d weight and bias.
+// kmap[j] = reference input channel of padded input channel j (or -1: zero weight); size c0 + c1.
+int build_conv(FilmState* f, StreamConvLayer& L, int ksize, int c0, int c1, int n_total, int act, const float* w,
+               const float* bias, int cout, int cin, const std::vector<int>& kmap) {
+  L = StreamConvLayer{};
+  L.ksize = ksize;
+  L.c0 = c0;
+  L.c1 = c1;
+  L.n_total = n_total;
+  L.act = act;
+  StreamConvParams p{};
+  std::vector<uint16_t> pk;
+  int rc = pack_conv(f->op_type, ksize, c0, c1, n_total, w, cout, cin, kmap, &pk, &p);
+  if (rc) return rc;
   std::vector<float> sh(n_total, 0.f);
   for (int n = 0; n < cout && n < n_total; ++n) sh[n] = bias[n];
-  int rc = fupload(f, pk.data(), pk.size(), &L.w);
+  rc = fupload(f, pk.data(), pk.size(), &L.w);
   if (rc) return rc;
   void* d = nullptr;
   rc = fupload(f, sh.data(), sh.size(), &d);
@@ -517,6 +536,39 @@ int vfi_film_layer_plan(vfi_ctx* c, int group, int layer, int* c0, int* c1, int*
   if (a_slots) *a_slots = p.a_slots;
   if (b_slots) *b_slots = p.b_slots;
   if (smem_bytes) *smem_bytes = (int)p.smem_bytes;
+  return VFI_OK;
+}
+
+/* Host-only (no GPU needed): the weight packer and channel maps of vfi_film_load on caller data.  layout 0: input
+ * channels in reference order, `cin` real of c0 = ceil64(cin) padded; layout 1: the fusion input of a level with C
+ * feature channels per frame, [wfeat0 C | wfeat1 C | misc 64] (+ nf channels of the decoder state in a second tensor). */
+int vfi_film_debug_pack_host(int layout, int C, int nf, int ksize, int n_total, int operand_type, const float* w,
+                             int cout, int cin, uint16_t* out, int64_t out_cap, int* c0, int* c1, int* n_cta,
+                             int* nsplit) {
+  if (!w || !out) return ffail(VFI_E_INVALID, "null argument");
+  std::vector<int> m;
+  int k0 = 0, k1 = 0;
+  if (layout == 0) {
+    k0 = (cin + 63) / 64 * 64;
+    m = identity_map(cin, k0);
+  } else if (layout == 1) {
+    m = aligned_map(C);
+    k0 = 2 * C + 64;
+    k1 = nf;
+    for (int j = 0; j < nf; ++j) m.push_back(2 * C + 10 + j);
+  } else {
+    return ffail(VFI_E_INVALID, "layout");
+  }
+  std::vector<uint16_t> pk;
+  StreamConvParams p{};
+  const int rc = pack_conv(operand_type, ksize, k0, k1, n_total, w, cout, cin, m, &pk, &p);
+  if (rc) return rc;
+  if ((int64_t)pk.size() > out_cap) return ffail(VFI_E_INVALID, "output buffer too small");
+  std::memcpy(out, pk.data(), pk.size() * 2);
+  if (c0) *c0 = k0;
+  if (c1) *c1 = k1;
+  if (n_cta) *n_cta = p.n_cta;
+  if (nsplit) *nsplit = p.nsplit;
   return VFI_OK;
 }
 

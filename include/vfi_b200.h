@@ -129,6 +129,12 @@ int vfi_film_debug_conv(vfi_ctx* ctx, int group, int layer, const void* src0, in
 int vfi_film_layer_plan(vfi_ctx* ctx, int group, int layer, int* c0, int* c1, int* n_total, int* ksize, int* n_cta,
                         int* nsplit, int* mt, int* a_slots, int* b_slots, int* smem_bytes);
 int64_t vfi_film_last_macs(const vfi_ctx* ctx);
+/* Host-only: vfi_film_load's weight packer on caller data (layout 0 = reference channel order padded to 64; layout 1 = a
+ * fusion level's [wfeat0 C | wfeat1 C | misc 64] + nf decoder channels); `out` receives the packed 16-bit operand:
+ * [split][k-block][tap][n_cta][64 ch, 16-byte chunks XOR (row & 7)]. */
+int vfi_film_debug_pack_host(int layout, int C, int nf, int ksize, int n_total, int operand_type, const float* w,
+                             int cout, int cin, uint16_t* out, int64_t out_cap, int* c0, int* c1, int* n_cta,
+                             int* nsplit);
 
 /* Test / profiling hooks (used by tests/ and bench.py only) --------------------------------------------- */
 /* Run ONE convolution layer of block `block` (0..3; arch 4.26: 0..4): layer 0 = conv0.0, 1 = conv0.1, 2..9 = ResConv

@@ -106,3 +106,70 @@ def forward_and_gather(run_slice, local_out: torch.Tensor, counts: Sequence[int]
     if cuda:
         torch.cuda.current_stream(local_out.device).wait_stream(comm)
     return gathered if rank == dst else None
+
+
+# ------------------------------------------------------------------------------------------------- FILM
+def shard_pairs_by_cost(costs: Sequence[float], world: int) -> List[Tuple[int, int]]:
+    """Contiguous [lo, hi) pair ranges, one per rank, balancing the summed cost (FILM: a pair costs multiplier - 1
+    forward calls, a skipped pair none - film/__init__.py:84-96).  Greedy on the running prefix: rank r ends at the
+    first pair where the prefix reaches (r + 1) / world of the total; trailing ranks may get empty ranges."""
+    n = len(costs)
+    total = float(sum(costs))
+    out, lo, acc = [], 0, 0.0
+    for r in range(world):
+        hi = lo
+        if r == world - 1:
+            hi = n
+        else:
+            target = total * (r + 1) / world
+            while hi < n and acc + costs[hi] <= target + 1e-9:
+                acc += costs[hi]
+                hi += 1
+            # take the pair that crosses the target if that leaves the split closer to it
+            if hi < n and hi < n - (world - 1 - r) + 1 and (target - acc) > (acc + costs[hi] - target):
+                acc += costs[hi]
+                hi += 1
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def film_vfi_sharded(run_node, frames: torch.Tensor, multiplier, states, dist, dst: int = 0, device=None):
+    """FILM_VFI.vfi over the ranks of one box: frame pairs (with their whole bisection schedules) are independent, so
+    every rank runs the node on a contiguous sub-clip (one-frame halo) and the only exchange is the gather of the output
+    frames on `dst`.  `run_node(sub_frames, sub_multipliers, sub_states) -> [M_r, H, W, 3]` is the node call
+    (`FILM_VFI().vfi(...)[0]`); `states` is None or (frame_indices, is_skip_list).  Returns the full output on `dst`
+    (identical to the unsharded node's), None elsewhere."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n = frames.shape[0]
+    if isinstance(multiplier, int):
+        mults = [multiplier] * (n - 1)
+    else:
+        mults = list(map(int, multiplier))[: n - 1]
+        mults += [2] * (n - 1 - len(mults))
+
+    def skipped(i):
+        if states is None:
+            return False
+        idx, is_skip = states
+        return (is_skip and i in idx) or (not is_skip and i not in idx)
+
+    costs = [0.0 if skipped(i) else float(max(mults[i], 1) - 1) + 0.01 for i in range(n - 1)]
+    counts_of = lambda lo, hi: sum(0 if skipped(i) else max(mults[i], 1) for i in range(lo, hi))  # noqa: E731
+    slices = shard_pairs_by_cost(costs, world)
+    lo, hi = slices[rank]
+    sub_states = None
+    if states is not None:
+        # keep-lists must stay keep-lists: list every pair of the sub-clip that is kept / skipped explicitly
+        sub_states = ([i - lo for i in range(lo, hi) if skipped(i)], True)
+    local = run_node(frames[lo:hi + 1], mults[lo:hi], sub_states)[:-1]  # the trailing frame belongs to the next rank
+    counts = [counts_of(a, b) for a, b in slices]
+    assert local.shape[0] == counts[rank], (local.shape, counts, rank)
+    if device is not None:
+        local = local.to(device)
+    if local.shape[0] == 0:
+        local = torch.zeros((0,) + tuple(frames.shape[1:3]) + (3,), dtype=torch.float32, device=local.device)
+    full = gather_frames(local.contiguous(), counts, dist, dst)
+    if rank != dst:
+        return None
+    return torch.cat([full.cpu(), frames[-1:, ..., :3].to(torch.float32)], 0)  # film/__init__.py:104

@@ -4,10 +4,12 @@ Exports the same mapping names ComfyUI discovers in the reference's root __init_
 """
 from .node import RIFE_VFI, MakeInterpolationStateList, FloatToInt, InterpolationStateList  # noqa: F401
 from .film_node import FILM_VFI  # noqa: F401
+from .sepconv_node import SepconvVFI  # noqa: F401
 
 NODE_CLASS_MAPPINGS = {
     "RIFE VFI": RIFE_VFI,
     "FILM VFI": FILM_VFI,
+    "Sepconv VFI": SepconvVFI,
     "Make Interpolation State List": MakeInterpolationStateList,
     "VFI FloatToInt": FloatToInt,
 }
@@ -15,4 +17,5 @@ NODE_CLASS_MAPPINGS = {
 NODE_DISPLAY_NAME_MAPPINGS = {
     "RIFE VFI": "RIFE VFI (B200 native, rife4.6)",
     "FILM VFI": "FILM VFI (B200 native)",
+    "Sepconv VFI": "Sepconv VFI (B200 native)",
 }

@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <functional>
 #include <string>
 
 #include "../../include/vfi_b200.h"
@@ -64,6 +65,29 @@ uint16_t to_op(float v, int op_type) {
 }
 
 }  // namespace
+
+// streamconv operand packer shared with sepconv.cu: wfun(n, tap, padded input channel) -> weight
+bool pack_streamconv(const StreamConvLayer& L, int op_type, const std::function<float(int, int, int)>& wfun,
+                     std::vector<uint16_t>* out, StreamConvParams* plan) {
+  StreamConvParams& p = *plan;
+  p = StreamConvParams{};
+  if (!streamconv_plan(L, &p)) return false;
+  const int ntaps = L.ksize * L.ksize;
+  const size_t per_split = (size_t)p.nkb * ntaps * p.n_cta * 64;
+  std::vector<uint16_t>& pk = *out;
+  pk.assign((size_t)p.nsplit * per_split, 0);
+  for (int sp = 0; sp < p.nsplit; ++sp)
+    for (int kb = 0; kb < p.nkb; ++kb)
+      for (int tap = 0; tap < ntaps; ++tap)
+        for (int nl = 0; nl < p.n_cta; ++nl) {
+          uint16_t* row = &pk[sp * per_split + ((size_t)(kb * ntaps + tap) * p.n_cta + nl) * 64];
+          for (int c = 0; c < 64; ++c) {
+            const float val = wfun(sp * p.n_cta + nl, tap, kb * 64 + c);
+            if (val != 0.f) row[(((c >> 3) ^ (nl & 7)) * 8) + (c & 7)] = to_op(val, op_type);
+          }
+        }
+  return true;
+}
 
 struct FilmState {
   int op_type = OP_F16;
@@ -132,35 +156,20 @@ int fupload(FilmState* f, const T* h, size_t n, void** dptr) {
 // has no reference channel (kmap[j] = -1) or the padded output column no filter (n >= cout).
 int pack_conv(int op_type, int ksize, int c0, int c1, int n_total, const float* w, int cout, int cin,
               const std::vector<int>& kmap, std::vector<uint16_t>* out, StreamConvParams* plan) {
+  if ((int)kmap.size() != c0 + c1) return ffail(VFI_E_INVALID, "film: channel map size");
+  for (int ci : kmap)
+    if (ci >= cin) return ffail(VFI_E_INVALID, "film: channel map out of range");
+  const int ntaps = ksize * ksize;
   StreamConvLayer L;
   L.ksize = ksize;
   L.c0 = c0;
   L.c1 = c1;
   L.n_total = n_total;
-  StreamConvParams& p = *plan;
-  p = StreamConvParams{};
-  if (!streamconv_plan(L, &p)) return ffail(VFI_E_INVALID, "film: layer shape not supported by streamconv");
-  if ((int)kmap.size() != c0 + c1) return ffail(VFI_E_INVALID, "film: channel map size");
-  const int ntaps = ksize * ksize;
-  const size_t per_split = (size_t)p.nkb * ntaps * p.n_cta * 64;
-  std::vector<uint16_t>& pk = *out;
-  pk.assign((size_t)p.nsplit * per_split, 0);
-  for (int sp = 0; sp < p.nsplit; ++sp)
-    for (int kb = 0; kb < p.nkb; ++kb)
-      for (int tap = 0; tap < ntaps; ++tap)
-        for (int nl = 0; nl < p.n_cta; ++nl) {
-          const int n = sp * p.n_cta + nl;
-          if (n >= cout) continue;
-          uint16_t* row = &pk[sp * per_split + ((size_t)(kb * ntaps + tap) * p.n_cta + nl) * 64];
-          for (int c = 0; c < 64; ++c) {
-            const int ci = kmap[kb * 64 + c];
-            if (ci < 0) continue;
-            if (ci >= cin) return ffail(VFI_E_INVALID, "film: channel map out of range");
-            // tap = ky * k + kx, PyTorch weight [n][ci][ky][kx]
-            const float val = w[((size_t)n * cin + ci) * ntaps + tap];
-            row[(((c >> 3) ^ (nl & 7)) * 8) + (c & 7)] = to_op(val, op_type);
-          }
-        }
+  if (!pack_streamconv(L, op_type, [&](int n, int tap, int j) -> float {
+        const int ci = kmap[j];  // tap = ky * k + kx, PyTorch weight [n][ci][ky][kx]
+        return (n < cout && ci >= 0) ? w[((size_t)n * cin + ci) * ntaps + tap] : 0.f;
+      }, out, plan))
+    return ffail(VFI_E_INVALID, "film: layer shape not supported by streamconv");
   return VFI_OK;
 }
 

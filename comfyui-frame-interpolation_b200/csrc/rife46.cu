@@ -146,11 +146,13 @@ struct vfi_ctx {
   DevBuf dbgF, dbgM;
   cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
   vfi::FilmState* film = nullptr;  // FILM weights and workspace (film.cu)
+  vfi::SepState* sep = nullptr;    // Sepconv weights and workspace (sepconv.cu)
 };
 
 namespace vfi {
 CtxInfo ctx_info(::vfi_ctx* c) { return CtxInfo{c->device, c->num_sms, c->s_h2d, c->s_comp, c->s_d2h}; }
 FilmState*& ctx_film(::vfi_ctx* c) { return c->film; }
+SepState*& ctx_sep(::vfi_ctx* c) { return c->sep; }
 void ctx_add_launches(::vfi_ctx* c, int n) { c->launches += n; }
 }  // namespace vfi
 
@@ -571,7 +573,7 @@ int check_tasks(const int32_t* f0, const int32_t* f1, int n_tasks, int lo, int h
 extern "C" {
 
 const char* vfi_last_error(void) { return g_err.c_str(); }
-const char* vfi_version(void) { return "vfi_b200 0.1 (sm_100a; RIFE 4.6/4.7/4.17/4.26, FILM; built " __DATE__ " " __TIME__ ")"; }
+const char* vfi_version(void) { return "vfi_b200 0.1 (sm_100a; RIFE 4.6/4.7/4.17/4.26, FILM, Sepconv; built " __DATE__ " " __TIME__ ")"; }
 
 int vfi_create(int device, vfi_ctx** out) {
   if (!out) return fail(VFI_E_INVALID, "null out");
@@ -599,6 +601,8 @@ int vfi_destroy(vfi_ctx* c) {
   free_weights(c);
   film_destroy(c->film);
   c->film = nullptr;
+  sepconv_destroy(c->sep);
+  c->sep = nullptr;
   for (DevBuf* b : {&c->imgs, &c->imgs_h, &c->flow, &c->mask, &c->x, &c->c00, &c->featA, &c->featB, &c->raw, &c->outdev, &c->feats, &c->e16, &c->hA, &c->hB, &c->dbgF,
                     &c->dbgM})
     b->release();

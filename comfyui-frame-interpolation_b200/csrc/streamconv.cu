@@ -81,7 +81,11 @@ __device__ __forceinline__ void ring_next(uint32_t& slot, uint32_t& ph, uint32_t
   }
 }
 
-template <typename T>
+// EXT = false is the FILM kernel as verified in r01 (bias + LeakyReLU(0.2) / identity).  EXT = true adds what the Sepconv
+// trunk needs in the epilogue: a PReLU with one learned slope (a > 0 ? a : slope * a, any sign / size of slope) and a
+// residual tensor added after it (same layout as the output; it may BE the output: every thread reads its 16 channels
+// before it writes them).
+template <typename T, bool EXT>
 __global__ void __launch_bounds__(kSThreads, 1) streamconv_kernel(const __grid_constant__ StreamConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   SCtrl* ctrl = reinterpret_cast<SCtrl*>(smem);
@@ -230,8 +234,9 @@ __global__ void __launch_bounds__(kSThreads, 1) streamconv_kernel(const __grid_c
         const bool valid = (tc.b < p.B) && (gy < p.H) && (gx < p.W);
         mbar_wait(bar_tfull + 8 * set, (uint32_t)((k / nsets) & 1), 17);
         tc_fence_after();
-        T* orow = reinterpret_cast<T*>(p.out) +
-                  (valid ? (((size_t)tc.b * p.H + gy) * p.W + gx) * (size_t)p.out_pitch + (size_t)n0 : 0);
+        const size_t opix = valid ? (((size_t)tc.b * p.H + gy) * p.W + gx) * (size_t)p.out_pitch + (size_t)n0 : 0;
+        T* orow = reinterpret_cast<T*>(p.out) + opix;
+        const T* rrow = reinterpret_cast<const T*>(p.res) + opix;  // EXT only
         for (int c = 0; c < nchunks; c += 2) {
           uint32_t v0[16], v1[16];
           const bool two = (c + 1 < nchunks);
@@ -249,11 +254,30 @@ __global__ void __launch_bounds__(kSThreads, 1) streamconv_kernel(const __grid_c
             const float shf[16] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w,
                                    s2.x, s2.y, s2.z, s2.w, s3.x, s3.y, s3.z, s3.w};
             uint32_t o[8];
+            if constexpr (EXT) {
+              uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+              if (p.res != nullptr && valid) {
+                r0 = *reinterpret_cast<const uint4*>(rrow + cc * 16);
+                r1 = *reinterpret_cast<const uint4*>(rrow + cc * 16 + 8);
+              }
+              const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+              const float ps = p.slope;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float a0 = __uint_as_float(vv[2 * j]) + shf[2 * j];
-              const float a1 = __uint_as_float(vv[2 * j + 1]) + shf[2 * j + 1];
-              o[j] = Pack2<T>::pack(fmaxf(a0, slope * a0), fmaxf(a1, slope * a1));
+              for (int j = 0; j < 8; ++j) {
+                float a0 = __uint_as_float(vv[2 * j]) + shf[2 * j];
+                float a1 = __uint_as_float(vv[2 * j + 1]) + shf[2 * j + 1];
+                a0 = a0 > 0.f ? a0 : ps * a0;
+                a1 = a1 > 0.f ? a1 : ps * a1;
+                const float2 rf = Pack2<T>::unpack(rw[j]);
+                o[j] = Pack2<T>::pack(a0 + rf.x, a1 + rf.y);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float a0 = __uint_as_float(vv[2 * j]) + shf[2 * j];
+                const float a1 = __uint_as_float(vv[2 * j + 1]) + shf[2 * j + 1];
+                o[j] = Pack2<T>::pack(fmaxf(a0, slope * a0), fmaxf(a1, slope * a1));
+              }
             }
             if (valid) stg256(orow + cc * 16, o);  // 32 contiguous, 32-byte aligned bytes (pitch and n0 multiples of 16)
           };
@@ -320,8 +344,14 @@ __global__ void streamconv_ref_kernel(const __grid_constant__ StreamConvParams p
       }
     }
     float v = acc + p.shift[n];
-    if (p.act) v = lrelu02(v);
-    T* o = reinterpret_cast<T*>(p.out) + (((size_t)b * p.H + gy) * p.W + gx) * (size_t)p.out_pitch + n;
+    const size_t oidx = (((size_t)b * p.H + gy) * p.W + gx) * (size_t)p.out_pitch + n;
+    if (p.ext) {
+      v = v > 0.f ? v : p.slope * v;
+      if (p.res != nullptr) v += sc_ld<T>(reinterpret_cast<const T*>(p.res) + oidx);
+    } else if (p.act) {
+      v = lrelu02(v);
+    }
+    T* o = reinterpret_cast<T*>(p.out) + oidx;
     *o = sc_cvt<T>(v);
   }
 }
@@ -366,7 +396,9 @@ bool streamconv_plan(const StreamConvLayer& L, StreamConvParams* pp) {
   if (L.ksize < 1 || L.ksize > 3 || L.c0 % 64 || L.c1 % 64 || L.c0 < 64 || L.n_total % 16 || L.n_total < 16) return false;
   p.ksize = L.ksize;
   p.ntaps = L.ksize * L.ksize;
-  p.halo_y0 = p.halo_x0 = -((L.ksize - 1) / 2);  // padding='same': (k-1)/2 before, the rest after (film_arch.py:789)
+  // padding='same': (k-1)/2 before, the rest after (film_arch.py:789); L.pad_before >= 0 overrides it (Sepconv's stride-2
+  // convs run as 2x2 convs over a space-to-depth input with their one padding row / column BEFORE)
+  p.halo_y0 = p.halo_x0 = -(L.pad_before >= 0 ? L.pad_before : (L.ksize - 1) / 2);
   p.halo_h = kTileH + L.ksize - 1;
   p.halo_w = kTileW + L.ksize - 1;
   p.nkb0 = L.c0 / 64;
@@ -425,7 +457,7 @@ bool streamconv_plan(const StreamConvLayer& L, StreamConvParams* pp) {
 
 cudaError_t launch_streamconv(const StreamConvLayer& L, int op_type, const void* src0, int pitch0, const void* src1,
                               int pitch1, void* out, int out_pitch, int B, int H, int W, int num_sms, bool use_ref,
-                              cudaStream_t st) {
+                              cudaStream_t st, const void* res) {
   StreamConvParams p{};
   if (!streamconv_plan(L, &p)) {
     set_error("streamconv: unsupported layer shape");
@@ -442,6 +474,17 @@ cudaError_t launch_streamconv(const StreamConvLayer& L, int op_type, const void*
   p.src_pitch[1] = L.c1 ? pitch1 : pitch0;
   p.out = out;
   p.out_pitch = out_pitch;
+  p.ext = L.ext;
+  p.slope = L.slope;
+  p.res = L.ext ? res : nullptr;
+  if (res && !L.ext) {
+    set_error("streamconv: a residual needs an ext layer");
+    return cudaErrorInvalidValue;
+  }
+  if ((uintptr_t)res & 31) {
+    set_error("streamconv: residual slice must be 32-byte aligned");
+    return cudaErrorInvalidValue;
+  }
   p.w = L.w;
   p.shift = L.shift;
   p.B = B;
@@ -495,7 +538,11 @@ cudaError_t launch_streamconv(const StreamConvLayer& L, int op_type, const void*
     cfg.numAttrs = pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kern, p);
   };
-  cudaError_t err = (op_type == OP_BF16) ? go(streamconv_kernel<__nv_bfloat16>) : go(streamconv_kernel<__half>);
+  cudaError_t err;
+  if (L.ext)
+    err = (op_type == OP_BF16) ? go(streamconv_kernel<__nv_bfloat16, true>) : go(streamconv_kernel<__half, true>);
+  else
+    err = (op_type == OP_BF16) ? go(streamconv_kernel<__nv_bfloat16, false>) : go(streamconv_kernel<__half, false>);
   if (err != cudaSuccess) return err;
   return cudaGetLastError();
 }

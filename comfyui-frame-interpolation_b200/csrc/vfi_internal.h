@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -156,6 +157,9 @@ struct StreamConvLayer {
   int c0 = 0, c1 = 0;     // input channels taken from source 0 / source 1 (multiples of 64; c1 may be 0)
   int n_total = 0;        // output channels (multiple of 16; padded with zero weights where the layer has fewer)
   int act = 1;            // 1: LeakyReLU(0.2), 0: none
+  int ext = 0;            // 1: Sepconv epilogue instead: PReLU with one learned `slope` (1.0 = none), then + residual
+  float slope = 1.f;
+  int pad_before = -1;    // rows / columns of zero padding before the window; -1: (ksize - 1) / 2 ('same')
   void* w = nullptr;      // device, packed [split][k-block][tap][n_cta][64 ch, 16-byte chunks XOR (n & 7)] 16-bit
   float* shift = nullptr; // device, [n_total] bias
 };
@@ -166,6 +170,9 @@ struct alignas(64) StreamConvParams {
   int src_pitch[2];
   void* out;              // 16-bit NHWC, channel 0 of this layer's slice
   int out_pitch;          // elements per pixel of the output tensor
+  const void* res;        // ext: residual added after the activation (layout of `out`), or nullptr
+  float slope;            // ext: PReLU slope
+  int ext;
   const void* w;
   const float* shift;
   size_t w_split_bytes;   // packed weight bytes of one output-channel split
@@ -186,6 +193,33 @@ struct alignas(64) StreamConvParams {
 bool streamconv_plan(const StreamConvLayer& L, StreamConvParams* p_out);
 cudaError_t launch_streamconv(const StreamConvLayer& L, int op_type, const void* src0, int pitch0, const void* src1,
                               int pitch1, void* out, int out_pitch, int B, int H, int W, int num_sms, bool use_ref,
+                              cudaStream_t st, const void* res = nullptr);
+
+// host-only operand packer (film.cu): wfun(output column n, tap = ky * k + kx, padded input channel) -> weight
+bool pack_streamconv(const StreamConvLayer& L, int op_type, const std::function<float(int, int, int)>& wfun,
+                     std::vector<uint16_t>* out, StreamConvParams* plan);
+
+// ---- Sepconv element-wise kernels (sepconv_elem.cu) ----
+struct SepPairIdx {  // source frames of every pair of a pass
+  int f0[16];
+  int f1[16];
+};
+struct SepState;
+void sepconv_destroy(SepState* s);  // sepconv.cu
+cudaError_t launch_sep_stats(const float* frames, int cstride, const SepPairIdx& idx, int B, int H, int W, int He, int We,
+                             double* stats, cudaStream_t st);
+cudaError_t launch_sep_input_conv(int op, const float* frames, int cstride, const SepPairIdx& idx, int B, int H, int W, int He,
+                                  int We, const double* stats, const float* w, const float* bias, float slope, void* out,
+                                  cudaStream_t st);
+cudaError_t launch_prelu_s2d16(int op, const void* in, void* out, float slope, int C, int B, int H, int W, cudaStream_t st);
+cudaError_t launch_prelu16(int op, const void* in, void* out, float slope, size_t n, cudaStream_t st);
+cudaError_t launch_prelu_up2_16(int op, const void* in, void* out, float slope, int C, int B, int h, int w, int Ht, int Wt,
+                                cudaStream_t st);
+cudaError_t launch_add_crop16(int op, const void* v, int Hv, int Wv, void* x, int C, int B, int H, int W, cudaStream_t st);
+cudaError_t launch_sep_coeff_nchw(int op, const void* in, int pitch, float* out, int K, int B, int H, int W, cudaStream_t st);
+cudaError_t launch_sep_pad_input(const float* frames, int cstride, const SepPairIdx& idx, int which, int B, int H, int W,
+                                 int Hp, int Wp, float* out, cudaStream_t st);
+cudaError_t launch_sep_finish(const float* o1, const float* o2, float* out, int B, int H, int W, int He, int We,
                               cudaStream_t st);
 
 // ---- FILM element-wise kernels (film_elem.cu); 16-bit tensors are NHWC slices {pointer, pixel pitch in elements} ----
@@ -223,6 +257,7 @@ void film_destroy(FilmState* f);  // film.cu
 
 CtxInfo ctx_info(::vfi_ctx* c);
 FilmState*& ctx_film(::vfi_ctx* c);
+SepState*& ctx_sep(::vfi_ctx* c);
 void ctx_add_launches(::vfi_ctx* c, int n);
 
 }  // namespace vfi

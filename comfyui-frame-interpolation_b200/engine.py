@@ -267,3 +267,94 @@ class FilmEngine:
 
     def sync(self):
         check(self._L.vfi_sync(self._ctx))
+
+
+# ------------------------------------------------------------------------------------------------- Sepconv
+def sepconv_state_dict_names():
+    """sepconv_enhanced.Network().state_dict() order (sepconv_enhanced.py:536-598)."""
+    names = ["netInput.weight", "netInput.bias"]
+
+    def basic(prefix, prelu0, c0, prelu1, c1):
+        out = []
+        if prelu0 is not None:
+            out.append(f"{prefix}.netMain.{prelu0}.weight")
+        out += [f"{prefix}.netMain.{c0}.weight", f"{prefix}.netMain.{c0}.bias", f"{prefix}.netMain.{prelu1}.weight",
+                f"{prefix}.netMain.{c1}.weight", f"{prefix}.netMain.{c1}.bias"]
+        return out
+
+    for r in range(1, 5):
+        names += basic(f"netEncode.0.netVer.{r}", 0, 1, 2, 3)
+    for k in range(4):
+        names += basic(f"netDecode.0.netHor.{k}", 0, 1, 2, 3)
+    for k in range(1, 4):
+        names += basic(f"netDecode.0.netVer.{k}", 0, 2, 3, 4)
+    for head in ("netVerone", "netVertwo", "netHorone", "netHortwo"):
+        names += basic(head, None, 1, 2, 3)
+    return names
+
+
+class SepconvEngine:
+    """Sepconv (sepconv.pth) on one B200: `state_dict` = sepconv_enhanced.Network's."""
+
+    MAX_PAIRS = 16
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device: int = 0, dtype: str = "float32"):
+        if not torch.cuda.is_available():
+            raise VfiError("no CUDA device: this path has no CPU fallback")
+        if dtype not in OPERAND:
+            raise ValueError(f"dtype must be one of {list(OPERAND)}")
+        self._L = lib()
+        self.device = int(device)
+        self._ctx = C.c_void_p()
+        check(self._L.vfi_create(self.device, C.byref(self._ctx)))
+        names = sepconv_state_dict_names()
+        missing = [n for n in names if n not in state_dict]
+        if missing:
+            raise KeyError(f"state_dict is not a Sepconv checkpoint; missing {missing[:3]} ...")
+        hold = [state_dict[n].detach().to("cpu", torch.float32).contiguous() for n in names]
+        ptrs = (C.c_void_p * len(hold))(*[t.data_ptr() for t in hold])
+        numel = (C.c_int64 * len(hold))(*[t.numel() for t in hold])
+        check(self._L.vfi_sepconv_load(self._ctx, ptrs, numel, len(hold), OPERAND[dtype]))
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self._L.vfi_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def forward(self, frames: torch.Tensor, f0: Sequence[int], f1: Sequence[int],
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """frames: CUDA float32 [N,H,W,C>=3] NHWC -> CUDA float32 [len(f0),H,W,3] = Network.forward(frame f0, frame f1)."""
+        assert frames.is_cuda and frames.dtype == torch.float32 and frames.is_contiguous() and frames.dim() == 4
+        n, h, w, c = frames.shape
+        f0a, f1a = _i32(f0), _i32(f1)
+        npairs = len(f0a)
+        assert npairs == len(f1a) and 1 <= npairs <= self.MAX_PAIRS
+        if out is None:
+            out = torch.empty((npairs, h, w, 3), dtype=torch.float32, device=frames.device)
+        assert out.is_cuda and out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == (npairs, h, w, 3)
+        st = torch.cuda.current_stream(frames.device).cuda_stream
+        check(self._L.vfi_sepconv_forward(self._ctx, frames.data_ptr(), n, h, w, c, f0a.ctypes.data, f1a.ctypes.data, npairs,
+                                          out.data_ptr(), st))
+        return out
+
+    def middle_frame(self, frame_0: torch.Tensor, frame_1: torch.Tensor) -> torch.Tensor:
+        """NCHW [1,3,H,W] x 2 -> NCHW [1,3,H,W]: `model(frame_0, frame_1)` as generic_frame_loop calls it
+        (sepconv/__init__.py:47-48)."""
+        dev = torch.device("cuda", self.device)
+        pair = torch.cat([frame_0, frame_1]).to(dev, torch.float32).permute(0, 2, 3, 1).contiguous()
+        return self.forward(pair, [0], [1]).permute(0, 3, 1, 2)
+
+    def set_ref(self, use_ref: bool):
+        check(self._L.vfi_sepconv_debug_set_ref(self._ctx, 1 if use_ref else 0))
+
+    def launch_count(self) -> int:
+        return int(self._L.vfi_launch_count(self._ctx))
+
+    def sync(self):
+        check(self._L.vfi_sync(self._ctx))

@@ -136,6 +136,24 @@ int vfi_film_debug_pack_host(int layout, int C, int nf, int ksize, int n_total, 
                              int cout, int cin, uint16_t* out, int64_t out_cap, int* c0, int* c1, int* n_cta,
                              int* nsplit);
 
+/* Sepconv (`Sepconv VFI` node) - SURVEY.md section 8 row a12 -------------------------------------------- */
+#define VFI_SEPCONV_NUM_TENSORS 88   /* sepconv_enhanced.Network().state_dict() (sepconv_enhanced.py:536-598) */
+/* Replaces: Network().load_state_dict(torch.load(path)) - sepconv/__init__.py:42-45.  HOST float32 arrays in
+ * state_dict order (netInput, netEncode.0.netVer.{1..4}, netDecode.0.netHor.{0..3}, netDecode.0.netVer.{1..3}, netVerone,
+ * netVertwo, netHorone, netHortwo); sizes are checked. */
+int vfi_sepconv_load(vfi_ctx* ctx, const float* const* tensors, const int64_t* numel, int n_tensors, int operand_type);
+/* Replaces: `model(frame_0, frame_1)` = Network.forward (sepconv_enhanced.py:605-706) for n_pairs independent pairs.
+ * DEVICE pointers: frames [n_frames, H, W, C >= 3] float32 NHWC, out [n_pairs, H, W, 3] float32 NHWC (not clamped, like
+ * the reference); f0 / f1: HOST index arrays.  Any H, W >= 2.  Asynchronous on `stream`. */
+int vfi_sepconv_forward(vfi_ctx* ctx, const float* frames, int n_frames, int H, int W, int C, const int32_t* f0,
+                        const int32_t* f1, int n_pairs, float* out, void* stream);
+/* Test hooks: every conv through the CUDA-core checker (1) / the tcgen05 kernel (0); the host-only weight packer of
+ * vfi_sepconv_load (a 3x3 conv packed as a stride-1 layer, or as the 2x2 conv over the space-to-depth input that runs
+ * its stride-2 form). */
+int vfi_sepconv_debug_set_ref(vfi_ctx* ctx, int use_ref);
+int vfi_sepconv_debug_pack_host(int stride2, int cin, int cout, int n_total, int operand_type, const float* w, uint16_t* out,
+                                int64_t out_cap, int* c0, int* n_cta, int* nsplit);
+
 /* Test / profiling hooks (used by tests/ and bench.py only) --------------------------------------------- */
 /* Run ONE convolution layer of block `block` (0..3; arch 4.26: 0..4): layer 0 = conv0.0, 1 = conv0.1, 2..9 = ResConv
  * 0..7, 10 = lastconv (flow + mask), 11 = arch 4.26 blocks 0..3: the 8 feature channels of lastconv, written as

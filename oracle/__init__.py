@@ -1,4 +1,5 @@
-"""CPU oracle for the RIFE-4.6 hot path.  TEST INFRASTRUCTURE ONLY.
+"""CPU oracles: RIFE 4.6 / 4.7 / 4.17 / 4.26 (rife46.py), FILM (film.py), Sepconv (sepconv.py), the op primitives (ops_ref.py).
+TEST INFRASTRUCTURE ONLY.
 
 Nothing under ``oracle/`` is product code.  Only ``tests/``, ``__graft_entry__.smoke()``
 and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it, and only

@@ -8,6 +8,9 @@
 
 namespace vfi {
 
+// (tests/host_emu compiles the element-wise kernels of sepconv_elem.cu for the HOST with g++ -DVFI_HOST_EMU: everything
+// that is inline PTX is left out there; the product build never defines the macro)
+#ifndef VFI_HOST_EMU
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -177,6 +180,8 @@ __device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t smem_addr, uint32_t 
   d |= (uint64_t)1 << 46;
   return d;
 }
+
+#endif  // VFI_HOST_EMU
 
 // ---------------------------------------------------------------- small math helpers
 __device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }

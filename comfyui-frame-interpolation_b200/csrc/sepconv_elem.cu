@@ -291,6 +291,7 @@ __global__ void sep_finish_kernel(const float* __restrict__ o1, const float* __r
 
 }  // namespace
 
+#ifndef VFI_HOST_EMU  // (the host emulation build of tests/host_emu calls the kernels directly)
 cudaError_t launch_sep_stats(const float* frames, int cstride, const SepPairIdx& idx, int B, int H, int W, int He, int We,
                              double* stats, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(stats, 0, (size_t)B * 2 * sizeof(double), st);
@@ -375,5 +376,7 @@ cudaError_t launch_sep_finish(const float* o1, const float* o2, float* out, int 
   sep_finish_kernel<<<sgrid((size_t)B * H * W, 256), 256, 0, st>>>(o1, o2, out, B, H, W, He, We);
   return cudaGetLastError();
 }
+
+#endif  // VFI_HOST_EMU
 
 }  // namespace vfi

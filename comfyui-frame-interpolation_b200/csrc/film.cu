@@ -52,42 +52,7 @@ struct Buf {
   }
 };
 
-uint16_t to_op(float v, int op_type) {
-  uint16_t u;
-  if (op_type == OP_BF16) {
-    __nv_bfloat16 h = __float2bfloat16_rn(v);
-    std::memcpy(&u, &h, 2);
-  } else {
-    __half h = __float2half_rn(v);
-    std::memcpy(&u, &h, 2);
-  }
-  return u;
-}
-
 }  // namespace
-
-// streamconv operand packer shared with sepconv.cu: wfun(n, tap, padded input channel) -> weight
-bool pack_streamconv(const StreamConvLayer& L, int op_type, const std::function<float(int, int, int)>& wfun,
-                     std::vector<uint16_t>* out, StreamConvParams* plan) {
-  StreamConvParams& p = *plan;
-  p = StreamConvParams{};
-  if (!streamconv_plan(L, &p)) return false;
-  const int ntaps = L.ksize * L.ksize;
-  const size_t per_split = (size_t)p.nkb * ntaps * p.n_cta * 64;
-  std::vector<uint16_t>& pk = *out;
-  pk.assign((size_t)p.nsplit * per_split, 0);
-  for (int sp = 0; sp < p.nsplit; ++sp)
-    for (int kb = 0; kb < p.nkb; ++kb)
-      for (int tap = 0; tap < ntaps; ++tap)
-        for (int nl = 0; nl < p.n_cta; ++nl) {
-          uint16_t* row = &pk[sp * per_split + ((size_t)(kb * ntaps + tap) * p.n_cta + nl) * 64];
-          for (int c = 0; c < 64; ++c) {
-            const float val = wfun(sp * p.n_cta + nl, tap, kb * 64 + c);
-            if (val != 0.f) row[(((c >> 3) ^ (nl & 7)) * 8) + (c & 7)] = to_op(val, op_type);
-          }
-        }
-  return true;
-}
 
 struct FilmState {
   int op_type = OP_F16;

@@ -291,13 +291,12 @@ __global__ void sep_finish_kernel(const float* __restrict__ o1, const float* __r
 
 }  // namespace
 
-#ifndef VFI_HOST_EMU  // (the host emulation build of tests/host_emu calls the kernels directly)
 cudaError_t launch_sep_stats(const float* frames, int cstride, const SepPairIdx& idx, int B, int H, int W, int He, int We,
                              double* stats, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(stats, 0, (size_t)B * 2 * sizeof(double), st);
   if (e != cudaSuccess) return e;
   const dim3 g((unsigned)sgrid((size_t)2 * He * We, 256 * 8), (unsigned)B);
-  sep_stats_kernel<<<g, 256, 0, st>>>(frames, cstride, idx, H, W, He, We, stats);
+  VFI_LAUNCH(sep_stats_kernel, g, 256, 0, st, frames, cstride, idx, H, W, He, We, stats);
   return cudaGetLastError();
 }
 
@@ -306,10 +305,10 @@ cudaError_t launch_sep_input_conv(int op, const float* frames, int cstride, cons
                                   cudaStream_t st) {
   const int g = sgrid((size_t)B * He * We * 2, 128);
   if (op == OP_BF16)
-    sep_input_conv_kernel<__nv_bfloat16><<<g, 128, 0, st>>>(frames, cstride, idx, H, W, He, We, stats, w, bias, slope,
+    VFI_LAUNCH(sep_input_conv_kernel<__nv_bfloat16>, g, 128, 0, st, frames, cstride, idx, H, W, He, We, stats, w, bias, slope,
                                                             (__nv_bfloat16*)out, B);
   else
-    sep_input_conv_kernel<__half><<<g, 128, 0, st>>>(frames, cstride, idx, H, W, He, We, stats, w, bias, slope, (__half*)out, B);
+    VFI_LAUNCH(sep_input_conv_kernel<__half>, g, 128, 0, st, frames, cstride, idx, H, W, He, We, stats, w, bias, slope, (__half*)out, B);
   return cudaGetLastError();
 }
 
@@ -317,9 +316,9 @@ cudaError_t launch_prelu_s2d16(int op, const void* in, void* out, float slope, i
   if (C & 7) return cudaErrorInvalidValue;
   const int g = sgrid((size_t)B * ((H + 1) / 2) * ((W + 1) / 2) * 4 * (C / 8), 256);
   if (op == OP_BF16)
-    prelu_s2d16_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, slope, C / 8, B, H, W);
+    VFI_LAUNCH(prelu_s2d16_kernel<__nv_bfloat16>, g, 256, 0, st, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, slope, C / 8, B, H, W);
   else
-    prelu_s2d16_kernel<__half><<<g, 256, 0, st>>>((const __half*)in, (__half*)out, slope, C / 8, B, H, W);
+    VFI_LAUNCH(prelu_s2d16_kernel<__half>, g, 256, 0, st, (const __half*)in, (__half*)out, slope, C / 8, B, H, W);
   return cudaGetLastError();
 }
 
@@ -327,9 +326,9 @@ cudaError_t launch_prelu16(int op, const void* in, void* out, float slope, size_
   if (n & 7) return cudaErrorInvalidValue;
   const int g = sgrid(n / 8, 256);
   if (op == OP_BF16)
-    prelu16_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, slope, n / 8);
+    VFI_LAUNCH(prelu16_kernel<__nv_bfloat16>, g, 256, 0, st, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, slope, n / 8);
   else
-    prelu16_kernel<__half><<<g, 256, 0, st>>>((const __half*)in, (__half*)out, slope, n / 8);
+    VFI_LAUNCH(prelu16_kernel<__half>, g, 256, 0, st, (const __half*)in, (__half*)out, slope, n / 8);
   return cudaGetLastError();
 }
 
@@ -338,10 +337,10 @@ cudaError_t launch_prelu_up2_16(int op, const void* in, void* out, float slope, 
   if ((C & 7) || Ht > 2 * h || Wt > 2 * w) return cudaErrorInvalidValue;
   const int g = sgrid((size_t)B * Ht * Wt * (C / 8), 256);
   if (op == OP_BF16)
-    prelu_up2_16_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, slope, C / 8, B, h, w,
+    VFI_LAUNCH(prelu_up2_16_kernel<__nv_bfloat16>, g, 256, 0, st, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, slope, C / 8, B, h, w,
                                                           Ht, Wt);
   else
-    prelu_up2_16_kernel<__half><<<g, 256, 0, st>>>((const __half*)in, (__half*)out, slope, C / 8, B, h, w, Ht, Wt);
+    VFI_LAUNCH(prelu_up2_16_kernel<__half>, g, 256, 0, st, (const __half*)in, (__half*)out, slope, C / 8, B, h, w, Ht, Wt);
   return cudaGetLastError();
 }
 
@@ -349,9 +348,9 @@ cudaError_t launch_add_crop16(int op, const void* v, int Hv, int Wv, void* x, in
   if ((C & 7) || Hv < H || Wv < W) return cudaErrorInvalidValue;
   const int g = sgrid((size_t)B * H * W * (C / 8), 256);
   if (op == OP_BF16)
-    add_crop16_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)v, Hv, Wv, (__nv_bfloat16*)x, C / 8, B, H, W);
+    VFI_LAUNCH(add_crop16_kernel<__nv_bfloat16>, g, 256, 0, st, (const __nv_bfloat16*)v, Hv, Wv, (__nv_bfloat16*)x, C / 8, B, H, W);
   else
-    add_crop16_kernel<__half><<<g, 256, 0, st>>>((const __half*)v, Hv, Wv, (__half*)x, C / 8, B, H, W);
+    VFI_LAUNCH(add_crop16_kernel<__half>, g, 256, 0, st, (const __half*)v, Hv, Wv, (__half*)x, C / 8, B, H, W);
   return cudaGetLastError();
 }
 
@@ -359,24 +358,22 @@ cudaError_t launch_sep_coeff_nchw(int op, const void* in, int pitch, float* out,
   const size_t hw = (size_t)H * W;
   const int g = sgrid((size_t)B * K * hw, 256);
   if (op == OP_BF16)
-    sep_coeff_nchw_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)in, pitch, out, K, B, hw);
+    VFI_LAUNCH(sep_coeff_nchw_kernel<__nv_bfloat16>, g, 256, 0, st, (const __nv_bfloat16*)in, pitch, out, K, B, hw);
   else
-    sep_coeff_nchw_kernel<__half><<<g, 256, 0, st>>>((const __half*)in, pitch, out, K, B, hw);
+    VFI_LAUNCH(sep_coeff_nchw_kernel<__half>, g, 256, 0, st, (const __half*)in, pitch, out, K, B, hw);
   return cudaGetLastError();
 }
 
 cudaError_t launch_sep_pad_input(const float* frames, int cstride, const SepPairIdx& idx, int which, int B, int H, int W,
                                  int Hp, int Wp, float* out, cudaStream_t st) {
-  sep_pad_input_kernel<<<sgrid((size_t)B * 4 * Hp * Wp, 256), 256, 0, st>>>(frames, cstride, idx, which, H, W, Hp, Wp, out, B);
+  VFI_LAUNCH(sep_pad_input_kernel, sgrid((size_t)B * 4 * Hp * Wp, 256), 256, 0, st, frames, cstride, idx, which, H, W, Hp, Wp, out, B);
   return cudaGetLastError();
 }
 
 cudaError_t launch_sep_finish(const float* o1, const float* o2, float* out, int B, int H, int W, int He, int We,
                               cudaStream_t st) {
-  sep_finish_kernel<<<sgrid((size_t)B * H * W, 256), 256, 0, st>>>(o1, o2, out, B, H, W, He, We);
+  VFI_LAUNCH(sep_finish_kernel, sgrid((size_t)B * H * W, 256), 256, 0, st, o1, o2, out, B, H, W, He, We);
   return cudaGetLastError();
 }
-
-#endif  // VFI_HOST_EMU
 
 }  // namespace vfi

@@ -32,6 +32,7 @@
 // Round-1 status: first GPU run parity-green (profiles/r01_film_gpu_check.jsonl: tcgen05 vs the CUDA-core checker below
 // <= 6e-4 relative on 11 layer shapes, whole FILM net 64.4 dB vs the unmodified reference); not yet timed or profiled.
 #include <cstdlib>
+#include <cstring>
 
 #include "ptx.cuh"
 #include "vfi_internal.h"
@@ -81,6 +82,7 @@ __device__ __forceinline__ void ring_next(uint32_t& slot, uint32_t& ph, uint32_t
   }
 }
 
+#ifndef VFI_HOST_EMU  // (tests/host_emu runs the schedule on the CPU with the checker kernel below; no tcgen05 there)
 // EXT = false is the FILM kernel as verified in r01 (bias + LeakyReLU(0.2) / identity).  EXT = true adds what the Sepconv
 // trunk needs in the epilogue: a PReLU with one learned slope (a > 0 ? a : slope * a, any sign / size of slope) and a
 // residual tensor added after it (same layout as the output; it may BE the output: every thread reads its 16 channels
@@ -296,6 +298,8 @@ __global__ void __launch_bounds__(kSThreads, 1) streamconv_kernel(const __grid_c
   }
 }
 
+#endif  // VFI_HOST_EMU
+
 // ---------------------------------------------------------------------------------------------
 // CUDA-core checker with the SAME parameters and packed weights: one thread per (pixel, n).
 // Test infrastructure for the tensor-core kernel (debug entry points only; never on the product path).
@@ -356,6 +360,7 @@ __global__ void streamconv_ref_kernel(const __grid_constant__ StreamConvParams p
   }
 }
 
+#ifndef VFI_HOST_EMU
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -385,6 +390,8 @@ bool make_slice_tmap(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, 
   }
   return true;
 }
+
+#endif  // VFI_HOST_EMU
 
 uint32_t sc_align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
@@ -455,6 +462,43 @@ bool streamconv_plan(const StreamConvLayer& L, StreamConvParams* pp) {
   return true;
 }
 
+// 16-bit operand element of a weight (host)
+static uint16_t to_op(float v, int op_type) {
+  uint16_t u;
+  if (op_type == OP_BF16) {
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    std::memcpy(&u, &h, 2);
+  } else {
+    __half h = __float2half_rn(v);
+    std::memcpy(&u, &h, 2);
+  }
+  return u;
+}
+
+// Host-only operand packer (film.cu, sepconv.cu): wfun(output column n, tap = ky * k + kx, padded input channel) -> weight;
+// layout [split][k-block][tap][n_cta rows][64 channels = 128 B, 16-byte chunks XOR (row & 7)] = what one B slot receives.
+bool pack_streamconv(const StreamConvLayer& L, int op_type, const std::function<float(int, int, int)>& wfun,
+                     std::vector<uint16_t>* out, StreamConvParams* plan) {
+  StreamConvParams& p = *plan;
+  p = StreamConvParams{};
+  if (!streamconv_plan(L, &p)) return false;
+  const int ntaps = L.ksize * L.ksize;
+  const size_t per_split = (size_t)p.nkb * ntaps * p.n_cta * 64;
+  std::vector<uint16_t>& pk = *out;
+  pk.assign((size_t)p.nsplit * per_split, 0);
+  for (int sp = 0; sp < p.nsplit; ++sp)
+    for (int kb = 0; kb < p.nkb; ++kb)
+      for (int tap = 0; tap < ntaps; ++tap)
+        for (int nl = 0; nl < p.n_cta; ++nl) {
+          uint16_t* row = &pk[sp * per_split + ((size_t)(kb * ntaps + tap) * p.n_cta + nl) * 64];
+          for (int c = 0; c < 64; ++c) {
+            const float val = wfun(sp * p.n_cta + nl, tap, kb * 64 + c);
+            if (val != 0.f) row[(((c >> 3) ^ (nl & 7)) * 8) + (c & 7)] = to_op(val, op_type);
+          }
+        }
+  return true;
+}
+
 cudaError_t launch_streamconv(const StreamConvLayer& L, int op_type, const void* src0, int pitch0, const void* src1,
                               int pitch1, void* out, int out_pitch, int B, int H, int W, int num_sms, bool use_ref,
                               cudaStream_t st, const void* res) {
@@ -501,11 +545,15 @@ cudaError_t launch_streamconv(const StreamConvLayer& L, int op_type, const void*
     const size_t total = (size_t)B * H * W * L.n_total;
     const int blocks = (int)((total + 255) / 256 < 65535 ? (total + 255) / 256 : 65535);
     if (op_type == OP_BF16)
-      streamconv_ref_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(p);
+      VFI_LAUNCH(streamconv_ref_kernel<__nv_bfloat16>, blocks, 256, 0, st, p);
     else
-      streamconv_ref_kernel<__half><<<blocks, 256, 0, st>>>(p);
+      VFI_LAUNCH(streamconv_ref_kernel<__half>, blocks, 256, 0, st, p);
     return cudaGetLastError();
   }
+#ifdef VFI_HOST_EMU
+  set_error("streamconv: the host emulation only has the checker kernel");
+  return cudaErrorInvalidConfiguration;
+#else
 
   const CUtensorMapDataType dt = (op_type == OP_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   if (!make_slice_tmap(&p.tm[0], dt, src0, L.c0, pitch0, W, H, B, p.halo_w, p.halo_h)) return cudaErrorInvalidValue;
@@ -545,6 +593,7 @@ cudaError_t launch_streamconv(const StreamConvLayer& L, int op_type, const void*
     err = (op_type == OP_BF16) ? go(streamconv_kernel<__nv_bfloat16, false>) : go(streamconv_kernel<__half, false>);
   if (err != cudaSuccess) return err;
   return cudaGetLastError();
+#endif  // VFI_HOST_EMU
 }
 
 }  // namespace vfi

@@ -10,6 +10,11 @@
 
 struct vfi_ctx;
 
+// kernel launch; tests/host_emu/cuda_shim.h defines a host version (a plain call per grid row) before this header
+#ifndef VFI_LAUNCH
+#define VFI_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
 namespace vfi {
 
 // ---------------------------------------------------------------------------------------------

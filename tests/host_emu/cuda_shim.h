@@ -35,3 +35,42 @@ static inline double atomicAdd(double* p, double v) {
 }
 using std::max;
 using std::min;
+
+// ---- launches and the few runtime calls the schedules make, for the whole-path emulation (sepconv_full_emu.cpp)
+#define __grid_constant__
+#define VFI_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  do {                                                      \
+    const dim3 _g(grid);                                    \
+    for (unsigned _y = 0; _y < _g.y; ++_y) {                \
+      blockIdx.y = _y;                                      \
+      kernel(__VA_ARGS__);                                  \
+    }                                                       \
+    blockIdx.y = 0;                                         \
+  } while (0)
+#include <cstdlib>
+#include <cstring>
+static inline cudaError_t emu_malloc(void** p, size_t n) {
+  const size_t bytes = ((n ? n : 1) + 255) / 256 * 256;   // cudaMalloc alignment
+  *p = std::aligned_alloc(256, bytes);
+  if (*p) std::memset(*p, 0, bytes);
+  return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+static inline cudaError_t emu_free(void* p) {
+  std::free(p);
+  return cudaSuccess;
+}
+static inline cudaError_t emu_memcpy(void* d, const void* s, size_t n, cudaMemcpyKind) {
+  std::memcpy(d, s, n);
+  return cudaSuccess;
+}
+static inline cudaError_t emu_memset_async(void* d, int v, size_t n, cudaStream_t) {
+  std::memset(d, v, n);
+  return cudaSuccess;
+}
+#define cudaMalloc(p, n) emu_malloc((void**)(p), (n))
+#define cudaFree(p) emu_free(p)
+#define cudaMemcpy(d, s, n, k) emu_memcpy((d), (s), (n), (k))
+#define cudaMemsetAsync(d, v, n, st) emu_memset_async((d), (v), (n), (st))
+#define cudaSetDevice(d) cudaSuccess
+#define cudaGetLastError() cudaSuccess
+#define cudaGetErrorString(e) "emulated CUDA error"

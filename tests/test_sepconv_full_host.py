@@ -1,0 +1,58 @@
+"""The WHOLE Sepconv path of the library on the CPU: csrc/sepconv.cu (vfi_sepconv_load + vfi_sepconv_forward: tensor order,
+PReLU slopes, buffer sizing, the schedule with its crop-after-conv decoder path), csrc/sepconv_elem.cu and streamconv.cu's
+packer + CUDA-core checker kernel, compiled for the host (tests/host_emu) and compared with the output of the unmodified
+reference Network (tests/golden/sepconv_net_21x30.npz).  The tcgen05 kernel and ops.cu's tiled op kernel are not part of
+this (the checker kernel / a plain restatement stand in); both have their own GPU tests."""
+import ctypes as C
+import math
+import os
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from make_golden_sepconv import sepconv_cases, sepconv_inputs  # noqa: E402
+from oracle import sepconv as OS  # noqa: E402
+
+CUDA_INC = "/usr/local/cuda/include"
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    if not (shutil.which("g++") and os.path.exists(os.path.join(CUDA_INC, "cuda_fp16.h"))):
+        pytest.skip("g++ / CUDA headers not available")
+    so = str(tmp_path_factory.mktemp("emu") / "libsepfull.so")
+    src = os.path.join(ROOT, "tests", "host_emu", "sepconv_full_emu.cpp")
+    r = subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I" + CUDA_INC, "-o", so, src],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return C.CDLL(so)
+
+
+def test_sepconv_whole_path_on_host_matches_reference(emu, pkg):
+    from cfi_b200.engine import sepconv_state_dict_names
+    name = "sepconv_net_21x30"
+    cfg = sepconv_cases()[name]
+    ref = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))["out"]).permute(0, 2, 3, 1)
+    sd = OS.synthetic_state_dict(cfg["seed"])
+    hold = [sd[n].contiguous() for n in sepconv_state_dict_names()]
+    ptrs = (C.c_void_p * len(hold))(*[t.data_ptr() for t in hold])
+    numel = (C.c_int64 * len(hold))(*[t.numel() for t in hold])
+    fr = sepconv_inputs(cfg).contiguous()
+    h, w = cfg["h"], cfg["w"]
+    out = torch.zeros(1, h, w, 3)
+    rc = emu.emu_sepconv(ptrs, numel, len(hold), C.c_void_p(fr.data_ptr()), h, w, 3, C.c_void_p(out.data_ptr()))
+    emu.vfi_last_error.restype = C.c_char_p
+    assert rc >= 1000, (rc, emu.vfi_last_error())
+    launches = rc - 1000
+    assert 45 <= launches <= 60     # 2 + 4*2+3 + 4*3 + 3*(3 or 4) + 1 + 4*3 + 5
+    mse = float(((out.double() - ref.double()) ** 2).mean())
+    psnr = 99.0 if mse == 0 else 10 * math.log10(1.0 / mse)
+    print(f"host emulation of the whole Sepconv path: {launches} launches, PSNR {psnr:.2f} dB, max abs {float((out - ref).abs().max()):.2e}")
+    assert psnr >= 50.0, psnr       # the north_star bar; fp16 operands / activations vs the fp32 reference
+    assert float((out - ref).abs().max()) < 0.02

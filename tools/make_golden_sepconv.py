@@ -34,6 +34,8 @@ def sepconv_cases():
         "sepconv_net_48x64": dict(kind="net", seed=0, h=48, w=64, clip_seed=51),
         # odd input size (replicate-padded to even), odd rows down the pyramid (the decoder's crop-by-one path)
         "sepconv_net_45x54": dict(kind="net", seed=1, h=45, w=54, clip_seed=52),
+        # small odd case for the whole-path host emulation (tests/test_sepconv_full_host.py): 21x30 -> 22x30, rows 11x15, 6x8, 3x4, 2x2
+        "sepconv_net_21x30": dict(kind="net", seed=3, h=21, w=30, clip_seed=54),
         # No node-level case: on this torch version (2.11) the unmodified SepconvVFI.vfi raises inside Network.forward
         # (`tenStack.view` at sepconv_enhanced.py:626 on the stack of the permuted frame views preprocess_frames hands it,
         # for even and odd sizes alike), so there is no reference node output to pin to.  The loop it would run,

@@ -47,8 +47,9 @@ extern "C" const char* vfi_last_error(void) { return vfi::g_err.c_str(); }
 
 extern "C" {
 // weights in, one pair in, one frame out - everything through the product's own vfi_sepconv_load / vfi_sepconv_forward
+// coef (optional): [4][51][He][We] fp32 = the coefficient planes of the heads Verone, Vertwo, Horone, Hortwo
 int emu_sepconv(const float* const* tensors, const int64_t* numel, int n_tensors, const float* frames, int H, int W, int C,
-                float* out) {
+                float* out, float* coef) {
   vfi_ctx ctx;
   int rc = vfi_sepconv_load(&ctx, tensors, numel, n_tensors, VFI_OPERAND_F16);
   if (rc) return rc;
@@ -56,6 +57,10 @@ int emu_sepconv(const float* const* tensors, const int64_t* numel, int n_tensors
   if (rc) return rc;
   const int32_t f0[1] = {0}, f1[1] = {1};
   rc = vfi_sepconv_forward(&ctx, frames, 2, H, W, C, f0, f1, 1, out, nullptr);
+  if (!rc && coef) {
+    const size_t n = (size_t)51 * (H + (H & 1)) * (W + (W & 1));
+    for (int k = 0; k < 4; ++k) std::memcpy(coef + k * n, ctx.sep->coef[k].p, n * sizeof(float));
+  }
   vfi::sepconv_destroy(ctx.sep);
   return rc ? rc : 1000 + ctx.launches;   // 1000 + number of launches on success
 }

@@ -46,7 +46,10 @@ def test_sepconv_whole_path_on_host_matches_reference(emu, pkg):
     fr = sepconv_inputs(cfg).contiguous()
     h, w = cfg["h"], cfg["w"]
     out = torch.zeros(1, h, w, 3)
-    rc = emu.emu_sepconv(ptrs, numel, len(hold), C.c_void_p(fr.data_ptr()), h, w, 3, C.c_void_p(out.data_ptr()))
+    he, we = h + h % 2, w + w % 2
+    coef = torch.zeros(4, 51, he, we)
+    rc = emu.emu_sepconv(ptrs, numel, len(hold), C.c_void_p(fr.data_ptr()), h, w, 3, C.c_void_p(out.data_ptr()),
+                         C.c_void_p(coef.data_ptr()))
     emu.vfi_last_error.restype = C.c_char_p
     assert rc >= 1000, (rc, emu.vfi_last_error())
     launches = rc - 1000
@@ -54,5 +57,17 @@ def test_sepconv_whole_path_on_host_matches_reference(emu, pkg):
     mse = float(((out.double() - ref.double()) ** 2).mean())
     psnr = 99.0 if mse == 0 else 10 * math.log10(1.0 / mse)
     print(f"host emulation of the whole Sepconv path: {launches} launches, PSNR {psnr:.2f} dB, max abs {float((out - ref).abs().max()):.2e}")
-    assert psnr >= 50.0, psnr       # the north_star bar; fp16 operands / activations vs the fp32 reference
-    assert float((out - ref).abs().max()) < 0.02
+    # the output is a normalised blur whose kernels are dominated by the heads' bias (a broken trunk still gives ~41 dB), so
+    # the bars are set at the level of fp16 rounding, and the coefficient planes - the trunk's actual product - are
+    # compared with the oracle's one by one
+    assert psnr >= 80.0, psnr
+    assert float((out - ref).abs().max()) < 1e-3
+    dbg = {}
+    x = fr.permute(0, 3, 1, 2).contiguous()
+    OS.network_forward(sd, x[0:1], x[1:2], debug=dbg)
+    for k, key in enumerate(("ver1", "ver2", "hor1", "hor2")):
+        want = dbg[key][0]
+        bias = sd[("netVerone", "netVertwo", "netHorone", "netHortwo")[k] + ".netMain.3.bias"].view(-1, 1, 1)
+        err = float((coef[k] - want).abs().max())
+        signal = float((want - bias).abs().max())       # what the trunk contributes on top of the bias
+        assert err <= 0.02 * signal + 2e-3, (key, err, signal)

@@ -173,3 +173,39 @@ def film_vfi_sharded(run_node, frames: torch.Tensor, multiplier, states, dist, d
     if rank != dst:
         return None
     return torch.cat([full.cpu(), frames[-1:, ..., :3].to(torch.float32)], 0)  # film/__init__.py:104
+
+
+def generic_vfi_sharded(run_node, frames: torch.Tensor, multiplier: int, states, dist, dst: int = 0, device=None):
+    """Nodes that run `generic_frame_loop` (Sepconv VFI, vfi_utils.py:339-389) over the ranks of one box, int multiplier:
+    every pair emits its first frame, plus multiplier - 1 new frames unless it is skipped (:260-265, :329-337), and the
+    last frame closes the clip - so contiguous pair ranges can run as independent sub-clips and be concatenated.
+    `run_node(sub_frames, multiplier, sub_states) -> [M_r, H, W, 3]`.  Returns the full output on `dst`, None elsewhere.
+    (List multipliers go through the reference's per-pair quirk - the skip predicate sees index 0 for every pair,
+    frame_loop.py - and are not sharded here.)"""
+    if not isinstance(multiplier, int):
+        raise NotImplementedError("generic_vfi_sharded: int multipliers only")
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n = frames.shape[0]
+
+    def skipped(i):
+        if states is None:
+            return False
+        idx, is_skip = states
+        return (is_skip and i in idx) or (not is_skip and i not in idx)
+
+    costs = [0.01 if skipped(i) else float(multiplier - 1) + 0.01 for i in range(n - 1)]
+    slices = shard_pairs_by_cost(costs, world)
+    counts = [sum(1 if skipped(i) else multiplier for i in range(a, b)) for a, b in slices]
+    lo, hi = slices[rank]
+    if hi > lo:
+        sub_states = None if states is None else ([i - lo for i in range(lo, hi) if skipped(i)], True)
+        local = run_node(frames[lo:hi + 1], multiplier, sub_states)[:-1]
+    else:
+        local = torch.zeros((0,) + tuple(frames.shape[1:3]) + (3,), dtype=torch.float32)
+    assert local.shape[0] == counts[rank], (local.shape, counts, rank)
+    if device is not None:
+        local = local.to(device)
+    full = gather_frames(local.contiguous(), counts, dist, dst)
+    if rank != dst:
+        return None
+    return torch.cat([full.cpu(), frames[-1:, ..., :3].to(torch.float32)], 0)

@@ -59,6 +59,24 @@ def _worker(rank, world, port, q):
             ref = FN.FILM_VFI().vfi("film_net_fp32.pt", fr, multiplier=c["multiplier"], optional_interpolation_states=s,
                                     _engine=eng)[0]
             ok = ok and got.shape == ref.shape and torch.equal(got, ref)
+    # Sepconv node (generic_frame_loop, recursive bisection) sharded the same way
+    import cfi_b200.sepconv_node as SN
+
+    class Mid:
+        def middle_frame(self, a, b):
+            return 0.25 * a + 0.75 * b + 0.1 * (a - b).abs()
+
+    def run_sep(sub, m, st):
+        s = None if st is None else FN.InterpolationStateList(list(st[0]), st[1])
+        return SN.SepconvVFI().vfi("sepconv.pth", sub, multiplier=m, optional_interpolation_states=s, _engine=Mid())[0]
+
+    for c in [dict(n=6, multiplier=4, states=None), dict(n=5, multiplier=3, states=([1, 2], True)),
+              dict(n=4, multiplier=2, states=([0], False))]:
+        fr = _clip(c["n"])
+        got = shard.generic_vfi_sharded(run_sep, fr, c["multiplier"], c["states"], dist)
+        if rank == 0:
+            ref = run_sep(fr, c["multiplier"], c["states"])
+            ok = ok and got.shape == ref.shape and torch.equal(got, ref)
     if rank == 0:
         q.put(ok)
     dist.destroy_process_group()

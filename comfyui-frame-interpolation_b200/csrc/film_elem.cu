@@ -371,13 +371,13 @@ __global__ void out_rgb_kernel(const T* __restrict__ x, int pitch, const float* 
 cudaError_t launch_film_gather_rgb(const float* frames, int cstride, const FilmFrameIdx& idx, int n, int H, int W,
                                    float* out, cudaStream_t st) {
   const size_t hw = (size_t)H * W;
-  gather_rgb_kernel<<<grid_for((size_t)n * hw, 256), 256, 0, st>>>(frames, cstride, idx, n, hw, out);
+  VFI_LAUNCH(gather_rgb_kernel, grid_for((size_t)n * hw, 256), 256, 0, st, frames, cstride, idx, n, hw, out);
   return cudaGetLastError();
 }
 
 cudaError_t launch_film_pool_rgb(const float* in, float* out, int n, int H, int W, cudaStream_t st) {
   if ((H >> 1) < 1 || (W >> 1) < 1) return cudaErrorInvalidValue;
-  pool_rgb_kernel<<<grid_for((size_t)n * (H >> 1) * (W >> 1), 256), 256, 0, st>>>(in, out, n, H, W);
+  VFI_LAUNCH(pool_rgb_kernel, grid_for((size_t)n * (H >> 1) * (W >> 1), 256), 256, 0, st, in, out, n, H, W);
   return cudaGetLastError();
 }
 
@@ -385,9 +385,9 @@ cudaError_t launch_film_conv_rgb(int op_type, const float* img, const float* w, 
                                  int out_pitch, int n, int H, int W, cudaStream_t st) {
   const int g = grid_for((size_t)n * H * W * 2, 256);
   if (op_type == OP_BF16)
-    conv_rgb_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(img, w, bias, (__nv_bfloat16*)out, out_pitch, n, H, W);
+    VFI_LAUNCH(conv_rgb_kernel<__nv_bfloat16>, g, 256, 0, st, img, w, bias, (__nv_bfloat16*)out, out_pitch, n, H, W);
   else
-    conv_rgb_kernel<__half><<<g, 256, 0, st>>>(img, w, bias, (__half*)out, out_pitch, n, H, W);
+    VFI_LAUNCH(conv_rgb_kernel<__half>, g, 256, 0, st, img, w, bias, (__half*)out, out_pitch, n, H, W);
   return cudaGetLastError();
 }
 
@@ -396,15 +396,15 @@ cudaError_t launch_film_pool16(int op_type, const void* in, int in_pitch, void* 
   if ((H >> 1) < 1 || (W >> 1) < 1 || (C & 7)) return cudaErrorInvalidValue;
   const int g = grid_for((size_t)n * (H >> 1) * (W >> 1) * (C / 8), 256);
   if (op_type == OP_BF16)
-    pool16_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)in, in_pitch, (__nv_bfloat16*)out, out_pitch,
+    VFI_LAUNCH(pool16_kernel<__nv_bfloat16>, g, 256, 0, st, (const __nv_bfloat16*)in, in_pitch, (__nv_bfloat16*)out, out_pitch,
                                                     C / 8, n, H, W);
   else
-    pool16_kernel<__half><<<g, 256, 0, st>>>((const __half*)in, in_pitch, (__half*)out, out_pitch, C / 8, n, H, W);
+    VFI_LAUNCH(pool16_kernel<__half>, g, 256, 0, st, (const __half*)in, in_pitch, (__half*)out, out_pitch, C / 8, n, H, W);
   return cudaGetLastError();
 }
 
 cudaError_t launch_film_flow_up(const float* v, int h, int w, float* out, int B, int H, int W, cudaStream_t st) {
-  flow_up_kernel<<<grid_for((size_t)B * H * W, 256), 256, 0, st>>>((const float2*)v, h, w, (float2*)out, B, H, W);
+  VFI_LAUNCH(flow_up_kernel, grid_for((size_t)B * H * W, 256), 256, 0, st, (const float2*)v, h, w, (float2*)out, B, H, W);
   return cudaGetLastError();
 }
 
@@ -413,10 +413,10 @@ cudaError_t launch_film_warp16(int op_type, const void* src, int src_pitch, int 
   if (C & 7) return cudaErrorInvalidValue;
   const int g = grid_for((size_t)B * H * W * (C / 8), 256);
   if (op_type == OP_BF16)
-    warp16_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, src_pitch, C / 8, (const float2*)flow,
+    VFI_LAUNCH(warp16_kernel<__nv_bfloat16>, g, 256, 0, st, (const __nv_bfloat16*)src, src_pitch, C / 8, (const float2*)flow,
                                                     fscale, (__nv_bfloat16*)dst, dst_pitch, B, H, W);
   else
-    warp16_kernel<__half><<<g, 256, 0, st>>>((const __half*)src, src_pitch, C / 8, (const float2*)flow, fscale,
+    VFI_LAUNCH(warp16_kernel<__half>, g, 256, 0, st, (const __half*)src, src_pitch, C / 8, (const float2*)flow, fscale,
                                              (__half*)dst, dst_pitch, B, H, W);
   return cudaGetLastError();
 }
@@ -425,17 +425,17 @@ cudaError_t launch_film_misc64(int op_type, const float* img0, const float* img1
                                const float* fflow, void* dst, int dst_pitch, int B, int H, int W, cudaStream_t st) {
   const int g = grid_for((size_t)B * H * W, 256);
   if (op_type == OP_BF16)
-    misc64_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(img0, img1, (const float2*)bflow, (const float2*)fflow,
+    VFI_LAUNCH(misc64_kernel<__nv_bfloat16>, g, 256, 0, st, img0, img1, (const float2*)bflow, (const float2*)fflow,
                                                     (__nv_bfloat16*)dst, dst_pitch, B, H, W);
   else
-    misc64_kernel<__half><<<g, 256, 0, st>>>(img0, img1, (const float2*)bflow, (const float2*)fflow, (__half*)dst,
+    VFI_LAUNCH(misc64_kernel<__half>, g, 256, 0, st, img0, img1, (const float2*)bflow, (const float2*)fflow, (__half*)dst,
                                              dst_pitch, B, H, W);
   return cudaGetLastError();
 }
 
 cudaError_t launch_film_nearest16(const void* in, int h, int w, void* out, int C, int B, int H, int W, cudaStream_t st) {
   if (C & 7) return cudaErrorInvalidValue;
-  nearest16_kernel<<<grid_for((size_t)B * H * W * (C / 8), 256), 256, 0, st>>>((const uint4*)in, h, w, (uint4*)out, C / 8,
+  VFI_LAUNCH(nearest16_kernel, grid_for((size_t)B * H * W * (C / 8), 256), 256, 0, st, (const uint4*)in, h, w, (uint4*)out, C / 8,
                                                                                B, H, W);
   return cudaGetLastError();
 }
@@ -446,10 +446,10 @@ cudaError_t launch_film_flow_head(int op_type, const void* x, int pitch, int C, 
   const size_t npx = (size_t)B * H * W;
   const int g = grid_for(npx, 128);
   if (op_type == OP_BF16)
-    flow_head_kernel<__nv_bfloat16><<<g, 128, 0, st>>>((const __nv_bfloat16*)x, pitch, C, w, bias, (const float2*)v_up,
+    VFI_LAUNCH(flow_head_kernel<__nv_bfloat16>, g, 128, 0, st, (const __nv_bfloat16*)x, pitch, C, w, bias, (const float2*)v_up,
                                                        (float2*)v_out, npx);
   else
-    flow_head_kernel<__half><<<g, 128, 0, st>>>((const __half*)x, pitch, C, w, bias, (const float2*)v_up, (float2*)v_out,
+    VFI_LAUNCH(flow_head_kernel<__half>, g, 128, 0, st, (const __half*)x, pitch, C, w, bias, (const float2*)v_up, (float2*)v_out,
                                                 npx);
   return cudaGetLastError();
 }
@@ -459,9 +459,9 @@ cudaError_t launch_film_out_rgb(int op_type, const void* x, int pitch, const flo
   const size_t npx = (size_t)B * H * W;
   const int g = grid_for(npx, 128);
   if (op_type == OP_BF16)
-    out_rgb_kernel<__nv_bfloat16><<<g, 128, 0, st>>>((const __nv_bfloat16*)x, pitch, w, bias, clamp01, out, npx);
+    VFI_LAUNCH(out_rgb_kernel<__nv_bfloat16>, g, 128, 0, st, (const __nv_bfloat16*)x, pitch, w, bias, clamp01, out, npx);
   else
-    out_rgb_kernel<__half><<<g, 128, 0, st>>>((const __half*)x, pitch, w, bias, clamp01, out, npx);
+    VFI_LAUNCH(out_rgb_kernel<__half>, g, 128, 0, st, (const __half*)x, pitch, w, bias, clamp01, out, npx);
   return cudaGetLastError();
 }
 

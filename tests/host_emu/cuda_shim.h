@@ -20,15 +20,18 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
-#define __shared__ static
+#define __shared__ static thread_local
 #define __restrict__
 struct EmuDim {
   unsigned x = 0, y = 0, z = 0;
 };
-static EmuDim blockIdx, threadIdx;
-static EmuDim blockDim{1, 1, 1}, gridDim{1, 1, 1};
+static thread_local EmuDim blockIdx, threadIdx;
+static thread_local EmuDim blockDim{1, 1, 1}, gridDim{1, 1, 1};
 static inline void __syncthreads() {}
+#include <mutex>
 static inline double atomicAdd(double* p, double v) {
+  static std::mutex m;
+  std::lock_guard<std::mutex> g(m);
   const double o = *p;
   *p += v;
   return o;
@@ -38,14 +41,26 @@ using std::min;
 
 // ---- launches and the few runtime calls the schedules make, for the whole-path emulation (sepconv_full_emu.cpp)
 #define __grid_constant__
-#define VFI_LAUNCH(kernel, grid, block, smem, stream, ...) \
-  do {                                                      \
-    const dim3 _g(grid);                                    \
-    for (unsigned _y = 0; _y < _g.y; ++_y) {                \
-      blockIdx.y = _y;                                      \
-      kernel(__VA_ARGS__);                                  \
-    }                                                       \
-    blockIdx.y = 0;                                         \
+// one host thread per emulated block in x (every kernel walks its range with a grid-stride loop), grid rows in turn
+#include <thread>
+#include <vector>
+#define VFI_LAUNCH(kernel, grid, block, smem, stream, ...)                        \
+  do {                                                                            \
+    const dim3 _g(grid);                                                          \
+    unsigned _t = std::thread::hardware_concurrency();                            \
+    _t = _t < 1 ? 1 : (_t > 16 ? 16 : _t);                                        \
+    if (_t > _g.x) _t = _g.x;                                                     \
+    for (unsigned _y = 0; _y < _g.y; ++_y) {                                      \
+      std::vector<std::thread> _th;                                               \
+      for (unsigned _x = 0; _x < _t; ++_x)                                        \
+        _th.emplace_back([&, _x]() {                                              \
+          blockIdx.x = _x;                                                        \
+          blockIdx.y = _y;                                                        \
+          gridDim.x = _t;                                                         \
+          kernel(__VA_ARGS__);                                                    \
+        });                                                                       \
+      for (auto& _h : _th) _h.join();                                             \
+    }                                                                             \
   } while (0)
 #include <cstdlib>
 #include <cstring>

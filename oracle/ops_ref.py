@@ -3,8 +3,8 @@
 cupy is not installed in this image (and the reference's taichi backend does not import), so the
 reference kernels cannot be launched as the reference launches them.  Pinning: `oracle/ref_ops.py` specialises the reference's
 own kernel strings with the reference's own pre-processor and runs them on the CPU (g++ through tests/host_emu);
-`tests/test_ops_ref_pinned.py` holds `softsplat_sum` / `softsplat` / `costvol_l1` / `sepconv` below to those outputs.
-`correlation_dot` (a kernel of cooperating threads) remains **unpinned**.  Each function below follows the
+`tests/test_ops_ref_pinned.py` holds `softsplat_sum` / `softsplat` / `costvol_l1` / `correlation_dot` / `sepconv` below to
+those outputs.  Each function below follows the
 CUDA-C source string of the reference kernel line by line (cited), in fp32 on NCHW tensors like the reference,
 and is cross-checked in tests/test_ops_ref.py against independent formulations (grid_sample adjoint for the splat,
 unfold-based volumes, explicit double loops on tiny inputs).

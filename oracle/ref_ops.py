@@ -16,7 +16,9 @@ closes that gap without copying any reference source into the repo:
 
 ``tests/test_ops_ref_pinned.py`` holds ``oracle/ops_ref.py`` to these outputs, which makes the chain
 reference kernel source -> oracle -> sm_100a kernels (GPU tests) complete for softsplat_out, costvol_out and sepconv_out.
-Not covered: ``kernel_Correlation_*`` (cooperating threads and shared memory: not expressible with one thread per block).
+``kernel_Correlation_rearrange`` / ``_updateOutput`` (blocks of cooperating threads, shared memory, ``__syncthreads``) run
+through a second shim, ``tests/host_emu/block_emu.h``: every thread of a block is a fiber and ``__syncthreads()`` yields to
+a round-robin scheduler, i.e. the block advances barrier phase by barrier phase in thread order (warp lock-step).
 Nothing here runs on the GPU box (``/root/reference`` does not exist there) and nothing here is product code.
 """
 from __future__ import annotations
@@ -134,3 +136,64 @@ def sepconv_out(ten_in: torch.Tensor, ver: torch.Tensor, hor: torch.Tensor) -> t
     out = ten_in.new_empty([ten_in.shape[0], ten_in.shape[1], ver.shape[2] and hor.shape[2], ver.shape[3] and hor.shape[3]])
     return _run("sepconv", "sepconv_out", {"tenIn": ten_in, "tenVer": ver, "tenHor": hor, "tenOut": out},
                 ("tenIn", "tenVer", "tenHor", "tenOut"), "tenOut")
+
+
+def correlation(first: torch.Tensor, second: torch.Tensor) -> torch.Tensor:
+    """_FunctionCorrelation.forward, cupy_ops/correlation.py:231-296: two rearrange launches (grid (ceil(HW/16), C, N), block
+    16) into zero-initialised padded NHWC buffers, then updateOutput (grid (W, H, N), block 32, C * 4 bytes of dynamic
+    shared memory)."""
+    first, second = first.contiguous().float(), second.contiguous().float()
+    n_, c, h, w = first.shape
+    rbot0 = first.new_zeros([n_, h + 8, w + 8, c])
+    rbot1 = first.new_zeros([n_, h + 8, w + 8, c])
+    out = first.new_zeros([n_, 81, h, w])
+    mod = _ref_module("correlation")
+    utils = importlib.import_module("cupy_ops.utils")
+    src = ""
+    for name, var in (("kernel_Correlation_rearrange", {"input": first, "output": rbot0}),
+                      ("kernel_Correlation_updateOutput", {"rbot0": rbot0, "rbot1": rbot1, "top": out})):
+        key = utils.cuda_kernel(name, getattr(mod, name), var)      # the reference's own pre-processor
+        src += utils.objCudacache[key]["strKernel"]
+    # the only textual change: CUDA's dynamic shared memory declaration becomes the emulation's buffer
+    src = src.replace("extern __shared__ char patch_data_char[];", "char* patch_data_char = emu_dyn_smem;")
+    driver = """
+extern "C" void emu_correlation(int N, int C, int H, int W, const float* first, const float* second, float* rbot0,
+                                float* rbot1, float* out) {
+  const int n = H * W;
+  blockDim.x = 16;
+  gridDim.x = (n + 15) / 16; gridDim.y = C; gridDim.z = N;
+  for (int pass = 0; pass < 2; ++pass)
+    for (unsigned z = 0; z < gridDim.z; ++z)
+      for (unsigned y = 0; y < gridDim.y; ++y)
+        for (unsigned x = 0; x < gridDim.x; ++x)
+          for (unsigned t = 0; t < 16; ++t) {
+            blockIdx.x = x; blockIdx.y = y; blockIdx.z = z; threadIdx.x = t;
+            kernel_Correlation_rearrange(n, pass ? second : first, pass ? rbot1 : rbot0);
+          }
+  std::vector<char> smem((size_t)C * 4);
+  emu_dyn_smem = smem.data();
+  blockDim.x = 32;
+  gridDim.x = W; gridDim.y = H; gridDim.z = N;
+  for (unsigned z = 0; z < gridDim.z; ++z)
+    for (unsigned y = 0; y < gridDim.y; ++y)
+      for (unsigned x = 0; x < gridDim.x; ++x) {
+        blockIdx.x = x; blockIdx.y = y; blockIdx.z = z;
+        block_emu::run_block(32, [&]() { kernel_Correlation_updateOutput(81 * H * W, rbot0, rbot1, out); });
+      }
+}
+"""
+    os.makedirs(OUT, exist_ok=True)
+    tag = hashlib.sha1((src + driver).encode()).hexdigest()[:12]
+    base = os.path.join(OUT, f"correlation_{tag}")
+    if not os.path.exists(base + ".so"):
+        with open(base + ".cpp", "w") as fh:
+            fh.write(f'#include "{os.path.join(ROOT, "tests", "host_emu", "block_emu.h")}"\n' + src + driver)
+        r = subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", base + ".so", base + ".cpp"],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("g++ failed on the specialised reference kernel:\n" + r.stderr[-3000:])
+    lib = ctypes.CDLL(base + ".so")
+    vp = ctypes.c_void_p
+    lib.emu_correlation(n_, c, h, w, vp(first.data_ptr()), vp(second.data_ptr()), vp(rbot0.data_ptr()), vp(rbot1.data_ptr()),
+                        vp(out.data_ptr()))
+    return out

@@ -53,3 +53,12 @@ def test_sepconv_matches_reference_kernel(k, hw):
     ref = ref_ops.sepconv_out(x, ver, hor)
     got = ops_ref.sepconv(x, ver, hor)
     assert (got - ref).abs().max().item() <= 1e-4 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("shape", [(1, 40, 5, 6), (2, 7, 4, 9)])
+def test_correlation_dot_matches_reference_kernels(shape):
+    """kernel_Correlation_rearrange + kernel_Correlation_updateOutput with blocks of 16 / 32 cooperating threads (fibers)."""
+    g = torch.Generator().manual_seed(shape[1])
+    a, b = torch.randn(*shape, generator=g), torch.randn(*shape, generator=g)
+    ref = ref_ops.correlation(a, b)
+    assert (ops_ref.correlation_dot(a, b) - ref).abs().max().item() <= 1e-5

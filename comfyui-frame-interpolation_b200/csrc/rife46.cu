@@ -929,6 +929,23 @@ int vfi_sepconv(vfi_ctx* c, const float* in, const float* ver, const float* hor,
   return VFI_OK;
 }
 
+int vfi_adacof(vfi_ctx* c, const float* in, const float* weight, const float* offset_i, const float* offset_j, float* out, int N,
+               int C, int Hin, int Win, int F, int dilation, int Ho, int Wo, void* stream) {
+  if (!c || !in || !weight || !offset_i || !offset_j || !out) return fail(VFI_E_INVALID, "null argument");
+  if (F < 1 || dilation < 1 || Hin - ((F - 1) * dilation + 1) != Ho - 1 || Win - ((F - 1) * dilation + 1) != Wo - 1)
+    return fail(VFI_E_INVALID, "adacof: input size must be output size + (F - 1) * dilation (adacof.py:274-279)");
+  CK(launch_adacof(in, weight, offset_i, offset_j, out, N, C, Hin, Win, F, dilation, Ho, Wo, static_cast<cudaStream_t>(stream)));
+  c->launches += 1;
+  return VFI_OK;
+}
+
+int vfi_edt_pass(vfi_ctx* c, const float* data, float* out, int bs, int h, int w, float diam2, void* stream) {
+  if (!c || !data || !out) return fail(VFI_E_INVALID, "null argument");
+  CK(launch_edt_pass(data, out, bs, h, w, diam2, static_cast<cudaStream_t>(stream)));
+  c->launches += 1;
+  return VFI_OK;
+}
+
 int vfi_rife46_debug_layer(vfi_ctx* c, int block, int layer, const void* in, void* out, void* out_mask, int B, int H,
                            int W, int impl, void* stream) {
   if (!c || block < 0 || layer < 0 || !in || !out) return fail(VFI_E_INVALID, "bad argument");

@@ -249,6 +249,10 @@ cudaError_t launch_film_flow_head(int op_type, const void* x, int pitch, int C, 
 cudaError_t launch_film_out_rgb(int op_type, const void* x, int pitch, const float* w, const float* bias, int clamp01,
                                 float* out, int B, int H, int W, cudaStream_t st);
 
+cudaError_t launch_adacof(const float* in, const float* weight, const float* off_i, const float* off_j, float* out, int N,
+                          int C, int Hin, int Win, int F, int dil, int Ho, int Wo, cudaStream_t st);
+cudaError_t launch_edt_pass(const float* data, float* out, int bs, int h, int w, float diam2, cudaStream_t st);
+
 void set_error(const std::string& s);
 
 // ---- context access for film.cu (vfi_ctx is defined in rife46.cu) ----

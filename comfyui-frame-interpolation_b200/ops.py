@@ -151,9 +151,45 @@ class ModuleCorrelation(torch.nn.Module):
         return _FunctionCorrelation.apply(tenFirst, tenSecond)
 
 
-def batch_edt(*a, **k):
-    raise NotImplementedError("batch_edt: only used by the unregistered EISAI node (SURVEY.md 2.1); not built")
+def batch_edt(img, block=1024):
+    """cupy_ops/batch_edt.py:46-117: Euclidean distance transform of a batch of line drawings (white lines, black
+    whitespace), img (bs,h,w) or (bs,1,h,w); `block` is accepted for signature compatibility only."""
+    expand = False
+    if len(img.shape) == 4:
+        assert img.shape[1] == 1
+        img = img.squeeze(1)
+        expand = True
+    if not img.is_cuda:
+        raise VfiError("vfi ops need CUDA tensors (no CPU fallback)")  # the reference raises NotImplementedError here (:97)
+    bs, h, w = img.shape
+    diam2 = h ** 2 + w ** 2
+    odtype = img.dtype
+    ctx, st = _context(img.device), _stream(img)
+    data = ((1 - img.type(torch.float32)) * diam2).contiguous()           # first pass, y-axis (:66-80)
+    intermed = torch.empty_like(data)
+    check(lib().vfi_edt_pass(ctx, data.data_ptr(), intermed.data_ptr(), bs, h, w, float(diam2), st))
+    intermed = intermed.permute(0, 2, 1).contiguous()                     # second pass, x-axis (:82-95)
+    out = torch.empty_like(intermed)
+    check(lib().vfi_edt_pass(ctx, intermed.data_ptr(), out.data_ptr(), bs, w, h, float(diam2), st))
+    ans = out.permute(0, 2, 1).sqrt()
+    ans = ans.type(odtype) if odtype != ans.dtype else ans
+    if expand:
+        ans = ans.unsqueeze(1)
+    return ans
 
 
-def FunctionAdaCoF(*a, **k):
-    raise NotImplementedError("FunctionAdaCoF: ST-MFNet only (4-frame model, out of scope, SURVEY.md 2.1)")
+class FunctionAdaCoF:
+    """cupy_ops/adacof.py:259-330 (forward only): adaptive collaboration of flows."""
+
+    @staticmethod
+    def apply(input, weight, offset_i, offset_j, dilation):
+        input, weight, offset_i, offset_j = _prep(input, weight, offset_i, offset_j)
+        n, c, hin, win = input.shape
+        f = int(round(weight.size(1) ** 0.5))
+        ho, wo = weight.size(2), weight.size(3)
+        assert hin - ((f - 1) * dilation + 1) == ho - 1 and win - ((f - 1) * dilation + 1) == wo - 1
+        assert tuple(offset_i.shape) == tuple(weight.shape) == tuple(offset_j.shape)
+        out = input.new_empty(n, c, ho, wo)
+        check(lib().vfi_adacof(_context(input.device), input.data_ptr(), weight.data_ptr(), offset_i.data_ptr(),
+                               offset_j.data_ptr(), out.data_ptr(), n, c, hin, win, f, int(dilation), ho, wo, _stream(input)))
+        return out

@@ -104,6 +104,13 @@ int vfi_corr_dot(vfi_ctx* ctx, const float* first, const float* second, float* o
                  void* stream);
 int vfi_sepconv(vfi_ctx* ctx, const float* in, const float* ver, const float* hor, float* out, int N, int C, int H,
                 int W, int Kv, int Kh, void* stream);
+/*   vfi_adacof        : kernel_AdaCoF_updateOutput (cupy_ops/adacof.py:5-62, wrapper :259-330): in [N,C,Hin,Win], weight /
+ *                       offset_i / offset_j [N,F*F,Ho,Wo] with Hin = Ho + (F-1)*dilation, out [N,C,Ho,Wo]
+ *   vfi_edt_pass      : kernel_dt (cupy_ops/batch_edt.py:9-41): one row pass of the separable squared distance transform,
+ *                       data / out [bs,h,w]; batch_edt (:46-117) runs it twice around a transpose */
+int vfi_adacof(vfi_ctx* ctx, const float* in, const float* weight, const float* offset_i, const float* offset_j, float* out,
+               int N, int C, int Hin, int Win, int F, int dilation, int Ho, int Wo, void* stream);
+int vfi_edt_pass(vfi_ctx* ctx, const float* data, float* out, int bs, int h, int w, float diam2, void* stream);
 
 /* FILM (film_net) - SURVEY.md section 8 row a10 --------------------------------------------------------- */
 #define VFI_FILM_NUM_TENSORS 82      /* film_arch.Interpolator().state_dict() (film_arch.py:377-393) */

@@ -116,3 +116,52 @@ def sepconv(ten_in: torch.Tensor, ver: torch.Tensor, hor: torch.Tensor) -> torch
             prod = ten_in[:, :, fy:fy + h, fx:fx + w] * ver[:, fy:fy + 1] * hor[:, fx:fx + 1]
             out += prod.double()
     return out.float()
+
+
+def adacof(inp: torch.Tensor, weight: torch.Tensor, off_i: torch.Tensor, off_j: torch.Tensor, dilation: int) -> torch.Tensor:
+    """kernel_AdaCoF_updateOutput - cupy_ops/adacof.py:5-62: for every tap (k, l) the input is sampled at
+    (i + k d + alpha, j + l d + beta) with A = (int) alpha TRUNCATED toward zero, the four tap indices clamped to the
+    image and the (unclamped, possibly negative) fractions alpha - A, beta - B as weights."""
+    n, c, hin, win = inp.shape
+    f = int(round(weight.shape[1] ** 0.5))
+    ho, wo = weight.shape[2], weight.shape[3]
+    ii = torch.arange(ho).view(1, ho, 1)
+    jj = torch.arange(wo).view(1, 1, wo)
+    nn = torch.arange(n).view(n, 1, 1)
+    out = torch.zeros(n, c, ho, wo, dtype=torch.float64)
+    for k in range(f):
+        for l in range(f):
+            t = k * f + l
+            w, al, be = weight[:, t], off_i[:, t], off_j[:, t]
+            a_, b_ = al.to(torch.int32).long(), be.to(torch.int32).long()   # C cast: truncation toward zero
+            y0 = (ii + k * dilation + a_).clamp(0, hin - 1)
+            y1 = (ii + k * dilation + a_ + 1).clamp(0, hin - 1)
+            x0 = (jj + l * dilation + b_).clamp(0, win - 1)
+            x1 = (jj + l * dilation + b_ + 1).clamp(0, win - 1)
+            fa, fb = (al - a_.float()), (be - b_.float())
+            g = lambda y, x: inp[nn, :, y, x].permute(0, 3, 1, 2)   # noqa: E731  -> [n, c, ho, wo]
+            val = (g(y0, x0) * ((1 - fa) * (1 - fb)).unsqueeze(1) + g(y1, x0) * (fa * (1 - fb)).unsqueeze(1) +
+                   g(y0, x1) * ((1 - fa) * fb).unsqueeze(1) + g(y1, x1) * (fa * fb).unsqueeze(1))
+            out += (w.unsqueeze(1) * val).double()
+    return out.float()
+
+
+def edt_pass(data: torch.Tensor, diam2: float) -> torch.Tensor:
+    """kernel_dt - cupy_ops/batch_edt.py:9-41: out[b,i,j] = min(diam2, min_j' data[b,i,j'] + (j - j')^2)."""
+    w = data.shape[-1]
+    j = torch.arange(w, dtype=torch.float32)
+    cost = data.unsqueeze(-2) + (j.view(-1, 1) - j.view(1, -1)) ** 2      # [..., j, j']
+    return torch.minimum(cost.min(-1).values, torch.tensor(float(diam2)))
+
+
+def batch_edt(img: torch.Tensor) -> torch.Tensor:
+    """batch_edt - cupy_ops/batch_edt.py:46-117 (the cupy branch): two kernel_dt passes around a transpose, then sqrt."""
+    expand = img.dim() == 4
+    if expand:
+        img = img.squeeze(1)
+    bs, h, w = img.shape
+    diam2 = h ** 2 + w ** 2
+    data = (1 - img.float()) * diam2
+    inter = edt_pass(data, diam2).permute(0, 2, 1).contiguous()
+    ans = edt_pass(inter, diam2).permute(0, 2, 1).sqrt().to(img.dtype)
+    return ans.unsqueeze(1) if expand else ans

@@ -197,3 +197,36 @@ extern "C" void emu_correlation(int N, int C, int H, int W, const float* first, 
     lib.emu_correlation(n_, c, h, w, vp(first.data_ptr()), vp(second.data_ptr()), vp(rbot0.data_ptr()), vp(rbot1.data_ptr()),
                         vp(out.data_ptr()))
     return out
+
+
+def adacof(inp, weight, off_i, off_j, dilation: int) -> torch.Tensor:
+    """FunctionAdaCoF.forward, cupy_ops/adacof.py:259-330: kernel_AdaCoF_updateOutput with F_SIZE / DILATION substituted."""
+    inp, weight, off_i, off_j = [t.contiguous().float() for t in (inp, weight, off_i, off_j)]
+    out = inp.new_zeros(inp.shape[0], inp.shape[1], weight.shape[2], weight.shape[3])
+    mod = _ref_module("adacof")
+    utils = importlib.import_module("cupy_ops.utils")
+    f = int(round(weight.shape[1] ** 0.5))
+    var = {"input": inp, "weight": weight, "offset_i": off_i, "offset_j": off_j, "output": out}
+    key = utils.cuda_kernel("kernel_AdaCoF_updateOutput", mod.kernel_AdaCoF_updateOutput, var, F_SIZE=str(f),
+                            DILATION=str(dilation))
+    lib = _compile("kernel_AdaCoF_updateOutput", utils.objCudacache[key]["strKernel"])
+    vp = ctypes.c_void_p
+    lib.kernel_AdaCoF_updateOutput(ctypes.c_int(out.nelement()), vp(inp.data_ptr()), vp(weight.data_ptr()), vp(off_i.data_ptr()),
+                                   vp(off_j.data_ptr()), vp(out.data_ptr()))
+    return out
+
+
+def edt_pass(data: torch.Tensor, diam2: float) -> torch.Tensor:
+    """kernel_dt, cupy_ops/batch_edt.py:9-41 (a raw string, no pre-processing; one thread per element, no stride loop:
+    every element index is emulated as its own block)."""
+    mod = _ref_module("batch_edt")
+    name, src = mod._batch_edt_kernel
+    data = data.contiguous().float()
+    bs, h, w = data.shape
+    out = torch.zeros_like(data)
+    driver = ("\nextern \"C\" void emu_dt(int bs, int h, int w, float diam2, float* data, float* out) {\n"
+              "  blockDim.x = 1; gridDim.x = bs * h * w; threadIdx.x = 0;\n"
+              "  for (int i = 0; i < bs * h * w; ++i) { blockIdx.x = i; kernel_dt(bs, h, w, diam2, data, out); }\n}\n")
+    lib = _compile(name, src + driver)
+    lib.emu_dt(bs, h, w, ctypes.c_float(diam2), ctypes.c_void_p(data.data_ptr()), ctypes.c_void_p(out.data_ptr()))
+    return out

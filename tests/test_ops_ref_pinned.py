@@ -62,3 +62,28 @@ def test_correlation_dot_matches_reference_kernels(shape):
     a, b = torch.randn(*shape, generator=g), torch.randn(*shape, generator=g)
     ref = ref_ops.correlation(a, b)
     assert (ops_ref.correlation_dot(a, b) - ref).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("f,dil", [(3, 1), (5, 2)])
+def test_adacof_matches_reference_kernel(f, dil):
+    g = torch.Generator().manual_seed(f)
+    n, c, ho, wo = 2, 3, 6, 7
+    x = torch.randn(n, c, ho + (f - 1) * dil, wo + (f - 1) * dil, generator=g)
+    w = torch.randn(n, f * f, ho, wo, generator=g)
+    oi = torch.randn(n, f * f, ho, wo, generator=g) * 2.5      # negative offsets: (int) truncation != floor
+    oj = torch.randn(n, f * f, ho, wo, generator=g) * 2.5
+    ref = ref_ops.adacof(x, w, oi, oj, dil)
+    assert (ops_ref.adacof(x, w, oi, oj, dil) - ref).abs().max().item() <= 2e-5 * max(1.0, float(ref.abs().max()))
+
+
+def test_edt_matches_reference_kernel_and_scipy():
+    g = torch.Generator().manual_seed(2)
+    img = (torch.rand(2, 9, 12, generator=g) > 0.85).float()
+    img[1] = 0                                                   # empty image: defaults to the diameter
+    diam2 = 9 ** 2 + 12 ** 2
+    data = (1 - img) * diam2
+    assert torch.equal(ops_ref.edt_pass(data, diam2), ref_ops.edt_pass(data, diam2))
+    from scipy import ndimage
+    want = ndimage.distance_transform_edt(1 - img[0].numpy())
+    assert abs(ops_ref.batch_edt(img)[0].numpy() - want).max() <= 1e-4
+    assert float(ops_ref.batch_edt(img)[1].min()) == pytest.approx(diam2 ** 0.5)

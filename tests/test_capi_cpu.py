@@ -83,3 +83,18 @@ def test_state_dict_layouts_agree(pkg):
         assert counts[code] == len(spec), arch
     assert [c for _, c in O.BLOCK_SPECS_426] == [192, 128, 96, 64, 32]
     assert len(O.SCALE_LIST["4.26"]) == 5 and set(ARCH_CODE) == set(O.SCALE_LIST)
+
+
+def test_ops_module_has_every_name_the_reference_exports(pkg):
+    """vfi_models/ops/__init__.py:19-21: the twelve names the reference re-exports from its cupy / taichi backends (and its
+    models import, e.g. gmfss_fortuna/GMFSS_Fortuna_union_arch.py:28, stmfnet/stmfnet_arch.py:28, eisai/eisai_arch.py:53);
+    `sys.modules["vfi_models.ops"] = cfi_b200.ops` is the drop-in for those models."""
+    import cfi_b200.ops as ops
+    names = ["softsplat", "ModuleSoftsplat", "FunctionSoftsplat", "softsplat_func", "costvol_func", "sepconv_func", "init",
+             "batch_edt", "FunctionAdaCoF", "ModuleCorrelation", "FunctionCorrelation", "_FunctionCorrelation"]
+    for n in names:
+        assert hasattr(ops, n), n
+    ref_init = "/root/reference/vfi_models/ops/__init__.py"
+    if os.path.exists(ref_init):   # build container: the list above IS the reference's
+        line = [ln for ln in open(ref_init) if "from .cupy_ops import" in ln][0]
+        assert sorted(x.strip() for x in line.split("import", 1)[1].split(",")) == sorted(names)

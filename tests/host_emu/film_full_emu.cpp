@@ -26,8 +26,10 @@ extern "C" const char* vfi_last_error(void) { return vfi::g_err.c_str(); }
 #include "../../comfyui-frame-interpolation_b200/csrc/film.cu"
 
 extern "C" {
+// flows (optional): the five finest levels of the forward, then of the backward flow pyramid, each [H_l, W_l, 2] fp32,
+// concatenated (what debug_forward returns as forward_flow_pyramid / backward_flow_pyramid, film_arch.py:417-419, :450-455)
 int emu_film(const float* const* tensors, const int64_t* numel, int n_tensors, const float* frames, int H, int W, int C,
-             int clamp01, float* out) {
+             int clamp01, float* out, float* flows) {
   vfi_ctx ctx;
   int rc = vfi_film_load(&ctx, tensors, numel, n_tensors, VFI_OPERAND_F16);
   if (rc) return rc;
@@ -35,6 +37,15 @@ int emu_film(const float* const* tensors, const int64_t* numel, int n_tensors, c
   if (rc) return rc;
   const int32_t f0[1] = {0}, f1[1] = {1};
   rc = vfi_film_forward(&ctx, frames, 2, H, W, C, f0, f1, 1, clamp01, out, nullptr);
+  if (!rc && flows) {
+    float* dst = flows;
+    for (int dir = 0; dir < 2; ++dir)
+      for (int l = 0; l < 5; ++l) {
+        const size_t n = (size_t)(H >> l) * (W >> l) * 2;
+        std::memcpy(dst, ctx.film->v[dir][l].p, n * sizeof(float));
+        dst += n;
+      }
+  }
   vfi::film_destroy(ctx.film);
   return rc ? rc : 1000 + ctx.launches;
 }

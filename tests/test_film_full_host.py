@@ -46,11 +46,28 @@ def test_film_whole_path_on_host_matches_reference(emu, pkg):
     fr = film_inputs(cfg).contiguous()
     out = torch.zeros(1, cfg["h"], cfg["w"], 3)
     emu.vfi_last_error.restype = C.c_char_p
-    rc = emu.emu_film(ptrs, numel, len(hold), C.c_void_p(fr.data_ptr()), cfg["h"], cfg["w"], 3, 0, C.c_void_p(out.data_ptr()))
+    h, w = cfg["h"], cfg["w"]
+    nflow = sum((h >> l) * (w >> l) * 2 for l in range(5))
+    flows = torch.zeros(2 * nflow)
+    rc = emu.emu_film(ptrs, numel, len(hold), C.c_void_p(fr.data_ptr()), h, w, 3, 0, C.c_void_p(out.data_ptr()),
+                      C.c_void_p(flows.data_ptr()))
     assert rc >= 1000, (rc, emu.vfi_last_error())
     mse = float(((out.double() - ref.double()) ** 2).mean())
     psnr = 99.0 if mse == 0 else 10 * math.log10(1.0 / mse)
     print(f"host emulation of the whole FILM path: {rc - 1000} launches, PSNR {psnr:.2f} dB, "
           f"max abs {float((out - ref).abs().max()):.2e}")
+    # the flow pyramids (fp32 recurrence on fp16 features) against the reference's debug_forward output, level by level
+    gold = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    off = 0
+    worst = 0.0
+    for key in ("fwd_flow", "bwd_flow"):
+        for l in range(5):
+            n = (h >> l) * (w >> l) * 2
+            got = flows[off:off + n].view(h >> l, w >> l, 2)
+            want = torch.from_numpy(gold[f"{key}{l}"])[0].permute(1, 2, 0)
+            worst = max(worst, float((got - want).abs().max()))
+            off += n
+    print(f"flow pyramids: max abs error {worst:.4f} px")
+    assert worst <= 0.05, worst
     assert rc - 1000 == 192
     assert psnr >= 55.0, psnr   # fp16 operands / activations vs the fp32 reference (GPU, same checker: 64.9 dB at 72x104)

@@ -87,7 +87,13 @@ __device__ __forceinline__ void ring_next(uint32_t& slot, uint32_t& ph, uint32_t
 // trunk needs in the epilogue: a PReLU with one learned slope (a > 0 ? a : slope * a, any sign / size of slope) and a
 // residual tensor added after it (same layout as the output; it may BE the output: every thread reads its 16 channels
 // before it writes them).
-template <typename T, bool EXT>
+//
+// CL = 2 (VFI_SC_CLUSTER=2; written at the end of r01, NEVER RUN, default off): two CTAs of a thread-block cluster work on
+// neighbouring passes of the same output-channel split and share every weight slot - each CTA's B producer fetches HALF of
+// a slot from L2 and the bulk copy is multicast into both CTAs' shared memory (each CTA's own `full` barrier counts the
+// bytes landing in it), and a slot's `empty` barrier (count 2) receives the multicast tcgen05.commit of BOTH CTAs' MMAs.
+// Weight bytes per SM and cycle halve (64 / (2 mt) B/clk), which is what the L2-bound estimate of DESIGN.md 6.1 asks for.
+template <typename T, bool EXT, int CL>
 __global__ void __launch_bounds__(kSThreads, 1) streamconv_kernel(const __grid_constant__ StreamConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   SCtrl* ctrl = reinterpret_cast<SCtrl*>(smem);
@@ -95,10 +101,26 @@ __global__ void __launch_bounds__(kSThreads, 1) streamconv_kernel(const __grid_c
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int split = blockIdx.x % p.nsplit;
-  const int first = blockIdx.x / p.nsplit;  // this CTA's first pass; it then strides by ctas_per_split
-  if (first >= p.ctas_per_split) return;
-  const int my_passes = (p.npasses - first + p.ctas_per_split - 1) / p.ctas_per_split;
+  // the k-th pass of this CTA is pass0 + k * pass_stride; passes past the end have no valid tile (zero-filled A, no stores)
+  int split, pass0, pass_stride, my_passes;
+  uint32_t crank = 0;
+  if constexpr (CL == 2) {
+    crank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1;          // cluster index; p.ctas_per_split counts CLUSTERS per split here
+    split = pair % p.nsplit;
+    const int pf = pair / p.nsplit;
+    const int npp = (p.npasses + 1) >> 1;      // pass pairs
+    my_passes = (npp - pf + p.ctas_per_split - 1) / p.ctas_per_split;   // the same for both CTAs of the cluster
+    pass0 = 2 * pf + (int)crank;
+    pass_stride = 2 * p.ctas_per_split;
+  } else {
+    split = blockIdx.x % p.nsplit;
+    const int first = blockIdx.x / p.nsplit;
+    if (first >= p.ctas_per_split) return;
+    my_passes = (p.npasses - first + p.ctas_per_split - 1) / p.ctas_per_split;
+    pass0 = first;
+    pass_stride = p.ctas_per_split;
+  }
   const int mt = p.mt, nsets = p.nsets;
 
   const uint32_t smem_base = smem_u32(smem);
@@ -118,7 +140,7 @@ __global__ void __launch_bounds__(kSThreads, 1) streamconv_kernel(const __grid_c
     }
     for (int s = 0; s < p.b_slots; ++s) {
       mbar_init(bar_bfull + 8 * s, 1);
-      mbar_init(bar_bempty + 8 * s, 1);
+      mbar_init(bar_bempty + 8 * s, (uint32_t)CL);  // the tcgen05.commit of every CTA that reads the slot
     }
     for (int s = 0; s < nsets; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);                     // tcgen05.commit after the last k-block
@@ -128,7 +150,10 @@ __global__ void __launch_bounds__(kSThreads, 1) streamconv_kernel(const __grid_c
   }
   if (warp == kSMmaWarp) tmem_alloc(smem_base + offsetof(SCtrl, tmem_base), p.tmem_cols);
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CL == 2)
+    cluster_sync_all();  // the peer's barriers are initialised before anything is multicast to them
+  else
+    __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctrl->tmem_base;
 
@@ -164,7 +189,10 @@ __global__ void __launch_bounds__(kSThreads, 1) streamconv_kernel(const __grid_c
               }
             }
             accum = 1u;
-            umma_commit(bar_bempty + 8 * bslot);  // weight slot free once these MMAs have read it
+            if constexpr (CL == 2)
+              umma_commit_multicast(bar_bempty + 8 * bslot, (uint16_t)0x3);  // ... in both CTAs of the cluster
+            else
+              umma_commit(bar_bempty + 8 * bslot);  // weight slot free once these MMAs have read it
             ring_next(bslot, bph, (uint32_t)p.b_slots);
           }
           umma_commit(bar_aempty + 8 * aslot);  // window slot free
@@ -179,7 +207,7 @@ __global__ void __launch_bounds__(kSThreads, 1) streamconv_kernel(const __grid_c
       asm volatile("griddepcontrol.wait;" ::: "memory");  // the input is the previous kernels' output
       uint32_t slot = 0, ph = 0;
       for (int k = 0; k < my_passes; ++k) {
-        const int pass = first + k * p.ctas_per_split;
+        const int pass = pass0 + k * pass_stride;
         TileCoord tc[2];
         tc[0] = tile_coord(p, pass * mt);
         tc[1] = tile_coord(p, pass * mt + 1);
@@ -206,8 +234,14 @@ __global__ void __launch_bounds__(kSThreads, 1) streamconv_kernel(const __grid_c
       for (int k = 0; k < my_passes; ++k) {
         for (int j = 0; j < per_pass; ++j) {
           mbar_wait(bar_bempty + 8 * slot, ph ^ 1u, 16);
-          mbar_arrive_expect_tx(bar_bfull + 8 * slot, p.b_slot_bytes);
-          bulk_g2s(b_smem + slot * p.b_slot_bytes, wsrc + (size_t)j * p.b_slot_bytes, p.b_slot_bytes, bar_bfull + 8 * slot);
+          mbar_arrive_expect_tx(bar_bfull + 8 * slot, p.b_slot_bytes);  // CL = 2: my half + the peer's half land here
+          if constexpr (CL == 2) {
+            const uint32_t half = p.b_slot_bytes >> 1;
+            bulk_g2s_multicast(b_smem + slot * p.b_slot_bytes + crank * half, wsrc + (size_t)j * p.b_slot_bytes + crank * half,
+                               half, bar_bfull + 8 * slot, (uint16_t)0x3);
+          } else {
+            bulk_g2s(b_smem + slot * p.b_slot_bytes, wsrc + (size_t)j * p.b_slot_bytes, p.b_slot_bytes, bar_bfull + 8 * slot);
+          }
           ring_next(slot, ph, (uint32_t)p.b_slots);
         }
       }
@@ -230,7 +264,7 @@ __global__ void __launch_bounds__(kSThreads, 1) streamconv_kernel(const __grid_c
       const float slope = p.act ? 0.2f : 1.f;  // max(a, slope * a): LeakyReLU(0.2) or identity
       const uint32_t taddr = tmem_base + (uint32_t)(set * mt + t) * p.acc_stride + ((uint32_t)(q * 32) << 16);
       for (int k = set; k < my_passes; k += nsets) {
-        const int pass = first + k * p.ctas_per_split;
+        const int pass = pass0 + k * pass_stride;
         const TileCoord tc = tile_coord(p, pass * mt + t);
         const int gy = tc.ty * kTileH + py, gx = tc.tx * kTileW + px;
         const bool valid = (tc.b < p.B) && (gy < p.H) && (gx < p.W);
@@ -291,7 +325,10 @@ __global__ void __launch_bounds__(kSThreads, 1) streamconv_kernel(const __grid_c
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CL == 2)
+    cluster_sync_all();  // no CTA leaves while its peer may still multicast into it or arrive on its barriers
+  else
+    __syncthreads();
   if (warp == kSMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
@@ -562,11 +599,17 @@ cudaError_t launch_streamconv(const StreamConvLayer& L, int op_type, const void*
   } else {
     p.tm[1] = p.tm[0];
   }
-  int cps = num_sms / p.nsplit;
+  static const int cluster = [] {  // VFI_SC_CLUSTER=2: two-CTA clusters sharing the weight stream by multicast (never run yet)
+    const char* e = std::getenv("VFI_SC_CLUSTER");
+    return (e && e[0] == '2') ? 2 : 1;
+  }();
+  const int cl = (cluster == 2 && p.npasses >= 2) ? 2 : 1;
+  const int units = cl == 2 ? (p.npasses + 1) / 2 : p.npasses;  // passes, or pass pairs (one per cluster)
+  int cps = num_sms / cl / p.nsplit;                             // CTAs (clusters) per output-channel split
   if (cps < 1) cps = 1;
-  if (cps > p.npasses) cps = p.npasses;
+  if (cps > units) cps = units;
   p.ctas_per_split = cps;
-  const int grid = cps * p.nsplit;
+  const int grid = cps * p.nsplit * cl;
   static const bool pdl = [] {
     const char* e = std::getenv("VFI_PDL");
     return !(e && e[0] == '0');
@@ -579,18 +622,33 @@ cudaError_t launch_streamconv(const StreamConvLayer& L, int op_type, const void*
     cfg.blockDim = dim3((unsigned)kSThreads);
     cfg.dynamicSmemBytes = p.smem_bytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pdl) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    if (cl == 2) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = 2;
+      attr[na].val.clusterDim.y = 1;
+      attr[na].val.clusterDim.z = 1;
+      ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, kern, p);
   };
   cudaError_t err;
-  if (L.ext)
-    err = (op_type == OP_BF16) ? go(streamconv_kernel<__nv_bfloat16, true>) : go(streamconv_kernel<__half, true>);
+  if (cl == 2 && L.ext)
+    err = (op_type == OP_BF16) ? go(streamconv_kernel<__nv_bfloat16, true, 2>) : go(streamconv_kernel<__half, true, 2>);
+  else if (cl == 2)
+    err = (op_type == OP_BF16) ? go(streamconv_kernel<__nv_bfloat16, false, 2>) : go(streamconv_kernel<__half, false, 2>);
+  else if (L.ext)
+    err = (op_type == OP_BF16) ? go(streamconv_kernel<__nv_bfloat16, true, 1>) : go(streamconv_kernel<__half, true, 1>);
   else
-    err = (op_type == OP_BF16) ? go(streamconv_kernel<__nv_bfloat16, false>) : go(streamconv_kernel<__half, false>);
+    err = (op_type == OP_BF16) ? go(streamconv_kernel<__nv_bfloat16, false, 1>) : go(streamconv_kernel<__half, false, 1>);
   if (err != cudaSuccess) return err;
   return cudaGetLastError();
 #endif  // VFI_HOST_EMU

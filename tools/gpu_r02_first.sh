@@ -7,6 +7,9 @@ TAILN=30 run film_check_full python tools/film_gpu_check.py
 TAILN=12 run sepconv_check python tools/sepconv_gpu_check.py
 TAILN=30 TMO=900 run gpu_tests_all python -m pytest tests -q -m gpu -p no:cacheprovider
 TAILN=2 run bench_film python tools/bench_film.py --frames 5 --steps 2 --layers
+# the cluster-multicast variant of streamconv (written blind at the end of r01, default off): parity first, then the A/B
+VFI_SC_CLUSTER=2 TAILN=20 run film_check_cluster2 python tools/film_gpu_check.py --quick
+VFI_SC_CLUSTER=2 TAILN=2 run bench_film_cluster2 python tools/bench_film.py --frames 5 --steps 2 --no-cpu
 TAILN=2 run bench_sepconv python tools/bench_sepconv.py --h 1080 --w 1920 --steps 3
 TAILN=2 run bench python bench.py
 TMO=300 TAILN=1 run film_launches ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_film_launches.csv python tools/bench_film.py --frames 2 --multiplier 2 --pairs 1 --steps 1 --warmup 3 --no-cpu

@@ -1,4 +1,4 @@
-// Thin inline-PTX wrappers for sm_100a: mbarrier, cp.async, cp.async.bulk, tcgen05 (alloc / mma / commit / ld).
+// Thin inline-PTX wrappers for sm_100a: mbarrier, cp.async.bulk / TMA, clusters, tcgen05 (alloc / mma / commit / ld).
 // Everything here is architecture-specific on purpose: this library targets B200 (sm_100a) only.
 #pragma once
 #include <cuda_fp16.h>
@@ -57,15 +57,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
   }
 }
 
-// ---------------------------------------------------------------- cp.async (LDGSTS) and bulk copy (UBLKCP)
-// 16-byte async copy global->shared; src_bytes == 0 writes zeros (conv zero padding / image border).
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-// arrive on `bar` once every cp.async this thread has issued so far has landed (does not add to the pending count)
-__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
+// ---------------------------------------------------------------- bulk copy (UBLKCP) and TMA tensor copies
 // 1-D bulk copy global->shared through the TMA engine, completion counted in bytes on an mbarrier
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -189,21 +181,6 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   return v;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, no-swizzle ("interleaved") shared-memory matrix descriptor:
-//   core matrix = 8 rows x 16 bytes, stored as 128 contiguous bytes;
-//   LBO = byte distance between the two core matrices of one K=16 step (K direction),
-//   SBO = byte distance between consecutive 8-row groups (M/N direction).
-// Bit layout as in CUTLASS cute/arch/mma_sm100_desc.hpp (SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
-// SBO>>4 [32,46), version=1 [46,48), base_offset=0, layout_type=0 (SWIZZLE_NONE) [61,64).
-__device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
 
 #endif  // VFI_HOST_EMU
 

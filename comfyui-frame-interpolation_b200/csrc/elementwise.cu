@@ -991,7 +991,7 @@ inline int grid_for(size_t total, int block) {
 cudaError_t launch_prep_frames(const float* frames, int n, int H, int W, int cstride, float4* imgs, uint2* imgs_h,
                                int Hp, int Wp, cudaStream_t st) {
   const size_t total = (size_t)n * Hp * Wp;
-  prep_frames_kernel<<<grid_for(total, 256), 256, 0, st>>>(frames, n, H, W, cstride, imgs, imgs_h, Hp, Wp);
+  VFI_LAUNCH((prep_frames_kernel), grid_for(total, 256), 256, 0, st, frames, n, H, W, cstride, imgs, imgs_h, Hp, Wp);
   return cudaGetLastError();
 }
 
@@ -1019,10 +1019,10 @@ template <typename T>
 static void launch_front47_t(int nlev, dim3 g, cudaStream_t st, const uint2* imgs, const uint2* feats,
                              const FlowLevels& L, const BatchTasks& tasks, int Hp, int Wp, int s, void* x) {
   switch (nlev) {
-    case 0: front47_kernel<T, 0><<<g, 128, 0, st>>>(imgs, feats, L, tasks, Hp, Wp, s, (T*)x); break;
-    case 1: front47_kernel<T, 1><<<g, 128, 0, st>>>(imgs, feats, L, tasks, Hp, Wp, s, (T*)x); break;
-    case 2: front47_kernel<T, 2><<<g, 128, 0, st>>>(imgs, feats, L, tasks, Hp, Wp, s, (T*)x); break;
-    default: front47_kernel<T, 3><<<g, 128, 0, st>>>(imgs, feats, L, tasks, Hp, Wp, s, (T*)x); break;
+    case 0: VFI_LAUNCH((front47_kernel<T, 0>), g, 128, 0, st, imgs, feats, L, tasks, Hp, Wp, s, (T*)x); break;
+    case 1: VFI_LAUNCH((front47_kernel<T, 1>), g, 128, 0, st, imgs, feats, L, tasks, Hp, Wp, s, (T*)x); break;
+    case 2: VFI_LAUNCH((front47_kernel<T, 2>), g, 128, 0, st, imgs, feats, L, tasks, Hp, Wp, s, (T*)x); break;
+    default: VFI_LAUNCH((front47_kernel<T, 3>), g, 128, 0, st, imgs, feats, L, tasks, Hp, Wp, s, (T*)x); break;
   }
 }
 
@@ -1030,9 +1030,9 @@ template <typename T>
 static void launch_front2_t(int nlev, int g, cudaStream_t st, const float4* imgs, const FlowLevels& L,
                             const BatchTasks& tasks, int Hp, int Wp, void* x) {
   switch (nlev) {
-    case 1: front2_kernel<T, 1><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, (T*)x); break;
-    case 2: front2_kernel<T, 2><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, (T*)x); break;
-    default: front2_kernel<T, 3><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, (T*)x); break;
+    case 1: VFI_LAUNCH((front2_kernel<T, 1>), g, 128, 0, st, imgs, L, tasks, Hp, Wp, (T*)x); break;
+    case 2: VFI_LAUNCH((front2_kernel<T, 2>), g, 128, 0, st, imgs, L, tasks, Hp, Wp, (T*)x); break;
+    default: VFI_LAUNCH((front2_kernel<T, 3>), g, 128, 0, st, imgs, L, tasks, Hp, Wp, (T*)x); break;
   }
 }
 
@@ -1040,10 +1040,10 @@ template <typename T, int S>
 static void launch_front_ts(int nlev, dim3 g, cudaStream_t st, const uint2* imgs, const FlowLevels& L,
                             const BatchTasks& tasks, int Hp, int Wp, int s, void* x) {
   switch (nlev) {
-    case 0: front_kernel<T, 0, S><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, s, (T*)x); break;
-    case 1: front_kernel<T, 1, S><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, s, (T*)x); break;
-    case 2: front_kernel<T, 2, S><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, s, (T*)x); break;
-    default: front_kernel<T, 3, S><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, s, (T*)x); break;
+    case 0: VFI_LAUNCH((front_kernel<T, 0, S>), g, 128, 0, st, imgs, L, tasks, Hp, Wp, s, (T*)x); break;
+    case 1: VFI_LAUNCH((front_kernel<T, 1, S>), g, 128, 0, st, imgs, L, tasks, Hp, Wp, s, (T*)x); break;
+    case 2: VFI_LAUNCH((front_kernel<T, 2, S>), g, 128, 0, st, imgs, L, tasks, Hp, Wp, s, (T*)x); break;
+    default: VFI_LAUNCH((front_kernel<T, 3, S>), g, 128, 0, st, imgs, L, tasks, Hp, Wp, s, (T*)x); break;
   }
 }
 
@@ -1052,9 +1052,9 @@ static void launch_front_t(int nlev, bool shared_taps, dim3 g, cudaStream_t st, 
                            const BatchTasks& tasks, int Hp, int Wp, int s, void* x) {
   if (shared_taps) {
     switch (nlev) {
-      case 1: front2_kernel<T, 1><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, (T*)x); break;
-      case 2: front2_kernel<T, 2><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, (T*)x); break;
-      default: front2_kernel<T, 3><<<g, 128, 0, st>>>(imgs, L, tasks, Hp, Wp, (T*)x); break;
+      case 1: VFI_LAUNCH((front2_kernel<T, 1>), g, 128, 0, st, imgs, L, tasks, Hp, Wp, (T*)x); break;
+      case 2: VFI_LAUNCH((front2_kernel<T, 2>), g, 128, 0, st, imgs, L, tasks, Hp, Wp, (T*)x); break;
+      default: VFI_LAUNCH((front2_kernel<T, 3>), g, 128, 0, st, imgs, L, tasks, Hp, Wp, (T*)x); break;
     }
   } else if (s == 1) {
     launch_front_ts<T, 1>(nlev, g, st, imgs, L, tasks, Hp, Wp, s, x);  // compile-time scale: 56 instead of 93 registers
@@ -1067,10 +1067,10 @@ template <typename T>
 static void launch_front417_t(int nlev, dim3 g, cudaStream_t st, const uint2* imgs, const uint4* feats,
                               const FlowLevels& L, const BatchTasks& tasks, int Hp, int Wp, int s, void* x) {
   switch (nlev) {
-    case 0: front417_kernel<T, 0><<<g, 128, 0, st>>>(imgs, feats, L, tasks, Hp, Wp, s, (T*)x); break;
-    case 1: front417_kernel<T, 1><<<g, 128, 0, st>>>(imgs, feats, L, tasks, Hp, Wp, s, (T*)x); break;
-    case 2: front417_kernel<T, 2><<<g, 128, 0, st>>>(imgs, feats, L, tasks, Hp, Wp, s, (T*)x); break;
-    default: front417_kernel<T, 3><<<g, 128, 0, st>>>(imgs, feats, L, tasks, Hp, Wp, s, (T*)x); break;
+    case 0: VFI_LAUNCH((front417_kernel<T, 0>), g, 128, 0, st, imgs, feats, L, tasks, Hp, Wp, s, (T*)x); break;
+    case 1: VFI_LAUNCH((front417_kernel<T, 1>), g, 128, 0, st, imgs, feats, L, tasks, Hp, Wp, s, (T*)x); break;
+    case 2: VFI_LAUNCH((front417_kernel<T, 2>), g, 128, 0, st, imgs, feats, L, tasks, Hp, Wp, s, (T*)x); break;
+    default: VFI_LAUNCH((front417_kernel<T, 3>), g, 128, 0, st, imgs, feats, L, tasks, Hp, Wp, s, (T*)x); break;
   }
 }
 
@@ -1079,11 +1079,11 @@ static void launch_front426_t(int nlev, dim3 g, cudaStream_t st, const uint2* im
                               const uint4* prev_feat, int prev_s, const FlowLevels& L, const BatchTasks& tasks, int Hp,
                               int Wp, int s, void* x) {
   switch (nlev) {
-    case 0: front426_kernel<T, 0><<<g, 128, 0, st>>>(imgs, feats, prev_feat, prev_s, L, tasks, Hp, Wp, s, (T*)x); break;
-    case 1: front426_kernel<T, 1><<<g, 128, 0, st>>>(imgs, feats, prev_feat, prev_s, L, tasks, Hp, Wp, s, (T*)x); break;
-    case 2: front426_kernel<T, 2><<<g, 128, 0, st>>>(imgs, feats, prev_feat, prev_s, L, tasks, Hp, Wp, s, (T*)x); break;
-    case 3: front426_kernel<T, 3><<<g, 128, 0, st>>>(imgs, feats, prev_feat, prev_s, L, tasks, Hp, Wp, s, (T*)x); break;
-    default: front426_kernel<T, 4><<<g, 128, 0, st>>>(imgs, feats, prev_feat, prev_s, L, tasks, Hp, Wp, s, (T*)x); break;
+    case 0: VFI_LAUNCH((front426_kernel<T, 0>), g, 128, 0, st, imgs, feats, prev_feat, prev_s, L, tasks, Hp, Wp, s, (T*)x); break;
+    case 1: VFI_LAUNCH((front426_kernel<T, 1>), g, 128, 0, st, imgs, feats, prev_feat, prev_s, L, tasks, Hp, Wp, s, (T*)x); break;
+    case 2: VFI_LAUNCH((front426_kernel<T, 2>), g, 128, 0, st, imgs, feats, prev_feat, prev_s, L, tasks, Hp, Wp, s, (T*)x); break;
+    case 3: VFI_LAUNCH((front426_kernel<T, 3>), g, 128, 0, st, imgs, feats, prev_feat, prev_s, L, tasks, Hp, Wp, s, (T*)x); break;
+    default: VFI_LAUNCH((front426_kernel<T, 4>), g, 128, 0, st, imgs, feats, prev_feat, prev_s, L, tasks, Hp, Wp, s, (T*)x); break;
   }
 }
 
@@ -1091,9 +1091,9 @@ cudaError_t launch_head0(int op_type, const float4* imgs, const float* w, const 
                          int Wp, cudaStream_t st) {
   const dim3 g((unsigned)((Wp / 2 + 127) / 128), (unsigned)(Hp / 2), (unsigned)n);
   if (op_type == OP_BF16)
-    head0_kernel<__nv_bfloat16><<<g, 128, 0, st>>>(imgs, w, bias, (__nv_bfloat16*)out, n, Hp, Wp);
+    VFI_LAUNCH((head0_kernel<__nv_bfloat16>), g, 128, 0, st, imgs, w, bias, (__nv_bfloat16*)out, n, Hp, Wp);
   else
-    head0_kernel<__half><<<g, 128, 0, st>>>(imgs, w, bias, (__half*)out, n, Hp, Wp);
+    VFI_LAUNCH((head0_kernel<__half>), g, 128, 0, st, imgs, w, bias, (__half*)out, n, Hp, Wp);
   return cudaGetLastError();
 }
 
@@ -1101,10 +1101,10 @@ cudaError_t launch_head0(int op_type, const float4* imgs, const float* w, const 
 cudaError_t launch_encode(const float4* imgs, const float* w0, const float* b0, const float* w1, const float* b1,
                           float* e16, uint2* feats, int n, int Hp, int Wp, cudaStream_t st) {
   const size_t t0 = (size_t)n * (Hp / 2) * (Wp / 2), t1 = (size_t)n * Hp * Wp;
-  encode_conv_kernel<<<grid_for(t0, 128), 128, 0, st>>>(imgs, w0, b0, e16, n, Hp, Wp);
+  VFI_LAUNCH((encode_conv_kernel), grid_for(t0, 128), 128, 0, st, imgs, w0, b0, e16, n, Hp, Wp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  encode_deconv_kernel<<<grid_for(t1, 256), 256, 0, st>>>(e16, w1, b1, feats, n, Hp, Wp);
+  VFI_LAUNCH((encode_deconv_kernel), grid_for(t1, 256), 256, 0, st, e16, w1, b1, feats, n, Hp, Wp);
   return cudaGetLastError();
 }
 
@@ -1157,11 +1157,11 @@ cudaError_t launch_materialize(const FlowState& fs, int lo, const float4* base_f
   FlowLevels L = make_levels(fs, lo, fs.n, base_f, base_m, nullptr, nullptr, Hp, Wp);
   const int nlev = fs.n - lo;
   switch (nlev) {
-    case 1: materialize_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(L, flow, mask, B, Hp, Wp); break;
-    case 2: materialize_kernel<2><<<grid_for(total, 256), 256, 0, st>>>(L, flow, mask, B, Hp, Wp); break;
-    case 3: materialize_kernel<3><<<grid_for(total, 256), 256, 0, st>>>(L, flow, mask, B, Hp, Wp); break;
-    case 4: materialize_kernel<4><<<grid_for(total, 256), 256, 0, st>>>(L, flow, mask, B, Hp, Wp); break;
-    default: materialize_kernel<5><<<grid_for(total, 256), 256, 0, st>>>(L, flow, mask, B, Hp, Wp); break;
+    case 1: VFI_LAUNCH((materialize_kernel<1>), grid_for(total, 256), 256, 0, st, L, flow, mask, B, Hp, Wp); break;
+    case 2: VFI_LAUNCH((materialize_kernel<2>), grid_for(total, 256), 256, 0, st, L, flow, mask, B, Hp, Wp); break;
+    case 3: VFI_LAUNCH((materialize_kernel<3>), grid_for(total, 256), 256, 0, st, L, flow, mask, B, Hp, Wp); break;
+    case 4: VFI_LAUNCH((materialize_kernel<4>), grid_for(total, 256), 256, 0, st, L, flow, mask, B, Hp, Wp); break;
+    default: VFI_LAUNCH((materialize_kernel<5>), grid_for(total, 256), 256, 0, st, L, flow, mask, B, Hp, Wp); break;
   }
   return cudaGetLastError();
 }
@@ -1171,11 +1171,11 @@ cudaError_t launch_final(const float4* imgs, const FlowState& fs, int lo, const 
   const FlowLevels L = make_levels(fs, lo, fs.n, base_f, base_m, nullptr, nullptr, Hp, Wp);
   const dim3 g((unsigned)((W + 255) / 256), (unsigned)H, (unsigned)tasks.n);
   switch (fs.n - lo) {
-    case 1: final_kernel<1><<<g, 256, 0, st>>>(imgs, L, tasks, Hp, Wp, H, W, out); break;
-    case 2: final_kernel<2><<<g, 256, 0, st>>>(imgs, L, tasks, Hp, Wp, H, W, out); break;
-    case 3: final_kernel<3><<<g, 256, 0, st>>>(imgs, L, tasks, Hp, Wp, H, W, out); break;
-    case 4: final_kernel<4><<<g, 256, 0, st>>>(imgs, L, tasks, Hp, Wp, H, W, out); break;
-    default: final_kernel<5><<<g, 256, 0, st>>>(imgs, L, tasks, Hp, Wp, H, W, out); break;
+    case 1: VFI_LAUNCH((final_kernel<1>), g, 256, 0, st, imgs, L, tasks, Hp, Wp, H, W, out); break;
+    case 2: VFI_LAUNCH((final_kernel<2>), g, 256, 0, st, imgs, L, tasks, Hp, Wp, H, W, out); break;
+    case 3: VFI_LAUNCH((final_kernel<3>), g, 256, 0, st, imgs, L, tasks, Hp, Wp, H, W, out); break;
+    case 4: VFI_LAUNCH((final_kernel<4>), g, 256, 0, st, imgs, L, tasks, Hp, Wp, H, W, out); break;
+    default: VFI_LAUNCH((final_kernel<5>), g, 256, 0, st, imgs, L, tasks, Hp, Wp, H, W, out); break;
   }
   return cudaGetLastError();
 }
@@ -1183,10 +1183,10 @@ cudaError_t launch_final(const float4* imgs, const FlowState& fs, int lo, const 
 cudaError_t launch_warp(const float* img, const float* flow, float* out, int B, int H, int W, int C, cudaStream_t st) {
   if (C % 4 == 0) {
     const size_t total = (size_t)B * H * W * (C / 4);
-    warp_kernel<4><<<grid_for(total, 256), 256, 0, st>>>(img, flow, out, B, H, W, C);
+    VFI_LAUNCH((warp_kernel<4>), grid_for(total, 256), 256, 0, st, img, flow, out, B, H, W, C);
   } else {
     const size_t total = (size_t)B * H * W * C;
-    warp_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(img, flow, out, B, H, W, C);
+    VFI_LAUNCH((warp_kernel<1>), grid_for(total, 256), 256, 0, st, img, flow, out, B, H, W, C);
   }
   return cudaGetLastError();
 }

@@ -65,6 +65,7 @@ __device__ __forceinline__ size_t out_pixel_offset(const TapConvParams& p, int b
   return (((size_t)b * p.H + gy) * p.W + gx) * (size_t)p.n_total;
 }
 
+#ifndef VFI_HOST_EMU  // (tests/host_emu runs the RIFE schedule on the CPU with the checker kernel; no tcgen05 there)
 // Walks the tiles of one CTA (t = first, first + cps, ...) keeping (image, tile row, tile column) incrementally
 // instead of two integer divisions per tile and role.
 struct TileIter {
@@ -580,6 +581,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
   }
 }
 
+#endif  // VFI_HOST_EMU
+
 // ---------------------------------------------------------------------------------------------
 // CUDA-core checker with the SAME parameters, packed weights and epilogue: one thread per (cell, n).
 // Test infrastructure for the tensor-core kernel (debug entry point only; never on the product path).
@@ -650,6 +653,7 @@ __global__ void tapconv_ref_kernel(const __grid_constant__ TapConvParams p) {
   }
 }
 
+#ifndef VFI_HOST_EMU
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -679,6 +683,8 @@ bool make_tmap(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, int C,
   }
   return true;
 }
+
+#endif  // VFI_HOST_EMU
 
 uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
@@ -854,15 +860,21 @@ cudaError_t launch_tapconv(const TapConvLayer& L, int op_type, const void* in, v
   const uint32_t fmt = (op_type == OP_BF16) ? 1u : 0u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(L.n_cta >> 3) << 17) | ((128u >> 4) << 24);
 
+#ifdef VFI_HOST_EMU
+  use_ref = true;  // the host emulation has only the checker kernel
+#endif
   if (use_ref) {
     const size_t total = (size_t)B * H * W * L.n_total;
     const int blocks = (int)((total + 255) / 256 < 65535 ? (total + 255) / 256 : 65535);
     if (op_type == OP_BF16)
-      tapconv_ref_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(p);
+      VFI_LAUNCH(tapconv_ref_kernel<__nv_bfloat16>, blocks, 256, 0, st, p);
     else
-      tapconv_ref_kernel<__half><<<blocks, 256, 0, st>>>(p);
+      VFI_LAUNCH(tapconv_ref_kernel<__half>, blocks, 256, 0, st, p);
     return cudaGetLastError();
   }
+#ifdef VFI_HOST_EMU
+  return cudaErrorInvalidConfiguration;
+#else
 
   const CUtensorMapDataType dt = (op_type == OP_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   if (L.cin >= 64 && !make_tmap(&p.tm64, dt, in, L.cin, W, H, B, 64, L.halo_w, L.halo_h, CU_TENSOR_MAP_SWIZZLE_128B))
@@ -916,6 +928,7 @@ cudaError_t launch_tapconv(const TapConvLayer& L, int op_type, const void* in, v
   }
   if (err != cudaSuccess) return err;
   return cudaGetLastError();
+#endif  // VFI_HOST_EMU
 }
 
 }  // namespace vfi

@@ -38,11 +38,13 @@ static void trampoline() {
 }
 // runs `kernel()` for every thread of one block (threadIdx.x = 0..nthreads-1), phase by phase
 static void run_block(int nthreads, std::function<void()> kernel) {
-  std::vector<Fiber> fs(nthreads);
+  static std::vector<Fiber> fs;   // fiber stacks are allocated once and reused by every block of every launch
+  if ((int)fs.size() < nthreads) fs.resize(nthreads);
   fibers = &fs;
   body = &kernel;
   for (int t = 0; t < nthreads; ++t) {
-    fs[t].stack.resize(256 * 1024);
+    if (fs[t].stack.empty()) fs[t].stack.resize(128 * 1024);
+    fs[t].done = false;
     getcontext(&fs[t].ctx);
     fs[t].ctx.uc_stack.ss_sp = fs[t].stack.data();
     fs[t].ctx.uc_stack.ss_size = fs[t].stack.size();

@@ -1,0 +1,81 @@
+// Host emulation with the FULL launch geometry (TEST INFRASTRUCTURE): every block of a launch runs through
+// block_emu::run_block (one fiber per thread, __syncthreads() = yield), blocks in turn.  For kernels that index with
+// blockIdx.{x,y,z} / threadIdx.x directly instead of a grid-stride loop (csrc/elementwise.cu) and for the few with
+// cooperative shared-memory loads.  Plus the CUDA runtime calls csrc/rife46.cu makes, as host stubs (one "device",
+// synchronous "streams").
+#pragma once
+#define VFI_HOST_EMU 1
+#include <algorithm>
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#undef __global__
+#undef __device__
+#undef __host__
+#undef __forceinline__
+#undef __shared__
+#undef __restrict__
+#include "block_emu.h"
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __grid_constant__
+#define __launch_bounds__(...)
+using std::max;
+using std::min;
+template <typename T>
+static inline T __ldg(const T* p) { return *p; }
+
+#define VFI_LAUNCH(kernel, grid, block, smem, stream, ...)                                   \
+  do {                                                                                        \
+    const dim3 _g(grid), _b(block);                                                           \
+    gridDim.x = _g.x; gridDim.y = _g.y; gridDim.z = _g.z;                                     \
+    blockDim.x = _b.x; blockDim.y = 1; blockDim.z = 1;                                        \
+    for (unsigned _z = 0; _z < _g.z; ++_z)                                                    \
+      for (unsigned _y = 0; _y < _g.y; ++_y)                                                  \
+        for (unsigned _x = 0; _x < _g.x; ++_x) {                                              \
+          blockIdx.x = _x; blockIdx.y = _y; blockIdx.z = _z;                                  \
+          block_emu::run_block((int)_b.x, [&]() { kernel(__VA_ARGS__); });                    \
+        }                                                                                     \
+  } while (0)
+
+static inline cudaError_t emu_malloc(void** p, size_t n) {
+  const size_t bytes = ((n ? n : 1) + 255) / 256 * 256;
+  *p = std::aligned_alloc(256, bytes);
+  if (*p) std::memset(*p, 0, bytes);
+  return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+static inline cudaError_t emu_props(cudaDeviceProp* p, int) {
+  std::memset(p, 0, sizeof(*p));
+  p->major = 10;
+  p->multiProcessorCount = 148;
+  return cudaSuccess;
+}
+static inline cudaError_t emu_memcpy(void* d, const void* s, size_t n) {
+  std::memcpy(d, s, n);
+  return cudaSuccess;
+}
+#define cudaMalloc(p, n) emu_malloc((void**)(p), (n))
+#define cudaFree(p) (std::free(p), cudaSuccess)
+#define cudaMemcpy(d, s, n, k) emu_memcpy((d), (s), (n))
+#define cudaMemcpyAsync(d, s, n, k, st) emu_memcpy((d), (s), (n))
+#define cudaMemsetAsync(d, v, n, st) (std::memset((d), (v), (n)), cudaSuccess)
+#define cudaSetDevice(d) cudaSuccess
+#define cudaGetLastError() cudaSuccess
+#define cudaGetErrorString(e) "emulated CUDA error"
+#define cudaGetDeviceCount(p) (*(p) = 1, cudaSuccess)
+#define cudaGetDeviceProperties(p, d) emu_props((p), (d))
+#define cudaDeviceSynchronize() cudaSuccess
+#define cudaStreamSynchronize(s) cudaSuccess
+#define cudaStreamCreateWithFlags(p, f) (*(p) = nullptr, cudaSuccess)
+#define cudaStreamDestroy(s) cudaSuccess
+#define cudaStreamWaitEvent(s, e, f) cudaSuccess
+#define cudaEventCreateWithFlags(p, f) (*(p) = nullptr, cudaSuccess)
+#define cudaEventRecord(e, s) cudaSuccess
+#define cudaEventDestroy(e) cudaSuccess

@@ -1,0 +1,128 @@
+"""The WHOLE RIFE path of the library on the CPU: csrc/rife46.cu (vfi_create / vfi_rife_load / vfi_rife46_forward: weight
+repacking, the per-block schedule with its implicit full-resolution flow, the C ABI), csrc/elementwise.cu (prep / front /
+final kernels with their 3-D launch geometry) and csrc/tapconv.cu's plan + CUDA-core checker kernel, compiled for the host
+(tests/host_emu/cuda_shim_block.h: every thread of every block a fiber) and compared with the unmodified reference IFNet's
+output (tests/golden).  The tcgen05 kernel is covered by the GPU tests (tests/test_gpu_layers.py: tcgen05 vs this checker)."""
+import ctypes as C
+import math
+import os
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from make_golden import cases, make_inputs  # noqa: E402
+from oracle import rife46 as O  # noqa: E402
+
+CUDA_INC = "/usr/local/cuda/include"
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    if not (shutil.which("g++") and os.path.exists(os.path.join(CUDA_INC, "cuda_fp16.h"))):
+        pytest.skip("g++ / CUDA headers not available")
+    so = str(tmp_path_factory.mktemp("emu") / "librifefull.so")
+    src = os.path.join(ROOT, "tests", "host_emu", "rife_full_emu.cpp")
+    r = subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I" + CUDA_INC, "-o", so, src],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    L = C.CDLL(so)
+    L.vfi_last_error.restype = C.c_char_p
+    return L
+
+
+def _engine_names(arch):
+    import __graft_entry__ as ge
+    ge.load_package()
+    from cfi_b200.engine import ARCH_CODE, state_dict_names
+    return state_dict_names(arch), ARCH_CODE[arch]
+
+
+@pytest.mark.parametrize("name", ["ifnet_64x64_gain4", "ifnet47_64x128_gain3", "ifnet417_64x128_gain3",
+                                  "ifnet426_128x128_gain3"])
+def test_rife_whole_path_on_host_matches_reference(emu, name):
+    cfg = cases()[name]
+    arch = cfg.get("arch", "4.6")
+    ref = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))["out"]).permute(0, 2, 3, 1)
+    sd = O.synthetic_state_dict(cfg["seed"], cfg["gain"], arch=arch)
+    names, code = _engine_names(arch)
+    hold = [sd[n].contiguous().float() for n in names]
+    ptrs = (C.c_void_p * len(hold))(*[t.data_ptr() for t in hold])
+    numel = (C.c_int64 * len(hold))(*[t.numel() for t in hold])
+    ctx = C.c_void_p()
+    assert emu.vfi_create(0, C.byref(ctx)) == 0, emu.vfi_last_error()
+    assert emu.vfi_rife_load(ctx, code, ptrs, numel, len(hold), 0) == 0, emu.vfi_last_error()
+    fr = make_inputs(cfg).contiguous()
+    n, h, w, c = fr.shape
+    ts = np.asarray(cfg["ts"], dtype=np.float32)
+    f0 = np.zeros(len(ts), dtype=np.int32)
+    f1 = np.ones(len(ts), dtype=np.int32)
+    out = torch.zeros(len(ts), h, w, 3)
+    rc = emu.vfi_rife46_forward(ctx, C.c_void_p(fr.data_ptr()), n, h, w, c, f0.ctypes.data_as(C.c_void_p),
+                                f1.ctypes.data_as(C.c_void_p), ts.ctypes.data_as(C.c_void_p), len(ts), C.c_float(1.0),
+                                C.c_void_p(out.data_ptr()), None)
+    assert rc == 0, emu.vfi_last_error()
+    emu.vfi_launch_count.restype = C.c_int64
+    launches = emu.vfi_launch_count(ctx)
+    assert emu.vfi_destroy(ctx) == 0
+    want = ref.clamp(0, 1)   # the library returns the node's clamped frame (rife/__init__.py:207)
+    mse = float(((out.double() - want.double()) ** 2).mean())
+    psnr = 99.0 if mse == 0 else 10 * math.log10(1.0 / mse)
+    print(f"host emulation of the whole RIFE {arch} path ({name}): {launches} launches, PSNR {psnr:.2f} dB")
+    assert psnr >= 60.0, psnr
+
+
+def test_rife_host_pipeline_on_host_matches_reference_node(emu):
+    """vfi_rife46_interpolate_host (the H2D / compute / D2H pipeline with its ring of raw frames and output slots) against
+    the unmodified reference node's output: multiplier 3, a skipped pair, 4-channel frames (tests/golden/node_m3_skip.npz)."""
+    import __graft_entry__ as ge
+    ge.load_package()
+    import cfi_b200.node as N
+    name = "node_m3_skip"
+    cfg = cases()[name]
+    ref = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))["out"])
+    sd = O.synthetic_state_dict(cfg["seed"], cfg["gain"])
+    names, code = _engine_names("4.6")
+    hold = [sd[n].contiguous().float() for n in names]
+    ptrs = (C.c_void_p * len(hold))(*[t.data_ptr() for t in hold])
+    numel = (C.c_int64 * len(hold))(*[t.numel() for t in hold])
+    ctx = C.c_void_p()
+    assert emu.vfi_create(0, C.byref(ctx)) == 0, emu.vfi_last_error()
+    assert emu.vfi_rife_load(ctx, code, ptrs, numel, len(hold), 0) == 0, emu.vfi_last_error()
+    fr = make_inputs(cfg).contiguous()
+    n, h, w, c = fr.shape
+    st = N.InterpolationStateList(list(cfg["states"][0]), cfg["states"][1])
+    tasks, _ = N.build_tasks(n - 1, cfg["multiplier"], st)
+    # output slots exactly as node.RIFE_VFI.vfi lays them out
+    per_pair = [0] * (n - 1)
+    for p_, _t in tasks:
+        per_pair[p_] += 1
+    first_slot, slot = [], 0
+    for p_ in range(n - 1):
+        first_slot.append(slot)
+        slot += 1 + per_pair[p_]
+    total = slot + 1
+    out = torch.zeros(total, h, w, 3)
+    seen = [0] * (n - 1)
+    f0, f1, ts, slots = [], [], [], []
+    for p_, t in tasks:
+        seen[p_] += 1
+        f0.append(p_); f1.append(p_ + 1); ts.append(t); slots.append(first_slot[p_] + seen[p_])
+    a = lambda v, dt: np.ascontiguousarray(np.asarray(v, dtype=dt))   # noqa: E731
+    f0a, f1a, tsa, sla = a(f0, np.int32), a(f1, np.int32), a(ts, np.float32), a(slots, np.int32)
+    vp = lambda x: x.ctypes.data_as(C.c_void_p)   # noqa: E731
+    rc = emu.vfi_rife46_interpolate_host(ctx, C.c_void_p(fr.data_ptr()), n, h, w, c, 0, n, vp(f0a), vp(f1a), vp(tsa), vp(sla),
+                                         len(ts), C.c_float(1.0), C.c_void_p(out.data_ptr()))
+    assert rc == 0, emu.vfi_last_error()
+    assert emu.vfi_destroy(ctx) == 0
+    out[first_slot + [total - 1]] = fr[..., :3]          # the node copies the pass-through frames itself
+    assert out.shape == ref.shape
+    mse = float(((out.double() - ref.double()) ** 2).mean())
+    psnr = 99.0 if mse == 0 else 10 * math.log10(1.0 / mse)
+    print(f"host emulation of the RIFE host pipeline ({name}): PSNR {psnr:.2f} dB")
+    assert psnr >= 60.0, psnr

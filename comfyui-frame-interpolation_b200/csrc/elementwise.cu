@@ -898,6 +898,91 @@ __global__ void front426_kernel(const uint2* __restrict__ imgs, const uint2* __r
 }
 
 // debug / tests only: materialise the accumulated full-resolution flow and mask
+
+// ---- up-scaled blocks (node scale_factor 2 / 4: block scale 1/k, k = 2 or 4) - arch 4.6 ------------------------------
+// The reference interpolates the full-resolution block input UP by k before conv0 (rife_arch.py:238-249 with
+// scale < 1): x = interpolate(cat(warped img0, warped img1, t, mask), k), flow = interpolate(flow, k) * k, bilinear,
+// align_corners=False.  One thread = one cell of the k-times finer grid: source position (cell + 0.5) / k - 0.5 clamped at
+// 0, the four surrounding full-resolution pixels each evaluated like front_kernel does (dense flow / mask planes F, M -
+// every earlier level has been folded into them - and the two border-clamped warps), then mixed.  Same 16-channel
+// space-to-depth store as front_kernel.
+template <typename T>
+__global__ void front_up_kernel(const uint2* __restrict__ imgs, const float4* __restrict__ F, const float* __restrict__ M,
+                                const BatchTasks tasks, int Hp, int Wp, int k, T* __restrict__ x_s2d) {
+  const int Hs = Hp * k, Ws = Wp * k;
+  const size_t plane = (size_t)Hp * Wp;
+  const float inv_k = 1.f / (float)k;
+  const int par = (int)(threadIdx.x & 1);
+  const int xl = (int)(blockIdx.x * (blockDim.x >> 1) + (threadIdx.x >> 1));
+  if (xl >= Ws) return;
+  const int yl = (int)blockIdx.y * 2 + par;
+  const int b = (int)blockIdx.z;
+  const uint2* img0 = imgs + (size_t)tasks.f0[b] * plane;
+  const uint2* img1 = imgs + (size_t)tasks.f1[b] * plane;
+  const float t = tasks.t[b];
+  const float sy = fmaxf(((float)yl + 0.5f) * inv_k - 0.5f, 0.f), sx = fmaxf(((float)xl + 0.5f) * inv_k - 0.5f, 0.f);
+  const int y0 = min((int)sy, Hp - 1), x0 = min((int)sx, Wp - 1);
+  const int y1 = min(y0 + 1, Hp - 1), x1 = min(x0 + 1, Wp - 1);
+  const float ly = sy - (float)y0, lx = sx - (float)x0;
+  const float wq[4] = {(1.f - ly) * (1.f - lx), (1.f - ly) * lx, ly * (1.f - lx), ly * lx};
+  const int qy[4] = {y0, y0, y1, y1}, qx[4] = {x0, x1, x0, x1};
+  float ch[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) ch[i] = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int Y = qy[q], X = qx[q];
+    const size_t pid = ((size_t)b * Hp + Y) * Wp + X;
+    const float4 f = F[pid];
+    const float m = M[pid];
+    const float4 a = sample_border(img0, Hp, Wp, (float)X + f.x, (float)Y + f.y);
+    const float4 c = sample_border(img1, Hp, Wp, (float)X + f.z, (float)Y + f.w);
+    const float v[12] = {a.x, a.y, a.z, c.x, c.y, c.z, t, m, f.x, f.y, f.z, f.w};
+#pragma unroll
+    for (int i = 0; i < 12; ++i) ch[i] = fmaf(v[i], wq[q], ch[i]);
+  }
+#pragma unroll
+  for (int i = 8; i < 12; ++i) ch[i] *= (float)k;  // flow * (1 / scale), rife_arch.py:245-248
+  const size_t cell = ((size_t)b * (Hs >> 1) + (yl >> 1)) * (Ws >> 1) + (xl >> 1);
+  T* dst = x_s2d + cell * 64 + ((yl & 1) * 2 + (xl & 1)) * 16;
+  uint4 lo, hi;
+  lo.x = Pack2<T>::pack(ch[0], ch[1]);
+  lo.y = Pack2<T>::pack(ch[2], ch[3]);
+  lo.z = Pack2<T>::pack(ch[4], ch[5]);
+  lo.w = Pack2<T>::pack(ch[6], ch[7]);
+  hi.x = Pack2<T>::pack(ch[8], ch[9]);
+  hi.y = Pack2<T>::pack(ch[10], ch[11]);
+  hi.z = 0u;
+  hi.w = 0u;
+  reinterpret_cast<uint4*>(dst)[0] = lo;
+  reinterpret_cast<uint4*>(dst)[1] = hi;
+}
+
+// The block's output T (flow increments float4 + mask, k times finer than full resolution) back onto the dense planes:
+// interpolate(T, scale_factor = 1 / k) takes the two central taps k p + k/2 - 1, k p + k/2 per axis with weight 1/2 (for
+// k = 2 the 2x2 mean), flow is multiplied by the scale 1 / k (rife_arch.py:263-266) and added; the mask is added (arch 4.6).
+__global__ void fold_down_kernel(const float4* __restrict__ tf, const float* __restrict__ tm, int k, float4* __restrict__ F,
+                                 float* __restrict__ M, int B, int Hp, int Wp) {
+  const size_t total = (size_t)B * Hp * Wp;
+  const int Ws = Wp * k;
+  const float inv_k = 1.f / (float)k;
+  for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
+    const int X = (int)(id % Wp);
+    const int Y = (int)((id / Wp) % Hp);
+    const int b = (int)(id / ((size_t)Wp * Hp));
+    const size_t base = ((size_t)b * Hp * k + (size_t)(k * Y + k / 2 - 1)) * Ws + (size_t)(k * X + k / 2 - 1);
+    const float4 a = tf[base], c = tf[base + 1], d = tf[base + Ws], e = tf[base + Ws + 1];
+    const float ma = tm[base], mc = tm[base + 1], md = tm[base + Ws], me = tm[base + Ws + 1];
+    float4 f = F[id];
+    f.x += (0.5f * (0.5f * a.x + 0.5f * c.x) + 0.5f * (0.5f * d.x + 0.5f * e.x)) * inv_k;
+    f.y += (0.5f * (0.5f * a.y + 0.5f * c.y) + 0.5f * (0.5f * d.y + 0.5f * e.y)) * inv_k;
+    f.z += (0.5f * (0.5f * a.z + 0.5f * c.z) + 0.5f * (0.5f * d.z + 0.5f * e.z)) * inv_k;
+    f.w += (0.5f * (0.5f * a.w + 0.5f * c.w) + 0.5f * (0.5f * d.w + 0.5f * e.w)) * inv_k;
+    F[id] = f;
+    M[id] += 0.5f * (0.5f * ma + 0.5f * mc) + 0.5f * (0.5f * md + 0.5f * me);
+  }
+}
+
 template <int NLEV>
 __global__ void materialize_kernel(const FlowLevels lev, float4* __restrict__ flow, float* __restrict__ mask, int B,
                                    int Hp, int Wp) {
@@ -1171,12 +1256,34 @@ cudaError_t launch_final(const float4* imgs, const FlowState& fs, int lo, const 
   const FlowLevels L = make_levels(fs, lo, fs.n, base_f, base_m, nullptr, nullptr, Hp, Wp);
   const dim3 g((unsigned)((W + 255) / 256), (unsigned)H, (unsigned)tasks.n);
   switch (fs.n - lo) {
+    case 0:  // every level already folded into the dense planes (up-scaled last blocks)
+      if (base_f == nullptr) return cudaErrorInvalidValue;
+      VFI_LAUNCH((final_kernel<0>), g, 256, 0, st, imgs, L, tasks, Hp, Wp, H, W, out);
+      break;
     case 1: VFI_LAUNCH((final_kernel<1>), g, 256, 0, st, imgs, L, tasks, Hp, Wp, H, W, out); break;
     case 2: VFI_LAUNCH((final_kernel<2>), g, 256, 0, st, imgs, L, tasks, Hp, Wp, H, W, out); break;
     case 3: VFI_LAUNCH((final_kernel<3>), g, 256, 0, st, imgs, L, tasks, Hp, Wp, H, W, out); break;
     case 4: VFI_LAUNCH((final_kernel<4>), g, 256, 0, st, imgs, L, tasks, Hp, Wp, H, W, out); break;
     default: VFI_LAUNCH((final_kernel<5>), g, 256, 0, st, imgs, L, tasks, Hp, Wp, H, W, out); break;
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_front_up(int op_type, const uint2* imgs_h, const float4* F, const float* M, BatchTasks tasks, int Hp, int Wp,
+                            int k, void* x_s2d, cudaStream_t st) {
+  if ((k != 2 && k != 4) || F == nullptr || M == nullptr) return cudaErrorInvalidValue;
+  const dim3 g((unsigned)((Wp * k + 63) / 64), (unsigned)(Hp * k / 2), (unsigned)tasks.n);
+  if (op_type == OP_BF16)
+    VFI_LAUNCH((front_up_kernel<__nv_bfloat16>), g, 128, 0, st, imgs_h, F, M, tasks, Hp, Wp, k, (__nv_bfloat16*)x_s2d);
+  else
+    VFI_LAUNCH((front_up_kernel<__half>), g, 128, 0, st, imgs_h, F, M, tasks, Hp, Wp, k, (__half*)x_s2d);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fold_down(const float4* tf, const float* tm, int k, float4* F, float* M, int B, int Hp, int Wp,
+                             cudaStream_t st) {
+  if (k != 2 && k != 4) return cudaErrorInvalidValue;
+  VFI_LAUNCH((fold_down_kernel), grid_for((size_t)B * Hp * Wp, 256), 256, 0, st, tf, tm, k, F, M, B, Hp, Wp);
   return cudaGetLastError();
 }
 

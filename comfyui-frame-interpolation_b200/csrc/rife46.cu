@@ -412,7 +412,8 @@ int build_deconv_s2d(vfi_ctx* c, TapConvLayer& L, int ch, int creal, int cout, c
 struct Geometry {
   int Hp, Wp;
   int nb;  // blocks: 4, arch 4.26: 5
-  int s[kMaxBlocks];
+  int s[kMaxBlocks];  // block scale (>= 1); 1 for an up-scaled block
+  int k[kMaxBlocks];  // 1, or the up-scaling factor 2 / 4 of a block whose scale is 1/k (node scale_factor 2 / 4)
 };
 
 int make_geometry(int arch, int H, int W, float scale_factor, Geometry* g) {
@@ -421,9 +422,20 @@ int make_geometry(int arch, int H, int W, float scale_factor, Geometry* g) {
   g->nb = num_blocks(arch);
   for (int i = 0; i < g->nb; ++i) {
     const float sf = (float)(1 << (g->nb - 1 - i)) / scale_factor;  // [8,4,2,1] or [16,8,4,2,1] / scale_factor, rife/__init__.py:156-160
+    g->k[i] = 1;
+    if (sf < 1.f) {  // a block that UP-scales its input by k = 1 / scale (scale_factor 2: last block, 4: last two)
+      const int ki = (int)std::lround(1.f / sf);
+      if (std::fabs(1.f / sf - (float)ki) > 1e-6f || (ki != 2 && ki != 4))
+        return fail(VFI_E_INVALID, "scale_factor must be one of 0.25, 0.5, 1, 2, 4");
+      if (arch != 46)
+        return fail(VFI_E_NOTIMPL, "scale_factor > 1 (up-scaled blocks) is implemented for arch 4.6 only; use 1.0, 0.5 or 0.25");
+      g->k[i] = ki;
+      g->s[i] = 1;
+      continue;
+    }
     const int si = (int)std::lround(sf);
     if (std::fabs(sf - (float)si) > 1e-6f || si < 1 || (si & (si - 1)))
-      return fail(VFI_E_NOTIMPL, "scale_factor > 1 (up-scaled blocks) is not implemented; use 1.0, 0.5 or 0.25");
+      return fail(VFI_E_INVALID, "scale_factor must be one of 0.25, 0.5, 1, 2, 4");
     g->s[i] = si;
     if ((g->Hp / si) % 4 || (g->Wp / si) % 4 || g->Hp % si || g->Wp % si)
       return fail(VFI_E_INVALID,
@@ -436,7 +448,7 @@ int make_geometry(int arch, int H, int W, float scale_factor, Geometry* g) {
 int ensure_workspace(vfi_ctx* c, const Geometry& g, int B, int n_frames_window) {
   size_t x = 0, c00 = 0, feat = 0;
   for (int i = 0; i < g.nb; ++i) {
-    const size_t Hs = g.Hp / g.s[i], Ws = g.Wp / g.s[i];
+    const size_t Hs = (size_t)g.Hp * g.k[i] / g.s[i], Ws = (size_t)g.Wp * g.k[i] / g.s[i];
     x = std::max(x, (size_t)B * (Hs / 2) * (Ws / 2) * (c->arch != 46 ? 128 : 64) * 2);
     c00 = std::max(c00, (size_t)B * (Hs / 4) * (Ws / 4) * 2 * kBlockC[i] * 2);
     feat = std::max(feat, (size_t)B * (Hs / 4) * (Ws / 4) * kBlockC[i] * 2);
@@ -522,10 +534,21 @@ int forward_pass(vfi_ctx* c, const Geometry& g, const BatchTasks& tasks, int H, 
   int lo = 0;  // levels [lo, i) are not yet folded into F
   for (int i = 0; i < nb; ++i) {
     const int s = g.s[i];
-    const int Hs = g.Hp / s, Ws = g.Wp / s;
+    const int Hs = g.Hp * g.k[i] / s, Ws = g.Wp * g.k[i] / s;
     const void* pfeat = (c->arch == 426 && i > 0) ? c->tE[i - 1].p : nullptr;  // previous block's 8 feature channels
     const int ps = i > 0 ? g.s[i - 1] : 1;
-    if (i == 0 || i < dense) {
+    if (g.k[i] > 1) {
+      // up-scaled block (arch 4.6): fold every level so far into the dense planes, build the k-times finer input from them
+      if (i == 0) return fail(VFI_E_INVALID, "the first block cannot be up-scaled");
+      if (lo < i) {
+        FlowState part = fs;
+        part.n = i;
+        LAUNCH(launch_materialize(part, lo, have_base ? F : nullptr, have_base ? M : nullptr, F, M, B, g.Hp, g.Wp, st));
+        have_base = true;
+        lo = i;
+      }
+      LAUNCH(launch_front_up(c->op_type, imgs_h, F, M, tasks, g.Hp, g.Wp, g.k[i], c->x.p, st));
+    } else if (i == 0 || i < dense) {
       LAUNCH(launch_front(c->op_type, c->arch, imgs, imgs_h, feats, feat_ch, pfeat, ps, fs, i, 0, nullptr, nullptr, nullptr,
                           nullptr, tasks, g.Hp, g.Wp, s, c->x.p, st));
     } else {
@@ -550,6 +573,10 @@ int forward_pass(vfi_ctx* c, const Geometry& g, const BatchTasks& tasks, int H, 
     if (c->arch == 426 && i + 1 < nb)  // the 8 feature channels of lastconv, for the next block's input
       LAUNCH(launch_tapconv(c->layers[i][11], c->op_type, a, c->tE[i].p, nullptr, nullptr, B, Hs / 4, Ws / 4, c->num_sms,
                             false, st));
+    if (g.k[i] > 1) {  // the up-scaled block's output goes straight back onto the dense planes
+      LAUNCH(launch_fold_down(fs.f[i], fs.m[i], g.k[i], F, M, B, g.Hp, g.Wp, st));
+      lo = i + 1;
+    }
   }
   LAUNCH(launch_final(imgs, fs, lo, have_base ? F : nullptr, have_base ? M : nullptr, tasks, g.Hp, g.Wp, H, W, out, st));
   c->last_fs = fs;
@@ -977,9 +1004,14 @@ int vfi_rife46_debug_state(vfi_ctx* c, float* flow4_out, float* mask_out, int ba
   const size_t n = (size_t)batch * c->ws_Hp * c->ws_Wp;
   CK(c->dbgF.ensure(n * sizeof(float4)));
   CK(c->dbgM.ensure(n * sizeof(float)));
-  LAUNCH(launch_materialize(c->last_fs, c->last_lo, c->last_have_base ? (const float4*)c->flow.p : nullptr,
-                            c->last_have_base ? (const float*)c->mask.p : nullptr, (float4*)c->dbgF.p,
-                            (float*)c->dbgM.p, batch, c->ws_Hp, c->ws_Wp, 0));
+  if (c->last_lo >= c->last_fs.n) {  // every level already folded into the dense planes (up-scaled last blocks)
+    CK(cudaMemcpy(c->dbgF.p, c->flow.p, n * sizeof(float4), cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(c->dbgM.p, c->mask.p, n * sizeof(float), cudaMemcpyDeviceToDevice));
+  } else {
+    LAUNCH(launch_materialize(c->last_fs, c->last_lo, c->last_have_base ? (const float4*)c->flow.p : nullptr,
+                              c->last_have_base ? (const float*)c->mask.p : nullptr, (float4*)c->dbgF.p,
+                              (float*)c->dbgM.p, batch, c->ws_Hp, c->ws_Wp, 0));
+  }
   CK(cudaDeviceSynchronize());
   if (flow4_out) CK(cudaMemcpy(flow4_out, c->dbgF.p, n * sizeof(float4), cudaMemcpyDeviceToDevice));
   if (mask_out) CK(cudaMemcpy(mask_out, c->dbgM.p, n * sizeof(float), cudaMemcpyDeviceToDevice));

@@ -26,7 +26,8 @@ def test_oracle_matches_reference_output(name):
         x = fr.permute(0, 3, 1, 2)
         b = len(cfg["ts"])
         ts = torch.tensor(cfg["ts"], dtype=torch.float32).view(-1, 1, 1, 1)
-        out = O.ifnet_forward(arch, sd, x[0:1].repeat(b, 1, 1, 1), x[1:2].repeat(b, 1, 1, 1), ts)
+        sl = [v / cfg.get("scale_factor", 1.0) for v in O.SCALE_LIST[arch]]
+        out = O.ifnet_forward(arch, sd, x[0:1].repeat(b, 1, 1, 1), x[1:2].repeat(b, 1, 1, 1), ts, sl)
     else:
         out = O.rife_vfi(sd, fr, multiplier=cfg["multiplier"], states=cfg["states"], arch=arch)
     assert out.shape == ref.shape

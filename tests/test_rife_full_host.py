@@ -44,7 +44,7 @@ def _engine_names(arch):
 
 
 @pytest.mark.parametrize("name", ["ifnet_64x64_gain4", "ifnet47_64x128_gain3", "ifnet417_64x128_gain3",
-                                  "ifnet426_128x128_gain3"])
+                                  "ifnet426_128x128_gain3", "ifnet_64x64_sf2", "ifnet_64x128_sf4"])
 def test_rife_whole_path_on_host_matches_reference(emu, name):
     cfg = cases()[name]
     arch = cfg.get("arch", "4.6")
@@ -64,7 +64,8 @@ def test_rife_whole_path_on_host_matches_reference(emu, name):
     f1 = np.ones(len(ts), dtype=np.int32)
     out = torch.zeros(len(ts), h, w, 3)
     rc = emu.vfi_rife46_forward(ctx, C.c_void_p(fr.data_ptr()), n, h, w, c, f0.ctypes.data_as(C.c_void_p),
-                                f1.ctypes.data_as(C.c_void_p), ts.ctypes.data_as(C.c_void_p), len(ts), C.c_float(1.0),
+                                f1.ctypes.data_as(C.c_void_p), ts.ctypes.data_as(C.c_void_p), len(ts),
+                                C.c_float(cfg.get("scale_factor", 1.0)),
                                 C.c_void_p(out.data_ptr()), None)
     assert rc == 0, emu.vfi_last_error()
     emu.vfi_launch_count.restype = C.c_int64

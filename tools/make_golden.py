@@ -72,6 +72,10 @@ def cases():
                                        clip_seed=33),
         "node426_m2": dict(kind="node", arch="4.26", ckpt="rife426.pth", seed=34, gain=1.0, n=3, h=56, w=88, c=3,
                            multiplier=2, states=None, clip_seed=35),
+        # node scale_factor 2 / 4 (rife/__init__.py:156-160: scale_list / scale_factor): the last one / two blocks run at
+        # scale 0.5 / 0.25, i.e. on an UP-scaled input
+        "ifnet_64x64_sf2": dict(kind="ifnet", seed=40, gain=2.0, h=64, w=64, ts=(0.5,), clip_seed=41, scale_factor=2.0),
+        "ifnet_64x128_sf4": dict(kind="ifnet", seed=42, gain=2.0, h=64, w=128, ts=(0.4,), clip_seed=43, scale_factor=4.0),
         # node level: keep-list (is_skip_list False)
         "node_keep": dict(kind="node", seed=4, gain=1.0, n=4, h=48, w=80, c=3, multiplier=2,
                           states=([0, 2], False), clip_seed=15),
@@ -138,7 +142,8 @@ def main():
             ts = torch.tensor(cfg["ts"], dtype=torch.float32).view(-1, 1, 1, 1)
             b = len(cfg["ts"])
             with torch.inference_mode():
-                out = m(x[0:1].repeat(b, 1, 1, 1), x[1:2].repeat(b, 1, 1, 1), ts, list(O.SCALE_LIST[arch]), False, False)
+                sl = [v / cfg.get("scale_factor", 1.0) for v in O.SCALE_LIST[arch]]
+                out = m(x[0:1].repeat(b, 1, 1, 1), x[1:2].repeat(b, 1, 1, 1), ts, sl, False, False)
             np.savez_compressed(os.path.join(out_dir, name + ".npz"), out=out.numpy())
         else:
             with tempfile.TemporaryDirectory() as td:

@@ -958,11 +958,70 @@ __global__ void front_up_kernel(const uint2* __restrict__ imgs, const float4* __
   reinterpret_cast<uint4*>(dst)[1] = hi;
 }
 
+// arch 4.7 variant: the 32-channel layout of front47_kernel ([w0.rgb, w1.rgb, warp(f0) 4, warp(f1) 4, t, mask, flow 4])
+template <typename T>
+__global__ void front_up47_kernel(const uint2* __restrict__ imgs, const uint2* __restrict__ feats, const float4* __restrict__ F,
+                                  const float* __restrict__ M, const BatchTasks tasks, int Hp, int Wp, int k,
+                                  T* __restrict__ x_s2d) {
+  const int Hs = Hp * k, Ws = Wp * k;
+  const size_t plane = (size_t)Hp * Wp;
+  const float inv_k = 1.f / (float)k;
+  const int par = (int)(threadIdx.x & 1);
+  const int xl = (int)(blockIdx.x * (blockDim.x >> 1) + (threadIdx.x >> 1));
+  if (xl >= Ws) return;
+  const int yl = (int)blockIdx.y * 2 + par;
+  const int b = (int)blockIdx.z;
+  const uint2* img0 = imgs + (size_t)tasks.f0[b] * plane;
+  const uint2* img1 = imgs + (size_t)tasks.f1[b] * plane;
+  const uint2* ft0 = feats + (size_t)tasks.f0[b] * plane;
+  const uint2* ft1 = feats + (size_t)tasks.f1[b] * plane;
+  const float t = tasks.t[b];
+  const float sy = fmaxf(((float)yl + 0.5f) * inv_k - 0.5f, 0.f), sx = fmaxf(((float)xl + 0.5f) * inv_k - 0.5f, 0.f);
+  const int y0 = min((int)sy, Hp - 1), x0 = min((int)sx, Wp - 1);
+  const int y1 = min(y0 + 1, Hp - 1), x1 = min(x0 + 1, Wp - 1);
+  const float ly = sy - (float)y0, lx = sx - (float)x0;
+  const float wq[4] = {(1.f - ly) * (1.f - lx), (1.f - ly) * lx, ly * (1.f - lx), ly * lx};
+  const int qy[4] = {y0, y0, y1, y1}, qx[4] = {x0, x1, x0, x1};
+  float ch[20];
+#pragma unroll
+  for (int i = 0; i < 20; ++i) ch[i] = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int Y = qy[q], X = qx[q];
+    const size_t pid = ((size_t)b * Hp + Y) * Wp + X;
+    const float4 f = F[pid];
+    const float m = M[pid];
+    const float4 a = sample_border(img0, Hp, Wp, (float)X + f.x, (float)Y + f.y);
+    const float4 c = sample_border(img1, Hp, Wp, (float)X + f.z, (float)Y + f.w);
+    const float4 fa = sample_border4(ft0, Hp, Wp, (float)X + f.x, (float)Y + f.y);
+    const float4 fc = sample_border4(ft1, Hp, Wp, (float)X + f.z, (float)Y + f.w);
+    const float v[20] = {a.x, a.y, a.z, c.x, c.y, c.z, fa.x, fa.y, fa.z, fa.w, fc.x, fc.y, fc.z, fc.w, t, m, f.x, f.y, f.z, f.w};
+#pragma unroll
+    for (int i = 0; i < 20; ++i) ch[i] = fmaf(v[i], wq[q], ch[i]);
+  }
+#pragma unroll
+  for (int i = 16; i < 20; ++i) ch[i] *= (float)k;
+  const size_t cell = ((size_t)b * (Hs >> 1) + (yl >> 1)) * (Ws >> 1) + (xl >> 1);
+  T* dst = x_s2d + cell * 128 + ((yl & 1) * 2 + (xl & 1)) * 32;
+  uint4 q0, q1, q2;
+  q0.x = Pack2<T>::pack(ch[0], ch[1]);   q0.y = Pack2<T>::pack(ch[2], ch[3]);
+  q0.z = Pack2<T>::pack(ch[4], ch[5]);   q0.w = Pack2<T>::pack(ch[6], ch[7]);
+  q1.x = Pack2<T>::pack(ch[8], ch[9]);   q1.y = Pack2<T>::pack(ch[10], ch[11]);
+  q1.z = Pack2<T>::pack(ch[12], ch[13]); q1.w = Pack2<T>::pack(ch[14], ch[15]);
+  q2.x = Pack2<T>::pack(ch[16], ch[17]); q2.y = Pack2<T>::pack(ch[18], ch[19]);
+  q2.z = 0u; q2.w = 0u;
+  reinterpret_cast<uint4*>(dst)[0] = q0;
+  reinterpret_cast<uint4*>(dst)[1] = q1;
+  reinterpret_cast<uint4*>(dst)[2] = q2;
+  reinterpret_cast<uint4*>(dst)[3] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 // The block's output T (flow increments float4 + mask, k times finer than full resolution) back onto the dense planes:
 // interpolate(T, scale_factor = 1 / k) takes the two central taps k p + k/2 - 1, k p + k/2 per axis with weight 1/2 (for
-// k = 2 the 2x2 mean), flow is multiplied by the scale 1 / k (rife_arch.py:263-266) and added; the mask is added (arch 4.6).
+// k = 2 the 2x2 mean), flow is multiplied by the scale 1 / k (rife_arch.py:263-266) and added; the mask is added (arch 4.6) or
+// replaces the old one (arch 4.7+, rife_arch.py:698-699).
 __global__ void fold_down_kernel(const float4* __restrict__ tf, const float* __restrict__ tm, int k, float4* __restrict__ F,
-                                 float* __restrict__ M, int B, int Hp, int Wp) {
+                                 float* __restrict__ M, int B, int Hp, int Wp, int mask_replace) {
   const size_t total = (size_t)B * Hp * Wp;
   const int Ws = Wp * k;
   const float inv_k = 1.f / (float)k;
@@ -979,7 +1038,8 @@ __global__ void fold_down_kernel(const float4* __restrict__ tf, const float* __r
     f.z += (0.5f * (0.5f * a.z + 0.5f * c.z) + 0.5f * (0.5f * d.z + 0.5f * e.z)) * inv_k;
     f.w += (0.5f * (0.5f * a.w + 0.5f * c.w) + 0.5f * (0.5f * d.w + 0.5f * e.w)) * inv_k;
     F[id] = f;
-    M[id] += 0.5f * (0.5f * ma + 0.5f * mc) + 0.5f * (0.5f * md + 0.5f * me);
+    const float md_ = 0.5f * (0.5f * ma + 0.5f * mc) + 0.5f * (0.5f * md + 0.5f * me);
+    M[id] = mask_replace ? md_ : M[id] + md_;
   }
 }
 
@@ -1269,10 +1329,19 @@ cudaError_t launch_final(const float4* imgs, const FlowState& fs, int lo, const 
   return cudaGetLastError();
 }
 
-cudaError_t launch_front_up(int op_type, const uint2* imgs_h, const float4* F, const float* M, BatchTasks tasks, int Hp, int Wp,
-                            int k, void* x_s2d, cudaStream_t st) {
-  if ((k != 2 && k != 4) || F == nullptr || M == nullptr) return cudaErrorInvalidValue;
+cudaError_t launch_front_up(int op_type, int arch, const uint2* imgs_h, const void* feats, const float4* F, const float* M,
+                            BatchTasks tasks, int Hp, int Wp, int k, void* x_s2d, cudaStream_t st) {
+  if ((k != 2 && k != 4) || F == nullptr || M == nullptr || (arch != 46 && arch != 47)) return cudaErrorInvalidValue;
   const dim3 g((unsigned)((Wp * k + 63) / 64), (unsigned)(Hp * k / 2), (unsigned)tasks.n);
+  if (arch == 47) {
+    if (feats == nullptr) return cudaErrorInvalidValue;
+    if (op_type == OP_BF16)
+      VFI_LAUNCH((front_up47_kernel<__nv_bfloat16>), g, 128, 0, st, imgs_h, (const uint2*)feats, F, M, tasks, Hp, Wp, k,
+                 (__nv_bfloat16*)x_s2d);
+    else
+      VFI_LAUNCH((front_up47_kernel<__half>), g, 128, 0, st, imgs_h, (const uint2*)feats, F, M, tasks, Hp, Wp, k, (__half*)x_s2d);
+    return cudaGetLastError();
+  }
   if (op_type == OP_BF16)
     VFI_LAUNCH((front_up_kernel<__nv_bfloat16>), g, 128, 0, st, imgs_h, F, M, tasks, Hp, Wp, k, (__nv_bfloat16*)x_s2d);
   else
@@ -1281,9 +1350,9 @@ cudaError_t launch_front_up(int op_type, const uint2* imgs_h, const float4* F, c
 }
 
 cudaError_t launch_fold_down(const float4* tf, const float* tm, int k, float4* F, float* M, int B, int Hp, int Wp,
-                             cudaStream_t st) {
+                             int mask_replace, cudaStream_t st) {
   if (k != 2 && k != 4) return cudaErrorInvalidValue;
-  VFI_LAUNCH((fold_down_kernel), grid_for((size_t)B * Hp * Wp, 256), 256, 0, st, tf, tm, k, F, M, B, Hp, Wp);
+  VFI_LAUNCH((fold_down_kernel), grid_for((size_t)B * Hp * Wp, 256), 256, 0, st, tf, tm, k, F, M, B, Hp, Wp, mask_replace);
   return cudaGetLastError();
 }
 

@@ -23,7 +23,7 @@ def test_ifnet_scale_factor_golden(pkg, name):
     from cfi_b200.engine import Rife46Engine
     cfg = cases()[name]
     ref = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))["out"]).clamp(0, 1)
-    sd = O.synthetic_state_dict(cfg["seed"], cfg["gain"])
+    sd = O.synthetic_state_dict(cfg["seed"], cfg["gain"], arch=cfg.get("arch", "4.6"))
     eng = Rife46Engine(sd, 0, "float32")
     fr = make_inputs(cfg)
     b = len(cfg["ts"])

@@ -75,9 +75,9 @@ def cases():
         # node scale_factor 2 / 4 (rife/__init__.py:156-160: scale_list / scale_factor): the last one / two blocks run at
         # scale 0.5 / 0.25, i.e. on an UP-scaled input
         "ifnet_64x64_sf2": dict(kind="ifnet", seed=40, gain=2.0, h=64, w=64, ts=(0.5,), clip_seed=41, scale_factor=2.0),
-        "ifnet_64x128_sf4": dict(kind="ifnet", seed=42, gain=2.0, h=64, w=128, ts=(0.4,), clip_seed=43, scale_factor=4.0),
+        "ifnet_64x64_sf4": dict(kind="ifnet", seed=42, gain=2.0, h=64, w=64, ts=(0.4,), clip_seed=43, scale_factor=4.0),
         "ifnet47_64x64_sf2": dict(kind="ifnet", arch="4.7", seed=44, gain=2.0, h=64, w=64, ts=(0.5,), clip_seed=45, scale_factor=2.0),
-        "ifnet47_64x128_sf4": dict(kind="ifnet", arch="4.7", seed=46, gain=2.0, h=64, w=128, ts=(0.6,), clip_seed=47,
+        "ifnet47_64x64_sf4": dict(kind="ifnet", arch="4.7", seed=46, gain=2.0, h=64, w=64, ts=(0.6,), clip_seed=47,
                                    scale_factor=4.0),
         # node level: keep-list (is_skip_list False)
         "node_keep": dict(kind="node", seed=4, gain=1.0, n=4, h=48, w=80, c=3, multiplier=2,

@@ -1016,6 +1016,156 @@ __global__ void front_up47_kernel(const uint2* __restrict__ imgs, const uint2* _
   reinterpret_cast<uint4*>(dst)[3] = make_uint4(0u, 0u, 0u, 0u);
 }
 
+// arch 4.17 variant: the 32-channel layout of front417_kernel ([w0.rgb, w1.rgb, warp(f0) 8, warp(f1) 8, t, mask, flow 4])
+template <typename T>
+__global__ void front_up417_kernel(const uint2* __restrict__ imgs, const uint4* __restrict__ feats, const float4* __restrict__ F,
+                                   const float* __restrict__ M, const BatchTasks tasks, int Hp, int Wp, int k,
+                                   T* __restrict__ x_s2d) {
+  const int Hs = Hp * k, Ws = Wp * k;
+  const size_t plane = (size_t)Hp * Wp;
+  const size_t fplane = plane / 4 * 4;
+  const float inv_k = 1.f / (float)k;
+  const int par = (int)(threadIdx.x & 1);
+  const int xl = (int)(blockIdx.x * (blockDim.x >> 1) + (threadIdx.x >> 1));
+  if (xl >= Ws) return;
+  const int yl = (int)blockIdx.y * 2 + par;
+  const int b = (int)blockIdx.z;
+  const uint2* img0 = imgs + (size_t)tasks.f0[b] * plane;
+  const uint2* img1 = imgs + (size_t)tasks.f1[b] * plane;
+  const uint4* ft0 = feats + (size_t)tasks.f0[b] * fplane;
+  const uint4* ft1 = feats + (size_t)tasks.f1[b] * fplane;
+  const float t = tasks.t[b];
+  const float sy = fmaxf(((float)yl + 0.5f) * inv_k - 0.5f, 0.f), sx = fmaxf(((float)xl + 0.5f) * inv_k - 0.5f, 0.f);
+  const int y0 = min((int)sy, Hp - 1), x0 = min((int)sx, Wp - 1);
+  const int y1 = min(y0 + 1, Hp - 1), x1 = min(x0 + 1, Wp - 1);
+  const float ly = sy - (float)y0, lx = sx - (float)x0;
+  const float wq[4] = {(1.f - ly) * (1.f - lx), (1.f - ly) * lx, ly * (1.f - lx), ly * lx};
+  const int qy[4] = {y0, y0, y1, y1}, qx[4] = {x0, x1, x0, x1};
+  float ch[28];
+#pragma unroll
+  for (int i = 0; i < 28; ++i) ch[i] = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int Y = qy[q], X = qx[q];
+    const size_t pid = ((size_t)b * Hp + Y) * Wp + X;
+    const float4 f = F[pid];
+    const float m = M[pid];
+    const float4 a = sample_border(img0, Hp, Wp, (float)X + f.x, (float)Y + f.y);
+    const float4 c = sample_border(img1, Hp, Wp, (float)X + f.z, (float)Y + f.w);
+    float fa[8], fc[8];
+    sample_border8<T>(ft0, Hp, Wp, (float)X + f.x, (float)Y + f.y, fa);
+    sample_border8<T>(ft1, Hp, Wp, (float)X + f.z, (float)Y + f.w, fc);
+    float v[28] = {a.x, a.y, a.z, c.x, c.y, c.z};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[6 + i] = fa[i];
+      v[14 + i] = fc[i];
+    }
+    v[22] = t; v[23] = m; v[24] = f.x; v[25] = f.y; v[26] = f.z; v[27] = f.w;
+#pragma unroll
+    for (int i = 0; i < 28; ++i) ch[i] = fmaf(v[i], wq[q], ch[i]);
+  }
+#pragma unroll
+  for (int i = 24; i < 28; ++i) ch[i] *= (float)k;
+  const size_t cell = ((size_t)b * (Hs >> 1) + (yl >> 1)) * (Ws >> 1) + (xl >> 1);
+  T* dst = x_s2d + cell * 128 + ((yl & 1) * 2 + (xl & 1)) * 32;
+  uint4 q4[4];
+  q4[0] = make_uint4(Pack2<T>::pack(ch[0], ch[1]), Pack2<T>::pack(ch[2], ch[3]), Pack2<T>::pack(ch[4], ch[5]),
+                     Pack2<T>::pack(ch[6], ch[7]));
+  q4[1] = make_uint4(Pack2<T>::pack(ch[8], ch[9]), Pack2<T>::pack(ch[10], ch[11]), Pack2<T>::pack(ch[12], ch[13]),
+                     Pack2<T>::pack(ch[14], ch[15]));
+  q4[2] = make_uint4(Pack2<T>::pack(ch[16], ch[17]), Pack2<T>::pack(ch[18], ch[19]), Pack2<T>::pack(ch[20], ch[21]),
+                     Pack2<T>::pack(ch[22], ch[23]));
+  q4[3] = make_uint4(Pack2<T>::pack(ch[24], ch[25]), Pack2<T>::pack(ch[26], ch[27]), 0u, 0u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(dst)[i] = q4[i];
+}
+
+// interpolate(scale_factor = 1 / k) of an 8-channel plane pf [k Hp][k Wp] at full-res (Y, X): the two central taps per axis
+template <typename T>
+__device__ __forceinline__ void down_feat8(const uint4* __restrict__ pf, int Ws, int k, int Y, int X, float (&o)[8]) {
+  const size_t base = (size_t)(k * Y + k / 2 - 1) * Ws + (size_t)(k * X + k / 2 - 1);
+  float a[8], b[8], c[8], d[8];
+  unpack8<T>(__ldg(pf + base), a);
+  unpack8<T>(__ldg(pf + base + 1), b);
+  unpack8<T>(__ldg(pf + base + Ws), c);
+  unpack8<T>(__ldg(pf + base + Ws + 1), d);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = 0.5f * (0.5f * a[i] + 0.5f * b[i]) + 0.5f * (0.5f * c[i] + 0.5f * d[i]);
+}
+
+// arch 4.26 variant: the layout of front426_kernel ([w0.rgb, w1.rgb, warp(f0) 4, warp(f1) 4, t, mask, feat 8, flow 4]); `feat`
+// = the previous block's 8 extra lastconv channels brought to full resolution (up by its scale prev_s, or - when that block
+// was itself up-scaled by prev_k - down by prev_k; rife_arch.py:267-274), then up-scaled with everything else.
+template <typename T>
+__global__ void front_up426_kernel(const uint2* __restrict__ imgs, const uint2* __restrict__ feats,
+                                   const uint4* __restrict__ prev_feat, int prev_s, int prev_k, const float4* __restrict__ F,
+                                   const float* __restrict__ M, const BatchTasks tasks, int Hp, int Wp, int k,
+                                   T* __restrict__ x_s2d) {
+  const int Hs = Hp * k, Ws = Wp * k;
+  const size_t plane = (size_t)Hp * Wp;
+  const size_t fplane = plane / 4 * 4;
+  const float inv_k = 1.f / (float)k;
+  const int par = (int)(threadIdx.x & 1);
+  const int xl = (int)(blockIdx.x * (blockDim.x >> 1) + (threadIdx.x >> 1));
+  if (xl >= Ws) return;
+  const int yl = (int)blockIdx.y * 2 + par;
+  const int b = (int)blockIdx.z;
+  const uint2* img0 = imgs + (size_t)tasks.f0[b] * plane;
+  const uint2* img1 = imgs + (size_t)tasks.f1[b] * plane;
+  const uint2* ft0 = feats + (size_t)tasks.f0[b] * fplane;
+  const uint2* ft1 = feats + (size_t)tasks.f1[b] * fplane;
+  const int pHs = prev_k > 1 ? Hp * prev_k : Hp / prev_s, pWs = prev_k > 1 ? Wp * prev_k : Wp / prev_s;
+  const uint4* pf = prev_feat + (size_t)b * pHs * pWs;
+  const float pinv = 1.f / (float)prev_s;
+  const float t = tasks.t[b];
+  const float sy = fmaxf(((float)yl + 0.5f) * inv_k - 0.5f, 0.f), sx = fmaxf(((float)xl + 0.5f) * inv_k - 0.5f, 0.f);
+  const int y0 = min((int)sy, Hp - 1), x0 = min((int)sx, Wp - 1);
+  const int y1 = min(y0 + 1, Hp - 1), x1 = min(x0 + 1, Wp - 1);
+  const float ly = sy - (float)y0, lx = sx - (float)x0;
+  const float wq[4] = {(1.f - ly) * (1.f - lx), (1.f - ly) * lx, ly * (1.f - lx), ly * lx};
+  const int qy[4] = {y0, y0, y1, y1}, qx[4] = {x0, x1, x0, x1};
+  float ch[28];
+#pragma unroll
+  for (int i = 0; i < 28; ++i) ch[i] = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int Y = qy[q], X = qx[q];
+    const size_t pid = ((size_t)b * Hp + Y) * Wp + X;
+    const float4 f = F[pid];
+    const float m = M[pid];
+    const float4 a = sample_border(img0, Hp, Wp, (float)X + f.x, (float)Y + f.y);
+    const float4 c = sample_border(img1, Hp, Wp, (float)X + f.z, (float)Y + f.w);
+    float fa[4], fc[4], pe[8];
+    sample_border4h<T>(ft0, Hp, Wp, (float)X + f.x, (float)Y + f.y, fa);
+    sample_border4h<T>(ft1, Hp, Wp, (float)X + f.z, (float)Y + f.w, fc);
+    if (prev_k > 1)
+      down_feat8<T>(pf, pWs, prev_k, Y, X, pe);
+    else
+      up_feat8<T>(pf, pHs, pWs, prev_s, pinv, Y, X, pe);
+    float v[28] = {a.x, a.y, a.z, c.x, c.y, c.z, fa[0], fa[1], fa[2], fa[3], fc[0], fc[1], fc[2], fc[3], t, m};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[16 + i] = pe[i];
+    v[24] = f.x; v[25] = f.y; v[26] = f.z; v[27] = f.w;
+#pragma unroll
+    for (int i = 0; i < 28; ++i) ch[i] = fmaf(v[i], wq[q], ch[i]);
+  }
+#pragma unroll
+  for (int i = 24; i < 28; ++i) ch[i] *= (float)k;
+  const size_t cell = ((size_t)b * (Hs >> 1) + (yl >> 1)) * (Ws >> 1) + (xl >> 1);
+  T* dst = x_s2d + cell * 128 + ((yl & 1) * 2 + (xl & 1)) * 32;
+  uint4 q4[4];
+  q4[0] = make_uint4(Pack2<T>::pack(ch[0], ch[1]), Pack2<T>::pack(ch[2], ch[3]), Pack2<T>::pack(ch[4], ch[5]),
+                     Pack2<T>::pack(ch[6], ch[7]));
+  q4[1] = make_uint4(Pack2<T>::pack(ch[8], ch[9]), Pack2<T>::pack(ch[10], ch[11]), Pack2<T>::pack(ch[12], ch[13]),
+                     Pack2<T>::pack(ch[14], ch[15]));
+  q4[2] = make_uint4(Pack2<T>::pack(ch[16], ch[17]), Pack2<T>::pack(ch[18], ch[19]), Pack2<T>::pack(ch[20], ch[21]),
+                     Pack2<T>::pack(ch[22], ch[23]));
+  q4[3] = make_uint4(Pack2<T>::pack(ch[24], ch[25]), Pack2<T>::pack(ch[26], ch[27]), 0u, 0u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(dst)[i] = q4[i];
+}
+
 // The block's output T (flow increments float4 + mask, k times finer than full resolution) back onto the dense planes:
 // interpolate(T, scale_factor = 1 / k) takes the two central taps k p + k/2 - 1, k p + k/2 per axis with weight 1/2 (for
 // k = 2 the 2x2 mean), flow is multiplied by the scale 1 / k (rife_arch.py:263-266) and added; the mask is added (arch 4.6) or
@@ -1329,10 +1479,31 @@ cudaError_t launch_final(const float4* imgs, const FlowState& fs, int lo, const 
   return cudaGetLastError();
 }
 
-cudaError_t launch_front_up(int op_type, int arch, const uint2* imgs_h, const void* feats, const float4* F, const float* M,
-                            BatchTasks tasks, int Hp, int Wp, int k, void* x_s2d, cudaStream_t st) {
-  if ((k != 2 && k != 4) || F == nullptr || M == nullptr || (arch != 46 && arch != 47)) return cudaErrorInvalidValue;
+cudaError_t launch_front_up(int op_type, int arch, const uint2* imgs_h, const void* feats, const void* prev_feat, int prev_s,
+                            int prev_k, const float4* F, const float* M, BatchTasks tasks, int Hp, int Wp, int k, void* x_s2d,
+                            cudaStream_t st) {
+  if ((k != 2 && k != 4) || F == nullptr || M == nullptr || (arch != 46 && arch != 47 && arch != 417 && arch != 426))
+    return cudaErrorInvalidValue;
   const dim3 g((unsigned)((Wp * k + 63) / 64), (unsigned)(Hp * k / 2), (unsigned)tasks.n);
+  if (arch == 426) {
+    if (feats == nullptr || prev_feat == nullptr || prev_s < 1 || prev_k < 1) return cudaErrorInvalidValue;
+    if (op_type == OP_BF16)
+      VFI_LAUNCH((front_up426_kernel<__nv_bfloat16>), g, 128, 0, st, imgs_h, (const uint2*)feats, (const uint4*)prev_feat, prev_s,
+                 prev_k, F, M, tasks, Hp, Wp, k, (__nv_bfloat16*)x_s2d);
+    else
+      VFI_LAUNCH((front_up426_kernel<__half>), g, 128, 0, st, imgs_h, (const uint2*)feats, (const uint4*)prev_feat, prev_s, prev_k,
+                 F, M, tasks, Hp, Wp, k, (__half*)x_s2d);
+    return cudaGetLastError();
+  }
+  if (arch == 417) {
+    if (feats == nullptr) return cudaErrorInvalidValue;
+    if (op_type == OP_BF16)
+      VFI_LAUNCH((front_up417_kernel<__nv_bfloat16>), g, 128, 0, st, imgs_h, (const uint4*)feats, F, M, tasks, Hp, Wp, k,
+                 (__nv_bfloat16*)x_s2d);
+    else
+      VFI_LAUNCH((front_up417_kernel<__half>), g, 128, 0, st, imgs_h, (const uint4*)feats, F, M, tasks, Hp, Wp, k, (__half*)x_s2d);
+    return cudaGetLastError();
+  }
   if (arch == 47) {
     if (feats == nullptr) return cudaErrorInvalidValue;
     if (op_type == OP_BF16)

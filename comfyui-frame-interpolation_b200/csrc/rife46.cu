@@ -427,9 +427,6 @@ int make_geometry(int arch, int H, int W, float scale_factor, Geometry* g) {
       const int ki = (int)std::lround(1.f / sf);
       if (std::fabs(1.f / sf - (float)ki) > 1e-6f || (ki != 2 && ki != 4))
         return fail(VFI_E_INVALID, "scale_factor must be one of 0.25, 0.5, 1, 2, 4");
-      if (arch != 46 && arch != 47)
-        return fail(VFI_E_NOTIMPL,
-                    "scale_factor > 1 (up-scaled blocks) is implemented for archs 4.6 and 4.7 only; use 1.0, 0.5 or 0.25");
       g->k[i] = ki;
       g->s[i] = 1;
       continue;
@@ -539,7 +536,7 @@ int forward_pass(vfi_ctx* c, const Geometry& g, const BatchTasks& tasks, int H, 
     const void* pfeat = (c->arch == 426 && i > 0) ? c->tE[i - 1].p : nullptr;  // previous block's 8 feature channels
     const int ps = i > 0 ? g.s[i - 1] : 1;
     if (g.k[i] > 1) {
-      // up-scaled block (archs 4.6, 4.7): fold every level so far into the dense planes, build the k-times finer input from them
+      // up-scaled block: fold every level so far into the dense planes, build the k-times finer input from them
       if (i == 0) return fail(VFI_E_INVALID, "the first block cannot be up-scaled");
       if (lo < i) {
         FlowState part = fs;
@@ -548,7 +545,8 @@ int forward_pass(vfi_ctx* c, const Geometry& g, const BatchTasks& tasks, int H, 
         have_base = true;
         lo = i;
       }
-      LAUNCH(launch_front_up(c->op_type, c->arch, imgs_h, feats, F, M, tasks, g.Hp, g.Wp, g.k[i], c->x.p, st));
+      LAUNCH(launch_front_up(c->op_type, c->arch, imgs_h, feats, pfeat, ps, g.k[i - 1], F, M, tasks, g.Hp, g.Wp, g.k[i], c->x.p,
+                             st));
     } else if (i == 0 || i < dense) {
       LAUNCH(launch_front(c->op_type, c->arch, imgs, imgs_h, feats, feat_ch, pfeat, ps, fs, i, 0, nullptr, nullptr, nullptr,
                           nullptr, tasks, g.Hp, g.Wp, s, c->x.p, st));

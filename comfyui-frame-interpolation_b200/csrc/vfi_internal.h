@@ -143,10 +143,11 @@ cudaError_t launch_materialize(const FlowState& fs, int lo, const float4* base_f
                                float* mask, int B, int Hp, int Wp, cudaStream_t st);
 cudaError_t launch_final(const float4* imgs, const FlowState& fs, int lo, const float4* base_f, const float* base_m,
                          BatchTasks tasks, int Hp, int Wp, int H, int W, float* out, cudaStream_t st);
-// up-scaled blocks (scale_factor 2 / 4, archs 4.6 and 4.7): block input k times finer than full resolution from the dense planes,
+// up-scaled blocks (scale_factor 2 / 4): block input k times finer than full resolution from the dense planes,
 // and the block's output folded back onto them
-cudaError_t launch_front_up(int op_type, int arch, const uint2* imgs_h, const void* feats, const float4* F, const float* M,
-                            BatchTasks tasks, int Hp, int Wp, int k, void* x_s2d, cudaStream_t st);
+cudaError_t launch_front_up(int op_type, int arch, const uint2* imgs_h, const void* feats, const void* prev_feat, int prev_s,
+                            int prev_k, const float4* F, const float* M, BatchTasks tasks, int Hp, int Wp, int k, void* x_s2d,
+                            cudaStream_t st);
 cudaError_t launch_fold_down(const float4* tf, const float* tm, int k, float4* F, float* M, int B, int Hp, int Wp,
                              int mask_replace, cudaStream_t st);
 cudaError_t launch_warp(const float* img, const float* flow, float* out, int B, int H, int W, int C, cudaStream_t st);

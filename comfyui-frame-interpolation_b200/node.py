@@ -157,8 +157,7 @@ class RIFE_VFI:
         Accepted for API compatibility, without effect on results: clear_cache_after_n_frames (the workspace is
         pre-allocated, nothing to clear), fast_mode / ensemble (they never reach the 4.6 maths in the reference
         either - positional mis-wiring), torch_compile, batch_size (internal passes are sized by
-        the engine).  scale_factor 0.25 / 0.5 / 1 work for every checkpoint, 2 / 4 for rife46 / rife47 / rife49 (the library
-        raises for rife417 / rife426).  dtype selects the tensor-core operand type: float32/float16 -> fp16 operands with fp32
+        the engine).  all five scale_factor values work for every checkpoint.  dtype selects the tensor-core operand type: float32/float16 -> fp16 operands with fp32
         accumulation (same 10-bit mantissa as the TF32 convs the reference's float32 mode runs on a GPU),
         bfloat16 -> bf16 operands; flow, mask, warps and blending are fp32 in every mode.
         """

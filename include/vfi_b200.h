@@ -67,8 +67,8 @@ int vfi_rife_load(vfi_ctx* ctx, int arch, const float* const* tensors, const int
  * for n_tasks (pair, timestep) tasks.  DEVICE pointers:
  *   frames : [n_frames, H, W, C] float32 NHWC, C >= 3 (only the first 3 channels are read, vfi_utils.py:139)
  *   out    : [n_tasks, H, W, 3] float32 NHWC
- * scale_factor: the node's widget (rife/__init__.py:49, :156-160), one of 0.25, 0.5, 1 (every arch) or 2, 4 (archs 4.6 and
- * 4.7: the last one / two blocks run on an up-scaled input; VFI_E_NOTIMPL for 4.17 / 4.26).
+ * scale_factor: the node's widget (rife/__init__.py:49, :156-160), one of 0.25, 0.5, 1, 2, 4 (with 2 / 4 the last one / two
+ * blocks run on an up-scaled input).
  * Asynchronous on `stream`. */
 int vfi_rife46_forward(vfi_ctx* ctx, const float* frames, int n_frames, int H, int W, int C, const int32_t* f0,
                        const int32_t* f1, const float* t, int n_tasks, float scale_factor, float* out, void* stream);

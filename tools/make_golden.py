@@ -79,6 +79,12 @@ def cases():
         "ifnet47_64x64_sf2": dict(kind="ifnet", arch="4.7", seed=44, gain=2.0, h=64, w=64, ts=(0.5,), clip_seed=45, scale_factor=2.0),
         "ifnet47_64x64_sf4": dict(kind="ifnet", arch="4.7", seed=46, gain=2.0, h=64, w=64, ts=(0.6,), clip_seed=47,
                                    scale_factor=4.0),
+        "ifnet417_64x64_sf2": dict(kind="ifnet", arch="4.17", seed=48, gain=2.0, h=64, w=64, ts=(0.5,), clip_seed=49,
+                                   scale_factor=2.0),
+        "ifnet426_64x64_sf2": dict(kind="ifnet", arch="4.26", seed=50, gain=2.0, h=64, w=64, ts=(0.5,), clip_seed=51,
+                                   scale_factor=2.0),
+        "ifnet426_64x64_sf4": dict(kind="ifnet", arch="4.26", seed=52, gain=2.0, h=64, w=64, ts=(0.45,), clip_seed=53,
+                                   scale_factor=4.0),
         # node level: keep-list (is_skip_list False)
         "node_keep": dict(kind="node", seed=4, gain=1.0, n=4, h=48, w=80, c=3, multiplier=2,
                           states=([0, 2], False), clip_seed=15),

@@ -129,3 +129,43 @@ def test_rife_host_pipeline_on_host_matches_reference_node(emu):
     psnr = 99.0 if mse == 0 else 10 * math.log10(1.0 / mse)
     print(f"host emulation of the RIFE host pipeline ({name}): PSNR {psnr:.2f} dB")
     assert psnr >= 60.0, psnr
+
+
+def test_rife_host_pipeline_ring_and_shards_on_host(emu):
+    """The host pipeline's bookkeeping on the CPU: more tasks than one internal pass holds (batch 2: ramped pass sizes, the
+    ring of uploaded source frames, double-buffered output), out-of-order output slots and a frame shard [frame_lo,
+    frame_hi) - every task's frame must equal what the device-level entry point returns for the same (pair, timestep)."""
+    names, code = _engine_names("4.6")
+    sd = O.synthetic_state_dict(7, 1.0)
+    hold = [sd[n].contiguous().float() for n in names]
+    ptrs = (C.c_void_p * len(hold))(*[t.data_ptr() for t in hold])
+    numel = (C.c_int64 * len(hold))(*[t.numel() for t in hold])
+    ctx = C.c_void_p()
+    assert emu.vfi_create(0, C.byref(ctx)) == 0, emu.vfi_last_error()
+    assert emu.vfi_rife_load(ctx, code, ptrs, numel, len(hold), 0) == 0, emu.vfi_last_error()
+    assert emu.vfi_set_batch(ctx, 2) == 0
+    n, h, w, c = 7, 40, 56, 3
+    fr = O.synthetic_clip(n, h, w, seed=77).contiguous()
+    # shard: only frames [1, 6) may be touched; tasks on pairs 1..4, two timesteps on pair 2, slots reversed
+    tasks = [(1, 0.5), (2, 0.25), (2, 0.75), (3, 0.5), (4, 0.5)]
+    f0 = np.asarray([p for p, _ in tasks], dtype=np.int32)
+    f1 = f0 + 1
+    ts = np.asarray([t for _, t in tasks], dtype=np.float32)
+    slots = np.asarray(list(range(len(tasks)))[::-1], dtype=np.int32)
+    vp = lambda x: x.ctypes.data_as(C.c_void_p)   # noqa: E731
+    out = torch.zeros(len(tasks), h, w, 3)
+    rc = emu.vfi_rife46_interpolate_host(ctx, C.c_void_p(fr.data_ptr()), n, h, w, c, 1, 6, vp(f0), vp(f1), vp(ts), vp(slots),
+                                         len(tasks), C.c_float(1.0), C.c_void_p(out.data_ptr()))
+    assert rc == 0, emu.vfi_last_error()
+    for i, (p_, t) in enumerate(tasks):
+        one = torch.zeros(1, h, w, 3)
+        a0, a1, at = np.asarray([p_], np.int32), np.asarray([p_ + 1], np.int32), np.asarray([t], np.float32)
+        assert emu.vfi_rife46_forward(ctx, C.c_void_p(fr.data_ptr()), n, h, w, c, vp(a0), vp(a1), vp(at), 1, C.c_float(1.0),
+                                      C.c_void_p(one.data_ptr()), None) == 0, emu.vfi_last_error()
+        assert torch.equal(out[slots[i]], one[0]), (i, p_, t)
+    # a task outside the shard is refused
+    bad0, bad1 = np.asarray([0], np.int32), np.asarray([1], np.int32)
+    rc = emu.vfi_rife46_interpolate_host(ctx, C.c_void_p(fr.data_ptr()), n, h, w, c, 1, 6, vp(bad0), vp(bad1), vp(ts), None, 1,
+                                         C.c_float(1.0), C.c_void_p(out.data_ptr()))
+    assert rc != 0
+    assert emu.vfi_destroy(ctx) == 0

@@ -15,10 +15,11 @@
 struct EmuDim3 {
   unsigned x = 1, y = 1, z = 1;
 };
-static EmuDim3 blockIdx, threadIdx, blockDim, gridDim;
-static char* emu_dyn_smem = nullptr;
+// thread_local: the full-geometry launcher of cuda_shim_block.h runs different blocks on different host threads
+static thread_local EmuDim3 blockIdx, threadIdx, blockDim, gridDim;
+static thread_local char* emu_dyn_smem = nullptr;
 #define __global__
-#define __shared__ static
+#define __shared__ static thread_local
 #define __restrict__
 
 namespace block_emu {
@@ -27,10 +28,10 @@ struct Fiber {
   std::vector<char> stack;
   bool done = false;
 };
-static ucontext_t sched_ctx;
-static std::vector<Fiber>* fibers = nullptr;
-static int current = -1;
-static std::function<void()>* body = nullptr;
+static thread_local ucontext_t sched_ctx;
+static thread_local std::vector<Fiber>* fibers = nullptr;
+static thread_local int current = -1;
+static thread_local std::function<void()>* body = nullptr;
 static void trampoline() {
   (*body)();
   (*fibers)[current].done = true;
@@ -38,7 +39,7 @@ static void trampoline() {
 }
 // runs `kernel()` for every thread of one block (threadIdx.x = 0..nthreads-1), phase by phase
 static void run_block(int nthreads, std::function<void()> kernel) {
-  static std::vector<Fiber> fs;   // fiber stacks are allocated once and reused by every block of every launch
+  static thread_local std::vector<Fiber> fs;   // fiber stacks: allocated once per host thread, reused by every block
   if ((int)fs.size() < nthreads) fs.resize(nthreads);
   fibers = &fs;
   body = &kernel;

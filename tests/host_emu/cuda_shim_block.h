@@ -32,17 +32,33 @@ using std::min;
 template <typename T>
 static inline T __ldg(const T* p) { return *p; }
 
-#define VFI_LAUNCH(kernel, grid, block, smem, stream, ...)                                   \
-  do {                                                                                        \
-    const dim3 _g(grid), _b(block);                                                           \
-    gridDim.x = _g.x; gridDim.y = _g.y; gridDim.z = _g.z;                                     \
-    blockDim.x = _b.x; blockDim.y = 1; blockDim.z = 1;                                        \
-    for (unsigned _z = 0; _z < _g.z; ++_z)                                                    \
-      for (unsigned _y = 0; _y < _g.y; ++_y)                                                  \
-        for (unsigned _x = 0; _x < _g.x; ++_x) {                                              \
-          blockIdx.x = _x; blockIdx.y = _y; blockIdx.z = _z;                                  \
-          block_emu::run_block((int)_b.x, [&]() { kernel(__VA_ARGS__); });                    \
-        }                                                                                     \
+// blocks are dealt round-robin to up to 16 host threads; inside a block the threads are fibers (block_emu.h)
+#include <thread>
+#include <vector>
+#define VFI_LAUNCH(kernel, grid, block, smem, stream, ...)                                          \
+  do {                                                                                               \
+    const dim3 _g(grid), _b(block);                                                                  \
+    const size_t _nb = (size_t)_g.x * _g.y * _g.z;                                                   \
+    unsigned _t = std::thread::hardware_concurrency();                                               \
+    _t = _t < 1 ? 1 : (_t > 16 ? 16 : _t);                                                           \
+    if ((size_t)_t > _nb) _t = (unsigned)_nb;                                                        \
+    auto _work = [&](unsigned _w) {                                                                  \
+      gridDim.x = _g.x; gridDim.y = _g.y; gridDim.z = _g.z;                                          \
+      blockDim.x = _b.x; blockDim.y = 1; blockDim.z = 1;                                             \
+      for (size_t _i = _w; _i < _nb; _i += _t) {                                                     \
+        blockIdx.x = (unsigned)(_i % _g.x);                                                          \
+        blockIdx.y = (unsigned)((_i / _g.x) % _g.y);                                                 \
+        blockIdx.z = (unsigned)(_i / ((size_t)_g.x * _g.y));                                         \
+        block_emu::run_block((int)_b.x, [&]() { kernel(__VA_ARGS__); });                             \
+      }                                                                                              \
+    };                                                                                               \
+    if (_t <= 1) {                                                                                   \
+      _work(0);                                                                                      \
+    } else {                                                                                         \
+      std::vector<std::thread> _th;                                                                  \
+      for (unsigned _w = 0; _w < _t; ++_w) _th.emplace_back(_work, _w);                              \
+      for (auto& _h : _th) _h.join();                                                                \
+    }                                                                                                \
   } while (0)
 
 static inline cudaError_t emu_malloc(void** p, size_t n) {

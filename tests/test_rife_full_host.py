@@ -80,6 +80,34 @@ def test_rife_whole_path_on_host_matches_reference(emu, name):
     assert psnr >= 60.0, psnr
 
 
+def test_rife_bf16_operands_on_host(emu):
+    """node dtype bfloat16 = bf16 conv operands (VFI_OPERAND_BF16): the bf16 instantiations of the element-wise kernels and of
+    the checker, same schedule; the bar is the north_star's 50 dB."""
+    name = "ifnet_64x64_gain4"
+    cfg = cases()[name]
+    ref = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))["out"]).permute(0, 2, 3, 1).clamp(0, 1)
+    sd = O.synthetic_state_dict(cfg["seed"], cfg["gain"])
+    names, code = _engine_names("4.6")
+    hold = [sd[n].contiguous().float() for n in names]
+    ptrs = (C.c_void_p * len(hold))(*[t.data_ptr() for t in hold])
+    numel = (C.c_int64 * len(hold))(*[t.numel() for t in hold])
+    ctx = C.c_void_p()
+    assert emu.vfi_create(0, C.byref(ctx)) == 0
+    assert emu.vfi_rife_load(ctx, code, ptrs, numel, len(hold), 1) == 0, emu.vfi_last_error()
+    fr = make_inputs(cfg).contiguous()
+    n, h, w, c = fr.shape
+    f0, f1, ts = np.zeros(1, np.int32), np.ones(1, np.int32), np.asarray(cfg["ts"], np.float32)
+    out = torch.zeros(1, h, w, 3)
+    vp = lambda x: x.ctypes.data_as(C.c_void_p)   # noqa: E731
+    assert emu.vfi_rife46_forward(ctx, C.c_void_p(fr.data_ptr()), n, h, w, c, vp(f0), vp(f1), vp(ts), 1, C.c_float(1.0),
+                                  C.c_void_p(out.data_ptr()), None) == 0, emu.vfi_last_error()
+    assert emu.vfi_destroy(ctx) == 0
+    mse = float(((out.double() - ref.double()) ** 2).mean())
+    psnr = 10 * math.log10(1.0 / mse)
+    print(f"host emulation, bf16 operands ({name}): PSNR {psnr:.2f} dB")
+    assert psnr >= 50.0, psnr
+
+
 def test_rife_host_pipeline_on_host_matches_reference_node(emu):
     """vfi_rife46_interpolate_host (the H2D / compute / D2H pipeline with its ring of raw frames and output slots) against
     the unmodified reference node's output: multiplier 3, a skipped pair, 4-channel frames (tests/golden/node_m3_skip.npz)."""

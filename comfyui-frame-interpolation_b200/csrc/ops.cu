@@ -190,7 +190,7 @@ template <int K, int PY>
 __global__ void __launch_bounds__(256) sepconv_tile_kernel(const float* __restrict__ in, const float* __restrict__ ver,
                                                            const float* __restrict__ hor, float* __restrict__ out,
                                                            int N, int C, int c0, int H, int W) {
-  extern __shared__ float4 sep_tile[];  // [8*PY + K-1][32 + K-1]
+  VFI_DYN_SMEM(float4, sep_tile);  // [8*PY + K-1][32 + K-1]
   constexpr int TW = 32 + K - 1, TH = 8 * PY + K - 1;
   const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
   const int x0 = blockIdx.x * 32, y0 = blockIdx.y * (8 * PY), n = blockIdx.z;
@@ -279,7 +279,7 @@ cudaError_t launch_softsplat_sum(const float* in, const float* flow, float* out,
   cudaError_t e = cudaMemsetAsync(out, 0, (size_t)N * C * H * W * sizeof(float), st);
   if (e != cudaSuccess) return e;
   const size_t total = (size_t)N * H * W;
-  softsplat_sum_kernel<<<grid_for(total, 256), 256, 0, st>>>(in, flow, out, N, C, H, W);
+  VFI_LAUNCH((softsplat_sum_kernel), grid_for(total, 256), 256, 0, st, in, flow, out, N, C, H, W);
   return cudaGetLastError();
 }
 
@@ -292,16 +292,16 @@ cudaError_t launch_volume81(bool dot, const float* one, const float* two, float*
   if (tiled && N <= 65535) {
     const dim3 g((unsigned)((W + 31) / 32), (unsigned)((H + 7) / 8), (unsigned)N);
     if (dot)
-      volume81_tile_kernel<true><<<g, 256, 0, st>>>(one, two, out, N, C, H, W);
+      VFI_LAUNCH((volume81_tile_kernel<true>), g, 256, 0, st, one, two, out, N, C, H, W);
     else
-      volume81_tile_kernel<false><<<g, 256, 0, st>>>(one, two, out, N, C, H, W);
+      VFI_LAUNCH((volume81_tile_kernel<false>), g, 256, 0, st, one, two, out, N, C, H, W);
     return cudaGetLastError();
   }
   const size_t total = (size_t)N * H * W;
   if (dot)
-    volume81_kernel<true><<<grid_for(total, 128), 128, 0, st>>>(one, two, out, N, C, H, W);
+    VFI_LAUNCH((volume81_kernel<true>), grid_for(total, 128), 128, 0, st, one, two, out, N, C, H, W);
   else
-    volume81_kernel<false><<<grid_for(total, 128), 128, 0, st>>>(one, two, out, N, C, H, W);
+    VFI_LAUNCH((volume81_kernel<false>), grid_for(total, 128), 128, 0, st, one, two, out, N, C, H, W);
   return cudaGetLastError();
 }
 
@@ -318,7 +318,7 @@ cudaError_t launch_sepconv(const float* in, const float* ver, const float* hor, 
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
       const dim3 g((unsigned)((W + 31) / 32), (unsigned)((H + 8 * PY - 1) / (8 * PY)), (unsigned)N);
-      for (int c0 = 0; c0 < C; c0 += 4) kern<<<g, 256, smem, st>>>(in, ver, hor, out, N, C, c0, H, W);
+      for (int c0 = 0; c0 < C; c0 += 4) VFI_LAUNCH((kern), g, 256, smem, st, in, ver, hor, out, N, C, c0, H, W);
       return cudaGetLastError();
     };
     if (py == 1) return go(sepconv_tile_kernel<51, 1>, 1);
@@ -327,7 +327,7 @@ cudaError_t launch_sepconv(const float* in, const float* ver, const float* hor, 
   }
   const size_t total = (size_t)N * H * W;
   for (int c0 = 0; c0 < C; c0 += 4) {
-    sepconv_kernel<4><<<grid_for(total, 128), 128, 0, st>>>(in, ver, hor, out, N, C, c0, H, W, Kv, Kh);
+    VFI_LAUNCH((sepconv_kernel<4>), grid_for(total, 128), 128, 0, st, in, ver, hor, out, N, C, c0, H, W, Kv, Kh);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }

@@ -14,6 +14,10 @@ struct vfi_ctx;
 #ifndef VFI_LAUNCH
 #define VFI_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
+// a kernel's dynamic shared memory as an array of `type` (the host emulation points it at a per-block buffer)
+#ifndef VFI_DYN_SMEM
+#define VFI_DYN_SMEM(type, name) extern __shared__ type name[]
+#endif
 
 namespace vfi {
 

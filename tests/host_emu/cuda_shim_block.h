@@ -27,11 +27,21 @@
 #define __forceinline__ inline
 #define __grid_constant__
 #define __launch_bounds__(...)
+using std::isfinite;
 using std::max;
 using std::min;
 template <typename T>
 static inline T __ldg(const T* p) { return *p; }
+#include <atomic>
+static inline float atomicAdd(float* p, float v) {  // blocks run on several host threads
+  std::atomic_ref<float> a(*p);
+  float o = a.load();
+  while (!a.compare_exchange_weak(o, o + v)) {
+  }
+  return o;
+}
 
+#define VFI_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu_dyn_smem)
 // blocks are dealt round-robin to up to 16 host threads; inside a block the threads are fibers (block_emu.h)
 #include <thread>
 #include <vector>
@@ -43,6 +53,8 @@ static inline T __ldg(const T* p) { return *p; }
     _t = _t < 1 ? 1 : (_t > 16 ? 16 : _t);                                                           \
     if ((size_t)_t > _nb) _t = (unsigned)_nb;                                                        \
     auto _work = [&](unsigned _w) {                                                                  \
+      std::vector<char> _dyn((size_t)(smem) + 64);                                                   \
+      emu_dyn_smem = _dyn.data();                                                                    \
       gridDim.x = _g.x; gridDim.y = _g.y; gridDim.z = _g.z;                                          \
       blockDim.x = _b.x; blockDim.y = 1; blockDim.z = 1;                                             \
       for (size_t _i = _w; _i < _nb; _i += _t) {                                                     \
@@ -95,3 +107,4 @@ static inline cudaError_t emu_memcpy(void* d, const void* s, size_t n) {
 #define cudaEventCreateWithFlags(p, f) (*(p) = nullptr, cudaSuccess)
 #define cudaEventRecord(e, s) cudaSuccess
 #define cudaEventDestroy(e) cudaSuccess
+#define cudaFuncSetAttribute(k, a, v) cudaSuccess

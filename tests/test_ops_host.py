@@ -1,0 +1,62 @@
+"""csrc/ops.cu (the kernels behind vfi_softsplat_sum / vfi_costvol_l1 / vfi_corr_dot / vfi_sepconv, incl. the shared-memory
+tiled ones) compiled for the HOST (tests/host_emu/cuda_shim_block.h: blocks on host threads, threads as fibers) against the
+oracle restatements that tests/test_ops_ref_pinned.py pins to the reference's own kernels.  The same kernels are GPU-tested
+in tests/test_gpu_ops.py; this keeps them under test where there is no GPU."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import pytest
+import torch
+
+from oracle import ops_ref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CUDA_INC = "/usr/local/cuda/include"
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    if not (shutil.which("g++") and os.path.exists(os.path.join(CUDA_INC, "cuda_fp16.h"))):
+        pytest.skip("g++ / CUDA headers not available")
+    so = str(tmp_path_factory.mktemp("emu") / "libopsemu.so")
+    src = os.path.join(ROOT, "tests", "host_emu", "ops_emu.cpp")
+    r = subprocess.run(["g++", "-O2", "-std=c++20", "-shared", "-fPIC", "-pthread", "-I" + CUDA_INC, "-o", so, src],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return C.CDLL(so)
+
+
+def vp(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def test_softsplat_kernel(emu):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 5, 19, 23, generator=g)
+    flow = (torch.rand(2, 2, 19, 23, generator=g) - 0.5) * 9
+    out = torch.full_like(x, 7.0)   # the launcher zeroes the output itself
+    assert emu.emu_softsplat(vp(x), vp(flow), vp(out), 2, 5, 19, 23) == 0
+    assert (out - ops_ref.softsplat_sum(x, flow)).abs().max().item() <= 1e-4   # atomics: summation order differs
+
+
+@pytest.mark.parametrize("dot", [0, 1])
+def test_volume81_kernels(emu, dot):
+    g = torch.Generator().manual_seed(dot)
+    a, b = torch.randn(1, 20, 21, 37, generator=g), torch.randn(1, 20, 21, 37, generator=g)
+    out = torch.zeros(1, 81, 21, 37)
+    assert emu.emu_volume81(dot, vp(a), vp(b), vp(out), 1, 20, 21, 37) == 0
+    ref = ops_ref.correlation_dot(a, b) if dot else ops_ref.costvol_l1(a, b)
+    assert (out - ref).abs().max().item() <= 1e-4
+
+
+def test_sepconv_tiled_kernel(emu):
+    g = torch.Generator().manual_seed(3)
+    h, w, k = 19, 45, 51                       # not multiples of the 16 x 32 tile
+    x = torch.randn(1, 4, h + k - 1, w + k - 1, generator=g)
+    ver, hor = torch.randn(1, k, h, w, generator=g), torch.randn(1, k, h, w, generator=g)
+    out = torch.zeros(1, 4, h, w)
+    assert emu.emu_sepconv(vp(x), vp(ver), vp(hor), vp(out), 1, 4, h, w, k, k) == 0
+    ref = ops_ref.sepconv(x, ver, hor)
+    assert (out - ref).abs().max().item() <= 2e-4 * max(1.0, float(ref.abs().max()))

@@ -33,9 +33,10 @@ using std::min;
 template <typename T>
 static inline T __ldg(const T* p) { return *p; }
 #include <atomic>
-static inline float atomicAdd(float* p, float v) {  // blocks run on several host threads
-  std::atomic_ref<float> a(*p);
-  float o = a.load();
+template <typename F>
+static inline F atomicAdd(F* p, F v) {  // float / double; blocks run on several host threads
+  std::atomic_ref<F> a(*p);
+  F o = a.load();
   while (!a.compare_exchange_weak(o, o + v)) {
   }
   return o;

@@ -1,8 +1,9 @@
 // Whole-path host emulation of the Sepconv trunk (TEST INFRASTRUCTURE): csrc/sepconv.cu (weight loading, the forward
 // schedule, buffer sizing, the C ABI), csrc/sepconv_elem.cu and csrc/streamconv.cu's packer + CUDA-core checker kernel,
-// compiled for the host through cuda_shim.h.  What is NOT emulated: the tcgen05 kernel (the checker stands in, exactly as
-// `vfi_sepconv_debug_set_ref(ctx, 1)` selects on a GPU) and ops.cu's tiled separable-convolution kernel (restated below).
-#include "cuda_shim.h"
+// and csrc/ops.cu's tiled separable-convolution kernel, compiled for the host through cuda_shim_block.h (blocks on host
+// threads, threads as fibers).  What is NOT emulated: the tcgen05 kernel (the checker stands in, exactly as
+// `vfi_sepconv_debug_set_ref(ctx, 1)` selects on a GPU).
+#include "cuda_shim_block.h"
 
 #include <string>
 
@@ -18,29 +19,10 @@ void set_error(const std::string& s) { g_err = s; }
 CtxInfo ctx_info(::vfi_ctx*) { return CtxInfo{0, 148, nullptr, nullptr, nullptr}; }
 SepState*& ctx_sep(::vfi_ctx* c) { return c->sep; }
 void ctx_add_launches(::vfi_ctx* c, int n) { c->launches += n; }
-// sepconv_out, cupy_ops/sepconv.py:86-117 (the role of ops.cu's kernel in this emulation)
-cudaError_t launch_sepconv(const float* in, const float* ver, const float* hor, float* out, int N, int C, int H, int W, int Kv,
-                           int Kh, cudaStream_t) {
-  const int Hp = H + Kv - 1, Wp = W + Kh - 1;
-  for (int n = 0; n < N; ++n)
-    for (int c = 0; c < C; ++c)
-      for (int y = 0; y < H; ++y)
-        for (int x = 0; x < W; ++x) {
-          double acc = 0.0;
-          for (int fy = 0; fy < Kv; ++fy) {
-            const float v = ver[(((size_t)n * Kv + fy) * H + y) * W + x];
-            const float* row = in + (((size_t)n * C + c) * Hp + y + fy) * Wp + x;
-            double r = 0.0;
-            for (int fx = 0; fx < Kh; ++fx) r += (double)row[fx] * hor[(((size_t)n * Kh + fx) * H + y) * W + x];
-            acc += r * v;
-          }
-          out[(((size_t)n * C + c) * H + y) * W + x] = (float)acc;
-        }
-  return cudaSuccess;
-}
 }  // namespace vfi
 extern "C" const char* vfi_last_error(void) { return vfi::g_err.c_str(); }
 
+#include "../../comfyui-frame-interpolation_b200/csrc/ops.cu"
 #include "../../comfyui-frame-interpolation_b200/csrc/sepconv_elem.cu"
 #include "../../comfyui-frame-interpolation_b200/csrc/streamconv.cu"
 #include "../../comfyui-frame-interpolation_b200/csrc/sepconv.cu"

@@ -1,8 +1,8 @@
 """The WHOLE Sepconv path of the library on the CPU: csrc/sepconv.cu (vfi_sepconv_load + vfi_sepconv_forward: tensor order,
 PReLU slopes, buffer sizing, the schedule with its crop-after-conv decoder path), csrc/sepconv_elem.cu and streamconv.cu's
 packer + CUDA-core checker kernel, compiled for the host (tests/host_emu) and compared with the output of the unmodified
-reference Network (tests/golden/sepconv_net_21x30.npz).  The tcgen05 kernel and ops.cu's tiled op kernel are not part of
-this (the checker kernel / a plain restatement stand in); both have their own GPU tests."""
+reference Network (tests/golden/sepconv_net_21x30.npz).  ops.cu's tiled
+separable-convolution kernel runs too; only the tcgen05 kernel is replaced (by the checker kernel with the same weights)."""
 import ctypes as C
 import math
 import os
@@ -28,7 +28,7 @@ def emu(tmp_path_factory):
         pytest.skip("g++ / CUDA headers not available")
     so = str(tmp_path_factory.mktemp("emu") / "libsepfull.so")
     src = os.path.join(ROOT, "tests", "host_emu", "sepconv_full_emu.cpp")
-    r = subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-I" + CUDA_INC, "-o", so, src],
+    r = subprocess.run(["g++", "-O2", "-std=c++20", "-shared", "-fPIC", "-pthread", "-I" + CUDA_INC, "-o", so, src],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     return C.CDLL(so)

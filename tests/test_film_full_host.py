@@ -34,9 +34,9 @@ def emu(tmp_path_factory):
     return C.CDLL(so)
 
 
-def test_film_whole_path_on_host_matches_reference(emu, pkg):
+@pytest.mark.parametrize("name", ["film_net_64x64_rand", "film_net_72x104"])   # the second: odd level sizes down the pyramid
+def test_film_whole_path_on_host_matches_reference(emu, pkg, name):
     from cfi_b200.engine import film_state_dict_names
-    name = "film_net_64x64_rand"
     cfg = film_cases()[name]
     ref = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))["out"]).permute(0, 2, 3, 1)
     sd = OF.synthetic_state_dict(cfg["seed"], cfg["flow_gain"])

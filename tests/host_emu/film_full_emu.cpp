@@ -49,4 +49,18 @@ int emu_film(const float* const* tensors, const int64_t* numel, int n_tensors, c
   vfi::film_destroy(ctx.film);
   return rc ? rc : 1000 + ctx.launches;
 }
+
+// two pairs (frames 0-1 and 1-2) in ONE call: out [2, H, W, 3]
+int emu_film_batch2(const float* const* tensors, const int64_t* numel, int n_tensors, const float* frames, int H, int W, int C,
+                    float* out) {
+  vfi_ctx ctx;
+  int rc = vfi_film_load(&ctx, tensors, numel, n_tensors, VFI_OPERAND_F16);
+  if (rc) return rc;
+  rc = vfi_film_debug_set_ref(&ctx, 1);
+  if (rc) return rc;
+  const int32_t f0[2] = {0, 1}, f1[2] = {1, 2};
+  rc = vfi_film_forward(&ctx, frames, 3, H, W, C, f0, f1, 2, 1, out, nullptr);
+  vfi::film_destroy(ctx.film);
+  return rc;
+}
 }

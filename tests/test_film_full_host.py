@@ -71,3 +71,23 @@ def test_film_whole_path_on_host_matches_reference(emu, pkg, name):
     assert worst <= 0.05, worst
     assert rc - 1000 == 192
     assert psnr >= 55.0, psnr   # fp16 operands / activations vs the fp32 reference (GPU, same checker: 64.9 dB at 72x104)
+
+
+def test_film_two_pairs_in_one_call_on_host(emu, pkg):
+    """B = 2 (images indexed k * B + pair through every buffer of the schedule) equals the single-pair call, bit for bit; frames have 4 channels (the alpha channel is skipped by gather_rgb)."""
+    from cfi_b200.engine import film_state_dict_names
+    sd = OF.synthetic_state_dict(5)
+    hold = [sd[n].contiguous() for n in film_state_dict_names()]
+    ptrs = (C.c_void_p * len(hold))(*[t.data_ptr() for t in hold])
+    numel = (C.c_int64 * len(hold))(*[t.numel() for t in hold])
+    fr = torch.cat([OF.synthetic_clip(3, 64, 64, seed=9), torch.ones(3, 64, 64, 1)], -1).contiguous()
+    both = torch.zeros(2, 64, 64, 3)
+    emu.vfi_last_error.restype = C.c_char_p
+    assert emu.emu_film_batch2(ptrs, numel, len(hold), C.c_void_p(fr.data_ptr()), 64, 64, 4, C.c_void_p(both.data_ptr())) == 0, \
+        emu.vfi_last_error()
+    for i in (1,):   # the second pair is the one whose images sit at the non-trivial indices (1 and B + 1)
+        one = torch.zeros(1, 64, 64, 3)
+        pair = fr[i:i + 2].contiguous()
+        rc = emu.emu_film(ptrs, numel, len(hold), C.c_void_p(pair.data_ptr()), 64, 64, 4, 1, C.c_void_p(one.data_ptr()), None)
+        assert rc >= 1000, emu.vfi_last_error()
+        assert torch.equal(both[i], one[0]), i

@@ -197,3 +197,57 @@ def test_rife_host_pipeline_ring_and_shards_on_host(emu):
                                          C.c_float(1.0), C.c_void_p(out.data_ptr()))
     assert rc != 0
     assert emu.vfi_destroy(ctx) == 0
+
+
+@pytest.mark.parametrize("sf", [1.0, 2.0])
+def test_rife_flow_state_on_host(emu, sf):
+    """vfi_rife46_debug_state: the accumulated full-resolution flow / mask of the last pass (implicit on the product path;
+    with scale_factor 2 every level has already been folded into the dense planes) against the oracle's final flow and
+    mask, in pixels."""
+    sd = O.synthetic_state_dict(11, 3.0)
+    names, code = _engine_names("4.6")
+    hold = [sd[n].contiguous().float() for n in names]
+    ptrs = (C.c_void_p * len(hold))(*[t.data_ptr() for t in hold])
+    numel = (C.c_int64 * len(hold))(*[t.numel() for t in hold])
+    ctx = C.c_void_p()
+    assert emu.vfi_create(0, C.byref(ctx)) == 0
+    assert emu.vfi_rife_load(ctx, code, ptrs, numel, len(hold), 0) == 0, emu.vfi_last_error()
+    fr = O.synthetic_clip(2, 64, 64, seed=5).contiguous()
+    f0, f1, ts = np.zeros(1, np.int32), np.ones(1, np.int32), np.asarray([0.5], np.float32)
+    out = torch.zeros(1, 64, 64, 3)
+    vp = lambda x: x.ctypes.data_as(C.c_void_p)   # noqa: E731
+    assert emu.vfi_rife46_forward(ctx, C.c_void_p(fr.data_ptr()), 2, 64, 64, 3, vp(f0), vp(f1), vp(ts), 1, C.c_float(sf),
+                                  C.c_void_p(out.data_ptr()), None) == 0, emu.vfi_last_error()
+    hp, wp = C.c_int(), C.c_int()
+    flow = torch.zeros(1, 64, 64, 4)
+    mask = torch.zeros(1, 64, 64)
+    assert emu.vfi_rife46_debug_state(ctx, C.c_void_p(flow.data_ptr()), C.c_void_p(mask.data_ptr()), 1, C.byref(hp),
+                                      C.byref(wp)) == 0, emu.vfi_last_error()
+    assert (hp.value, wp.value) == (64, 64)
+    assert emu.vfi_destroy(ctx) == 0
+    taps = {}
+    x = fr.permute(0, 3, 1, 2)
+    O.ifnet46_forward(sd, x[0:1], x[1:2], torch.tensor([0.5]).view(1, 1, 1, 1), [v / sf for v in (8, 4, 2, 1)], taps)
+    want_f, want_m = taps["flow3"].permute(0, 2, 3, 1), taps["mask3"][:, 0]
+    assert float(want_f.abs().max()) > 2.0                       # a few pixels of motion
+    assert (flow - want_f).abs().max().item() <= 0.05            # fp16 conv operands: hundredths of a pixel
+    assert (mask - want_m).abs().max().item() <= 0.05
+
+
+def test_load_refuses_a_wrong_checkpoint(emu):
+    sd = O.synthetic_state_dict(0, 1.0)
+    names, code = _engine_names("4.6")
+    hold = [sd[n].contiguous().float() for n in names]
+    ptrs = (C.c_void_p * len(hold))(*[t.data_ptr() for t in hold])
+    numel = (C.c_int64 * len(hold))(*[t.numel() for t in hold])
+    ctx = C.c_void_p()
+    assert emu.vfi_create(0, C.byref(ctx)) == 0
+    assert emu.vfi_rife_load(ctx, 47, ptrs, numel, len(hold), 0) != 0      # 4.6 tensors offered as arch 4.7
+    assert len(emu.vfi_last_error()) > 0
+    out = torch.zeros(1, 64, 64, 3)
+    fr = torch.zeros(2, 64, 64, 3)
+    f0, f1, ts = np.zeros(1, np.int32), np.ones(1, np.int32), np.asarray([0.5], np.float32)
+    vp = lambda x: x.ctypes.data_as(C.c_void_p)   # noqa: E731
+    assert emu.vfi_rife46_forward(ctx, C.c_void_p(fr.data_ptr()), 2, 64, 64, 3, vp(f0), vp(f1), vp(ts), 1, C.c_float(1.0),
+                                  C.c_void_p(out.data_ptr()), None) != 0   # forward before a successful load
+    assert emu.vfi_destroy(ctx) == 0

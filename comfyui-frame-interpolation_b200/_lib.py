@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(HERE, "libvfi_b200.so")
 SYMBOLS = [
     "vfi_last_error", "vfi_version", "vfi_create", "vfi_destroy", "vfi_launch_count", "vfi_set_batch",
     "vfi_rife46_load", "vfi_rife_load", "vfi_rife46_forward", "vfi_rife46_interpolate_host", "vfi_warp_bilinear_border",
-    "vfi_softsplat_sum", "vfi_costvol_l1", "vfi_corr_dot", "vfi_sepconv", "vfi_adacof", "vfi_edt_pass",
+    "vfi_softsplat_sum", "vfi_softsplat_weighted", "vfi_costvol_l1", "vfi_corr_dot", "vfi_sepconv", "vfi_adacof", "vfi_edt_pass",
     "vfi_rife46_debug_layer", "vfi_rife46_debug_state", "vfi_rife46_layer_plan", "vfi_sync",
     "vfi_film_load", "vfi_film_forward", "vfi_film_debug_set_ref", "vfi_film_debug_conv", "vfi_film_layer_plan",
     "vfi_film_last_macs", "vfi_film_debug_pack_host",
@@ -46,6 +46,7 @@ def lib():
     L.vfi_rife46_interpolate_host.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, f32, vp]
     L.vfi_warp_bilinear_border.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
     L.vfi_softsplat_sum.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    L.vfi_softsplat_weighted.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, vp]
     L.vfi_costvol_l1.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
     L.vfi_corr_dot.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
     L.vfi_sepconv.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]

@@ -49,6 +49,63 @@ __global__ void softsplat_sum_kernel(const float* __restrict__ in, const float* 
   }
 }
 
+// Fused avg / linear / soft splat (the wrapper modes of cupy_ops/softsplat.py:382-435 without their temporaries): the source
+// pixel's weight (1, metric or exp(metric)) is applied on the fly, the weights are splatted into a one-channel `norm` plane
+// next to the C channels, and a second kernel divides.  Same association of the products as the reference's
+// softsplat_out on cat(in * weight, weight): (in * weight) rounded first, then times the corner weight.
+__global__ void softsplat_weighted_kernel(const float* __restrict__ in, const float* __restrict__ flow,
+                                          const float* __restrict__ metric, int mode, float* __restrict__ out,
+                                          float* __restrict__ norm, int N, int C, int H, int W) {
+  const size_t hw = (size_t)H * W;
+  const size_t total = (size_t)N * hw;
+  for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(id % W);
+    const int y = (int)((id / W) % H);
+    const int n = (int)(id / hw);
+    const size_t pix = (size_t)y * W + x;
+    const float fx = (float)x + __ldg(flow + ((size_t)n * 2 + 0) * hw + pix);
+    const float fy = (float)y + __ldg(flow + ((size_t)n * 2 + 1) * hw + pix);
+    if (!isfinite(fx) || !isfinite(fy)) continue;
+    const float ws = mode == 0 ? 1.f : (mode == 1 ? __ldg(metric + (size_t)n * hw + pix) : expf(__ldg(metric + (size_t)n * hw + pix)));
+    const int x0 = (int)floorf(fx), y0 = (int)floorf(fy);
+    const int x1 = x0 + 1, y1 = y0 + 1;
+    const float wnw = ((float)x1 - fx) * ((float)y1 - fy);
+    const float wne = (fx - (float)x0) * ((float)y1 - fy);
+    const float wsw = ((float)x1 - fx) * (fy - (float)y0);
+    const float wse = (fx - (float)x0) * (fy - (float)y0);
+    const bool inx0 = x0 >= 0 && x0 < W, inx1 = x1 >= 0 && x1 < W;
+    const bool iny0 = y0 >= 0 && y0 < H, iny1 = y1 >= 0 && y1 < H;
+    const float* src = in + (size_t)n * C * hw + pix;
+    float* dst = out + (size_t)n * C * hw;
+    float* nd = norm + (size_t)n * hw;
+    if (inx0 && iny0) atomicAdd(nd + (size_t)y0 * W + x0, ws * wnw);
+    if (inx1 && iny0) atomicAdd(nd + (size_t)y0 * W + x1, ws * wne);
+    if (inx0 && iny1) atomicAdd(nd + (size_t)y1 * W + x0, ws * wsw);
+    if (inx1 && iny1) atomicAdd(nd + (size_t)y1 * W + x1, ws * wse);
+    for (int c = 0; c < C; ++c) {
+      const float v = __ldg(src + (size_t)c * hw) * ws;
+      float* d = dst + (size_t)c * hw;
+      if (inx0 && iny0) atomicAdd(d + (size_t)y0 * W + x0, v * wnw);
+      if (inx1 && iny0) atomicAdd(d + (size_t)y0 * W + x1, v * wne);
+      if (inx0 && iny1) atomicAdd(d + (size_t)y1 * W + x0, v * wsw);
+      if (inx1 && iny1) atomicAdd(d + (size_t)y1 * W + x1, v * wse);
+    }
+  }
+}
+
+// eps: 0 addeps (norm + 1e-7, the default), 1 zeroeps (0 -> 1), 2 clipeps (max(norm, 1e-7))  - softsplat.py:418-431
+__global__ void softsplat_normalize_kernel(float* __restrict__ out, const float* __restrict__ norm, int eps, int N, int C,
+                                           size_t hw) {
+  const size_t total = (size_t)N * C * hw;
+  for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
+    const size_t pix = id % hw;
+    const int n = (int)(id / (hw * C));
+    float d = norm[(size_t)n * hw + pix];
+    d = eps == 0 ? d + 0.0000001f : (eps == 1 ? (d == 0.f ? 1.f : d) : fmaxf(d, 0.0000001f));
+    out[id] = out[id] / d;
+  }
+}
+
 // kDot = false: mean_c |one - two(shifted)|, outside -> mean_c |one|      (costvol)
 // kDot = true : mean_c one * two(shifted), outside -> 0                   (correlation, zero padded)
 template <bool kDot>
@@ -280,6 +337,19 @@ cudaError_t launch_softsplat_sum(const float* in, const float* flow, float* out,
   if (e != cudaSuccess) return e;
   const size_t total = (size_t)N * H * W;
   VFI_LAUNCH((softsplat_sum_kernel), grid_for(total, 256), 256, 0, st, in, flow, out, N, C, H, W);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_softsplat_weighted(const float* in, const float* flow, const float* metric, int mode, int eps, float* out,
+                                      float* norm, int N, int C, int H, int W, cudaStream_t st) {
+  if (mode < 0 || mode > 2 || eps < 0 || eps > 2 || (mode != 0 && metric == nullptr)) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(out, 0, (size_t)N * C * H * W * sizeof(float), st);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(norm, 0, (size_t)N * H * W * sizeof(float), st);
+  if (e != cudaSuccess) return e;
+  VFI_LAUNCH((softsplat_weighted_kernel), grid_for((size_t)N * H * W, 256), 256, 0, st, in, flow, metric, mode, out, norm, N, C, H,
+             W);
+  VFI_LAUNCH((softsplat_normalize_kernel), grid_for((size_t)N * C * H * W, 256), 256, 0, st, out, norm, eps, N, C, (size_t)H * W);
   return cudaGetLastError();
 }
 

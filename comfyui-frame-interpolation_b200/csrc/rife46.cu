@@ -930,6 +930,15 @@ int vfi_softsplat_sum(vfi_ctx* c, const float* in, const float* flow, float* out
   return VFI_OK;
 }
 
+int vfi_softsplat_weighted(vfi_ctx* c, const float* in, const float* flow, const float* metric, int mode, int eps, float* out,
+                           float* norm, int N, int C, int H, int W, void* stream) {
+  if (!c || !in || !flow || !out || !norm) return fail(VFI_E_INVALID, "null argument");
+  if (mode < 0 || mode > 2 || eps < 0 || eps > 2 || (mode != 0 && !metric)) return fail(VFI_E_INVALID, "softsplat mode / eps / metric");
+  CK(launch_softsplat_weighted(in, flow, metric, mode, eps, out, norm, N, C, H, W, static_cast<cudaStream_t>(stream)));
+  c->launches += 2;
+  return VFI_OK;
+}
+
 int vfi_costvol_l1(vfi_ctx* c, const float* one, const float* two, float* out, int N, int C, int H, int W,
                    void* stream) {
   if (!c || !one || !two || !out || N < 1 || C < 1 || H < 1 || W < 1) return fail(VFI_E_INVALID, "bad argument");

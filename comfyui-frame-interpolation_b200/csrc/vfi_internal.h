@@ -158,6 +158,8 @@ cudaError_t launch_warp(const float* img, const float* flow, float* out, int B, 
 
 cudaError_t launch_softsplat_sum(const float* in, const float* flow, float* out, int N, int C, int H, int W,
                                  cudaStream_t st);
+cudaError_t launch_softsplat_weighted(const float* in, const float* flow, const float* metric, int mode, int eps, float* out,
+                                      float* norm, int N, int C, int H, int W, cudaStream_t st);
 cudaError_t launch_volume81(bool dot, const float* one, const float* two, float* out, int N, int C, int H, int W,
                             cudaStream_t st);
 cudaError_t launch_sepconv(const float* in, const float* ver, const float* hor, float* out, int N, int C, int H, int W,

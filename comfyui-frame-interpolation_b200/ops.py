@@ -53,6 +53,33 @@ class softsplat_func:
         return out
 
 
+import os as _os
+
+# VFI_SPLAT_FUSED=1: avg / linear / soft through the fused kernels (vfi_softsplat_weighted) instead of the reference's
+# cat -> splat -> slice -> divide chain around vfi_softsplat_sum.  Off by default until its first GPU run has been read.
+_FUSED = _os.environ.get("VFI_SPLAT_FUSED", "0") == "1"
+
+
+def softsplat_fused(tenIn, tenFlow, tenMetric, strMode: str):
+    """avg / linear / soft (+ -addeps / -zeroeps / -clipeps) in two launches, no temporaries."""
+    base = strMode.split("-")[0]
+    mode = {"avg": 0, "linear": 1, "soft": 2}[base]
+    variant = strMode.split("-")[1] if "-" in strMode else "addeps"
+    eps = {"addeps": 0, "zeroeps": 1, "clipeps": 2}[variant]
+    if mode == 0:
+        tenIn, tenFlow = _prep(tenIn, tenFlow)
+        tenMetric = None
+    else:
+        tenIn, tenFlow, tenMetric = _prep(tenIn, tenFlow, tenMetric)
+    n, c, h, w = tenIn.shape
+    out = torch.empty_like(tenIn)
+    norm = tenIn.new_empty(n, 1, h, w)
+    check(lib().vfi_softsplat_weighted(_context(tenIn.device), tenIn.data_ptr(), tenFlow.data_ptr(),
+                                       None if tenMetric is None else tenMetric.data_ptr(), mode, eps, out.data_ptr(),
+                                       norm.data_ptr(), n, c, h, w, _stream(tenIn)))
+    return out
+
+
 def softsplat(tenIn, tenFlow, tenMetric, strMode: str):
     """cupy_ops/softsplat.py:382-435."""
     assert strMode.split("-")[0] in ["sum", "avg", "linear", "soft"]
@@ -64,6 +91,8 @@ def softsplat(tenIn, tenFlow, tenMetric, strMode: str):
         assert tenMetric is not None
     if strMode.split("-")[0] == "soft":
         assert tenMetric is not None
+    if _FUSED and strMode != "sum":
+        return softsplat_fused(tenIn, tenFlow, tenMetric, strMode)
     if strMode == "avg":
         tenIn = torch.cat([tenIn, tenIn.new_ones([tenIn.shape[0], 1, tenIn.shape[2], tenIn.shape[3]])], 1)
     elif strMode.split("-")[0] == "linear":

@@ -100,6 +100,11 @@ int vfi_warp_bilinear_border(vfi_ctx* ctx, const float* img, const float* flow, 
  *   vfi_sepconv       : sepconv_out (cupy_ops/sepconv.py:86-117): in [N,C,H+Kv-1,W+Kh-1], ver [N,Kv,H,W], hor [N,Kh,H,W] */
 int vfi_softsplat_sum(vfi_ctx* ctx, const float* in, const float* flow, float* out, int N, int C, int H, int W,
                       void* stream);
+/* Fused form of the wrapper modes of softsplat() (cupy_ops/softsplat.py:382-435): mode 0 avg, 1 linear, 2 soft (weight 1,
+ * metric, exp(metric) per source pixel), eps 0 addeps (default) / 1 zeroeps / 2 clipeps; `norm` is a caller-provided
+ * [N,1,H,W] scratch plane (the splatted weights); out [N,C,H,W] = splat(in * weight) / f(norm).  metric may be NULL for avg. */
+int vfi_softsplat_weighted(vfi_ctx* ctx, const float* in, const float* flow, const float* metric, int mode, int eps, float* out,
+                           float* norm, int N, int C, int H, int W, void* stream);
 int vfi_costvol_l1(vfi_ctx* ctx, const float* one, const float* two, float* out, int N, int C, int H, int W,
                    void* stream);
 int vfi_corr_dot(vfi_ctx* ctx, const float* first, const float* second, float* out, int N, int C, int H, int W,

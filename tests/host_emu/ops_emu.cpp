@@ -14,6 +14,10 @@ extern "C" {
 int emu_softsplat(const float* in, const float* flow, float* out, int N, int C, int H, int W) {
   return (int)vfi::launch_softsplat_sum(in, flow, out, N, C, H, W, nullptr);
 }
+int emu_softsplat_weighted(const float* in, const float* flow, const float* metric, int mode, int eps, float* out, float* norm,
+                          int N, int C, int H, int W) {
+  return (int)vfi::launch_softsplat_weighted(in, flow, metric, mode, eps, out, norm, N, C, H, W, nullptr);
+}
 int emu_volume81(int dot, const float* one, const float* two, float* out, int N, int C, int H, int W) {
   return (int)vfi::launch_volume81(dot != 0, one, two, out, N, C, H, W, nullptr);
 }

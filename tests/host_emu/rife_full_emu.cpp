@@ -12,6 +12,7 @@ namespace vfi {
 void film_destroy(FilmState*) {}
 void sepconv_destroy(SepState*) {}
 cudaError_t launch_softsplat_sum(const float*, const float*, float*, int, int, int, int, cudaStream_t) { return cudaErrorNotSupported; }
+cudaError_t launch_softsplat_weighted(const float*, const float*, const float*, int, int, float*, float*, int, int, int, int, cudaStream_t) { return cudaErrorNotSupported; }
 cudaError_t launch_volume81(bool, const float*, const float*, float*, int, int, int, int, cudaStream_t) { return cudaErrorNotSupported; }
 cudaError_t launch_sepconv(const float*, const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t) { return cudaErrorNotSupported; }
 cudaError_t launch_adacof(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int, cudaStream_t) { return cudaErrorNotSupported; }

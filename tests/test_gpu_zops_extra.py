@@ -30,3 +30,18 @@ def test_batch_edt_gpu(pkg):
     out = ops.batch_edt(img.cuda()).cpu()
     assert out.shape == img.shape
     assert (out - ops_ref.batch_edt(img)).abs().max().item() <= 1e-4
+
+
+@pytest.mark.parametrize("mode", ["avg", "linear", "soft", "soft-zeroeps", "linear-clipeps"])
+def test_softsplat_fused_gpu(pkg, mode):
+    """vfi_softsplat_weighted (VFI_SPLAT_FUSED=1 makes ops.softsplat use it) vs the oracle at a GMFSS-like shape."""
+    from cfi_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 32, 96, 128, generator=g)
+    flow = (torch.rand(2, 2, 96, 128, generator=g) - 0.5) * 20
+    metric = torch.rand(2, 1, 96, 128, generator=g) * 2 - (0.5 if mode.startswith("soft") else -0.2)
+    m = None if mode == "avg" else metric
+    out = ops.softsplat_fused(x.cuda(), flow.cuda(), None if m is None else m.cuda(), mode).cpu()
+    ref = ops_ref.softsplat(x, flow, m, mode)
+    ok = ref.abs() < 1e4
+    assert (out - ref)[ok].abs().max().item() <= 2e-3 * max(1.0, float(ref[ok].abs().max()))

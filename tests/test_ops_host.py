@@ -60,3 +60,20 @@ def test_sepconv_tiled_kernel(emu):
     assert emu.emu_sepconv(vp(x), vp(ver), vp(hor), vp(out), 1, 4, h, w, k, k) == 0
     ref = ops_ref.sepconv(x, ver, hor)
     assert (out - ref).abs().max().item() <= 2e-4 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("mode", ["avg", "linear", "soft", "soft-zeroeps", "linear-clipeps"])
+def test_softsplat_fused_modes(emu, mode):
+    """vfi_softsplat_weighted (two launches, no temporaries) == the reference's cat -> splat -> divide chain."""
+    g = torch.Generator().manual_seed(len(mode))
+    x = torch.randn(2, 6, 17, 21, generator=g)
+    flow = (torch.rand(2, 2, 17, 21, generator=g) - 0.5) * 8
+    metric = torch.rand(2, 1, 17, 21, generator=g) * 2 - (0.5 if mode.startswith("soft") else -0.2)
+    base = mode.split("-")[0]
+    m = {"avg": 0, "linear": 1, "soft": 2}[base]
+    e = {"addeps": 0, "zeroeps": 1, "clipeps": 2}[mode.split("-")[1] if "-" in mode else "addeps"]
+    out, norm = torch.full_like(x, 3.0), torch.full((2, 1, 17, 21), 3.0)
+    assert emu.emu_softsplat_weighted(vp(x), vp(flow), None if m == 0 else vp(metric), m, e, vp(out), vp(norm), 2, 6, 17, 21) == 0
+    ref = ops_ref.softsplat(x, flow, None if m == 0 else metric, mode)
+    ok = ref.abs() < 1e4                       # addeps: untouched targets are 0 / 1e-7 in both, tiny norms blow up alike
+    assert (out - ref)[ok].abs().max().item() <= 2e-3 * max(1.0, float(ref[ok].abs().max()))

@@ -1,4 +1,5 @@
-"""CPU oracles: RIFE 4.6 / 4.7 / 4.17 / 4.26 (rife46.py), FILM (film.py), Sepconv (sepconv.py), the op primitives (ops_ref.py).
+"""CPU oracles: RIFE 4.6 / 4.7 / 4.17 / 4.26 (rife46.py), FILM (film.py), Sepconv (sepconv.py), GMFSS Fortuna
+(gmflow.py + gmfss.py; target only, the GPU path is not built), the op primitives (ops_ref.py).
 TEST INFRASTRUCTURE ONLY.
 
 Nothing under ``oracle/`` is product code.  Only ``tests/``, ``__graft_entry__.smoke()``

@@ -1,4 +1,4 @@
-"""CPU restatement (fp32) of GMFSS Fortuna (union) WITHOUT its flow network - SURVEY.md section 8 row a11.
+"""CPU restatement (fp32) of GMFSS Fortuna (union) around its flow network (oracle/gmflow.py) - SURVEY.md section 8 row a11.
 TEST INFRASTRUCTURE ONLY; GMFSS is not built in this repo yet, this file pins most of its target.
 
 Follows ``vfi_models/gmfss_fortuna/GMFSS_Fortuna_union_arch.py`` of Fannovel16/ComfyUI-Frame-Interpolation @ 26545cc:
@@ -6,9 +6,11 @@ Follows ``vfi_models/gmfss_fortuna/GMFSS_Fortuna_union_arch.py`` of Fannovel16/C
 :985-991 / ``bilinear_sample`` :955-983), ``FeatureNet`` :1470-1500, ``GridNet`` :1582-1688 with its blocks :1503-1579,
 and ``Model.reuse`` / ``Model.inference`` :1726-1857.  The IFNet inside is ``oracle.rife46.ifnet46_forward`` (arch 4.6), the
 one custom op ``softsplat`` is ``oracle.ops_ref.softsplat`` (pinned to the reference's own kernel by
-tests/test_ops_ref_pinned.py).  NOT restated: ``GMFlow`` (:35-1372, the transformer flow network) - ``reuse`` below takes
-the two flows as inputs; the goldens of tools/make_golden_gmfss.py store the unmodified reference's flows so that everything
-downstream of GMFlow is pinned (tests/test_oracle_gmfss.py: metrics from the golden flows, the frame from the golden flows).
+tests/test_ops_ref_pinned.py), ``GMFlow`` (:35-1372, the transformer flow network) is ``oracle.gmflow.gmflow``.
+``reuse_from_flows`` takes the two flows as inputs: the goldens of tools/make_golden_gmfss.py store the unmodified
+reference's flows, so everything downstream of GMFlow is pinned on its own (tests/test_oracle_gmfss.py: metrics and the frame
+from the golden flows), GMFlow on its own (the flows), and ``interpolate`` - the whole model as
+``CommonModelInference.forward`` (gmfss_fortuna/__init__.py:41-77) runs it at scale 1 - end to end (the frame from the images).
 """
 from __future__ import annotations
 
@@ -17,6 +19,7 @@ from typing import Dict, Tuple
 import torch
 import torch.nn.functional as F
 
+from . import gmflow as GF
 from . import ops_ref
 from . import rife46 as R
 
@@ -144,3 +147,21 @@ def inference(sds: Dict[str, dict], img0, img1, flow01, flow10, metric0, metric1
     out = gridnet(sds["fusionnet"], torch.cat([I1t, rife, I2t], 1), torch.cat([a1, b1], 1), torch.cat([a2, b2], 1),
                   torch.cat([a3, b3], 1))
     return torch.clamp(out, 0, 1)
+
+
+def reuse(sds: Dict[str, dict], img0, img1):
+    """Model.reuse :1726-1782 at scale 1.0: both GMFlow directions on the half-size frames, then reuse_from_flows."""
+    h0 = F.interpolate(img0, scale_factor=0.5, mode="bilinear", align_corners=False)
+    h1 = F.interpolate(img1, scale_factor=0.5, mode="bilinear", align_corners=False)
+    flow01, flow10 = GF.gmflow(sds["flownet"], h0, h1), GF.gmflow(sds["flownet"], h1, h0)
+    return (flow01, flow10) + tuple(reuse_from_flows(sds, img0, img1, flow01, flow10))
+
+
+def interpolate(sds: Dict[str, dict], frame0, frame1, timestep: float) -> torch.Tensor:
+    """CommonModelInference.forward, gmfss_fortuna/__init__.py:41-77, scale 1: pad to multiples of 64 at the bottom / right,
+    reuse + inference, crop."""
+    h, w = frame0.shape[2], frame0.shape[3]
+    ph, pw = ((h - 1) // 64 + 1) * 64, ((w - 1) // 64 + 1) * 64
+    i0, i1 = F.pad(frame0, (0, pw - w, 0, ph - h)), F.pad(frame1, (0, pw - w, 0, ph - h))
+    flow01, flow10, m0, m1, f1, f2 = reuse(sds, i0, i1)
+    return inference(sds, i0, i1, flow01, flow10, m0, m1, f1, f2, timestep)[:, :, :h, :w]

@@ -932,8 +932,9 @@ int vfi_softsplat_sum(vfi_ctx* c, const float* in, const float* flow, float* out
 
 int vfi_softsplat_weighted(vfi_ctx* c, const float* in, const float* flow, const float* metric, int mode, int eps, float* out,
                            float* norm, int N, int C, int H, int W, void* stream) {
-  if (!c || !in || !flow || !out || !norm) return fail(VFI_E_INVALID, "null argument");
+  if (!c || !in || !flow || !out || !norm || N < 1 || C < 1 || H < 1 || W < 1) return fail(VFI_E_INVALID, "bad argument");
   if (mode < 0 || mode > 2 || eps < 0 || eps > 2 || (mode != 0 && !metric)) return fail(VFI_E_INVALID, "softsplat mode / eps / metric");
+  CK(cudaSetDevice(c->device));
   CK(launch_softsplat_weighted(in, flow, metric, mode, eps, out, norm, N, C, H, W, static_cast<cudaStream_t>(stream)));
   c->launches += 2;
   return VFI_OK;
@@ -966,16 +967,19 @@ int vfi_sepconv(vfi_ctx* c, const float* in, const float* ver, const float* hor,
 
 int vfi_adacof(vfi_ctx* c, const float* in, const float* weight, const float* offset_i, const float* offset_j, float* out, int N,
                int C, int Hin, int Win, int F, int dilation, int Ho, int Wo, void* stream) {
-  if (!c || !in || !weight || !offset_i || !offset_j || !out) return fail(VFI_E_INVALID, "null argument");
+  if (!c || !in || !weight || !offset_i || !offset_j || !out || N < 1 || C < 1 || Ho < 1 || Wo < 1)
+    return fail(VFI_E_INVALID, "bad argument");
   if (F < 1 || dilation < 1 || Hin - ((F - 1) * dilation + 1) != Ho - 1 || Win - ((F - 1) * dilation + 1) != Wo - 1)
     return fail(VFI_E_INVALID, "adacof: input size must be output size + (F - 1) * dilation (adacof.py:274-279)");
+  CK(cudaSetDevice(c->device));
   CK(launch_adacof(in, weight, offset_i, offset_j, out, N, C, Hin, Win, F, dilation, Ho, Wo, static_cast<cudaStream_t>(stream)));
   c->launches += 1;
   return VFI_OK;
 }
 
 int vfi_edt_pass(vfi_ctx* c, const float* data, float* out, int bs, int h, int w, float diam2, void* stream) {
-  if (!c || !data || !out) return fail(VFI_E_INVALID, "null argument");
+  if (!c || !data || !out || bs < 1 || h < 1 || w < 1) return fail(VFI_E_INVALID, "bad argument");
+  CK(cudaSetDevice(c->device));
   CK(launch_edt_pass(data, out, bs, h, w, diam2, static_cast<cudaStream_t>(stream)));
   c->launches += 1;
   return VFI_OK;

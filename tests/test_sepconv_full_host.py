@@ -1,7 +1,7 @@
 """The WHOLE Sepconv path of the library on the CPU: csrc/sepconv.cu (vfi_sepconv_load + vfi_sepconv_forward: tensor order,
 PReLU slopes, buffer sizing, the schedule with its crop-after-conv decoder path), csrc/sepconv_elem.cu and streamconv.cu's
 packer + CUDA-core checker kernel, compiled for the host (tests/host_emu) and compared with the output of the unmodified
-reference Network (tests/golden/sepconv_net_21x30.npz).  ops.cu's tiled
+reference Network (tests/golden/sepconv_net_*.npz, three sizes).  ops.cu's tiled
 separable-convolution kernel runs too; only the tcgen05 kernel is replaced (by the checker kernel with the same weights)."""
 import ctypes as C
 import math
@@ -34,9 +34,11 @@ def emu(tmp_path_factory):
     return C.CDLL(so)
 
 
-def test_sepconv_whole_path_on_host_matches_reference(emu, pkg):
+@pytest.mark.parametrize("name", ["sepconv_net_21x30", "sepconv_net_48x64", "sepconv_net_45x54"])
+def test_sepconv_whole_path_on_host_matches_reference(emu, pkg, name):
+    """21x30: small and odd; 48x64: every encoder row even (no crop in the decoder); 45x54: odd height only, odd rows at
+    different pyramid levels in the two axes."""
     from cfi_b200.engine import sepconv_state_dict_names
-    name = "sepconv_net_21x30"
     cfg = sepconv_cases()[name]
     ref = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))["out"]).permute(0, 2, 3, 1)
     sd = OS.synthetic_state_dict(cfg["seed"])

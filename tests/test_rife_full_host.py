@@ -46,7 +46,7 @@ def _engine_names(arch):
 @pytest.mark.parametrize("name", ["ifnet_64x64_gain4", "ifnet47_64x128_gain3", "ifnet417_64x128_gain3",
                                   "ifnet426_128x128_gain3", "ifnet_64x64_sf2", "ifnet_64x64_sf4", "ifnet47_64x64_sf2",
                                   "ifnet47_64x64_sf4", "ifnet417_64x64_sf2", "ifnet426_64x64_sf2",
-                                  "ifnet426_64x64_sf4"])
+                                  "ifnet426_64x64_sf4", "ifnet_40x100_sf2", "ifnet426_40x100_sf4"])
 def test_rife_whole_path_on_host_matches_reference(emu, name):
     cfg = cases()[name]
     arch = cfg.get("arch", "4.6")

@@ -75,6 +75,10 @@ def cases():
         # node scale_factor 2 / 4 (rife/__init__.py:156-160: scale_list / scale_factor): the last one / two blocks run at
         # scale 0.5 / 0.25, i.e. on an UP-scaled input
         "ifnet_64x64_sf2": dict(kind="ifnet", seed=40, gain=2.0, h=64, w=64, ts=(0.5,), clip_seed=41, scale_factor=2.0),
+        # not square, padded (40x100 -> 64x128): rows / columns of the up-scaled blocks must not be interchangeable
+        "ifnet_40x100_sf2": dict(kind="ifnet", seed=54, gain=2.0, h=40, w=100, ts=(0.35,), clip_seed=55, scale_factor=2.0),
+        "ifnet426_40x100_sf4": dict(kind="ifnet", arch="4.26", seed=56, gain=2.0, h=40, w=100, ts=(0.5,), clip_seed=57,
+                                    scale_factor=4.0),
         "ifnet_64x64_sf4": dict(kind="ifnet", seed=42, gain=2.0, h=64, w=64, ts=(0.4,), clip_seed=43, scale_factor=4.0),
         "ifnet47_64x64_sf2": dict(kind="ifnet", arch="4.7", seed=44, gain=2.0, h=64, w=64, ts=(0.5,), clip_seed=45, scale_factor=2.0),
         "ifnet47_64x64_sf4": dict(kind="ifnet", arch="4.7", seed=46, gain=2.0, h=64, w=64, ts=(0.6,), clip_seed=47,

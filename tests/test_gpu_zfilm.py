@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.mark.gpu
 def test_film_gpu_check_subprocess():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "film_gpu_check.py"), "--quick"],
-                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+                       capture_output=True, text=True, timeout=420, cwd=ROOT)
     tail = (r.stdout[-6000:] + "\n--- stderr ---\n" + r.stderr[-3000:])
     assert r.returncode == 0, tail
 
@@ -26,6 +26,6 @@ def test_film_gpu_check_subprocess():
                           "with a skip list) has not been run on a GPU yet: r01 ended with 0 GPU-minutes", strict=False)
 def test_film_gpu_check_full_subprocess():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "film_gpu_check.py")],
-                       capture_output=True, text=True, timeout=1200, cwd=ROOT)
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
     tail = (r.stdout[-8000:] + "\n--- stderr ---\n" + r.stderr[-3000:])
     assert r.returncode == 0, tail

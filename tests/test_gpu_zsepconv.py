@@ -17,6 +17,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
                    strict=False)
 def test_sepconv_gpu_check_subprocess():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sepconv_gpu_check.py")],
-                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+                       capture_output=True, text=True, timeout=420, cwd=ROOT)
     tail = (r.stdout[-6000:] + "\n--- stderr ---\n" + r.stderr[-3000:])
     assert r.returncode == 0, tail

@@ -33,6 +33,31 @@ def test_no_gpu_is_a_loud_error(pkg):
     assert len(lib().vfi_last_error()) > 0
 
 
+def test_null_context_is_refused_before_any_cuda_call(pkg):
+    """Error behaviour of the boundary without a GPU: every entry point that takes a context refuses a NULL one with
+    VFI_E_INVALID (-1) and leaves a message; nothing is launched (include/vfi_b200.h: error convention)."""
+    from cfi_b200._lib import lib
+    L = lib()
+    names = ["vfi_set_batch", "vfi_sync", "vfi_rife_load", "vfi_rife46_load", "vfi_rife46_forward", "vfi_rife46_interpolate_host",
+             "vfi_warp_bilinear_border", "vfi_softsplat_sum", "vfi_softsplat_weighted", "vfi_costvol_l1", "vfi_corr_dot",
+             "vfi_sepconv", "vfi_adacof", "vfi_edt_pass", "vfi_film_load", "vfi_film_forward", "vfi_sepconv_load",
+             "vfi_sepconv_forward"]
+    for name in names:
+        fn = getattr(L, name)
+        assert fn.argtypes, name
+        args = []
+        for t in fn.argtypes:                       # NULL for every pointer (the context first), 1 / 1.0 for scalars
+            if t in (ctypes.c_float, ctypes.c_double):
+                args.append(1.0)
+            elif t in (ctypes.c_int, ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t):
+                args.append(1)
+            else:
+                args.append(None)
+        rc = fn(*args)
+        assert rc == -1, (name, rc)
+        assert len(L.vfi_last_error()) > 0, name
+
+
 def test_node_surface_matches_reference(pkg):
     """rife/__init__.py:36-75 and root __init__.py:23-47."""
     import cfi_b200 as P

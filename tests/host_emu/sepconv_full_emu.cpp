@@ -46,4 +46,18 @@ int emu_sepconv(const float* const* tensors, const int64_t* numel, int n_tensors
   vfi::sepconv_destroy(ctx.sep);
   return rc ? rc : 1000 + ctx.launches;   // 1000 + number of launches on success
 }
+
+// several pairs of one clip in ONE call (the C ABI takes up to 16): frames [n_frames][H][W][C], pairs (f0[i], f1[i]),
+// out [n_pairs][H][W][3]; 4-channel frames exercise the channel stride
+int emu_sepconv_pairs(const float* const* tensors, const int64_t* numel, int n_tensors, const float* frames, int n_frames, int H,
+                      int W, int C, const int32_t* f0, const int32_t* f1, int n_pairs, float* out) {
+  vfi_ctx ctx;
+  int rc = vfi_sepconv_load(&ctx, tensors, numel, n_tensors, VFI_OPERAND_F16);
+  if (rc) return rc;
+  rc = vfi_sepconv_debug_set_ref(&ctx, 1);
+  if (rc) return rc;
+  rc = vfi_sepconv_forward(&ctx, frames, n_frames, H, W, C, f0, f1, n_pairs, out, nullptr);
+  vfi::sepconv_destroy(ctx.sep);
+  return rc ? rc : 1000 + ctx.launches;
+}
 }

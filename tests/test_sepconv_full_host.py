@@ -73,3 +73,29 @@ def test_sepconv_whole_path_on_host_matches_reference(emu, pkg, name):
         err = float((coef[k] - want).abs().max())
         signal = float((want - bias).abs().max())       # what the trunk contributes on top of the bias
         assert err <= 0.02 * signal + 2e-3, (key, err, signal)
+
+
+def test_sepconv_three_pairs_in_one_call_on_host(emu, pkg):
+    """n_pairs = 3 in one vfi_sepconv_forward (per-pair statistics, batch strides of every buffer, a repeated and a reversed
+    pair, 4-channel frames): each output equals the oracle run on that pair alone."""
+    from cfi_b200.engine import sepconv_state_dict_names
+    sd = OS.synthetic_state_dict(5)
+    hold = [sd[n].contiguous() for n in sepconv_state_dict_names()]
+    ptrs = (C.c_void_p * len(hold))(*[t.data_ptr() for t in hold])
+    numel = (C.c_int64 * len(hold))(*[t.numel() for t in hold])
+    h, w = 19, 26
+    g = torch.Generator().manual_seed(77)
+    fr = torch.rand(3, h, w, 4, generator=g)
+    fr[1] = fr[1] * 0.5 + 0.4            # different mean / std per pair
+    fr[2] = fr[2] * 0.2
+    f0 = (C.c_int32 * 3)(0, 1, 2)
+    f1 = (C.c_int32 * 3)(1, 2, 0)
+    out = torch.zeros(3, h, w, 3)
+    rc = emu.emu_sepconv_pairs(ptrs, numel, len(hold), C.c_void_p(fr.data_ptr()), 3, h, w, 4, f0, f1, 3, C.c_void_p(out.data_ptr()))
+    emu.vfi_last_error.restype = C.c_char_p
+    assert rc >= 1000, (rc, emu.vfi_last_error())
+    x = fr[..., :3].permute(0, 3, 1, 2).contiguous()
+    for i, (a, b) in enumerate(((0, 1), (1, 2), (2, 0))):
+        ref = OS.network_forward(sd, x[a:a + 1], x[b:b + 1])[0].permute(1, 2, 0)
+        err = float((out[i] - ref).abs().max())
+        assert err < 2e-3, (i, err)

@@ -21,7 +21,7 @@ def emu(tmp_path_factory):
         pytest.skip("g++ / CUDA headers not available")
     so = str(tmp_path_factory.mktemp("emu") / "libopsx.so")
     src = os.path.join(ROOT, "tests", "host_emu", "ops_extra_emu.cpp")
-    r = subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-pthread", "-I" + CUDA_INC, "-o", so, src],
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-pthread", "-I" + CUDA_INC, "-o", so, src] + os.environ.get("VFI_EMU_CXXFLAGS", "").split(),
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     return C.CDLL(so)

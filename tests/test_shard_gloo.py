@@ -51,7 +51,8 @@ def _worker(rank, world, port, q):
 
     bufs = shard.forward_and_gather(run_slice, local, counts, dist, nchunks=2)
     if rank == 0:
-        q.put((out, torch.cat([b_[:c] for b_, c in zip(bufs, counts)], 0)))
+        # numpy arrays pickle by value; torch tensors would travel as shared-memory handles that die with this process
+        q.put((out.numpy(), torch.cat([b_[:c] for b_, c in zip(bufs, counts)], 0).numpy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -64,7 +65,7 @@ def test_sharded_equals_single_process(pkg):
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got, got_pipelined = q.get(timeout=120)
+    got, got_pipelined = (torch.from_numpy(a) for a in q.get(timeout=120))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0

@@ -169,5 +169,5 @@ def test_errors_are_loud(pkg):
     with pytest.raises(VfiError):
         eng.forward(fr, [0], [5], [0.5])            # frame index out of range
     with pytest.raises(VfiError):
-        eng.forward(fr, [0], [1], [0.5], scale_factor=2.0)   # up-scaled blocks: not implemented, says so
+        eng.forward(fr, [0], [1], [0.5], scale_factor=3.0)   # not one of the widget's values 0.25 / 0.5 / 1 / 2 / 4
     eng.close()

@@ -22,8 +22,6 @@ def test_film_gpu_check_subprocess():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(reason="the full form (1984-channel fusion layers alone, 128x192 and white-noise nets, multiplier-4 node "
-                          "with a skip list) has not been run on a GPU yet: r01 ended with 0 GPU-minutes", strict=False)
 def test_film_gpu_check_full_subprocess():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "film_gpu_check.py")],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)

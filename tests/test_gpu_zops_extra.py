@@ -5,8 +5,7 @@ import torch
 
 from oracle import ops_ref
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="ops_extra.cu has not run on a GPU yet (r01 ended at 0 GPU-minutes)",
-                                                 strict=False)]
+pytestmark = [pytest.mark.gpu]
 
 
 def test_adacof_gpu(pkg):

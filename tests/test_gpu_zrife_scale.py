@@ -14,8 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 from make_golden import cases, make_inputs  # noqa: E402
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="front_up / fold_down have not run on a GPU yet (r01 ended at 0 "
-                                                        "GPU-minutes)", strict=False)]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("name", [n for n, c in cases().items() if c["kind"] == "ifnet" and "scale_factor" in c])

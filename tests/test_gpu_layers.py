@@ -52,14 +52,14 @@ def test_warp_primitive(engines):
 
 
 IMPLS = [pytest.param(1, id="ref"), pytest.param(0, id="tc")]  # CUDA-core checker / tcgen05 kernel
+# (impl, dtype) pairs: the tcgen05 kernel in both operand types, the CUDA-core checker in one (no skipped combinations)
+IMPL_DTYPE = [pytest.param(1, "float16", id="ref-float16"), pytest.param(0, "float16", id="tc-float16"),
+              pytest.param(0, "bfloat16", id="tc-bfloat16")]
 
 
-@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
 @pytest.mark.parametrize("block", [3, 2, 1, 0])
-@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("impl,dtype", IMPL_DTYPE)
 def test_resconv(engines, block, dtype, impl):
-    if impl == 1 and dtype != "float16":
-        pytest.skip("CUDA-core checker: one dtype is enough")
     sd, e = engines
     eng, c, tdt = e[dtype], BLOCK_C[block], _tdt(dtype)
     g = torch.Generator().manual_seed(block)
@@ -87,13 +87,10 @@ def test_resconv_many_tiles(engines, block):
     assert rel_err(out.cpu().float(), ref) < _tol("float16")
 
 
-@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
 @pytest.mark.parametrize("block", [3, 1, 0])
-@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("impl,dtype", IMPL_DTYPE)
 def test_conv0(engines, block, dtype, impl):
     """conv0.0 then conv0.1 (both stride 2) on space-to-depth inputs."""
-    if impl == 1 and dtype != "float16":
-        pytest.skip("CUDA-core checker: one dtype is enough")
     sd, e = engines
     eng, c, tdt = e[dtype], BLOCK_C[block], _tdt(dtype)
     cin = 7 if block == 0 else 12
@@ -118,13 +115,10 @@ def test_conv0(engines, block, dtype, impl):
     assert rel_err(y1.cpu().float(), ref1) < _tol(dtype)
 
 
-@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
 @pytest.mark.parametrize("block", [3, 2, 1, 0])
-@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("impl,dtype", IMPL_DTYPE)
 def test_lastconv(engines, block, dtype, impl):
     """ConvTranspose2d(c,24,4,2,1)+PixelShuffle(2) as one 3x3 tap conv producing 4x4 sub-pixel patches."""
-    if impl == 1 and dtype != "float16":
-        pytest.skip("CUDA-core checker: one dtype is enough")
     sd, e = engines
     eng, c, tdt = e[dtype], BLOCK_C[block], _tdt(dtype)
     g = torch.Generator().manual_seed(20 + block)
@@ -163,11 +157,8 @@ def engines426(pkg):
         v.close()
 
 
-@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
-@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("impl,dtype", IMPL_DTYPE)
 def test_block4_resconv_and_conv0(engines426, dtype, impl):
-    if impl == 1 and dtype != "float16":
-        pytest.skip("CUDA-core checker: one dtype is enough")
     sd, e = engines426
     eng, c, tdt = e[dtype], 32, _tdt(dtype)
     g = torch.Generator().manual_seed(77)
@@ -194,14 +185,11 @@ def test_block4_resconv_and_conv0(engines426, dtype, impl):
     assert rel_err(y1.cpu().float(), ref1) < _tol(dtype)
 
 
-@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
 @pytest.mark.parametrize("block", [4, 3, 2, 1, 0])
-@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("impl,dtype", IMPL_DTYPE)
 def test_lastconv426(engines426, block, dtype, impl):
     """ConvTranspose2d(c,52,4,2,1)+PixelShuffle(2): channels 0-4 (flow, mask) as fp32 planes, 5-12 (features) as a
     16-bit [B,4H,4W,8] tensor from a second tap conv over the same input."""
-    if impl == 1 and dtype != "float16":
-        pytest.skip("CUDA-core checker: one dtype is enough")
     sd, e = engines426
     eng, c, tdt = e[dtype], BLOCK_C426[block], _tdt(dtype)
     g = torch.Generator().manual_seed(120 + block)

@@ -10,9 +10,15 @@ interpolates its own 64-frame shard of a (63*N+1)-frame clip (frame pairs are in
 and for N > 1 the interpolated frames are gathered on rank 0 over NCCL inside the timed region (the path's
 only exchange step).
   value : whole-job interpolated frames/s with the clip already resident in HBM (CUDA events, max over ranks)
-  e2e   : same metric through the C-ABI host call (pinned host buffers, H2D + D2H inside the timed region)
+  e2e   : same metric through the plugin call a ComfyUI user makes - RIFE_VFI().vfi(ckpt, frames, multiplier=2) - with a
+          PAGEABLE [64,1080,1920,3] fp32 input tensor and the node's own output tensor; H2D + D2H (and the host-side
+          staging and pass-through copies) inside the timed region.  e2e_capi is the same through the bare C-ABI call
+          on pre-pinned buffers (the r01 figure).
   roofline     : the dominant kernel (tcgen05 tap-conv, block-3 ResConv layer) timed alone, against the measured
-                 bf16 tensor peak in MEASURED_PEAKS.json; plus the HBM-bound warp kernel as roofline_hbm
+                 bf16 tensor peak in MEASURED_PEAKS.json
+  roofline_hbm : the HBM-bound kernels the step actually runs (block-3 / block-2 `front`, `final`), timed with CUDA
+                 events on their launching stream inside real passes (vfi_rife_profile), against measured HBM bandwidth
+  psnr_db      : the GPU's interpolated frames against the CPU leg's output on the CPU leg's sample of the same clip
   cpu_baseline : the CPU oracle port (oracle/rife46.py == the reference's PyTorch-CPU path) on the
                  host cores, on a bounded sample of the same clip (rank 0, N = 1 only)
 --impl reference times that CPU port alone (all host threads), same metric / config.
@@ -129,7 +135,31 @@ def _pick_threads(sd):
     return best, ncpu
 
 
-def cpu_port_fps(clip, sd, steps, warmup, min_seconds=0.0):
+def bind_to_gpu_numa_node(local_rank):
+    """Multi-process runs: pin this rank's threads (and, by first touch, its host buffers) to the NUMA node its GPU hangs
+    off.  r01: eight unbound ranks streaming pinned H2D + D2H at once reached 14.9 GB/s per direction per GPU against 41
+    alone (GPU0-3 sit on node 0, GPU4-7 on node 1).  Returns a description for the JSON line, or None."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return {"gpu": local_rank, "pci": bdf, "numa_node": node, "cpus": len(allowed)}
+    except Exception:
+        return None
+
+
+def cpu_port_fps(clip, sd, steps, warmup, min_seconds=0.0, keep=None):
     """The CPU restatement of the reference path (== reference PyTorch-CPU eager, fp32) on the host cores.
     Runs `steps` timed repetitions, and more until `min_seconds` of timed CPU work (at most 16 repetitions)."""
     import torch
@@ -141,8 +171,10 @@ def cpu_port_fps(clip, sd, steps, warmup, min_seconds=0.0):
     i = 0
     while i < warmup + steps or (sum(times) < min_seconds and len(times) < 16):
         t0 = time.perf_counter()
-        O.rife_vfi(sd, sample, multiplier=2, arch=CPU_ARCH)
+        res = O.rife_vfi(sd, sample, multiplier=2, arch=CPU_ARCH)
         dt = time.perf_counter() - t0
+        if keep is not None:
+            keep["out"] = res
         if i >= warmup:
             times.append(dt)
         i += 1
@@ -175,7 +207,7 @@ def main():
     config = {"workload": f"RIFE {a.arch}, 2x multiplier, {a.frames}-frame synthetic 1080p clip per GPU (BASELINE configs[1])",
               "resolution": [H, W], "frames_per_gpu": a.frames, "pairs_per_gpu": a.frames - 1,
               "padded": [1088, 1920], "weights": "seeded synthetic (oracle.synthetic_state_dict(0)); no checkpoint ships",
-              "parallelism": f"frame-pair shards x{a.gpus}; each rank's outputs gathered to rank 0 by NCCL in 4 chunks, overlapped with the next chunk's compute" if a.gpus > 1 else "1 GPU",
+              "parallelism": f"frame-pair shards x{a.gpus}; each rank's outputs gathered to rank 0 by NCCL in 16 chunks, overlapped with the next chunk's compute" if a.gpus > 1 else "1 GPU",
               "l2": "inputs larger than L2 (1.6 GB clip, 1.6 GB output per step)"}
 
     sd = O.synthetic_state_dict(0, arch=a.arch)
@@ -206,6 +238,7 @@ def main():
     from cfi_b200 import _lib as cfi_lib
 
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -240,7 +273,7 @@ def main():
         if dist is None:
             eng.forward(dev_clip, f0, f1, ts, out=dev_out)
         else:  # chunks of the shard are gathered to rank 0 while the next chunk computes (shard.forward_and_gather)
-            shard.forward_and_gather(run_slice, dev_out, [npairs] * world, dist, dst=0, nchunks=4, gathered=gather_list)
+            shard.forward_and_gather(run_slice, dev_out, [npairs] * world, dist, dst=0, nchunks=16, gathered=gather_list)
 
     for _ in range(a.warmup):
         step_device()
@@ -265,7 +298,7 @@ def main():
     ms_dev = e0.elapsed_time(e1)
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
 
-    # ---- end to end through the host C-ABI call ("e2e")
+    # ---- end to end through the bare C-ABI call on pre-pinned buffers ("e2e_capi", the r01 figure)
     host_in = clip.contiguous().pin_memory()
     host_out = torch.empty((npairs, H, W, 3), dtype=torch.float32).pin_memory()
     for _ in range(max(1, min(a.warmup, 2))):
@@ -275,21 +308,57 @@ def main():
     for _ in range(a.steps):
         eng.interpolate_host(host_in, f0, f1, ts, host_out)
     barrier()
-    sec_e2e = time.perf_counter() - t0
+    sec_capi = time.perf_counter() - t0
     # parity spot check inside the bench: host path == device path on this rank's data
     same = bool(torch.equal(host_out[:2], dev_out[:2].cpu()))
+    del host_in, host_out
+
+    # ---- per-kernel-group device times inside real passes (CUDA events on the launching stream, one profiled step)
+    prof = None
+    if rank == 0:
+        eng.profile(True)
+        eng.forward(dev_clip, f0, f1, ts, out=dev_out)
+        prof = eng.profile_read()
+        eng.profile(False)
+
+    # ---- end to end through the plugin call ("e2e"): pageable input tensor, node-owned output tensor
+    import tempfile
+    from cfi_b200 import node as N
+    ckpt = {"4.6": "rife46.pth", "4.7": "rife47.pth", "4.17": "rife417.pth", "4.26": "rife426.pth"}[a.arch]
+    ckpt_dir = tempfile.mkdtemp(prefix="vfi_bench_ckpt_")
+    os.makedirs(os.path.join(ckpt_dir, "rife"), exist_ok=True)
+    torch.save(sd, os.path.join(ckpt_dir, "rife", ckpt))
+    os.environ["VFI_CKPT_DIR"] = ckpt_dir
+    node = N.RIFE_VFI()
+    pageable = clip.contiguous()          # an ordinary CPU tensor, as ComfyUI hands an IMAGE over
+    assert not pageable.is_pinned()
+    res = None
+    for _ in range(max(2, min(a.warmup, 3))):   # (two warm-ups: the output blocks of the caching host allocator exist)
+        (res,) = node.vfi(ckpt, pageable, multiplier=2, dtype=a.dtype, batch_size=a.batch)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        (res,) = node.vfi(ckpt, pageable, multiplier=2, dtype=a.dtype, batch_size=a.batch)
+    barrier()
+    sec_e2e = time.perf_counter() - t0
+    node_ok = bool(tuple(res.shape) == (2 * nf - 1, H, W, 3) and torch.equal(res[1], dev_out[0].cpu())
+                   and torch.equal(res[0], clip[0]) and torch.equal(res[2], clip[1]))
+    node_out_pinned = bool(res.is_pinned())
+    del res
+    N.clear_model_cache()
 
     # ---- reduce timings: max over ranks
-    tt = torch.tensor([ms_dev, sec_e2e * 1e3], dtype=torch.float64, device="cuda")
+    tt = torch.tensor([ms_dev, sec_e2e * 1e3, sec_capi * 1e3], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e = tt.tolist()
+    ms_dev, ms_e2e, ms_capi = tt.tolist()
 
     if rank == 0:
         peaks = _peaks()
         total = npairs * world
         value = total * a.steps / (ms_dev / 1e3)
         e2e = total * a.steps / (ms_e2e / 1e3)
+        e2e_capi = total * a.steps / (ms_capi / 1e3)
 
         # ---- roofline of the dominant kernel, timed alone with CUDA events (flush L2 between launches)
         tdt = torch.bfloat16 if a.dtype == "bfloat16" else torch.float16
@@ -320,32 +389,48 @@ def main():
                     "algorithmic_bytes": 2.0 * B * 272 * 480 * 64 * 2,
                     "peak_source": peaks["source"] + ", burst figure (kernel timed alone)",
                     "launch_ms": k_ms, "flops_per_launch": k_flops}
-        # HBM-bound primitive: stand-alone warp on the padded 1080p frame, float4 pixels (C=4)
-        img = torch.rand(B, 1088, 1920, 4, device="cuda")
-        # piecewise-smooth flow of a few pixels (what optical flow looks like): low-res noise, bilinearly up-sampled
-        fl = torch.nn.functional.interpolate(4 * torch.randn(B, 2, 34, 60, device="cuda"), size=(1088, 1920),
-                                             mode="bilinear", align_corners=False).permute(0, 2, 3, 1).contiguous()
-        tl = []
-        for i in range(13):
-            flush.zero_()
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
-            eng.warp(img, fl)
-            a1.record()
-            torch.cuda.synchronize()
-            if i >= 3:
-                tl.append(a0.elapsed_time(a1))
-        w_ms = sum(tl) / len(tl)
-        w_bytes = B * 1088 * 1920 * (4 + 2 + 4) * 4.0
-        roofline_hbm = {"kernel": "warp_kernel<4> (backward bilinear warp, [B,1088,1920,4] fp32, smooth +-4 px flow)", "bound": "hbm",
-                        "achieved": w_bytes / (w_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": w_bytes / (w_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
-                        "peak_source": peaks["source"], "launch_ms": w_ms, "bytes_per_launch": w_bytes}
-        del img, fl, x, y, flush
+        # HBM-bound kernels ON the path, from the profiled step (ids: 10 * block + 0 = front, 90 = final).  Bytes per
+        # padded pixel and task that the kernel has to move in this schedule: block-3 front =
+        # two half4 image gathers (16) + accumulated flow / mask (20) + the block-2 level at 1/4 of the pixels (5) +
+        # the 16-channel 16-bit block input (32); block-2 front = the image gathers at full resolution (16) + the two
+        # coarse levels (1.56) + the block input at half resolution (32 / 4) + the accumulated flow / mask it stores (20);
+        # final = flow / mask (20) + block-2 level (5) + block-3 level (20) + two float4 image gathers (32) + RGB out (12,
+        # on the cropped frame).
+        px = 1088 * 1920
+        passes = {k: v[1] for k, v in prof.items()}
+        def per_pair_ms(gid):
+            return prof[gid][0] / npairs if gid in prof else None
+        hbm_rows = []
+        if a.arch == "4.6":
+            for gid, name, bpp in ((30, "front<block 3> (flow up-sample + 2 warps + resample + concat -> conv0.0 input)", 16 + 20 + 5 + 32),
+                                   (90, "final (flow up-sample + 2 warps + sigmoid blend + crop + clamp)", 20 + 5 + 20 + 32 + 12 * (H * W) / px),
+                                   (20, "front<block 2> (same at scale 2; stores the accumulated flow plane)", 16 + 1.5625 + 32 / 4 + 20)):
+                ms = per_pair_ms(gid)
+                if ms:
+                    gbs = bpp * px / (ms * 1e-3) / 1e9
+                    hbm_rows.append({"kernel": name, "ms_per_pair": ms, "bytes_per_pair": bpp * px, "achieved": gbs,
+                                     "frac": gbs / peaks["hbm_gbs"]})
+        roofline_hbm = {"bound": "hbm", "unit": "GB/s", "peak": peaks["hbm_gbs"], "peak_source": peaks["source"],
+                        "how": "CUDA events on the launching stream around each launch inside one profiled 63-pair step "
+                               "(vfi_rife_profile); bytes = what the kernel must read + write per pair in this schedule",
+                        "kernels": hbm_rows,
+                        "achieved": hbm_rows[0]["achieved"] if hbm_rows else None,
+                        "frac": hbm_rows[0]["frac"] if hbm_rows else None,
+                        "kernel": hbm_rows[0]["kernel"] if hbm_rows else None,
+                        # dram__bytes of the same launches: profiles/ (ncu --set full), per pass of 8 pairs
+                        "traffic": None}
+        groups = {str(k): {"ms_per_pair": v[0] / npairs, "spans": v[1]} for k, v in sorted(prof.items())}
+        del x, y, flush
 
         cpu = None
+        psnr_db = None
         if world == 1 and not a.no_cpu:
-            fps, sec, cores, ncpu, reps = cpu_port_fps(clip, sd, 0, 1, min_seconds=10.0)
+            keep = {}
+            fps, sec, cores, ncpu, reps = cpu_port_fps(clip, sd, 0, 1, min_seconds=10.0, keep=keep)
+            # parity at the quoted configuration: the CPU leg's interpolated frames (fp32 oracle = reference CPU path)
+            # against the GPU's frames for the same two pairs of the same clip
+            mids = keep["out"][1::2][: CPU_SAMPLE_FRAMES - 1]
+            psnr_db = float(O.psnr(dev_out[: CPU_SAMPLE_FRAMES - 1].cpu(), mids))
             cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{CPU_SAMPLE_FRAMES - 1} pairs of the same 1080p clip, 1 warm-up + {reps} timed repetitions "
                              f"({sec * reps:.1f} s of CPU work), oracle/rife46.py == reference PyTorch-CPU path, {cores} "
@@ -357,9 +442,13 @@ def main():
                 "dtype_note": "conv operands 16-bit, fp32 accumulate (TMEM); flow/mask/warp/blend fp32; PSNR>=50 dB "
                               "vs fp32 oracle enforced by tests/test_gpu_forward.py",
                 "data": "synthetic", "config": dict(config, batch=a.batch),
-                "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
+                "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / a.steps, "via": "RIFE_VFI.vfi (node call)",
+                        "input": "pageable CPU tensor [64,1080,1920,3] fp32", "output": "node-allocated" + (" (page-locked, torch caching host allocator)" if node_out_pinned else " (pageable)"),
                         "h2d_bytes_per_step": nf * H * W * 3 * 4, "d2h_bytes_per_step": npairs * H * W * 3 * 4,
-                        "host_equals_device_path": same},
+                        "node_output_matches_device_path": node_ok},
+                "e2e_capi": {"value": e2e_capi, "unit": UNIT, "ms_per_step": ms_capi / a.steps,
+                             "via": "vfi_rife46_interpolate_host on pre-pinned buffers", "host_equals_device_path": same},
+                "psnr_db": psnr_db, "numa": numa, "kernel_groups": groups,
                 "gpu_launches": launches, "lib": cfi_lib.lib().vfi_version().decode(), "clocks": clocks,
                 "model_tflops": value * FLOPS_PER_FRAME / 1e12 if a.arch == "4.6" else None,
                 "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu}

@@ -1,0 +1,128 @@
+// Host-side staging for the HOST-pointer entry points (vfi_*_interpolate_host): pageable caller memory <-> a small
+// ring of pinned buffers <-> the GPU, so that a ComfyUI IMAGE tensor (pageable) moves at PCIe rate without pinning the
+// caller's clip (the reference's loop does blocking `.to(device)` / `.cpu()` per batch, rife/__init__.py:195-207).
+//   * CopyPool: a few persistent threads that split one large memcpy (one thread copies ~10 GB/s; PCIe Gen5 needs ~45).
+//   * PinnedBuf: a cudaHostAlloc'ed buffer that is kept by the context and only ever grows.
+// Plain C++ (no CUDA kernels); the pipelines themselves live next to their models (rife46.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <condition_variable>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace vfi {
+
+class CopyPool {
+ public:
+  explicit CopyPool(int nthreads) {
+    if (nthreads < 1) nthreads = 1;
+    for (int i = 0; i < nthreads; ++i) workers_.emplace_back([this, i, nthreads] { run(i, nthreads); });
+  }
+  ~CopyPool() {
+    {
+      std::lock_guard<std::mutex> l(m_);
+      stop_ = true;
+      ++gen_;
+    }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  CopyPool(const CopyPool&) = delete;
+  CopyPool& operator=(const CopyPool&) = delete;
+
+  // blocking; one caller at a time (each pipeline thread owns its pool)
+  void copy(void* dst, const void* src, size_t bytes) {
+    if (bytes < (1u << 20) || workers_.size() == 1) {  // not worth a hand-off
+      std::memcpy(dst, src, bytes);
+      return;
+    }
+    {
+      std::lock_guard<std::mutex> l(m_);
+      dst_ = static_cast<uint8_t*>(dst);
+      src_ = static_cast<const uint8_t*>(src);
+      bytes_ = bytes;
+      pending_ = (int)workers_.size();
+      ++gen_;
+    }
+    cv_.notify_all();
+    std::unique_lock<std::mutex> l(m_);
+    done_.wait(l, [this] { return pending_ == 0; });
+  }
+
+ private:
+  void run(int idx, int n) {
+    uint64_t seen = 0;
+    for (;;) {
+      uint8_t* d;
+      const uint8_t* s;
+      size_t bytes;
+      {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+        d = dst_;
+        s = src_;
+        bytes = bytes_;
+      }
+      // 4 KB-aligned chunk boundaries (whole pages per thread)
+      const size_t chunk = ((bytes + n - 1) / n + 4095) & ~(size_t)4095;
+      const size_t lo = std::min(bytes, chunk * idx), hi = std::min(bytes, chunk * (idx + 1));
+      if (hi > lo) std::memcpy(d + lo, s + lo, hi - lo);
+      {
+        std::lock_guard<std::mutex> l(m_);
+        if (--pending_ == 0) done_.notify_all();
+      }
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+  uint8_t* dst_ = nullptr;
+  const uint8_t* src_ = nullptr;
+  size_t bytes_ = 0;
+  int pending_ = 0;
+};
+
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    release();
+    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// true when `ptr` is page-locked memory CUDA knows (cudaHostAlloc / cudaHostRegister / torch pin_memory)
+inline bool is_pinned_host(const void* ptr) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+inline int env_int(const char* name, int dflt, int lo, int hi) {
+  const char* e = std::getenv(name);
+  if (!e || !*e) return dflt;
+  const int v = std::atoi(e);
+  return v < lo ? lo : (v > hi ? hi : v);
+}
+
+}  // namespace vfi

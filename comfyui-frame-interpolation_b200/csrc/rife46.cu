@@ -18,10 +18,13 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 
 #include "../../include/vfi_b200.h"
 #include "vfi_internal.h"
+#include "hoststage.h"
 
 namespace vfi {
 
@@ -97,6 +100,30 @@ void choose_split(TapConvLayer& L, const std::vector<int>& splits, int want_stag
   L.n_cta = L.n_total / best_split;
 }
 
+// CTA-pair form (tapconv.cu, cta_group::2): pair-split s covers n_epi = n_total / psp output channels, each CTA of the
+// pair holding half of them as its B rows (packed slices 2s and 2s+1).  Returns false when no split reaches
+// `want_stages` (the caller then keeps the single-CTA plan).  VFI_PAIR=0 switches the form off (A/B runs).
+bool choose_split_pair(TapConvLayer& L, const std::vector<int>& psplits, int want_stages) {
+  static const bool on = [] {
+    const char* e = std::getenv("VFI_PAIR");
+    return !(e && e[0] == '0');
+  }();
+  if (!on) return false;
+  const TapConvLayer keep = L;
+  for (int psp : psplits) {
+    if (L.n_total % (2 * psp)) continue;
+    const int n_epi = L.n_total / psp;
+    if ((n_epi & 15) || n_epi > 128) continue;
+    L.pair = 1;
+    L.nsplit = 2 * psp;
+    L.n_cta = n_epi / 2;
+    TapConvParams p{};
+    if (tapconv_plan(L, &p) >= want_stages) return true;
+  }
+  L = keep;
+  return false;
+}
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
@@ -145,6 +172,12 @@ struct vfi_ctx {
   bool last_have_base = false;
   DevBuf dbgF, dbgM;
   cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+  vfi::PinnedBuf pin_in, pin_out;
+  // per-kernel-group timing of the forward schedule (vfi_rife_profile): CUDA events recorded on the launching stream
+  // around each group while `profile` is set; read (and summed per group id) by vfi_rife_profile_read
+  bool profile = false;
+  struct ProfSpan { int id; cudaEvent_t e0, e1; };
+  std::vector<ProfSpan> prof_spans;  // pinned staging rings of the host-pointer path (pageable caller memory)
   vfi::FilmState* film = nullptr;  // FILM weights and workspace (film.cu)
   vfi::SepState* sep = nullptr;    // Sepconv weights and workspace (sepconv.cu)
 };
@@ -265,7 +298,12 @@ int build_resconv(vfi_ctx* c, TapConvLayer& L, int ch, const float* beta, const 
   L.epi_mode = EPI_RESCONV;
   const bool ring = want_ring(ch);
   set_taps_3x3(L, ch, ring);
-  choose_split(L, {1, 2, 3, 4, 6, 8, 12}, ring ? 2 : 3);
+  // CTA pairs where they halve the output-channel splits (c >= 96).  Measured at the 1080p geometry, batch 8
+  // (profiles/r02_b_layers_b8_{pair,nopair}.json): c = 96 60.4 -> 46.1 us, c = 128 33.8 -> 31.7, c = 192 29.7 -> 25.6; at
+  // c = 64, where a single CTA already holds all 64 columns, the pair is SLOWER (82.9 -> 91.2 us: half of every MMA's B
+  // operand then comes from the peer SM's shared memory), so the 64-channel layers stay single-CTA.
+  if (!(ch >= 96 && choose_split_pair(L, {1, 2, 3, 4, 6}, ring ? 2 : 3)))
+    choose_split(L, {1, 2, 3, 4, 6, 8, 12}, ring ? 2 : 3);
   // (conv(x) + b) * beta + x  ==  conv_{w*beta}(x) + b*beta + x : beta is folded into the packed weights (one 16-bit
   // rounding of w*beta instead of w) so the epilogue is a pure add
   auto wf = [&](int e, int ci, int n) -> float {  // e = kb * 9 + tap (kb = 0 unless ring), ci relative to the k-block
@@ -294,10 +332,14 @@ int build_lastconv(vfi_ctx* c, TapConvLayer& L, int ch, int cout, const float* w
   L.epi_mode = EPI_LASTCONV;
   const bool ring = want_ring(ch);
   set_taps_3x3(L, ch, ring);
-  choose_split(L, {1, 5}, 2);
-  if (ring && L.nsplit != 1) {  // the ring only pays when it keeps all 80 columns in one CTA (c = 128)
-    set_taps_3x3(L, ch, false);
+  // all 80 columns in one CTA pair (40 B rows each) only where single CTAs would need five splits (c = 192: 27.6 ->
+  // 19.5 us); elsewhere the single-CTA form is as fast or faster (c = 64: 93.2 vs 111.6 us, same measurement as above)
+  if (!(ch >= 192 && choose_split_pair(L, {1}, 2))) {
     choose_split(L, {1, 5}, 2);
+    if (ring && L.nsplit != 1) {  // the ring only pays when it keeps all 80 columns in one CTA (c = 128)
+      set_taps_3x3(L, ch, false);
+      choose_split(L, {1, 5}, 2);
+    }
   }
   auto oc_of = [](int n) {
     const int c5 = n >> 4, pos = n & 15, py = pos >> 2, px = pos & 3;
@@ -530,11 +572,31 @@ int forward_pass(vfi_ctx* c, const Geometry& g, const BatchTasks& tasks, int H, 
     if (g.s[i] <= 2) dense = i;
   bool have_base = false;
   int lo = 0;  // levels [lo, i) are not yet folded into F
+  // group ids of vfi_rife_profile: 10 * block + {0 front, 1 conv0.0, 2 conv0.1, 3 the 8 ResConvs, 4 lastconv(s)}, 90 final
+  auto span_begin = [&](int id) {
+    if (!c->profile) return;
+    vfi_ctx::ProfSpan sp{id, nullptr, nullptr};
+    cudaEventCreate(&sp.e0);
+    cudaEventCreate(&sp.e1);
+    cudaEventRecord(sp.e0, st);
+    c->prof_spans.push_back(sp);
+  };
+  auto span_end = [&]() {
+    if (c->profile) cudaEventRecord(c->prof_spans.back().e1, st);
+  };
+  // VFI_FLOW_STORE_LAST=1: the last block's front also stores the accumulated flow (r01 behaviour: `final` then adds
+  // one level).  Default 0: it does not - `final` adds the last TWO levels on the fly, which saves the 20 B/px store of
+  // the largest front for a quarter-resolution read in `final`.
+  static const bool store_last = [] {
+    const char* e = std::getenv("VFI_FLOW_STORE_LAST");
+    return e && e[0] == '1';
+  }();
   for (int i = 0; i < nb; ++i) {
     const int s = g.s[i];
     const int Hs = g.Hp * g.k[i] / s, Ws = g.Wp * g.k[i] / s;
     const void* pfeat = (c->arch == 426 && i > 0) ? c->tE[i - 1].p : nullptr;  // previous block's 8 feature channels
     const int ps = i > 0 ? g.s[i - 1] : 1;
+    span_begin(10 * i);
     if (g.k[i] > 1) {
       // up-scaled block: fold every level so far into the dense planes, build the k-times finer input from them
       if (i == 0) return fail(VFI_E_INVALID, "the first block cannot be up-scaled");
@@ -550,23 +612,35 @@ int forward_pass(vfi_ctx* c, const Geometry& g, const BatchTasks& tasks, int H, 
     } else if (i == 0 || i < dense) {
       LAUNCH(launch_front(c->op_type, c->arch, imgs, imgs_h, feats, feat_ch, pfeat, ps, fs, i, 0, nullptr, nullptr, nullptr,
                           nullptr, tasks, g.Hp, g.Wp, s, c->x.p, st));
+    } else if (i == nb - 1 && have_base && !store_last && i - lo + 1 <= 2) {
+      // last block: read the dense planes (+ the levels since), store nothing; `final` adds those levels and this one
+      LAUNCH(launch_front(c->op_type, c->arch, imgs, imgs_h, feats, feat_ch, pfeat, ps, fs, i, lo, F, M, nullptr, nullptr, tasks,
+                          g.Hp, g.Wp, s, c->x.p, st));
     } else {
       LAUNCH(launch_front(c->op_type, c->arch, imgs, imgs_h, feats, feat_ch, pfeat, ps, fs, i, lo, have_base ? F : nullptr,
                           have_base ? M : nullptr, F, M, tasks, g.Hp, g.Wp, s, c->x.p, st));
       have_base = true;
       lo = i;
     }
+    span_end();
+    span_begin(10 * i + 1);
     LAUNCH(launch_tapconv(c->layers[i][0], c->op_type, c->x.p, c->c00.p, nullptr, nullptr, B, Hs / 2, Ws / 2,
                           c->num_sms, false, st));
+    span_end();
+    span_begin(10 * i + 2);
     LAUNCH(launch_tapconv(c->layers[i][1], c->op_type, c->c00.p, c->featA.p, nullptr, nullptr, B, Hs / 4, Ws / 4,
                           c->num_sms, false, st));
+    span_end();
     void* a = c->featA.p;
     void* b = c->featB.p;
+    span_begin(10 * i + 3);
     for (int j = 0; j < 8; ++j) {
       LAUNCH(launch_tapconv(c->layers[i][2 + j], c->op_type, a, b, nullptr, nullptr, B, Hs / 4, Ws / 4, c->num_sms,
                             false, st));
       std::swap(a, b);
     }
+    span_end();
+    span_begin(10 * i + 4);
     LAUNCH(launch_tapconv(c->layers[i][10], c->op_type, a, nullptr, fs.f[i], fs.m[i], B, Hs / 4, Ws / 4, c->num_sms,
                           false, st));
     if (c->arch == 426 && i + 1 < nb)  // the 8 feature channels of lastconv, for the next block's input
@@ -576,8 +650,11 @@ int forward_pass(vfi_ctx* c, const Geometry& g, const BatchTasks& tasks, int H, 
       LAUNCH(launch_fold_down(fs.f[i], fs.m[i], g.k[i], F, M, B, g.Hp, g.Wp, fs.mask_replace, st));
       lo = i + 1;
     }
+    span_end();
   }
+  span_begin(90);
   LAUNCH(launch_final(imgs, fs, lo, have_base ? F : nullptr, have_base ? M : nullptr, tasks, g.Hp, g.Wp, H, W, out, st));
+  span_end();
   c->last_fs = fs;
   c->last_lo = lo;
   c->last_have_base = have_base;
@@ -637,6 +714,8 @@ int vfi_destroy(vfi_ctx* c) {
     c->tM[i].release();
     c->tE[i].release();
   }
+  c->pin_in.release();
+  c->pin_out.release();
   if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
   if (c->s_comp) cudaStreamDestroy(c->s_comp);
   if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
@@ -649,6 +728,51 @@ int64_t vfi_launch_count(const vfi_ctx* c) { return c ? c->launches : 0; }
 int vfi_set_batch(vfi_ctx* c, int batch) {
   if (!c || batch < 1 || batch > kMaxBatch) return fail(VFI_E_INVALID, "batch must be in [1,16]");
   c->batch = batch;
+  return VFI_OK;
+}
+
+// Per-group device times of the forward schedule: CUDA events on the launching stream around each kernel group of every
+// pass run while profiling is on (the groups and their ids are listed in forward_pass).  Off by default: the event
+// records break the dependent-launch chaining between groups, so the timed bench steps run without it.
+int vfi_rife_profile(vfi_ctx* c, int enable) {
+  if (!c) return fail(VFI_E_INVALID, "null ctx");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  for (auto& sp : c->prof_spans) {
+    cudaEventDestroy(sp.e0);
+    cudaEventDestroy(sp.e1);
+  }
+  c->prof_spans.clear();
+  c->profile = enable != 0;
+  return VFI_OK;
+}
+
+// Synchronises, then sums the recorded spans per group id: ids[i], total_ms[i], count[i] for up to `cap` groups; returns
+// the number of groups through *n_out and clears the record.
+int vfi_rife_profile_read(vfi_ctx* c, int32_t* ids, float* total_ms, int32_t* count, int cap, int* n_out) {
+  if (!c || !ids || !total_ms || !count || !n_out || cap < 1) return fail(VFI_E_INVALID, "bad argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  int n = 0;
+  for (auto& sp : c->prof_spans) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, sp.e0, sp.e1) != cudaSuccess) ms = 0.f;
+    int k = 0;
+    while (k < n && ids[k] != sp.id) ++k;
+    if (k == n) {
+      if (n == cap) continue;
+      ids[n] = sp.id;
+      total_ms[n] = 0.f;
+      count[n] = 0;
+      ++n;
+    }
+    total_ms[k] += ms;
+    count[k] += 1;
+    cudaEventDestroy(sp.e0);
+    cudaEventDestroy(sp.e1);
+  }
+  c->prof_spans.clear();
+  *n_out = n;
   return VFI_OK;
 }
 
@@ -815,11 +939,8 @@ int vfi_rife46_interpolate_host(vfi_ctx* c, const float* frames, int n_frames, i
   if ((r = make_geometry(c->arch, H, W, scale_factor, &g))) return r;
   const int nf = frame_hi - frame_lo;
   const int B = std::min(c->batch, n_tasks);
-  if ((r = ensure_workspace(c, g, B, nf))) return r;
   const size_t frame_elems = (size_t)H * W * C, out_elems = (size_t)H * W * 3;
-  const int kRaw = 2 * kMaxBatch + 4;  // raw upload ring (frames)
-  CK(c->raw.ensure((size_t)kRaw * frame_elems * sizeof(float)));
-  CK(c->outdev.ensure((size_t)2 * B * out_elems * sizeof(float)));
+  const size_t frame_bytes = frame_elems * sizeof(float), out_bytes = out_elems * sizeof(float);
   // pass sizes: full batches in the middle; on a long clip the first and the last passes are small (1, 2, 4 pairs) so
   // that the exposed head (upload before the first pass) and tail (download after the last) are one or two frames
   // instead of a whole batch (r01: 64 frames e2e = 63 x 0.574 ms + 7.3 ms of head and tail with uniform passes)
@@ -844,35 +965,160 @@ int vfi_rife46_interpolate_host(vfi_ctx* c, const float* frames, int n_frames, i
     }
   }
   const int nb = (int)pass_n.size();
-  std::vector<cudaEvent_t> ev_up(nb), ev_comp(nb), ev_down(nb);
-  for (int i = 0; i < nb; ++i) {
-    CK(cudaEventCreateWithFlags(&ev_up[i], cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&ev_down[i], cudaEventDisableTiming));
+
+  // ---- the prepared-frame window is a RING: only frames some task references are uploaded, in order of first use, into
+  // slot (upload counter % R).  R covers every frame from its upload to the pass after its last use, so that the slot a
+  // pass's uploads overwrite was last read two passes ago (the copy stream runs one pass ahead of the compute stream
+  // without waiting) - 2 B + 1 slots for consecutive pairs instead of the whole clip (r01: 50-67 MB per 1080p frame for
+  // every frame of the clip; a few thousand frames did not fit).  An event wait keeps any reuse correct regardless.
+  std::vector<int> first_pass(nf, -1), last_pass(nf, -1), ctr(nf, -1), up_frames, up_end(nb, 0);
+  for (int k = 0; k < nb; ++k)
+    for (int i = 0; i < pass_n[k]; ++i)
+      for (int f : {f0[pass_pos[k] + i] - frame_lo, f1[pass_pos[k] + i] - frame_lo}) {
+        if (first_pass[f] < 0) first_pass[f] = k;
+        last_pass[f] = k;
+      }
+  {
+    std::vector<std::vector<int>> by_pass(nb);
+    for (int f = 0; f < nf; ++f)
+      if (first_pass[f] >= 0) by_pass[first_pass[f]].push_back(f);
+    for (int k = 0; k < nb; ++k) {
+      for (int f : by_pass[k]) {
+        ctr[f] = (int)up_frames.size();
+        up_frames.push_back(f);
+      }
+      up_end[k] = (int)up_frames.size();
+    }
   }
-  int uploaded = frame_lo;  // frames [frame_lo, uploaded) are prepared in c->imgs
+  int R = 1;
+  for (int f = 0; f < nf; ++f)
+    if (ctr[f] >= 0) R = std::max(R, up_end[std::min(last_pass[f] + 1, nb - 1)] - ctr[f]);
+  if ((r = ensure_workspace(c, g, B, R))) return r;
+  const int kRaw = 2 * kMaxBatch + 4;  // raw upload ring (frames), overwritten in stream order on the copy stream
+  CK(c->raw.ensure((size_t)kRaw * frame_bytes));
+  CK(c->outdev.ensure((size_t)2 * B * out_bytes));
+
+  // ---- host staging.  Pinned caller memory is copied from / to directly.  Pageable memory (what a ComfyUI IMAGE
+  // tensor is) goes through a small ring of pinned buffers: an uploader thread memcpy's frame by frame into it ahead of
+  // the H2D copies, a downloader thread empties the D2H ring into the caller's tensor; each uses a few copy threads.
+  const bool stage_in = !is_pinned_host(frames + (size_t)frame_lo * frame_elems);
+  const bool stage_out = !is_pinned_host(out);
+  const int copy_threads = env_int("VFI_COPY_THREADS", 6, 1, 32);
+  const size_t ring_mb = (size_t)env_int("VFI_STAGE_MB", 384, 32, 8192);
+  const int force_slots = env_int("VFI_STAGE_SLOTS", 0, 0, 64);  // tests: a ring far smaller than the clip
+  const int NS = !stage_in ? 0 : force_slots ? force_slots : (int)std::max<size_t>(4, std::min<size_t>(32, (ring_mb << 20) / frame_bytes));
+  const int ND = !stage_out ? 0 : force_slots ? force_slots : (int)std::max<size_t>(4, std::min<size_t>(48, (ring_mb << 20) / out_bytes));
+  if (stage_in) CK(c->pin_in.ensure((size_t)NS * frame_bytes));
+  if (stage_out) CK(c->pin_out.ensure((size_t)ND * out_bytes));
+
+  std::vector<cudaEvent_t> ev_up(nb), ev_comp(nb), ev_down(nb), ev_in(NS), ev_out(ND);
+  auto mk = [](std::vector<cudaEvent_t>& v) {
+    for (auto& e : v)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return false;
+    return true;
+  };
+  for (auto& e : ev_up) e = nullptr;
+  for (auto& e : ev_comp) e = nullptr;
+  for (auto& e : ev_down) e = nullptr;
+  for (auto& e : ev_in) e = nullptr;
+  for (auto& e : ev_out) e = nullptr;
+  if (!(mk(ev_up) && mk(ev_comp) && mk(ev_down) && mk(ev_in) && mk(ev_out))) return fail(VFI_E_CUDA, "cudaEventCreate failed");
+
+  // shared progress counters of the three host threads (all under one mutex; the hand-offs are per frame, ~0.5 ms apart)
+  std::mutex mu;
+  std::condition_variable cv;
+  bool abort_all = false;
+  int staged = 0;        // uploader: frames [0, staged) of up_frames sit in the pinned ring
+  int h2d_issued = 0;    // main: H2D copies [0, h2d_issued) have been enqueued (their ev_in is recorded)
+  int d2h_issued = 0;    // main: D2H copies [0, d2h_issued) have been enqueued (their ev_out is recorded)
+  int drained = 0;       // downloader: output frames [0, drained) have been copied to the caller's tensor
+  std::vector<int> d2h_slot;  // output slot of D2H copy i
+  d2h_slot.reserve(n_tasks);
+  const int n_up = (int)up_frames.size();
+
+  std::thread uploader, downloader;
+  if (stage_in)
+    uploader = std::thread([&] {
+      cudaSetDevice(c->device);
+      CopyPool pool(copy_threads);
+      for (int u = 0; u < n_up; ++u) {
+        if (u >= NS) {  // the H2D copy that last read this pinned slot has been enqueued, then: has completed
+          {
+            std::unique_lock<std::mutex> l(mu);
+            cv.wait(l, [&] { return abort_all || h2d_issued > u - NS; });
+            if (abort_all) return;
+          }
+          cudaEventSynchronize(ev_in[u % NS]);
+        }
+        pool.copy((uint8_t*)c->pin_in.p + (size_t)(u % NS) * frame_bytes,
+                  frames + (size_t)(up_frames[u] + frame_lo) * frame_elems, frame_bytes);
+        {
+          std::lock_guard<std::mutex> l(mu);
+          staged = u + 1;
+        }
+        cv.notify_all();
+      }
+    });
+  if (stage_out)
+    downloader = std::thread([&] {
+      cudaSetDevice(c->device);
+      CopyPool pool(copy_threads);
+      for (int v = 0; v < n_tasks; ++v) {
+        int slot;
+        {
+          std::unique_lock<std::mutex> l(mu);
+          cv.wait(l, [&] { return abort_all || d2h_issued > v; });
+          if (abort_all) return;
+          slot = d2h_slot[v];
+        }
+        cudaEventSynchronize(ev_out[v % ND]);
+        pool.copy(out + (size_t)slot * out_elems, (const uint8_t*)c->pin_out.p + (size_t)(v % ND) * out_bytes, out_bytes);
+        {
+          std::lock_guard<std::mutex> l(mu);
+          drained = v + 1;
+        }
+        cv.notify_all();
+      }
+    });
+
   int rc = VFI_OK;
   auto body = [&]() -> int {
+    int up = 0, down = 0;  // upload / download counters
     for (int k = 0; k < nb; ++k) {
       const int pos = pass_pos[k], n = pass_n[k];
-      int need = uploaded;
-      for (int i = 0; i < n; ++i) need = std::max(need, std::max(f0[pos + i], f1[pos + i]) + 1);
-      // H2D + prep of the frames this pass needs, in ring-sized groups, on the copy stream
-      while (uploaded < need) {
-        // one copy + one prep launch per contiguous run of ring slots (source frames are contiguous on the host)
-        const int slot = uploaded % kRaw;
-        const int run = std::min(std::min(need - uploaded, kRaw / 2), kRaw - slot);
-        float* rawp = (float*)c->raw.p + (size_t)slot * frame_elems;
-        float4* imgp = (float4*)c->imgs.p + (size_t)(uploaded - frame_lo) * g.Hp * g.Wp;
-        CK(cudaMemcpyAsync(rawp, frames + (size_t)uploaded * frame_elems, (size_t)run * frame_elems * sizeof(float),
-                           cudaMemcpyHostToDevice, c->s_h2d));
-        LAUNCH(launch_prep_frames(rawp, run, H, W, C, imgp,
-                                  (uint2*)c->imgs_h.p + (size_t)(uploaded - frame_lo) * g.Hp * g.Wp, g.Hp, g.Wp, c->s_h2d));
+      // H2D + prep of the frames this pass uses for the first time, on the copy stream
+      while (up < up_end[k]) {
+        const int slot = up % R, rslot = up % kRaw;
+        const int run = std::min(std::min(up_end[k] - up, kRaw / 2), std::min(R - slot, kRaw - rslot));
+        for (int j = 0; j < run; ++j) {
+          const int u = up + j;
+          if (u >= R) CK(cudaStreamWaitEvent(c->s_h2d, ev_comp[last_pass[up_frames[u - R]]], 0));  // slot's last reader
+          const float* src = frames + (size_t)(up_frames[u] + frame_lo) * frame_elems;
+          if (stage_in) {
+            std::unique_lock<std::mutex> l(mu);
+            cv.wait(l, [&] { return staged > u; });
+            src = (const float*)((const uint8_t*)c->pin_in.p + (size_t)(u % NS) * frame_bytes);
+          }
+          CK(cudaMemcpyAsync((float*)c->raw.p + (size_t)(rslot + j) * frame_elems, src, frame_bytes, cudaMemcpyHostToDevice,
+                             c->s_h2d));
+          if (stage_in) {
+            CK(cudaEventRecord(ev_in[u % NS], c->s_h2d));
+            {
+              std::lock_guard<std::mutex> l(mu);
+              h2d_issued = u + 1;
+            }
+            cv.notify_all();
+          }
+        }
+        const size_t px = (size_t)g.Hp * g.Wp;
+        LAUNCH(launch_prep_frames((float*)c->raw.p + (size_t)rslot * frame_elems, run, H, W, C,
+                                  (float4*)c->imgs.p + (size_t)slot * px, (uint2*)c->imgs_h.p + (size_t)slot * px, g.Hp, g.Wp,
+                                  c->s_h2d));
         if (c->arch != 46) {
-          const int r3 = run_encode(c, g, uploaded - frame_lo, run, c->s_h2d);
+          const int r3 = run_encode(c, g, slot, run, c->s_h2d);
           if (r3) return r3;
         }
-        uploaded += run;
+        up += run;
       }
       CK(cudaEventRecord(ev_up[k], c->s_h2d));
       CK(cudaStreamWaitEvent(c->s_comp, ev_up[k], 0));
@@ -880,8 +1126,8 @@ int vfi_rife46_interpolate_host(vfi_ctx* c, const float* frames, int n_frames, i
       BatchTasks bt{};
       bt.n = n;
       for (int i = 0; i < n; ++i) {
-        bt.f0[i] = f0[pos + i] - frame_lo;
-        bt.f1[i] = f1[pos + i] - frame_lo;
+        bt.f0[i] = ctr[f0[pos + i] - frame_lo] % R;
+        bt.f1[i] = ctr[f1[pos + i] - frame_lo] % R;
         bt.t[i] = t[pos + i];
       }
       float* od = (float*)c->outdev.p + (size_t)(k & 1) * B * out_elems;
@@ -889,13 +1135,28 @@ int vfi_rife46_interpolate_host(vfi_ctx* c, const float* frames, int n_frames, i
       if (r2) return r2;
       CK(cudaEventRecord(ev_comp[k], c->s_comp));
       CK(cudaStreamWaitEvent(c->s_d2h, ev_comp[k], 0));
-      if (!out_slot) {
-        CK(cudaMemcpyAsync(out + (size_t)pos * out_elems, od, (size_t)n * out_elems * sizeof(float),
-                           cudaMemcpyDeviceToHost, c->s_d2h));
+      if (stage_out) {
+        for (int i = 0; i < n; ++i, ++down) {
+          {  // the downloader has emptied the pinned slot this copy lands in
+            std::unique_lock<std::mutex> l(mu);
+            cv.wait(l, [&] { return drained > down - ND; });
+          }
+          CK(cudaMemcpyAsync((uint8_t*)c->pin_out.p + (size_t)(down % ND) * out_bytes, od + (size_t)i * out_elems, out_bytes,
+                             cudaMemcpyDeviceToHost, c->s_d2h));
+          CK(cudaEventRecord(ev_out[down % ND], c->s_d2h));
+          {
+            std::lock_guard<std::mutex> l(mu);
+            d2h_slot.push_back(out_slot ? out_slot[pos + i] : pos + i);
+            d2h_issued = down + 1;
+          }
+          cv.notify_all();
+        }
+      } else if (!out_slot) {
+        CK(cudaMemcpyAsync(out + (size_t)pos * out_elems, od, (size_t)n * out_bytes, cudaMemcpyDeviceToHost, c->s_d2h));
       } else {
         for (int i = 0; i < n; ++i)
-          CK(cudaMemcpyAsync(out + (size_t)out_slot[pos + i] * out_elems, od + (size_t)i * out_elems,
-                             out_elems * sizeof(float), cudaMemcpyDeviceToHost, c->s_d2h));
+          CK(cudaMemcpyAsync(out + (size_t)out_slot[pos + i] * out_elems, od + (size_t)i * out_elems, out_bytes,
+                             cudaMemcpyDeviceToHost, c->s_d2h));
       }
       CK(cudaEventRecord(ev_down[k], c->s_d2h));
     }
@@ -905,12 +1166,19 @@ int vfi_rife46_interpolate_host(vfi_ctx* c, const float* frames, int n_frames, i
     return VFI_OK;
   };
   rc = body();
-  if (rc != VFI_OK) cudaDeviceSynchronize();
-  for (int i = 0; i < nb; ++i) {
-    cudaEventDestroy(ev_up[i]);
-    cudaEventDestroy(ev_comp[i]);
-    cudaEventDestroy(ev_down[i]);
+  if (rc != VFI_OK) {
+    {
+      std::lock_guard<std::mutex> l(mu);
+      abort_all = true;
+    }
+    cv.notify_all();
+    cudaDeviceSynchronize();
   }
+  if (uploader.joinable()) uploader.join();
+  if (downloader.joinable()) downloader.join();
+  for (auto* v : {&ev_up, &ev_comp, &ev_down, &ev_in, &ev_out})
+    for (auto e : *v)
+      if (e) cudaEventDestroy(e);
   return rc;
 }
 

@@ -43,6 +43,7 @@ constexpr int kDefaultStoreMode = 2;  // see VFI_STORE in tapconv_plan
 constexpr int kDefaultMaxStages = 4;  // window stages of the non-ring layers (VFI_STAGES_MAX = 1..6 for A/B runs)
 struct Ctrl {
   uint64_t w_full;
+  uint64_t w_peer;  // pair mode, leader CTA only: the follower's weights have landed (remote arrive)
   uint64_t a_full[kMaxStages];
   uint64_t a_empty[kMaxStages];
   uint64_t t_full[kAccBufs];
@@ -102,7 +103,7 @@ struct TileIter {
 // 32 bytes per step).  NR and L are compile-time constants, so every p.mma[r] is a fixed constant-bank address and the
 // steps inside a run are immediate adds: ~4.7 SASS instructions per MMA for L = 4 (r01_v11: a table entry per step
 // cost 8-15 - LDC/IMAD/R2UR chains - and the issuing warp, not the tensor pipe, set the tile time).
-template <int NR, int L>
+template <int NR, int L, bool PAIR>
 __device__ __forceinline__ void issue_runs(const TapConvParams& p, uint32_t d_tmem, uint32_t a_lo0, uint32_t b_lo0,
                                            uint32_t b_hi, uint32_t idesc, uint32_t accumulate_first = 0u) {
 #pragma unroll
@@ -114,7 +115,10 @@ __device__ __forceinline__ void issue_runs(const TapConvParams& p, uint32_t d_tm
     uint64_t b64 = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo0 + d.z);
 #pragma unroll
     for (int i = 0; i < L; ++i) {
-      umma_f16(d_tmem, a64, b64, idesc, (r | i) ? 1u : accumulate_first);
+      if (PAIR)
+        umma_f16_pair(d_tmem, a64, b64, idesc, (r | i) ? 1u : accumulate_first);
+      else
+        umma_f16(d_tmem, a64, b64, idesc, (r | i) ? 1u : accumulate_first);
       a64 += 2;
       b64 += 2;
     }
@@ -155,7 +159,15 @@ __device__ __forceinline__ void advance_stage(uint32_t& stage, uint32_t& ph, uin
   }
 }
 
-template <int NR, int L, bool RING>
+template <bool PAIR>
+__device__ __forceinline__ void commit_to(uint32_t bar) {
+  if (PAIR)
+    umma_commit_pair(bar);  // the same barrier offset in both CTAs of the pair
+  else
+    umma_commit(bar);
+}
+
+template <int NR, int L, bool RING, bool PAIR>
 __device__ __forceinline__ void mma_tile_loop(const TapConvParams& p, const MmaLoopArgs& g, uint32_t which,
                                               uint32_t nissuers) {
   const uint32_t idesc = p.idesc;
@@ -167,32 +179,37 @@ __device__ __forceinline__ void mma_tile_loop(const TapConvParams& p, const MmaL
   for (uint32_t k = which; k < (uint32_t)g.ntiles; k += nissuers) {
     const uint32_t acc = k % kAccBufs;  // accumulator buffer; its "empty" barrier is waited with parity (uses & 1) ^ 1
     const uint32_t d_tmem = g.tmem_base + acc * p.acc_stride;
-    if (!ABLATE(32)) mbar_wait(g.bar_tempty + 8 * acc, ((k / kAccBufs) & 1u) ^ 1u, 2);
+    if (!ABLATE(32)) {
+      if (PAIR)  // both CTAs' epilogue groups have drained this accumulator (the follower's arrive remotely)
+        mbar_wait_cluster(g.bar_tempty + 8 * acc, ((k / kAccBufs) & 1u) ^ 1u, 2);
+      else
+        mbar_wait(g.bar_tempty + 8 * acc, ((k / kAccBufs) & 1u) ^ 1u, 2);
+    }
     if (RING) {
       for (int kb = 0; kb < p.nkb; ++kb) {
         mbar_wait(g.bar_afull + 8 * stage, aph, 3);
         tc_fence_after();
-        issue_runs<NR, L>(p, d_tmem, g.a_base + stage * stage_units, g.b_lo0 + (uint32_t)kb * b_kb, g.b_hi, idesc,
-                          kb > 0 ? 1u : 0u);
-        umma_commit(g.bar_aempty + 8 * stage);
+        issue_runs<NR, L, PAIR>(p, d_tmem, g.a_base + stage * stage_units, g.b_lo0 + (uint32_t)kb * b_kb, g.b_hi, idesc,
+                                kb > 0 ? 1u : 0u);
+        commit_to<PAIR>(g.bar_aempty + 8 * stage);
         advance_stage(stage, aph, 1u, g.S);
       }
-      umma_commit(g.bar_tfull + 8 * acc);
+      commit_to<PAIR>(g.bar_tfull + 8 * acc);
       if (nissuers > 1) advance_stage(stage, aph, per_tile, g.S);  // the other thread's tile
     } else {
       if (!ABLATE(64)) mbar_wait(g.bar_afull + 8 * stage, aph, 3);
       if (!ABLATE(256)) tc_fence_after();
-      if (!ABLATE(16)) issue_runs<NR, L>(p, d_tmem, g.a_base + stage * stage_units, g.b_lo0, g.b_hi, idesc);
+      if (!ABLATE(16)) issue_runs<NR, L, PAIR>(p, d_tmem, g.a_base + stage * stage_units, g.b_lo0, g.b_hi, idesc);
       if (!ABLATE(512)) {
-        if (g.commit_stage) umma_commit(g.bar_aempty + 8 * stage);  // window free once the MMAs have read it
-        umma_commit(g.bar_tfull + 8 * acc);                          // accumulator ready for the epilogue
+        if (g.commit_stage) commit_to<PAIR>(g.bar_aempty + 8 * stage);  // window free once the MMAs have read it
+        commit_to<PAIR>(g.bar_tfull + 8 * acc);                          // accumulator ready for the epilogue
       }
       advance_stage(stage, aph, nissuers, g.S);
     }
   }
 }
 
-template <typename T, bool RING, bool LAST>
+template <typename T, bool RING, bool LAST, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_constant__ TapConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem);
@@ -204,15 +221,35 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int split = blockIdx.x % p.nsplit;
-  const int first = blockIdx.x / p.nsplit;
-  if (first >= p.ctas_per_split) return;  // whole CTA leaves together
+  // Work assignment.  Single CTAs: CTA (split, first) takes the output-channel slice `split` of tiles first, first + cps,
+  // ...  CTA PAIRS (PAIR, a cluster of two CTAs = the two SMs of a TPC): pair (split, pi) takes the TILE PAIRS pi,
+  // pi + pps, ...; rank r of the pair owns tile 2 * j + r of tile pair j, its own window of it and ITS HALF (n_cta rows,
+  // packed slice 2 * split + r) of the B operand; one tcgen05.mma.cta_group::2 (M = 256, N = n_epi = 2 * n_cta) issued
+  // by rank 0 multiplies both windows with both halves and leaves each CTA's tile, all n_epi columns, in that CTA's own
+  // TMEM.  Per MMA a CTA's shared memory is read for 128 x 32 B of A and only n_cta x 32 B of B: for c = 64 that is 40
+  // instead of 48 wavefronts against 32 cycles of math (the r01 limiter), for c >= 96 the MMA is math bound; the
+  // per-tile issue / fence / commit cost of the issuing thread is paid once per TWO tiles; and the wide layers need
+  // half as many output-channel splits.  If the tile count is odd the last tile of rank 1 is a dummy: its window
+  // coordinates are outside the tensor (TMA fills zeros) and its epilogue stores nothing.
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;  // pair index / CTA index in the grid
+  const int nsplit_u = PAIR ? (p.nsplit >> 1) : p.nsplit;            // output-channel splits of the grid
+  const int split = unit % nsplit_u;
+  const int ufirst = unit / nsplit_u;
+  if (!PAIR && ufirst >= p.ctas_per_split) return;  // whole CTA leaves together (never taken in pair mode)
+  const int first = PAIR ? 2 * ufirst + (int)rank : ufirst;                  // this CTA's first tile ...
+  const int tstep = PAIR ? 2 * p.ctas_per_split : p.ctas_per_split;           // ... and its stride
+  const int nunits = PAIR ? (p.ntiles + 1) >> 1 : p.ntiles;                   // tile pairs / tiles of the layer
+  const int my_tiles = (nunits - ufirst + p.ctas_per_split - 1) / p.ctas_per_split;  // same for both ranks of a pair
+  const int wslice = PAIR ? 2 * split + (int)rank : split;                    // packed weight slice of this CTA
+  const int n0 = split * p.n_epi;                                             // first output channel of the epilogue
   const int S = p.stages;
   const bool residual = !LAST && (p.epi_mode == EPI_RESCONV);
   const bool res_smem = residual && !RING;  // ring layers read the residual from global memory (L2 hit)
 
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_w = smem_base + offsetof(Ctrl, w_full);
+  const uint32_t bar_wpeer = smem_base + offsetof(Ctrl, w_peer);
   const uint32_t bar_afull = smem_base + offsetof(Ctrl, a_full);
   const uint32_t bar_aempty = smem_base + offsetof(Ctrl, a_empty);
   const uint32_t bar_tfull = smem_base + offsetof(Ctrl, t_full);
@@ -223,19 +260,28 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
 
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
+    mbar_init(bar_wpeer, 1);
     for (int s = 0; s < S; ++s) {
       mbar_init(bar_afull + 8 * s, 1);                  // producer's arrive.expect_tx (+ TMA transaction bytes)
       mbar_init(bar_aempty + 8 * s, (residual && !RING) ? 4 : 1);  // the tile's 4 epilogue warps, or the MMA commit
     }
     for (int a = 0; a < kAccBufs; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 4);  // the four warps of the accumulator's epilogue group
+      mbar_init(bar_tempty + 8 * a, PAIR ? 8 : 4);  // the four warps of the accumulator's epilogue group (of both CTAs)
     }
     mbar_fence_init();
   }
-  if (warp == kMmaWarp) tmem_alloc(smem_base + offsetof(Ctrl, tmem_base), p.tmem_cols);
+  if (warp == kMmaWarp) {
+    if (PAIR)
+      tmem_alloc_pair(smem_base + offsetof(Ctrl, tmem_base), p.tmem_cols);
+    else
+      tmem_alloc(smem_base + offsetof(Ctrl, tmem_base), p.tmem_cols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR)
+    cluster_sync_all();  // the peer's barriers are initialised before anything of ours signals them
+  else
+    __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctrl->tmem_base;
 
@@ -246,11 +292,19 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
     // state is carried incrementally and the issue shape is dispatched once, outside the loop (r01 ablation: with a
     // division, a switch and warp re-convergence per tile the loop cost 660 cycles per tile on top of the MMAs, none
     // of it overlapped with the tensor pipe, whose queue is only a few MMAs deep).
-    if (elect_one_sync()) {
-      if (!ABLATE(1024)) mbar_wait(bar_w, 0, 1);
+    if (PAIR && rank != 0) {
+      // follower CTA: its second issuing warp only tells the leader when this CTA's half of the weights has landed
+      if (warp == kMmaWarp2 && elect_one_sync() && !ABLATE(1024)) {
+        mbar_wait(bar_w, 0, 1);
+        mbar_arrive_remote(mapa_u32(bar_wpeer, 0));
+      }
+    } else if (elect_one_sync()) {
+      if (!ABLATE(1024)) {
+        mbar_wait(bar_w, 0, 1);
+        if (PAIR && warp == kMmaWarp) mbar_wait_cluster(bar_wpeer, 0, 7);
+      }
       const uint32_t b_lo0 = (1u << 16) | (w_smem >> 4);              // LBO(=1) | start address, 16-byte units
       const uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO | version | SWIZZLE_128B
-      const int my_tiles = (p.ntiles - first + p.ctas_per_split - 1) / p.ctas_per_split;
       MmaLoopArgs g;
       g.bar_tfull = bar_tfull;
       g.bar_tempty = bar_tempty;
@@ -267,19 +321,19 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
       // Two issuers lift the MMA-only floor (ablation, block-3 ResConv: 2445 -> 2154 cycles per tile) but not the whole
       // kernel (3397 vs 3686: more contention with the epilogue warps on the same schedulers), so one is the default;
       // p.issuers = 2 (VFI_ISSUERS=2) keeps the other path measurable.
-      const uint32_t nissuers = (p.issuers == 2 && !RING && (S & 1) == 0) ? 2u : 1u;
+      const uint32_t nissuers = (!PAIR && p.issuers == 2 && !RING && (S & 1) == 0) ? 2u : 1u;
       if (which >= nissuers) g.ntiles = 0;
       if (RING) {
-        mma_tile_loop<9, 4, true>(p, g, which, nissuers);
+        mma_tile_loop<9, 4, true, PAIR>(p, g, which, nissuers);
       } else {
         switch (p.nruns * 8 + p.run_len) {  // fully unrolled issue sequences (tapconv_plan admits only these)
-          case 9 * 8 + 1: mma_tile_loop<9, 1, false>(p, g, which, nissuers); break;
-          case 27 * 8 + 1: mma_tile_loop<27, 1, false>(p, g, which, nissuers); break;
-          case 9 * 8 + 2: mma_tile_loop<9, 2, false>(p, g, which, nissuers); break;
-          case 27 * 8 + 2: mma_tile_loop<27, 2, false>(p, g, which, nissuers); break;
-          case 9 * 8 + 4: mma_tile_loop<9, 4, false>(p, g, which, nissuers); break;
-          case 18 * 8 + 4: mma_tile_loop<18, 4, false>(p, g, which, nissuers); break;
-          default: mma_tile_loop<27, 4, false>(p, g, which, nissuers); break;
+          case 9 * 8 + 1: mma_tile_loop<9, 1, false, PAIR>(p, g, which, nissuers); break;
+          case 27 * 8 + 1: mma_tile_loop<27, 1, false, PAIR>(p, g, which, nissuers); break;
+          case 9 * 8 + 2: mma_tile_loop<9, 2, false, PAIR>(p, g, which, nissuers); break;
+          case 27 * 8 + 2: mma_tile_loop<27, 2, false, PAIR>(p, g, which, nissuers); break;
+          case 9 * 8 + 4: mma_tile_loop<9, 4, false, PAIR>(p, g, which, nissuers); break;
+          case 18 * 8 + 4: mma_tile_loop<18, 4, false, PAIR>(p, g, which, nissuers); break;
+          default: mma_tile_loop<27, 4, false, PAIR>(p, g, which, nissuers); break;
         }
       }
     }
@@ -287,20 +341,30 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
     // ======================================================= TMA producer (one thread feeds the whole pipeline)
     if (elect_one_sync() && !ABLATE(1024)) {
       mbar_arrive_expect_tx(bar_w, p.w_bytes);
-      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + (size_t)split * p.w_bytes;
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + (size_t)wslice * p.w_bytes;
       for (uint32_t off = 0; off < p.w_bytes; off += 32768u)
         bulk_g2s(w_smem + off, wsrc + off, min(32768u, p.w_bytes - off), bar_w);
       // weights do not depend on the previous kernel; its output (our input tensor) does
       asm volatile("griddepcontrol.wait;" ::: "memory");
-      TileIter it(p, first, p.ctas_per_split);
+      TileIter it(p, first, tstep);
+      // pair mode: the transaction bytes of BOTH CTAs' window copies are counted on the LEADER's "full" barrier (the
+      // MMA-issuing thread lives there); the leader's producer announces twice the bytes, the follower's nothing
+      const uint32_t full_base = PAIR ? mapa_u32(bar_afull, 0) : bar_afull;
+      const uint32_t expect = PAIR ? 2u * p.tx_bytes : p.tx_bytes;
+      auto load = [&](uint32_t dst, const void* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+        if (PAIR)
+          tma_load_4d_pair(dst, tm, bar, c0, c1, c2, c3);
+        else
+          tma_load_4d(dst, tm, bar, c0, c1, c2, c3);
+      };
       if (RING) {
         uint32_t slot = 0, ph = 0;
-        for (int t = first; t < p.ntiles; t += p.ctas_per_split, it.next()) {
+        for (int k = 0; k < my_tiles; ++k, it.next()) {
           const int gy0 = it.ty * kTileH + p.halo_y0, gx0 = it.tx * kTileW + p.halo_x0;
           for (int kb = 0; kb < p.nkb; ++kb) {
             mbar_wait(bar_aempty + 8 * slot, ph ^ 1u, 4);
-            mbar_arrive_expect_tx(bar_afull + 8 * slot, p.tx_bytes);
-            tma_load_4d(a_smem + slot * p.stage_bytes, &p.tm64, bar_afull + 8 * slot, kb * 64, gx0, gy0, it.b);
+            if (rank == 0) mbar_arrive_expect_tx(bar_afull + 8 * slot, expect);
+            load(a_smem + slot * p.stage_bytes, &p.tm64, full_base + 8 * slot, kb * 64, gx0, gy0, it.b);
             if (++slot == (uint32_t)S) {
               slot = 0;
               ph ^= 1u;
@@ -309,18 +373,18 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
         }
       } else {
       uint32_t stage = 0, eph = 1;  // window stage and the parity of its "empty" barrier
-      for (int t = first; t < p.ntiles; t += p.ctas_per_split, it.next()) {
+      for (int k = 0; k < my_tiles; ++k, it.next()) {
         const int b = it.b;
         const int gy0 = it.ty * kTileH + p.halo_y0, gx0 = it.tx * kTileW + p.halo_x0;
         mbar_wait(bar_aempty + 8 * stage, eph, 4);
         if (ABLATE(8)) {
-          mbar_arrive(bar_afull + 8 * stage);
+          if (rank == 0) mbar_arrive(bar_afull + 8 * stage);
         } else {
-          mbar_arrive_expect_tx(bar_afull + 8 * stage, p.tx_bytes);
+          if (rank == 0) mbar_arrive_expect_tx(bar_afull + 8 * stage, expect);
           const uint32_t dst = a_smem + stage * p.stage_bytes;
           for (int kb = 0; kb < p.nkb; ++kb) {
             const bool tail = has_tail && (kb == p.nkb - 1);
-            tma_load_4d(dst + p.kb_off[kb], tail ? &p.tm32 : &p.tm64, bar_afull + 8 * stage, kb * 64, gx0, gy0, b);
+            load(dst + p.kb_off[kb], tail ? &p.tm32 : &p.tm64, full_base + 8 * stage, kb * 64, gx0, gy0, b);
           }
         }
         if (++stage == (uint32_t)S) {
@@ -339,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
     const int q = warp & 3;                    // TMEM lane quarter this warp may read
     const uint32_t acc = (uint32_t)warp >> 2;  // group == TMEM accumulator == tile index mod 4
     float* ss = reinterpret_cast<float*>(smem + p.off_ss);  // per-channel shift of this CTA's output slice
-    for (int i = threadIdx.x; i < p.n_cta; i += 32 * kEpiWarps) ss[i] = p.shift[split * p.n_cta + i];
+    for (int i = threadIdx.x; i < p.n_epi; i += 32 * kEpiWarps) ss[i] = p.shift[n0 + i];
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
     // the previous kernel may still be reading the buffer we store to (ping-pong) and ring layers read the residual from
     // global memory: every storing / loading thread orders itself after the previous grid
@@ -347,9 +411,15 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
 
     const int r = q * 32 + lane;  // accumulator row == TMEM lane == tile cell
     const int py = r >> 3, px = r & 7;
-    const int n0 = split * p.n_cta;
     const uint32_t center_px = (uint32_t)((py - p.halo_y0) * p.halo_w + (px - p.halo_x0));
-    const int nchunks = p.n_cta >> 4;  // 16-column chunks of this CTA's accumulator (<= 6)
+    const int nchunks = p.n_epi >> 4;  // 16-column chunks of this CTA's accumulator (<= 8)
+    // "accumulator drained": the issuing thread (pair mode: in the leader CTA) waits for the groups of both CTAs
+    auto release_acc = [&](uint32_t a) {
+      if (PAIR && rank != 0)
+        mbar_arrive_remote(mapa_u32(bar_tempty + 8 * a, 0));
+      else
+        mbar_arrive(bar_tempty + 8 * a);
+    };
     // stage_out (n_cta == 64, plain NHWC output): this group's tile goes to its own 16 KB staging buffer in the
     // SWIZZLE_128B form (row = cell, 128 B = the 64 channels) and leaves with one TMA tensor store.  ncu r01_v12: the
     // direct stores - every lane of an STG.128 in a different 128-byte line - were 2048 L1 tag lookups per tile, 60 %
@@ -365,9 +435,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
     uint32_t k = acc;
     uint32_t stage = acc % (uint32_t)S, use = acc / (uint32_t)S;
     if (ABLATE(1024)) k = 0x7fffffffu;
-    TileIter it(p, first + (int)acc * p.ctas_per_split, kAccBufs * p.ctas_per_split);
-    for (int t = first + (int)acc * p.ctas_per_split; t < p.ntiles && k != 0x7fffffffu;
-         t += kAccBufs * p.ctas_per_split, k += kAccBufs, it.next()) {
+    TileIter it(p, first + (int)acc * tstep, kAccBufs * tstep);
+    for (; k < (uint32_t)my_tiles; k += kAccBufs, it.next()) {
       if (k != acc) {  // advance (stage, use) by kAccBufs tiles
         stage += kAccBufs;
         while (stage >= (uint32_t)S) {
@@ -378,7 +447,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
       const uint32_t vuse = k / kAccBufs;
       const int b = it.b;
       const int gy = it.ty * kTileH + py, gx = it.tx * kTileW + px;
-      const bool valid = (gy < p.H) && (gx < p.W);
+      const bool valid = (gy < p.H) && (gx < p.W) && (b < p.B);  // (b == B: the dummy tile of an odd tile count)
 
       mbar_wait(bar_tfull + 8 * acc, vuse & 1, 5);
       tc_fence_after();
@@ -398,7 +467,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
           if (half == 1) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);  // TMEM buffer free again
+            if (lane == 0) release_acc(acc);  // TMEM buffer free again
           }
           if (valid) {
             const int Hs = p.H * 4, Ws = p.W * 4;
@@ -529,11 +598,14 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
       };
       if (ABLATE(4)) {
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        if (lane == 0) release_acc(acc);
         if (res_smem && lane == 0) mbar_arrive(bar_aempty + 8 * stage);
         continue;
       }
-      if (res_smem) mbar_wait(bar_afull + 8 * stage, use & 1, 6);  // acquire the TMA-written window
+      // acquire the TMA-written window.  (The follower CTA of a pair has no "full" barrier of its own - its copies are
+      // counted on the leader's - and is ordered behind them through the MMAs that read the window and their commit
+      // on t_full, which it has just waited for.)
+      if (res_smem && !(PAIR && rank != 0)) mbar_wait(bar_afull + 8 * stage, use & 1, 6);
       for (int c = 0; c < nchunks; c += 2) {
         uint32_t v0[16], v1[16];
         const bool two = (c + 1 < nchunks);
@@ -546,7 +618,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
         if (c + 2 >= nchunks) {  // last round: the accumulator has been read completely
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);  // TMEM buffer free: its next tile's MMAs may start
+          if (lane == 0) release_acc(acc);  // TMEM buffer free: its next tile's MMAs may start
         }
         if (ABLATE(2)) {
           if (v0[0] == 0x12345678u && v1[1] == 0x9abcdef0u) reinterpret_cast<T*>(p.out)[0] = T(1.f);  // keep the loads
@@ -564,7 +636,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
       if (stage_out) {
         fence_proxy_async();  // this thread's staging writes -> visible to the TMA (async proxy)
         asm volatile("bar.sync %0, 128;" ::"r"(2 + (int)acc) : "memory");
-        if (stg_leader) {
+        if (stg_leader && b < p.B) {
           tma_store_4d(&p.tm_out, stg_u32, n0, it.tx * kTileW, it.ty * kTileH, b);
           bulk_commit_group();
         }
@@ -574,10 +646,16 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_kernel(const __grid_const
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR)
+    cluster_sync_all();  // neither CTA may leave (or free TMEM) while the pair's MMAs, commits or remote arrives are in flight
+  else
+    __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if (PAIR)
+      tmem_dealloc_pair(tmem_base, p.tmem_cols);
+    else
+      tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
@@ -710,8 +788,13 @@ int tapconv_plan(const TapConvLayer& L, TapConvParams* pp) {
   // input window: one 1024-aligned region per k-block (64 channels = 128-byte rows; 32-channel tail = 64-byte rows)
   p.nkb = (L.cin + 63) / 64;
   p.ring = L.ring;
+  p.pair = L.pair;
+  p.n_epi = L.pair ? 2 * L.n_cta : L.n_cta;
   if (L.ktotal16 > kMaxK16) return 0;
-  if (p.nkb > kMaxKBlocks || L.n_cta > 96 || (L.n_cta & 15)) return 0;
+  // n_cta rows of B per CTA (whole 8-row swizzle atoms); n_epi accumulator columns: a multiple of 16 (the MMA's N for
+  // M = 128 / 256 and the epilogue's chunk), four accumulators of at most 128 columns in the 512 TMEM columns
+  if (p.nkb > kMaxKBlocks || L.n_cta > 96 || (L.n_cta & 7) || (p.n_epi & 15) || p.n_epi > 128) return 0;
+  if (L.pair && (L.nsplit & 1)) return 0;
   if (L.ring && ((L.cin & 63) || L.ntaps != 9 * p.nkb || L.ktotal16 != 36 * p.nkb)) return 0;
   uint32_t off = 0;
   p.tx_bytes = 0;
@@ -776,7 +859,7 @@ int tapconv_plan(const TapConvLayer& L, TapConvParams* pp) {
     for (int r = 0; r < p.nruns; ++r) p.mma[r] = step[r * run_len];
   }
   p.off_ss = kCtrlBytes;
-  p.off_w = align_up(p.off_ss + (uint32_t)L.n_cta * 4u, 1024);
+  p.off_w = align_up(p.off_ss + (uint32_t)p.n_epi * 4u, 1024);
   p.off_a = align_up(p.off_w + p.w_bytes, 1024);
   // staged output (TMA tensor store): 64-channel slices of a plain NHWC output, when four 16 KB staging buffers still
   // leave room for three window stages
@@ -789,7 +872,7 @@ int tapconv_plan(const TapConvLayer& L, TapConvParams* pp) {
   // (r01_v13, block 3 at batch 8: conv0.1 84.8 -> 69.7 us with the staged store; the ResConv layers, whose window
   // stages are held until the epilogue has read the residual, lost more from the fourth stage than they gained:
   // 94.2 us with STG.256 and 4 stages, 109 us staged with 3 - so only layers without a residual stage their output)
-  p.stage_out = (opt_store >= 2 && L.n_cta == 64 && L.out_s2d == 0 && !L.ring &&
+  p.stage_out = (opt_store >= 2 && p.n_epi == 64 && L.out_s2d == 0 && !L.ring &&
                  (L.epi_mode == EPI_BIAS_LRELU || L.epi_mode == EPI_BIAS) &&
                  p.off_a + 3u * p.stage_bytes + stg_bytes <= (uint32_t)kSmemLimit)
                     ? 1 : 0;
@@ -813,7 +896,7 @@ int tapconv_plan(const TapConvLayer& L, TapConvParams* pp) {
   p.smem_bytes = p.off_stg + (p.stage_out ? stg_bytes : 0u);
   // accumulators: kAccBufs buffers of n_cta fp32 columns, allocation is a power of two >= 32 (<= 4 x 128 = 512)
   uint32_t stride = 16;
-  while (stride < (uint32_t)L.n_cta) stride <<= 1;
+  while (stride < (uint32_t)p.n_epi) stride <<= 1;
   p.acc_stride = stride;
   p.tmem_cols = stride * kAccBufs < 32 ? 32 : stride * kAccBufs;
   return stages;
@@ -858,7 +941,7 @@ cudaError_t launch_tapconv(const TapConvLayer& L, int op_type, const void* in, v
   // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=f32, A/B = f16|bf16, both K-major,
   // N>>3 at [17,23), M>>4 at [24,29)
   const uint32_t fmt = (op_type == OP_BF16) ? 1u : 0u;
-  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(L.n_cta >> 3) << 17) | ((128u >> 4) << 24);
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.n_epi >> 3) << 17) | (((L.pair ? 256u : 128u) >> 4) << 24);
 
 #ifdef VFI_HOST_EMU
   use_ref = true;  // the host emulation has only the checker kernel
@@ -889,11 +972,14 @@ cudaError_t launch_tapconv(const TapConvLayer& L, int op_type, const void* in, v
   if (p.stage_out &&
       !make_tmap(&p.tm_out, dt, out, L.n_total, W, H, B, 64, kTileW, kTileH, CU_TENSOR_MAP_SWIZZLE_128B))
     return cudaErrorInvalidValue;
-  int cps = num_sms / L.nsplit;
+  // single CTAs: cps persistent CTAs per output-channel split; pairs: cps PAIRS (= TPCs) per pair-split
+  const int nsplit_u = L.pair ? L.nsplit / 2 : L.nsplit;
+  const int nunits = L.pair ? (p.ntiles + 1) / 2 : p.ntiles;
+  int cps = (L.pair ? num_sms / 2 : num_sms) / nsplit_u;
   if (cps < 1) cps = 1;
-  if (cps > p.ntiles) cps = p.ntiles;
+  if (cps > nunits) cps = nunits;
   p.ctas_per_split = cps;
-  const int grid = cps * L.nsplit;
+  const int grid = cps * nsplit_u * (L.pair ? 2 : 1);
   cudaError_t err;  // (per device: set on every launch, it is a cheap driver call)
   static const bool pdl = [] {  // VFI_PDL=0: plain stream-ordered launches (A/B runs)
     const char* e = std::getenv("VFI_PDL");
@@ -907,25 +993,40 @@ cudaError_t launch_tapconv(const TapConvLayer& L, int op_type, const void* in, v
     cfg.blockDim = dim3((unsigned)kThreads);
     cfg.dynamicSmemBytes = p.smem_bytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (L.pair) {  // the two CTAs of a pair are a cluster: co-scheduled on the two SMs of one TPC
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = 2;
+      attr[na].val.clusterDim.y = 1;
+      attr[na].val.clusterDim.z = 1;
+      ++na;
+    }
+    if (pdl) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, kern, p);
   };
   const bool last = (L.epi_mode == EPI_LASTCONV);
-  if (op_type == OP_BF16) {
-    if (last)
-      err = L.ring ? go(tapconv_kernel<__nv_bfloat16, true, true>) : go(tapconv_kernel<__nv_bfloat16, false, true>);
-    else
-      err = L.ring ? go(tapconv_kernel<__nv_bfloat16, true, false>) : go(tapconv_kernel<__nv_bfloat16, false, false>);
-  } else {
-    if (last)
-      err = L.ring ? go(tapconv_kernel<__half, true, true>) : go(tapconv_kernel<__half, false, true>);
-    else
-      err = L.ring ? go(tapconv_kernel<__half, true, false>) : go(tapconv_kernel<__half, false, false>);
-  }
+  auto pick = [&](auto tag) -> cudaError_t {
+    using T = decltype(tag);
+    const int key = (L.ring ? 4 : 0) | (last ? 2 : 0) | (L.pair ? 1 : 0);
+    switch (key) {
+      case 0: return go(tapconv_kernel<T, false, false, false>);
+      case 1: return go(tapconv_kernel<T, false, false, true>);
+      case 2: return go(tapconv_kernel<T, false, true, false>);
+      case 3: return go(tapconv_kernel<T, false, true, true>);
+      case 4: return go(tapconv_kernel<T, true, false, false>);
+      case 5: return go(tapconv_kernel<T, true, false, true>);
+      case 6: return go(tapconv_kernel<T, true, true, false>);
+      default: return go(tapconv_kernel<T, true, true, true>);
+    }
+  };
+  err = (op_type == OP_BF16) ? pick(__nv_bfloat16{}) : pick(__half{});
   if (err != cudaSuccess) return err;
   return cudaGetLastError();
 #endif  // VFI_HOST_EMU

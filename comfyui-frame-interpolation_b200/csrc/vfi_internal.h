@@ -68,6 +68,9 @@ struct alignas(64) TapConvParams {
   int issuers;           // MMA-issuing threads: 1 (default) or 2 (even stage counts only; VFI_ISSUERS=2)
   int ablate;            // diagnostic builds only (-DVFI_ABLATE): pipeline parts switched off, see tapconv.cu
   int ring;              // 1: the window streams through a ring of single k-block slots (see tapconv.cu)
+  int pair;              // 1: CTA pairs (cluster of 2, tcgen05 cta_group::2): one M = 256 MMA over two tiles, each CTA
+                         //    holding n_cta = n_epi / 2 rows of the B operand; ctas_per_split counts PAIRS
+  int n_epi;             // accumulator columns of a CTA = output channels its epilogue writes (n_cta, pair: 2 * n_cta)
   int tiles_x, tiles_y, ntiles;
   int ctas_per_split;
   uint32_t idesc;
@@ -95,6 +98,7 @@ struct TapConvLayer {
   int halo_y0 = 0, halo_x0 = 0, halo_h = 0, halo_w = 0;
   int epi_mode = 0, out_s2d = 0;
   int ring = 0;           // taps are listed k-block-major (kb, tap) with nk16 = 4; needs cin % 64 == 0
+  int pair = 0;           // CTA pairs: packed slices 2s and 2s+1 (n_cta rows each) are the two halves of pair-split s
   TapEntry taps[kMaxTaps];
   void* w = nullptr;      // device
   float* shift = nullptr; // device

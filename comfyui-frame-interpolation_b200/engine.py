@@ -154,6 +154,20 @@ class Rife46Engine:
                                              C.byref(wp)))
         return flow, mask
 
+    def profile(self, enable: bool):
+        """Start / stop per-kernel-group event timing of the forward schedule (vfi_rife_profile)."""
+        check(self._L.vfi_rife_profile(self._ctx, 1 if enable else 0))
+
+    def profile_read(self):
+        """{group id: (total ms, spans)} since profile(True); ids: 10 * block + {0 front, 1 conv0.0, 2 conv0.1, 3 ResConv x8,
+        4 lastconv}, 90 final."""
+        ids = np.zeros(64, np.int32)
+        ms = np.zeros(64, np.float32)
+        cnt = np.zeros(64, np.int32)
+        n = C.c_int()
+        check(self._L.vfi_rife_profile_read(self._ctx, ids.ctypes.data, ms.ctypes.data, cnt.ctypes.data, 64, C.byref(n)))
+        return {int(ids[i]): (float(ms[i]), int(cnt[i])) for i in range(n.value)}
+
     def set_batch(self, b):
         check(self._L.vfi_set_batch(self._ctx, int(b)))
 

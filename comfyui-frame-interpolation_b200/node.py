@@ -3,8 +3,21 @@
 Mirrors vfi_models/rife/__init__.py:34-239 (class attributes, kwargs, task order, skip / multiplier-list
 semantics, output assembly, dtype round trip) and vfi_utils.py:49-81, :391-407 (InterpolationStateList,
 MakeInterpolationStateList, FloatToInt).  The per-batch hot loop (:185-222) is replaced by ONE call into
-libvfi_b200.so; there is no PyTorch/CPU fallback.
+libvfi_b200.so per GPU; there is no PyTorch/CPU fallback.
+
+Host memory.  `frames` is taken as it comes (a ComfyUI IMAGE is a pageable CPU tensor): the library stages it
+through a small ring of pinned buffers (csrc/hoststage.h), nothing of the caller's is pinned or copied here.
+The output is allocated page-locked through torch's caching host allocator - its block is reused by the next call
+once the previous result has been dropped, so only the first call pays for the allocation - up to
+VFI_PINNED_OUT_MAX_GB (default 8); larger results are ordinary pageable tensors that the library fills through its
+pinned download ring.
+
+Several GPUs in one process.  set_devices([0, 1, ...]) (or VFI_DEVICES="0,1,2,3" / "all") shards the (pair, timestep)
+task list over the listed devices: one engine (vfi_ctx) and one host thread per device, each with a contiguous,
+task-count-balanced slice and only its own frame range, every device writing its frames straight into their slots
+of the shared output tensor - no gather (rife/__init__.py:185-222 is one loop on one device).
 """
+import collections
 import os
 import pathlib
 import threading
@@ -28,7 +41,56 @@ CKPT_NAME_VER_DICT = {
 DTYPE_OPTIONS = ["float32", "float16", "bfloat16"]
 DTYPE_MAP = {"float32": torch.float32, "float16": torch.float16, "bfloat16": torch.bfloat16}
 
-_model_cache: typing.Dict[typing.Tuple, Rife46Engine] = {}
+# (ckpt_name, dtype, device) -> engine, most recently used last.  An engine owns a multi-GB device workspace, so the
+# cache is bounded (VFI_MODEL_CACHE entries per device, default 2) and evicted engines are closed.
+_model_cache: "collections.OrderedDict[typing.Tuple, Rife46Engine]" = collections.OrderedDict()
+_devices: typing.Optional[typing.List[int]] = None
+
+
+def set_devices(devices: typing.Optional[typing.Sequence[int]]):
+    """GPUs the node shards a clip over (None: the current device only, like the reference)."""
+    global _devices
+    _devices = None if devices is None else list(dict.fromkeys(int(d) for d in devices))
+
+
+def _device_list() -> typing.List[int]:
+    if _devices is not None:
+        return list(_devices)
+    env = os.environ.get("VFI_DEVICES", "").strip()
+    if env == "all":
+        return list(range(torch.cuda.device_count()))
+    if env:
+        return list(dict.fromkeys(int(x) for x in env.split(",") if x.strip() != ""))  # (an engine serves one thread)
+    return [torch.cuda.current_device()]
+
+
+def _engine_for(ckpt_name, dtype, device, arch_ver, model_path) -> Rife46Engine:
+    key = (ckpt_name, dtype, int(device))
+    eng = _model_cache.get(key)
+    if eng is None:
+        sd = torch.load(model_path, map_location="cpu", weights_only=False)
+        eng = Rife46Engine(sd, device=int(device), dtype=dtype, arch=arch_ver)
+        _model_cache[key] = eng
+        cap = max(1, int(os.environ.get("VFI_MODEL_CACHE", "2")))
+        on_dev = [k for k in _model_cache if k[2] == int(device)]
+        for k in on_dev[:-cap]:
+            _model_cache.pop(k).close()
+    else:
+        _model_cache.move_to_end(key)
+    return eng
+
+
+def clear_model_cache():
+    while _model_cache:
+        _model_cache.popitem()[1].close()
+
+
+def _alloc_output(shape) -> torch.Tensor:
+    nbytes = 4
+    for d in shape:
+        nbytes *= int(d)
+    cap = float(os.environ.get("VFI_PINNED_OUT_MAX_GB", "8")) * (1 << 30)
+    return torch.empty(shape, dtype=torch.float32, pin_memory=bool(torch.cuda.is_available() and nbytes <= cap))
 
 
 class InterpolationStateList:
@@ -164,15 +226,13 @@ class RIFE_VFI:
         arch_ver = CKPT_NAME_VER_DICT[ckpt_name]
         model_path = load_file_from_github_release(MODEL_TYPE, ckpt_name)
         torch_dtype = DTYPE_MAP[dtype]
-        cache_key = (ckpt_name, dtype)
-        if cache_key not in _model_cache:
-            sd = torch.load(model_path, map_location="cpu", weights_only=False)
-            _model_cache[cache_key] = Rife46Engine(sd, device=torch.cuda.current_device(), dtype=dtype, arch=arch_ver)
-        engine = _model_cache[cache_key]
+        devices = _device_list()
+        engines = [_engine_for(ckpt_name, dtype, d, arch_ver, model_path) for d in devices]
 
         assert len(frames) >= 2, f"RIFE needs at least 2 frames, only found {frames.shape[0]}"
         frames = frames.detach()
-        src = frames.to("cpu", torch.float32).contiguous()  # borrowed, never mutated
+        # borrowed, never mutated; a CPU float32 contiguous IMAGE (the normal case) is used in place, pageable or not
+        src = frames.to("cpu", torch.float32).contiguous()
         n, h, w, _ = src.shape
         n_pairs = n - 1
         tasks, _ = build_tasks(n_pairs, multiplier, optional_interpolation_states)
@@ -186,30 +246,38 @@ class RIFE_VFI:
             first_slot.append(slot)
             slot += 1 + per_pair[p]
         total = slot + 1
-        out = torch.empty((total, h, w, 3), dtype=torch.float32, pin_memory=torch.cuda.is_available())
+        out = _alloc_output((total, h, w, 3))
         seen = [0] * n_pairs
         f0, f1, ts, slots = [], [], [], []
         for p, t in tasks:
             seen[p] += 1
             f0.append(p); f1.append(p + 1); ts.append(t); slots.append(first_slot[p] + seen[p])
 
+        # one contiguous, task-count-balanced slice per device (skip lists / multiplier lists stay balanced); a device
+        # uploads only the frames its slice touches and downloads straight into the slots of the shared output
+        from .shard import shard_tasks
+        jobs = [(e, lo, hi) for e, (lo, hi) in zip(engines, shard_tasks(len(tasks), len(engines))) if hi > lo]
         err: typing.List[BaseException] = []
 
-        def run():
+        def run(engine, lo, hi):
             try:
-                engine.interpolate_host(src, f0, f1, ts, out, out_slots=slots, scale_factor=float(scale_factor))
+                fr = (min(f0[lo:hi]), max(f1[lo:hi]) + 1)
+                engine.interpolate_host(src, f0[lo:hi], f1[lo:hi], ts[lo:hi], out, out_slots=slots[lo:hi], frame_range=fr,
+                                        scale_factor=float(scale_factor))
             except BaseException as e:  # surfaced on the caller's thread below
                 err.append(e)
 
-        th = threading.Thread(target=run)
-        th.start()
-        # pass-through frames are copied on the host while the GPU pipeline runs (ctypes drops the GIL)
+        threads = [threading.Thread(target=run, args=j) for j in jobs]
+        for th in threads:
+            th.start()
+        # pass-through frames are copied on the host while the GPU pipelines run (ctypes drops the GIL)
         orig_slots = torch.tensor(first_slot + [total - 1], dtype=torch.long)
         passthrough = src[..., :3]
         if torch_dtype != torch.float32:  # the reference round-trips every frame through `dtype` (:227,:230,:238)
             passthrough = passthrough.to(torch_dtype).to(torch.float32)
-        out.index_copy_(0, orig_slots, passthrough.contiguous())
-        th.join()
+        out.index_copy_(0, orig_slots, passthrough)
+        for th in threads:
+            th.join()
         if err:
             raise err[0]
         if torch_dtype != torch.float32 and slots:

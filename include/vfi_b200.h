@@ -184,6 +184,14 @@ int vfi_rife46_layer_plan(vfi_ctx* ctx, int block, int layer, int* stages, int* 
                           int64_t* macs_per_cell);
 int vfi_sync(vfi_ctx* ctx);
 
+/* Measurement hook (bench.py's roofline lines): while enabled, every internal pass of the RIFE forward schedule records
+ * CUDA events on its launching stream around each kernel group - id = 10 * block + {0 front (warps + resample + concat,
+ * rife_arch.py:238-249, :703-704), 1 conv0.0, 2 conv0.1, 3 the eight ResConvs, 4 lastconv}, 90 = the final warp / blend /
+ * crop kernel (rife_arch.py:713-732).  vfi_rife_profile_read synchronises and returns, per group id, the summed device
+ * time in ms and the number of spans; at most `cap` groups.  No counterpart in the reference (it has no timing code). */
+int vfi_rife_profile(vfi_ctx* ctx, int enable);
+int vfi_rife_profile_read(vfi_ctx* ctx, int32_t* ids, float* total_ms, int32_t* count, int cap, int* n_groups);
+
 #ifdef __cplusplus
 }
 #endif

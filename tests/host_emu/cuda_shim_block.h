@@ -109,3 +109,11 @@ static inline cudaError_t emu_memcpy(void* d, const void* s, size_t n) {
 #define cudaEventRecord(e, s) cudaSuccess
 #define cudaEventDestroy(e) cudaSuccess
 #define cudaFuncSetAttribute(k, a, v) cudaSuccess
+// the host-pointer pipeline's staging (csrc/hoststage.h): every caller buffer counts as pageable here, so the emulation
+// exercises the pinned-ring / uploader / downloader threads
+#define cudaEventSynchronize(e) cudaSuccess
+#define cudaEventCreate(p) (*(p) = nullptr, cudaSuccess)
+#define cudaEventElapsedTime(ms, a, b) (*(ms) = 0.f, cudaSuccess)
+#define cudaHostAlloc(p, n, f) emu_malloc((void**)(p), (n))
+#define cudaFreeHost(p) (std::free(p), cudaSuccess)
+#define cudaPointerGetAttributes(a, p) ((a)->type = cudaMemoryTypeUnregistered, cudaSuccess)

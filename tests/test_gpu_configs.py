@@ -71,3 +71,27 @@ def test_config2_geometry_1080p_batch8(pkg, arch):
     print(f"config 2 geometry (1080p, B=8, arch {arch}): crops PSNR {p_crops:.2f} dB (worst crop {worst:.2f}), "
           f"8x8-box max abs {b8:.2e}, full frames vs oracle {p_full:.2f} dB")
     assert worst >= 50.0 and p_full >= 50.0 and b8 <= 2e-3
+
+
+def test_node_shards_over_the_devices_of_this_process(pkg, tmp_path, monkeypatch):
+    """set_devices: one engine + host thread per GPU, contiguous task slices, every device writing its own slots of the
+    shared output (two GPUs when the box has them, else the same code path with one) == the single-device result."""
+    import cfi_b200.node as N
+    sd = O.synthetic_state_dict(3, 1.5, arch="4.6")
+    path = tmp_path / "rife46.pth"
+    torch.save(sd, path)
+    monkeypatch.setattr(N, "load_file_from_github_release", lambda model_type, ckpt_name: str(path))
+    fr = O.synthetic_clip(9, 72, 104, seed=31)
+    st = N.InterpolationStateList([2], True)
+    N._model_cache.clear()
+    (one,) = N.RIFE_VFI().vfi("rife46.pth", fr, multiplier=[3, 2, 2, 4], optional_interpolation_states=st)
+    devs = list(range(min(2, torch.cuda.device_count())))
+    N.set_devices(devs)
+    try:
+        (two,) = N.RIFE_VFI().vfi("rife46.pth", fr, multiplier=[3, 2, 2, 4], optional_interpolation_states=st)
+    finally:
+        N.set_devices(None)
+        N.clear_model_cache()
+    assert torch.equal(one, two)
+    ref = O.rife_vfi(sd, fr, multiplier=[3, 2, 2, 4], states=([2], True))
+    assert one.shape == ref.shape and O.psnr(one, ref) >= 50.0

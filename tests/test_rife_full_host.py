@@ -191,6 +191,28 @@ def test_rife_host_pipeline_ring_and_shards_on_host(emu):
         assert emu.vfi_rife46_forward(ctx, C.c_void_p(fr.data_ptr()), n, h, w, c, vp(a0), vp(a1), vp(at), 1, C.c_float(1.0),
                                       C.c_void_p(one.data_ptr()), None) == 0, emu.vfi_last_error()
         assert torch.equal(out[slots[i]], one[0]), (i, p_, t)
+    # a longer task list with gaps (skipped pairs: their frames are never uploaded), a prepared-frame ring that wraps
+    # several times and pinned staging rings of two slots (every caller buffer counts as pageable in the emulation)
+    n2 = 12
+    fr2 = O.synthetic_clip(n2, h, w, seed=78).contiguous()
+    tasks2 = [(0, 0.5), (1, 0.5), (1, 0.25), (4, 0.5), (5, 0.5), (6, 0.75), (9, 0.5), (10, 0.5)]
+    g0 = np.asarray([p for p, _ in tasks2], dtype=np.int32)
+    g1 = g0 + 1
+    gt = np.asarray([t for _, t in tasks2], dtype=np.float32)
+    out2 = torch.zeros(len(tasks2), h, w, 3)
+    os.environ["VFI_STAGE_SLOTS"] = "2"
+    try:
+        rc = emu.vfi_rife46_interpolate_host(ctx, C.c_void_p(fr2.data_ptr()), n2, h, w, c, 0, n2, vp(g0), vp(g1), vp(gt), None,
+                                             len(tasks2), C.c_float(1.0), C.c_void_p(out2.data_ptr()))
+    finally:
+        del os.environ["VFI_STAGE_SLOTS"]
+    assert rc == 0, emu.vfi_last_error()
+    for i, (p_, t) in enumerate(tasks2):
+        one = torch.zeros(1, h, w, 3)
+        a0, a1, at = np.asarray([p_], np.int32), np.asarray([p_ + 1], np.int32), np.asarray([t], np.float32)
+        assert emu.vfi_rife46_forward(ctx, C.c_void_p(fr2.data_ptr()), n2, h, w, c, vp(a0), vp(a1), vp(at), 1, C.c_float(1.0),
+                                      C.c_void_p(one.data_ptr()), None) == 0, emu.vfi_last_error()
+        assert torch.equal(out2[i], one[0]), (i, p_, t)
     # a task outside the shard is refused
     bad0, bad1 = np.asarray([0], np.int32), np.asarray([1], np.int32)
     rc = emu.vfi_rife46_interpolate_host(ctx, C.c_void_p(fr.data_ptr()), n, h, w, c, 1, 6, vp(bad0), vp(bad1), vp(ts), None, 1,

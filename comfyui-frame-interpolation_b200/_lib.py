@@ -11,7 +11,7 @@ SYMBOLS = [
     "vfi_rife46_load", "vfi_rife_load", "vfi_rife46_forward", "vfi_rife46_interpolate_host", "vfi_warp_bilinear_border",
     "vfi_softsplat_sum", "vfi_softsplat_weighted", "vfi_costvol_l1", "vfi_corr_dot", "vfi_sepconv", "vfi_adacof", "vfi_edt_pass",
     "vfi_rife46_debug_layer", "vfi_rife46_debug_state", "vfi_rife46_layer_plan", "vfi_sync",
-    "vfi_rife_profile", "vfi_rife_profile_read",
+    "vfi_rife_profile", "vfi_rife_profile_read", "vfi_host_copy_frames",
     "vfi_film_load", "vfi_film_forward", "vfi_film_debug_set_ref", "vfi_film_debug_conv", "vfi_film_layer_plan",
     "vfi_film_last_macs", "vfi_film_debug_pack_host",
     "vfi_sepconv_load", "vfi_sepconv_forward", "vfi_sepconv_debug_set_ref", "vfi_sepconv_debug_pack_host",
@@ -44,7 +44,7 @@ def lib():
     L.vfi_rife46_load.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i32, i32]
     L.vfi_rife_load.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64), i32, i32]
     L.vfi_rife46_forward.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, f32, vp, vp]
-    L.vfi_rife46_interpolate_host.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, f32, vp]
+    L.vfi_rife46_interpolate_host.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, f32, vp]
     L.vfi_warp_bilinear_border.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
     L.vfi_softsplat_sum.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
     L.vfi_softsplat_weighted.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, vp]
@@ -59,6 +59,7 @@ def lib():
                                         C.POINTER(i32), C.POINTER(i64)]
     L.vfi_sync.argtypes = [vp]
     L.vfi_rife_profile.argtypes = [vp, i32]
+    L.vfi_host_copy_frames.argtypes = [vp, i32, i32, i32, i32, vp, vp, i32]
     L.vfi_rife_profile_read.argtypes = [vp, vp, vp, vp, i32, C.POINTER(i32)]
     L.vfi_film_load.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i32, i32]
     L.vfi_film_forward.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp]

@@ -41,17 +41,15 @@ class CopyPool {
       std::memcpy(dst, src, bytes);
       return;
     }
-    {
-      std::lock_guard<std::mutex> l(m_);
-      dst_ = static_cast<uint8_t*>(dst);
-      src_ = static_cast<const uint8_t*>(src);
-      bytes_ = bytes;
-      pending_ = (int)workers_.size();
-      ++gen_;
+    dispatch(dst, src, bytes, 0);
+  }
+  // dst[i*3 + k] = src[i*C + k], k < 3, for `px` fp32 pixels: the first three channels of an NHWC frame (C == 3: memcpy)
+  void copy_rgb(float* dst, const float* src, size_t px, int C) {
+    if (C == 3) {
+      copy(dst, src, px * 3 * sizeof(float));
+      return;
     }
-    cv_.notify_all();
-    std::unique_lock<std::mutex> l(m_);
-    done_.wait(l, [this] { return pending_ == 0; });
+    dispatch(dst, src, px, C);
   }
 
  private:
@@ -61,6 +59,7 @@ class CopyPool {
       uint8_t* d;
       const uint8_t* s;
       size_t bytes;
+      int C;
       {
         std::unique_lock<std::mutex> l(m_);
         cv_.wait(l, [&] { return gen_ != seen; });
@@ -69,16 +68,43 @@ class CopyPool {
         d = dst_;
         s = src_;
         bytes = bytes_;
+        C = chan_;
       }
-      // 4 KB-aligned chunk boundaries (whole pages per thread)
-      const size_t chunk = ((bytes + n - 1) / n + 4095) & ~(size_t)4095;
-      const size_t lo = std::min(bytes, chunk * idx), hi = std::min(bytes, chunk * (idx + 1));
-      if (hi > lo) std::memcpy(d + lo, s + lo, hi - lo);
+      if (C == 0) {
+        // 4 KB-aligned chunk boundaries (whole pages per thread)
+        const size_t chunk = ((bytes + n - 1) / n + 4095) & ~(size_t)4095;
+        const size_t lo = std::min(bytes, chunk * idx), hi = std::min(bytes, chunk * (idx + 1));
+        if (hi > lo) std::memcpy(d + lo, s + lo, hi - lo);
+      } else {  // `bytes` counts pixels here
+        const size_t chunk = (bytes + n - 1) / n;
+        const size_t lo = std::min(bytes, chunk * idx), hi = std::min(bytes, chunk * (idx + 1));
+        float* df = reinterpret_cast<float*>(d);
+        const float* sf = reinterpret_cast<const float*>(s);
+        for (size_t i = lo; i < hi; ++i) {
+          df[i * 3 + 0] = sf[i * C + 0];
+          df[i * 3 + 1] = sf[i * C + 1];
+          df[i * 3 + 2] = sf[i * C + 2];
+        }
+      }
       {
         std::lock_guard<std::mutex> l(m_);
         if (--pending_ == 0) done_.notify_all();
       }
     }
+  }
+  void dispatch(void* dst, const void* src, size_t n, int chan) {
+    {
+      std::lock_guard<std::mutex> l(m_);
+      dst_ = static_cast<uint8_t*>(dst);
+      src_ = static_cast<const uint8_t*>(src);
+      bytes_ = n;
+      chan_ = chan;
+      pending_ = (int)workers_.size();
+      ++gen_;
+    }
+    cv_.notify_all();
+    std::unique_lock<std::mutex> l(m_);
+    done_.wait(l, [this] { return pending_ == 0; });
   }
   std::vector<std::thread> workers_;
   std::mutex m_;
@@ -88,6 +114,7 @@ class CopyPool {
   uint8_t* dst_ = nullptr;
   const uint8_t* src_ = nullptr;
   size_t bytes_ = 0;
+  int chan_ = 0;  // 0: byte copy; C > 3: first-three-channels copy of `bytes_` pixels
   int pending_ = 0;
 };
 

@@ -15,10 +15,13 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <condition_variable>
+#include <cstdio>
 #include <mutex>
 #include <thread>
 
@@ -584,12 +587,13 @@ int forward_pass(vfi_ctx* c, const Geometry& g, const BatchTasks& tasks, int H, 
   auto span_end = [&]() {
     if (c->profile) cudaEventRecord(c->prof_spans.back().e1, st);
   };
-  // VFI_FLOW_STORE_LAST=1: the last block's front also stores the accumulated flow (r01 behaviour: `final` then adds
-  // one level).  Default 0: it does not - `final` adds the last TWO levels on the fly, which saves the 20 B/px store of
-  // the largest front for a quarter-resolution read in `final`.
+  // The last block's front stores the accumulated flow too and `final` adds one level to it.  VFI_FLOW_STORE_LAST=0: it
+  // does not, `final` adds the last TWO levels on the fly.  Measured r02 (profiles/r02_c_bench*.log, per pair): the
+  // largest front 38.1 -> 33.6 us without its 20 B/px store, but `final` 35.8 -> 45.4 us (the second level's eight taps
+  // per pixel make it instruction bound) - a net loss, so storing stays the default.
   static const bool store_last = [] {
     const char* e = std::getenv("VFI_FLOW_STORE_LAST");
-    return e && e[0] == '1';
+    return !(e && e[0] == '0');
   }();
   for (int i = 0; i < nb; ++i) {
     const int s = g.s[i];
@@ -923,7 +927,8 @@ int vfi_rife46_forward(vfi_ctx* c, const float* frames, int n_frames, int H, int
 
 int vfi_rife46_interpolate_host(vfi_ctx* c, const float* frames, int n_frames, int H, int W, int C, int frame_lo,
                                 int frame_hi, const int32_t* f0, const int32_t* f1, const float* t,
-                                const int32_t* out_slot, int n_tasks, float scale_factor, float* out) {
+                                const int32_t* out_slot, const int32_t* frame_slot, int n_tasks, float scale_factor,
+                                float* out) {
   if (!c || !frames || (n_tasks > 0 && (!out || !f0 || !f1 || !t))) return fail(VFI_E_INVALID, "null argument");
   if (!c->loaded) return fail(VFI_E_STATE, "vfi_rife46_load has not been called");
   if (C < 3 || H < 1 || W < 1 || frame_lo < 0 || frame_hi > n_frames || frame_lo >= frame_hi)
@@ -1001,9 +1006,20 @@ int vfi_rife46_interpolate_host(vfi_ctx* c, const float* frames, int n_frames, i
   // ---- host staging.  Pinned caller memory is copied from / to directly.  Pageable memory (what a ComfyUI IMAGE
   // tensor is) goes through a small ring of pinned buffers: an uploader thread memcpy's frame by frame into it ahead of
   // the H2D copies, a downloader thread empties the D2H ring into the caller's tensor; each uses a few copy threads.
-  const bool stage_in = !is_pinned_host(frames + (size_t)frame_lo * frame_elems);
+  // Pass-through frames (frame_slot): source frame f is also wanted unchanged (first 3 channels) at out + frame_slot[f].
+  // The uploader thread makes that copy - and when `out` is page-locked the frame is then UPLOADED FROM THERE: the one
+  // host copy the node contract needs anyway doubles as the staging copy (r02: staging and pass-through as two separate
+  // copies ran at ~20 GB/s each on the box's cgroup-limited host cores and were the critical path, 91 ms for a 40 ms
+  // pipeline).
   const bool stage_out = !is_pinned_host(out);
-  const int copy_threads = env_int("VFI_COPY_THREADS", 6, 1, 32);
+  auto via_out = [&](int f_abs) { return frame_slot != nullptr && !stage_out && frame_slot[f_abs] >= 0; };
+  bool any_ring = false, any_pt = false;
+  const bool src_pinned = is_pinned_host(frames + (size_t)frame_lo * frame_elems);
+  for (int f : up_frames) any_ring = any_ring || (!src_pinned && !via_out(f + frame_lo));
+  if (frame_slot)
+    for (int f = frame_lo; f < frame_hi; ++f) any_pt = any_pt || frame_slot[f] >= 0;
+  const bool stage_in = any_ring;
+  const int copy_threads = env_int("VFI_COPY_THREADS", 8, 1, 32);
   const size_t ring_mb = (size_t)env_int("VFI_STAGE_MB", 384, 32, 8192);
   const int force_slots = env_int("VFI_STAGE_SLOTS", 0, 0, 64);  // tests: a ring far smaller than the clip
   const int NS = !stage_in ? 0 : force_slots ? force_slots : (int)std::max<size_t>(4, std::min<size_t>(32, (ring_mb << 20) / frame_bytes));
@@ -1035,29 +1051,68 @@ int vfi_rife46_interpolate_host(vfi_ctx* c, const float* frames, int n_frames, i
   std::vector<int> d2h_slot;  // output slot of D2H copy i
   d2h_slot.reserve(n_tasks);
   const int n_up = (int)up_frames.size();
+  // upload u comes from: the caller's pinned tensor (-2), its pass-through slot in the pinned output (-1), or pinned
+  // staging ring entry ring_of[u] >= 0 (a running count of ring uploads)
+  std::vector<int> ring_of(n_up, -2);
+  {
+    int nr = 0;
+    for (int u = 0; u < n_up; ++u) {
+      const int fa = up_frames[u] + frame_lo;
+      if (via_out(fa)) ring_of[u] = -1;
+      else if (!src_pinned) ring_of[u] = nr++;
+    }
+  }
+  const size_t px_frame = (size_t)H * W;
+
+  // VFI_TRACE=1: where the host threads spent their time (stderr, one line per call)
+  const bool trace = env_int("VFI_TRACE", 0, 0, 1) != 0;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double>(b - a).count();
+  };
+  double up_copy_s = 0, up_wait_s = 0, dn_copy_s = 0, dn_wait_s = 0, main_wait_stage_s = 0, main_wait_drain_s = 0;
+  const auto t_call = now();
 
   std::thread uploader, downloader;
-  if (stage_in)
+  if (stage_in || any_pt)
     uploader = std::thread([&] {
       cudaSetDevice(c->device);
       CopyPool pool(copy_threads);
+      std::vector<char> pt_done(nf, 0);
       for (int u = 0; u < n_up; ++u) {
-        if (u >= NS) {  // the H2D copy that last read this pinned slot has been enqueued, then: has completed
+        const auto tw = now();
+        const int fa = up_frames[u] + frame_lo;
+        const float* src = frames + (size_t)fa * frame_elems;
+        const int ri = ring_of[u];
+        if (ri >= NS && ri >= 0) {  // the H2D copy that last read this pinned slot has been enqueued, then: has completed
           {
             std::unique_lock<std::mutex> l(mu);
-            cv.wait(l, [&] { return abort_all || h2d_issued > u - NS; });
+            cv.wait(l, [&] { return abort_all || h2d_issued > ri - NS; });
             if (abort_all) return;
           }
-          cudaEventSynchronize(ev_in[u % NS]);
+          cudaEventSynchronize(ev_in[ri % NS]);
         }
-        pool.copy((uint8_t*)c->pin_in.p + (size_t)(u % NS) * frame_bytes,
-                  frames + (size_t)(up_frames[u] + frame_lo) * frame_elems, frame_bytes);
+        const auto tc = now();
+        if (ri >= 0) pool.copy((uint8_t*)c->pin_in.p + (size_t)(ri % NS) * frame_bytes, src, frame_bytes);
+        if (frame_slot && frame_slot[fa] >= 0) {
+          pool.copy_rgb(out + (size_t)frame_slot[fa] * out_elems, src, px_frame, C);
+          pt_done[fa - frame_lo] = 1;
+        }
+        up_wait_s += secs(tw, tc);
+        up_copy_s += secs(tc, now());
         {
           std::lock_guard<std::mutex> l(mu);
           staged = u + 1;
         }
         cv.notify_all();
       }
+      if (frame_slot)  // pass-through frames no task references (skipped pairs)
+        for (int f = frame_lo; f < frame_hi; ++f)
+          if (frame_slot[f] >= 0 && !pt_done[f - frame_lo]) {
+            const auto tc = now();
+            pool.copy_rgb(out + (size_t)frame_slot[f] * out_elems, frames + (size_t)f * frame_elems, px_frame, C);
+            up_copy_s += secs(tc, now());
+          }
     });
   if (stage_out)
     downloader = std::thread([&] {
@@ -1065,6 +1120,7 @@ int vfi_rife46_interpolate_host(vfi_ctx* c, const float* frames, int n_frames, i
       CopyPool pool(copy_threads);
       for (int v = 0; v < n_tasks; ++v) {
         int slot;
+        const auto tw = now();
         {
           std::unique_lock<std::mutex> l(mu);
           cv.wait(l, [&] { return abort_all || d2h_issued > v; });
@@ -1072,7 +1128,10 @@ int vfi_rife46_interpolate_host(vfi_ctx* c, const float* frames, int n_frames, i
           slot = d2h_slot[v];
         }
         cudaEventSynchronize(ev_out[v % ND]);
+        const auto tc = now();
         pool.copy(out + (size_t)slot * out_elems, (const uint8_t*)c->pin_out.p + (size_t)(v % ND) * out_bytes, out_bytes);
+        dn_wait_s += secs(tw, tc);
+        dn_copy_s += secs(tc, now());
         {
           std::lock_guard<std::mutex> l(mu);
           drained = v + 1;
@@ -1089,29 +1148,40 @@ int vfi_rife46_interpolate_host(vfi_ctx* c, const float* frames, int n_frames, i
       // H2D + prep of the frames this pass uses for the first time, on the copy stream
       while (up < up_end[k]) {
         const int slot = up % R, rslot = up % kRaw;
-        const int run = std::min(std::min(up_end[k] - up, kRaw / 2), std::min(R - slot, kRaw - rslot));
+        int run = std::min(std::min(up_end[k] - up, kRaw / 2), std::min(R - slot, kRaw - rslot));
+        // a run is prepared by one kernel launch: its frames must have the same channel stride (3 from the output's
+        // pass-through slots, C otherwise)
+        const bool run_rgb = ring_of[up] == -1;
+        for (int j = 1; j < run; ++j)
+          if ((ring_of[up + j] == -1) != run_rgb) run = j;
+        const size_t run_elems = run_rgb ? out_elems : frame_elems;
         for (int j = 0; j < run; ++j) {
           const int u = up + j;
           if (u >= R) CK(cudaStreamWaitEvent(c->s_h2d, ev_comp[last_pass[up_frames[u - R]]], 0));  // slot's last reader
-          const float* src = frames + (size_t)(up_frames[u] + frame_lo) * frame_elems;
-          if (stage_in) {
+          const int fa = up_frames[u] + frame_lo;
+          const int ri = ring_of[u];
+          const float* src = frames + (size_t)fa * frame_elems;
+          if (ri != -2) {  // staged by the uploader thread
+            const auto tw = now();
             std::unique_lock<std::mutex> l(mu);
             cv.wait(l, [&] { return staged > u; });
-            src = (const float*)((const uint8_t*)c->pin_in.p + (size_t)(u % NS) * frame_bytes);
+            src = (ri == -1) ? out + (size_t)frame_slot[fa] * out_elems
+                             : (const float*)((const uint8_t*)c->pin_in.p + (size_t)(ri % NS) * frame_bytes);
+            main_wait_stage_s += secs(tw, now());
           }
-          CK(cudaMemcpyAsync((float*)c->raw.p + (size_t)(rslot + j) * frame_elems, src, frame_bytes, cudaMemcpyHostToDevice,
-                             c->s_h2d));
-          if (stage_in) {
-            CK(cudaEventRecord(ev_in[u % NS], c->s_h2d));
+          CK(cudaMemcpyAsync((float*)c->raw.p + (size_t)rslot * frame_elems + (size_t)j * run_elems, src,
+                             run_elems * sizeof(float), cudaMemcpyHostToDevice, c->s_h2d));
+          if (ri >= 0) {
+            CK(cudaEventRecord(ev_in[ri % NS], c->s_h2d));
             {
               std::lock_guard<std::mutex> l(mu);
-              h2d_issued = u + 1;
+              h2d_issued = ri + 1;
             }
             cv.notify_all();
           }
         }
         const size_t px = (size_t)g.Hp * g.Wp;
-        LAUNCH(launch_prep_frames((float*)c->raw.p + (size_t)rslot * frame_elems, run, H, W, C,
+        LAUNCH(launch_prep_frames((float*)c->raw.p + (size_t)rslot * frame_elems, run, H, W, run_rgb ? 3 : C,
                                   (float4*)c->imgs.p + (size_t)slot * px, (uint2*)c->imgs_h.p + (size_t)slot * px, g.Hp, g.Wp,
                                   c->s_h2d));
         if (c->arch != 46) {
@@ -1138,8 +1208,10 @@ int vfi_rife46_interpolate_host(vfi_ctx* c, const float* frames, int n_frames, i
       if (stage_out) {
         for (int i = 0; i < n; ++i, ++down) {
           {  // the downloader has emptied the pinned slot this copy lands in
+            const auto tw = now();
             std::unique_lock<std::mutex> l(mu);
             cv.wait(l, [&] { return drained > down - ND; });
+            main_wait_drain_s += secs(tw, now());
           }
           CK(cudaMemcpyAsync((uint8_t*)c->pin_out.p + (size_t)(down % ND) * out_bytes, od + (size_t)i * out_elems, out_bytes,
                              cudaMemcpyDeviceToHost, c->s_d2h));
@@ -1176,10 +1248,52 @@ int vfi_rife46_interpolate_host(vfi_ctx* c, const float* frames, int n_frames, i
   }
   if (uploader.joinable()) uploader.join();
   if (downloader.joinable()) downloader.join();
+  if (trace)
+    fprintf(stderr,
+            "vfi trace: interpolate_host dev %d  %d tasks  %d uploads (ring %d)  total %.1f ms | stage_in=%d NS=%d copy %.1f ms "
+            "wait %.1f ms | stage_out=%d ND=%d copy %.1f ms wait %.1f ms | main waited %.1f ms for staging, %.1f ms for draining\n",
+            c->device, n_tasks, n_up, R, 1e3 * secs(t_call, now()), (int)stage_in, NS, 1e3 * up_copy_s, 1e3 * up_wait_s, (int)stage_out,
+            ND, 1e3 * dn_copy_s, 1e3 * dn_wait_s, 1e3 * main_wait_stage_s, 1e3 * main_wait_drain_s);
   for (auto* v : {&ev_up, &ev_comp, &ev_down, &ev_in, &ev_out})
     for (auto e : *v)
       if (e) cudaEventDestroy(e);
   return rc;
+}
+
+// Host utility of the node: copy source frame i (first 3 of C channels) to out + slot[i] * H * W * 3 for every i with
+// slot[i] >= 0, with `threads` copy threads - the pass-through frames of the output clip (rife/__init__.py:227-231 does a
+// torch.cat of per-frame tensors).  Plain host memory on both sides; runs beside vfi_rife46_interpolate_host.
+int vfi_host_copy_frames(const float* frames, int n_frames, int H, int W, int C, const int32_t* slot, float* out, int threads) {
+  if (!frames || !slot || !out || n_frames < 1 || H < 1 || W < 1 || C < 3) return fail(VFI_E_INVALID, "bad argument");
+  if (threads < 1) threads = 1;
+  if (threads > 64) threads = 64;
+  const size_t px = (size_t)H * W;
+  std::vector<std::thread> th;
+  std::atomic<int> next{0};
+  for (int k = 0; k < threads; ++k)
+    th.emplace_back([&] {
+      // work items: (frame, quarter of the frame) so that a handful of frames still spreads over all threads
+      for (;;) {
+        const int item = next.fetch_add(1);
+        const int f = item >> 2, q = item & 3;
+        if (f >= n_frames) return;
+        if (slot[f] < 0) continue;
+        const size_t lo = px * q / 4, hi = px * (q + 1) / 4;
+        const float* s = frames + (size_t)f * px * C;
+        float* d = out + (size_t)slot[f] * px * 3;
+        if (C == 3) {
+          std::memcpy(d + lo * 3, s + lo * 3, (hi - lo) * 3 * sizeof(float));
+        } else {
+          for (size_t i = lo; i < hi; ++i) {
+            d[i * 3 + 0] = s[i * C + 0];
+            d[i * 3 + 1] = s[i * C + 1];
+            d[i * 3 + 2] = s[i * C + 2];
+          }
+        }
+      }
+    });
+  for (auto& t : th) t.join();
+  return VFI_OK;
 }
 
 int vfi_warp_bilinear_border(vfi_ctx* c, const float* img, const float* flow, float* out, int B, int H, int W, int C,

@@ -38,6 +38,20 @@ def _i32(a):
     return np.ascontiguousarray(np.asarray(a, dtype=np.int32))
 
 
+def host_copy_frames(frames: torch.Tensor, slots, out: torch.Tensor, threads: int = 0):
+    """out[slots[i]] = frames[i, ..., :3] for every i with slots[i] >= 0 (CPU float32 tensors), on `threads` copy threads of
+    the library (default VFI_COPY_THREADS or 8) - vfi_host_copy_frames."""
+    assert not frames.is_cuda and not out.is_cuda and frames.dtype == torch.float32 and out.dtype == torch.float32
+    assert frames.is_contiguous() and out.is_contiguous() and frames.dim() == 4 and tuple(out.shape[1:3]) == tuple(frames.shape[1:3])
+    n, h, w, c = frames.shape
+    sl = _i32(slots)
+    assert len(sl) == n and (len(sl) == 0 or int(sl.max()) < out.shape[0]) and out.shape[3] == 3
+    if threads <= 0:
+        import os
+        threads = int(os.environ.get("VFI_COPY_THREADS", "8"))
+    check(lib().vfi_host_copy_frames(frames.data_ptr(), n, h, w, c, sl.ctypes.data, out.data_ptr(), int(threads)))
+
+
 class Rife46Engine:
     """RIFE 4.6 / 4.7 / 4.17 / 4.26 (rife46.pth; rife47.pth, rife49.pth; rife417.pth; rife426.pth) on one B200.  `state_dict` maps the reference's parameter names to tensors (any float dtype)."""
 
@@ -99,8 +113,9 @@ class Rife46Engine:
 
     # ------------------------------------------------------------------ host-buffer path (node / e2e)
     def interpolate_host(self, frames: torch.Tensor, f0, f1, t, out: torch.Tensor, out_slots=None,
-                         frame_range=None, scale_factor: float = 1.0):
-        """frames: CPU float32 [N,H,W,C]; out: CPU float32 [M,H,W,3]; task i -> out[out_slots[i]] (default i)."""
+                         frame_range=None, scale_factor: float = 1.0, frame_slots=None):
+        """frames: CPU float32 [N,H,W,C]; out: CPU float32 [M,H,W,3]; task i -> out[out_slots[i]] (default i);
+        frame_slots (optional, one per source frame, -1 = none): frame i is also copied unchanged to out[frame_slots[i]]."""
         assert not frames.is_cuda and frames.dtype == torch.float32 and frames.is_contiguous()
         assert not out.is_cuda and out.dtype == torch.float32 and out.is_contiguous()
         n, h, w, c = frames.shape
@@ -114,10 +129,14 @@ class Rife46Engine:
             assert len(slots) == len(ta) and (len(slots) == 0 or int(slots.max()) < out.shape[0])
         else:
             assert out.shape[0] >= len(ta)
+        fslots = None
+        if frame_slots is not None:
+            fslots = _i32(frame_slots)
+            assert len(fslots) == n and int(fslots.max()) < out.shape[0]
         check(self._L.vfi_rife46_interpolate_host(
             self._ctx, frames.data_ptr(), n, h, w, c, int(lo), int(hi), f0a.ctypes.data, f1a.ctypes.data,
-            ta.ctypes.data, None if slots is None else slots.ctypes.data, len(ta), float(scale_factor),
-            out.data_ptr()))
+            ta.ctypes.data, None if slots is None else slots.ctypes.data, None if fslots is None else fslots.ctypes.data,
+            len(ta), float(scale_factor), out.data_ptr()))
         return out
 
     # ------------------------------------------------------------------ primitives / hooks

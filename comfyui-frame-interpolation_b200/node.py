@@ -25,7 +25,7 @@ import typing
 
 import torch
 
-from .engine import Rife46Engine
+from .engine import Rife46Engine, host_copy_frames
 
 MODEL_TYPE = "rife"
 # The reference table (rife/__init__.py:10-20) has no 4.6 entry at this commit although IFNet supports it and
@@ -256,26 +256,41 @@ class RIFE_VFI:
         # one contiguous, task-count-balanced slice per device (skip lists / multiplier lists stay balanced); a device
         # uploads only the frames its slice touches and downloads straight into the slots of the shared output
         from .shard import shard_tasks
-        jobs = [(e, lo, hi) for e, (lo, hi) in zip(engines, shard_tasks(len(tasks), len(engines))) if hi > lo]
+        jobs = [[e, lo, hi, None] for e, (lo, hi) in zip(engines, shard_tasks(len(tasks), len(engines))) if hi > lo]
+        # pass-through frames (rife/__init__.py:227-231): every source frame also appears unchanged in the output.  The
+        # library's copy threads put frame i into its slot while staging it for upload (one host copy for both); each
+        # frame belongs to the first device whose frame range holds it, frames no device touches to the first device.
+        orig_slots = first_slot + [total - 1]
+        fast_pt = torch_dtype == torch.float32 and len(jobs) > 0
+        if fast_pt:
+            owner = [-1] * n
+            for j, (_e, lo, hi, _) in enumerate(jobs):
+                for f in range(min(f0[lo:hi]), max(f1[lo:hi]) + 1):
+                    if owner[f] < 0:
+                        owner[f] = j
+            for j, job in enumerate(jobs):
+                job[3] = [orig_slots[f] if owner[f] == j else -1 for f in range(n)]
         err: typing.List[BaseException] = []
 
-        def run(engine, lo, hi):
+        def run(engine, lo, hi, fslots):
             try:
                 fr = (min(f0[lo:hi]), max(f1[lo:hi]) + 1)
                 engine.interpolate_host(src, f0[lo:hi], f1[lo:hi], ts[lo:hi], out, out_slots=slots[lo:hi], frame_range=fr,
-                                        scale_factor=float(scale_factor))
+                                        scale_factor=float(scale_factor), frame_slots=fslots)
             except BaseException as e:  # surfaced on the caller's thread below
                 err.append(e)
 
-        threads = [threading.Thread(target=run, args=j) for j in jobs]
+        threads = [threading.Thread(target=run, args=tuple(j)) for j in jobs]
         for th in threads:
             th.start()
-        # pass-through frames are copied on the host while the GPU pipelines run (ctypes drops the GIL)
-        orig_slots = torch.tensor(first_slot + [total - 1], dtype=torch.long)
-        passthrough = src[..., :3]
-        if torch_dtype != torch.float32:  # the reference round-trips every frame through `dtype` (:227,:230,:238)
-            passthrough = passthrough.to(torch_dtype).to(torch.float32)
-        out.index_copy_(0, orig_slots, passthrough)
+        if fast_pt:
+            rest = [orig_slots[f] if owner[f] < 0 else -1 for f in range(n)]  # frames of skipped pairs, never uploaded
+            if any(v >= 0 for v in rest):
+                host_copy_frames(src, rest, out)
+        elif torch_dtype == torch.float32:
+            host_copy_frames(src, orig_slots, out)
+        else:  # the reference round-trips every frame through `dtype` (:227,:230,:238)
+            out.index_copy_(0, torch.tensor(orig_slots, dtype=torch.long), src[..., :3].to(torch_dtype).to(torch.float32))
         for th in threads:
             th.join()
         if err:

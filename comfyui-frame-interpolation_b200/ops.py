@@ -53,65 +53,41 @@ class softsplat_func:
         return out
 
 
-import os as _os
-
-# VFI_SPLAT_FUSED=1: avg / linear / soft through the fused kernels (vfi_softsplat_weighted) instead of the reference's
-# cat -> splat -> slice -> divide chain around vfi_softsplat_sum.  Off by default until its first GPU run has been read.
-_FUSED = _os.environ.get("VFI_SPLAT_FUSED", "0") == "1"
+_SPLAT_MODE = {"avg": 0, "linear": 1, "soft": 2}
+_SPLAT_EPS = {"addeps": 0, "zeroeps": 1, "clipeps": 2}
 
 
-def softsplat_fused(tenIn, tenFlow, tenMetric, strMode: str):
-    """avg / linear / soft (+ -addeps / -zeroeps / -clipeps) in two launches, no temporaries."""
-    base = strMode.split("-")[0]
-    mode = {"avg": 0, "linear": 1, "soft": 2}[base]
-    variant = strMode.split("-")[1] if "-" in strMode else "addeps"
-    eps = {"addeps": 0, "zeroeps": 1, "clipeps": 2}[variant]
-    if mode == 0:
-        tenIn, tenFlow = _prep(tenIn, tenFlow)
-        tenMetric = None
-    else:
+def softsplat(tenIn, tenFlow, tenMetric, strMode: str):
+    """Forward splat with the reference's modes - same call contract as cupy_ops/softsplat.py:382-435: strMode is
+    "sum" | "avg" | "linear" | "soft", the last three optionally suffixed "-addeps" (default) / "-zeroeps" / "-clipeps";
+    tenMetric is required for linear / soft and must be None for sum / avg.
+
+    Not the reference's tensor chain (concatenate a weight channel, splat C + 1 channels, slice, divide): "sum" is one
+    launch of the splat kernel; the weighted modes go through vfi_softsplat_weighted, which applies the per-source-pixel
+    weight (1, metric or exp(metric)) while splatting, splats the weights into one normalisation plane and divides in a
+    second launch - no temporaries and about half the HBM traffic."""
+    base, _, variant = strMode.partition("-")
+    if base == "sum":
+        if tenMetric is not None or variant:
+            raise AssertionError("sum mode takes no metric and no eps variant")
+        return softsplat_func.apply(tenIn, tenFlow)
+    if base not in _SPLAT_MODE or (variant or "addeps") not in _SPLAT_EPS:
+        raise AssertionError(f"unknown softsplat mode {strMode!r}")
+    needs_metric = base != "avg"
+    if needs_metric != (tenMetric is not None):
+        raise AssertionError(f"{base} mode {'needs' if needs_metric else 'takes no'} metric")
+    if needs_metric:
         tenIn, tenFlow, tenMetric = _prep(tenIn, tenFlow, tenMetric)
+    else:
+        tenIn, tenFlow = _prep(tenIn, tenFlow)
     n, c, h, w = tenIn.shape
     out = torch.empty_like(tenIn)
     norm = tenIn.new_empty(n, 1, h, w)
     check(lib().vfi_softsplat_weighted(_context(tenIn.device), tenIn.data_ptr(), tenFlow.data_ptr(),
-                                       None if tenMetric is None else tenMetric.data_ptr(), mode, eps, out.data_ptr(),
-                                       norm.data_ptr(), n, c, h, w, _stream(tenIn)))
+                                       tenMetric.data_ptr() if needs_metric else None, _SPLAT_MODE[base],
+                                       _SPLAT_EPS[variant or "addeps"], out.data_ptr(), norm.data_ptr(), n, c, h, w,
+                                       _stream(tenIn)))
     return out
-
-
-def softsplat(tenIn, tenFlow, tenMetric, strMode: str):
-    """cupy_ops/softsplat.py:382-435."""
-    assert strMode.split("-")[0] in ["sum", "avg", "linear", "soft"]
-    if strMode == "sum":
-        assert tenMetric is None
-    if strMode == "avg":
-        assert tenMetric is None
-    if strMode.split("-")[0] == "linear":
-        assert tenMetric is not None
-    if strMode.split("-")[0] == "soft":
-        assert tenMetric is not None
-    if _FUSED and strMode != "sum":
-        return softsplat_fused(tenIn, tenFlow, tenMetric, strMode)
-    if strMode == "avg":
-        tenIn = torch.cat([tenIn, tenIn.new_ones([tenIn.shape[0], 1, tenIn.shape[2], tenIn.shape[3]])], 1)
-    elif strMode.split("-")[0] == "linear":
-        tenIn = torch.cat([tenIn * tenMetric, tenMetric], 1)
-    elif strMode.split("-")[0] == "soft":
-        tenIn = torch.cat([tenIn * tenMetric.exp(), tenMetric.exp()], 1)
-    tenOut = softsplat_func.apply(tenIn, tenFlow)
-    if strMode.split("-")[0] in ["avg", "linear", "soft"]:
-        tenNormalize = tenOut[:, -1:, :, :]
-        if len(strMode.split("-")) == 1:
-            tenNormalize = tenNormalize + 0.0000001
-        elif strMode.split("-")[1] == "addeps":
-            tenNormalize = tenNormalize + 0.0000001
-        elif strMode.split("-")[1] == "zeroeps":
-            tenNormalize[tenNormalize == 0.0] = 1.0
-        elif strMode.split("-")[1] == "clipeps":
-            tenNormalize = tenNormalize.clip(0.0000001, None)
-        tenOut = tenOut[:, :-1, :, :] / tenNormalize
-    return tenOut
 
 
 def FunctionSoftsplat(tenInput, tenFlow, tenMetric, strType):

@@ -80,10 +80,21 @@ int vfi_rife46_forward(vfi_ctx* ctx, const float* frames, int n_frames, int H, i
  * interpolated frames land directly between the pass-through frames of the node's output tensor
  * (rife/__init__.py:225-238) without a second host copy.
  * Only frames in [frame_lo, frame_hi) are uploaded (the shard of this rank); tasks must reference only those.
+ * frame_slot (NULL or [n_frames]): source frame f in [frame_lo, frame_hi) with frame_slot[f] >= 0 is also copied unchanged
+ * (first 3 channels) to out + frame_slot[f]*H*W*3 - the pass-through frames of rife/__init__.py:227-231 - by the library's
+ * copy threads; with a page-locked `out` that copy doubles as the staging copy of the upload.
+ * Pageable `frames` / `out` go through pinned staging rings (VFI_STAGE_MB, VFI_COPY_THREADS); the prepared-frame window
+ * on the device is a ring of ~2 x batch + 1 frames whatever the clip length.
  * Synchronous: returns when `out` is complete. */
 int vfi_rife46_interpolate_host(vfi_ctx* ctx, const float* frames, int n_frames, int H, int W, int C, int frame_lo,
                                 int frame_hi, const int32_t* f0, const int32_t* f1, const float* t,
-                                const int32_t* out_slot, int n_tasks, float scale_factor, float* out);
+                                const int32_t* out_slot, const int32_t* frame_slot, int n_tasks, float scale_factor,
+                                float* out);
+
+/* Host utility for the node's output assembly (rife/__init__.py:225-238: every source frame is passed through between
+ * the interpolated ones): frame i (first 3 of C channels) -> out + slot[i]*H*W*3 for every i with slot[i] >= 0, split over
+ * `threads` host threads.  HOST pointers, any host memory; no GPU involved.  Runs beside vfi_rife46_interpolate_host. */
+int vfi_host_copy_frames(const float* frames, int n_frames, int H, int W, int C, const int32_t* slot, float* out, int threads);
 
 /* Primitive: backward bilinear warp == rife_arch.warp (rife_arch.py:31-70) ==
  * grid_sample(bilinear, padding_mode="border", align_corners=True) on a pixel-unit flow.  DEVICE pointers, NHWC:

@@ -1,5 +1,5 @@
 """FunctionAdaCoF / batch_edt on the GPU vs the oracle (pinned to the reference's kernels on the CPU).  The kernels were
-written after r01's last GPU minute (host-emulated on the CPU only), hence xfail(strict=False) until a GPU run is read."""
+written after r01's last GPU minute; first GPU run r02 (profiles/r02_a_gpu_tests.log): green."""
 import pytest
 import torch
 
@@ -33,14 +33,14 @@ def test_batch_edt_gpu(pkg):
 
 @pytest.mark.parametrize("mode", ["avg", "linear", "soft", "soft-zeroeps", "linear-clipeps"])
 def test_softsplat_fused_gpu(pkg, mode):
-    """vfi_softsplat_weighted (VFI_SPLAT_FUSED=1 makes ops.softsplat use it) vs the oracle at a GMFSS-like shape."""
+    """ops.softsplat's weighted modes (vfi_softsplat_weighted: the implementation since r02) vs the oracle at a GMFSS-like shape."""
     from cfi_b200 import ops
     g = torch.Generator().manual_seed(11)
     x = torch.randn(2, 32, 96, 128, generator=g)
     flow = (torch.rand(2, 2, 96, 128, generator=g) - 0.5) * 20
     metric = torch.rand(2, 1, 96, 128, generator=g) * 2 - (0.5 if mode.startswith("soft") else -0.2)
     m = None if mode == "avg" else metric
-    out = ops.softsplat_fused(x.cuda(), flow.cuda(), None if m is None else m.cuda(), mode).cpu()
+    out = ops.softsplat(x.cuda(), flow.cuda(), None if m is None else m.cuda(), mode).cpu()
     ref = ops_ref.softsplat(x, flow, m, mode)
     ok = ref.abs() < 1e4
     assert (out - ref)[ok].abs().max().item() <= 2e-3 * max(1.0, float(ref[ok].abs().max()))

@@ -1,8 +1,7 @@
 """Sepconv on the GPU: tools/sepconv_gpu_check.py in a SUBPROCESS (sorted after the verified
 tests; a trap in new code must not poison their CUDA context).  The Sepconv trunk was written at the end of r01 with no
-GPU minutes left - streamconv's EXT epilogue, nine element-wise kernels and the schedule have never run on a GPU - so the
-test is xfail(strict=False): it still runs on the GPU box at round end and reports XPASS / XFAIL with the checker's
-per-stage JSON lines."""
+GPU minutes left; its first GPU run (r02, profiles/r02_sepconv_gpu_check.jsonl) was green on every stage: 98 - 101 dB on
+the tcgen05 kernel vs the unmodified reference Network."""
 import os
 import subprocess
 import sys

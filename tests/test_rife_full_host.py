@@ -147,7 +147,7 @@ def test_rife_host_pipeline_on_host_matches_reference_node(emu):
     a = lambda v, dt: np.ascontiguousarray(np.asarray(v, dtype=dt))   # noqa: E731
     f0a, f1a, tsa, sla = a(f0, np.int32), a(f1, np.int32), a(ts, np.float32), a(slots, np.int32)
     vp = lambda x: x.ctypes.data_as(C.c_void_p)   # noqa: E731
-    rc = emu.vfi_rife46_interpolate_host(ctx, C.c_void_p(fr.data_ptr()), n, h, w, c, 0, n, vp(f0a), vp(f1a), vp(tsa), vp(sla),
+    rc = emu.vfi_rife46_interpolate_host(ctx, C.c_void_p(fr.data_ptr()), n, h, w, c, 0, n, vp(f0a), vp(f1a), vp(tsa), vp(sla), None,
                                          len(ts), C.c_float(1.0), C.c_void_p(out.data_ptr()))
     assert rc == 0, emu.vfi_last_error()
     assert emu.vfi_destroy(ctx) == 0
@@ -182,7 +182,7 @@ def test_rife_host_pipeline_ring_and_shards_on_host(emu):
     slots = np.asarray(list(range(len(tasks)))[::-1], dtype=np.int32)
     vp = lambda x: x.ctypes.data_as(C.c_void_p)   # noqa: E731
     out = torch.zeros(len(tasks), h, w, 3)
-    rc = emu.vfi_rife46_interpolate_host(ctx, C.c_void_p(fr.data_ptr()), n, h, w, c, 1, 6, vp(f0), vp(f1), vp(ts), vp(slots),
+    rc = emu.vfi_rife46_interpolate_host(ctx, C.c_void_p(fr.data_ptr()), n, h, w, c, 1, 6, vp(f0), vp(f1), vp(ts), vp(slots), None,
                                          len(tasks), C.c_float(1.0), C.c_void_p(out.data_ptr()))
     assert rc == 0, emu.vfi_last_error()
     for i, (p_, t) in enumerate(tasks):
@@ -202,11 +202,30 @@ def test_rife_host_pipeline_ring_and_shards_on_host(emu):
     out2 = torch.zeros(len(tasks2), h, w, 3)
     os.environ["VFI_STAGE_SLOTS"] = "2"
     try:
-        rc = emu.vfi_rife46_interpolate_host(ctx, C.c_void_p(fr2.data_ptr()), n2, h, w, c, 0, n2, vp(g0), vp(g1), vp(gt), None,
+        rc = emu.vfi_rife46_interpolate_host(ctx, C.c_void_p(fr2.data_ptr()), n2, h, w, c, 0, n2, vp(g0), vp(g1), vp(gt), None, None,
                                              len(tasks2), C.c_float(1.0), C.c_void_p(out2.data_ptr()))
     finally:
         del os.environ["VFI_STAGE_SLOTS"]
     assert rc == 0, emu.vfi_last_error()
+    # the same with pass-through slots (what the node does): frames 0..11 -> slots 20.., 4-channel source, frame 3 and 8 are
+    # referenced by no task, frame 7 has no slot
+    fr4 = torch.cat([fr2, torch.full((n2, h, w, 1), 0.25)], -1).contiguous()
+    big = torch.full((40, h, w, 3), -1.0)
+    fs = np.asarray([20 + i for i in range(n2)], dtype=np.int32)
+    fs[7] = -1
+    sl2 = np.arange(len(tasks2), dtype=np.int32)
+    os.environ["VFI_STAGE_SLOTS"] = "2"
+    try:
+        rc = emu.vfi_rife46_interpolate_host(ctx, C.c_void_p(fr4.data_ptr()), n2, h, w, 4, 0, n2, vp(g0), vp(g1), vp(gt), vp(sl2),
+                                             vp(fs), len(tasks2), C.c_float(1.0), C.c_void_p(big.data_ptr()))
+    finally:
+        del os.environ["VFI_STAGE_SLOTS"]
+    assert rc == 0, emu.vfi_last_error()
+    assert torch.equal(big[: len(tasks2)], out2)
+    for i in range(n2):
+        if i != 7:
+            assert torch.equal(big[20 + i], fr2[i]), i
+    assert float(big[27].max()) == -1.0 and float(big[len(tasks2):20].max()) == -1.0
     for i, (p_, t) in enumerate(tasks2):
         one = torch.zeros(1, h, w, 3)
         a0, a1, at = np.asarray([p_], np.int32), np.asarray([p_ + 1], np.int32), np.asarray([t], np.float32)
@@ -215,7 +234,7 @@ def test_rife_host_pipeline_ring_and_shards_on_host(emu):
         assert torch.equal(out2[i], one[0]), (i, p_, t)
     # a task outside the shard is refused
     bad0, bad1 = np.asarray([0], np.int32), np.asarray([1], np.int32)
-    rc = emu.vfi_rife46_interpolate_host(ctx, C.c_void_p(fr.data_ptr()), n, h, w, c, 1, 6, vp(bad0), vp(bad1), vp(ts), None, 1,
+    rc = emu.vfi_rife46_interpolate_host(ctx, C.c_void_p(fr.data_ptr()), n, h, w, c, 1, 6, vp(bad0), vp(bad1), vp(ts), None, None, 1,
                                          C.c_float(1.0), C.c_void_p(out.data_ptr()))
     assert rc != 0
     assert emu.vfi_destroy(ctx) == 0

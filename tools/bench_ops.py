@@ -81,13 +81,8 @@ def main():
         # soft mode (what GMFSS calls): the reference's cat -> splat -> slice -> divide chain vs the fused two-launch form
         m = torch.randn(1, 1, h, w, device="cuda", generator=g)
         soft_bytes = (x.numel() * 4 + f.numel() + 3 * m.numel()) * 4      # read C + 3, memset C + 1, splat, normalise r/w C
-        try:
-            ms = timed(lambda: OPS.softsplat(x, f, m, "soft"), flush)
-            add("softsplat_soft_chain", (1, c, h, w), ms, soft_bytes, 8.0 * x.numel(), "cat, exp, splat, slice, divide")
-            ms = timed(lambda: OPS.softsplat_fused(x, f, m, "soft"), flush)
-            add("softsplat_soft_fused", (1, c, h, w), ms, soft_bytes, 8.0 * x.numel(), "vfi_softsplat_weighted, two launches")
-        except Exception as e:  # noqa: BLE001  (the fused form had not run on a GPU when this was written)
-            print("softsplat soft-mode timing failed:", repr(e)[:300], file=sys.stderr)
+        ms = timed(lambda: OPS.softsplat(x, f, m, "soft"), flush)
+        add("softsplat_soft", (1, c, h, w), ms, soft_bytes, 8.0 * x.numel(), "vfi_softsplat_weighted, two launches")
     # 9x9 volumes
     for c, h, w in ((64, 96, 160), (128, 192, 320)):
         one = torch.randn(1, c, h, w, device="cuda", generator=g)

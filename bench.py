@@ -249,7 +249,9 @@ def main():
     from cfi_b200 import _lib as cfi_lib
 
     torch.cuda.set_device(local_rank)
-    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
+    # every rank (also the single one) runs on the cores of its GPU's NUMA node: host staging copies and the pinned
+    # buffers then stay local to the PCIe root the GPU hangs off (what `numactl --cpunodebind` would do for a ComfyUI worker)
+    numa = bind_to_gpu_numa_node(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist

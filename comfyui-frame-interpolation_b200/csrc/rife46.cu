@@ -1019,7 +1019,7 @@ int vfi_rife46_interpolate_host(vfi_ctx* c, const float* frames, int n_frames, i
   if (frame_slot)
     for (int f = frame_lo; f < frame_hi; ++f) any_pt = any_pt || frame_slot[f] >= 0;
   const bool stage_in = any_ring;
-  const int copy_threads = env_int("VFI_COPY_THREADS", 8, 1, 32);
+  const int copy_threads = env_int("VFI_COPY_THREADS", 12, 1, 32);
   const size_t ring_mb = (size_t)env_int("VFI_STAGE_MB", 384, 32, 8192);
   const int force_slots = env_int("VFI_STAGE_SLOTS", 0, 0, 64);  // tests: a ring far smaller than the clip
   const int NS = !stage_in ? 0 : force_slots ? force_slots : (int)std::max<size_t>(4, std::min<size_t>(32, (ring_mb << 20) / frame_bytes));
@@ -1282,7 +1282,7 @@ int vfi_host_copy_frames(const float* frames, int n_frames, int H, int W, int C,
         const float* s = frames + (size_t)f * px * C;
         float* d = out + (size_t)slot[f] * px * 3;
         if (C == 3) {
-          std::memcpy(d + lo * 3, s + lo * 3, (hi - lo) * 3 * sizeof(float));
+          stream_copy(d + lo * 3, s + lo * 3, (hi - lo) * 3 * sizeof(float));
         } else {
           for (size_t i = lo; i < hi; ++i) {
             d[i * 3 + 0] = s[i * C + 0];

@@ -40,7 +40,7 @@ def _i32(a):
 
 def host_copy_frames(frames: torch.Tensor, slots, out: torch.Tensor, threads: int = 0):
     """out[slots[i]] = frames[i, ..., :3] for every i with slots[i] >= 0 (CPU float32 tensors), on `threads` copy threads of
-    the library (default VFI_COPY_THREADS or 8) - vfi_host_copy_frames."""
+    the library (default VFI_COPY_THREADS or 12) - vfi_host_copy_frames."""
     assert not frames.is_cuda and not out.is_cuda and frames.dtype == torch.float32 and out.dtype == torch.float32
     assert frames.is_contiguous() and out.is_contiguous() and frames.dim() == 4 and tuple(out.shape[1:3]) == tuple(frames.shape[1:3])
     n, h, w, c = frames.shape
@@ -48,7 +48,7 @@ def host_copy_frames(frames: torch.Tensor, slots, out: torch.Tensor, threads: in
     assert len(sl) == n and (len(sl) == 0 or int(sl.max()) < out.shape[0]) and out.shape[3] == 3
     if threads <= 0:
         import os
-        threads = int(os.environ.get("VFI_COPY_THREADS", "8"))
+        threads = int(os.environ.get("VFI_COPY_THREADS", "12"))
     check(lib().vfi_host_copy_frames(frames.data_ptr(), n, h, w, c, sl.ctypes.data, out.data_ptr(), int(threads)))
 
 

@@ -41,6 +41,10 @@ UNIT = "frames/s"
 FLOPS_PER_FRAME = 175.245e9          # SURVEY.md section 8d (87.62 GMAC)
 CPU_SAMPLE_FRAMES = 3                # 2 pairs of the same clip for the CPU legs (bounded sample)
 CPU_ARCH = "4.6"
+# N > 1: the shard's 63 pairs leave for rank 0 in this many chunks, each behind the kernels that produce it.  8 chunks = one
+# internal pass of 8 pairs per chunk (r02: 16 chunks of 4 pairs made every pass half as wide - the latency-bound blocks 0 / 1
+# cost the same per pass - and the step 4.7 ms slower than N = 1, whatever the transport)
+GATHER_CHUNKS = int(os.environ.get("VFI_GATHER_CHUNKS", "8"))
 
 
 def _peaks():
@@ -218,7 +222,9 @@ def main():
     config = {"workload": f"RIFE {a.arch}, 2x multiplier, {a.frames}-frame synthetic 1080p clip per GPU (BASELINE configs[1])",
               "resolution": [H, W], "frames_per_gpu": a.frames, "pairs_per_gpu": a.frames - 1,
               "padded": [1088, 1920], "weights": "seeded synthetic (oracle.synthetic_state_dict(0)); no checkpoint ships",
-              "parallelism": f"frame-pair shards x{a.gpus}; each rank's outputs gathered to rank 0 by NCCL in 16 chunks, overlapped with the next chunk's compute" if a.gpus > 1 else "1 GPU",
+              "parallelism": (f"frame-pair shards x{a.gpus}; each rank's output frames land on rank 0 over NVLink in {GATHER_CHUNKS} chunks behind the kernels that "
+                              f"produce them ({'NCCL send/recv' if os.environ.get('VFI_GATHER', 'nccl') != 'push' else 'copy-engine pushes into an IPC-shared buffer, NCCL for the handle and the barriers'})")
+              if a.gpus > 1 else "1 GPU",
               "l2": "inputs larger than L2 (1.6 GB clip, 1.6 GB output per step)"}
 
     sd = O.synthetic_state_dict(0, arch=a.arch)
@@ -282,11 +288,22 @@ def main():
     def run_slice(lo, hi):
         eng.forward(dev_clip, f0[lo:hi], f1[lo:hi], ts[lo:hi], out=dev_out[lo:hi])
 
+    # the only exchange of the path, inside the timed region for N > 1: every rank's interpolated frames end up on rank 0.
+    # Default: chunked dist.gather (NCCL send / recv kernels over NVLink, 595 GB/s alone at N = 2).  VFI_GATHER=push: copy-engine
+    # pushes into an IPC-shared buffer on rank 0 (shard.PushGather) - measured r02 on this pool: 35 GB/s, i.e. the IPC mapping
+    # gets no peer access inside these containers and the copy is staged through the host, so it stays an option only.
+    pusher = None
+    if dist is not None and os.environ.get("VFI_GATHER", "nccl") == "push":
+        pusher = shard.PushGather(npairs, (H, W, 3), torch.float32, dist, dst=0)
+        gather_list = None
+
     def step_device():
         if dist is None:
             eng.forward(dev_clip, f0, f1, ts, out=dev_out)
+        elif pusher is not None:
+            shard.forward_and_push(run_slice, dev_out, npairs, pusher, nchunks=GATHER_CHUNKS)
         else:  # chunks of the shard are gathered to rank 0 while the next chunk computes (shard.forward_and_gather)
-            shard.forward_and_gather(run_slice, dev_out, [npairs] * world, dist, dst=0, nchunks=16, gathered=gather_list)
+            shard.forward_and_gather(run_slice, dev_out, [npairs] * world, dist, dst=0, nchunks=GATHER_CHUNKS, gathered=gather_list)
 
     for _ in range(a.warmup):
         step_device()
@@ -310,6 +327,15 @@ def main():
     launches = eng.launch_count() - l0
     ms_dev = e0.elapsed_time(e1)
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
+    gather_ok = None
+    if dist is not None:  # what landed on rank 0 is what every rank computed (sums of each rank's first and last frame)
+        mine = torch.stack([dev_out[0].double().sum(), dev_out[-1].double().sum()])
+        sums = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(sums, mine)
+        if rank == 0:
+            got = pusher.buffer if pusher is not None else torch.stack(gather_list)
+            gather_ok = all(bool(torch.equal(torch.stack([got[r][0].double().sum(), got[r][-1].double().sum()]), sums[r]))
+                            for r in range(world))
 
     # ---- end to end through the bare C-ABI call on pre-pinned buffers ("e2e_capi", the r01 figure)
     host_in = clip.contiguous().pin_memory()
@@ -461,7 +487,7 @@ def main():
                         "node_output_matches_device_path": node_ok},
                 "e2e_capi": {"value": e2e_capi, "unit": UNIT, "ms_per_step": ms_capi / a.steps,
                              "via": "vfi_rife46_interpolate_host on pre-pinned buffers", "host_equals_device_path": same},
-                "psnr_db": psnr_db, "numa": numa, "kernel_groups": groups,
+                "psnr_db": psnr_db, "numa": numa, "gather_verified": gather_ok, "kernel_groups": groups,
                 "gpu_launches": launches, "lib": cfi_lib.lib().vfi_version().decode(), "clocks": clocks,
                 "model_tflops": value * FLOPS_PER_FRAME / 1e12 if a.arch == "4.6" else None,
                 "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu}

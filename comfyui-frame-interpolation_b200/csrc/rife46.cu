@@ -694,6 +694,12 @@ int vfi_create(int device, vfi_ctx** out) {
   vfi_ctx* c = new vfi_ctx();
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
+  {
+    // VFI_NUM_SMS=n: size the persistent grids for n SMs (an even number, at least 2), leaving the rest to kernels of other
+    // streams - e.g. NCCL's receive kernels on the rank that gathers every other rank's frames
+    const int want = env_int("VFI_NUM_SMS", 0, 0, 4096);
+    if (want >= 2 && want < c->num_sms) c->num_sms = want & ~1;
+  }
   CK(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));

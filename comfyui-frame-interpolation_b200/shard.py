@@ -108,6 +108,70 @@ def forward_and_gather(run_slice, local_out: torch.Tensor, counts: Sequence[int]
     return gathered if rank == dst else None
 
 
+class PushGather:
+    """The output-frame gather as copy-engine pushes over NVLink into the destination rank's HBM (GPU box only).
+
+    dist.gather is NCCL send / recv: its kernels need SMs on both ends, and every hot kernel of this path is a persistent
+    grid of exactly one CTA per SM - with a few SMs taken by NCCL the last CTAs of each layer wait for a free SM and the
+    layer takes up to twice as long (r02, N = 2: 21.7 -> 26.7 ms per step with the chunked NCCL gather, the same 26.7 ms as
+    in r01 although the step itself had become 3.4 ms faster).  Here the destination rank allocates one [world, rows, ...]
+    buffer, shares it through CUDA IPC, and every rank writes its rows straight into its slice with an ordinary
+    device-to-device copy on a side stream (a peer copy = DMA engines over NVLink / NVSwitch, no SMs anywhere), chunk by
+    chunk behind the kernels that produce them.  torch.distributed (NCCL) carries the IPC handle once and the barrier that
+    ends a step.
+
+    Measured r02 (profiles/r02_n2c_probe.log): correct, but 35 GB/s - inside this pool's containers the IPC mapping gets no
+    NVLink peer access and the copy is staged through host memory - against 595 GB/s for the NCCL gather, so bench.py keeps
+    the NCCL gather (in chunks of one internal pass) and this class is opt-in (VFI_GATHER=push) for hosts where IPC peer
+    mappings work."""
+
+    def __init__(self, rows: int, row_shape, dtype, dist, dst: int = 0, device=None):
+        import torch.multiprocessing.reductions as red
+        self.dist, self.dst = dist, dst
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        box = [None]
+        self.buffer = None
+        if self.rank == dst:
+            self.buffer = torch.empty((self.world, rows) + tuple(row_shape), dtype=dtype, device=self.device)
+            fn, args = red.reduce_tensor(self.buffer)
+            box = [(fn, args)]
+        dist.broadcast_object_list(box, src=dst)
+        if self.rank == dst:
+            self.remote = self.buffer
+        else:
+            fn, args = box[0]
+            self.remote = fn(*args)      # the destination's buffer, mapped into this process (lives on the dst GPU)
+        self.mine = self.remote[self.rank]
+        self.stream = torch.cuda.Stream(device=self.device)
+
+    def push(self, local_rows: torch.Tensor, lo: int, hi: int):
+        """Copy local_rows[lo:hi] into this rank's slice on the destination, behind the work already queued on the current
+        stream (call it right after the kernels that produce these rows)."""
+        ev = torch.cuda.Event()
+        ev.record()
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            self.mine[lo:hi].copy_(local_rows[lo:hi], non_blocking=True)
+
+    def finish(self):
+        """All pushes of this rank have landed (the caller still needs a barrier before the destination reads)."""
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+    def close(self):
+        self.mine = None
+        self.remote = None
+        self.buffer = None
+
+
+def forward_and_push(run_slice, local_out: torch.Tensor, n_rows: int, gather: "PushGather", nchunks: int = 16):
+    """Compute this rank's rows chunk by chunk and push every chunk to the destination while the next one computes."""
+    for lo, hi in chunk_bounds(n_rows, nchunks):
+        run_slice(lo, hi)
+        gather.push(local_out, lo, hi)
+    gather.finish()
+
+
 # ------------------------------------------------------------------------------------------------- FILM
 def shard_pairs_by_cost(costs: Sequence[float], world: int) -> List[Tuple[int, int]]:
     """Contiguous [lo, hi) pair ranges, one per rank, balancing the summed cost (FILM: a pair costs multiplier - 1

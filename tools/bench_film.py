@@ -144,7 +144,7 @@ def main():
         peaks = B._peaks()
         total = n_interp * world
         value = total * a.steps / (ms_dev / 1e3)
-        tf = 2.0 * macs_per_call * value / 1e12
+        tf = 2.0 * macs_per_call * value / world / 1e12   # per GPU: the peak is one GPU's
         line = {
             "metric": "interpolated frames/sec @1080p FILM %dx" % m if (H, W) == (1080, 1920) else
                       "interpolated frames/sec @%dx%d FILM %dx" % (W, H, m),

@@ -126,7 +126,7 @@ def main():
         total = npairs * world
         value = total * a.steps / (ms_dev / 1e3)
         px = float(H * W)
-        tf = 2.0 * TRUNK_MACS_PER_PX * px * value / 1e12
+        tf = 2.0 * TRUNK_MACS_PER_PX * px * value / world / 1e12   # per GPU: the peak is one GPU's
         peak_t = peaks["tflops_sustained"] or peaks["tflops"]
         line = {"metric": f"interpolated frames/sec @{W}x{H} Sepconv 2x", "value": value, "unit": "frames/s", "n_gpus": world,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_dev / a.steps, "higher_is_better": True,

@@ -268,6 +268,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if rank == 0 and world > 1 and os.environ.get("VFI_NUM_SMS_RANK0"):
+        # the gathering rank leaves a few SMs to NCCL's receive kernels (its persistent grids are sized for the rest)
+        os.environ["VFI_NUM_SMS"] = os.environ["VFI_NUM_SMS_RANK0"]
     nf = a.frames
     clip = O.synthetic_clip(nf, H, W, seed=1234 + rank)            # this rank's shard (own content, same shape)
     eng = Rife46Engine(sd, device=local_rank, dtype=a.dtype, batch=a.batch, arch=a.arch)

@@ -196,7 +196,7 @@ def main():
     ap.add_argument("--dtype", default="float32", help="node dtype: float32/float16 -> fp16 operands, bfloat16 -> bf16")
     ap.add_argument("--frames", type=int, default=NFRAMES)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--workload", default="rife", choices=["rife", "film", "sepconv"],
+    ap.add_argument("--workload", default="rife", choices=["rife", "film", "sepconv", "gmfss"],
                     help="rife = the BASELINE.json metric (default).  film / sepconv: the side workloads of BASELINE configs[2] / "
                          "[4] through tools/bench_film.py / tools/bench_sepconv.py (same JSON-line contract, own metric name)")
     ap.add_argument("--arch", default="4.6", choices=["4.6", "4.7", "4.17", "4.26"],
@@ -204,7 +204,7 @@ def main():
     a, extra = ap.parse_known_args()
     if a.workload != "rife":  # the other model families keep their own harness; same launch convention (torchrun for N > 1)
         import runpy
-        tool = {"film": "bench_film.py", "sepconv": "bench_sepconv.py"}[a.workload]
+        tool = {"film": "bench_film.py", "sepconv": "bench_sepconv.py", "gmfss": "bench_gmfss.py"}[a.workload]
         sys.argv = [os.path.join(ROOT, "tools", tool), "--steps", str(a.steps), "--warmup", str(a.warmup)] + extra
         runpy.run_path(sys.argv[0], run_name="__main__")
         return

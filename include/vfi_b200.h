@@ -203,6 +203,36 @@ int vfi_sync(vfi_ctx* ctx);
 int vfi_rife_profile(vfi_ctx* ctx, int enable);
 int vfi_rife_profile_read(vfi_ctx* ctx, int32_t* ids, float* total_ms, int32_t* count, int cap, int* n_groups);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * GMFSS Fortuna (union) building blocks - csrc/gmops.cu; the schedule that strings them together is host code
+ * (comfyui-frame-interpolation_b200/gmfss.py), mirroring vfi_models/gmfss_fortuna/GMFSS_Fortuna_union_arch.py :1726-1857.
+ * They replace what that file runs through ATen / cuDNN / cuBLAS between its softsplat calls: F.conv2d / conv_transpose2d
+ * with the nn.PReLU in front and the residual adds behind (:1420-1688, :165-312), F.instance_norm (:165-215), nn.Linear /
+ * torch.matmul / softmax / LayerNorm / GELU of the swin transformer (:315-685) and of the flow propagation (:688-803),
+ * split_feature / merge_splits with torch.roll (:366-436, :1059-1131), PositionEmbeddingSine (:1015-1056),
+ * local_correlation_softmax (:846-913), upsample_flow (:1220-1260), grid_sample / F.interpolate (:955-991, :1375-1417),
+ * MetricNet's input assembly with the forward-backward check (:994-1013, :1429-1455), F.pixel_shuffle, torch.cat / slicing.
+ * DEVICE pointers, contiguous float32, NCHW tensors (tokens: [B, L, C]); `stream` is the caller's CUDA stream; 0 = OK.
+ * Argument meaning is documented at each kernel in csrc/gmops.cu. */
+int vfi_gm_conv2d(const float* in, const float* w, const float* bias, const float* res1, const float* res2, float* out, int N, int Cin, int H, int W, int Cout, int k, int stride, int pad, int in_ctot, int in_coff, int out_ctot, int out_coff, int has_pre, float pre_slope, int post, float post_slope, void* stream);
+int vfi_gm_convt4(const float* in, const float* w, const float* bias, float* out, int N, int Cin, int H, int W, int Cout, int has_pre, float pre_slope, void* stream);
+int vfi_gm_instance_norm(const float* in, float* out, int planes, int HW, float eps, int relu, void* stream);
+int vfi_gm_layer_norm(const float* x, const float* gamma, const float* beta, const float* src, float* out, int rows, int C, float eps, void* stream);
+int vfi_gm_softmax_rows(float* x, int rows, int L, void* stream);
+int vfi_gm_gemm(int bt, const float* A, const float* B, const float* bias, const float* mask, float* C, int nb, int M, int N, int K, int lda, int ldb, int ldc, long long sA, long long sB, long long sC, float alpha, int nmask, int act, void* stream);
+int vfi_gm_window(const float* src, float* dst, int B, int H, int W, int C, int k, int sh, int sw, int to_windows, void* stream);
+int vfi_gm_nchw_tokens(const float* src, float* dst, int B, int C, int HW, int to_tokens, void* stream);
+int vfi_gm_add_position(float* x, int B, int C, int H, int W, int k, void* stream);
+int vfi_gm_local_match(const float* f0, const float* f1, float* flow, int B, int C, int H, int W, int R, void* stream);
+int vfi_gm_local_prop(const float* q, const float* k, const float* flow, float* out, int B, int C, int H, int W, void* stream);
+int vfi_gm_convex_up(const float* mask, const float* flow, float* up, int B, int H, int W, int f, void* stream);
+int vfi_gm_warp_zeros(const float* in, const float* flow, float* out, int B, int C, int H, int W, void* stream);
+int vfi_gm_resize(const float* in, float* out, int BC, int H, int W, int Ho, int Wo, int align, float mul, void* stream);
+int vfi_gm_metric_input(const float* img0, const float* img1, const float* f01, const float* f10, float* out, int B, int H, int W, void* stream);
+int vfi_gm_pixel_shuffle2(const float* in, float* out, int B, int C, int H, int W, void* stream);
+int vfi_gm_axpby(const float* a, const float* b, float* out, long long n, float alpha, float beta, float gamma, int post, void* stream);
+int vfi_gm_copy_slice(const float* src, float* dst, int B, int C, int Hs, int Ws, int Hd, int Wd, int s_ctot, int s_coff, int d_ctot, int d_coff, int src_nhwc, int dst_nhwc, const float* mean, const float* stdv, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

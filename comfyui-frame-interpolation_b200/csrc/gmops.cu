@@ -16,6 +16,7 @@
 // First version: correct and simple - one thread per small output tile with register blocking, operands through L1 (no
 // shared-memory staging, no tensor cores); its parity is pinned on the CPU through tests/host_emu before any GPU run.
 #include <cmath>
+#include <cstdint>
 #include <string>
 
 #include "../../include/vfi_b200.h"
@@ -97,6 +98,83 @@ __global__ void conv2d_kernel(const float* __restrict__ in, const float* __restr
         else if (post == 2) v = tanhf(v) * 10.f;
         else if (post == 3) v = v < 0.f ? v * post_slope : v;
         out[(((size_t)n * out_ctot + out_coff + co) * Ho + yo) * Wo + xo] = v;
+      }
+    }
+  }
+}
+
+// The same convolution, the form the heavy layers run in: weights re-packed once at load time to wt[(ci, ky, kx)][CoutP]
+// (output channel fastest, padded to a multiple of 16, gmfss.Ops.pack_conv) so that the 16 weights of a tap are four 16-byte
+// loads; thread = (n, 16 output channels, yo, PX = 8 consecutive xo); per (ci, ky) the input row segment the 8 pixels need
+// is loaded once into registers and reused by all kx taps: (7 S + K) + 4 K loads for 128 K multiply-adds, K and the stride S
+// compile-time so that everything stays in registers.  (First GPU run of the scalar-weight form above, r02: 4.7 TFLOP/s over
+// the whole GMFSS frame - one scalar weight load per four multiply-adds.)
+template <int K, int S>
+__global__ void conv2d_packed_kernel(const float* __restrict__ in, const float* __restrict__ wt, const float* __restrict__ bias,
+                                     const float* __restrict__ res1, const float* __restrict__ res2, float* __restrict__ out, int N,
+                                     int Cin, int H, int W, int Cout, int CoutP, int Ho, int Wo, int pad, int in_ctot, int in_coff,
+                                     int out_ctot, int out_coff, int has_pre, float pre_slope, int post, float post_slope) {
+  constexpr int PX = 8, SEG = (PX - 1) * S + K;
+  const int cog = CoutP / 16, xq = (Wo + PX - 1) / PX;
+  const size_t total = (size_t)N * cog * Ho * xq;
+  for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
+    const int xo0 = (int)(id % xq) * PX;
+    size_t r = id / xq;
+    const int yo = (int)(r % Ho);
+    r /= Ho;
+    const int co0 = (int)(r % cog) * 16;
+    const int n = (int)(r / cog);
+    float acc[PX][16];
+#pragma unroll
+    for (int p = 0; p < PX; ++p)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[p][j] = 0.f;
+    const int xs = xo0 * S - pad;
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float* ip = in + ((size_t)n * in_ctot + in_coff + ci) * H * W;
+#pragma unroll
+      for (int ky = 0; ky < K; ++ky) {
+        const int yi = yo * S - pad + ky;
+        if (yi < 0 || yi >= H) continue;
+        float seg[SEG];
+#pragma unroll
+        for (int i = 0; i < SEG; ++i) {
+          const int xi = xs + i;
+          seg[i] = (xi >= 0 && xi < W) ? act_pre(__ldg(ip + (size_t)yi * W + xi), has_pre, pre_slope) : 0.f;
+        }
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          const float4* wp = reinterpret_cast<const float4*>(wt + ((size_t)(ci * K + ky) * K + kx) * CoutP + co0);
+          const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3);
+          const float wv[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+#pragma unroll
+          for (int p = 0; p < PX; ++p) {
+            const float v = seg[p * S + kx];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[p][j] = fmaf(v, wv[j], acc[p][j]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int co = co0 + j;
+      if (co < Cout) {
+        const float b = bias ? __ldg(bias + co) : 0.f;
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+          const int xo = xo0 + p;
+          if (xo < Wo) {
+            float v = acc[p][j] + b;
+            const size_t ro = (((size_t)n * Cout + co) * Ho + yo) * Wo + xo;
+            if (res1) v += res1[ro];
+            if (res2) v += res2[ro];
+            if (post == 1) v = fmaxf(v, 0.f);
+            else if (post == 2) v = tanhf(v) * 10.f;
+            else if (post == 3) v = v < 0.f ? v * post_slope : v;
+            out[(((size_t)n * out_ctot + out_coff + co) * Ho + yo) * Wo + xo] = v;
+          }
+        }
       }
     }
   }
@@ -285,6 +363,74 @@ __global__ void gemm_kernel(const float* __restrict__ A, const float* __restrict
       if (act == 1) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));  // GELU (erf form, nn.GELU default)
       C[(size_t)b * sC + (size_t)(m0 + i) * ldc + n] = v;
     }
+  }
+}
+
+// C[b][m][n] = act( alpha * sum_k A[b][m][k] * B[b][k][n] + bias[n] + mask[b % nmask][m][n] ), the form the heavy products run
+// in (linears with the weight transposed once at load time, attention scores against the transposed keys, P V): thread = an
+// 8 x 8 tile of C, lanes along n; per four k: eight 16-byte loads of A (one per row, the same for every lane of a row group)
+// and eight of B (coalesced) for 256 multiply-adds.  Needs K % 4 == 0, N % 8 == 0, 16-byte aligned rows.
+__global__ void gemm_nn8_kernel(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ bias,
+                                const float* __restrict__ mask, float* __restrict__ C, int nb, int M, int N, int K, int lda, int ldb,
+                                int ldc, long long sA, long long sB, long long sC, float alpha, int nmask, int act) {
+  const int mq = (M + 7) / 8, nq = N / 8;
+  const size_t total = (size_t)nb * mq * nq;
+  for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
+    const int n0 = (int)(id % nq) * 8;
+    size_t r = id / nq;
+    const int m0 = (int)(r % mq) * 8;
+    const int b = (int)(r / mq);
+    const float* a = A + (size_t)b * sA;
+    const float* bp = B + (size_t)b * sB + n0;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    int row[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) row[i] = min(m0 + i, M - 1);  // rows past M recompute the last one and are not stored
+    for (int k = 0; k < K; k += 4) {
+      float4 av[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) av[i] = __ldg(reinterpret_cast<const float4*>(a + (size_t)row[i] * lda + k));
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp + (size_t)(k + kk) * ldb));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bp + (size_t)(k + kk) * ldb + 4));
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float x = kk == 0 ? av[i].x : kk == 1 ? av[i].y : kk == 2 ? av[i].z : av[i].w;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(x, bv[j], acc[i][j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (m0 + i < M) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v = acc[i][j] * alpha + (bias ? __ldg(bias + n0 + j) : 0.f);
+          if (mask) v += __ldg(mask + ((size_t)(b % nmask) * M + m0 + i) * N + n0 + j);
+          if (act == 1) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+          C[(size_t)b * sC + (size_t)(m0 + i) * ldc + n0 + j] = v;
+        }
+      }
+    }
+  }
+}
+
+// [nb, R, C] -> [nb, C, R]
+__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int nb, int R, int C) {
+  const size_t total = (size_t)nb * R * C;
+  for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
+    const int rr = (int)(id % R);
+    size_t q = id / R;
+    const int c = (int)(q % C);
+    const int b = (int)(q / C);
+    dst[id] = src[((size_t)b * R + rr) * C + c];
   }
 }
 
@@ -626,6 +772,24 @@ cudaError_t gm_conv2d(const float* in, const float* w, const float* bias, const 
   GM_LAUNCH(conv2d_kernel, total, in, w, bias, res1, res2, out, N, Cin, H, W, Cout, Ho, Wo, k, stride, pad, in_ctot, in_coff, out_ctot,
             out_coff, has_pre, pre_slope, post, post_slope);
 }
+// packed form: wt [Cin * k * k][CoutP]; returns cudaErrorNotSupported for a (k, stride) the fast kernel is not built for
+cudaError_t gm_conv2d_packed(const float* in, const float* wt, const float* bias, const float* res1, const float* res2, float* out,
+                             int N, int Cin, int H, int W, int Cout, int CoutP, int k, int stride, int pad, int in_ctot, int in_coff,
+                             int out_ctot, int out_coff, int has_pre, float pre_slope, int post, float post_slope, cudaStream_t st) {
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  const size_t total = (size_t)N * (CoutP / 16) * Ho * ((Wo + 7) / 8);
+#define GM_CONV_CASE(KK, SS)                                                                                                        \
+  if (k == KK && stride == SS)                                                                                                      \
+    GM_LAUNCH((conv2d_packed_kernel<KK, SS>), total, in, wt, bias, res1, res2, out, N, Cin, H, W, Cout, CoutP, Ho, Wo, pad, in_ctot, \
+              in_coff, out_ctot, out_coff, has_pre, pre_slope, post, post_slope)
+  GM_CONV_CASE(3, 1);
+  GM_CONV_CASE(3, 2);
+  GM_CONV_CASE(1, 1);
+  GM_CONV_CASE(1, 2);
+  GM_CONV_CASE(7, 2);
+#undef GM_CONV_CASE
+  return cudaErrorNotSupported;
+}
 cudaError_t gm_convt4(const float* in, const float* w, const float* bias, float* out, int N, int Cin, int H, int W, int Cout,
                       int has_pre, float pre_slope, cudaStream_t st) {
   const size_t total = (size_t)N * ((Cout + 15) / 16) * (2 * H) * ((2 * W + 3) / 4);
@@ -647,9 +811,17 @@ cudaError_t gm_softmax_rows(float* x, int rows, int L, cudaStream_t st) {
 cudaError_t gm_gemm(int bt, const float* A, const float* B, const float* bias, const float* mask, float* C, int nb, int M, int N, int K,
                     int lda, int ldb, int ldc, long long sA, long long sB, long long sC, float alpha, int nmask, int act,
                     cudaStream_t st) {
+  const bool aligned = ((K | N | lda | ldb) & 3) == 0 && (N & 7) == 0 && ((sA | sB) & 3) == 0 &&
+                       ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0;
+  if (!bt && aligned)
+    GM_LAUNCH(gemm_nn8_kernel, (size_t)nb * ((M + 7) / 8) * (N / 8), A, B, bias, mask, C, nb, M, N, K, lda, ldb, ldc, sA, sB, sC, alpha,
+              nmask, act);
   const size_t total = (size_t)nb * ((M + 7) / 8) * N;
   if (bt) GM_LAUNCH(gemm_kernel<true>, total, A, B, bias, mask, C, nb, M, N, K, lda, ldb, ldc, sA, sB, sC, alpha, nmask, act);
   GM_LAUNCH(gemm_kernel<false>, total, A, B, bias, mask, C, nb, M, N, K, lda, ldb, ldc, sA, sB, sC, alpha, nmask, act);
+}
+cudaError_t gm_transpose(const float* src, float* dst, int nb, int R, int C, cudaStream_t st) {
+  GM_LAUNCH(transpose_kernel, (size_t)nb * R * C, src, dst, nb, R, C);
 }
 cudaError_t gm_window(const float* src, float* dst, int B, int H, int W, int C, int k, int sh, int sw, int to_windows, cudaStream_t st) {
   GM_LAUNCH(window_kernel, (size_t)B * H * W * C, src, dst, B, H, W, C, k, sh, sw, to_windows);
@@ -718,6 +890,21 @@ int vfi_gm_conv2d(const float* in, const float* w, const float* bias, const floa
   if (in_coff < 0 || in_coff + Cin > in_ctot || out_coff < 0 || out_coff + Cout > out_ctot) return gm_fail("conv2d: channel slice out of range");
   return gm_done(vfi::gm_conv2d(in, w, bias, res1, res2, out, N, Cin, H, W, Cout, k, stride, pad, in_ctot, in_coff, out_ctot, out_coff,
                                 has_pre, pre_slope, post, post_slope, (cudaStream_t)stream), "conv2d");
+}
+int vfi_gm_conv2d_packed(const float* in, const float* wt, const float* bias, const float* res1, const float* res2, float* out, int N,
+                         int Cin, int H, int W, int Cout, int CoutP, int k, int stride, int pad, int in_ctot, int in_coff, int out_ctot,
+                         int out_coff, int has_pre, float pre_slope, int post, float post_slope, void* stream) {
+  if (!in || !wt || !out || N < 1 || Cin < 1 || Cout < 1 || CoutP < Cout || (CoutP & 15) || H < 1 || W < 1 || pad < 0 ||
+      (reinterpret_cast<uintptr_t>(wt) & 15))
+    return gm_fail("conv2d_packed: bad argument");
+  if (in_coff < 0 || in_coff + Cin > in_ctot || out_coff < 0 || out_coff + Cout > out_ctot) return gm_fail("conv2d_packed: channel slice out of range");
+  if (!((k == 3 || k == 1) && (stride == 1 || stride == 2)) && !(k == 7 && stride == 2)) return gm_fail("conv2d_packed: kernel size / stride not built");
+  return gm_done(vfi::gm_conv2d_packed(in, wt, bias, res1, res2, out, N, Cin, H, W, Cout, CoutP, k, stride, pad, in_ctot, in_coff, out_ctot,
+                                       out_coff, has_pre, pre_slope, post, post_slope, (cudaStream_t)stream), "conv2d_packed");
+}
+int vfi_gm_transpose(const float* src, float* dst, int nb, int R, int C, void* stream) {
+  if (!src || !dst || nb < 1 || R < 1 || C < 1) return gm_fail("transpose: bad argument");
+  return gm_done(vfi::gm_transpose(src, dst, nb, R, C, (cudaStream_t)stream), "transpose");
 }
 int vfi_gm_convt4(const float* in, const float* w, const float* bias, float* out, int N, int Cin, int H, int W, int Cout, int has_pre,
                   float pre_slope, void* stream) {

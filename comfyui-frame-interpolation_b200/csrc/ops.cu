@@ -236,6 +236,142 @@ __global__ void __launch_bounds__(256) volume81_tile_kernel(const float* __restr
   for (int k = 0; k < 81; ++k) o[(size_t)k * hw] = acc[k] / (float)C;
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Channel-last forms (r02).  The reference's tensors are NCHW, and both ops above pay for it: the splat issues four scalar
+// atomics per (pixel, channel) into four different planes (r01 / r02 measurements: 4 - 14 % of HBM bandwidth), the volumes
+// read one value per (channel, displacement) from shared memory (one LDS per multiply-add, 6.7 % of the fp32 rate).  With
+// the channels of a pixel contiguous, a splat corner is ONE 16-byte vector atomic per four channels and a displacement of
+// the volume is a dot product of two contiguous channel vectors, reduced over the lanes of a warp with shuffles.  The C-ABI
+// keeps the reference's NCHW contract: the inputs are transposed into context-owned scratch first (coalesced both ways),
+// the results are transposed back by the kernel that finishes them (normalise / the block's staging of the 81 values).
+
+// [N, C, HW] -> [N, HW, Cp] (channels padded with zeros to Cp), 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int Cp,
+                                                           size_t HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const size_t p0 = (size_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j;
+    const size_t p = p0 + tx;
+    tile[j][tx] = (c < C && p < HW) ? src[((size_t)n * C + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const size_t p = p0 + j;
+    const int c = c0 + tx;
+    if (p < HW && c < Cp) dst[((size_t)n * HW + p) * Cp + c] = tile[tx][j];
+  }
+}
+
+// Soft / linear / average splat on channel-last data: thread = (source pixel, four channels); the pixel's weight (1, metric
+// or exp(metric)) and its four corner weights are recomputed per thread (a handful of FLOPs against a 16-byte atomic), the
+// first thread of a pixel also splats the weight into the normalisation plane.  acc [N, HW, Cp], norm [N, HW], both zeroed.
+__global__ void softsplat_nhwc_kernel(const float* __restrict__ in, const float* __restrict__ flow, const float* __restrict__ metric,
+                                      int mode, float* __restrict__ acc, float* __restrict__ norm, int N, int Cp, int H, int W) {
+  const size_t hw = (size_t)H * W;
+  const int cq = Cp >> 2;
+  const size_t total = (size_t)N * hw * cq;
+  for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
+    const int q = (int)(id % cq);
+    const size_t pid = id / cq;  // n * hw + pixel
+    const size_t pix = pid % hw;
+    const int n = (int)(pid / hw);
+    const int x = (int)(pix % W), y = (int)(pix / W);
+    const float fx = (float)x + __ldg(flow + ((size_t)n * 2 + 0) * hw + pix);
+    const float fy = (float)y + __ldg(flow + ((size_t)n * 2 + 1) * hw + pix);
+    if (!isfinite(fx) || !isfinite(fy)) continue;  // softsplat.py:158-159
+    const float ws = mode == 0 ? 1.f : (mode == 1 ? __ldg(metric + pid) : expf(__ldg(metric + pid)));
+    const int x0 = (int)floorf(fx), y0 = (int)floorf(fy);
+    const int x1 = x0 + 1, y1 = y0 + 1;
+    const float wnw = ((float)x1 - fx) * ((float)y1 - fy);
+    const float wne = (fx - (float)x0) * ((float)y1 - fy);
+    const float wsw = ((float)x1 - fx) * (fy - (float)y0);
+    const float wse = (fx - (float)x0) * (fy - (float)y0);
+    const bool inx0 = x0 >= 0 && x0 < W, inx1 = x1 >= 0 && x1 < W;
+    const bool iny0 = y0 >= 0 && y0 < H, iny1 = y1 >= 0 && y1 < H;
+    float4 v = __ldg(reinterpret_cast<const float4*>(in + pid * Cp) + q);
+    v.x *= ws; v.y *= ws; v.z *= ws; v.w *= ws;   // (in * weight) rounded first, then times the corner weight: the reference's order
+    float* base = acc + (size_t)n * hw * Cp + 4 * q;
+    float* nd = norm + (size_t)n * hw;
+    auto put = [&](int yy, int xx, float wc) {
+      atomicAdd(reinterpret_cast<float4*>(base + ((size_t)yy * W + xx) * Cp), make_float4(v.x * wc, v.y * wc, v.z * wc, v.w * wc));
+      if (q == 0) atomicAdd(nd + (size_t)yy * W + xx, ws * wc);
+    };
+    if (inx0 && iny0) put(y0, x0, wnw);
+    if (inx1 && iny0) put(y0, x1, wne);
+    if (inx0 && iny1) put(y1, x0, wsw);
+    if (inx1 && iny1) put(y1, x1, wse);
+  }
+}
+
+// out[n, c, p] = acc[n, p, c] / f(norm[n, p])  (eps: 0 addeps, 1 zeroeps, 2 clipeps; -1: no division = "sum" mode)
+__global__ void __launch_bounds__(256) nhwc_normalize_to_nchw_kernel(const float* __restrict__ acc, const float* __restrict__ norm,
+                                                                     float* __restrict__ out, int C, int Cp, size_t HW, int eps) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const size_t p0 = (size_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const size_t p = p0 + j;
+    const int c = c0 + tx;
+    float v = 0.f;
+    if (p < HW && c < Cp) {
+      v = acc[((size_t)n * HW + p) * Cp + c];
+      if (eps >= 0) {
+        float d = norm[(size_t)n * HW + p];
+        d = eps == 0 ? d + 0.0000001f : (eps == 1 ? (d == 0.f ? 1.f : d) : fmaxf(d, 0.0000001f));
+        v = v / d;
+      }
+    }
+    tile[j][tx] = v;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j;
+    const size_t p = p0 + tx;
+    if (c < C && p < HW) out[((size_t)n * C + c) * HW + p] = tile[tx][j];
+  }
+}
+
+// 9 x 9 volume on channel-last data, one WARP per output pixel, eight pixels (consecutive x) per block: for each of the 81
+// displacements the lanes walk the two channel vectors 32 channels at a time (128-byte coalesced loads, the 81-fold reuse of
+// `two` comes out of L1 / L2) and the lanes' partial sums are reduced with five shuffles; lane 0 parks the value in shared
+// memory so that the block writes each displacement plane 32 contiguous bytes at a time.
+template <bool kDot>
+__global__ void __launch_bounds__(256) volume81_warp_kernel(const float* __restrict__ one, const float* __restrict__ two,
+                                                            float* __restrict__ out, int C, int Cp, int H, int W) {
+  __shared__ float res[81][8];
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  const int x = blockIdx.x * 8 + wq, y = blockIdx.y, n = blockIdx.z;
+  const size_t hw = (size_t)H * W;
+  const bool valid = x < W;
+  const float* a = one + ((size_t)n * hw + (size_t)y * W + (valid ? x : 0)) * Cp;
+  for (int d = 0; d < 81; ++d) {
+    const int yy = y + d / 9 - 4, xx = x + d % 9 - 4;
+    const bool in = valid && yy >= 0 && yy < H && xx >= 0 && xx < W;
+    const float* b = two + ((size_t)n * hw + (size_t)(in ? yy : 0) * W + (in ? xx : 0)) * Cp;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float av = a[c];
+      const float bv = in ? b[c] : 0.f;   // outside the image: 0 (correlation: zero padding; cost volume: |one|, costvol.py:27-31)
+      s = kDot ? fmaf(av, bv, s) : s + fabsf(av - bv);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) res[d][wq] = s / (float)C;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 81 * 8; i += 256) {
+    const int d = i >> 3, j = i & 7;
+    const int xo = blockIdx.x * 8 + j;
+    if (xo < W) out[((size_t)n * 81 + d) * hw + (size_t)y * W + xo] = res[d][j];
+  }
+}
+
 // ---- shared-memory tiled separable convolution, K x K taps (K compile time), up to 4 channels per pass.
 // Block = 32 x (8*PY) output pixels, 256 threads; thread (lx, ly) owns the PY vertically adjacent pixels
 // (y0 + ly*PY + j, x0 + lx).  The input window of the block, (8*PY + K-1) x (32 + K-1) positions x 4 channels, sits in
@@ -372,6 +508,41 @@ cudaError_t launch_volume81(bool dot, const float* one, const float* two, float*
     VFI_LAUNCH((volume81_kernel<true>), grid_for(total, 128), 128, 0, st, one, two, out, N, C, H, W);
   else
     VFI_LAUNCH((volume81_kernel<false>), grid_for(total, 128), 128, 0, st, one, two, out, N, C, H, W);
+  return cudaGetLastError();
+}
+
+// channel-last forms: `sa` / `sb` are caller-provided scratch of N * H * W * round4(C) floats each (context-owned)
+size_t ops_scratch_floats(int N, int C, int H, int W) { return (size_t)N * H * W * (size_t)((C + 3) & ~3); }
+
+cudaError_t launch_softsplat_weighted_nhwc(const float* in, const float* flow, const float* metric, int mode, int eps, float* out,
+                                           float* norm, float* sa, float* sb, int N, int C, int H, int W, cudaStream_t st) {
+  if (mode < 0 || mode > 2 || eps < -1 || eps > 2 || (mode != 0 && metric == nullptr) || N > 65535) return cudaErrorInvalidValue;
+  const int Cp = (C + 3) & ~3;
+  const size_t hw = (size_t)H * W;
+  cudaError_t e = cudaMemsetAsync(sb, 0, (size_t)N * hw * Cp * sizeof(float), st);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(norm, 0, (size_t)N * hw * sizeof(float), st);
+  if (e != cudaSuccess) return e;
+  const dim3 gt((unsigned)((hw + 31) / 32), (unsigned)((Cp + 31) / 32), (unsigned)N);
+  VFI_LAUNCH((nchw_to_nhwc_kernel), gt, 256, 0, st, in, sa, C, Cp, hw);
+  VFI_LAUNCH((softsplat_nhwc_kernel), grid_for((size_t)N * hw * (Cp / 4), 256), 256, 0, st, sa, flow, metric, mode, sb, norm, N, Cp, H, W);
+  VFI_LAUNCH((nhwc_normalize_to_nchw_kernel), gt, 256, 0, st, sb, norm, out, C, Cp, hw, eps);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_volume81_warp(bool dot, const float* one, const float* two, float* out, float* sa, float* sb, int N, int C, int H,
+                                 int W, cudaStream_t st) {
+  if (N > 65535 || H > 65535) return cudaErrorInvalidValue;
+  const int Cp = (C + 3) & ~3;
+  const size_t hw = (size_t)H * W;
+  const dim3 gt((unsigned)((hw + 31) / 32), (unsigned)((Cp + 31) / 32), (unsigned)N);
+  VFI_LAUNCH((nchw_to_nhwc_kernel), gt, 256, 0, st, one, sa, C, Cp, hw);
+  VFI_LAUNCH((nchw_to_nhwc_kernel), gt, 256, 0, st, two, sb, C, Cp, hw);
+  const dim3 g((unsigned)((W + 7) / 8), (unsigned)H, (unsigned)N);
+  if (dot)
+    VFI_LAUNCH((volume81_warp_kernel<true>), g, 256, 0, st, sa, sb, out, C, Cp, H, W);
+  else
+    VFI_LAUNCH((volume81_warp_kernel<false>), g, 256, 0, st, sa, sb, out, C, Cp, H, W);
   return cudaGetLastError();
 }
 

@@ -175,6 +175,7 @@ struct vfi_ctx {
   bool last_have_base = false;
   DevBuf dbgF, dbgM;
   cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+  DevBuf ops_a, ops_b;           // scratch of the channel-last op kernels (splat, 9 x 9 volumes)
   vfi::PinnedBuf pin_in, pin_out;
   // per-kernel-group timing of the forward schedule (vfi_rife_profile): CUDA events recorded on the launching stream
   // around each group while `profile` is set; read (and summed per group id) by vfi_rife_profile_read
@@ -717,7 +718,7 @@ int vfi_destroy(vfi_ctx* c) {
   sepconv_destroy(c->sep);
   c->sep = nullptr;
   for (DevBuf* b : {&c->imgs, &c->imgs_h, &c->flow, &c->mask, &c->x, &c->c00, &c->featA, &c->featB, &c->raw, &c->outdev, &c->feats, &c->e16, &c->hA, &c->hB, &c->dbgF,
-                    &c->dbgM})
+                    &c->dbgM, &c->ops_a, &c->ops_b})
     b->release();
   for (int i = 0; i < kMaxBlocks; ++i) {
     c->tF[i].release();
@@ -1323,6 +1324,20 @@ int vfi_softsplat_weighted(vfi_ctx* c, const float* in, const float* flow, const
   if (!c || !in || !flow || !out || !norm || N < 1 || C < 1 || H < 1 || W < 1) return fail(VFI_E_INVALID, "bad argument");
   if (mode < 0 || mode > 2 || eps < 0 || eps > 2 || (mode != 0 && !metric)) return fail(VFI_E_INVALID, "softsplat mode / eps / metric");
   CK(cudaSetDevice(c->device));
+  // default: the channel-last form (16-byte vector atomics); VFI_SPLAT_NHWC=0: the NCHW scalar-atomic kernels (A/B runs)
+  static const bool nhwc = [] {
+    const char* e = std::getenv("VFI_SPLAT_NHWC");
+    return !(e && e[0] == '0');
+  }();
+  if (nhwc && N <= 65535) {
+    const size_t fl = ops_scratch_floats(N, C, H, W) * sizeof(float);
+    CK(c->ops_a.ensure(fl));
+    CK(c->ops_b.ensure(fl));
+    CK(launch_softsplat_weighted_nhwc(in, flow, metric, mode, eps, out, norm, (float*)c->ops_a.p, (float*)c->ops_b.p, N, C, H, W,
+                                      static_cast<cudaStream_t>(stream)));
+    c->launches += 3;
+    return VFI_OK;
+  }
   CK(launch_softsplat_weighted(in, flow, metric, mode, eps, out, norm, N, C, H, W, static_cast<cudaStream_t>(stream)));
   c->launches += 2;
   return VFI_OK;
@@ -1332,6 +1347,19 @@ int vfi_costvol_l1(vfi_ctx* c, const float* one, const float* two, float* out, i
                    void* stream) {
   if (!c || !one || !two || !out || N < 1 || C < 1 || H < 1 || W < 1) return fail(VFI_E_INVALID, "bad argument");
   CK(cudaSetDevice(c->device));
+  // default: the warp-per-pixel channel-last form (shuffle reduction over the channels); VFI_VOLUME_WARP=0: the tiled NCHW kernel
+  static const bool warp_form = [] {
+    const char* e = std::getenv("VFI_VOLUME_WARP");
+    return !(e && e[0] == '0');
+  }();
+  if (warp_form && N <= 65535 && H <= 65535) {
+    const size_t fl = ops_scratch_floats(N, C, H, W) * sizeof(float);
+    CK(c->ops_a.ensure(fl));
+    CK(c->ops_b.ensure(fl));
+    CK(launch_volume81_warp(false, one, two, out, (float*)c->ops_a.p, (float*)c->ops_b.p, N, C, H, W, (cudaStream_t)stream));
+    c->launches += 3;
+    return VFI_OK;
+  }
   LAUNCH(launch_volume81(false, one, two, out, N, C, H, W, (cudaStream_t)stream));
   return VFI_OK;
 }
@@ -1340,6 +1368,19 @@ int vfi_corr_dot(vfi_ctx* c, const float* first, const float* second, float* out
                  void* stream) {
   if (!c || !first || !second || !out || N < 1 || C < 1 || H < 1 || W < 1) return fail(VFI_E_INVALID, "bad argument");
   CK(cudaSetDevice(c->device));
+  // default: the warp-per-pixel channel-last form (shuffle reduction over the channels); VFI_VOLUME_WARP=0: the tiled NCHW kernel
+  static const bool warp_form = [] {
+    const char* e = std::getenv("VFI_VOLUME_WARP");
+    return !(e && e[0] == '0');
+  }();
+  if (warp_form && N <= 65535 && H <= 65535) {
+    const size_t fl = ops_scratch_floats(N, C, H, W) * sizeof(float);
+    CK(c->ops_a.ensure(fl));
+    CK(c->ops_b.ensure(fl));
+    CK(launch_volume81_warp(true, first, second, out, (float*)c->ops_a.p, (float*)c->ops_b.p, N, C, H, W, (cudaStream_t)stream));
+    c->launches += 3;
+    return VFI_OK;
+  }
   LAUNCH(launch_volume81(true, first, second, out, N, C, H, W, (cudaStream_t)stream));
   return VFI_OK;
 }

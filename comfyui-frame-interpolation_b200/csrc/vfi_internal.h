@@ -164,6 +164,12 @@ cudaError_t launch_softsplat_sum(const float* in, const float* flow, float* out,
                                  cudaStream_t st);
 cudaError_t launch_softsplat_weighted(const float* in, const float* flow, const float* metric, int mode, int eps, float* out,
                                       float* norm, int N, int C, int H, int W, cudaStream_t st);
+// channel-last forms (ops.cu): NCHW in / out like the forms above, `sa` / `sb` = scratch of ops_scratch_floats() floats each
+size_t ops_scratch_floats(int N, int C, int H, int W);
+cudaError_t launch_softsplat_weighted_nhwc(const float* in, const float* flow, const float* metric, int mode, int eps, float* out,
+                                           float* norm, float* sa, float* sb, int N, int C, int H, int W, cudaStream_t st);
+cudaError_t launch_volume81_warp(bool dot, const float* one, const float* two, float* out, float* sa, float* sb, int N, int C, int H,
+                                 int W, cudaStream_t st);
 cudaError_t launch_volume81(bool dot, const float* one, const float* two, float* out, int N, int C, int H, int W,
                             cudaStream_t st);
 cudaError_t launch_sepconv(const float* in, const float* ver, const float* hor, float* out, int N, int C, int H, int W,

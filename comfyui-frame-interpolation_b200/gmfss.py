@@ -27,6 +27,8 @@ class Ops:
         vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_longlong, C.c_float
         sig = {
             "vfi_gm_conv2d": [vp] * 6 + [i32] * 13 + [f32, i32, f32, vp],
+            "vfi_gm_conv2d_packed": [vp] * 6 + [i32] * 14 + [f32, i32, f32, vp],
+            "vfi_gm_transpose": [vp, vp, i32, i32, i32, vp],
             "vfi_gm_convt4": [vp] * 4 + [i32] * 6 + [f32, vp],
             "vfi_gm_instance_norm": [vp, vp, i32, i32, f32, i32, vp],
             "vfi_gm_layer_norm": [vp] * 5 + [i32, i32, f32, vp],
@@ -52,6 +54,21 @@ class Ops:
         self._err = getattr(lib, "vfi_last_error", None)
         if self._err is not None:
             self._err.restype = C.c_char_p
+        self._packed: Dict[int, torch.Tensor] = {}   # conv weight data_ptr -> [Cin*k*k, CoutP] (output channel fastest)
+        self._wt: Dict[int, torch.Tensor] = {}       # linear weight data_ptr -> its transpose [K, N]
+
+    # ------------------------------------------------------------------ load-time weight layouts (host side, once)
+    def register_conv(self, w: torch.Tensor):
+        """the fast conv kernel reads wt[(ci, ky, kx)][co] with co padded to a multiple of 16"""
+        cout, cin, k, _ = w.shape
+        coutp = (cout + 15) // 16 * 16
+        wt = torch.zeros(cin * k * k, coutp, dtype=torch.float32)
+        wt[:, :cout] = w.detach().to("cpu", torch.float32).permute(1, 2, 3, 0).reshape(cin * k * k, cout)
+        self._packed[w.data_ptr()] = wt.to(self.dev).contiguous()
+
+    def register_linear(self, w: torch.Tensor):
+        if w.shape[0] % 8 == 0 and w.shape[1] % 4 == 0:
+            self._wt[w.data_ptr()] = w.detach().t().contiguous().to(self.dev)
 
     # ------------------------------------------------------------------ plumbing
     def _st(self):
@@ -90,6 +107,12 @@ class Ops:
         assert tuple(out.shape[2:]) == (ho, wo) and out.shape[0] == n
         slope = float(pre) if pre is not None else 0.0
         self._chk(x, w, b, res1, res2, out)
+        wt = self._packed.get(w.data_ptr())
+        if wt is not None and ((k in (1, 3) and stride in (1, 2)) or (k == 7 and stride == 2)):
+            self._ck(self.L.vfi_gm_conv2d_packed(self._p(x), self._p(wt), self._p(b), self._p(res1), self._p(res2), self._p(out), n, cin, h,
+                                                 wd, cout, wt.shape[1], k, stride, pad, ctot, in_coff, out.shape[1], out_coff,
+                                                 1 if pre is not None else 0, slope, post, float(post_slope), self._st()), "conv2d_packed")
+            return out
         self._ck(self.L.vfi_gm_conv2d(self._p(x), self._p(w), self._p(b), self._p(res1), self._p(res2), self._p(out), n, cin, h, wd, cout,
                                       k, stride, pad, ctot, in_coff, out.shape[1], out_coff, 1 if pre is not None else 0, slope, post,
                                       float(post_slope), self._st()), "conv2d")
@@ -131,9 +154,29 @@ class Ops:
         n = w.shape[0]
         out = self.new(*x.shape[:-1], n)
         self._chk(x, w, b)
+        wt = self._wt.get(w.data_ptr())
+        if wt is not None:   # x @ wt, the 8 x 8-tile kernel
+            self._ck(self.L.vfi_gm_gemm(0, self._p(x), self._p(wt), self._p(b), None, self._p(out), 1, m, n, k, k, n, n, 0, 0, 0, 1.0, 1, act,
+                                        self._st()), "gemm")
+            return out
         self._ck(self.L.vfi_gm_gemm(1, self._p(x), self._p(w), self._p(b), None, self._p(out), 1, m, n, k, k, k, n, 0, 0, 0, 1.0, 1, act,
                                     self._st()), "gemm")
         return out
+
+    def transpose(self, x):
+        """[nb, R, C] -> [nb, C, R]"""
+        nb, r, c = x.shape
+        out = self.new(nb, c, r)
+        self._chk(x)
+        self._ck(self.L.vfi_gm_transpose(self._p(x), self._p(out), nb, r, c, self._st()), "transpose")
+        return out
+
+    def scores(self, q, k, alpha, mask=None):
+        """alpha * q k^T (+ mask): [nb, L, C] x [nb, Lk, C] -> [nb, L, Lk]; the keys are transposed once so that the product
+        runs in the coalesced 8 x 8-tile form"""
+        if k.shape[1] % 8 == 0 and k.shape[2] % 4 == 0:
+            return self.bmm(q, self.transpose(k), False, alpha, mask)
+        return self.bmm(q, k, True, alpha, mask)
 
     def bmm(self, a, b, bt, alpha=1.0, mask=None):
         """a [nb, M, K] x (b [nb, N, K] if bt else b [nb, K, N]) * alpha (+ mask[nb % nmask]) -> [nb, M, N]"""
@@ -264,6 +307,12 @@ class GMFSS:
         dev = ops.dev
         self.sd = {net: {k: v.detach().to(dev, torch.float32).contiguous() for k, v in sd.items()} for net, sd in sds.items() if net != "ifnet"}
         self.slope = {net: {k: float(v) for k, v in sd.items() if v.numel() == 1 and k.endswith(".weight")} for net, sd in sds.items() if net != "ifnet"}
+        for sd in self.sd.values():
+            for k_, v_ in sd.items():
+                if v_.dim() == 4 and not ("upsample_model" in k_ and k_.endswith(".1.weight")):   # (ConvTranspose weights keep their layout)
+                    ops.register_conv(v_)
+                elif v_.dim() == 2:
+                    ops.register_linear(v_)
         self._mask: Dict = {}
         self.mean = torch.tensor([0.485, 0.456, 0.406], device=dev)
         self.std = torch.tensor([0.229, 0.224, 0.225], device=dev)
@@ -296,7 +345,7 @@ class GMFSS:
         b, _, c = q.shape
         scale = 1.0 / math.sqrt(c)
         if splits <= 1:
-            return o.bmm(o.softmax_(o.bmm(q, k, True, scale)), v, False)
+            return o.bmm(o.softmax_(o.scores(q, k, scale)), v, False)
         sh, sw = ((h // splits) // 2, (w // splits) // 2) if shifted else (0, 0)
         qw, kw, vw = (o.window(t, splits, sh, sw, True, b, h, w, c) for t in (q, k, v))
         mask = None
@@ -305,7 +354,7 @@ class GMFSS:
             if key not in self._mask:
                 self._mask[key] = _shift_mask(h, w, splits).to(o.dev)
             mask = self._mask[key]
-        out = o.bmm(o.softmax_(o.bmm(qw, kw, True, scale, mask)), vw, False)
+        out = o.bmm(o.softmax_(o.scores(qw, kw, scale, mask)), vw, False)
         return o.window(out, splits, sh, sw, False, b, h, w, c)
 
     def _layer(self, p, source, target, h, w, splits, shifted, ffn):
@@ -360,7 +409,7 @@ class GMFSS:
         o = self.o
         b, c, h, w = f0.shape
         grid = self._grid_tokens(b, h, w)                                           # [B, L, 2] (x, y)
-        prob = o.softmax_(o.bmm(o.to_tokens(f0), o.to_tokens(f1), True, 1.0 / math.sqrt(c)))
+        prob = o.softmax_(o.scores(o.to_tokens(f0), o.to_tokens(f1), 1.0 / math.sqrt(c)))
         corr = o.bmm(prob, grid, False)                                             # expected match position
         return o.to_nchw(o.axpby(corr, grid, 1.0, -1.0), h, w)
 
@@ -372,7 +421,7 @@ class GMFSS:
         q = o.linear(x, sd[p + "q_proj.weight"], sd[p + "q_proj.bias"])
         if radius <= 0:
             k = o.linear(q, sd[p + "k_proj.weight"], sd[p + "k_proj.bias"])         # the reference projects the projected query
-            prob = o.softmax_(o.bmm(q, k, True, 1.0 / math.sqrt(c)))
+            prob = o.softmax_(o.scores(q, k, 1.0 / math.sqrt(c)))
             return o.to_nchw(o.bmm(prob, o.to_tokens(flow), False), h, w)
         k = o.linear(x, sd[p + "k_proj.weight"], sd[p + "k_proj.bias"])
         return o.local_prop(q, k, flow)

@@ -42,6 +42,25 @@ static inline F atomicAdd(F* p, F v) {  // float / double; blocks run on several
   return o;
 }
 
+static inline float4 atomicAdd(float4* p, float4 v) {  // the 16-byte vector atomic of sm_90+: four scalar atomics here
+  float4 o;
+  o.x = atomicAdd(&p->x, v.x);
+  o.y = atomicAdd(&p->y, v.y);
+  o.z = atomicAdd(&p->z, v.z);
+  o.w = atomicAdd(&p->w, v.w);
+  return o;
+}
+// warp shuffle through a per-block exchange buffer: every thread of the block calls it (the kernels that shuffle do so
+// uniformly), the two block barriers stand in for the lock-step of a warp
+static thread_local float emu_shfl_buf[1024];
+static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
+  emu_shfl_buf[threadIdx.x] = v;
+  __syncthreads();
+  const float r = emu_shfl_buf[threadIdx.x ^ (unsigned)lane_mask];
+  __syncthreads();
+  return r;
+}
+
 #define VFI_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu_dyn_smem)
 // blocks are dealt round-robin to up to 16 host threads; inside a block the threads are fibers (block_emu.h)
 #include <thread>

@@ -18,6 +18,13 @@ int emu_softsplat_weighted(const float* in, const float* flow, const float* metr
                           int N, int C, int H, int W) {
   return (int)vfi::launch_softsplat_weighted(in, flow, metric, mode, eps, out, norm, N, C, H, W, nullptr);
 }
+int emu_softsplat_weighted_nhwc(const float* in, const float* flow, const float* metric, int mode, int eps, float* out, float* norm,
+                               float* sa, float* sb, int N, int C, int H, int W) {
+  return (int)vfi::launch_softsplat_weighted_nhwc(in, flow, metric, mode, eps, out, norm, sa, sb, N, C, H, W, nullptr);
+}
+int emu_volume81_warp(int dot, const float* one, const float* two, float* out, float* sa, float* sb, int N, int C, int H, int W) {
+  return (int)vfi::launch_volume81_warp(dot != 0, one, two, out, sa, sb, N, C, H, W, nullptr);
+}
 int emu_volume81(int dot, const float* one, const float* two, float* out, int N, int C, int H, int W) {
   return (int)vfi::launch_volume81(dot != 0, one, two, out, N, C, H, W, nullptr);
 }

@@ -13,6 +13,9 @@ void film_destroy(FilmState*) {}
 void sepconv_destroy(SepState*) {}
 cudaError_t launch_softsplat_sum(const float*, const float*, float*, int, int, int, int, cudaStream_t) { return cudaErrorNotSupported; }
 cudaError_t launch_softsplat_weighted(const float*, const float*, const float*, int, int, float*, float*, int, int, int, int, cudaStream_t) { return cudaErrorNotSupported; }
+size_t ops_scratch_floats(int, int, int, int) { return 0; }
+cudaError_t launch_softsplat_weighted_nhwc(const float*, const float*, const float*, int, int, float*, float*, float*, float*, int, int, int, int, cudaStream_t) { return cudaErrorNotSupported; }
+cudaError_t launch_volume81_warp(bool, const float*, const float*, float*, float*, float*, int, int, int, int, cudaStream_t) { return cudaErrorNotSupported; }
 cudaError_t launch_volume81(bool, const float*, const float*, float*, int, int, int, int, cudaStream_t) { return cudaErrorNotSupported; }
 cudaError_t launch_sepconv(const float*, const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t) { return cudaErrorNotSupported; }
 cudaError_t launch_adacof(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int, cudaStream_t) { return cudaErrorNotSupported; }

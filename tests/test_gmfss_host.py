@@ -69,6 +69,24 @@ def test_primitives_against_torch(model_factory):
     assert (o.conv(x, w, b, stride=2, pre=0.3, res1=r1) - ref).abs().max() <= 1e-5
     w7 = torch.randn(4, 5, 7, 7, generator=g) * 0.1
     assert (o.conv(x, w7, stride=2, pad=3) - F.conv2d(x, w7, None, stride=2, padding=3)).abs().max() <= 1e-5
+    # the packed-weight fast forms (3x3 s1 / s2, 1x1 s2, 7x7 s2; Cout not a multiple of 16; channel slices in and out)
+    for (kk, st, pd) in ((3, 1, 1), (3, 2, 1), (1, 2, 0), (1, 1, 0), (7, 2, 3)):
+        wk = torch.randn(19, 5, kk, kk, generator=g) * 0.2
+        o.register_conv(wk)
+        big_in = torch.randn(2, 9, 13, 18, generator=g)
+        ref = F.conv2d(F.prelu(big_in[:, 3:8], torch.tensor([0.3])), wk, b.repeat(3)[:19], stride=st, padding=pd)
+        dst = torch.zeros(2, 25, ref.shape[2], ref.shape[3])
+        rr = torch.randn_like(ref)
+        o.conv(big_in, wk, b.repeat(3)[:19].contiguous(), stride=st, pad=pd, pre=0.3, res1=rr, out=dst, out_coff=4, in_coff=3, cin=5, post=1)
+        assert (dst[:, 4:23] - F.relu(ref + rr)).abs().max() <= 1e-5, (kk, st)
+        assert float(dst[:, :4].abs().max()) == 0.0 and float(dst[:, 23:].abs().max()) == 0.0
+    wl8 = torch.randn(24, 16, generator=g)
+    o.register_linear(wl8)
+    t21 = torch.randn(3, 7, 16, generator=g)       # 21 rows: a partial 8-row tile
+    assert (o.linear(t21, wl8, torch.arange(24.0), act=1) - F.gelu(F.linear(t21, wl8, torch.arange(24.0)))).abs().max() <= 1e-5
+    qq, kk2 = torch.randn(4, 10, 16, generator=g), torch.randn(4, 24, 16, generator=g)
+    mm = torch.randn(2, 10, 24, generator=g)
+    assert (o.scores(qq, kk2, 0.5, mm) - (0.5 * qq @ kk2.transpose(1, 2) + mm.repeat(2, 1, 1))).abs().max() <= 1e-5
     wt = torch.randn(5, 6, 4, 4, generator=g) * 0.2
     bt = torch.randn(6, generator=g)
     ref = F.conv_transpose2d(F.prelu(x, torch.tensor([0.2])), wt, bt, stride=2, padding=1)

@@ -77,3 +77,38 @@ def test_softsplat_fused_modes(emu, mode):
     ref = ops_ref.softsplat(x, flow, None if m == 0 else metric, mode)
     ok = ref.abs() < 1e4                       # addeps: untouched targets are 0 / 1e-7 in both, tiny norms blow up alike
     assert (out - ref)[ok].abs().max().item() <= 2e-3 * max(1.0, float(ref[ok].abs().max()))
+
+
+@pytest.mark.parametrize("mode", ["avg", "linear", "soft", "soft-zeroeps", "linear-clipeps"])
+@pytest.mark.parametrize("c", [6, 3])
+def test_softsplat_channel_last_modes(emu, mode, c):
+    """the channel-last form behind vfi_softsplat_weighted since r02 (NCHW -> NHWC transpose, 16-byte vector atomics per four
+    channels, normalise + transpose back) == the reference's chain; C = 3 exercises the channel padding"""
+    g = torch.Generator().manual_seed(len(mode) + c)
+    x = torch.randn(2, c, 17, 21, generator=g)
+    flow = (torch.rand(2, 2, 17, 21, generator=g) - 0.5) * 8
+    metric = torch.rand(2, 1, 17, 21, generator=g) * 2 - (0.5 if mode.startswith("soft") else -0.2)
+    base = mode.split("-")[0]
+    m = {"avg": 0, "linear": 1, "soft": 2}[base]
+    e = {"addeps": 0, "zeroeps": 1, "clipeps": 2}[mode.split("-")[1] if "-" in mode else "addeps"]
+    out, norm = torch.full_like(x, 3.0), torch.full((2, 1, 17, 21), 3.0)
+    cp = (c + 3) // 4 * 4
+    sa, sb = torch.full((2 * 17 * 21 * cp,), 5.0), torch.full((2 * 17 * 21 * cp,), 5.0)
+    assert emu.emu_softsplat_weighted_nhwc(vp(x), vp(flow), None if m == 0 else vp(metric), m, e, vp(out), vp(norm), vp(sa), vp(sb), 2, c,
+                                           17, 21) == 0
+    ref = ops_ref.softsplat(x, flow, None if m == 0 else metric, mode)
+    ok = ref.abs() < 1e4
+    assert (out - ref)[ok].abs().max().item() <= 2e-3 * max(1.0, float(ref[ok].abs().max()))
+
+
+@pytest.mark.parametrize("dot", [0, 1])
+def test_volume81_warp_kernels(emu, dot):
+    """the warp-per-pixel channel-last volume (shuffle reduction over the channels) == the oracle; C = 20 is not a multiple of
+    32 (partial lane coverage) nor of 4 (channel padding), W = 37 not a multiple of the 8 pixels of a block"""
+    g = torch.Generator().manual_seed(10 + dot)
+    a, b = torch.randn(1, 20, 13, 37, generator=g), torch.randn(1, 20, 13, 37, generator=g)
+    out = torch.zeros(1, 81, 13, 37)
+    sa, sb = torch.zeros(13 * 37 * 20), torch.zeros(13 * 37 * 20)
+    assert emu.emu_volume81_warp(dot, vp(a), vp(b), vp(out), vp(sa), vp(sb), 1, 20, 13, 37) == 0
+    ref = ops_ref.correlation_dot(a, b) if dot else ops_ref.costvol_l1(a, b)
+    assert (out - ref).abs().max().item() <= 1e-4

@@ -71,6 +71,7 @@ def main():
     ms_reuse = ms_inf = 0.0
     ph, pw = ((a.h - 1) // 64 + 1) * 64, ((a.w - 1) // 64 + 1) * 64
     for _ in range(a.steps):
+        macs["n"] = 0   # (per frame)
         i0, i1 = m.o.new(1, 3, ph, pw), m.o.new(1, 3, ph, pw)
         e[0].record()
         m.o.copy_slice(f0, i0, 3)

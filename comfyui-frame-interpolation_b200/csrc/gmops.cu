@@ -370,37 +370,38 @@ __global__ void gemm_kernel(const float* __restrict__ A, const float* __restrict
 // in (linears with the weight transposed once at load time, attention scores against the transposed keys, P V): thread = an
 // 8 x 8 tile of C, lanes along n; per four k: eight 16-byte loads of A (one per row, the same for every lane of a row group)
 // and eight of B (coalesced) for 256 multiply-adds.  Needs K % 4 == 0, N % 8 == 0, 16-byte aligned rows.
+template <int MT>
 __global__ void gemm_nn8_kernel(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ bias,
                                 const float* __restrict__ mask, float* __restrict__ C, int nb, int M, int N, int K, int lda, int ldb,
                                 int ldc, long long sA, long long sB, long long sC, float alpha, int nmask, int act) {
-  const int mq = (M + 7) / 8, nq = N / 8;
+  const int mq = (M + MT - 1) / MT, nq = N / 8;
   const size_t total = (size_t)nb * mq * nq;
   for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
     const int n0 = (int)(id % nq) * 8;
     size_t r = id / nq;
-    const int m0 = (int)(r % mq) * 8;
+    const int m0 = (int)(r % mq) * MT;
     const int b = (int)(r / mq);
     const float* a = A + (size_t)b * sA;
     const float* bp = B + (size_t)b * sB + n0;
-    float acc[8][8];
+    float acc[MT][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < MT; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    int row[8];
+    int row[MT];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) row[i] = min(m0 + i, M - 1);  // rows past M recompute the last one and are not stored
+    for (int i = 0; i < MT; ++i) row[i] = min(m0 + i, M - 1);  // rows past M recompute the last one and are not stored
     for (int k = 0; k < K; k += 4) {
-      float4 av[8];
+      float4 av[MT];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) av[i] = __ldg(reinterpret_cast<const float4*>(a + (size_t)row[i] * lda + k));
+      for (int i = 0; i < MT; ++i) av[i] = __ldg(reinterpret_cast<const float4*>(a + (size_t)row[i] * lda + k));
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp + (size_t)(k + kk) * ldb));
         const float4 b1 = __ldg(reinterpret_cast<const float4*>(bp + (size_t)(k + kk) * ldb + 4));
         const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < MT; ++i) {
           const float x = kk == 0 ? av[i].x : kk == 1 ? av[i].y : kk == 2 ? av[i].z : av[i].w;
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(x, bv[j], acc[i][j]);
@@ -408,7 +409,7 @@ __global__ void gemm_nn8_kernel(const float* __restrict__ A, const float* __rest
       }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < MT; ++i) {
       if (m0 + i < M) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -813,9 +814,16 @@ cudaError_t gm_gemm(int bt, const float* A, const float* B, const float* bias, c
                     cudaStream_t st) {
   const bool aligned = ((K | N | lda | ldb) & 3) == 0 && (N & 7) == 0 && ((sA | sB) & 3) == 0 &&
                        ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0;
-  if (!bt && aligned)
-    GM_LAUNCH(gemm_nn8_kernel, (size_t)nb * ((M + 7) / 8) * (N / 8), A, B, bias, mask, C, nb, M, N, K, lda, ldb, ldc, sA, sB, sC, alpha,
-              nmask, act);
+  if (!bt && aligned) {
+    // rows per thread: 8 when that still gives the GPU enough threads, else 4 or 2 (r02 capture: the 7680 x 128 x 1024 linear
+    // ran as 120 blocks of 8 x 8-tile threads - 6 % of the warp slots - and took 456 us)
+    const size_t cols = (size_t)nb * (N / 8);
+    const int mt = cols * ((M + 7) / 8) >= 60000 ? 8 : (cols * ((M + 3) / 4) >= 60000 ? 4 : 2);
+    const size_t threads = cols * ((M + mt - 1) / mt);
+    if (mt == 8) GM_LAUNCH(gemm_nn8_kernel<8>, threads, A, B, bias, mask, C, nb, M, N, K, lda, ldb, ldc, sA, sB, sC, alpha, nmask, act);
+    if (mt == 4) GM_LAUNCH(gemm_nn8_kernel<4>, threads, A, B, bias, mask, C, nb, M, N, K, lda, ldb, ldc, sA, sB, sC, alpha, nmask, act);
+    GM_LAUNCH(gemm_nn8_kernel<2>, threads, A, B, bias, mask, C, nb, M, N, K, lda, ldb, ldc, sA, sB, sC, alpha, nmask, act);
+  }
   const size_t total = (size_t)nb * ((M + 7) / 8) * N;
   if (bt) GM_LAUNCH(gemm_kernel<true>, total, A, B, bias, mask, C, nb, M, N, K, lda, ldb, ldc, sA, sB, sC, alpha, nmask, act);
   GM_LAUNCH(gemm_kernel<false>, total, A, B, bias, mask, C, nb, M, N, K, lda, ldb, ldc, sA, sB, sC, alpha, nmask, act);

@@ -1347,10 +1347,13 @@ int vfi_costvol_l1(vfi_ctx* c, const float* one, const float* two, float* out, i
                    void* stream) {
   if (!c || !one || !two || !out || N < 1 || C < 1 || H < 1 || W < 1) return fail(VFI_E_INVALID, "bad argument");
   CK(cudaSetDevice(c->device));
-  // default: the warp-per-pixel channel-last form (shuffle reduction over the channels); VFI_VOLUME_WARP=0: the tiled NCHW kernel
+  // VFI_VOLUME_WARP=1: the warp-per-pixel channel-last form (shuffle reduction over the channels).  Measured r02
+  // (profiles/r02_h_bench_ops*.log): 189 / 705 us against 123 / 258 us of the shared-memory tiled kernel on the 64-channel
+  // 96x160 and 128-channel 192x320 shapes - each displacement re-reads its channel vector through L1, 81 times per pixel -
+  // so the tiled kernel stays the default and this form is kept for comparison.
   static const bool warp_form = [] {
     const char* e = std::getenv("VFI_VOLUME_WARP");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
   }();
   if (warp_form && N <= 65535 && H <= 65535) {
     const size_t fl = ops_scratch_floats(N, C, H, W) * sizeof(float);
@@ -1368,10 +1371,13 @@ int vfi_corr_dot(vfi_ctx* c, const float* first, const float* second, float* out
                  void* stream) {
   if (!c || !first || !second || !out || N < 1 || C < 1 || H < 1 || W < 1) return fail(VFI_E_INVALID, "bad argument");
   CK(cudaSetDevice(c->device));
-  // default: the warp-per-pixel channel-last form (shuffle reduction over the channels); VFI_VOLUME_WARP=0: the tiled NCHW kernel
+  // VFI_VOLUME_WARP=1: the warp-per-pixel channel-last form (shuffle reduction over the channels).  Measured r02
+  // (profiles/r02_h_bench_ops*.log): 189 / 705 us against 123 / 258 us of the shared-memory tiled kernel on the 64-channel
+  // 96x160 and 128-channel 192x320 shapes - each displacement re-reads its channel vector through L1, 81 times per pixel -
+  // so the tiled kernel stays the default and this form is kept for comparison.
   static const bool warp_form = [] {
     const char* e = std::getenv("VFI_VOLUME_WARP");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
   }();
   if (warp_form && N <= 65535 && H <= 65535) {
     const size_t fl = ops_scratch_floats(N, C, H, W) * sizeof(float);

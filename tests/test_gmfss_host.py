@@ -84,6 +84,9 @@ def test_primitives_against_torch(model_factory):
     o.register_linear(wl8)
     t21 = torch.randn(3, 7, 16, generator=g)       # 21 rows: a partial 8-row tile
     assert (o.linear(t21, wl8, torch.arange(24.0), act=1) - F.gelu(F.linear(t21, wl8, torch.arange(24.0)))).abs().max() <= 1e-5
+    for rows in (60001, 40003, 37):            # 8, 4 and 2 rows per thread in the tiled product (a partial last tile each)
+        aa, bb8 = torch.randn(1, rows, 8, generator=g), torch.randn(1, 8, 64, generator=g)
+        assert (o.bmm(aa, bb8, False, 0.25) - 0.25 * aa @ bb8).abs().max() <= 1e-5, rows
     qq, kk2 = torch.randn(4, 10, 16, generator=g), torch.randn(4, 24, 16, generator=g)
     mm = torch.randn(2, 10, 24, generator=g)
     assert (o.scores(qq, kk2, 0.5, mm) - (0.5 * qq @ kk2.transpose(1, 2) + mm.repeat(2, 1, 1))).abs().max() <= 1e-5

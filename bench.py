@@ -433,19 +433,19 @@ def main():
                     "launch_ms": k_ms, "flops_per_launch": k_flops}
         # HBM-bound kernels ON the path, from the profiled step (ids: 10 * block + 0 = front, 90 = final).  Bytes per
         # padded pixel and task that the kernel has to move in this schedule: block-3 front =
-        # two half4 image gathers (16) + accumulated flow / mask (20) + the block-2 level at 1/4 of the pixels (5) +
-        # the 16-channel 16-bit block input (32); block-2 front = the image gathers at full resolution (16) + the two
-        # coarse levels (1.56) + the block input at half resolution (32 / 4) + the accumulated flow / mask it stores (20);
-        # final = flow / mask (20) + block-2 level (5) + block-3 level (20) + two float4 image gathers (32) + RGB out (12,
-        # on the cropped frame).
+        # two half4 image gathers (16) + accumulated flow / mask read (20) and written back with the block-2 level
+        # folded in (20) + that level at 1/4 of the pixels (5) + the 16-channel 16-bit block input (32); block-2 front =
+        # the image gathers at full resolution (16) + the two coarse levels (1.56) + the block input at half resolution
+        # (32 / 4) + the accumulated flow / mask it stores (20); final = flow / mask (20) + block-3 level (20) + two float4
+        # image gathers (32) + RGB out (12, on the cropped frame).
         px = 1088 * 1920
         passes = {k: v[1] for k, v in prof.items()}
         def per_pair_ms(gid):
             return prof[gid][0] / npairs if gid in prof else None
         hbm_rows = []
         if a.arch == "4.6":
-            for gid, name, bpp in ((30, "front<block 3> (flow up-sample + 2 warps + resample + concat -> conv0.0 input)", 16 + 20 + 5 + 32),
-                                   (90, "final (flow up-sample + 2 warps + sigmoid blend + crop + clamp)", 20 + 5 + 20 + 32 + 12 * (H * W) / px),
+            for gid, name, bpp in ((30, "front<block 3> (flow up-sample + 2 warps + resample + concat -> conv0.0 input)", 16 + 20 + 20 + 5 + 32),
+                                   (90, "final (flow up-sample + 2 warps + sigmoid blend + crop + clamp)", 20 + 20 + 32 + 12 * (H * W) / px),
                                    (20, "front<block 2> (same at scale 2; stores the accumulated flow plane)", 16 + 1.5625 + 32 / 4 + 20)):
                 ms = per_pair_ms(gid)
                 if ms:

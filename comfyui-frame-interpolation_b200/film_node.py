@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from .engine import FilmEngine
-from .node import InterpolationStateList, load_file_from_github_release
+from .node import InterpolationStateList, _alloc_output, load_file_from_github_release
 
 MODEL_TYPE = "film"
 PAIRS_PER_PASS = 4  # pairs interpolated together (about 6 GB of workspace per 1080p pair)
@@ -102,8 +102,8 @@ class FILM_VFI:
             first_slot[i] = slot
             slot += multipliers[i]
         total = slot + 1
-        pin = dev.type == "cuda"
-        out = torch.empty((total, h, w, 3), dtype=torch.float32, pin_memory=pin)
+        # page-locked through torch's caching host allocator up to VFI_PINNED_OUT_MAX_GB (node._alloc_output), pageable above
+        out = _alloc_output((total, h, w, 3)) if dev.type == "cuda" else torch.empty((total, h, w, 3), dtype=torch.float32)
         out[total - 1] = src[n - 1]
         # pairs with the same multiplier share a schedule and are interpolated PAIRS_PER_PASS at a time
         by_mult: typing.Dict[int, typing.List[int]] = {}

@@ -103,7 +103,8 @@ class FILM_VFI:
             slot += multipliers[i]
         total = slot + 1
         # page-locked through torch's caching host allocator up to VFI_PINNED_OUT_MAX_GB (node._alloc_output), pageable above
-        out = _alloc_output((total, h, w, 3)) if dev.type == "cuda" else torch.empty((total, h, w, 3), dtype=torch.float32)
+        pin = dev.type == "cuda"
+        out = _alloc_output((total, h, w, 3)) if pin else torch.empty((total, h, w, 3), dtype=torch.float32)
         out[total - 1] = src[n - 1]
         # pairs with the same multiplier share a schedule and are interpolated PAIRS_PER_PASS at a time
         by_mult: typing.Dict[int, typing.List[int]] = {}

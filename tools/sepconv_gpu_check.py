@@ -75,6 +75,17 @@ def main():
         left = eng.middle_frame(x[0:1], mid).cpu().permute(0, 2, 3, 1)[0]
         report("node", out.shape == (7, 40, 56, 3) and bool(torch.equal(out[1], left)) and bool(torch.equal(out[0], fr.cpu()[0])),
                shape=list(out.shape))
+        # multiplier 2: the node's pipelined path (NHWC frames, staged uploads, downloads into the output's slots) must equal
+        # the reference loop it replaces (frame_loop.generic_frame_loop), also with a skip list and an odd number of pairs
+        from cfi_b200.frame_loop import generic_frame_loop
+        from cfi_b200.node import InterpolationStateList
+        fr6 = sepconv_inputs(dict(kind="node", n=6, h=40, w=56, clip_seed=61)).contiguous()
+        for states in (None, InterpolationStateList([1, 3], True)):
+            (fast,) = SN.SepconvVFI().vfi("sepconv.pth", fr6, multiplier=2, optional_interpolation_states=states, _engine=eng)
+            slow = generic_frame_loop("SepconvVFI", fr6.permute(0, 3, 1, 2), 10, 2, lambda a, b, t, m: m.middle_frame(a, b), eng,
+                                      interpolation_states=states, use_timestep=False, dtype=torch.float32).permute(0, 2, 3, 1)
+            report("node_x2_pipelined" + ("" if states is None else "_skip"), fast.shape == slow.shape and bool(torch.equal(fast, slow)),
+                   shape=list(fast.shape))
         eng.close()
     except Exception as e:
         report("batch/node", False, error=repr(e)[:300])

@@ -205,7 +205,10 @@ def main():
     if a.workload != "rife":  # the other model families keep their own harness; same launch convention (torchrun for N > 1)
         import runpy
         tool = {"film": "bench_film.py", "sepconv": "bench_sepconv.py", "gmfss": "bench_gmfss.py"}[a.workload]
-        sys.argv = [os.path.join(ROOT, "tools", tool), "--steps", str(a.steps), "--warmup", str(a.warmup)] + extra
+        fwd = ["--steps", str(a.steps), "--warmup", str(a.warmup)] + (["--no-cpu"] if a.no_cpu else [])
+        if a.workload != "gmfss" and a.frames != NFRAMES:
+            fwd += ["--frames", str(a.frames)]
+        sys.argv = [os.path.join(ROOT, "tools", tool)] + fwd + extra
         runpy.run_path(sys.argv[0], run_name="__main__")
         return
     if extra:
@@ -425,9 +428,9 @@ def main():
         roofline = {"kernel": "tapconv_kernel (block-3 ResConv 64->64, 272x480 cells, tcgen05)", "bound": "tensor",
                     "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
                     # dram__bytes_read.sum + dram__bytes_write.sum of this launch (batch 8) in the committed capture
-                    # profiles/r01_v15_resconv_b3.ncu-rep: 133.9 MB + 89.3 MB against 2 x 133.7 MB of algorithmic
+                    # profiles/r02_c_resconv_b3.ncu-rep: 133.8 MB + 90.6 MB against 2 x 133.7 MB of algorithmic
                     # activation bytes (part of the output is still in L2 when the kernel ends); not re-measured here
-                    "traffic": (223.16e6 if B == 8 else None), "traffic_source": "ncu profiles/r01_v15_resconv_b3",
+                    "traffic": (224.4e6 if B == 8 else None), "traffic_source": "ncu profiles/r02_c_resconv_b3 (133.8 MB read + 90.6 MB written)",
                     "algorithmic_bytes": 2.0 * B * 272 * 480 * 64 * 2,
                     "peak_source": peaks["source"] + ", burst figure (kernel timed alone)",
                     "launch_ms": k_ms, "flops_per_launch": k_flops}
@@ -444,14 +447,17 @@ def main():
             return prof[gid][0] / npairs if gid in prof else None
         hbm_rows = []
         if a.arch == "4.6":
-            for gid, name, bpp in ((30, "front<block 3> (flow up-sample + 2 warps + resample + concat -> conv0.0 input)", 16 + 20 + 20 + 5 + 32),
-                                   (90, "final (flow up-sample + 2 warps + sigmoid blend + crop + clamp)", 20 + 20 + 32 + 12 * (H * W) / px),
-                                   (20, "front<block 2> (same at scale 2; stores the accumulated flow plane)", 16 + 1.5625 + 32 / 4 + 20)):
+            # traffic: dram__bytes_read.sum + dram__bytes_write.sum of the same kernels in the committed capture
+            # profiles/r02_i_elementwise.ncu-rep (one pass of 8 pairs: 1497 / 1382 / 645 MB), per pair
+            for gid, name, bpp, traffic in (
+                    (30, "front<block 3> (flow up-sample + 2 warps + resample + concat -> conv0.0 input)", 16 + 20 + 20 + 5 + 32, 1497e6 / 8),
+                    (90, "final (flow up-sample + 2 warps + sigmoid blend + crop + clamp)", 20 + 20 + 32 + 12 * (H * W) / px, 1382e6 / 8),
+                    (20, "front<block 2> (same at scale 2; stores the accumulated flow plane)", 16 + 1.5625 + 32 / 4 + 20, 645e6 / 8)):
                 ms = per_pair_ms(gid)
                 if ms:
                     gbs = bpp * px / (ms * 1e-3) / 1e9
                     hbm_rows.append({"kernel": name, "ms_per_pair": ms, "bytes_per_pair": bpp * px, "achieved": gbs,
-                                     "frac": gbs / peaks["hbm_gbs"]})
+                                     "frac": gbs / peaks["hbm_gbs"], "traffic": traffic if a.batch == 8 else None})
         roofline_hbm = {"bound": "hbm", "unit": "GB/s", "peak": peaks["hbm_gbs"], "peak_source": peaks["source"],
                         "how": "CUDA events on the launching stream around each launch inside one profiled 63-pair step "
                                "(vfi_rife_profile); bytes = what the kernel must read + write per pair in this schedule",
@@ -459,8 +465,8 @@ def main():
                         "achieved": hbm_rows[0]["achieved"] if hbm_rows else None,
                         "frac": hbm_rows[0]["frac"] if hbm_rows else None,
                         "kernel": hbm_rows[0]["kernel"] if hbm_rows else None,
-                        # dram__bytes of the same launches: profiles/ (ncu --set full), per pass of 8 pairs
-                        "traffic": None}
+                        "traffic": hbm_rows[0]["traffic"] if hbm_rows else None,
+                        "traffic_source": "ncu profiles/r02_i_elementwise.ncu-rep (per pair = per-launch bytes / 8)"}
         groups = {str(k): {"ms_per_pair": v[0] / npairs, "spans": v[1]} for k, v in sorted(prof.items())}
         del x, y, flush
 

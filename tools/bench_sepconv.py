@@ -167,7 +167,7 @@ def main():
         if world == 1 and not a.no_cpu:
             torch.set_num_threads(min(32, os.cpu_count() or 1))
             hs, ws = 270, 480
-            small = OF.synthetic_clip(2, hs, ws, seed=7).permute(0, 3, 1, 2)
+            small = OF.synthetic_clip(2, hs, ws, seed=7).permute(0, 3, 1, 2).contiguous()
             OS.network_forward(sd, small[0:1], small[1:2])
             t0 = time.perf_counter()
             OS.network_forward(sd, small[0:1], small[1:2])

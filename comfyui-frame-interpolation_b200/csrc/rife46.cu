@@ -681,7 +681,7 @@ int check_tasks(const int32_t* f0, const int32_t* f1, int n_tasks, int lo, int h
 extern "C" {
 
 const char* vfi_last_error(void) { return g_err.c_str(); }
-const char* vfi_version(void) { return "vfi_b200 0.1 (sm_100a; RIFE 4.6/4.7/4.17/4.26, FILM, Sepconv; built " __DATE__ " " __TIME__ ")"; }
+const char* vfi_version(void) { return "vfi_b200 0.2 (sm_100a; RIFE 4.6/4.7/4.17/4.26, FILM, Sepconv, GMFSS Fortuna building blocks; built " __DATE__ " " __TIME__ ")"; }
 
 int vfi_create(int device, vfi_ctx** out) {
   if (!out) return fail(VFI_E_INVALID, "null out");

@@ -228,7 +228,7 @@ def main():
               "parallelism": (f"frame-pair shards x{a.gpus}; each rank's output frames land on rank 0 over NVLink in {GATHER_CHUNKS} chunks behind the kernels that "
                               f"produce them ({'NCCL send/recv' if os.environ.get('VFI_GATHER', 'nccl') != 'push' else 'copy-engine pushes into an IPC-shared buffer, NCCL for the handle and the barriers'})")
               if a.gpus > 1 else "1 GPU",
-              "l2": "inputs larger than L2 (1.6 GB clip, 1.6 GB output per step)"}
+              "l2": "inputs larger than L2 (1.6 GB clip, 1.6 GB output per step)", "batch": a.batch}
 
     sd = O.synthetic_state_dict(0, arch=a.arch)
     global CPU_ARCH
@@ -489,7 +489,7 @@ def main():
                 "dtype": "bf16" if a.dtype == "bfloat16" else "f16",
                 "dtype_note": "conv operands 16-bit, fp32 accumulate (TMEM); flow/mask/warp/blend fp32; PSNR>=50 dB "
                               "vs fp32 oracle enforced by tests/test_gpu_forward.py",
-                "data": "synthetic", "config": dict(config, batch=a.batch),
+                "data": "synthetic", "config": config,
                 "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / a.steps, "via": "RIFE_VFI.vfi (node call)",
                         "input": "pageable CPU tensor [64,1080,1920,3] fp32", "output": "node-allocated" + (" (page-locked, torch caching host allocator)" if node_out_pinned else " (pageable)"),
                         "h2d_bytes_per_step": nf * H * W * 3 * 4, "d2h_bytes_per_step": npairs * H * W * 3 * 4,
